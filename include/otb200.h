@@ -1,0 +1,334 @@
+/*
+ * otb200.h — C ABI of libotb200.so, the sm_100a implementation of the per-step
+ * training hot path that OneTrainer owns itself.
+ *
+ * The reference (sangoi-exe/OneTrainer) is 100 % Python and has no FFI today; its
+ * plugin API for this path is three Python seams:
+ *   S1  LoRAModule.forward                 modules/module/LoRAModule.py:319-323
+ *   S2  ModelSetupNoiseMixin / DiffusionMixin / FlowMatchingMixin / DiffusionLossMixin
+ *                                          modules/modelSetup/mixin/*.py
+ *   S3  patch_adamw / EMAModuleWrapper     modules/util/optimizer/adamw_extensions.py:202-205,
+ *                                          modules/module/EMAModule.py:37-54
+ * Every entry point below cites the reference lines it replaces.  The thin Python host
+ * (onetrainer_b200/) binds these with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - no allocation, no host synchronisation, no implicit stream: the caller passes
+ *     a cudaStream_t (as void*) and any workspace;
+ *   - return 0 on success, a negative OTB_E* code on failure; otb_last_error()
+ *     returns a thread-local message;
+ *   - the library keeps no reference to caller memory after the call returns
+ *     (kernels read it asynchronously on the given stream).
+ */
+#ifndef OTB200_H
+#define OTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OTB_ABI_VERSION 1
+
+/* error codes */
+#define OTB_OK            0
+#define OTB_EINVAL       -1   /* bad argument (shape, alignment, dtype, null pointer) */
+#define OTB_EUNSUPPORTED -2   /* legal in the reference but not implemented here: fails loudly, never falls back */
+#define OTB_ECUDA        -3   /* CUDA runtime/driver error; message carries cudaGetErrorString */
+#define OTB_EARCH        -4   /* device is not sm_100 */
+
+/* dtype enum (matches the host-side mirror) */
+#define OTB_F32  0
+#define OTB_BF16 1
+#define OTB_F16  2
+
+/* Arithmetic flavour bits.  torch's CPU and CUDA eager kernels round the AdamW
+ * update differently in three places; the oracle and the kernel implement both so
+ * parity can be pinned against the reference run on CPU (golden fixtures) AND the
+ * reference run on the GPU (torch CUDA eager).  See DESIGN.md §numerics. */
+#define OTB_FLAVOR_DIV_RECIPROCAL   1u   /* sqrt(v)/c computed as sqrt(v)*(1/c)  (CUDA eager div-by-scalar)  */
+#define OTB_FLAVOR_ADDCDIV_MUL_LAST 2u   /* p + a*(m/d) (CUDA)  vs  p + (a*m)/d (CPU)                          */
+#define OTB_FLAVOR_FMA_LERP         4u   /* m + w*(g-m) as one fma (both torch back-ends do)                   */
+#define OTB_FLAVOR_FMA_ADDCMUL      8u   /* v + ((1-b2)*g)*g as fma(.., g, v)                                  */
+#define OTB_FLAVOR_FMA_ADDCDIV      16u  /* p + a*q as fma(a, q, p)                                            */
+#define OTB_FLAVOR_FMA_ADD_ALPHA    32u  /* Adam L2: g + wd*p as fma(wd, p, g)                                 */
+#define OTB_FLAVOR_TORCH_CPU   (OTB_FLAVOR_FMA_LERP)
+#define OTB_FLAVOR_TORCH_CUDA  (OTB_FLAVOR_DIV_RECIPROCAL | OTB_FLAVOR_ADDCDIV_MUL_LAST | OTB_FLAVOR_FMA_LERP | \
+                                OTB_FLAVOR_FMA_ADDCMUL | OTB_FLAVOR_FMA_ADDCDIV | OTB_FLAVOR_FMA_ADD_ALPHA)
+
+const char* otb_last_error(void);
+int         otb_abi_version(void);
+/* sm count / compute capability of the current device; OTB_EARCH if not 10.x */
+int         otb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------
+ * Counter-based RNG shared by every kernel (and restated in oracle/otb_oracle.c):
+ * Philox4x32-10, key = 64-bit seed, counter = (group_lo, group_hi, offset_lo,
+ * stream<<24 | offset_hi[0:24)).  Streams keep the draws of one step disjoint.
+ * Indexing by GLOBAL sample / element index makes an N-GPU run draw exactly what a
+ * 1-GPU run at the same global batch draws (SURVEY.md §5 "RNG under DP").
+ * ---------------------------------------------------------------------------------- */
+#define OTB_STREAM_NOISE     0u
+#define OTB_STREAM_OFFSET    1u
+#define OTB_STREAM_PERTURB   2u
+#define OTB_STREAM_TIMESTEP  3u
+#define OTB_STREAM_SR        4u
+#define OTB_STREAM_DROPOUT   5u
+
+/* ------------------------------------------------------------------------------------
+ * K-c  multi-tensor AdamW / Adam step with bf16 stochastic rounding, fused EMA update,
+ *      fused gradient-clip scaling and optional bf16 shadow emission.
+ * Replaces: step_adamw_parameter  modules/util/optimizer/adamw_extensions.py:17-150
+ *           step_adam_parameter   modules/util/optimizer/adam_extensions.py (L2 variant)
+ *           copy_stochastic_/addcdiv_stochastic_  modules/util/bf16_stochastic_rounding.py:5-61
+ *           EMAModuleWrapper.step modules/module/EMAModule.py:37-54
+ *           nn.utils.clip_grad_norm_ scaling  modules/trainer/GenericTrainer.py:712-713
+ * One launch updates every tensor in the table.
+ * ---------------------------------------------------------------------------------- */
+typedef struct otb_optim_tensor {
+    void*       p;            /* parameter, dtype p_dtype, updated in place                 */
+    const void* g;            /* gradient, same dtype as p                                  */
+    void*       exp_avg;      /* state, same dtype as p                                     */
+    void*       exp_avg_sq;   /* state, same dtype as p                                     */
+    void*       ema;          /* EMA shadow (same dtype as p) or NULL                       */
+    void*       shadow_bf16;  /* optional bf16 copy of the updated p (fp32 masters) or NULL */
+    int64_t     numel;
+    int64_t     rng_base;     /* global element offset of this tensor in the SR stream      */
+    /* per-tensor scalars, already rounded the way torch rounds python scalars to float     */
+    float       decay_mul;    /* 1 - lr*weight_decay   (AdamW)   | 1 (Adam)                 */
+    float       l2;           /* 0 (AdamW)             | weight_decay (Adam: g += l2*p)     */
+    float       lerp_w;       /* 1 - beta1                                                  */
+    float       beta2;
+    float       one_minus_beta2;
+    float       bc2_sqrt;     /* sqrt(1 - beta2^step)                                       */
+    float       inv_bc2_sqrt; /* 1 / bc2_sqrt (used under OTB_FLAVOR_DIV_RECIPROCAL)        */
+    float       eps;
+    float       neg_step_size;/* -lr / (1 - beta1^step)                                     */
+    int32_t     p_dtype;      /* OTB_F32 | OTB_BF16                                         */
+    int32_t     flags;        /* bit0: stochastic rounding of p; bit1: maximize (g = -g)    */
+} otb_optim_tensor;
+
+typedef struct otb_optim_launch {
+    const otb_optim_tensor* tensors;   /* device array [n_tensors]                          */
+    const int32_t* chunk_tensor;       /* device [n_chunks] tensor index of each chunk      */
+    const int32_t* chunk_index;        /* device [n_chunks] chunk number inside that tensor */
+    int32_t  n_tensors;
+    int32_t  n_chunks;
+    int32_t  chunk_elems;              /* elements per chunk (multiple of 2048)             */
+    uint32_t flavor;                   /* OTB_FLAVOR_* bits                                 */
+    uint64_t seed;                     /* SR Philox key                                     */
+    uint64_t offset;                   /* SR Philox offset: the optimizer step number       */
+    float    ema_one_minus_decay;      /* 1 - min((1+s)/(10+s), decay); used iff do_ema     */
+    int32_t  do_ema;                   /* 1 on EMA update steps ((s+1) % interval == 0)     */
+    const float* clip_coef;            /* device scalar: g is scaled by it first, or NULL   */
+} otb_optim_launch;
+
+int otb_adamw_sr_ema_multi(const otb_optim_launch* args, void* stream);
+
+/* EMA-only multi-tensor step (optimizer not ours, e.g. third-party optimizers).
+ * Replaces EMAModuleWrapper.step modules/module/EMAModule.py:43-54.  Uses p/ema/numel/p_dtype of the table. */
+int otb_ema_multi(const otb_optim_launch* args, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Global gradient norm + clip coefficient.
+ * Replaces nn.utils.clip_grad_norm_(parameters, max_norm)  GenericTrainer.py:712-713
+ *   total_norm = ||g||_2 over all tensors; coef = min(1, max_norm / (total_norm + 1e-6)).
+ * partials: device float[n_chunks] workspace; out: device float[2] = {total_norm, coef}.
+ * Deterministic (fixed-order two-level reduction).  grad_prescale multiplies g before
+ * the norm (1/world_size under data parallel when the allreduce summed).
+ * ---------------------------------------------------------------------------------- */
+int otb_grad_norm_multi(const otb_optim_launch* args, float max_norm, float grad_prescale,
+                        float* partials, float* out_norm_coef, void* stream);
+/* in-place g *= coef for callers that want the reference's two-pass behaviour */
+int otb_grad_scale_multi(const otb_optim_launch* args, const float* coef, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * bf16 shadow refresh: for every LoRA tensor (fp32 or bf16 master, [rows, cols])
+ * emit a bf16 copy and a bf16 transposed copy, one launch for all leaves.
+ * (No reference counterpart: under autocast the reference re-casts A/B on every
+ *  call, modules/util/dtype_util.py:44-48; here the cast is hoisted to once per step.)
+ * ---------------------------------------------------------------------------------- */
+typedef struct otb_shadow_tensor {
+    const void* src;      /* master [rows, cols], dtype src_dtype */
+    void*       dst;      /* bf16 [rows, cols] or NULL            */
+    void*       dst_t;    /* bf16 [cols, rows] or NULL            */
+    int32_t     rows, cols;
+    int32_t     src_dtype;
+    int32_t     tile_base; /* first 32x32 tile index of this tensor in the launch */
+} otb_shadow_tensor;
+int otb_shadow_refresh_multi(const otb_shadow_tensor* tensors, int32_t n_tensors,
+                             int32_t n_tiles, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K-b1  noise + timestep + add-noise (+ target), the pre-network half of the
+ *       memory-bound step kernel.
+ * Replaces: _create_noise           ModelSetupNoiseMixin.py:18-49
+ *           _get_timestep_discrete  ModelSetupNoiseMixin.py:51-155 (UNIFORM, LOGIT_NORMAL,
+ *                                   HEAVY_TAIL, static + dynamic shift, deterministic)
+ *           _add_noise_discrete     ModelSetupDiffusionMixin.py:15-38 (DDPM tables)
+ *                                   ModelSetupFlowMatchingMixin.py:14-39 (rectified flow)
+ *           latent scaling          BaseStableDiffusionXLSetup.py:215, BaseFluxSetup.py:230
+ *           v / flow targets        BaseStableDiffusionXLSetup.py:285, BaseFluxSetup.py:307
+ * ---------------------------------------------------------------------------------- */
+#define OTB_TS_UNIFORM       0
+#define OTB_TS_LOGIT_NORMAL  1
+#define OTB_TS_HEAVY_TAIL    2
+#define OTB_TS_DETERMINISTIC 3   /* int(T*0.5)-1 */
+#define OTB_TS_GIVEN         4   /* timesteps supplied by the caller in `timestep` */
+
+#define OTB_TARGET_NONE    0
+#define OTB_TARGET_EPSILON 1     /* target = noise                               */
+#define OTB_TARGET_V       2     /* target = coef_x0*noise - coef_noise*x0       */
+#define OTB_TARGET_FLOW    3     /* target = noise - x0                          */
+
+typedef struct otb_noise_args {
+    /* tensors; B = batch, chw = C*hw */
+    const void* latent;        /* [B, chw] latent image, dtype latent_dtype                           */
+    const void* noise_in;      /* optional externally supplied noise (parity mode), latent_dtype or NULL */
+    void*       x0_out;        /* optional scaled latent (latent - shift)*scale, latent_dtype         */
+    void*       noise_out;     /* optional noise, latent_dtype                                        */
+    void*       noisy_out;     /* optional noisy latent, latent_dtype                                 */
+    void*       noisy_cast_out;/* optional noisy latent in cast_dtype (the network's train dtype)     */
+    void*       target_out;    /* optional target, latent_dtype                                       */
+    int32_t*    timestep;      /* [B] int32: output, or input when ts_mode == OTB_TS_GIVEN            */
+    float*      sigma_out;     /* optional [B]: coef_noise[t] (flow: sigma)                           */
+    const float* coef_x0;      /* [T] DDPM: sqrt(alphas_cumprod);     flow: 1 - sigma                 */
+    const float* coef_noise;   /* [T] DDPM: sqrt(1 - alphas_cumprod); flow: sigma = (t+1)/T           */
+    int32_t B, C, hw;
+    int32_t latent_dtype, cast_dtype;
+    int32_t target, ts_mode;
+    int32_t num_train_timesteps;   /* T */
+    int32_t generate_noise;        /* 1: draw from Philox; 0: read noise_in                           */
+    int32_t do_add_noise;          /* 0: only noise / timesteps are produced                          */
+    /* latent transform: x0 = (latent - shift) * scale */
+    float latent_scale, latent_shift;
+    /* noise options (_create_noise) */
+    float offset_noise_weight, perturbation_noise_weight;
+    /* timestep options (_get_timestep_discrete), pre-reduced on the host exactly as python does */
+    int32_t min_timestep, max_timestep;   /* int(T*min_noising_strength), int(T*max_noising_strength) */
+    float noising_weight, noising_bias;
+    float shift_c1;                /* (float)(T * shift)                                              */
+    float shift_c2;                /* (float)(shift - 1)                                              */
+    /* RNG */
+    uint64_t seed, offset;
+    int64_t  sample_base;          /* global index of sample 0 of this rank's batch (DP invariance)   */
+} otb_noise_args;
+
+int otb_noise_addnoise(const otb_noise_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K-b2  loss forward + backward in one pass: per-sample masked MSE/MAE with optional
+ *       mask-area normalisation and prior-preservation term, loss scaler, concept
+ *       weight, timestep weighting, and d(loss)/d(predicted) for an ASSUMED upstream
+ *       gradient (1/(B*GA) — what `.mean()` then `/GA` produces).
+ * Replaces: _diffusion_losses / _flow_matching_losses  ModelSetupDiffusionLossMixin.py:233-321
+ *           __masked_losses :36-117, __unmasked_losses :119-168
+ *           masked_losses_with_prior  modules/util/loss/masked_loss.py:21-45
+ *           __snr/__min_snr_weight/__debiased_estimation_weight/__p2_loss_weight/
+ *           __sigma_loss_weight :170-231
+ *           and the autograd backward of that chain (GenericTrainer.py:692-696)
+ * ---------------------------------------------------------------------------------- */
+#define OTB_LW_CONSTANT   0
+#define OTB_LW_MIN_SNR    1
+#define OTB_LW_DEBIASED   2
+#define OTB_LW_P2         3
+#define OTB_LW_SIGMA      4
+
+typedef struct otb_loss_args {
+    const void*  predicted;     /* [B, chw] pred_dtype                                     */
+    const void*  target;        /* [B, chw] target_dtype                                   */
+    const void*  prior_target;  /* [B, chw] target_dtype or NULL                           */
+    const void*  mask;          /* [B, hw] mask_dtype or NULL (unmasked)                   */
+    const float* loss_weight;   /* [B] per-concept weight or NULL (=1)                     */
+    const int32_t* timestep;    /* [B] or NULL                                             */
+    const float* sqrt_ac;       /* [T] (for snr weights) or NULL                           */
+    const float* sqrt_1mac;     /* [T]                                                     */
+    const float* sigmas;        /* [T] (t+1)/T for OTB_LW_SIGMA or NULL                    */
+    float*       losses;        /* [B] fp32 out                                            */
+    void*        dpred;         /* [B, chw] pred_dtype out, or NULL (forward only)         */
+    float*       partials;      /* workspace float[B * blocks_per_sample]                  */
+    uint32_t*    counters;      /* workspace uint32[B], zero on entry, zero on exit        */
+    float*       mask_stats;    /* workspace float[B*2]: mean(clamp(mask)), mean(1-clamp); filled by the call when needed */
+    int32_t B, C, hw;
+    int32_t pred_dtype, target_dtype, mask_dtype;
+    int32_t masked;             /* 1: __masked_losses; 0: __unmasked_losses                */
+    int32_t normalize_masked_area_loss;
+    int32_t loss_weight_fn;     /* OTB_LW_*                                                */
+    int32_t v_prediction;
+    int32_t num_train_timesteps;
+    int32_t blocks_per_sample;
+    float mse_strength, mae_strength;
+    float unmasked_weight, masked_prior_preservation_weight;
+    float loss_scale;           /* batch_size_scale * gradient_accumulation_steps_scale    */
+    float loss_weight_strength; /* gamma                                                   */
+    float upstream;             /* assumed d(total)/d(losses[b]); 1/(B*GA)                 */
+} otb_loss_args;
+
+int otb_loss_fwd_bwd(const otb_loss_args* args, void* stream);
+/* grid heuristic shared with the host so it can size `partials`: blocks per sample for a [B, C*hw] problem */
+int otb_loss_blocks_per_sample(int32_t B, int32_t C, int32_t hw);
+/* fix-up used by autograd.backward: dpred[b,:] *= grad_out[b] / assumed, skipped on the
+ * device (no write) when they are equal — the normal case. */
+int otb_loss_bwd_rescale(void* dpred, int32_t dtype, const float* grad_out, float assumed,
+                         int32_t B, int64_t chw, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K-a  LoRA down/up projections fused with the frozen base Linear / 1x1 conv.
+ *      tcgen05 (UTCHMMA) tiles, fp32 accumulators in TMEM, operands fed by TMA.
+ * Replaces LoRAModule.forward  modules/module/LoRAModule.py:319-323
+ *      y = x W^T + bias + ((s * x A^T)_bf16 [dropout]) B^T
+ * and its autograd backward:
+ *      dx = dy W + ((s * dy B)_bf16 [dropout]) A     -- the same kernel, called with the
+ *                                                       transposed bf16 shadows
+ *      dA = Gs^T x,  dB = dy^T Ts                    -- otb_lora_grad_ab
+ * All operands bf16, row-major, K-major ("x[M,K] . w[N,K]^T").
+ * ---------------------------------------------------------------------------------- */
+typedef struct otb_lora_linear_args {
+    const void* x;        /* [M, K]  bf16                                                   */
+    const void* w;        /* [N, K]  bf16 frozen base weight (fwd) / W^T shadow [K_in, N_out] (bwd) */
+    const void* down;     /* [R, K]  bf16 LoRA down (fwd: A; bwd: B^T)                      */
+    const void* up;       /* [N, R]  bf16 LoRA up   (fwd: B; bwd: A^T)                      */
+    const void* bias;     /* [N] bias_dtype or NULL                                         */
+    void*       y;        /* [M, N]  bf16 out                                               */
+    void*       t_out;    /* [M, R]  bf16 out: (s * x down^T) after dropout, or NULL        */
+    int32_t M, N, K, R;
+    int32_t bias_dtype;
+    float   scale;        /* alpha / rank                                                   */
+    float   dropout_p;    /* 0 disables                                                     */
+    uint64_t seed, offset;/* dropout Philox key (same in fwd and bwd => same mask)          */
+    int32_t tile_n;       /* 0 = let the library choose                                     */
+    int32_t stages;       /* 0 = let the library choose                                     */
+} otb_lora_linear_args;
+
+int otb_lora_linear(const otb_lora_linear_args* args, void* stream);
+
+/* dA[R,K] (+)= Gs[M,R]^T x[M,K] ;  dB[N,R] (+)= dy[M,N]^T Ts[M,R]   (fp32 accumulate via
+ * split-M partial sums; outputs must be zero or hold the running accumulation). */
+typedef struct otb_lora_grad_args {
+    const void* x;     /* [M, K] bf16 */
+    const void* dy;    /* [M, N] bf16 */
+    const void* gs;    /* [M, R] bf16 */
+    const void* ts;    /* [M, R] bf16 */
+    float*      dA;    /* [R, K] fp32 */
+    float*      dB;    /* [N, R] fp32 */
+    int32_t M, N, K, R;
+} otb_lora_grad_args;
+
+int otb_lora_grad_ab(const otb_lora_grad_args* args, void* stream);
+
+/* Utility used by tests and the data-parallel bucket path: fp32 <-> bf16 casts with
+ * round-to-nearest-even, and a device-side Philox dump for known-answer tests. */
+/* sizeof() of every argument struct, in declaration order: optim_tensor, optim_launch, shadow_tensor,
+ * noise_args, loss_args, lora_linear_args, lora_grad_args.  Bindings assert these at load time. */
+int otb_struct_sizes(int32_t* out7);
+
+int otb_philox_dump(uint64_t seed, uint64_t offset, uint32_t stream_id, int64_t first_group,
+                    int64_t n_groups, uint32_t* out4, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTB200_H */

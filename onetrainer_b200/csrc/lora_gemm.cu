@@ -1,0 +1,440 @@
+// lora_gemm.cu — K-a: LoRA down/up projections fused with the frozen base Linear.
+//
+//   y[M,N] = x[M,K] . w[N,K]^T  + bias[N] + drop(s * x . down[R,K]^T)_bf16 . up[N,R]^T
+//
+// Replaces LoRAModule.forward  /root/reference/modules/module/LoRAModule.py:319-323 (three GEMMs,
+// dropout, scale and add as separate ATen launches) and, called with the transposed shadows,
+// the dX half of its autograd backward.
+//
+// sm_100a design (one CTA per 128 x tile_n output tile, 192 threads, warp-specialised):
+//   warp 0     TMA producer: x / w / down tiles (64-wide K slabs, 128B swizzle) into a
+//              multi-stage smem ring, mbarrier full/empty pairs
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer.  The w tile and the down
+//              tile are adjacent in smem, so ONE UMMA of N' = tile_n + R per 16-wide k-step
+//              accumulates both x.w^T (TMEM columns [0,tile_n)) and T = x.down^T (columns
+//              [tile_n, tile_n+R)) — the skinny LoRA GEMM costs no extra pass over x.
+//   warps 2-5  epilogue: read T from TMEM, scale/dropout, round to bf16, park it in smem in
+//              the canonical K-major 128B-swizzled layout; warp 1 then issues R/16 more
+//              UMMAs (T . up^T) into the same accumulator; finally the accumulator is read
+//              back with tcgen05.ld, bias added, rounded to bf16 and stored.
+// Accumulation is fp32 in TMEM; T is rounded to bf16 once (it is an MMA operand) and the
+// output once — fewer roundings than the reference's five.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 64;           // one 128-byte swizzle row of bf16
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr long long WAIT_LIMIT_CYCLES = 6000000000ll;   // ~3 s: a protocol bug traps instead of hanging the GPU
+
+struct GemmParams {
+    int M, N, K;
+    int R;             // LoRA rank as stored (t_out leading dimension)
+    int Rp;            // rank padded to a multiple of 16 (UMMA N / K granularity); 0 = no LoRA branch
+    int tile_n;        // output tile width, multiple of 16, tile_n + Rp <= 256
+    int stages;
+    int num_kb;        // ceil(K / 64)
+    int n_tiles;
+    int tmem_cols;     // power of two >= tile_n + Rp
+    float scale;
+    float dropout_p;
+    uint64_t seed, offset;
+    const void* bias;
+    int bias_dtype;
+    uint16_t* y;
+    uint16_t* t_out;
+};
+
+// ------------------------------- PTX wrappers ---------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    long long t0 = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if ((++spins & 1023u) == 0) {
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > WAIT_LIMIT_CYCLES) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(m) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// all tcgen05 ops issued so far by this thread arrive on the mbarrier when complete
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile whose rows are 128 B apart and whose 8-row groups are
+// 1024 B apart (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;            // leading byte offset (unused for swizzled K-major), 16 B
+    d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+    return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b_format BF16 (1) [7,10)/[10,13),
+// a/b K-major (0) [15]/[16], N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    return (uint32_t)float_to_bf16_bits_rn(a) | ((uint32_t)float_to_bf16_bits_rn(b) << 16);
+}
+
+// smem carve-up (all tile bases stay 1024 B aligned because tile_n and Rp are multiples of 16)
+struct SmemLayout {
+    uint32_t stage_bytes, x_off, w_off, up_off, t_off, bar_off, total;
+};
+__host__ __device__ inline SmemLayout make_layout(int tile_n, int Rp, int stages) {
+    SmemLayout L;
+    L.x_off = 0;
+    L.w_off = BM * 128;
+    L.stage_bytes = (uint32_t)(BM + tile_n + Rp) * 128;
+    L.up_off = L.stage_bytes * stages;
+    L.t_off = L.up_off + (Rp ? (uint32_t)tile_n * 128 : 0);
+    L.bar_off = L.t_off + (Rp ? BM * 128 : 0);
+    L.total = L.bar_off + 256;
+    return L;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lora_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                   const __grid_constant__ CUtensorMap tm_dn, const __grid_constant__ CUtensorMap tm_up,
+                   const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem is only guaranteed 16 B aligned by the ABI; align by hand (host adds 1 KiB of slack)
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const SmemLayout L = make_layout(p.tile_n, p.Rp, p.stages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x / p.n_tiles, n_tile = blockIdx.x % p.n_tiles;
+    const int m0 = m_tile * BM, n0 = n_tile * p.tile_n;
+    const bool lora = p.Rp > 0;
+
+    const uint32_t bar_base = smem_base + L.bar_off;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+    const uint32_t up_full = bar_base + 8u * (2 * MAX_STAGES + 0);
+    const uint32_t t_full = bar_base + 8u * (2 * MAX_STAGES + 1);
+    const uint32_t t_ready = bar_base + 8u * (2 * MAX_STAGES + 2);
+    const uint32_t d_full = bar_base + 8u * (2 * MAX_STAGES + 3);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bar_off + 8u * (2 * MAX_STAGES + 4));
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
+        if (lora) { prefetch_tmap(&tm_dn); prefetch_tmap(&tm_up); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(up_full, 1); mbar_init(t_full, 1); mbar_init(t_ready, 128); mbar_init(d_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            if (lora) {
+                mbar_expect_tx(up_full, (uint32_t)p.tile_n * 128);
+                tma_load_2d(smem_base + L.up_off, &tm_up, up_full, 0, n0);
+            }
+            int s = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(empty_bar(s), ph ^ 1);
+                const uint32_t st = smem_base + L.stage_bytes * s;
+                mbar_expect_tx(full_bar(s), L.stage_bytes);
+                tma_load_2d(st + L.x_off, &tm_x, full_bar(s), kb * BK, m0);
+                tma_load_2d(st + L.w_off, &tm_w, full_bar(s), kb * BK, n0);
+                if (lora) tma_load_2d(st + L.w_off + (uint32_t)p.tile_n * 128, &tm_dn, full_bar(s), kb * BK, 0);
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc_main = umma_idesc_bf16(BM, p.tile_n + p.Rp);
+            int s = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t st = smem_base + L.stage_bytes * s;
+                const uint64_t adesc = umma_desc_sw128(st + L.x_off);
+                const uint64_t bdesc = umma_desc_sw128(st + L.w_off);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)   // +32 B per k-step inside the swizzle row
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_main, (kb | k) != 0);
+                umma_commit(empty_bar(s));               // frees the smem stage once these MMAs retire
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+            if (lora) {
+                umma_commit(t_full);                     // T = x.down^T complete (and the base GEMM with it)
+                mbar_wait(t_ready, 0);                   // epilogue parked bf16 T in smem
+                mbar_wait(up_full, 0);
+                tc_fence_after();
+                const uint32_t idesc_up = umma_idesc_bf16(BM, p.tile_n);
+                const uint64_t adesc = umma_desc_sw128(smem_base + L.t_off);
+                const uint64_t bdesc = umma_desc_sw128(smem_base + L.up_off);
+                for (int k = 0; k < p.Rp / UMMA_K; ++k)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_up, 1u);
+            }
+            umma_commit(d_full);
+        }
+    } else {
+        // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =================
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;                // row inside the 128-row tile == TMEM lane
+        const int m = m0 + row;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        if (lora) {
+            mbar_wait(t_full, 0);
+            tc_fence_after();
+            const float keep_scale = p.dropout_p > 0.0f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+            uint8_t* t_row = smem_gen + L.t_off + row * 128;
+            for (int c = 0; c < p.Rp; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_lane + (uint32_t)(p.tile_n + c), v);
+                tmem_ld_wait();
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.scale;
+                if (p.dropout_p > 0.0f) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const uint64_t e = (uint64_t)m * (uint64_t)p.Rp + (uint64_t)(c + j);
+                        Philox4 r = otb_rng(p.seed, p.offset, OTB_STREAM_DROPOUT, e >> 2);
+                        f[j + 0] = otb_u01(r.x) >= p.dropout_p ? f[j + 0] * keep_scale : 0.0f;
+                        f[j + 1] = otb_u01(r.y) >= p.dropout_p ? f[j + 1] * keep_scale : 0.0f;
+                        f[j + 2] = otb_u01(r.z) >= p.dropout_p ? f[j + 2] * keep_scale : 0.0f;
+                        f[j + 3] = otb_u01(r.w) >= p.dropout_p ? f[j + 3] * keep_scale : 0.0f;
+                    }
+                }
+                uint4 lo = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                uint4 hi = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+                // canonical SW128 K-major: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
+                const int j0 = c >> 3;
+                *reinterpret_cast<uint4*>(t_row + (((j0 + 0) ^ (row & 7)) << 4)) = lo;
+                *reinterpret_cast<uint4*>(t_row + (((j0 + 1) ^ (row & 7)) << 4)) = hi;
+                if (p.t_out != nullptr && n_tile == 0 && m < p.M) {
+                    uint16_t* dst = p.t_out + (size_t)m * p.R + c;
+                    if (c + 8 <= p.R) *reinterpret_cast<uint4*>(dst) = lo;
+                    if (c + 16 <= p.R) *reinterpret_cast<uint4*>(dst + 8) = hi;
+                }
+            }
+            fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            tc_fence_before();
+            mbar_arrive(t_ready);
+        }
+        mbar_wait(d_full, 0);
+        tc_fence_after();
+        for (int c = 0; c < p.tile_n; c += 16) {
+            const int n = n0 + c;
+            if (n >= p.N) break;                         // warp-uniform
+            uint32_t v[16];
+            tmem_ld16(t_lane + (uint32_t)c, v);
+            tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n + j < p.N) f[j] += load_as_float(p.bias, n + j, p.bias_dtype);
+            }
+            if (m < p.M) {
+                uint16_t* dst = p.y + (size_t)m * p.N + n;
+                if (n + 8 <= p.N)
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                if (n + 16 <= p.N)
+                    *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ------------------------------- host side ------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (PFN_encodeTiled)p;
+    return fn;
+}
+
+// row-major bf16 [rows, cols] tensor, box = box_rows x 64 columns, 128B swizzle, OOB -> 0
+int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows, const char* what) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { otb_set_error("cuTensorMapEncodeTiled entry point not available"); return OTB_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        otb_set_error("cuTensorMapEncodeTiled(%s: ptr=%p rows=%lld cols=%lld box_rows=%d) failed with CUresult %d", what, ptr,
+                      (long long)rows, (long long)cols, box_rows, (int)r);
+        return OTB_ECUDA;
+    }
+    return OTB_OK;
+}
+
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+// Pick the tile width that minimises (waves x per-tile time) on `sms` SMs.  Per 16-wide k-step a
+// tile costs max(N'/2, 32 + N'/4) cycles (tensor pipe vs 128 B/clk of smem operand fetch,
+// N' = tile_n + Rp); the epilogue adds ~12 cycles per output column.
+int choose_tile_n(int M, int N, int K, int Rp, int sms) {
+    const int m_tiles = (M + BM - 1) / BM;
+    const int kb4 = ((K + BK - 1) / BK) * 4;
+    double best = 1e30; int best_tn = 64;
+    for (int tn = 32; tn + Rp <= 256; tn += 16) {
+        int n_tiles = (N + tn - 1) / tn;
+        int64_t tiles = (int64_t)m_tiles * n_tiles;
+        int64_t waves = (tiles + sms - 1) / sms;
+        int np = tn + Rp;
+        double kstep = np / 2.0 > 32 + np / 4.0 ? np / 2.0 : 32 + np / 4.0;
+        double tile_time = kb4 * kstep + 12.0 * tn + 1500.0;
+        double t = waves * tile_time;
+        if (t < best - 1e-9) { best = t; best_tn = tn; }
+    }
+    return best_tn;
+}
+
+}  // namespace
+
+extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
+    OTB_CHECK_ARG(a != nullptr, "null args");
+    OTB_CHECK_ARG(a->x && a->w && a->y, "null x / w / y");
+    OTB_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+    OTB_CHECK_ARG(a->R >= 0, "negative rank");
+    OTB_UNSUPPORTED(a->K % 8 != 0 || a->N % 8 != 0, "K (%d) and N (%d) must be multiples of 8 (16-byte TMA strides / vector stores)", a->K, a->N);
+    OTB_UNSUPPORTED(a->R % 8 != 0 || a->R > 64, "LoRA rank %d unsupported: must be a multiple of 8 and <= 64", a->R);
+    OTB_CHECK_ARG(a->R == 0 || (a->down && a->up), "rank > 0 needs down / up");
+    OTB_CHECK_ARG(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "dropout_p must be in [0,1)");
+    OTB_CHECK_ARG((((uintptr_t)a->x | (uintptr_t)a->w | (uintptr_t)a->y | (uintptr_t)a->down | (uintptr_t)a->up |
+                    (uintptr_t)a->t_out) & 15) == 0, "all tensor pointers must be 16-byte aligned");
+    int sms = otb_sm_count();
+    GemmParams p;
+    p.M = a->M; p.N = a->N; p.K = a->K; p.R = a->R;
+    p.Rp = (a->R + 15) / 16 * 16;
+    p.tile_n = a->tile_n > 0 ? a->tile_n : choose_tile_n(a->M, a->N, a->K, p.Rp, sms);
+    OTB_CHECK_ARG(p.tile_n % 16 == 0 && p.tile_n >= 16 && p.tile_n + p.Rp <= 256, "tile_n %d invalid (multiple of 16, tile_n + rank <= 256)", p.tile_n);
+    p.num_kb = (a->K + BK - 1) / BK;
+    p.n_tiles = (a->N + p.tile_n - 1) / p.tile_n;
+    int cols = 32;
+    while (cols < p.tile_n + p.Rp) cols <<= 1;
+    p.tmem_cols = cols;
+    int stages = a->stages > 0 ? a->stages : MAX_STAGES;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages > p.num_kb) stages = p.num_kb;
+    while (stages > 1 && (int)make_layout(p.tile_n, p.Rp, stages).total + 1024 > SMEM_LIMIT) --stages;
+    p.stages = stages;
+    const SmemLayout L = make_layout(p.tile_n, p.Rp, stages);
+    OTB_CHECK_ARG((int)L.total + 1024 <= SMEM_LIMIT, "tile does not fit shared memory");
+    p.scale = a->scale; p.dropout_p = a->dropout_p; p.seed = a->seed; p.offset = a->offset;
+    p.bias = a->bias; p.bias_dtype = a->bias_dtype;
+    p.y = (uint16_t*)a->y; p.t_out = (uint16_t*)a->t_out;
+
+    CUtensorMap tm_x, tm_w, tm_dn, tm_up;
+    int rc;
+    if ((rc = make_tmap(&tm_x, a->x, a->M, a->K, BM, "x")) != OTB_OK) return rc;
+    if ((rc = make_tmap(&tm_w, a->w, a->N, a->K, p.tile_n, "w")) != OTB_OK) return rc;
+    if (p.Rp > 0) {
+        if ((rc = make_tmap(&tm_dn, a->down, a->R, a->K, p.Rp, "down")) != OTB_OK) return rc;
+        if ((rc = make_tmap(&tm_up, a->up, a->N, a->R, p.tile_n, "up")) != OTB_OK) return rc;
+    } else {
+        tm_dn = tm_x; tm_up = tm_x;
+    }
+    static thread_local int smem_set_for_dev = -1;
+    int dev = 0;
+    OTB_CUDA(cudaGetDevice(&dev));
+    if (smem_set_for_dev != dev) {
+        OTB_CUDA(cudaFuncSetAttribute(lora_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        smem_set_for_dev = dev;
+    }
+    const int m_tiles = (a->M + BM - 1) / BM;
+    dim3 grid((unsigned)(m_tiles * p.n_tiles));
+    lora_linear_kernel<<<grid, NUM_THREADS, L.total + 1024, (cudaStream_t)stream>>>(tm_x, tm_w, tm_dn, tm_up, p);
+    OTB_LAUNCH_CHECK("lora_linear_kernel");
+    return OTB_OK;
+}

@@ -1,0 +1,201 @@
+// lora_grad.cu — the two skinny weight-gradient contractions of the LoRA backward:
+//
+//   dA[R,K] += Gs[M,R]^T . x[M,K]          dB[N,R] += dy[M,N]^T . Ts[M,R]
+//
+// (dA = s (dY B)^T X, dB = s dY^T (X A^T); Gs and Ts are the bf16,
+// already-scaled rank-R activations the fused forward / dX kernels park in HBM.)
+// Both are "out[R,Q] = U[M,R]^T . V[M,Q]" with a contraction over the LONG dimension M and
+// a rank-R (16..64) output: arithmetic intensity is 2R flop per 2 bytes of V, i.e. they are
+// bound by streaming V once (HBM/L2), not by the tensor pipe — R=32 needs 32 flop/B x 6.5 TB/s
+// = 0.2 PFLOP/s.  So they use warp-level mma.sync (HMMA) fed by cp.async + ldmatrix.trans,
+// split M across CTAs to fill the chip, and reduce the partial sums with fp32 red.global.add.
+// One launch computes both gradients (grid.z selects the problem).
+#include "common.cuh"
+
+namespace {
+
+constexpr int GQ = 128;        // output columns (of V) per CTA
+constexpr int GM = 64;         // rows of M per pipeline stage
+constexpr int G_STAGES = 3;
+constexpr int G_THREADS = 256; // 8 warps x 16 columns
+constexpr int V_PITCH = GQ * 2 + 16;   // bytes; +16 keeps ldmatrix rows on distinct bank groups
+
+struct GradProblem {
+    const uint16_t* U;   // [M, R]
+    const uint16_t* V;   // [M, Q]
+    float* out;          // transposed_out ? [Q, R] : [R, Q]
+    int Q;
+    int q_tiles;
+    int transposed_out;
+};
+struct GradParams {
+    GradProblem pr[2];
+    int M, R, Rp;        // Rp: rank padded to 16
+    int m_per_cta;       // multiple of GM
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;     // src-size 0 => zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// grid = (max q_tiles, m_splits, 2)
+__global__ void __launch_bounds__(G_THREADS) lora_grad_kernel(const GradParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const GradProblem pr = p.pr[blockIdx.z];
+    if ((int)blockIdx.x >= pr.q_tiles || pr.out == nullptr) return;
+    const int q0 = blockIdx.x * GQ;
+    const int m_begin = blockIdx.y * p.m_per_cta;
+    int m_end = m_begin + p.m_per_cta;
+    if (m_end > p.M) m_end = p.M;
+    if (m_begin >= m_end) return;
+    const int n_steps = (m_end - m_begin + GM - 1) / GM;
+
+    const int u_pitch = p.Rp * 2 + 16;
+    const uint32_t v_stage = GM * V_PITCH, u_stage = GM * u_pitch;
+    const uint32_t smem_v = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t smem_u = smem_v + G_STAGES * v_stage;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    auto issue = [&](int step) {
+        const int st = step % G_STAGES;
+        const int mrow0 = m_begin + step * GM;
+        // V tile: GM rows x 16 chunks of 16 B
+        for (int c = threadIdx.x; c < GM * (GQ / 8); c += G_THREADS) {
+            const int r = c >> 4, ch = c & 15;
+            const int m = mrow0 + r, q = q0 + ch * 8;
+            const bool ok = (m < m_end) && (q < pr.Q);
+            const uint16_t* src = ok ? pr.V + (size_t)m * pr.Q + q : pr.V;
+            cp_async16(smem_v + st * v_stage + r * V_PITCH + ch * 16, src, ok);
+        }
+        // U tile: GM rows x Rp/8 chunks
+        const int uch = p.Rp >> 3;
+        for (int c = threadIdx.x; c < GM * uch; c += G_THREADS) {
+            const int r = c / uch, ch = c % uch;
+            const int m = mrow0 + r;
+            const bool ok = (m < m_end) && (ch * 8 < p.R);
+            const uint16_t* src = ok ? pr.U + (size_t)m * p.R + ch * 8 : pr.U;
+            cp_async16(smem_u + st * u_stage + r * u_pitch + ch * 16, src, ok);
+        }
+    };
+
+    float acc[4][2][4];     // [r tile of 16][n tile of 8][frag]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.0f;
+
+    for (int s = 0; s < G_STAGES - 1; ++s) {
+        if (s < n_steps) issue(s);
+        cp_async_commit();
+    }
+    const int r_tiles = p.Rp >> 4;
+    for (int step = 0; step < n_steps; ++step) {
+        cp_async_wait<G_STAGES - 2>();
+        __syncthreads();
+        if (step + G_STAGES - 1 < n_steps) issue(step + G_STAGES - 1);
+        cp_async_commit();
+        const int st = step % G_STAGES;
+        const uint32_t vb = smem_v + st * v_stage, ub = smem_u + st * u_stage;
+#pragma unroll
+        for (int kk = 0; kk < GM / 16; ++kk) {
+            // B fragments for this warp's 16 columns: smem is [k][n] (n contiguous) -> .trans
+            // matrices: (k 0-7, n 0-7), (k 8-15, n 0-7), (k 0-7, n 8-15), (k 8-15, n 8-15)
+            uint32_t b[4];
+            {
+                const int krow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int ncol = warp * 16 + (lane >> 4) * 8;
+                ldsm_x4_trans(vb + krow * V_PITCH + ncol * 2, b[0], b[1], b[2], b[3]);
+            }
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                if (rt < r_tiles) {
+                    // A = U^T: smem is [k][r] (r contiguous) -> .trans
+                    // matrices: (r 0-7, k 0-7), (r 8-15, k 0-7), (r 0-7, k 8-15), (r 8-15, k 8-15)
+                    uint32_t a[4];
+                    const int krow = kk * 16 + (lane & 7) + (lane >> 4) * 8;
+                    const int rcol = rt * 16 + ((lane >> 3) & 1) * 8;
+                    ldsm_x4_trans(ub + krow * u_pitch + rcol * 2, a[0], a[1], a[2], a[3]);
+                    mma_bf16_16816(acc[rt][0], a, b[0], b[1]);
+                    mma_bf16_16816(acc[rt][1], a, b[2], b[3]);
+                }
+            }
+        }
+    }
+    // partial sums -> global (fp32 reductions)
+    const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+    for (int rt = 0; rt < 4; ++rt) {
+        if (rt >= r_tiles) continue;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = rt * 16 + g + (k >> 1) * 8;
+                const int q = q0 + warp * 16 + nt * 8 + t4 * 2 + (k & 1);
+                if (r < p.R && q < pr.Q) {
+                    float* dst = pr.transposed_out ? pr.out + (size_t)q * p.R + r : pr.out + (size_t)r * pr.Q + q;
+                    atomicAdd(dst, acc[rt][nt][k]);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int otb_lora_grad_ab(const otb_lora_grad_args* a, void* stream) {
+    OTB_CHECK_ARG(a != nullptr, "null args");
+    OTB_CHECK_ARG(a->M > 0 && a->R > 0 && a->R <= 64 && a->R % 8 == 0, "bad M=%d R=%d (R multiple of 8, <= 64)", a->M, a->R);
+    const bool doA = a->dA != nullptr, doB = a->dB != nullptr;
+    if (!doA && !doB) return OTB_OK;
+    if (doA) OTB_CHECK_ARG(a->gs && a->x && a->K > 0 && a->K % 8 == 0, "dA needs gs, x and K %% 8 == 0");
+    if (doB) OTB_CHECK_ARG(a->ts && a->dy && a->N > 0 && a->N % 8 == 0, "dB needs ts, dy and N %% 8 == 0");
+    OTB_CHECK_ARG((((uintptr_t)a->x | (uintptr_t)a->dy | (uintptr_t)a->gs | (uintptr_t)a->ts) & 15) == 0,
+                  "all operand pointers must be 16-byte aligned");
+    GradParams p;
+    p.M = a->M; p.R = a->R; p.Rp = (a->R + 15) / 16 * 16;
+    p.pr[0].U = (const uint16_t*)a->gs; p.pr[0].V = (const uint16_t*)a->x; p.pr[0].out = doA ? a->dA : nullptr;
+    p.pr[0].Q = a->K; p.pr[0].q_tiles = doA ? (a->K + GQ - 1) / GQ : 0; p.pr[0].transposed_out = 0;
+    p.pr[1].U = (const uint16_t*)a->ts; p.pr[1].V = (const uint16_t*)a->dy; p.pr[1].out = doB ? a->dB : nullptr;
+    p.pr[1].Q = a->N; p.pr[1].q_tiles = doB ? (a->N + GQ - 1) / GQ : 0; p.pr[1].transposed_out = 1;
+    const int q_tiles_total = p.pr[0].q_tiles + p.pr[1].q_tiles;
+    const int q_tiles_max = p.pr[0].q_tiles > p.pr[1].q_tiles ? p.pr[0].q_tiles : p.pr[1].q_tiles;
+    // split M so that the launch fills ~2 waves of the chip, but keep >= GM rows per CTA
+    const int sms = otb_sm_count();
+    int splits = (2 * sms + q_tiles_total - 1) / q_tiles_total;
+    const int max_splits = (a->M + GM - 1) / GM;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    int m_per = (a->M + splits - 1) / splits;
+    m_per = (m_per + GM - 1) / GM * GM;
+    splits = (a->M + m_per - 1) / m_per;
+    p.m_per_cta = m_per;
+    const int u_pitch = p.Rp * 2 + 16;
+    const size_t smem = (size_t)G_STAGES * GM * (V_PITCH + u_pitch);
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    OTB_CUDA(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        OTB_CUDA(cudaFuncSetAttribute(lora_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_dev = dev;
+    }
+    dim3 grid((unsigned)q_tiles_max, (unsigned)splits, 2);
+    lora_grad_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(p);
+    OTB_LAUNCH_CHECK("lora_grad_kernel");
+    return OTB_OK;
+}

@@ -1,0 +1,481 @@
+// noise_loss.cu — K-b1 (noise + timestep + add-noise + target) and K-b2 (loss fwd+bwd).
+//
+// Reference behaviour restated:
+//   _create_noise            modules/modelSetup/mixin/ModelSetupNoiseMixin.py:18-49
+//   _get_timestep_discrete   modules/modelSetup/mixin/ModelSetupNoiseMixin.py:51-155
+//   _add_noise_discrete      modules/modelSetup/mixin/ModelSetupDiffusionMixin.py:15-38
+//                            modules/modelSetup/mixin/ModelSetupFlowMatchingMixin.py:14-39
+//   targets                  modules/modelSetup/BaseStableDiffusionXLSetup.py:277-291, BaseFluxSetup.py:307
+//   _diffusion_losses / _flow_matching_losses  mixin/ModelSetupDiffusionLossMixin.py:233-321
+//   masked_losses_with_prior modules/util/loss/masked_loss.py:21-45
+//
+// Both kernels are HBM-bound with O(1) flop/byte: 128-bit accesses, warp-shuffle reductions,
+// one deterministic last-block reduction per sample.  Separate torch ops in the reference are
+// separate roundings here (explicit _rn intrinsics, no contraction).
+#include "common.cuh"
+
+#define NL_THREADS 256
+
+namespace {
+
+// ------------------------------------------------------------------------------------
+// timestep for global sample `gs` — fp32 op order of ModelSetupNoiseMixin.py:97-121
+// transcendental pieces are evaluated in fp64 and rounded once to fp32 so the CPU oracle
+// (libm) and the GPU agree bit-for-bit on the resulting integer.
+// ------------------------------------------------------------------------------------
+__device__ int32_t sample_timestep(const otb_noise_args& a, int64_t gs) {
+    const int T = a.num_train_timesteps;
+    if (a.ts_mode == OTB_TS_DETERMINISTIC) return (int)((double)T * 0.5) - 1;
+    Philox4 r = otb_rng(a.seed, a.offset, OTB_STREAM_TIMESTEP, (uint64_t)gs);
+    const float num_t = (float)(a.max_timestep - a.min_timestep);
+    const float min_t = (float)a.min_timestep;
+    float ts;
+    if (a.ts_mode == OTB_TS_UNIFORM) {
+        float u = otb_u01(r.x);
+        ts = __fadd_rn(min_t, __fmul_rn(num_t, u));
+    } else if (a.ts_mode == OTB_TS_LOGIT_NORMAL) {
+        double u1 = ((double)(r.x >> 8) + 0.5) * 5.9604644775390625e-08;
+        double th = ((double)((int32_t)r.y >> 8) + 0.5) * 1.1920928955078125e-07 * 3.14159265358979323846;
+        float z = (float)(sqrt(-2.0 * log(u1)) * cos(th));
+        float scale = __fadd_rn(a.noising_weight, 1.0f);
+        float nrm = __fadd_rn(__fmul_rn(z, scale), a.noising_bias);
+        float sg = (float)(1.0 / (1.0 + exp(-(double)nrm)));
+        ts = __fadd_rn(__fmul_rn(sg, num_t), min_t);
+    } else {  // HEAVY_TAIL
+        float u = otb_u01(r.x);
+        float ang = __fmul_rn(1.57079632679489661923f, u);
+        float c = (float)cos((double)ang);
+        float c2 = __fmul_rn(c, c);
+        float e = __fadd_rn(__fsub_rn(c2, 1.0f), u);
+        float f = __fmul_rn(a.noising_weight, e);
+        float h = __fsub_rn(__fsub_rn(1.0f, u), f);
+        ts = __fadd_rn(__fmul_rn(h, num_t), min_t);
+    }
+    // timestep = T*shift*ts / ((shift-1)*ts + T)
+    float num = __fmul_rn(a.shift_c1, ts);
+    float den = __fadd_rn(__fmul_rn(a.shift_c2, ts), (float)T);
+    ts = __fdiv_rn(num, den);
+    return (int32_t)ts;   // .int(): truncation toward zero
+}
+
+__device__ __forceinline__ void load4(const void* p, int64_t i, int dtype, float (&f)[4]) {
+    if (dtype == OTB_F32) {
+        uint4 r = ld_stream_u4((const float*)p + i);
+        f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y); f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+    } else if (dtype == OTB_BF16) {
+        uint2 r = ld_stream_u2((const uint16_t*)p + i);
+        f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xFFFF0000u);
+        f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xFFFF0000u);
+    } else {
+        uint2 r = ld_stream_u2((const __half*)p + i);
+        __half2 a = *reinterpret_cast<__half2*>(&r.x), b = *reinterpret_cast<__half2*>(&r.y);
+        f[0] = __low2float(a); f[1] = __high2float(a); f[2] = __low2float(b); f[3] = __high2float(b);
+    }
+}
+__device__ __forceinline__ void store4(void* p, int64_t i, int dtype, const float (&f)[4]) {
+    if (dtype == OTB_F32) {
+        st_stream_u4((float*)p + i, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+    } else if (dtype == OTB_BF16) {
+        uint32_t lo = (uint32_t)float_to_bf16_bits_rn(f[0]) | ((uint32_t)float_to_bf16_bits_rn(f[1]) << 16);
+        uint32_t hi = (uint32_t)float_to_bf16_bits_rn(f[2]) | ((uint32_t)float_to_bf16_bits_rn(f[3]) << 16);
+        st_stream_u2((uint16_t*)p + i, make_uint2(lo, hi));
+    } else {
+        __half2 a = __floats2half2_rn(f[0], f[1]), b = __floats2half2_rn(f[2], f[3]);
+        st_stream_u2((__half*)p + i, make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b)));
+    }
+}
+
+__device__ __forceinline__ float rnd_dt(float x, int dtype) {
+    if (dtype == OTB_BF16) return round_bf16(x);
+    if (dtype == OTB_F16) return __half2float(__float2half_rn(x));
+    return x;
+}
+
+// four N(0,1) draws for global element group `grp` of stream `stream`
+__device__ __forceinline__ void normal4(const otb_noise_args& a, uint32_t stream, uint64_t grp, float (&z)[4]) {
+    Philox4 r = otb_rng(a.seed, a.offset, stream, grp);
+    otb_box_muller_fast(r.x, r.y, z[0], z[1]);
+    otb_box_muller_fast(r.z, r.w, z[2], z[3]);
+}
+__device__ __forceinline__ float normal1(const otb_noise_args& a, uint32_t stream, uint64_t elem) {
+    float z[4];
+    normal4(a, stream, elem >> 2, z);
+    return z[elem & 3];
+}
+
+// grid = (blocks_per_sample, B); each thread owns groups of 4 consecutive elements.
+__global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_args a) {
+    const int b = blockIdx.y;
+    const int64_t chw = (int64_t)a.C * a.hw;
+    const int64_t gs = a.sample_base + b;
+    __shared__ int32_t s_t;
+    if (threadIdx.x == 0) {
+        int32_t t = (a.ts_mode == OTB_TS_GIVEN) ? a.timestep[b] : sample_timestep(a, gs);
+        s_t = t;
+        if (blockIdx.x == 0) {
+            if (a.ts_mode != OTB_TS_GIVEN && a.timestep) a.timestep[b] = t;
+            if (a.sigma_out && a.coef_noise) a.sigma_out[b] = a.coef_noise[t];
+        }
+    }
+    __syncthreads();
+    const int32_t t = s_t;
+    const bool add = a.do_add_noise != 0;
+    const float cx = add ? a.coef_x0[t] : 0.0f;
+    const float cn = add ? a.coef_noise[t] : 0.0f;
+    const int ldt = a.latent_dtype;
+    const bool need_noise = a.generate_noise || a.noise_in;
+    const int64_t base = (int64_t)b * chw;
+
+    if ((chw & 3) == 0) {
+        const int64_t ngroups = chw >> 2;
+        for (int64_t gi = (int64_t)blockIdx.x * NL_THREADS + threadIdx.x; gi < ngroups; gi += (int64_t)gridDim.x * NL_THREADS) {
+            const int64_t i = gi << 2;
+            float n[4] = {0, 0, 0, 0};
+            if (a.generate_noise) {
+                const uint64_t ge = (uint64_t)(gs * chw + i);
+                normal4(a, OTB_STREAM_NOISE, ge >> 2, n);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) n[k] = rnd_dt(n[k], ldt);
+                if (a.offset_noise_weight > 0.0f) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        int c = (int)((i + k) / a.hw);
+                        float on = rnd_dt(normal1(a, OTB_STREAM_OFFSET, (uint64_t)(gs * a.C + c)), ldt);
+                        n[k] = rnd_dt(__fadd_rn(n[k], rnd_dt(__fmul_rn(a.offset_noise_weight, on), ldt)), ldt);
+                    }
+                }
+                if (a.perturbation_noise_weight > 0.0f) {
+                    float pn[4];
+                    normal4(a, OTB_STREAM_PERTURB, ge >> 2, pn);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        n[k] = rnd_dt(__fadd_rn(n[k], rnd_dt(__fmul_rn(a.perturbation_noise_weight, rnd_dt(pn[k], ldt)), ldt)), ldt);
+                }
+            } else if (a.noise_in) {
+                load4(a.noise_in, base + i, ldt, n);
+            }
+            if (a.noise_out && need_noise) store4(a.noise_out, base + i, ldt, n);
+            if (!a.latent) continue;
+            float x[4];
+            load4(a.latent, base + i, ldt, x);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = rnd_dt(__fmul_rn(rnd_dt(__fsub_rn(x[k], a.latent_shift), ldt), a.latent_scale), ldt);
+            if (a.x0_out) store4(a.x0_out, base + i, ldt, x);
+            if (add) {
+                float y[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) y[k] = __fadd_rn(__fmul_rn(x[k], cx), __fmul_rn(n[k], cn));
+                if (a.noisy_out) store4(a.noisy_out, base + i, ldt, y);
+                if (a.noisy_cast_out) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) y[k] = rnd_dt(y[k], ldt);
+                    store4(a.noisy_cast_out, base + i, a.cast_dtype, y);
+                }
+            }
+            if (a.target_out && a.target != OTB_TARGET_NONE) {
+                float tg[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (a.target == OTB_TARGET_EPSILON) tg[k] = n[k];
+                    else if (a.target == OTB_TARGET_V) tg[k] = __fsub_rn(__fmul_rn(cx, n[k]), __fmul_rn(cn, x[k]));
+                    else tg[k] = __fsub_rn(n[k], x[k]);
+                }
+                store4(a.target_out, base + i, ldt, tg);
+            }
+        }
+    } else {
+        // ragged tail path (chw not a multiple of 4): one element per thread, same RNG indexing
+        for (int64_t i = (int64_t)blockIdx.x * NL_THREADS + threadIdx.x; i < chw; i += (int64_t)gridDim.x * NL_THREADS) {
+            float n = 0.0f;
+            if (a.generate_noise) {
+                const uint64_t ge = (uint64_t)(gs * chw + i);
+                n = rnd_dt(normal1(a, OTB_STREAM_NOISE, ge), ldt);
+                if (a.offset_noise_weight > 0.0f) {
+                    int c = (int)(i / a.hw);
+                    float on = rnd_dt(normal1(a, OTB_STREAM_OFFSET, (uint64_t)(gs * a.C + c)), ldt);
+                    n = rnd_dt(__fadd_rn(n, rnd_dt(__fmul_rn(a.offset_noise_weight, on), ldt)), ldt);
+                }
+                if (a.perturbation_noise_weight > 0.0f) {
+                    float pn = rnd_dt(normal1(a, OTB_STREAM_PERTURB, ge), ldt);
+                    n = rnd_dt(__fadd_rn(n, rnd_dt(__fmul_rn(a.perturbation_noise_weight, pn), ldt)), ldt);
+                }
+            } else if (a.noise_in) {
+                n = load_as_float(a.noise_in, base + i, ldt);
+            }
+            if (a.noise_out && need_noise) store_from_float(a.noise_out, base + i, ldt, n);
+            if (!a.latent) continue;
+            float x = load_as_float(a.latent, base + i, ldt);
+            x = rnd_dt(__fmul_rn(rnd_dt(__fsub_rn(x, a.latent_shift), ldt), a.latent_scale), ldt);
+            if (a.x0_out) store_from_float(a.x0_out, base + i, ldt, x);
+            if (add) {
+                float y = __fadd_rn(__fmul_rn(x, cx), __fmul_rn(n, cn));
+                if (a.noisy_out) store_from_float(a.noisy_out, base + i, ldt, y);
+                if (a.noisy_cast_out) store_from_float(a.noisy_cast_out, base + i, a.cast_dtype, rnd_dt(y, ldt));
+            }
+            if (a.target_out && a.target != OTB_TARGET_NONE) {
+                float tg = a.target == OTB_TARGET_EPSILON ? n
+                         : a.target == OTB_TARGET_V ? __fsub_rn(__fmul_rn(cx, n), __fmul_rn(cn, x))
+                                                    : __fsub_rn(n, x);
+                store_from_float(a.target_out, base + i, ldt, tg);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K-b2
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* sm) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = threadIdx.x < NL_THREADS / 32 ? sm[threadIdx.x] : 0.0f;
+    if (threadIdx.x < 32) r = warp_sum(r);
+    __syncthreads();
+    return r;  // valid in warp 0
+}
+
+// mean(clamp(mask, uw, 1)) and mean(1 - clamp(mask, uw, 1)) per sample; grid = B
+__global__ void __launch_bounds__(NL_THREADS) mask_stats_kernel(const void* mask, int mask_dtype, int hw, float uw, float* stats) {
+    __shared__ float sm[NL_THREADS / 32];
+    const int b = blockIdx.x;
+    float s0 = 0.0f, s1 = 0.0f;
+    for (int i = threadIdx.x; i < hw; i += NL_THREADS) {
+        float m = load_as_float(mask, (int64_t)b * hw + i, mask_dtype);
+        m = fminf(fmaxf(m, uw), 1.0f);
+        s0 += m;
+        s1 += __fsub_rn(1.0f, m);
+    }
+    s0 = block_sum(s0, sm);
+    s1 = block_sum(s1, sm);
+    if (threadIdx.x == 0) {
+        stats[2 * b] = s0 / (float)hw;
+        stats[2 * b + 1] = s1 / (float)hw;
+    }
+}
+
+// timestep weight of sample b — ModelSetupDiffusionLossMixin.py:170-231
+__device__ float timestep_weight(const otb_loss_args& a, int b) {
+    if (a.loss_weight_fn == OTB_LW_CONSTANT || a.timestep == nullptr) return 1.0f;
+    const int t = a.timestep[b];
+    if (a.loss_weight_fn == OTB_LW_SIGMA) return a.sigmas ? a.sigmas[t] : 1.0f;
+    if (a.sqrt_ac == nullptr) return 1.0f;
+    float q = __fdiv_rn(a.sqrt_ac[t], a.sqrt_1mac[t]);
+    float snr = __fmul_rn(q, q);
+    if (a.loss_weight_fn == OTB_LW_MIN_SNR) {
+        float mn = fminf(snr, a.loss_weight_strength);
+        if (a.v_prediction) snr = __fadd_rn(snr, 1.0f);
+        return __fdiv_rn(mn, snr);
+    }
+    if (a.loss_weight_fn == OTB_LW_DEBIASED) {
+        float w = fminf(snr, 1.0e3f);
+        if (a.v_prediction) w = __fadd_rn(w, 1.0f);
+        return __fdiv_rn(1.0f, __fsqrt_rn(w));
+    }
+    // P2
+    if (a.v_prediction) snr = __fadd_rn(snr, 1.0f);
+    return powf(__fadd_rn(1.0f, snr), -a.loss_weight_strength);
+}
+
+// grid = (blocks_per_sample, B)
+__global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args a) {
+    __shared__ float sm[NL_THREADS / 32];
+    __shared__ bool s_last;
+    const int b = blockIdx.y;
+    const int64_t chw = (int64_t)a.C * a.hw;
+    const int64_t base = (int64_t)b * chw;
+    const bool masked = a.masked != 0 && a.mask != nullptr;
+    const bool prior = masked && a.prior_target != nullptr && a.masked_prior_preservation_weight != 0.0f;
+    // per-sample constants
+    float inv_mm = 1.0f, inv_mp = 1.0f;
+    if (a.normalize_masked_area_loss && a.mask != nullptr) {
+        inv_mm = 1.0f / a.mask_stats[2 * b];
+        inv_mp = 1.0f / a.mask_stats[2 * b + 1];
+    }
+    const float wt = timestep_weight(a, b);
+    const float lw = a.loss_weight ? a.loss_weight[b] : 1.0f;
+    const float inv_n = 1.0f / (float)chw;
+    // post factor applied to the per-sample mean: scale * loss_weight * timestep weight
+    const float post = a.loss_scale * lw * wt;
+    // coefficients of the element terms
+    const float k_main = masked ? inv_mm : ((a.normalize_masked_area_loss && a.mask) ? inv_mm : 1.0f);
+    const float k_prior = prior ? a.masked_prior_preservation_weight * inv_mp : 0.0f;
+    const float gfac = post * inv_n * a.upstream;        // multiplies d(elem term)/d(pred)
+    const bool want_grad = a.dpred != nullptr;
+
+    float acc = 0.0f;
+    if ((chw & 3) == 0 && (a.hw & 3) == 0) {
+        const int64_t ngroups = chw >> 2;
+        for (int64_t gi = (int64_t)blockIdx.x * NL_THREADS + threadIdx.x; gi < ngroups; gi += (int64_t)gridDim.x * NL_THREADS) {
+            const int64_t i = gi << 2;
+            float p[4], t[4], pt[4] = {0, 0, 0, 0}, m[4] = {1, 1, 1, 1}, g[4];
+            load4(a.predicted, base + i, a.pred_dtype, p);
+            load4(a.target, base + i, a.target_dtype, t);
+            if (prior) load4(a.prior_target, base + i, a.target_dtype, pt);
+            if (masked) {
+                const int64_t mi = (int64_t)b * a.hw + (i % a.hw);
+                if (a.mask_dtype == OTB_F32) {   // mask is re-read C times: keep it cacheable
+                    float4 mv = *reinterpret_cast<const float4*>((const float*)a.mask + mi);
+                    m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) m[k] = load_as_float(a.mask, mi + k, a.mask_dtype);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) m[k] = fminf(fmaxf(m[k], a.unmasked_weight), 1.0f);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float d = __fsub_rn(p[k], t[k]);
+                const float wm = m[k] * k_main;
+                float term = a.mse_strength * (d * d) * wm;
+                float gr = a.mse_strength * 2.0f * d * wm;
+                if (a.mae_strength != 0.0f) {
+                    term += a.mae_strength * fabsf(d) * wm;
+                    gr += a.mae_strength * (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * wm;
+                }
+                if (prior) {
+                    const float dp = __fsub_rn(p[k], pt[k]);
+                    const float wp = __fsub_rn(1.0f, m[k]) * k_prior;
+                    term += a.mse_strength * (dp * dp) * wp;
+                    gr += a.mse_strength * 2.0f * dp * wp;
+                    if (a.mae_strength != 0.0f) {
+                        term += a.mae_strength * fabsf(dp) * wp;
+                        gr += a.mae_strength * (dp > 0.0f ? 1.0f : (dp < 0.0f ? -1.0f : 0.0f)) * wp;
+                    }
+                }
+                acc += term;
+                g[k] = gr * gfac;
+            }
+            if (want_grad) store4(a.dpred, base + i, a.pred_dtype, g);
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * NL_THREADS + threadIdx.x; i < chw; i += (int64_t)gridDim.x * NL_THREADS) {
+            const float p = load_as_float(a.predicted, base + i, a.pred_dtype);
+            const float t = load_as_float(a.target, base + i, a.target_dtype);
+            float m = 1.0f;
+            if (masked) m = fminf(fmaxf(load_as_float(a.mask, (int64_t)b * a.hw + (i % a.hw), a.mask_dtype), a.unmasked_weight), 1.0f);
+            const float d = __fsub_rn(p, t);
+            const float wm = m * k_main;
+            float term = a.mse_strength * (d * d) * wm;
+            float gr = a.mse_strength * 2.0f * d * wm;
+            if (a.mae_strength != 0.0f) {
+                term += a.mae_strength * fabsf(d) * wm;
+                gr += a.mae_strength * (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * wm;
+            }
+            if (prior) {
+                const float dp = __fsub_rn(p, load_as_float(a.prior_target, base + i, a.target_dtype));
+                const float wp = __fsub_rn(1.0f, m) * k_prior;
+                term += a.mse_strength * (dp * dp) * wp;
+                gr += a.mse_strength * 2.0f * dp * wp;
+                if (a.mae_strength != 0.0f) {
+                    term += a.mae_strength * fabsf(dp) * wp;
+                    gr += a.mae_strength * (dp > 0.0f ? 1.0f : (dp < 0.0f ? -1.0f : 0.0f)) * wp;
+                }
+            }
+            acc += term;
+            if (want_grad) store_from_float(a.dpred, base + i, a.pred_dtype, gr * gfac);
+        }
+    }
+    acc = block_sum(acc, sm);
+    // deterministic cross-block reduction: the last block to arrive sums the partials in order
+    if (threadIdx.x == 0) {
+        a.partials[(int64_t)b * gridDim.x + blockIdx.x] = acc;
+        __threadfence();
+        unsigned prev = atomicAdd(&a.counters[b], 1u);
+        s_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        float s = 0.0f;
+        for (int k = threadIdx.x; k < (int)gridDim.x; k += NL_THREADS)
+            s += __ldcg(&a.partials[(int64_t)b * gridDim.x + k]);
+        s = block_sum(s, sm);
+        if (threadIdx.x == 0) {
+            a.losses[b] = s * inv_n * post;
+            a.counters[b] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NL_THREADS) loss_bwd_rescale_kernel(void* dpred, int dtype, const float* grad_out,
+                                                                      float assumed, int64_t chw) {
+    const int b = blockIdx.y;
+    const float go = grad_out[b];
+    if (go == assumed) return;              // the normal case: nothing to do, nothing touched
+    const float ratio = go / assumed;
+    const int64_t base = (int64_t)b * chw;
+    for (int64_t i = (int64_t)blockIdx.x * NL_THREADS + threadIdx.x; i < chw; i += (int64_t)gridDim.x * NL_THREADS)
+        store_from_float(dpred, base + i, dtype, load_as_float(dpred, base + i, dtype) * ratio);
+}
+
+int blocks_per_sample_for(int64_t chw, int B) {
+    // 4 elements per thread per iteration; aim at >= 4 waves of 148 SMs x 8 resident blocks when the
+    // problem is large, never more blocks than there are 1024-element slabs.
+    int64_t slabs = (chw / 4 + NL_THREADS - 1) / NL_THREADS;
+    if (slabs < 1) slabs = 1;
+    int64_t want = (int64_t)otb_sm_count() * 8 * 4 / (B > 0 ? B : 1);
+    if (want < 1) want = 1;
+    int64_t bps = slabs < want ? slabs : want;
+    if (bps > 65535) bps = 65535;
+    return (int)bps;
+}
+
+}  // namespace
+
+extern "C" int otb_noise_addnoise(const otb_noise_args* a, void* stream) {
+    OTB_CHECK_ARG(a != nullptr, "null args");
+    OTB_CHECK_ARG(a->B > 0 && a->C > 0 && a->hw > 0, "bad shape B=%d C=%d hw=%d", a->B, a->C, a->hw);
+    OTB_CHECK_ARG(a->B <= 65535, "batch %d too large for one launch", a->B);
+    OTB_CHECK_ARG(a->latent_dtype >= OTB_F32 && a->latent_dtype <= OTB_F16, "bad latent dtype");
+    OTB_CHECK_ARG(a->ts_mode >= OTB_TS_UNIFORM && a->ts_mode <= OTB_TS_GIVEN, "bad timestep mode %d", a->ts_mode);
+    OTB_CHECK_ARG(a->timestep != nullptr || (!a->do_add_noise && a->ts_mode != OTB_TS_GIVEN && a->target != OTB_TARGET_V),
+                  "timestep buffer required");
+    if (a->do_add_noise || a->target == OTB_TARGET_V) {
+        OTB_CHECK_ARG(a->coef_x0 && a->coef_noise, "schedule tables required for add-noise / v-target");
+        OTB_CHECK_ARG(a->latent != nullptr, "latent required for add-noise");
+    }
+    OTB_CHECK_ARG(!(a->generate_noise && a->noise_in), "generate_noise and noise_in are mutually exclusive");
+    OTB_CHECK_ARG(a->num_train_timesteps > 0, "num_train_timesteps must be positive");
+    if (a->ts_mode != OTB_TS_GIVEN && a->ts_mode != OTB_TS_DETERMINISTIC)
+        OTB_CHECK_ARG(a->max_timestep >= a->min_timestep && a->min_timestep >= 0 && a->max_timestep <= a->num_train_timesteps,
+                      "bad timestep range [%d,%d)", a->min_timestep, a->max_timestep);
+    const int64_t chw = (int64_t)a->C * a->hw;
+    dim3 grid(blocks_per_sample_for(chw, a->B), a->B);
+    noise_addnoise_kernel<<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+    OTB_LAUNCH_CHECK("noise_addnoise_kernel");
+    return OTB_OK;
+}
+
+extern "C" int otb_loss_fwd_bwd(const otb_loss_args* a, void* stream) {
+    OTB_CHECK_ARG(a != nullptr, "null args");
+    OTB_CHECK_ARG(a->B > 0 && a->C > 0 && a->hw > 0 && a->B <= 65535, "bad shape B=%d C=%d hw=%d", a->B, a->C, a->hw);
+    OTB_CHECK_ARG(a->predicted && a->target && a->losses && a->partials && a->counters, "null tensor");
+    OTB_CHECK_ARG(a->blocks_per_sample > 0 && a->blocks_per_sample <= 65535, "bad blocks_per_sample");
+    OTB_CHECK_ARG(!(a->masked && !a->mask), "masked loss needs a mask");
+    if (a->loss_weight_fn == OTB_LW_MIN_SNR || a->loss_weight_fn == OTB_LW_DEBIASED || a->loss_weight_fn == OTB_LW_P2)
+        OTB_CHECK_ARG(a->timestep == nullptr || (a->sqrt_ac && a->sqrt_1mac), "snr weighting needs the schedule tables");
+    if (a->normalize_masked_area_loss && a->mask) {
+        OTB_CHECK_ARG(a->mask_stats != nullptr, "mask_stats workspace required");
+        mask_stats_kernel<<<a->B, NL_THREADS, 0, (cudaStream_t)stream>>>(a->mask, a->mask_dtype, a->hw, a->unmasked_weight, a->mask_stats);
+        OTB_LAUNCH_CHECK("mask_stats_kernel");
+    }
+    dim3 grid(a->blocks_per_sample, a->B);
+    loss_fwd_bwd_kernel<<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+    OTB_LAUNCH_CHECK("loss_fwd_bwd_kernel");
+    return OTB_OK;
+}
+
+extern "C" int otb_loss_blocks_per_sample(int32_t B, int32_t C, int32_t hw) {
+    return blocks_per_sample_for((int64_t)C * hw, B);
+}
+
+extern "C" int otb_loss_bwd_rescale(void* dpred, int32_t dtype, const float* grad_out, float assumed,
+                                    int32_t B, int64_t chw, void* stream) {
+    OTB_CHECK_ARG(dpred && grad_out && B > 0 && chw > 0 && assumed != 0.0f, "bad rescale args");
+    dim3 grid(blocks_per_sample_for(chw, B), B);
+    loss_bwd_rescale_kernel<<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(dpred, dtype, grad_out, assumed, chw);
+    OTB_LAUNCH_CHECK("loss_bwd_rescale_kernel");
+    return OTB_OK;
+}

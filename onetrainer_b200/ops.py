@@ -1,0 +1,394 @@
+"""Functional wrappers over the C ABI: tensors in, kernels launched on the current stream.
+
+These are the only call sites of libotb200 in the package; the reference-facing classes
+(modules/..., util/...) are written on top of them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+_OPT_DTYPE = np.dtype(N.OptimTensor)
+_SHADOW_DTYPE = np.dtype(N.ShadowTensor)
+
+CHUNK_ELEMS = 16384          # elements of one tensor handled by one CTA of the multi-tensor kernels
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _aligned16(*tensors) -> bool:
+    return all(t is None or (t.data_ptr() & 15) == 0 for t in tensors)
+
+
+# --------------------------------------------------------------------------------------
+# K-a
+# --------------------------------------------------------------------------------------
+def lora_linear(x: torch.Tensor, w: torch.Tensor, down: torch.Tensor | None, up: torch.Tensor | None,
+                bias: torch.Tensor | None, scale: float, *, dropout_p: float = 0.0, seed: int = 0,
+                offset: int = 0, want_t: bool = True, tile_n: int = 0, stages: int = 0):
+    """y = x w^T + bias + drop(scale * x down^T)_bf16 up^T  on tcgen05.  Returns (y, t) with
+    t = drop(scale * x down^T) in bf16 ([M, R]) or None.  x:[M,K] w:[N,K] down:[R,K] up:[N,R], bf16."""
+    N.require_cuda(x, w, down, up, bias)
+    for name, t in (("x", x), ("w", w), ("down", down), ("up", up)):
+        if t is not None and (t.dtype != torch.bfloat16 or not t.is_contiguous() or t.dim() != 2):
+            raise ValueError(f"lora_linear: {name} must be a contiguous 2-D bf16 tensor")
+    M, K = x.shape
+    Nn = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"lora_linear: w is {tuple(w.shape)}, expected [N, {K}]")
+    R = 0
+    if down is not None:
+        R = down.shape[0]
+        if down.shape[1] != K or up is None or tuple(up.shape) != (Nn, R):
+            raise ValueError("lora_linear: down must be [R, K] and up [N, R]")
+    y = torch.empty((M, Nn), dtype=torch.bfloat16, device=x.device)
+    t = torch.empty((M, R), dtype=torch.bfloat16, device=x.device) if (want_t and R > 0) else None
+    if M == 0:
+        return y, t
+    a = N.LoraLinearArgs(
+        x=x.data_ptr(), w=w.data_ptr(), down=N.ptr(down), up=N.ptr(up), bias=N.ptr(bias), y=y.data_ptr(),
+        t_out=N.ptr(t), M=M, N=Nn, K=K, R=R,
+        bias_dtype=N.dtype_code(bias.dtype) if bias is not None else N.F32,
+        scale=float(scale), dropout_p=float(dropout_p), seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1),
+        tile_n=int(tile_n), stages=int(stages))
+    N.check(N.lib().otb_lora_linear(C.byref(a), _stream()), "otb_lora_linear")
+    return y, t
+
+
+def lora_grad_ab(x, dy, gs, ts, dA: torch.Tensor | None, dB: torch.Tensor | None) -> None:
+    """dA[R,K] += gs^T x ; dB[N,R] += dy^T ts  (fp32 accumulation into the given buffers)."""
+    N.require_cuda(x, dy, gs, ts, dA, dB)
+    M = x.shape[0] if x is not None else dy.shape[0]
+    R = gs.shape[1] if gs is not None else ts.shape[1]
+    for t in (dA, dB):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise ValueError("lora_grad_ab: dA / dB must be contiguous fp32")
+    a = N.LoraGradArgs(x=N.ptr(x), dy=N.ptr(dy), gs=N.ptr(gs), ts=N.ptr(ts), dA=N.ptr(dA), dB=N.ptr(dB),
+                       M=M, N=dy.shape[1] if dy is not None else 0, K=x.shape[1] if x is not None else 0, R=R)
+    N.check(N.lib().otb_lora_grad_ab(C.byref(a), _stream()), "otb_lora_grad_ab")
+
+
+# --------------------------------------------------------------------------------------
+# K-b1
+# --------------------------------------------------------------------------------------
+def noise_addnoise(*, latent=None, noise_in=None, coef_x0=None, coef_noise=None, timestep=None,
+                   B: int, C_: int, hw: int, latent_dtype: torch.dtype, device,
+                   want_x0=False, want_noise=False, want_noisy=False, cast_dtype: torch.dtype | None = None,
+                   target: int = N.TARGET_NONE, ts_mode: int = N.TS_GIVEN, num_train_timesteps: int = 1000,
+                   generate_noise: bool = True, do_add_noise: bool = True,
+                   latent_scale: float = 1.0, latent_shift: float = 0.0,
+                   offset_noise_weight: float = 0.0, perturbation_noise_weight: float = 0.0,
+                   min_timestep: int = 0, max_timestep: int = 1000, noising_weight: float = 0.0,
+                   noising_bias: float = 0.0, shift: float = 1.0, seed: int = 0, offset: int = 0,
+                   sample_base: int = 0, want_sigma: bool = False, shape=None) -> dict:
+    """One launch of the pre-network half of the step kernel; returns the requested tensors."""
+    N.require_cuda(latent, noise_in, coef_x0, coef_noise, timestep)
+    shape = tuple(shape) if shape is not None else (B, C_ * hw)
+    ldt = N.dtype_code(latent_dtype)
+
+    def new(dt):
+        return torch.empty(shape, dtype=dt, device=device)
+
+    out = {}
+    x0 = new(latent_dtype) if want_x0 else None
+    noise = new(latent_dtype) if want_noise else None
+    noisy = new(latent_dtype) if want_noisy else None
+    noisy_cast = new(cast_dtype) if cast_dtype is not None else None
+    tgt = new(latent_dtype) if target != N.TARGET_NONE else None
+    if ts_mode == N.TS_GIVEN:
+        if timestep is None:
+            raise ValueError("noise_addnoise: ts_mode GIVEN needs timesteps")
+        ts = timestep.to(dtype=torch.int32).contiguous()
+    else:
+        ts = torch.empty((B,), dtype=torch.int32, device=device)
+    sigma = torch.empty((B,), dtype=torch.float32, device=device) if want_sigma else None
+    T = int(num_train_timesteps)
+    a = N.NoiseArgs(
+        latent=N.ptr(latent), noise_in=N.ptr(noise_in), x0_out=N.ptr(x0), noise_out=N.ptr(noise), noisy_out=N.ptr(noisy),
+        noisy_cast_out=N.ptr(noisy_cast), target_out=N.ptr(tgt), timestep=ts.data_ptr(), sigma_out=N.ptr(sigma),
+        coef_x0=N.ptr(coef_x0), coef_noise=N.ptr(coef_noise),
+        B=B, C=C_, hw=hw, latent_dtype=ldt,
+        cast_dtype=N.dtype_code(cast_dtype) if cast_dtype is not None else ldt,
+        target=target, ts_mode=ts_mode, num_train_timesteps=T,
+        generate_noise=1 if generate_noise else 0, do_add_noise=1 if do_add_noise else 0,
+        latent_scale=float(latent_scale), latent_shift=float(latent_shift),
+        offset_noise_weight=float(offset_noise_weight), perturbation_noise_weight=float(perturbation_noise_weight),
+        min_timestep=int(min_timestep), max_timestep=int(max_timestep),
+        noising_weight=float(noising_weight), noising_bias=float(noising_bias),
+        shift_c1=float(T * shift), shift_c2=float(shift - 1),
+        seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1), sample_base=int(sample_base))
+    N.check(N.lib().otb_noise_addnoise(C.byref(a), _stream()), "otb_noise_addnoise")
+    out.update(x0=x0, noise=noise, noisy=noisy, noisy_cast=noisy_cast, target=tgt, timestep=ts, sigma=sigma)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# K-b2
+# --------------------------------------------------------------------------------------
+class LossWorkspace:
+    """Per-device scratch of the loss kernel (partials, arrival counters, mask statistics)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, device, B: int, bps: int):
+        key = (str(device), B, bps)
+        if key not in self._bufs:
+            self._bufs[key] = (
+                torch.empty((B * bps,), dtype=torch.float32, device=device),
+                torch.zeros((B,), dtype=torch.int32, device=device),
+                torch.empty((B * 2,), dtype=torch.float32, device=device),
+            )
+        return self._bufs[key]
+
+
+_loss_ws = LossWorkspace()
+
+
+def loss_fwd_bwd(predicted, target, *, prior_target=None, mask=None, loss_weight=None, timestep=None,
+                 sqrt_ac=None, sqrt_1mac=None, sigmas=None, masked=False, normalize_masked_area_loss=False,
+                 loss_weight_fn=N.LW_CONSTANT, v_prediction=False, num_train_timesteps=1000,
+                 mse_strength=1.0, mae_strength=0.0, unmasked_weight=0.1, masked_prior_preservation_weight=0.0,
+                 loss_scale=1.0, loss_weight_strength=5.0, upstream=1.0, want_grad=True):
+    """Per-sample losses [B] (fp32) and d(sum_b upstream*losses[b])/d(predicted) in one pass."""
+    N.require_cuda(predicted, target, prior_target, mask, loss_weight, timestep, sqrt_ac, sqrt_1mac, sigmas)
+    if predicted.shape != target.shape:
+        raise ValueError("loss_fwd_bwd: predicted / target shapes differ")
+    predicted = predicted.contiguous()
+    target = target.contiguous()
+    B = predicted.shape[0]
+    Cc = predicted.shape[1] if predicted.dim() > 2 else 1
+    hw = predicted[0].numel() // Cc
+    dev = predicted.device
+    if prior_target is not None:
+        prior_target = prior_target.to(dtype=target.dtype).contiguous()
+    if mask is not None:
+        mask = mask.contiguous()
+        if mask.numel() != B * hw:
+            raise ValueError(f"loss_fwd_bwd: mask has {mask.numel()} elements, expected B*H*W = {B * hw}")
+    if loss_weight is not None:
+        loss_weight = loss_weight.to(device=dev, dtype=torch.float32).contiguous()
+    if timestep is not None:
+        timestep = timestep.to(dtype=torch.int32).contiguous()
+        if timestep.numel() == 1 and B > 1:
+            timestep = timestep.expand(B).contiguous()
+    bps = N.lib().otb_loss_blocks_per_sample(B, Cc, hw)
+    partials, counters, mask_stats = _loss_ws.get(dev, B, bps)
+    losses = torch.empty((B,), dtype=torch.float32, device=dev)
+    dpred = torch.empty_like(predicted) if want_grad else None
+    if not _aligned16(predicted, target, prior_target, mask, dpred):
+        raise ValueError("loss_fwd_bwd: tensors must be 16-byte aligned")
+    a = N.LossArgs(
+        predicted=predicted.data_ptr(), target=target.data_ptr(), prior_target=N.ptr(prior_target), mask=N.ptr(mask),
+        loss_weight=N.ptr(loss_weight), timestep=N.ptr(timestep), sqrt_ac=N.ptr(sqrt_ac), sqrt_1mac=N.ptr(sqrt_1mac),
+        sigmas=N.ptr(sigmas), losses=losses.data_ptr(), dpred=N.ptr(dpred), partials=partials.data_ptr(),
+        counters=counters.data_ptr(), mask_stats=mask_stats.data_ptr(),
+        B=B, C=Cc, hw=hw, pred_dtype=N.dtype_code(predicted.dtype), target_dtype=N.dtype_code(target.dtype),
+        mask_dtype=N.dtype_code(mask.dtype) if mask is not None else N.F32,
+        masked=1 if masked else 0, normalize_masked_area_loss=1 if normalize_masked_area_loss else 0,
+        loss_weight_fn=int(loss_weight_fn), v_prediction=1 if v_prediction else 0,
+        num_train_timesteps=int(num_train_timesteps), blocks_per_sample=bps,
+        mse_strength=float(mse_strength), mae_strength=float(mae_strength), unmasked_weight=float(unmasked_weight),
+        masked_prior_preservation_weight=float(masked_prior_preservation_weight), loss_scale=float(loss_scale),
+        loss_weight_strength=float(loss_weight_strength), upstream=float(upstream))
+    N.check(N.lib().otb_loss_fwd_bwd(C.byref(a), _stream()), "otb_loss_fwd_bwd")
+    return losses, dpred
+
+
+def loss_bwd_rescale(dpred: torch.Tensor, grad_out: torch.Tensor, assumed: float) -> None:
+    B = dpred.shape[0]
+    go = grad_out.to(dtype=torch.float32).contiguous()
+    N.check(N.lib().otb_loss_bwd_rescale(dpred.data_ptr(), N.dtype_code(dpred.dtype), go.data_ptr(), float(assumed),
+                                         B, dpred[0].numel(), _stream()), "otb_loss_bwd_rescale")
+
+
+# --------------------------------------------------------------------------------------
+# K-c: multi-tensor tables
+# --------------------------------------------------------------------------------------
+class OptimTable:
+    """Device-resident pointer table for the multi-tensor kernels.
+
+    `entries` is a list of dicts with tensors p, g, exp_avg, exp_avg_sq, ema, shadow (any may be
+    None) — all of one tensor sharing a dtype.  The chunk map is static; per-step scalars and
+    gradient pointers are refreshed on the host (numpy, vectorised) and re-uploaded with one
+    pinned async copy.
+    """
+
+    def __init__(self, entries: list[dict], device, chunk_elems: int = CHUNK_ELEMS):
+        self.device = torch.device(device)
+        self.n = len(entries)
+        self.chunk_elems = chunk_elems
+        self.host = np.zeros(self.n, dtype=_OPT_DTYPE)
+        self._pinned = torch.empty((max(self.n, 1) * _OPT_DTYPE.itemsize,), dtype=torch.uint8).pin_memory() \
+            if torch.cuda.is_available() else None
+        self.dev = torch.empty((max(self.n, 1) * _OPT_DTYPE.itemsize,), dtype=torch.uint8, device=self.device)
+        chunk_tensor, chunk_index = [], []
+        rng_base = 0
+        self.numels = []
+        for i, e in enumerate(entries):
+            p = e["p"]
+            n = p.numel()
+            self.numels.append(n)
+            h = self.host[i]
+            h["numel"] = n
+            h["rng_base"] = rng_base
+            rng_base += (n + 7) // 8 * 8
+            h["p_dtype"] = N.dtype_code(p.dtype)
+            nch = (n + chunk_elems - 1) // chunk_elems
+            chunk_tensor += [i] * nch
+            chunk_index += list(range(nch))
+        self.total_rng = rng_base
+        self.n_chunks = len(chunk_tensor)
+        self.chunk_tensor = torch.tensor(chunk_tensor, dtype=torch.int32).to(self.device)
+        self.chunk_index = torch.tensor(chunk_index, dtype=torch.int32).to(self.device)
+        self.partials = torch.empty((max(self.n_chunks, 1),), dtype=torch.float32, device=self.device)
+        self.norm_coef = torch.zeros((2,), dtype=torch.float32, device=self.device)
+        self.set_pointers(entries)
+
+    def set_pointers(self, entries: list[dict]) -> None:
+        h = self.host
+        for i, e in enumerate(entries):
+            ptrs = [e.get(k) for k in ("p", "g", "exp_avg", "exp_avg_sq", "ema", "shadow")]
+            for name, t in zip(("p", "g", "exp_avg", "exp_avg_sq", "ema", "shadow_bf16"), ptrs):
+                if t is not None:
+                    if not t.is_contiguous():
+                        raise ValueError("multi-tensor kernels need contiguous tensors")
+                    if name not in ("shadow_bf16",) and t.dtype != e["p"].dtype:
+                        raise NotImplementedError(
+                            f"optimizer/EMA tensor '{name}' has dtype {t.dtype} but the parameter is {e['p'].dtype}")
+                    if t.numel() != e["p"].numel():
+                        raise ValueError(f"'{name}' has {t.numel()} elements, parameter has {e['p'].numel()}")
+                h[name][i] = 0 if t is None else t.data_ptr()
+            aligned = all(t is None or (t.data_ptr() & 15) == 0 for t in ptrs)
+            h["flags"][i] = (int(h["flags"][i]) & ~N.OPT_FLAG_ALIGNED16) | (N.OPT_FLAG_ALIGNED16 if aligned else 0)
+
+    def set_grad_pointers(self, grads: list[torch.Tensor | None]) -> None:
+        h = self.host
+        for i, g in enumerate(grads):
+            if g is None:
+                h["g"][i] = 0
+                continue
+            if not g.is_contiguous() or g.numel() != self.numels[i]:
+                raise ValueError("gradient must be contiguous and match its parameter")
+            h["g"][i] = g.data_ptr()
+            if g.data_ptr() & 15:
+                h["flags"][i] = int(h["flags"][i]) & ~N.OPT_FLAG_ALIGNED16
+
+    def upload(self) -> None:
+        raw = self.host.view(np.uint8).reshape(-1)
+        if self._pinned is not None:
+            self._pinned[: raw.size].numpy()[:] = raw
+            self.dev[: raw.size].copy_(self._pinned[: raw.size], non_blocking=True)
+        else:
+            self.dev[: raw.size].copy_(torch.from_numpy(raw.copy()))
+
+    def launch_args(self, *, flavor=N.FLAVOR_TORCH_CUDA, seed=0, offset=0, ema_one_minus_decay=0.0, do_ema=False,
+                    clip_coef: torch.Tensor | None = None) -> N.OptimLaunch:
+        return N.OptimLaunch(
+            tensors=self.dev.data_ptr(), chunk_tensor=self.chunk_tensor.data_ptr(), chunk_index=self.chunk_index.data_ptr(),
+            n_tensors=self.n, n_chunks=self.n_chunks, chunk_elems=self.chunk_elems, flavor=int(flavor),
+            seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1),
+            ema_one_minus_decay=float(ema_one_minus_decay), do_ema=1 if do_ema else 0, clip_coef=N.ptr(clip_coef))
+
+
+def adam_scalars(lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, step: float,
+                 decoupled: bool) -> dict:
+    """Per-tensor float scalars exactly as the reference derives them in python doubles and torch
+    then narrows to fp32 (adamw_extensions.py:83-132)."""
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    step_size = lr / bc1
+    bc2_sqrt = math.sqrt(bc2)
+    f = np.float32
+    return dict(
+        decay_mul=f(1 - lr * weight_decay) if decoupled else f(1.0),
+        l2=f(0.0) if decoupled else f(weight_decay),
+        lerp_w=f(1 - beta1), beta2=f(beta2), one_minus_beta2=f(1 - beta2),
+        bc2_sqrt=f(bc2_sqrt), inv_bc2_sqrt=f(1.0) / f(bc2_sqrt), eps=f(eps), neg_step_size=f(-step_size))
+
+
+def adamw_sr_ema_multi(table: OptimTable, **kw) -> None:
+    a = table.launch_args(**kw)
+    N.check(N.lib().otb_adamw_sr_ema_multi(C.byref(a), _stream()), "otb_adamw_sr_ema_multi")
+
+
+def ema_multi(table: OptimTable, one_minus_decay: float) -> None:
+    a = table.launch_args(ema_one_minus_decay=one_minus_decay, do_ema=True)
+    N.check(N.lib().otb_ema_multi(C.byref(a), _stream()), "otb_ema_multi")
+
+
+def grad_norm_multi(table: OptimTable, max_norm: float, grad_prescale: float = 1.0) -> torch.Tensor:
+    """Returns the device tensor [total_norm, clip_coef] (no host sync)."""
+    a = table.launch_args()
+    N.check(N.lib().otb_grad_norm_multi(C.byref(a), float(max_norm), float(grad_prescale), table.partials.data_ptr(),
+                                        table.norm_coef.data_ptr(), _stream()), "otb_grad_norm_multi")
+    return table.norm_coef
+
+
+def grad_scale_multi(table: OptimTable, coef: torch.Tensor) -> None:
+    a = table.launch_args()
+    N.check(N.lib().otb_grad_scale_multi(C.byref(a), coef.data_ptr(), _stream()), "otb_grad_scale_multi")
+
+
+class ShadowTable:
+    """bf16 (and transposed bf16) shadows of a list of 2-D master tensors, refreshed in one launch."""
+
+    def __init__(self, masters: list[torch.Tensor], device, transposed: bool = True):
+        self.device = torch.device(device)
+        self.masters = masters
+        total = sum(m.numel() for m in masters)
+        self.flat = torch.empty((total,), dtype=torch.bfloat16, device=self.device)
+        self.flat_t = torch.empty((total,), dtype=torch.bfloat16, device=self.device) if transposed else None
+        host = np.zeros(len(masters), dtype=_SHADOW_DTYPE)
+        self.views, self.views_t = [], []
+        off, tile = 0, 0
+        for i, m in enumerate(masters):
+            if m.dim() != 2 or not m.is_contiguous():
+                raise ValueError("ShadowTable masters must be contiguous 2-D tensors")
+            # keep every shadow 16-byte aligned (TMA base alignment): pad offsets to 8 elements
+            r, c = m.shape
+            v = self.flat[off:off + r * c].view(r, c)
+            vt = self.flat_t[off:off + r * c].view(c, r) if transposed else None
+            self.views.append(v)
+            self.views_t.append(vt)
+            host[i]["dst"] = v.data_ptr()
+            host[i]["dst_t"] = vt.data_ptr() if vt is not None else 0
+            host[i]["rows"], host[i]["cols"] = r, c
+            host[i]["src_dtype"] = N.dtype_code(m.dtype)
+            host[i]["tile_base"] = tile
+            tile += ((r + 31) // 32) * ((c + 31) // 32)
+            off += r * c
+            if (r * c) % 8:
+                raise NotImplementedError("ShadowTable: tensor sizes must be multiples of 8 elements")
+        self.n_tiles = tile
+        self.host = host
+        self.dev = torch.empty((max(len(masters), 1) * _SHADOW_DTYPE.itemsize,), dtype=torch.uint8, device=self.device)
+        self.sync_pointers()
+
+    def sync_pointers(self) -> None:
+        for i, m in enumerate(self.masters):
+            self.host[i]["src"] = m.data_ptr()
+            self.host[i]["src_dtype"] = N.dtype_code(m.dtype)
+        raw = self.host.view(np.uint8).reshape(-1)
+        self.dev[: raw.size].copy_(torch.from_numpy(raw.copy()))
+        self._ptrs = [m.data_ptr() for m in self.masters]
+
+    def refresh(self) -> None:
+        if any(m.data_ptr() != p for m, p in zip(self.masters, self._ptrs)):
+            self.sync_pointers()
+        N.check(N.lib().otb_shadow_refresh_multi(self.dev.data_ptr(), len(self.masters), self.n_tiles, _stream()),
+                "otb_shadow_refresh_multi")
+
+
+def philox_dump(seed: int, offset: int, stream_id: int, first_group: int, n_groups: int, device) -> torch.Tensor:
+    out = torch.empty((n_groups, 4), dtype=torch.int32, device=device)
+    N.check(N.lib().otb_philox_dump(seed, offset, stream_id, first_group, n_groups, out.data_ptr(), _stream()),
+            "otb_philox_dump")
+    return out
