@@ -39,63 +39,106 @@ __device__ __forceinline__ float rnd(float x) {
     if (BF16) return round_bf16(x);
     return x;
 }
-
-// One element of the reference update.  All arithmetic through explicit _rn intrinsics so
-// nvcc cannot contract; FMA is used only where the flavour says torch's kernel does.
+// round two values at once: one F2FP.BF16.PACK_AB instead of two scalar conversions
 template <bool BF16>
-__device__ __forceinline__ void adam_elem(const OptScalars& s, float& p, float g, float& m, float& v,
-                                          float& e, uint32_t rnd16, bool has_ema) {
-    if (s.maximize) g = -g;
-    if (s.has_clip) g = rnd<BF16>(__fmul_rn(g, s.clip));            // grads.mul_(clip_coef)
-    if (s.l2 != 0.0f) {                                              // Adam: grad.add(p, alpha=wd)
-        g = (s.flavor & OTB_FLAVOR_FMA_ADD_ALPHA) ? rnd<BF16>(__fmaf_rn(s.l2, p, g))
-                                                  : rnd<BF16>(__fadd_rn(g, __fmul_rn(s.l2, p)));
-    } else {
-        p = rnd<BF16>(__fmul_rn(p, s.decay_mul));                    // p.mul_(1 - lr*wd)
+__device__ __forceinline__ void rnd2(float& a, float& b) {
+    if (BF16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        uint32_t u = *reinterpret_cast<uint32_t*>(&h);
+        a = __uint_as_float(u << 16);
+        b = __uint_as_float(u & 0xFFFF0000u);
+    }
+}
+
+// Two elements of the reference update.  All arithmetic through explicit _rn intrinsics so
+// nvcc cannot contract; FMA is used only where the flavour says torch's kernel does.
+// FL is the compile-time flavour when >= 0 (the hot instantiation is OTB_FLAVOR_TORCH_CUDA),
+// or -1 to read the run-time bits.
+template <bool BF16, int FL>
+__device__ __forceinline__ void adam_pair(const OptScalars& s, float (&p)[2], float (&g)[2], float (&m)[2],
+                                          float (&v)[2], float (&e)[2], const uint32_t (&rnd16)[2], bool has_ema) {
+    const uint32_t fl = FL >= 0 ? (uint32_t)FL : s.flavor;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (s.maximize) g[k] = -g[k];
+        if (s.has_clip) g[k] = __fmul_rn(g[k], s.clip);                 // grads.mul_(clip_coef)
+    }
+    if (s.has_clip) rnd2<BF16>(g[0], g[1]);
+    if (s.l2 != 0.0f) {                                                 // Adam: grad.add(p, alpha=wd)
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            g[k] = (fl & OTB_FLAVOR_FMA_ADD_ALPHA) ? __fmaf_rn(s.l2, p[k], g[k]) : __fadd_rn(g[k], __fmul_rn(s.l2, p[k]));
+        rnd2<BF16>(g[0], g[1]);
+    } else {                                                            // AdamW: p.mul_(1 - lr*wd)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) p[k] = __fmul_rn(p[k], s.decay_mul);
+        rnd2<BF16>(p[0], p[1]);
     }
     // exp_avg.lerp_(grad, 1-beta1)
-    {
-        float d = __fsub_rn(g, m);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        float d = __fsub_rn(g[k], m[k]);
         if (s.lerp_w < 0.5f) {
-            m = (s.flavor & OTB_FLAVOR_FMA_LERP) ? __fmaf_rn(s.lerp_w, d, m) : __fadd_rn(m, __fmul_rn(s.lerp_w, d));
+            m[k] = (fl & OTB_FLAVOR_FMA_LERP) ? __fmaf_rn(s.lerp_w, d, m[k]) : __fadd_rn(m[k], __fmul_rn(s.lerp_w, d));
         } else {
             float w1 = __fsub_rn(1.0f, s.lerp_w);
-            m = (s.flavor & OTB_FLAVOR_FMA_LERP) ? __fmaf_rn(-w1, d, g) : __fsub_rn(g, __fmul_rn(d, w1));
+            m[k] = (fl & OTB_FLAVOR_FMA_LERP) ? __fmaf_rn(-w1, d, g[k]) : __fsub_rn(g[k], __fmul_rn(d, w1));
         }
-        m = rnd<BF16>(m);
     }
+    rnd2<BF16>(m[0], m[1]);
     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
-    v = rnd<BF16>(__fmul_rn(v, s.beta2));
-    {
-        float t = __fmul_rn(s.omb2, g);
-        v = (s.flavor & OTB_FLAVOR_FMA_ADDCMUL) ? __fmaf_rn(t, g, v) : __fadd_rn(v, __fmul_rn(t, g));
-        v = rnd<BF16>(v);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) v[k] = __fmul_rn(v[k], s.beta2);
+    rnd2<BF16>(v[0], v[1]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        float x, y;
+        if (fl & OTB_FLAVOR_ADDCMUL_SQUARE_FIRST) { x = s.omb2; y = __fmul_rn(g[k], g[k]); }
+        else { x = __fmul_rn(s.omb2, g[k]); y = g[k]; }
+        v[k] = (fl & OTB_FLAVOR_FMA_ADDCMUL) ? __fmaf_rn(x, y, v[k]) : __fadd_rn(v[k], __fmul_rn(x, y));
     }
+    rnd2<BF16>(v[0], v[1]);
     // denom = (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
-    float d = rnd<BF16>(__fsqrt_rn(v));
-    d = (s.flavor & OTB_FLAVOR_DIV_RECIPROCAL) ? __fmul_rn(d, s.inv_bc2) : __fdiv_rn(d, s.bc2);
-    d = rnd<BF16>(d);
-    d = rnd<BF16>(__fadd_rn(d, s.eps));
+    float d[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) d[k] = __fsqrt_rn(v[k]);
+    rnd2<BF16>(d[0], d[1]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) d[k] = (fl & OTB_FLAVOR_DIV_RECIPROCAL) ? __fmul_rn(d[k], s.inv_bc2) : __fdiv_rn(d[k], s.bc2);
+    rnd2<BF16>(d[0], d[1]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) d[k] = __fadd_rn(d[k], s.eps);
+    rnd2<BF16>(d[0], d[1]);
     // p.addcdiv_(exp_avg, denom, value=-step_size)   [fp32 math; SR or RN write-back]
-    float r;
-    if (s.flavor & OTB_FLAVOR_ADDCDIV_MUL_LAST) {
-        float q = __fdiv_rn(m, d);
-        r = (s.flavor & OTB_FLAVOR_FMA_ADDCDIV) ? __fmaf_rn(s.nss, q, p) : __fadd_rn(p, __fmul_rn(s.nss, q));
-    } else {
-        float q = __fdiv_rn(__fmul_rn(s.nss, m), d);
-        r = __fadd_rn(p, q);
+    float r[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (fl & OTB_FLAVOR_ADDCDIV_MUL_LAST) {
+            float q = __fdiv_rn(m[k], d[k]);
+            r[k] = (fl & OTB_FLAVOR_FMA_ADDCDIV) ? __fmaf_rn(s.nss, q, p[k]) : __fadd_rn(p[k], __fmul_rn(s.nss, q));
+        } else {
+            r[k] = __fadd_rn(p[k], __fdiv_rn(__fmul_rn(s.nss, m[k]), d[k]));
+        }
     }
     if (BF16 && s.sr) {
-        uint32_t bits = __float_as_uint(r) + rnd16;                  // copy_stochastic_
-        bits &= 0xFFFF0000u;
-        p = __uint_as_float(bits);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)                                      // copy_stochastic_
+            p[k] = __uint_as_float((__float_as_uint(r[k]) + rnd16[k]) & 0xFFFF0000u);
     } else {
-        p = rnd<BF16>(r);
+        p[0] = r[0]; p[1] = r[1];
+        rnd2<BF16>(p[0], p[1]);
     }
-    if (has_ema) {                                                   // ema.add_(omd * (p - ema))
-        float t1 = rnd<BF16>(__fsub_rn(p, e));
-        float t2 = rnd<BF16>(__fmul_rn(t1, s.ema_omd));
-        e = rnd<BF16>(__fadd_rn(e, t2));
+    if (has_ema) {                                                      // ema.add_(omd * (p - ema))
+        float t[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) t[k] = __fsub_rn(p[k], e[k]);
+        rnd2<BF16>(t[0], t[1]);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) t[k] = __fmul_rn(t[k], s.ema_omd);
+        rnd2<BF16>(t[0], t[1]);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) e[k] = __fadd_rn(e[k], t[k]);
+        rnd2<BF16>(e[0], e[1]);
     }
 }
 
@@ -139,9 +182,9 @@ __device__ __forceinline__ uint32_t sr_bits(const Philox4& r, int lane) {
     return (lane & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
-template <bool BF16>
-__device__ void adam_chunk(const otb_optim_tensor& t, const OptScalars& s, int64_t start, int64_t end,
-                           uint64_t seed, uint64_t offset) {
+template <bool BF16, int FL>
+__device__ __forceinline__ void adam_chunk(const otb_optim_tensor& t, const OptScalars& s, int64_t start, int64_t end,
+                                           uint64_t seed, uint64_t offset) {
     const bool has_ema = s.do_ema && t.ema != nullptr;
     const bool aligned = (t.flags & OPT_FLAG_ALIGNED16) != 0;
     int64_t vec_end = aligned ? start + ((end - start) & ~int64_t(7)) : start;
@@ -155,8 +198,16 @@ __device__ void adam_chunk(const otb_optim_tensor& t, const OptScalars& s, int64
         if (has_ema) Pack8<BF16>::load(t.ema, i, e, false);
         Philox4 r{0, 0, 0, 0};
         if (BF16 && s.sr) r = otb_rng(seed, offset, OTB_STREAM_SR, (uint64_t)(t.rng_base + i) >> 3);
+        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) adam_elem<BF16>(s, p[k], g[k], m[k], v[k], e[k], sr_bits(r, k), has_ema);
+        for (int k = 0; k < 4; ++k) {
+            float pp[2] = {p[2 * k], p[2 * k + 1]}, gg[2] = {g[2 * k], g[2 * k + 1]}, mm[2] = {m[2 * k], m[2 * k + 1]};
+            float vv[2] = {v[2 * k], v[2 * k + 1]}, ee[2] = {e[2 * k], e[2 * k + 1]};
+            const uint32_t r16[2] = {rw[k] & 0xFFFFu, rw[k] >> 16};
+            adam_pair<BF16, FL>(s, pp, gg, mm, vv, ee, r16, has_ema);
+            p[2 * k] = pp[0]; p[2 * k + 1] = pp[1]; m[2 * k] = mm[0]; m[2 * k + 1] = mm[1];
+            v[2 * k] = vv[0]; v[2 * k + 1] = vv[1]; e[2 * k] = ee[0]; e[2 * k + 1] = ee[1];
+        }
         Pack8<BF16>::store(t.p, i, p);
         Pack8<BF16>::store(t.exp_avg, i, m);
         Pack8<BF16>::store(t.exp_avg_sq, i, v);
@@ -171,24 +222,24 @@ __device__ void adam_chunk(const otb_optim_tensor& t, const OptScalars& s, int64
     // scalar tail (and the whole chunk for unaligned tensors)
     const int dt = BF16 ? OTB_BF16 : OTB_F32;
     for (int64_t i = vec_end + threadIdx.x; i < end; i += OPT_THREADS) {
-        float p = load_as_float(t.p, i, dt), g = load_as_float(t.g, i, dt);
-        float m = load_as_float(t.exp_avg, i, dt), v = load_as_float(t.exp_avg_sq, i, dt);
-        float e = has_ema ? load_as_float(t.ema, i, dt) : 0.0f;
-        uint32_t r16 = 0;
+        float p[2] = {load_as_float(t.p, i, dt), 0.0f}, g[2] = {load_as_float(t.g, i, dt), 0.0f};
+        float m[2] = {load_as_float(t.exp_avg, i, dt), 0.0f}, v[2] = {load_as_float(t.exp_avg_sq, i, dt), 1.0f};
+        float e[2] = {has_ema ? load_as_float(t.ema, i, dt) : 0.0f, 0.0f};
+        uint32_t r16[2] = {0, 0};
         if (BF16 && s.sr) {
             uint64_t ge = (uint64_t)(t.rng_base + i);
-            r16 = sr_bits(otb_rng(seed, offset, OTB_STREAM_SR, ge >> 3), (int)(ge & 7));
+            r16[0] = sr_bits(otb_rng(seed, offset, OTB_STREAM_SR, ge >> 3), (int)(ge & 7));
         }
-        adam_elem<BF16>(s, p, g, m, v, e, r16, has_ema);
-        store_from_float(t.p, i, dt, p);
-        store_from_float(t.exp_avg, i, dt, m);
-        store_from_float(t.exp_avg_sq, i, dt, v);
-        if (has_ema) store_from_float(t.ema, i, dt, e);
-        if (t.shadow_bf16) ((uint16_t*)t.shadow_bf16)[i] = float_to_bf16_bits_rn(p);
+        adam_pair<BF16, FL>(s, p, g, m, v, e, r16, has_ema);
+        store_from_float(t.p, i, dt, p[0]);
+        store_from_float(t.exp_avg, i, dt, m[0]);
+        store_from_float(t.exp_avg_sq, i, dt, v[0]);
+        if (has_ema) store_from_float(t.ema, i, dt, e[0]);
+        if (t.shadow_bf16) ((uint16_t*)t.shadow_bf16)[i] = float_to_bf16_bits_rn(p[0]);
     }
 }
 
-__global__ void __launch_bounds__(OPT_THREADS) adamw_sr_ema_kernel(otb_optim_launch a) {
+__global__ void __launch_bounds__(OPT_THREADS, 3) adamw_sr_ema_kernel(otb_optim_launch a) {
     const int chunk = blockIdx.x;
     const otb_optim_tensor t = a.tensors[a.chunk_tensor[chunk]];
     const int64_t start = (int64_t)a.chunk_index[chunk] * a.chunk_elems;
@@ -204,8 +255,14 @@ __global__ void __launch_bounds__(OPT_THREADS) adamw_sr_ema_kernel(otb_optim_lau
     s.sr = (t.flags & OPT_FLAG_SR) != 0;
     s.maximize = (t.flags & OPT_FLAG_MAXIMIZE) != 0;
     s.do_ema = a.do_ema != 0;
-    if (t.p_dtype == OTB_BF16) adam_chunk<true>(t, s, start, end, a.seed, a.offset);
-    else adam_chunk<false>(t, s, start, end, a.seed, a.offset);
+    const bool hot = a.flavor == OTB_FLAVOR_TORCH_CUDA;      // block-uniform
+    if (t.p_dtype == OTB_BF16) {
+        if (hot) adam_chunk<true, (int)OTB_FLAVOR_TORCH_CUDA>(t, s, start, end, a.seed, a.offset);
+        else adam_chunk<true, -1>(t, s, start, end, a.seed, a.offset);
+    } else {
+        if (hot) adam_chunk<false, (int)OTB_FLAVOR_TORCH_CUDA>(t, s, start, end, a.seed, a.offset);
+        else adam_chunk<false, -1>(t, s, start, end, a.seed, a.offset);
+    }
 }
 
 // ------------------------------- EMA only -------------------------------------------
