@@ -139,9 +139,10 @@ int otb_ema_multi(const otb_optim_launch* args, void* stream);
  * Global gradient norm + clip coefficient.
  * Replaces nn.utils.clip_grad_norm_(parameters, max_norm)  GenericTrainer.py:712-713
  *   total_norm = ||g||_2 over all tensors; coef = min(1, max_norm / (total_norm + 1e-6)).
- * partials: device float[n_chunks] workspace; out: device float[2] = {total_norm, coef}.
+ * partials: device float[n_chunks] workspace; out: device float[2] = {total_norm, coef * grad_prescale}.
  * Deterministic (fixed-order two-level reduction).  grad_prescale multiplies g before
- * the norm (1/world_size under data parallel when the allreduce summed).
+ * the norm (1/world_size under data parallel when the allreduce summed) and is folded into
+ * the returned scale factor, so one multiply both averages and clips.
  * ---------------------------------------------------------------------------------- */
 int otb_grad_norm_multi(const otb_optim_launch* args, float max_norm, float grad_prescale,
                         float* partials, float* out_norm_coef, void* stream);

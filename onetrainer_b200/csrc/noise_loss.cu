@@ -15,6 +15,8 @@
 #include "common.cuh"
 
 #define NL_THREADS 256
+#define NB1_UNROLL 2   /* groups of 4 elements per thread per iteration, K-b1 */
+#define NB2_UNROLL 4   /* K-b2 */
 
 namespace {
 
@@ -128,59 +130,74 @@ __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_ar
 
     if ((chw & 3) == 0) {
         const int64_t ngroups = chw >> 2;
-        for (int64_t gi = (int64_t)blockIdx.x * NL_THREADS + threadIdx.x; gi < ngroups; gi += (int64_t)gridDim.x * NL_THREADS) {
-            const int64_t i = gi << 2;
-            float n[4] = {0, 0, 0, 0};
-            if (a.generate_noise) {
-                const uint64_t ge = (uint64_t)(gs * chw + i);
-                normal4(a, OTB_STREAM_NOISE, ge >> 2, n);
+        constexpr int U = NB1_UNROLL;
+        for (int64_t g0 = (int64_t)blockIdx.x * (NL_THREADS * U) + threadIdx.x; g0 < ngroups; g0 += (int64_t)gridDim.x * (NL_THREADS * U)) {
+            float x[U][4], n[U][4];
+            bool live[U];
+            // all global loads of the iteration are issued before any math (memory-level parallelism)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) n[k] = rnd_dt(n[k], ldt);
-                if (a.offset_noise_weight > 0.0f) {
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = (g0 + (int64_t)u * NL_THREADS) << 2;
+                live[u] = i < chw;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        int c = (int)((i + k) / a.hw);
-                        float on = rnd_dt(normal1(a, OTB_STREAM_OFFSET, (uint64_t)(gs * a.C + c)), ldt);
-                        n[k] = rnd_dt(__fadd_rn(n[k], rnd_dt(__fmul_rn(a.offset_noise_weight, on), ldt)), ldt);
+                for (int k = 0; k < 4; ++k) { x[u][k] = 0.0f; n[u][k] = 0.0f; }
+                if (live[u]) {
+                    if (a.latent) load4(a.latent, base + i, ldt, x[u]);
+                    if (!a.generate_noise && a.noise_in) load4(a.noise_in, base + i, ldt, n[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!live[u]) continue;
+                const int64_t i = (g0 + (int64_t)u * NL_THREADS) << 2;
+                if (a.generate_noise) {
+                    const uint64_t ge = (uint64_t)(gs * chw + i);
+                    normal4(a, OTB_STREAM_NOISE, ge >> 2, n[u]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) n[u][k] = rnd_dt(n[u][k], ldt);
+                    if (a.offset_noise_weight > 0.0f) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            int c = (int)((uint32_t)(i + k) / (uint32_t)a.hw);
+                            float on = rnd_dt(normal1(a, OTB_STREAM_OFFSET, (uint64_t)(gs * a.C + c)), ldt);
+                            n[u][k] = rnd_dt(__fadd_rn(n[u][k], rnd_dt(__fmul_rn(a.offset_noise_weight, on), ldt)), ldt);
+                        }
+                    }
+                    if (a.perturbation_noise_weight > 0.0f) {
+                        float pn[4];
+                        normal4(a, OTB_STREAM_PERTURB, ge >> 2, pn);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            n[u][k] = rnd_dt(__fadd_rn(n[u][k], rnd_dt(__fmul_rn(a.perturbation_noise_weight, rnd_dt(pn[k], ldt)), ldt)), ldt);
                     }
                 }
-                if (a.perturbation_noise_weight > 0.0f) {
-                    float pn[4];
-                    normal4(a, OTB_STREAM_PERTURB, ge >> 2, pn);
+                if (a.noise_out && need_noise) store4(a.noise_out, base + i, ldt, n[u]);
+                if (!a.latent) continue;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        n[k] = rnd_dt(__fadd_rn(n[k], rnd_dt(__fmul_rn(a.perturbation_noise_weight, rnd_dt(pn[k], ldt)), ldt)), ldt);
+                for (int k = 0; k < 4; ++k)
+                    x[u][k] = rnd_dt(__fmul_rn(rnd_dt(__fsub_rn(x[u][k], a.latent_shift), ldt), a.latent_scale), ldt);
+                if (a.x0_out) store4(a.x0_out, base + i, ldt, x[u]);
+                if (add) {
+                    float y[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) y[k] = __fadd_rn(__fmul_rn(x[u][k], cx), __fmul_rn(n[u][k], cn));
+                    if (a.noisy_out) store4(a.noisy_out, base + i, ldt, y);
+                    if (a.noisy_cast_out) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) y[k] = rnd_dt(y[k], ldt);
+                        store4(a.noisy_cast_out, base + i, a.cast_dtype, y);
+                    }
                 }
-            } else if (a.noise_in) {
-                load4(a.noise_in, base + i, ldt, n);
-            }
-            if (a.noise_out && need_noise) store4(a.noise_out, base + i, ldt, n);
-            if (!a.latent) continue;
-            float x[4];
-            load4(a.latent, base + i, ldt, x);
+                if (a.target_out && a.target != OTB_TARGET_NONE) {
+                    float tg[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) x[k] = rnd_dt(__fmul_rn(rnd_dt(__fsub_rn(x[k], a.latent_shift), ldt), a.latent_scale), ldt);
-            if (a.x0_out) store4(a.x0_out, base + i, ldt, x);
-            if (add) {
-                float y[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) y[k] = __fadd_rn(__fmul_rn(x[k], cx), __fmul_rn(n[k], cn));
-                if (a.noisy_out) store4(a.noisy_out, base + i, ldt, y);
-                if (a.noisy_cast_out) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) y[k] = rnd_dt(y[k], ldt);
-                    store4(a.noisy_cast_out, base + i, a.cast_dtype, y);
+                    for (int k = 0; k < 4; ++k) {
+                        if (a.target == OTB_TARGET_EPSILON) tg[k] = n[u][k];
+                        else if (a.target == OTB_TARGET_V) tg[k] = __fsub_rn(__fmul_rn(cx, n[u][k]), __fmul_rn(cn, x[u][k]));
+                        else tg[k] = __fsub_rn(n[u][k], x[u][k]);
+                    }
+                    store4(a.target_out, base + i, ldt, tg);
                 }
-            }
-            if (a.target_out && a.target != OTB_TARGET_NONE) {
-                float tg[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (a.target == OTB_TARGET_EPSILON) tg[k] = n[k];
-                    else if (a.target == OTB_TARGET_V) tg[k] = __fsub_rn(__fmul_rn(cx, n[k]), __fmul_rn(cn, x[k]));
-                    else tg[k] = __fsub_rn(n[k], x[k]);
-                }
-                store4(a.target_out, base + i, ldt, tg);
             }
         }
     } else {
@@ -306,48 +323,62 @@ __global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args 
     float acc = 0.0f;
     if ((chw & 3) == 0 && (a.hw & 3) == 0) {
         const int64_t ngroups = chw >> 2;
-        for (int64_t gi = (int64_t)blockIdx.x * NL_THREADS + threadIdx.x; gi < ngroups; gi += (int64_t)gridDim.x * NL_THREADS) {
-            const int64_t i = gi << 2;
-            float p[4], t[4], pt[4] = {0, 0, 0, 0}, m[4] = {1, 1, 1, 1}, g[4];
-            load4(a.predicted, base + i, a.pred_dtype, p);
-            load4(a.target, base + i, a.target_dtype, t);
-            if (prior) load4(a.prior_target, base + i, a.target_dtype, pt);
-            if (masked) {
-                const int64_t mi = (int64_t)b * a.hw + (i % a.hw);
-                if (a.mask_dtype == OTB_F32) {   // mask is re-read C times: keep it cacheable
-                    float4 mv = *reinterpret_cast<const float4*>((const float*)a.mask + mi);
-                    m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
-                } else {
+        constexpr int U = NB2_UNROLL;
+        for (int64_t g0 = (int64_t)blockIdx.x * (NL_THREADS * U) + threadIdx.x; g0 < ngroups; g0 += (int64_t)gridDim.x * (NL_THREADS * U)) {
+            float p[U][4], t[U][4], pt[U][4], m[U][4];
+            bool live[U];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) m[k] = load_as_float(a.mask, mi + k, a.mask_dtype);
-                }
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = (g0 + (int64_t)u * NL_THREADS) << 2;
+                live[u] = i < chw;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) m[k] = fminf(fmaxf(m[k], a.unmasked_weight), 1.0f);
-            }
+                for (int k = 0; k < 4; ++k) { p[u][k] = 0.0f; t[u][k] = 0.0f; pt[u][k] = 0.0f; m[u][k] = 1.0f; }
+                if (!live[u]) continue;
+                load4(a.predicted, base + i, a.pred_dtype, p[u]);
+                load4(a.target, base + i, a.target_dtype, t[u]);
+                if (prior) load4(a.prior_target, base + i, a.target_dtype, pt[u]);
+                if (masked) {
+                    const int64_t mi = (int64_t)b * a.hw + (int64_t)((uint32_t)i % (uint32_t)a.hw);
+                    if (a.mask_dtype == OTB_F32) {   // mask is re-read C times: keep it cacheable
+                        float4 mv = *reinterpret_cast<const float4*>((const float*)a.mask + mi);
+                        m[u][0] = mv.x; m[u][1] = mv.y; m[u][2] = mv.z; m[u][3] = mv.w;
+                    } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float d = __fsub_rn(p[k], t[k]);
-                const float wm = m[k] * k_main;
-                float term = a.mse_strength * (d * d) * wm;
-                float gr = a.mse_strength * 2.0f * d * wm;
-                if (a.mae_strength != 0.0f) {
-                    term += a.mae_strength * fabsf(d) * wm;
-                    gr += a.mae_strength * (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * wm;
-                }
-                if (prior) {
-                    const float dp = __fsub_rn(p[k], pt[k]);
-                    const float wp = __fsub_rn(1.0f, m[k]) * k_prior;
-                    term += a.mse_strength * (dp * dp) * wp;
-                    gr += a.mse_strength * 2.0f * dp * wp;
-                    if (a.mae_strength != 0.0f) {
-                        term += a.mae_strength * fabsf(dp) * wp;
-                        gr += a.mae_strength * (dp > 0.0f ? 1.0f : (dp < 0.0f ? -1.0f : 0.0f)) * wp;
+                        for (int k = 0; k < 4; ++k) m[u][k] = load_as_float(a.mask, mi + k, a.mask_dtype);
                     }
                 }
-                acc += term;
-                g[k] = gr * gfac;
             }
-            if (want_grad) store4(a.dpred, base + i, a.pred_dtype, g);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!live[u]) continue;
+                const int64_t i = (g0 + (int64_t)u * NL_THREADS) << 2;
+                float g[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float mk = masked ? fminf(fmaxf(m[u][k], a.unmasked_weight), 1.0f) : 1.0f;
+                    const float d = __fsub_rn(p[u][k], t[u][k]);
+                    const float wm = mk * k_main;
+                    float term = a.mse_strength * (d * d) * wm;
+                    float gr = a.mse_strength * 2.0f * d * wm;
+                    if (a.mae_strength != 0.0f) {
+                        term += a.mae_strength * fabsf(d) * wm;
+                        gr += a.mae_strength * (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * wm;
+                    }
+                    if (prior) {
+                        const float dp = __fsub_rn(p[u][k], pt[u][k]);
+                        const float wp = __fsub_rn(1.0f, mk) * k_prior;
+                        term += a.mse_strength * (dp * dp) * wp;
+                        gr += a.mse_strength * 2.0f * dp * wp;
+                        if (a.mae_strength != 0.0f) {
+                            term += a.mae_strength * fabsf(dp) * wp;
+                            gr += a.mae_strength * (dp > 0.0f ? 1.0f : (dp < 0.0f ? -1.0f : 0.0f)) * wp;
+                        }
+                    }
+                    acc += term;
+                    g[k] = gr * gfac;
+                }
+                if (want_grad) store4(a.dpred, base + i, a.pred_dtype, g);
+            }
         }
     } else {
         for (int64_t i = (int64_t)blockIdx.x * NL_THREADS + threadIdx.x; i < chw; i += (int64_t)gridDim.x * NL_THREADS) {
@@ -410,10 +441,10 @@ __global__ void __launch_bounds__(NL_THREADS) loss_bwd_rescale_kernel(void* dpre
         store_from_float(dpred, base + i, dtype, load_as_float(dpred, base + i, dtype) * ratio);
 }
 
-int blocks_per_sample_for(int64_t chw, int B) {
-    // 4 elements per thread per iteration; aim at >= 4 waves of 148 SMs x 8 resident blocks when the
-    // problem is large, never more blocks than there are 1024-element slabs.
-    int64_t slabs = (chw / 4 + NL_THREADS - 1) / NL_THREADS;
+int blocks_per_sample_for(int64_t chw, int B, int unroll) {
+    // 4*unroll elements per thread per iteration; aim at >= 4 waves of 148 SMs x 8 resident blocks when
+    // the problem is large, never more blocks than there are slabs of one block-iteration.
+    int64_t slabs = (chw / 4 + NL_THREADS * unroll - 1) / (NL_THREADS * unroll);
     if (slabs < 1) slabs = 1;
     int64_t want = (int64_t)otb_sm_count() * 8 * 4 / (B > 0 ? B : 1);
     if (want < 1) want = 1;
@@ -426,7 +457,7 @@ int blocks_per_sample_for(int64_t chw, int B) {
 
 extern "C" int otb_noise_addnoise(const otb_noise_args* a, void* stream) {
     OTB_CHECK_ARG(a != nullptr, "null args");
-    OTB_CHECK_ARG(a->B > 0 && a->C > 0 && a->hw > 0, "bad shape B=%d C=%d hw=%d", a->B, a->C, a->hw);
+    OTB_CHECK_ARG(a->B > 0 && a->C > 0 && a->hw > 0 && (int64_t)a->C * a->hw < (1ll << 31), "bad shape B=%d C=%d hw=%d", a->B, a->C, a->hw);
     OTB_CHECK_ARG(a->B <= 65535, "batch %d too large for one launch", a->B);
     OTB_CHECK_ARG(a->latent_dtype >= OTB_F32 && a->latent_dtype <= OTB_F16, "bad latent dtype");
     OTB_CHECK_ARG(a->ts_mode >= OTB_TS_UNIFORM && a->ts_mode <= OTB_TS_GIVEN, "bad timestep mode %d", a->ts_mode);
@@ -442,7 +473,7 @@ extern "C" int otb_noise_addnoise(const otb_noise_args* a, void* stream) {
         OTB_CHECK_ARG(a->max_timestep >= a->min_timestep && a->min_timestep >= 0 && a->max_timestep <= a->num_train_timesteps,
                       "bad timestep range [%d,%d)", a->min_timestep, a->max_timestep);
     const int64_t chw = (int64_t)a->C * a->hw;
-    dim3 grid(blocks_per_sample_for(chw, a->B), a->B);
+    dim3 grid(blocks_per_sample_for(chw, a->B, NB1_UNROLL), a->B);
     noise_addnoise_kernel<<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
     OTB_LAUNCH_CHECK("noise_addnoise_kernel");
     return OTB_OK;
@@ -450,7 +481,7 @@ extern "C" int otb_noise_addnoise(const otb_noise_args* a, void* stream) {
 
 extern "C" int otb_loss_fwd_bwd(const otb_loss_args* a, void* stream) {
     OTB_CHECK_ARG(a != nullptr, "null args");
-    OTB_CHECK_ARG(a->B > 0 && a->C > 0 && a->hw > 0 && a->B <= 65535, "bad shape B=%d C=%d hw=%d", a->B, a->C, a->hw);
+    OTB_CHECK_ARG(a->B > 0 && a->C > 0 && a->hw > 0 && a->B <= 65535 && (int64_t)a->C * a->hw < (1ll << 31), "bad shape B=%d C=%d hw=%d", a->B, a->C, a->hw);
     OTB_CHECK_ARG(a->predicted && a->target && a->losses && a->partials && a->counters, "null tensor");
     OTB_CHECK_ARG(a->blocks_per_sample > 0 && a->blocks_per_sample <= 65535, "bad blocks_per_sample");
     OTB_CHECK_ARG(!(a->masked && !a->mask), "masked loss needs a mask");
@@ -468,13 +499,13 @@ extern "C" int otb_loss_fwd_bwd(const otb_loss_args* a, void* stream) {
 }
 
 extern "C" int otb_loss_blocks_per_sample(int32_t B, int32_t C, int32_t hw) {
-    return blocks_per_sample_for((int64_t)C * hw, B);
+    return blocks_per_sample_for((int64_t)C * hw, B, NB2_UNROLL);
 }
 
 extern "C" int otb_loss_bwd_rescale(void* dpred, int32_t dtype, const float* grad_out, float assumed,
                                     int32_t B, int64_t chw, void* stream) {
     OTB_CHECK_ARG(dpred && grad_out && B > 0 && chw > 0 && assumed != 0.0f, "bad rescale args");
-    dim3 grid(blocks_per_sample_for(chw, B), B);
+    dim3 grid(blocks_per_sample_for(chw, B, 1), B);
     loss_bwd_rescale_kernel<<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(dpred, dtype, grad_out, assumed, chw);
     OTB_LAUNCH_CHECK("loss_bwd_rescale_kernel");
     return OTB_OK;

@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(OPT_THREADS) grad_sqnorm_kernel(otb_optim_laun
 }
 
 // fixed-order final reduction: thread i sums partials[i], [i+1024], ... then a tree
-__global__ void __launch_bounds__(1024) grad_norm_finish_kernel(const float* partials, int n, float max_norm, float* out) {
+__global__ void __launch_bounds__(1024) grad_norm_finish_kernel(const float* partials, int n, float max_norm, float prescale, float* out) {
     __shared__ double sm[1024];
     double acc = 0.0;
     for (int i = threadIdx.x; i < n; i += 1024) acc += (double)partials[i];
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(1024) grad_norm_finish_kernel(const float* par
         float total = sqrtf((float)sm[0]);
         float coef = max_norm / (total + 1e-6f);          // torch: clip_coef = max_norm / (total_norm + 1e-6)
         out[0] = total;
-        out[1] = coef < 1.0f ? coef : 1.0f;               // clamp(max=1.0)
+        out[1] = (coef < 1.0f ? coef : 1.0f) * prescale;  // clamp(max=1.0); the 1/world_size average rides along
     }
 }
 
@@ -467,7 +467,7 @@ extern "C" int otb_grad_norm_multi(const otb_optim_launch* a, float max_norm, fl
         grad_sqnorm_kernel<<<a->n_chunks, OPT_THREADS, 0, (cudaStream_t)stream>>>(*a, grad_prescale, partials);
         OTB_LAUNCH_CHECK("grad_sqnorm_kernel");
     }
-    grad_norm_finish_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, c == 0 ? a->n_chunks : 0, max_norm, out);
+    grad_norm_finish_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, c == 0 ? a->n_chunks : 0, max_norm, grad_prescale, out);
     OTB_LAUNCH_CHECK("grad_norm_finish_kernel");
     return OTB_OK;
 }

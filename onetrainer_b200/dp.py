@@ -1,0 +1,105 @@
+"""Data parallelism for the hot path — net-new: the reference is single-process, single-device
+(/root/reference/modules/trainer/BaseTrainer.py:33-34 builds exactly one train_device).
+
+One process per GPU (torchrun / torch.distributed.run), NCCL over NVLink 5 / NVSwitch on GPUs,
+gloo on CPU for the host-logic tests.  The path shards by batch with exactly ONE exchange step
+(SURVEY.md §8e): rank k owns global samples [k*b, (k+1)*b); everything before the optimizer is
+per-sample; gradients of the trainable tensors are summed across ranks and averaged (1/n is folded
+into the grad-norm / optimizer kernels as `grad_prescale`, so no extra pass over the gradients).
+
+RNG: the reference seeds a fresh generator with `global_step` on every rank
+(BaseStableDiffusionXLSetup.py:189-191); naive replication would draw identical noise everywhere.
+Here every draw is keyed by the GLOBAL sample index, so an N-GPU run at per-GPU batch b draws
+bit-for-bit what a 1-GPU run at batch N*b draws.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def is_initialized() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+def rank() -> int:
+    return dist.get_rank() if is_initialized() else 0
+
+
+def world_size() -> int:
+    return dist.get_world_size() if is_initialized() else 1
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
+    """Join the process group described by RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT.
+    Returns (rank, local_rank, world_size).  No-op for a single process."""
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rk = int(os.environ.get("RANK", "0"))
+    lr = int(os.environ.get("LOCAL_RANK", "0"))
+    if ws > 1 and not is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(lr)
+            dist.init_process_group(backend=backend, rank=rk, world_size=ws, device_id=torch.device("cuda", lr))
+        else:
+            dist.init_process_group(backend=backend, rank=rk, world_size=ws)
+    return rk, lr, ws
+
+
+def global_sample_base(local_batch_size: int) -> int:
+    """Global index of this rank's first sample: rank * b."""
+    return rank() * int(local_batch_size)
+
+
+class GradientBucket:
+    """Flat view of the trainable tensors' gradients for the one exchange step.
+
+    When the gradients already live in one arena (LoRAModuleWrapper's GradArena) the allreduce
+    runs in place on it; otherwise they are gathered into a flat buffer with one
+    torch._foreach_copy_ and scattered back.  The collective is a SUM; the 1/n average is applied
+    by the consumer (`grad_prescale`) — no extra read/write of the gradients.
+    """
+
+    def __init__(self, arena: torch.Tensor | None = None):
+        self.arena = arena
+        self._flat = None
+
+    def allreduce(self, grads: list[torch.Tensor]) -> float:
+        """Sum gradients over ranks in place.  Returns the prescale (1/world_size) to apply."""
+        n = world_size()
+        if n == 1:
+            return 1.0
+        if self.arena is not None and all(_is_view_of(g, self.arena) for g in grads):
+            dist.all_reduce(self.arena, op=dist.ReduceOp.SUM)
+            return 1.0 / n
+        total = sum(g.numel() for g in grads)
+        if self._flat is None or self._flat.numel() != total or self._flat.dtype != grads[0].dtype:
+            self._flat = torch.empty(total, dtype=grads[0].dtype, device=grads[0].device)
+        views, off = [], 0
+        for g in grads:
+            views.append(self._flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        torch._foreach_copy_(views, grads)
+        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+        torch._foreach_copy_(grads, views)
+        return 1.0 / n
+
+
+def _is_view_of(t: torch.Tensor, base: torch.Tensor) -> bool:
+    lo = base.data_ptr()
+    hi = lo + base.numel() * base.element_size()
+    return lo <= t.data_ptr() and t.data_ptr() + t.numel() * t.element_size() <= hi
+
+
+def average_scalar(x: torch.Tensor) -> torch.Tensor:
+    """Mean of a (device) scalar over ranks — used only for the logged loss."""
+    if world_size() == 1:
+        return x
+    y = x.clone()
+    dist.all_reduce(y, op=dist.ReduceOp.SUM)
+    return y / world_size()

@@ -1,0 +1,222 @@
+"""Stand-in networks with the reference's LoRA-relevant topology (HARNESS, not product).
+
+diffusers is not installed here and the wrapped UNet/DiT is out of scope by design
+(BASELINE.json north_star: the path OneTrainer owns itself, "as opposed to the diffusers UNet/DiT
+it wraps").  To exercise the path at the true shapes, these modules reproduce the *hooked leaves* of
+the real networks — same diffusers module names (so LoRAModuleWrapper's substring filter selects the
+same leaves: 192 for SD 1.5, 722 for SDXL), same (M, K, N) per leaf, same
+attention/GEGLU dataflow between them — with seeded random-init frozen weights.  ResNet blocks and
+down/up-sampling between the attention stages are replaced by frozen strided 2x2 / 1x1 convolutions:
+they are not hooked by the `attn-mlp` presets and are not part of the measured path.
+Hyper-parameters: /root/reference/resources/model_config/stable_diffusion_xl/sd_xl_base.yaml:19-37,
+/root/reference/resources/model_config/stable_diffusion/v1-inference.yaml:29-44.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim: int, ctx_dim: int | None, head_dim: int = 64):
+        super().__init__()
+        self.heads = dim // head_dim
+        self.to_q = nn.Linear(dim, dim, bias=False)
+        self.to_k = nn.Linear(ctx_dim or dim, dim, bias=False)
+        self.to_v = nn.Linear(ctx_dim or dim, dim, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
+
+    def forward(self, x, ctx=None):
+        ctx = x if ctx is None else ctx
+        B, L, D = x.shape
+        q = self.to_q(x).view(B, L, self.heads, -1).transpose(1, 2)
+        k = self.to_k(ctx).view(B, ctx.shape[1], self.heads, -1).transpose(1, 2)
+        v = self.to_v(ctx).view(B, ctx.shape[1], self.heads, -1).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, L, D)
+        return self.to_out[0](o)
+
+
+class _GEGLU(nn.Module):
+    def __init__(self, dim: int, inner: int):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner * 2)
+
+    def forward(self, x):
+        h, gate = self.proj(x).chunk(2, dim=-1)
+        return h * F.gelu(gate)
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.net = nn.ModuleList([_GEGLU(dim, dim * 4), nn.Dropout(0.0), nn.Linear(dim * 4, dim)])
+
+    def forward(self, x):
+        return self.net[2](self.net[0](x))
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim: int, ctx_dim: int):
+        super().__init__()
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+        self.attn1 = _Attention(dim, None)
+        self.attn2 = _Attention(dim, ctx_dim)
+        self.ff = _FeedForward(dim)
+
+    def forward(self, x, ctx):
+        x = x + self.attn1(self.norm1(x))
+        x = x + self.attn2(self.norm2(x), ctx)
+        return x + self.ff(self.norm3(x))
+
+
+class Transformer2DModel(nn.Module):
+    """`use_linear_projection=True` (SDXL): proj_in/out are Linear; SD 1.5: 1x1 Conv2d."""
+
+    def __init__(self, dim: int, depth: int, ctx_dim: int, linear_proj: bool):
+        super().__init__()
+        self.linear_proj = linear_proj
+        self.norm = nn.GroupNorm(32, dim, eps=1e-6)
+        self.proj_in = nn.Linear(dim, dim) if linear_proj else nn.Conv2d(dim, dim, 1)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(dim, ctx_dim) for _ in range(depth)])
+        self.proj_out = nn.Linear(dim, dim) if linear_proj else nn.Conv2d(dim, dim, 1)
+
+    def forward(self, x, ctx):
+        B, C, H, W = x.shape
+        res = x
+        h = self.norm(x)
+        if self.linear_proj:
+            h = self.proj_in(h.permute(0, 2, 3, 1).reshape(B, H * W, C))
+        else:
+            h = self.proj_in(h).permute(0, 2, 3, 1).reshape(B, H * W, C)
+        for blk in self.transformer_blocks:
+            h = blk(h, ctx)
+        if self.linear_proj:
+            h = self.proj_out(h).view(B, H, W, C).permute(0, 3, 1, 2)
+        else:
+            h = self.proj_out(h.view(B, H, W, C).permute(0, 3, 1, 2))
+        return h + res
+
+
+class _Stage(nn.Module):
+    def __init__(self, dim, n_attn, depth, ctx_dim, linear_proj):
+        super().__init__()
+        self.attentions = nn.ModuleList([Transformer2DModel(dim, depth, ctx_dim, linear_proj) for _ in range(n_attn)])
+
+    def forward(self, x, ctx):
+        for a in self.attentions:
+            x = a(x, ctx)
+        return x
+
+
+class _Output:
+    def __init__(self, sample):
+        self.sample = sample
+
+
+class StandInUNet(nn.Module):
+    """UNet2DConditionModel-shaped stand-in: `unet(sample, timestep, encoder_hidden_states,
+    added_cond_kwargs=None).sample`."""
+
+    def __init__(self, in_ch: int, stages: list[tuple[int, int, int, int]], mid: tuple[int, int] | None, ctx_dim: int,
+                 linear_proj: bool, pooled_dim: int = 0):
+        """stages: (dim, downsample_factor_vs_latent, n_attn_down, depth); the up path mirrors it with n_attn_down+1."""
+        super().__init__()
+        self.in_ch = in_ch
+        dims = [s[0] for s in stages]
+        self.time_embed = nn.Linear(256, dims[-1])
+        self.add_embed = nn.Linear(pooled_dim + 6 * 256, dims[-1]) if pooled_dim else None
+        self.down_convs = nn.ModuleList()
+        prev_c, prev_f = in_ch, 1
+        for (dim, factor, _, _) in stages:
+            k = factor // prev_f
+            self.down_convs.append(nn.Conv2d(prev_c, dim, k, stride=k))
+            prev_c, prev_f = dim, factor
+        first = 4 - len(stages)          # diffusers numbering: attention stages are the LAST down blocks
+        self.down_blocks = nn.ModuleList([nn.Module() for _ in range(first)] +
+                                         [_Stage(d, n, dep, ctx_dim, linear_proj) for (d, _, n, dep) in stages])
+        self.mid_block = _Stage(mid[0], 1, mid[1], ctx_dim, linear_proj) if mid else None
+        self.up_blocks = nn.ModuleList([_Stage(d, n + 1, dep, ctx_dim, linear_proj) for (d, _, n, dep) in reversed(stages)])
+        self.up_convs = nn.ModuleList()
+        rev = list(reversed(stages))
+        for i, (dim, factor, _, _) in enumerate(rev):
+            nxt = rev[i + 1] if i + 1 < len(rev) else (in_ch, 1, 0, 0)
+            k = factor // nxt[1]
+            self.up_convs.append(nn.ConvTranspose2d(dim, nxt[0], k, stride=k))
+        self.time_projs = nn.ModuleList([nn.Linear(dims[-1], d) for d in dims])
+
+    @staticmethod
+    def _sinusoid(t, dim=256):
+        half = dim // 2
+        freqs = torch.exp(-math.log(10000.0) * torch.arange(half, device=t.device, dtype=torch.float32) / half)
+        args = t.float().reshape(-1, 1) * freqs
+        return torch.cat([args.cos(), args.sin()], dim=-1)
+
+    def forward(self, sample, timestep, encoder_hidden_states, added_cond_kwargs=None):
+        B = sample.shape[0]
+        dt = sample.dtype
+        temb = self.time_embed(self._sinusoid(timestep.expand(B) if timestep.numel() == 1 else timestep).to(dt))
+        if self.add_embed is not None and added_cond_kwargs is not None:
+            ids = self._sinusoid(added_cond_kwargs["time_ids"].flatten()).view(B, -1).to(dt)
+            temb = temb + self.add_embed(torch.cat([added_cond_kwargs["text_embeds"].to(dt), ids], dim=-1))
+        x = sample
+        skips = []
+        n_pass = len(self.down_blocks) - len(self.down_convs)
+        for i, conv in enumerate(self.down_convs):
+            x = conv(x) + self.time_projs[i](temb)[:, :, None, None]
+            x = self.down_blocks[n_pass + i](x, encoder_hidden_states)
+            skips.append(x)
+        if self.mid_block is not None:
+            x = self.mid_block(x, encoder_hidden_states)
+        for i, (blk, conv) in enumerate(zip(self.up_blocks, self.up_convs)):
+            x = blk(x + skips[-1 - i], encoder_hidden_states)
+            x = conv(x)
+        return _Output(x)
+
+
+def sdxl_unet() -> StandInUNet:
+    """SDXL base: attention at 64x64 (C=640, depth 2) and 32x32 (C=1280, depth 10), mid depth 10, ctx 2048.
+    722 hooked leaves / 85.1 M LoRA parameters at rank 32."""
+    return StandInUNet(4, [(640, 2, 2, 2), (1280, 4, 2, 10)], (1280, 10), ctx_dim=2048, linear_proj=True, pooled_dim=1280)
+
+
+def sd15_unet() -> StandInUNet:
+    """SD 1.5: attention at 64x64 (320), 32x32 (640), 16x16 (1280), depth 1, mid 1280, ctx 768, conv projections.
+    192 hooked leaves."""
+    return StandInUNet(4, [(320, 1, 2, 1), (640, 2, 2, 1), (1280, 4, 2, 1)], (1280, 1), ctx_dim=768, linear_proj=False)
+
+
+def tiny_unet(dim: int = 64, ctx_dim: int = 64) -> StandInUNet:
+    """A few-leaf network of the same shape for smoke tests."""
+    return StandInUNet(4, [(dim, 2, 1, 1)], (dim, 1), ctx_dim=ctx_dim, linear_proj=True)
+
+
+class StandInScheduler:
+    """The three things the hot path reads from a diffusers DDIMScheduler."""
+
+    def __init__(self, betas: torch.Tensor, prediction_type: str = "epsilon"):
+        self.betas = betas
+        self.alphas = 1.0 - betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.config = {"num_train_timesteps": betas.shape[0], "prediction_type": prediction_type}
+
+    @property
+    def prediction_type(self):
+        return self.config["prediction_type"]
+
+    def get_velocity(self, sample, noise, timesteps):
+        """diffusers DDIMScheduler.get_velocity (not vendored in the reference; call site
+        BaseStableDiffusionXLSetup.py:285): v = sqrt(abar) * eps - sqrt(1 - abar) * x0."""
+        ac = self.alphas_cumprod.to(device=sample.device)
+        a = (ac[timesteps] ** 0.5).flatten()
+        b = ((1 - ac[timesteps]) ** 0.5).flatten()
+        while a.dim() < sample.dim():
+            a, b = a.unsqueeze(-1), b.unsqueeze(-1)
+        return a * noise - b * sample
+
+
+def count_lora_leaves(net: nn.Module, filters: list[str]) -> int:
+    return sum(1 for name, m in net.named_modules()
+               if isinstance(m, (nn.Linear, nn.Conv2d)) and any(f in name for f in filters))

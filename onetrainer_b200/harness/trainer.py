@@ -1,0 +1,191 @@
+"""Training-step harness: the reference's step body on the B200 hot path (HARNESS, not product).
+
+`predict` / `calculate_loss` restate the family setup bodies the reference keeps unchanged
+(BaseStableDiffusionXLSetup.predict :188-291,357 and calculate_loss :360-373; SD 1.5 is the same
+minus added_cond_kwargs, BaseStableDiffusionSetup.py:144-224,312-325) with the mixins of this package
+underneath; `train_step` follows GenericTrainer.train :683-747 (predict -> loss -> /GA -> backward ->
+[allreduce] -> clip -> optimizer.step -> zero_grad -> ema.step).  Conditioning comes from the batch
+(cached text-encoder states), as with latent/text caching in the reference.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .. import dp
+from ..modules.module.EMAModule import EMAModuleWrapper
+from ..modules.module.LoRAModule import LoRAModuleWrapper
+from ..modules.modelSetup.mixin.ModelSetupDiffusionLossMixin import ModelSetupDiffusionLossMixin
+from ..modules.modelSetup.mixin.ModelSetupDiffusionMixin import ModelSetupDiffusionMixin
+from ..modules.modelSetup.mixin.ModelSetupFusedNoiseMixin import ModelSetupFusedNoiseMixin
+from ..modules.modelSetup.mixin.ModelSetupNoiseMixin import ModelSetupNoiseMixin
+from ..modules.util.optimizer.adamw_extensions import patch_adamw
+from . import standin
+
+
+class TrainProgress:
+    def __init__(self):
+        self.global_step = 0
+
+    def next_step(self, batch_size: int):
+        self.global_step += 1
+
+
+class StandInModel:
+    """The fields of the reference's BaseModel / StableDiffusionXLModel the step touches."""
+
+    def __init__(self, unet: nn.Module, scheduler: standin.StandInScheduler, vae_scaling_factor: float,
+                 train_dtype: torch.dtype, sdxl: bool):
+        self.unet = unet
+        self.noise_scheduler = scheduler
+        self.vae_scaling_factor = vae_scaling_factor
+        self.train_dtype = train_dtype
+        self.sdxl = sdxl
+        self.unet_lora: LoRAModuleWrapper | None = None
+        self.optimizer = None
+        self.ema: EMAModuleWrapper | None = None
+        self.parameters: list[nn.Parameter] = []
+        self.train_progress = TrainProgress()
+        self.autocast_context = torch.autocast(device_type="cuda", dtype=train_dtype)
+
+
+class DiffusionSetup(ModelSetupFusedNoiseMixin, ModelSetupNoiseMixin, ModelSetupDiffusionMixin, ModelSetupDiffusionLossMixin):
+    """SD 1.5 / SDXL flavoured setup (epsilon or v-prediction, DDPM schedule)."""
+
+    def __init__(self, train_device: torch.device, fused_noise: bool = True):
+        super().__init__()
+        self.train_device = train_device
+        self.fused_noise = fused_noise
+
+    def predict(self, model: StandInModel, batch: dict, config, train_progress: TrainProgress, *, deterministic: bool = False) -> dict:
+        with model.autocast_context:
+            batch_seed = 0 if deterministic else train_progress.global_step
+            generator = torch.Generator(device=config.train_device)
+            generator.manual_seed(batch_seed)
+            latent_image = batch["latent_image"]
+            T = model.noise_scheduler.config["num_train_timesteps"]
+            ptype = model.noise_scheduler.config["prediction_type"]
+            if self.fused_noise:
+                st = self._noise_timestep_addnoise(
+                    latent_image, config, generator, num_train_timesteps=T, deterministic=deterministic,
+                    prediction_type=ptype, betas=model.noise_scheduler.betas, latent_scale=model.vae_scaling_factor,
+                    train_dtype=model.train_dtype)
+                timestep, latent_input, target = st["timestep"], st["noisy"], st["target"]
+            else:   # the reference's call-by-call sequence, each call one launch
+                scaled_latent_image = latent_image * model.vae_scaling_factor
+                latent_noise = self._create_noise(scaled_latent_image, config, generator)
+                timestep = self._get_timestep_discrete(T, deterministic, generator, scaled_latent_image.shape[0], config)
+                noisy = self._add_noise_discrete(scaled_latent_image, latent_noise, timestep, model.noise_scheduler.betas)
+                latent_input = noisy.to(dtype=model.train_dtype)
+                target = latent_noise if ptype == "epsilon" else model.noise_scheduler.get_velocity(
+                    scaled_latent_image, latent_noise, timestep)
+            kwargs = {}
+            if model.sdxl:
+                add_time_ids = torch.stack([
+                    batch["original_resolution"][0], batch["original_resolution"][1],
+                    batch["crop_offset"][0], batch["crop_offset"][1],
+                    batch["crop_resolution"][0], batch["crop_resolution"][1]], dim=1).to(dtype=latent_input.dtype, device=latent_input.device)
+                kwargs["added_cond_kwargs"] = {"text_embeds": batch["text_encoder_2_pooled_state"], "time_ids": add_time_ids}
+            predicted = model.unet(latent_input, timestep, batch["text_encoder_hidden_state"].to(dtype=model.train_dtype), **kwargs).sample
+            data = {"loss_type": "target", "timestep": timestep, "predicted": predicted, "target": target}
+        data["prediction_type"] = ptype
+        return data
+
+    def calculate_loss(self, model: StandInModel, batch: dict, data: dict, config) -> torch.Tensor:
+        return self._diffusion_losses(batch=batch, data=data, config=config, train_device=self.train_device,
+                                      betas=model.noise_scheduler.betas.to(device=self.train_device)).mean()
+
+
+def build_model(kind: str, config, device, *, train_dtype=torch.bfloat16, lora_weight_dtype=torch.float32,
+                prediction_type: str = "epsilon", ema: bool = False, stochastic_rounding: bool = True,
+                fused_clip: bool = True, fused_ema: bool = True, seed: int = 1234, lr: float = 3e-4,
+                lora_up_std: float = 0.0) -> tuple[StandInModel, DiffusionSetup]:
+    """Random-init stand-in + LoRA wrapper + patched AdamW (+EMA), as StableDiffusionXLLoRASetup.setup_model
+    (:103-158) and init_model_parameters (optimizer_util.py:50-65) wire them."""
+    torch.manual_seed(seed)
+    with torch.device(device):
+        unet = {"sdxl": standin.sdxl_unet, "sd15": standin.sd15_unet, "tiny": standin.tiny_unet}[kind]()
+    unet = unet.to(dtype=train_dtype)
+    unet.requires_grad_(False)
+    unet.train()
+    sched = standin.StandInScheduler(standin_betas(), prediction_type)
+    model = StandInModel(unet, sched, 0.13025 if kind == "sdxl" else 0.18215, train_dtype, sdxl=(kind == "sdxl"))
+    model.unet_lora = LoRAModuleWrapper(unet, "lora_unet", config, ["attentions"])
+    model.unet_lora.set_dropout(config.dropout_probability)
+    model.unet_lora.to(dtype=lora_weight_dtype)
+    if lora_up_std > 0:
+        g = torch.Generator(device=device).manual_seed(seed + 1)
+        for m in model.unet_lora.lora_modules.values():
+            m.lora_up.weight.data.normal_(0.0, lora_up_std, generator=g)
+    model.unet_lora.hook_to_module()
+    model.unet_lora.requires_grad_(True)
+    model.parameters = model.unet_lora.parameters()
+    model.optimizer = torch.optim.AdamW(model.parameters, lr=lr, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    if ema:
+        model.ema = EMAModuleWrapper(model.parameters, decay=config.ema_decay,
+                                     update_step_interval=config.ema_update_step_interval, device=torch.device(device))
+    progress = model.train_progress
+    patch_adamw(model.optimizer, stochastic_rounding,
+                ema=model.ema if (ema and fused_ema) else None,
+                ema_step_fn=(lambda: progress.global_step // config.gradient_accumulation_steps) if (ema and fused_ema) else None,
+                clip_grad_norm=config.clip_grad_norm if fused_clip else None)
+    return model, DiffusionSetup(torch.device(device))
+
+
+def standin_betas():
+    from ..modules.util.DiffusionScheduleCoefficients import scaled_linear_betas
+    return scaled_linear_betas()
+
+
+def synthetic_batch(kind: str, batch_size: int, device, seed: int = 1234, latent_hw: int | None = None, masked: bool = False) -> dict:
+    """Seeded synthetic batch with the dataloader's keys."""
+    g = torch.Generator(device="cpu").manual_seed(seed + dp.rank())
+    hw = latent_hw or (128 if kind == "sdxl" else 64)
+    ctx = {"sdxl": 2048, "sd15": 768, "tiny": 64}[kind]
+    b = {
+        "latent_image": torch.randn(batch_size, 4, hw, hw, generator=g) * 0.8,
+        "loss_weight": torch.ones(batch_size),
+        "text_encoder_hidden_state": torch.randn(batch_size, 77, ctx, generator=g),
+    }
+    if masked:
+        blocks = (torch.rand(batch_size, 1, hw // 8, hw // 8, generator=g) > 0.5).float()
+        b["latent_mask"] = blocks.repeat_interleave(8, dim=2).repeat_interleave(8, dim=3)
+    if kind == "sdxl":
+        b["text_encoder_2_pooled_state"] = torch.randn(batch_size, 1280, generator=g)
+        px = float(hw * 8)
+        b["original_resolution"] = [torch.full((batch_size,), px), torch.full((batch_size,), px)]
+        b["crop_offset"] = [torch.zeros(batch_size), torch.zeros(batch_size)]
+        b["crop_resolution"] = [torch.full((batch_size,), px), torch.full((batch_size,), px)]
+    return b
+
+
+def batch_to_device(batch: dict, device, non_blocking: bool = True) -> dict:
+    out = {}
+    for k, v in batch.items():
+        if isinstance(v, list):
+            out[k] = [t.to(device, non_blocking=non_blocking) for t in v]
+        else:
+            out[k] = v.to(device, non_blocking=non_blocking)
+    return out
+
+
+def train_step(setup: DiffusionSetup, model: StandInModel, batch: dict, config, bucket: dp.GradientBucket | None = None) -> torch.Tensor:
+    """One optimisation step (gradient accumulation 1), GenericTrainer.py:683-747.  Returns the loss as a
+    DEVICE scalar — the reference's `loss.item()` every micro-step (:699) is left to the caller."""
+    data = setup.predict(model, batch, config, model.train_progress)
+    loss = setup.calculate_loss(model, batch, data, config)
+    loss = loss / config.gradient_accumulation_steps
+    loss.backward()
+    driver = model.optimizer.otb_driver
+    if dp.world_size() > 1:
+        bucket = bucket or dp.GradientBucket(model.unet_lora.grad_arena)
+        driver.grad_prescale = bucket.allreduce([p.grad for p in model.parameters if p.grad is not None])
+    if config.clip_grad_norm is not None and driver.clip_max_norm is None:
+        from ..modules.util.grad_clip import clip_grad_norm_
+        clip_grad_norm_(model.parameters, config.clip_grad_norm, driver.grad_prescale)
+    model.optimizer.step()
+    model.optimizer.zero_grad(set_to_none=True)
+    if model.ema is not None:
+        model.ema.step(model.parameters, model.train_progress.global_step // config.gradient_accumulation_steps)
+    model.train_progress.next_step(config.batch_size)
+    return loss.detach()

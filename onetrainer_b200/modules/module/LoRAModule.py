@@ -1,0 +1,573 @@
+"""LoRA adapters on the B200 fused kernel — drop-in for the LoRA part of
+/root/reference/modules/module/LoRAModule.py (PeftBase :17-206, LoRAModule :283-331,
+LoRAModuleWrapper :427-587; DoRA/LoHa are outside SURVEY.md §8 and raise).
+
+Seam contract kept: `klass(prefix, orig_module, rank, alpha)`;
+`forward(x, *args, **kwargs)`; `hook_to_module()/remove_hook_from_module()` swapping the wrapped
+module's forward/train/eval; `lora_down` / `lora_up` sub-modules whose `.weight` are real
+nn.Parameters (optimizer, EMA, clipping and savers hold references to those objects); buffer
+`alpha`; `dropout.p`; `state_dict(prefix=module.prefix)` keys `{prefix}lora_down.weight`,
+`{prefix}lora_up.weight`, `{prefix}alpha`; prefix-filtered `load_state_dict`; `make_dummy()`.
+
+What changes underneath: instead of base GEMM + down GEMM + dropout + up GEMM + scale + add
+(3 GEMMs and 2-3 elementwise launches forward, ~7 GEMMs backward, the skinny ones at a few % of
+tensor peak) every hooked leaf is
+    forward : 1 launch  otb_lora_linear   (tcgen05; T = s*x*A^T rides in the same UMMA as x*W^T)
+    backward: 2 launches otb_lora_linear (dX, with the transposed bf16 shadows) + otb_lora_grad_ab (dA, dB)
+bf16 shadows of A/B (and their transposes) and of the frozen W^T are kept resident in HBM — on a
+180 GB part the duplicated frozen weights are cheap and remove every per-call cast/transposition.
+"""
+from __future__ import annotations
+
+import copy
+import math
+from abc import abstractmethod
+from collections.abc import Mapping
+from typing import Any
+
+import torch
+from torch import Tensor, nn
+from torch.nn import Conv2d, Dropout, Linear, Parameter
+
+from ... import ops
+from ..util.enum import enum_name
+
+
+# ---------------------------------------------------------------------------------------
+# gradient arena + bf16 shadows shared by all leaves of one wrapper
+# ---------------------------------------------------------------------------------------
+class GradArena:
+    """One flat fp32 buffer holding dA/dB of every leaf.
+
+    The split-M gradient kernel accumulates with fp32 reductions, so its outputs must start at
+    zero; one memset per step replaces two per leaf.  The views are handed to autograd as the
+    gradients, which makes `p.grad` of every LoRA tensor a slice of ONE buffer — the data-parallel
+    allreduce then runs in place on the arena with no gather/scatter (onetrainer_b200/dp.py).
+    """
+
+    def __init__(self, shapes: list[tuple[int, ...]], device):
+        total = 0
+        self.offsets = []
+        for s in shapes:
+            n = math.prod(s)
+            self.offsets.append((total, n, s))
+            total += (n + 3) // 4 * 4           # keep every slice 16-byte aligned
+        self.flat = torch.zeros((max(total, 1),), dtype=torch.float32, device=device)
+        self.generation = 0
+
+    def view(self, i: int) -> Tensor:
+        off, n, s = self.offsets[i]
+        return self.flat[off:off + n].view(s)
+
+    def start_new_accumulation(self) -> None:
+        self.flat.zero_()
+        self.generation += 1
+
+
+class _LoraLinearFn(torch.autograd.Function):
+    """y = base(x) + drop(s * x A^T) B^T with the fused kernels.  Saves only x and Ts (M x r)."""
+
+    @staticmethod
+    def forward(ctx, x2: Tensor, a_param: Tensor, b_param: Tensor, mod: "LoRAModule"):
+        sh = mod._operands()
+        p = mod.dropout.p if mod.training else 0.0
+        seed = offset = 0
+        if p > 0.0:
+            gen = torch.cuda.default_generators[x2.device.index]
+            seed, offset = gen.initial_seed(), gen.get_offset()
+            gen.set_offset(offset + 4)      # checkpoint recompute restores this state -> same mask
+        y, ts = ops.lora_linear(x2, sh["w"], sh["a"], sh["b"], sh["bias"], mod._scale(), dropout_p=p,
+                                seed=seed, offset=offset, want_t=any(ctx.needs_input_grad[:3]))
+        ctx.mod, ctx.p, ctx.key = mod, p, (seed, offset)
+        ctx.save_for_backward(x2, ts)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        mod: LoRAModule = ctx.mod
+        x2, ts = ctx.saved_tensors
+        sh = mod._operands()
+        dy = dy.contiguous()
+        if dy.dtype != torch.bfloat16:
+            dy = dy.to(torch.bfloat16)
+        # dX = dY W + drop(s * dY B) A  — same kernel, transposed shadows; also parks Gs = drop(s * dY B)
+        dx, gs = ops.lora_linear(dy, sh["wt"], sh["bt"], sh["at"], None, mod._scale(), dropout_p=ctx.p,
+                                 seed=ctx.key[0], offset=ctx.key[1], want_t=True)
+        need_a, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dA, dB, ret_a, ret_b = mod._grad_buffers(need_a, need_b)
+        if dA is not None or dB is not None:
+            ops.lora_grad_ab(x2, dy, gs, ts, dA, dB)
+        if ret_a is not None and ret_a.dtype != mod.lora_down.weight.dtype:
+            ret_a = ret_a.to(mod.lora_down.weight.dtype)
+        if ret_b is not None and ret_b.dtype != mod.lora_up.weight.dtype:
+            ret_b = ret_b.to(mod.lora_up.weight.dtype)
+        return (dx if ctx.needs_input_grad[0] else None), ret_a, ret_b, None
+
+
+# ---------------------------------------------------------------------------------------
+# PeftBase
+# ---------------------------------------------------------------------------------------
+class PeftBase(nn.Module):
+    """Hooking / state-dict plumbing shared by adapter types (reference PeftBase, :17-206)."""
+    is_applied: bool
+    orig_forward: Any | None
+    orig_eval: Any | None
+    orig_train: Any | None
+    _orig_module: list[nn.Module] | None   # in a list so nn.Module does not register it
+    prefix: str
+    layer_kwargs: dict
+    _initialized: bool
+
+    def __init__(self, prefix: str, orig_module: nn.Module | None):
+        super().__init__()
+        self.prefix = prefix + "."
+        self._orig_module = [orig_module] if orig_module else None
+        self.is_applied = False
+        self.layer_kwargs = {}
+        self._initialized = False
+        self.orig_forward = self.orig_train = self.orig_eval = None
+        if orig_module is not None:
+            if isinstance(orig_module, nn.Linear):
+                self.shape = tuple(orig_module.weight.shape)
+            elif isinstance(orig_module, nn.Conv2d):
+                self.shape = tuple(orig_module.weight.shape)
+                for k in ("stride", "padding", "dilation", "groups"):
+                    self.layer_kwargs.setdefault(k, getattr(orig_module, k))
+            else:
+                raise NotImplementedError("Only Linear and Conv2d are supported layers.")
+
+    @property
+    def orig_module(self) -> nn.Module:
+        assert self._orig_module is not None
+        return self._orig_module[0]
+
+    def hook_to_module(self):
+        if self.is_applied:
+            return
+        om = self.orig_module
+        self.orig_forward, self.orig_train, self.orig_eval = om.forward, om.train, om.eval
+        om.forward, om.train, om.eval = self.forward, self._wrap_train, self._wrap_eval
+        self.is_applied = True
+
+    def remove_hook_from_module(self):
+        assert self.orig_forward is not None
+        if not self.is_applied:
+            return
+        om = self.orig_module
+        om.forward, om.train, om.eval = self.orig_forward, self.orig_train, self.orig_eval
+        self.is_applied = False
+
+    def _wrap_train(self, mode=True):
+        self.orig_train(mode)
+        self.train(mode)
+
+    def _wrap_eval(self):
+        self.orig_eval()
+        self.eval()
+
+    def make_weight(self, A: Tensor, B: Tensor):
+        """Full-size delta weight B @ A for Linear and Conv2d alike (reference :76-91)."""
+        return (B.view(B.size(0), -1) @ A.view(A.size(0), -1)).view(self.shape)
+
+    def check_initialized(self):
+        if not self._initialized:
+            raise RuntimeError(f"Module {self.prefix} is not initialized.")
+        assert self.orig_forward is not None
+        assert self.orig_module is not None
+
+    def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True, assign: bool = False):
+        own = {k.removeprefix(self.prefix): v for k, v in state_dict.items() if k.startswith(self.prefix)}
+        return super().load_state_dict(own, strict, assign)
+
+    @abstractmethod
+    def initialize_weights(self):
+        pass
+
+    @abstractmethod
+    def apply_to_module(self):
+        pass
+
+    @abstractmethod
+    def extract_from_module(self, base_module: nn.Module):
+        pass
+
+    def create_layer(self) -> tuple[nn.Module, nn.Module]:
+        """Down/up modules for the wrapped layer type; uninitialised (reference :125-160)."""
+        om = self.orig_module
+        device = om.weight.device
+        if isinstance(om, nn.Linear):
+            down = nn.Linear(om.in_features, self.rank, bias=False, device=device)
+            up = nn.Linear(self.rank, om.out_features, bias=False, device=device)
+        elif isinstance(om, nn.Conv2d):
+            down = Conv2d(om.in_channels, self.rank, om.kernel_size, om.stride, om.padding, dilation=om.dilation,
+                          bias=False, device=device)
+            up = Conv2d(self.rank, om.out_channels // om.groups, (1, 1), 1, bias=False, device=device)
+        else:
+            raise NotImplementedError("Only Linear and Conv2d are supported layers.")
+        return down, up
+
+    @classmethod
+    def make_dummy(cls):
+        """A holder for state-dict keys that match no trainable layer (reference :162-206): keeps
+        and returns the loaded dict, never hooks, never trains."""
+
+        class Dummy(cls):
+            def __init__(self, *args, **kwargs):
+                super().__init__(*args, **kwargs)
+                self._state_dict = {}
+
+            def forward(self, *args, **kwargs):
+                raise NotImplementedError("Should never be called on a dummy module.")
+
+            def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True, assign: bool = False):
+                self._initialized = True
+                self._state_dict = copy.deepcopy(state_dict)
+                return nn.modules.module._IncompatibleKeys([], [])
+
+            def state_dict(self, *args, **kwargs):  # type: ignore
+                if not self._initialized:
+                    raise RuntimeError("A state dict must be loaded before one can be returned.")
+                return self._state_dict
+
+            def initialize_weights(self):
+                raise NotImplementedError("Should never be called on a dummy module.")
+
+            def hook_to_module(self):
+                raise NotImplementedError("Should never be called on a dummy module.")
+
+            def remove_hook_from_module(self):
+                raise NotImplementedError("Should never be called on a dummy module.")
+
+            def apply_to_module(self):
+                raise NotImplementedError("Should never be called on a dummy module.")
+
+            def extract_from_module(self, base_module: nn.Module):
+                raise NotImplementedError("Should never be called on a dummy module.")
+
+        return Dummy
+
+
+# ---------------------------------------------------------------------------------------
+# LoRAModule
+# ---------------------------------------------------------------------------------------
+class LoRAModule(PeftBase):
+    lora_down: nn.Module | None
+    lora_up: nn.Module | None
+    rank: int
+    alpha: torch.Tensor
+    dropout: Dropout
+
+    def __init__(self, prefix: str, orig_module: nn.Module | None, rank: int, alpha: float):
+        super().__init__(prefix, orig_module)
+        self.rank = rank
+        self.dropout = Dropout(0)
+        self.register_buffer("alpha", torch.tensor(alpha))
+        self.lora_down = None
+        self.lora_up = None
+        # fused-path state (not part of the state dict)
+        self._wrapper_slot = None       # (wrapper, index) when owned by a LoRAModuleWrapper
+        self._own_shadow = None         # ShadowTable of [A, B] for a stand-alone module
+        self._own_versions = None
+        self._base_cache = None         # (key, w_bf16, wt_bf16)
+        self._scale_cache = None
+        if orig_module is not None:
+            self._check_supported(orig_module)
+            self.initialize_weights()
+            self.alpha = self.alpha.to(orig_module.weight.device)
+        self.alpha.requires_grad_(False)
+
+    @staticmethod
+    def _check_supported(om: nn.Module) -> None:
+        # fail loudly instead of silently falling back: quantised bases and
+        # general convolutions have no fused kernel yet
+        if type(om) not in (nn.Linear, nn.Conv2d) and type(om).__name__ in ("LinearNf4", "LinearFp8", "Linear4bit", "Linear8bitLt"):
+            raise NotImplementedError(f"quantized base layer {type(om).__name__} is not supported by the fused LoRA kernel")
+        if isinstance(om, nn.Conv2d):
+            if om.kernel_size != (1, 1) or om.stride != (1, 1) or om.padding not in ((0, 0), 0) or om.dilation != (1, 1) or om.groups != 1:
+                raise NotImplementedError(
+                    "fused LoRA supports Linear and 1x1/stride-1/groups-1 Conv2d leaves; "
+                    f"got Conv2d(kernel={om.kernel_size}, stride={om.stride}, padding={om.padding}, groups={om.groups})")
+
+    def initialize_weights(self):
+        self._initialized = True
+        self.lora_down, self.lora_up = self.create_layer()
+        nn.init.kaiming_uniform_(self.lora_down.weight, a=math.sqrt(5))
+        nn.init.zeros_(self.lora_up.weight)
+
+    def check_initialized(self):
+        super().check_initialized()
+        assert self.lora_down is not None
+        assert self.lora_up is not None
+
+    # ---- operands of the fused kernels --------------------------------------------------
+    def _scale(self) -> float:
+        # alpha is a buffer; reading it back every call would be a device sync, so cache by version
+        key = (self.alpha._version, self.alpha.data_ptr(), self.rank)
+        if self._scale_cache is None or self._scale_cache[0] != key:
+            self._scale_cache = (key, float(self.alpha) / self.rank)
+        return self._scale_cache[1]
+
+    def _base(self):
+        om = self.orig_module
+        w = om.weight
+        key = (w.data_ptr(), w._version, w.dtype)
+        if self._base_cache is None or self._base_cache[0] != key:
+            if w.dtype not in (torch.bfloat16, torch.float32, torch.float16):
+                raise NotImplementedError(f"base weight dtype {w.dtype} is not supported by the fused LoRA kernel")
+            w2 = w.detach().reshape(w.shape[0], -1)
+            wb = w2 if w2.dtype == torch.bfloat16 and w2.is_contiguous() else w2.to(torch.bfloat16).contiguous()
+            self._base_cache = (key, wb, wb.t().contiguous())
+        return self._base_cache[1], self._base_cache[2]
+
+    def _operands(self) -> dict:
+        w, wt = self._base()
+        if self._wrapper_slot is not None:
+            wrapper, idx = self._wrapper_slot
+            a, at, b, bt = wrapper._shadows_for(idx, self)
+        else:
+            A, B = self.lora_down.weight, self.lora_up.weight
+            vers = (A._version, B._version, A.data_ptr(), B.data_ptr(), A.dtype)
+            if self._own_shadow is None or self._own_versions != vers:
+                if self._own_shadow is None or self._own_versions[2:] != vers[2:]:
+                    self._own_shadow = ops.ShadowTable([A.detach().view(A.shape[0], -1), B.detach().view(B.shape[0], -1)], A.device)
+                self._own_shadow.refresh()
+                self._own_versions = vers
+            (a, b), (at, bt) = self._own_shadow.views, self._own_shadow.views_t
+        return dict(w=w, wt=wt, a=a, at=at, b=b, bt=bt, bias=self.orig_module.bias)
+
+    def _grad_buffers(self, need_a: bool, need_b: bool):
+        """(dA accumulate target, dB accumulate target, value to return for A, for B)."""
+        A, B = self.lora_down.weight, self.lora_up.weight
+        if self._wrapper_slot is not None:
+            wrapper, idx = self._wrapper_slot
+            return wrapper._grad_views(idx, A, B, need_a, need_b)
+        dA = torch.zeros((A.shape[0], A[0].numel()), dtype=torch.float32, device=A.device) if need_a else None
+        dB = torch.zeros((B.shape[0], B[0].numel()), dtype=torch.float32, device=B.device) if need_b else None
+        return dA, dB, (dA.view(A.shape) if need_a else None), (dB.view(B.shape) if need_b else None)
+
+    # ---- forward ------------------------------------------------------------------------
+    def forward(self, x, *args, **kwargs):
+        self.check_initialized()
+        if not x.is_cuda:
+            raise RuntimeError("the fused LoRA path runs on sm_100a CUDA tensors only; there is no CPU fallback")
+        out_dtype = x.dtype
+        if torch.is_autocast_enabled("cuda"):
+            out_dtype = torch.get_autocast_dtype("cuda")
+        if out_dtype != torch.bfloat16:
+            raise NotImplementedError(
+                f"the fused LoRA kernel computes in bf16 (tcgen05 kind::f16); got compute dtype {out_dtype}. "
+                "Run under bf16 autocast or with a bf16 train dtype (every B200 config in BASELINE.json is bf16).")
+        om = self.orig_module
+        A, B = self.lora_down.weight, self.lora_up.weight
+        if isinstance(om, nn.Conv2d):
+            b_, c_, h_, w_ = x.shape
+            x2 = x.permute(0, 2, 3, 1).reshape(-1, c_)
+        else:
+            x2 = x.reshape(-1, x.shape[-1])
+        if x2.dtype != torch.bfloat16:
+            x2 = x2.to(torch.bfloat16)
+        x2 = x2.contiguous()
+        y2 = _LoraLinearFn.apply(x2, A, B, self)
+        if isinstance(om, nn.Conv2d):
+            return y2.view(b_, h_, w_, -1).permute(0, 3, 1, 2)
+        return y2.view(*x.shape[:-1], y2.shape[-1])
+
+    def apply_to_module(self):
+        pass  # not implemented in the reference either (:325-327)
+
+    def extract_from_module(self, base_module: nn.Module):
+        pass  # not implemented in the reference either (:329-331)
+
+
+DummyLoRAModule = LoRAModule.make_dummy()
+
+
+# ---------------------------------------------------------------------------------------
+# LoRAModuleWrapper
+# ---------------------------------------------------------------------------------------
+class LoRAModuleWrapper:
+    """Builds one adapter per Linear/Conv2d whose name matches the filter (reference :427-587)."""
+    orig_module: nn.Module
+    rank: int
+    alpha: float
+    lora_modules: dict[str, PeftBase]
+
+    def __init__(self, orig_module: nn.Module | None, prefix: str, config, module_filter: list[str] = None):
+        self.orig_module = orig_module
+        self.prefix = prefix
+        self.peft_type = config.peft_type
+        self.rank = config.lora_rank
+        self.alpha = config.lora_alpha
+        self.module_filter = [x.strip() for x in module_filter] if module_filter is not None else []
+        if enum_name(self.peft_type) != "LORA" or getattr(config, "lora_decompose", False):
+            raise NotImplementedError("only plain LoRA is implemented on the B200 path (DoRA / LoHa: SURVEY.md §8f rank 4)")
+        self.klass = LoRAModule
+        self.dummy_klass = DummyLoRAModule
+        self.additional_args = [self.rank, self.alpha]
+        self.additional_kwargs = {}
+        self.lora_modules = self.__create_modules(orig_module)
+        self._shadow = None
+        self._shadow_key = None
+        self._arena = None
+        self._arena_key = None
+        self._written_gen = {}
+
+    def __create_modules(self, orig_module: nn.Module | None) -> dict[str, PeftBase]:
+        found = {}
+        if orig_module is not None:
+            for name, child in orig_module.named_modules():
+                if len(self.module_filter) == 0 or any(f in name for f in self.module_filter):
+                    if isinstance(child, Linear | Conv2d):
+                        found[name] = self.klass(self.prefix + "." + name, child, *self.additional_args, **self.additional_kwargs)
+        return found
+
+    # ---- fused-path services for the leaves ---------------------------------------------
+    def _trainable(self) -> list[LoRAModule]:
+        return [m for m in self.lora_modules.values() if isinstance(m, LoRAModule) and not isinstance(m, self.dummy_klass)]
+
+    def _bind(self) -> None:
+        for i, m in enumerate(self._trainable()):
+            m._wrapper_slot = (self, i)
+
+    def refresh_shadows(self) -> None:
+        """Re-emit the bf16 (and transposed) shadows of every A/B in ONE launch.  Called after each
+        optimizer step (post-step hook) and whenever a leaf sees its parameters changed."""
+        mods = self._trainable()
+        if not mods:
+            return
+        key = tuple((m.lora_down.weight.data_ptr(), m.lora_up.weight.data_ptr(), m.lora_down.weight.dtype) for m in mods)
+        if self._shadow is None or key != self._shadow_key:
+            masters = []
+            for m in mods:
+                A, B = m.lora_down.weight.detach(), m.lora_up.weight.detach()
+                masters += [A.view(A.shape[0], -1), B.view(B.shape[0], -1)]
+            self._shadow = ops.ShadowTable(masters, masters[0].device)
+            self._shadow_key = key
+        self._shadow.refresh()
+        self._versions = [(m.lora_down.weight._version, m.lora_up.weight._version) for m in mods]
+
+    def _shadows_for(self, idx: int, m: LoRAModule):
+        A, B = m.lora_down.weight, m.lora_up.weight
+        stale = (self._shadow is None or self._versions[idx] != (A._version, B._version)
+                 or self._shadow_key[idx][:2] != (A.data_ptr(), B.data_ptr()))
+        if stale:
+            self.refresh_shadows()
+        v, vt = self._shadow.views, self._shadow.views_t
+        return v[2 * idx], vt[2 * idx], v[2 * idx + 1], vt[2 * idx + 1]
+
+    def mark_parameters_updated(self) -> None:
+        """Post-step hook for optimizers that write parameters outside torch (our fused AdamW)."""
+        self.refresh_shadows()
+
+    def _grad_views(self, idx: int, A: Tensor, B: Tensor, need_a: bool, need_b: bool):
+        mods = self._trainable()
+        key = tuple((tuple(m.lora_down.weight.shape), tuple(m.lora_up.weight.shape)) for m in mods) + (str(A.device),)
+        if self._arena is None or key != self._arena_key:
+            shapes = []
+            for m in mods:
+                a, b = m.lora_down.weight, m.lora_up.weight
+                shapes += [(a.shape[0], a[0].numel()), (b.shape[0], b[0].numel())]
+            self._arena = GradArena(shapes, A.device)
+            self._arena_key = key
+            self._written_gen = {}
+        arena = self._arena
+        va, vb = arena.view(2 * idx), arena.view(2 * idx + 1)
+
+        def state(p: Tensor, v: Tensor) -> str:
+            if p.grad is None:
+                return "fresh"                  # first accumulation of this step: hand the arena slice to autograd
+            return "inplace" if p.grad.data_ptr() == v.data_ptr() else "foreign"
+
+        sa, sb = state(A, va) if need_a else "skip", state(B, vb) if need_b else "skip"
+        if "fresh" in (sa, sb) and self._written_gen.get(idx) == arena.generation:
+            arena.start_new_accumulation()      # first leaf of a new step: one memset for everyone
+        self._written_gen[idx] = arena.generation
+
+        def pick(st: str, p: Tensor, v: Tensor):
+            if st == "skip":
+                return None, None
+            if st == "fresh":
+                return v, v.view(p.shape)
+            if st == "inplace":                 # p.grad already IS the slice (gradient accumulation): add in place
+                return v, None
+            tmp = torch.zeros_like(v)           # someone replaced p.grad: plain autograd accumulation
+            return tmp, tmp.view(p.shape)
+
+        dA, ret_a = pick(sa, A, va)
+        dB, ret_b = pick(sb, B, vb)
+        return dA, dB, ret_a, ret_b
+
+    @property
+    def grad_arena(self) -> Tensor | None:
+        return None if self._arena is None else self._arena.flat
+
+    # ---- reference API ------------------------------------------------------------------
+    def requires_grad_(self, requires_grad: bool):
+        for m in self.lora_modules.values():
+            m.requires_grad_(requires_grad)
+
+    def parameters(self) -> list[Parameter]:
+        out = []
+        for m in self.lora_modules.values():
+            out += m.parameters()
+        return out
+
+    def to(self, device: torch.device = None, dtype: torch.dtype = None) -> "LoRAModuleWrapper":
+        for m in self.lora_modules.values():
+            m.to(device, dtype)
+        self._shadow = None
+        return self
+
+    def load_state_dict(self, state_dict: dict[str, Tensor]):
+        state_dict = {k: v for k, v in state_dict.items() if k.startswith(self.prefix)}
+        for name, m in self.lora_modules.items():
+            try:
+                m.load_state_dict(state_dict)
+            except RuntimeError:  # noqa: PERF203
+                print(f"Missing key for {name}; initializing it to zero.")
+        leftover = set(state_dict) - set(self.state_dict())
+        for name in leftover:
+            if name.endswith(".alpha"):
+                prefix = name.removesuffix(".alpha")
+                dummy = self.dummy_klass(prefix, None, *self.additional_args, **self.additional_kwargs)
+                dummy.load_state_dict(state_dict)
+                self.lora_modules[prefix] = dummy
+        self._shadow = None
+
+    def state_dict(self) -> dict:
+        out = {}
+        for m in self.lora_modules.values():
+            out |= m.state_dict(prefix=m.prefix)
+        return out
+
+    def modules(self) -> list[nn.Module]:
+        out = []
+        for m in self.lora_modules.values():
+            out += m.modules()
+        return out
+
+    def hook_to_module(self):
+        self._bind()
+        for m in self.lora_modules.values():
+            m.hook_to_module()
+
+    def remove_hook_from_module(self):
+        for m in self.lora_modules.values():
+            m.remove_hook_from_module()
+
+    def apply_to_module(self):
+        for m in self.lora_modules.values():
+            m.apply_to_module()
+
+    def extract_from_module(self, base_module: nn.Module):
+        for m in self.lora_modules.values():
+            m.extract_from_module(base_module)
+
+    def prune(self):
+        self.lora_modules = {k: v for k, v in self.lora_modules.items() if not isinstance(v, self.dummy_klass)}
+
+    def set_dropout(self, dropout_probability: float):
+        if dropout_probability < 0 or dropout_probability > 1:
+            raise ValueError("Dropout probability must be in [0, 1]")
+        for m in self.lora_modules.values():
+            m.dropout.p = dropout_probability

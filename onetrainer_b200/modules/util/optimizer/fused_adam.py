@@ -1,0 +1,197 @@
+"""Shared implementation behind patch_adamw / patch_adam: one multi-tensor launch per step.
+
+The reference runs ~13 ATen launches plus fp32/int32 temporaries PER PARAMETER TENSOR in a python
+loop (~20-25 k launches per step for SDXL); here `optimizer.step()` is:
+  [optional] otb_grad_norm_multi   (2 launches, deterministic)   — clip_grad_norm_ fused in
+  otb_adamw_sr_ema_multi           (1 launch)                    — AdamW/Adam + SR + EMA + clip scale
+and `step_parameter` (fused-back-pass mode, GenericTrainer.py:531-558) is one single-tensor launch.
+
+Checkpoint compatibility: `optimizer.state[p]` keeps exactly the reference's
+entries — 'step' (CPU fp32 scalar), 'exp_avg', 'exp_avg_sq' (zeros_like(p)) — as real tensors.
+"""
+from __future__ import annotations
+
+import torch
+
+from .... import ops
+from .... import _native as N
+
+
+def _init_state(state: dict, p: torch.Tensor, group: dict) -> None:
+    """Lazy state initialisation, same tensors as adamw_extensions.py:28-48."""
+    if group.get("amsgrad"):
+        raise NotImplementedError("amsgrad is not implemented on the B200 path (default off in the reference)")
+    if group.get("capturable") or group.get("differentiable"):
+        raise NotImplementedError("capturable/differentiable AdamW is not implemented on the B200 path")
+    state["step"] = torch.tensor(0.0, dtype=torch.float32)
+    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+
+
+def _bump_versions(params) -> None:
+    """The kernels write parameters behind torch's back; bump the autograd version counters so
+    everything keyed on `_version` (the LoRA bf16 shadows, saved-tensor checks) sees the update."""
+    try:
+        torch.autograd.graph.increment_version(params)
+    except TypeError:
+        for p in params:
+            torch.autograd.graph.increment_version(p)
+
+
+class FusedAdamDriver:
+    """Owns the device pointer table of one optimizer and launches the kernels."""
+
+    def __init__(self, optimizer, decoupled_weight_decay: bool):
+        self.opt = optimizer
+        self.decoupled = decoupled_weight_decay
+        self.flavor = N.FLAVOR_TORCH_CUDA
+        self.table: ops.OptimTable | None = None
+        self.table_key = None
+        self.ema = None                 # EMAModuleWrapper fused into the step, or None
+        self.ema_step_fn = None         # () -> optimization_step the trainer will pass to ema.step
+        self.clip_max_norm: float | None = None
+        self.grad_prescale = 1.0        # 1/world_size under data parallel
+        self.post_step_hooks = []       # e.g. LoRAModuleWrapper.refresh_shadows
+        self.step_count = 0             # SR Philox offset
+        self.last_norm_coef: torch.Tensor | None = None
+        self._single = {}               # id(p) -> one-entry table for step_parameter
+        self._prescale_dev, self._prescale_val = None, None
+
+    # -- table construction ---------------------------------------------------------------
+    def _active(self):
+        out = []
+        for group in self.opt.param_groups:
+            for p in group["params"]:
+                if p.grad is not None:
+                    out.append((p, group))
+        return out
+
+    def _entries(self, active):
+        ema_of = {}
+        if self.ema is not None:
+            ema_of = self.ema.ema_lookup()
+        entries = []
+        for p, group in active:
+            if p.grad.is_sparse:
+                raise RuntimeError("AdamW does not support sparse gradients")
+            st = self.opt.state[p]
+            if len(st) == 0:
+                _init_state(st, p, group)
+            entries.append(dict(p=p.data, g=p.grad, exp_avg=st["exp_avg"], exp_avg_sq=st["exp_avg_sq"],
+                                ema=ema_of.get(id(p))))
+        return entries
+
+    def _ensure_table(self, active):
+        key = tuple((id(p), p.data_ptr(), p.dtype) for p, _ in active) + (id(self.ema),)
+        if self.table is None or key != self.table_key:
+            if active and not active[0][0].is_cuda:
+                N.require_cuda(active[0][0])
+            self.table = ops.OptimTable(self._entries(active), active[0][0].device)
+            self.table_key = key
+            self._prepare_static(self.table, active)
+        return self.table
+
+    def _prepare_static(self, table: ops.OptimTable, active) -> None:
+        """Per-table constants: flags, and the step counters re-homed into ONE cpu tensor so that
+        `step_t += 1` for every parameter (adamw_extensions.py:80) is a single host op.  Each
+        state['step'] stays a real 0-dim fp32 CPU tensor (a view), as checkpoints expect."""
+        sr = bool(getattr(self.opt, "stochastic_rounding", False))
+        h = table.host
+        steps = torch.stack([self.opt.state[p]["step"].detach().to("cpu", torch.float32).reshape(()) for p, _ in active]) \
+            if active else torch.zeros(0)
+        for i, (p, group) in enumerate(active):
+            self.opt.state[p]["step"] = steps[i]
+            flags = int(h["flags"][i]) & N.OPT_FLAG_ALIGNED16
+            if sr and p.dtype == torch.bfloat16:
+                flags |= N.OPT_FLAG_SR
+            if group.get("maximize"):
+                flags |= N.OPT_FLAG_MAXIMIZE
+            h["flags"][i] = flags
+        table.steps_flat = steps
+
+    def _fill_scalars(self, table: ops.OptimTable, active) -> None:
+        table.steps_flat += 1                                   # step_t += 1 for every tensor
+        steps = table.steps_flat.tolist()
+        h = table.host
+        i, n = 0, len(active)
+        while i < n:                                            # runs of equal (group, step) share scalars
+            group, s = active[i][1], steps[i]
+            j = i + 1
+            while j < n and active[j][1] is group and steps[j] == s:
+                j += 1
+            beta1, beta2 = group["betas"]
+            sc = ops.adam_scalars(float(group["lr"]), beta1, beta2, group["eps"], group["weight_decay"], s, self.decoupled)
+            for k, v in sc.items():
+                h[k][i:j] = v
+            i = j
+
+    # -- entry points ---------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        active = self._active()
+        if not active:
+            return loss
+        table = self._ensure_table(active)
+        table.set_grad_pointers([p.grad for p, _ in active])
+        self._fill_scalars(table, active)
+        table.upload()
+        clip = None
+        if self.clip_max_norm is not None:
+            self.last_norm_coef = ops.grad_norm_multi(table, self.clip_max_norm, self.grad_prescale)
+            clip = self.last_norm_coef[1:2]
+        elif self.grad_prescale != 1.0:                         # data parallel without clipping: g * 1/n only
+            if self._prescale_dev is None or self._prescale_val != self.grad_prescale:
+                self._prescale_dev = torch.full((1,), self.grad_prescale, dtype=torch.float32, device=table.device)
+                self._prescale_val = self.grad_prescale
+            clip = self._prescale_dev
+        do_ema, omd = False, 0.0
+        if self.ema is not None and self.ema_step_fn is not None:
+            s = int(self.ema_step_fn())
+            do_ema, omd = self.ema.fused_schedule(s)
+        self.step_count += 1
+        ops.adamw_sr_ema_multi(table, flavor=self.flavor, seed=torch.initial_seed(), offset=self.step_count,
+                               ema_one_minus_decay=omd, do_ema=do_ema, clip_coef=clip)
+        _bump_versions([p for p, _ in active])
+        for hook in self.post_step_hooks:
+            hook()
+        return loss
+
+    @torch.no_grad()
+    def step_parameter(self, p, group, i):
+        """Per-parameter step used from post-accumulate-grad hooks (fused back pass)."""
+        if p.grad is None:
+            return
+        if p.grad.is_sparse:
+            raise RuntimeError("AdamW does not support sparse gradients")
+        st = self.opt.state[p]
+        if len(st) == 0:
+            _init_state(st, p, group)
+        key = (id(p), p.data_ptr())
+        tab = self._single.get(key)
+        if tab is None:
+            tab = ops.OptimTable([dict(p=p.data, g=p.grad, exp_avg=st["exp_avg"], exp_avg_sq=st["exp_avg_sq"])], p.device)
+            self._prepare_static(tab, [(p, group)])
+            self._single[key] = tab
+        tab.set_grad_pointers([p.grad])
+        self._fill_scalars(tab, [(p, group)])
+        tab.upload()
+        self.step_count += 1
+        ops.adamw_sr_ema_multi(tab, flavor=self.flavor, seed=torch.initial_seed(), offset=self.step_count)
+        _bump_versions([p])
+
+
+def install(optimizer, stochastic_rounding: bool, decoupled: bool, ema=None, ema_step_fn=None,
+            clip_grad_norm: float | None = None):
+    optimizer.stochastic_rounding = stochastic_rounding
+    driver = FusedAdamDriver(optimizer, decoupled)
+    driver.ema, driver.ema_step_fn, driver.clip_max_norm = ema, ema_step_fn, clip_grad_norm
+    if ema is not None:
+        ema.attach_fused_driver(driver)
+    optimizer.otb_driver = driver
+    optimizer.step = driver.step
+    optimizer.step_parameter = driver.step_parameter
+    return driver

@@ -1,0 +1,35 @@
+"""End-to-end probe on the GPU: builds a stand-in model, runs a few eager training steps on the fused
+path and prints loss + timing split.  usage: python tools/e2e_probe.py {tiny|sd15|sdxl} [batch] [steps]"""
+import sys
+import time
+import torch
+sys.path.insert(0, ".")
+from onetrainer_b200.harness import trainer
+from onetrainer_b200.modules.util.config.TrainConfig import TrainConfig
+from onetrainer_b200.modules.util.enum import LossWeight
+
+kind = sys.argv[1] if len(sys.argv) > 1 else "tiny"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+dev = torch.device("cuda:0")
+cfg = TrainConfig(batch_size=B, lora_rank=32 if kind == "sdxl" else 16, loss_weight_fn=LossWeight.MIN_SNR_GAMMA,
+                  masked_training=(kind == "sd15"))
+t0 = time.time()
+model, setup = trainer.build_model(kind, cfg, dev, ema=True, lora_up_std=0.02)
+torch.cuda.synchronize()
+print(f"built {kind}: {len(model.parameters)} LoRA tensors, {sum(p.numel() for p in model.parameters)/1e6:.2f} M params, "
+      f"{torch.cuda.memory_allocated()/2**30:.2f} GiB, {time.time()-t0:.1f}s")
+batch = trainer.batch_to_device(trainer.synthetic_batch(kind, B, dev, masked=(kind == "sd15")), dev)
+for i in range(steps):
+    torch.cuda.synchronize(); t = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss = trainer.train_step(setup, model, batch, cfg)
+    e1.record()
+    host = time.time() - t
+    torch.cuda.synchronize()
+    print(f"step {i}: loss {loss.item():.6f} host {host*1e3:.1f} ms gpu-span {e0.elapsed_time(e1):.1f} ms wall {(time.time()-t)*1e3:.1f} ms", flush=True)
+print("max mem GiB", torch.cuda.max_memory_allocated() / 2**30)
+p0 = model.parameters[0]
+print("param0 grad None after zero_grad:", p0.grad is None, "state keys", list(model.optimizer.state[p0].keys()),
+      "step", model.optimizer.state[p0]["step"].item())
