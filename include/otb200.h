@@ -56,8 +56,9 @@ extern "C" {
 #define OTB_FLAVOR_FMA_ADDCDIV      16u  /* p + a*q as fma(a, q, p)                                            */
 #define OTB_FLAVOR_FMA_ADD_ALPHA    32u  /* Adam L2: g + wd*p as fma(wd, p, g)                                 */
 #define OTB_FLAVOR_ADDCMUL_SQUARE_FIRST 64u /* v + (1-b2)*(g*g) (CUDA) vs v + ((1-b2)*g)*g (CPU)                 */
+#define OTB_FLAVOR_ALPHA_IN_DTYPE   128u /* Adam L2 on bf16 tensors: alpha itself is rounded to bf16 first (CPU) */
 /* measured with tools/probe_torch_flavor.py against torch 2.11 eager on each back-end */
-#define OTB_FLAVOR_TORCH_CPU   (OTB_FLAVOR_FMA_LERP | OTB_FLAVOR_FMA_ADDCMUL | OTB_FLAVOR_FMA_ADD_ALPHA)
+#define OTB_FLAVOR_TORCH_CPU   (OTB_FLAVOR_FMA_LERP | OTB_FLAVOR_FMA_ADDCMUL | OTB_FLAVOR_FMA_ADD_ALPHA | OTB_FLAVOR_ALPHA_IN_DTYPE)
 #define OTB_FLAVOR_TORCH_CUDA  (OTB_FLAVOR_DIV_RECIPROCAL | OTB_FLAVOR_ADDCDIV_MUL_LAST | OTB_FLAVOR_FMA_LERP | \
                                 OTB_FLAVOR_FMA_ADDCMUL | OTB_FLAVOR_FMA_ADDCDIV | OTB_FLAVOR_FMA_ADD_ALPHA | \
                                 OTB_FLAVOR_ADDCMUL_SQUARE_FIRST)

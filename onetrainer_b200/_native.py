@@ -22,7 +22,8 @@ FLAVOR_FMA_ADDCMUL = 8
 FLAVOR_FMA_ADDCDIV = 16
 FLAVOR_FMA_ADD_ALPHA = 32
 FLAVOR_ADDCMUL_SQUARE_FIRST = 64
-FLAVOR_TORCH_CPU = FLAVOR_FMA_LERP | FLAVOR_FMA_ADDCMUL | FLAVOR_FMA_ADD_ALPHA
+FLAVOR_ALPHA_IN_DTYPE = 128
+FLAVOR_TORCH_CPU = FLAVOR_FMA_LERP | FLAVOR_FMA_ADDCMUL | FLAVOR_FMA_ADD_ALPHA | FLAVOR_ALPHA_IN_DTYPE
 FLAVOR_TORCH_CUDA = (FLAVOR_DIV_RECIPROCAL | FLAVOR_ADDCDIV_MUL_LAST | FLAVOR_FMA_LERP | FLAVOR_FMA_ADDCMUL
                      | FLAVOR_FMA_ADDCDIV | FLAVOR_FMA_ADD_ALPHA | FLAVOR_ADDCMUL_SQUARE_FIRST)
 

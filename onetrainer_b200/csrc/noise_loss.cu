@@ -13,6 +13,7 @@
 // one deterministic last-block reduction per sample.  Separate torch ops in the reference are
 // separate roundings here (explicit _rn intrinsics, no contraction).
 #include "common.cuh"
+#include <stdlib.h>
 
 #define NL_THREADS 256
 #define NB1_UNROLL 2   /* groups of 4 elements per thread per iteration, K-b1 */
@@ -106,6 +107,8 @@ __device__ __forceinline__ float normal1(const otb_noise_args& a, uint32_t strea
 }
 
 // grid = (blocks_per_sample, B); each thread owns groups of 4 consecutive elements.
+// LD: compile-time latent dtype (-1 = read a.latent_dtype)
+template <int U, int LD>
 __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_args a) {
     const int b = blockIdx.y;
     const int64_t chw = (int64_t)a.C * a.hw;
@@ -124,13 +127,12 @@ __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_ar
     const bool add = a.do_add_noise != 0;
     const float cx = add ? a.coef_x0[t] : 0.0f;
     const float cn = add ? a.coef_noise[t] : 0.0f;
-    const int ldt = a.latent_dtype;
+    const int ldt = LD >= 0 ? LD : a.latent_dtype;
     const bool need_noise = a.generate_noise || a.noise_in;
     const int64_t base = (int64_t)b * chw;
 
     if ((chw & 3) == 0) {
         const int64_t ngroups = chw >> 2;
-        constexpr int U = NB1_UNROLL;
         for (int64_t g0 = (int64_t)blockIdx.x * (NL_THREADS * U) + threadIdx.x; g0 < ngroups; g0 += (int64_t)gridDim.x * (NL_THREADS * U)) {
             float x[U][4], n[U][4];
             bool live[U];
@@ -294,8 +296,11 @@ __device__ float timestep_weight(const otb_loss_args& a, int b) {
     return powf(__fadd_rn(1.0f, snr), -a.loss_weight_strength);
 }
 
-// grid = (blocks_per_sample, B)
+// grid = (blocks_per_sample, B).  PD / TD: compile-time predicted / target dtype (-1 = read a.*_dtype)
+template <int U, int PD, int TD>
 __global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args a) {
+    const int pred_dt = PD >= 0 ? PD : a.pred_dtype;
+    const int tgt_dt = TD >= 0 ? TD : a.target_dtype;
     __shared__ float sm[NL_THREADS / 32];
     __shared__ bool s_last;
     const int b = blockIdx.y;
@@ -323,8 +328,7 @@ __global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args 
     float acc = 0.0f;
     if ((chw & 3) == 0 && (a.hw & 3) == 0) {
         const int64_t ngroups = chw >> 2;
-        constexpr int U = NB2_UNROLL;
-        for (int64_t g0 = (int64_t)blockIdx.x * (NL_THREADS * U) + threadIdx.x; g0 < ngroups; g0 += (int64_t)gridDim.x * (NL_THREADS * U)) {
+                for (int64_t g0 = (int64_t)blockIdx.x * (NL_THREADS * U) + threadIdx.x; g0 < ngroups; g0 += (int64_t)gridDim.x * (NL_THREADS * U)) {
             float p[U][4], t[U][4], pt[U][4], m[U][4];
             bool live[U];
 #pragma unroll
@@ -334,9 +338,9 @@ __global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args 
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { p[u][k] = 0.0f; t[u][k] = 0.0f; pt[u][k] = 0.0f; m[u][k] = 1.0f; }
                 if (!live[u]) continue;
-                load4(a.predicted, base + i, a.pred_dtype, p[u]);
-                load4(a.target, base + i, a.target_dtype, t[u]);
-                if (prior) load4(a.prior_target, base + i, a.target_dtype, pt[u]);
+                load4(a.predicted, base + i, pred_dt, p[u]);
+                load4(a.target, base + i, tgt_dt, t[u]);
+                if (prior) load4(a.prior_target, base + i, tgt_dt, pt[u]);
                 if (masked) {
                     const int64_t mi = (int64_t)b * a.hw + (int64_t)((uint32_t)i % (uint32_t)a.hw);
                     if (a.mask_dtype == OTB_F32) {   // mask is re-read C times: keep it cacheable
@@ -377,13 +381,13 @@ __global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args 
                     acc += term;
                     g[k] = gr * gfac;
                 }
-                if (want_grad) store4(a.dpred, base + i, a.pred_dtype, g);
+                if (want_grad) store4(a.dpred, base + i, pred_dt, g);
             }
         }
     } else {
         for (int64_t i = (int64_t)blockIdx.x * NL_THREADS + threadIdx.x; i < chw; i += (int64_t)gridDim.x * NL_THREADS) {
-            const float p = load_as_float(a.predicted, base + i, a.pred_dtype);
-            const float t = load_as_float(a.target, base + i, a.target_dtype);
+            const float p = load_as_float(a.predicted, base + i, pred_dt);
+            const float t = load_as_float(a.target, base + i, tgt_dt);
             float m = 1.0f;
             if (masked) m = fminf(fmaxf(load_as_float(a.mask, (int64_t)b * a.hw + (i % a.hw), a.mask_dtype), a.unmasked_weight), 1.0f);
             const float d = __fsub_rn(p, t);
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args 
                 gr += a.mae_strength * (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * wm;
             }
             if (prior) {
-                const float dp = __fsub_rn(p, load_as_float(a.prior_target, base + i, a.target_dtype));
+                const float dp = __fsub_rn(p, load_as_float(a.prior_target, base + i, tgt_dt));
                 const float wp = __fsub_rn(1.0f, m) * k_prior;
                 term += a.mse_strength * (dp * dp) * wp;
                 gr += a.mse_strength * 2.0f * dp * wp;
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args 
                 }
             }
             acc += term;
-            if (want_grad) store_from_float(a.dpred, base + i, a.pred_dtype, gr * gfac);
+            if (want_grad) store_from_float(a.dpred, base + i, pred_dt, gr * gfac);
         }
     }
     acc = block_sum(acc, sm);
@@ -441,6 +445,14 @@ __global__ void __launch_bounds__(NL_THREADS) loss_bwd_rescale_kernel(void* dpre
         store_from_float(dpred, base + i, dtype, load_as_float(dpred, base + i, dtype) * ratio);
 }
 
+// tuning knob for A/B runs on the GPU box (unset in production: the compiled default is used)
+int tuning_unroll(const char* env, int dflt) {
+    const char* v = getenv(env);
+    if (!v) return dflt;
+    int u = atoi(v);
+    return (u == 1 || u == 2 || u == 4) ? u : dflt;
+}
+
 int blocks_per_sample_for(int64_t chw, int B, int unroll) {
     // 4*unroll elements per thread per iteration; aim at >= 4 waves of 148 SMs x 8 resident blocks when
     // the problem is large, never more blocks than there are slabs of one block-iteration.
@@ -473,8 +485,15 @@ extern "C" int otb_noise_addnoise(const otb_noise_args* a, void* stream) {
         OTB_CHECK_ARG(a->max_timestep >= a->min_timestep && a->min_timestep >= 0 && a->max_timestep <= a->num_train_timesteps,
                       "bad timestep range [%d,%d)", a->min_timestep, a->max_timestep);
     const int64_t chw = (int64_t)a->C * a->hw;
-    dim3 grid(blocks_per_sample_for(chw, a->B, NB1_UNROLL), a->B);
-    noise_addnoise_kernel<<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+    dim3 grid(blocks_per_sample_for(chw, a->B, tuning_unroll("OTB_NB1_UNROLL", NB1_UNROLL)), a->B);
+    if (a->latent_dtype == OTB_F32) {
+        const int u = tuning_unroll("OTB_NB1_UNROLL", NB1_UNROLL);
+        if (u == 1) noise_addnoise_kernel<1, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+        else if (u == 4) noise_addnoise_kernel<4, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+        else noise_addnoise_kernel<2, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+    }
+    else
+        noise_addnoise_kernel<NB1_UNROLL, -1><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
     OTB_LAUNCH_CHECK("noise_addnoise_kernel");
     return OTB_OK;
 }
@@ -493,13 +512,22 @@ extern "C" int otb_loss_fwd_bwd(const otb_loss_args* a, void* stream) {
         OTB_LAUNCH_CHECK("mask_stats_kernel");
     }
     dim3 grid(a->blocks_per_sample, a->B);
-    loss_fwd_bwd_kernel<<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+    if (a->pred_dtype == OTB_BF16 && a->target_dtype == OTB_F32) {     // the training configuration
+        const int u = tuning_unroll("OTB_NB2_UNROLL", NB2_UNROLL);
+        if (u == 1) loss_fwd_bwd_kernel<1, OTB_BF16, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+        else if (u == 2) loss_fwd_bwd_kernel<2, OTB_BF16, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+        else loss_fwd_bwd_kernel<4, OTB_BF16, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+    }
+    else if (a->pred_dtype == OTB_F32 && a->target_dtype == OTB_F32)
+        loss_fwd_bwd_kernel<NB2_UNROLL, OTB_F32, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+    else
+        loss_fwd_bwd_kernel<NB2_UNROLL, -1, -1><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
     OTB_LAUNCH_CHECK("loss_fwd_bwd_kernel");
     return OTB_OK;
 }
 
 extern "C" int otb_loss_blocks_per_sample(int32_t B, int32_t C, int32_t hw) {
-    return blocks_per_sample_for((int64_t)C * hw, B, NB2_UNROLL);
+    return blocks_per_sample_for((int64_t)C * hw, B, tuning_unroll("OTB_NB2_UNROLL", NB2_UNROLL));
 }
 
 extern "C" int otb_loss_bwd_rescale(void* dpred, int32_t dtype, const float* grad_out, float assumed,

@@ -65,9 +65,10 @@ __device__ __forceinline__ void adam_pair(const OptScalars& s, float (&p)[2], fl
     }
     if (s.has_clip) rnd2<BF16>(g[0], g[1]);
     if (s.l2 != 0.0f) {                                                 // Adam: grad.add(p, alpha=wd)
+        const float l2 = (fl & OTB_FLAVOR_ALPHA_IN_DTYPE) ? rnd<BF16>(s.l2) : s.l2;
 #pragma unroll
         for (int k = 0; k < 2; ++k)
-            g[k] = (fl & OTB_FLAVOR_FMA_ADD_ALPHA) ? __fmaf_rn(s.l2, p[k], g[k]) : __fadd_rn(g[k], __fmul_rn(s.l2, p[k]));
+            g[k] = (fl & OTB_FLAVOR_FMA_ADD_ALPHA) ? __fmaf_rn(l2, p[k], g[k]) : __fadd_rn(g[k], __fmul_rn(l2, p[k]));
         rnd2<BF16>(g[0], g[1]);
     } else {                                                            // AdamW: p.mul_(1 - lr*wd)
 #pragma unroll

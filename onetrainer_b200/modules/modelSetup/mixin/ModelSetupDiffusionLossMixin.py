@@ -35,7 +35,7 @@ class _FusedLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, predicted: Tensor, kernel_kwargs: dict):
-        want_grad = predicted.requires_grad and torch.is_grad_enabled()
+        want_grad = ctx.needs_input_grad[0]      # grad mode is off inside Function.forward: ask autograd instead
         losses, dpred = ops.loss_fwd_bwd(predicted.detach(), want_grad=want_grad, **kernel_kwargs)
         ctx.assumed = kernel_kwargs["upstream"]
         ctx.dpred = dpred

@@ -17,12 +17,16 @@ from .... import ops
 from .... import _native as N
 
 
-def _init_state(state: dict, p: torch.Tensor, group: dict) -> None:
-    """Lazy state initialisation, same tensors as adamw_extensions.py:28-48."""
+def _check_group(group: dict) -> None:
     if group.get("amsgrad"):
         raise NotImplementedError("amsgrad is not implemented on the B200 path (default off in the reference)")
     if group.get("capturable") or group.get("differentiable"):
         raise NotImplementedError("capturable/differentiable AdamW is not implemented on the B200 path")
+
+
+def _init_state(state: dict, p: torch.Tensor, group: dict) -> None:
+    """Lazy state initialisation, same tensors as adamw_extensions.py:28-48."""
+    _check_group(group)
     state["step"] = torch.tensor(0.0, dtype=torch.float32)
     state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
     state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
@@ -132,6 +136,8 @@ class FusedAdamDriver:
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        for group in self.opt.param_groups:
+            _check_group(group)
         active = self._active()
         if not active:
             return loss

@@ -38,6 +38,7 @@
 #define FL_FMA_ADDCDIV      16u
 #define FL_FMA_ADD_ALPHA    32u
 #define FL_ADDCMUL_SQUARE_FIRST 64u
+#define FL_ALPHA_IN_DTYPE   128u
 
 enum { DT_F32 = 0, DT_BF16 = 1 };
 
@@ -114,11 +115,12 @@ void otb_o_adam_step(void* p, const void* g_in, void* m, void* v, int64_t n, int
         tmp_g[i] = g;
     }
     if (s->l2 != 0.0f) {
-        /* Adam: grad = grad.add(p, alpha=weight_decay) */
+        /* Adam: grad = grad.add(p, alpha=weight_decay); torch's CPU kernel narrows alpha to the tensor dtype */
+        const float l2 = (flavor & FL_ALPHA_IN_DTYPE) ? rnd(s->l2, dt) : s->l2;
 #pragma omp parallel for
         for (i = 0; i < n; ++i) {
             float pv = ld(p, i, dt);
-            tmp_g[i] = rnd((flavor & FL_FMA_ADD_ALPHA) ? fmaf(s->l2, pv, tmp_g[i]) : tmp_g[i] + s->l2 * pv, dt);
+            tmp_g[i] = rnd((flavor & FL_FMA_ADD_ALPHA) ? fmaf(l2, pv, tmp_g[i]) : tmp_g[i] + l2 * pv, dt);
         }
     } else {
         /* AdamW: p.mul_(1 - lr * weight_decay) */

@@ -1,0 +1,219 @@
+"""numpy front-end of oracle/otb_oracle.c.
+
+TEST INFRASTRUCTURE ONLY — see the header of otb_oracle.c.  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+SRC = HERE / "otb_oracle.c"
+LIB = HERE / "_build" / "libotb_oracle.so"
+
+FL_DIV_RECIPROCAL, FL_ADDCDIV_MUL_LAST, FL_FMA_LERP, FL_FMA_ADDCMUL, FL_FMA_ADDCDIV, FL_FMA_ADD_ALPHA, FL_ADDCMUL_SQUARE_FIRST = 1, 2, 4, 8, 16, 32, 64
+FL_ALPHA_IN_DTYPE = 128
+FLAVOR_TORCH_CPU = FL_FMA_LERP | FL_FMA_ADDCMUL | FL_FMA_ADD_ALPHA | FL_ALPHA_IN_DTYPE
+FLAVOR_TORCH_CUDA = (FL_DIV_RECIPROCAL | FL_ADDCDIV_MUL_LAST | FL_FMA_LERP | FL_FMA_ADDCMUL | FL_FMA_ADDCDIV
+                     | FL_FMA_ADD_ALPHA | FL_ADDCMUL_SQUARE_FIRST)
+DT_F32, DT_BF16 = 0, 1
+TS_UNIFORM, TS_LOGIT_NORMAL, TS_HEAVY_TAIL, TS_DETERMINISTIC = 0, 1, 2, 3
+TARGET_EPSILON, TARGET_V, TARGET_FLOW = 1, 2, 3
+LW_CONSTANT, LW_MIN_SNR, LW_DEBIASED, LW_P2, LW_SIGMA = range(5)
+
+
+def build(force: bool = False) -> Path:
+    LIB.parent.mkdir(exist_ok=True)
+    if force or not LIB.exists() or LIB.stat().st_mtime < SRC.stat().st_mtime:
+        subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-fno-fast-math",
+                        "-o", str(LIB), str(SRC), "-lm"], check=True)
+    return LIB
+
+
+class AdamScalars(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("decay_mul", "l2", "lerp_w", "beta2", "one_minus_beta2", "bc2_sqrt",
+                                         "inv_bc2_sqrt", "eps", "neg_step_size")]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(LIB))
+        _lib.otb_o_sqsum.restype = C.c_double
+        _lib.otb_o_timestep.restype = C.c_int32
+        _lib.otb_o_timestep_from_draw.restype = C.c_int32
+        _lib.otb_o_timestep_weight.restype = C.c_float
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def set_threads(n: int) -> None:
+    os.environ["OMP_NUM_THREADS"] = str(n)
+
+
+# ---- Philox -------------------------------------------------------------------------------------
+def philox(seed: int, offset: int, stream: int, group: int) -> np.ndarray:
+    out = np.zeros(4, dtype=np.uint32)
+    lib().otb_o_philox(C.c_uint64(seed), C.c_uint64(offset), C.c_uint32(stream), C.c_uint64(group), _p(out))
+    return out
+
+
+def philox_raw(ctr, key) -> np.ndarray:
+    c = np.asarray(ctr, dtype=np.uint32)
+    k = np.asarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    lib().otb_o_philox_raw(_p(c), _p(k), _p(out))
+    return out
+
+
+def sr_bits(seed: int, offset: int, first_elem: int, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.int32)
+    lib().otb_o_sr_bits(C.c_uint64(seed), C.c_uint64(offset), C.c_int64(first_elem), C.c_int64(n), _p(out))
+    return out
+
+
+# ---- bf16 helpers (numpy has no bf16: carried as uint16) -------------------------------------
+def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    nan = (u & 0x7FFFFFFF) > 0x7F800000
+    r = ((u + (0x7FFF + ((u >> 16) & 1))) >> 16).astype(np.uint16)
+    r[nan] = 0x7FC0
+    return r
+
+
+def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
+    return (b.astype(np.uint32) << 16).view(np.float32)
+
+
+# ---- optimizer -------------------------------------------------------------------------------------
+def adam_scalars(lr, beta1, beta2, eps, weight_decay, step, decoupled=True) -> AdamScalars:
+    """python-double -> fp32 narrowing exactly as adamw_extensions.py:83-132 + torch's scalar casts."""
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    step_size = lr / bc1
+    bc2_sqrt = math.sqrt(bc2)
+    f = np.float32
+    return AdamScalars(float(f(1 - lr * weight_decay)) if decoupled else 1.0, 0.0 if decoupled else float(f(weight_decay)),
+                       float(f(1 - beta1)), float(f(beta2)), float(f(1 - beta2)), float(f(bc2_sqrt)),
+                       float(f(1.0) / f(bc2_sqrt)), float(f(eps)), float(f(-step_size)))
+
+
+def adam_step(p, g, m, v, dt, scalars: AdamScalars, flavor=FLAVOR_TORCH_CPU, sr=False, maximize=False, seed=0, offset=0,
+              rng_base=0, clip_coef=None) -> None:
+    """In place on contiguous numpy arrays (float32, or uint16 carrying bf16 bits)."""
+    n = p.size
+    tg = np.empty(n, dtype=np.float32)
+    td = np.empty(n, dtype=np.float32)
+    lib().otb_o_adam_step(_p(p), _p(g), _p(m), _p(v), C.c_int64(n), C.c_int(dt), C.byref(scalars), C.c_uint32(flavor),
+                          C.c_int(int(sr)), C.c_int(int(maximize)), C.c_uint64(seed), C.c_uint64(offset), C.c_int64(rng_base),
+                          C.c_int(0 if clip_coef is None else 1), C.c_float(0.0 if clip_coef is None else clip_coef),
+                          _p(tg), _p(td))
+
+
+def ema_step(ema, p, dt, one_minus_decay: float) -> None:
+    lib().otb_o_ema_step(_p(ema), _p(p), C.c_int64(p.size), C.c_int(dt), C.c_float(one_minus_decay))
+
+
+def grad_norm(grads: list[np.ndarray], dt=DT_F32) -> float:
+    return math.sqrt(sum(lib().otb_o_sqsum(_p(g), C.c_int64(g.size), C.c_int(dt)) for g in grads))
+
+
+def clip_coef(total_norm: float, max_norm: float) -> float:
+    c = np.float32(max_norm) / (np.float32(total_norm) + np.float32(1e-6))
+    return float(min(c, np.float32(1.0)))
+
+
+# ---- timesteps / noise -----------------------------------------------------------------------------
+def timestep(mode, seed, offset, global_sample, T=1000, min_t=0, max_t=1000, noising_weight=0.0, noising_bias=0.0, shift=1.0) -> int:
+    return int(lib().otb_o_timestep(C.c_int(mode), C.c_uint64(seed), C.c_uint64(offset), C.c_int64(global_sample), C.c_int(T),
+                                    C.c_int(min_t), C.c_int(max_t), C.c_float(noising_weight), C.c_float(noising_bias),
+                                    C.c_float(float(T * shift)), C.c_float(float(shift - 1))))
+
+
+def timestep_from_draw(mode, draw, T=1000, min_t=0, max_t=1000, noising_weight=0.0, noising_bias=0.0, shift=1.0) -> int:
+    return int(lib().otb_o_timestep_from_draw(C.c_int(mode), C.c_float(draw), C.c_int(T), C.c_int(min_t), C.c_int(max_t),
+                                              C.c_float(noising_weight), C.c_float(noising_bias),
+                                              C.c_float(float(T * shift)), C.c_float(float(shift - 1))))
+
+
+def create_noise(B, Cc, hw, offset_w=0.0, perturb_w=0.0, seed=0, offset=0, sample_base=0) -> np.ndarray:
+    out = np.empty((B, Cc * hw), dtype=np.float32)
+    lib().otb_o_create_noise(_p(out), C.c_int(B), C.c_int(Cc), C.c_int(hw), C.c_float(offset_w), C.c_float(perturb_w),
+                             C.c_uint64(seed), C.c_uint64(offset), C.c_int64(sample_base))
+    return out
+
+
+def add_noise(latent, noise, timestep_, coef_x0, coef_noise, latent_scale=1.0, latent_shift=0.0, target=TARGET_EPSILON):
+    latent = np.ascontiguousarray(latent, dtype=np.float32)
+    noise = np.ascontiguousarray(noise, dtype=np.float32)
+    ts = np.ascontiguousarray(timestep_, dtype=np.int32)
+    B = latent.shape[0]
+    chw = latent.size // B
+    x0, noisy, tgt = np.empty_like(latent), np.empty_like(latent), np.empty_like(latent)
+    lib().otb_o_add_noise(_p(latent), _p(noise), _p(ts), _p(np.ascontiguousarray(coef_x0, dtype=np.float32)),
+                          _p(np.ascontiguousarray(coef_noise, dtype=np.float32)), C.c_int(B), C.c_int64(chw),
+                          C.c_float(latent_scale), C.c_float(latent_shift), C.c_int(target), _p(x0), _p(noisy), _p(tgt))
+    return x0, noisy, tgt
+
+
+# ---- losses --------------------------------------------------------------------------------------
+def losses(pred, target, *, prior=None, mask=None, loss_weight=None, timestep_=None, sqrt_ac=None, sqrt_1mac=None, sigmas=None,
+           C_=1, masked=False, normalize=False, lw_fn=LW_CONSTANT, v_pred=False, mse=1.0, mae=0.0, unmasked_weight=0.1,
+           prior_w=0.0, loss_scale=1.0, gamma=5.0, upstream=1.0, want_grad=True):
+    pred = np.ascontiguousarray(pred, dtype=np.float32)
+    target = np.ascontiguousarray(target, dtype=np.float32)
+    B = pred.shape[0]
+    hw = pred.size // B // C_
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)  # noqa: E731
+    prior, mask, loss_weight, sqrt_ac, sqrt_1mac, sigmas = map(f32, (prior, mask, loss_weight, sqrt_ac, sqrt_1mac, sigmas))
+    ts = None if timestep_ is None else np.ascontiguousarray(timestep_, dtype=np.int32)
+    out = np.empty(B, dtype=np.float32)
+    dp = np.empty_like(pred) if want_grad else None
+    lib().otb_o_losses(_p(pred), _p(target), _p(prior), _p(mask), _p(loss_weight), _p(ts), _p(sqrt_ac), _p(sqrt_1mac), _p(sigmas),
+                       C.c_int(B), C.c_int(C_), C.c_int(hw), C.c_int(int(masked)), C.c_int(int(normalize)), C.c_int(lw_fn),
+                       C.c_int(int(v_pred)), C.c_float(mse), C.c_float(mae), C.c_float(unmasked_weight), C.c_float(prior_w),
+                       C.c_float(loss_scale), C.c_float(gamma), C.c_float(upstream), _p(out), _p(dp))
+    return out, dp
+
+
+# ---- LoRA linear ---------------------------------------------------------------------------------
+def lora_linear(x, w, down, up, bias, scale, round_t_bf16=True):
+    x, w = (np.ascontiguousarray(a, dtype=np.float32) for a in (x, w))
+    M, K = x.shape
+    Nn = w.shape[0]
+    R = 0 if down is None else down.shape[0]
+    down = None if down is None else np.ascontiguousarray(down, dtype=np.float32)
+    up = None if up is None else np.ascontiguousarray(up, dtype=np.float32)
+    bias = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+    y = np.empty((M, Nn), dtype=np.float32)
+    t = np.empty((M, max(R, 1)), dtype=np.float32)
+    lib().otb_o_lora_linear(_p(x), _p(w), _p(down), _p(up), _p(bias), C.c_int(M), C.c_int(Nn), C.c_int(K), C.c_int(R),
+                            C.c_float(scale), C.c_int(int(round_t_bf16)), _p(y), _p(t))
+    return y, t[:, :R]
+
+
+def lora_backward(x, dy, w, down, up, scale, round_bf16=True):
+    """dx, dA, dB of y = x w^T + (s x down^T) up^T  (SURVEY.md §3.4), fp64 accumulate via numpy."""
+    x64, dy64, w64, a64, b64 = (np.asarray(a, dtype=np.float64) for a in (x, dy, w, down, up))
+    t = scale * (x64 @ a64.T)
+    g = scale * (dy64 @ b64)
+    if round_bf16:
+        t = bf16_bits_to_f32(f32_to_bf16_bits(t.astype(np.float32))).astype(np.float64)
+        g = bf16_bits_to_f32(f32_to_bf16_bits(g.astype(np.float32))).astype(np.float64)
+    dx = dy64 @ w64 + g @ a64
+    dA = g.T @ x64
+    dB = dy64.T @ t
+    return dx.astype(np.float32), dA.astype(np.float32), dB.astype(np.float32)

@@ -1,0 +1,242 @@
+"""Host-side mirror of the reference seams: API shape, state-dict keys, error behaviour, scalar derivation.
+Runs on CPU (no kernel is launched)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from onetrainer_b200.modules.module.EMAModule import EMAModuleWrapper
+from onetrainer_b200.modules.module.LoRAModule import DummyLoRAModule, LoRAModule, LoRAModuleWrapper
+from onetrainer_b200.modules.util.config.TrainConfig import TrainConfig
+from onetrainer_b200.modules.util.convert.rescale_noise_scheduler_to_zero_terminal_snr import rescale_noise_scheduler_to_zero_terminal_snr
+from onetrainer_b200.modules.util.DiffusionScheduleCoefficients import DiffusionScheduleCoefficients, flow_sigmas, scaled_linear_betas
+from onetrainer_b200.modules.util.enum import LossWeight, PeftType, TimestepDistribution, enum_name
+
+
+def test_schedule_tables_match_reference_bit_for_bit(golden):
+    """DiffusionScheduleCoefficients.from_betas (reference :36-60) and the diffusers scaled-linear betas."""
+    g = golden("schedule")
+    betas = scaled_linear_betas()
+    assert np.array_equal(betas.numpy(), g["betas"])
+    co = DiffusionScheduleCoefficients.from_betas(betas)
+    assert np.array_equal(co.alphas_cumprod.numpy(), g["alphas_cumprod"])
+    assert np.array_equal(co.sqrt_alphas_cumprod.numpy(), g["sqrt_ac"])
+    assert np.array_equal(co.sqrt_one_minus_alphas_cumprod.numpy(), g["sqrt_1mac"])
+    # SURVEY.md §8c known answers
+    assert abs(g["sqrt_ac"][499] - 0.52694350) < 1e-7 and abs(g["sqrt_1mac"][999] - 0.99766725) < 1e-7
+
+
+def test_zero_terminal_snr_rescale_matches_reference(golden):
+    g = golden("schedule")
+
+    class Sched:
+        alphas_cumprod = torch.from_numpy(g["alphas_cumprod"].copy())
+
+    s = Sched()
+    betas = rescale_noise_scheduler_to_zero_terminal_snr(s)
+    assert np.array_equal(betas.numpy(), g["zt_betas"])
+    assert np.array_equal(s.alphas_cumprod.numpy(), g["zt_alphas_cumprod"])
+    assert s.alphas_cumprod[-1].item() == 0.0            # zero terminal SNR
+
+
+def test_flow_sigmas(golden):
+    sigma, one_minus = flow_sigmas(1000, "cpu")
+    t = golden("addnoise")["t"]
+    assert np.array_equal(sigma.numpy()[t], golden("addnoise")["flow_sigmas"])
+    assert sigma[0].item() == pytest.approx(0.001) and sigma[499].item() == 0.5 and one_minus[999].item() == 0.0
+
+
+def test_enum_interop_with_reference_style_enums():
+    from enum import Enum
+
+    class RefStyle(Enum):       # same shape as /root/reference/modules/util/enum/LossWeight.py
+        MIN_SNR_GAMMA = "MIN_SNR_GAMMA"
+
+        def __str__(self):
+            return self.value
+
+    assert enum_name(RefStyle.MIN_SNR_GAMMA) == enum_name(LossWeight.MIN_SNR_GAMMA) == enum_name("MIN_SNR_GAMMA")
+    assert str(TimestepDistribution.LOGIT_NORMAL) == "LOGIT_NORMAL"
+
+
+def _net():
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.to_q = nn.Linear(32, 48)
+            self.proj = nn.Conv2d(8, 16, 1)
+            self.conv3 = nn.Conv2d(8, 8, 3, padding=1)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.attentions = nn.ModuleList([Block()])
+            self.other = nn.Linear(4, 4)
+
+    return Net()
+
+
+def test_wrapper_selects_leaves_by_substring_and_keeps_state_dict_keys(golden):
+    cfg = TrainConfig(lora_rank=16, lora_alpha=8.0)
+    net = _net()
+    w = LoRAModuleWrapper(net, "lora_unet", cfg, ["attentions.0.to_q", " attentions.0.proj "])   # filters are stripped
+    assert sorted(w.lora_modules) == ["attentions.0.proj", "attentions.0.to_q"]
+    keys = sorted(w.state_dict())
+    assert keys == ["lora_unet.attentions.0.proj.alpha", "lora_unet.attentions.0.proj.lora_down.weight",
+                    "lora_unet.attentions.0.proj.lora_up.weight", "lora_unet.attentions.0.to_q.alpha",
+                    "lora_unet.attentions.0.to_q.lora_down.weight", "lora_unet.attentions.0.to_q.lora_up.weight"]
+    # same key shape the reference module produced in the fixture
+    assert list(golden("lora")["linear_keys"]) == ["lora_unet.x.alpha", "lora_unet.x.lora_down.weight", "lora_unet.x.lora_up.weight"]
+    m = w.lora_modules["attentions.0.to_q"]
+    assert tuple(m.lora_down.weight.shape) == (16, 32) and tuple(m.lora_up.weight.shape) == (48, 16)
+    assert torch.count_nonzero(m.lora_up.weight) == 0                      # up = 0 at init
+    bound = 1 / math.sqrt(32)                                              # kaiming_uniform(a=sqrt(5)) bound
+    assert m.lora_down.weight.abs().max() <= bound
+    assert float(m.alpha) == 8.0 and not m.alpha.requires_grad
+    c = w.lora_modules["attentions.0.proj"]
+    assert tuple(c.lora_down.weight.shape) == (16, 8, 1, 1) and tuple(c.lora_up.weight.shape) == (16, 16, 1, 1)
+    assert len(w.parameters()) == 4
+
+
+def test_empty_filter_selects_everything_supported_and_unsupported_layers_raise():
+    cfg = TrainConfig()
+    with pytest.raises(NotImplementedError, match="1x1"):
+        LoRAModuleWrapper(_net(), "lora_unet", cfg, [""])                   # "" matches the 3x3 conv too
+    with pytest.raises(NotImplementedError):
+        LoRAModuleWrapper(_net(), "lora_unet", TrainConfig(lora_decompose=True), ["to_q"])     # DoRA
+    with pytest.raises(NotImplementedError):
+        LoRAModuleWrapper(_net(), "lora_unet", TrainConfig(peft_type=PeftType.LOHA), ["to_q"])
+    with pytest.raises(NotImplementedError, match="Only Linear and Conv2d"):
+        LoRAModule("p", nn.LayerNorm(4), 8, 1.0)
+
+
+def test_hook_swaps_and_restores_forward_train_eval():
+    net = _net()
+    lin = net.attentions[0].to_q
+    w = LoRAModuleWrapper(net, "lora_unet", TrainConfig(), ["to_q"])
+    orig_forward = lin.forward
+    w.hook_to_module()
+    m = w.lora_modules["attentions.0.to_q"]
+    assert lin.forward == m.forward and m.is_applied
+    lin.eval()
+    assert not m.training and not lin.training
+    lin.train()
+    assert m.training
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lin(torch.randn(2, 32))                                            # product path refuses CPU tensors loudly
+    w.remove_hook_from_module()
+    assert lin.forward == orig_forward and not m.is_applied
+    assert lin(torch.randn(2, 32)).shape == (2, 48)
+
+
+def test_load_state_dict_prefix_filter_and_dummies():
+    cfg = TrainConfig(lora_rank=8)
+    w1 = LoRAModuleWrapper(_net(), "lora_unet", cfg, ["to_q"])
+    sd = {k: torch.randn_like(v) for k, v in w1.state_dict().items()}
+    sd["lora_unet.somewhere.else.alpha"] = torch.tensor(4.0)
+    sd["lora_unet.somewhere.else.lora_down.weight"] = torch.randn(8, 4)
+    sd["lora_te1.ignored.alpha"] = torch.tensor(1.0)
+    w2 = LoRAModuleWrapper(_net(), "lora_unet", cfg, ["to_q"])
+    w2.load_state_dict(sd)
+    out = w2.state_dict()
+    for k in w1.state_dict():
+        assert torch.equal(out[k], sd[k])
+    assert "lora_unet.somewhere.else.alpha" in out and "lora_te1.ignored.alpha" not in out     # kept by a dummy
+    assert isinstance(w2.lora_modules["lora_unet.somewhere.else"], DummyLoRAModule)
+    w2.prune()
+    assert "lora_unet.somewhere.else.alpha" not in w2.state_dict()
+    with pytest.raises(ValueError):
+        w2.set_dropout(1.5)
+    w2.set_dropout(0.25)
+    assert all(m.dropout.p == 0.25 for m in w2.lora_modules.values())
+
+
+def test_uninitialised_module_raises_like_the_reference():
+    d = DummyLoRAModule("x", None, 8, 1.0)
+    with pytest.raises(RuntimeError, match="state dict must be loaded"):
+        d.state_dict()
+    with pytest.raises(NotImplementedError):
+        d.hook_to_module()
+
+
+def test_ema_wrapper_api_and_state_dict():
+    ps = [nn.Parameter(torch.randn(5)), nn.Parameter(torch.randn(3, 2))]
+    ema = EMAModuleWrapper(ps, decay=0.999, update_step_interval=5, device=torch.device("cpu"))
+    assert [e.shape for e in ema.ema_parameters] == [p.shape for p in ps]
+    assert ema.get_current_decay(0) == 0.1 and ema.get_current_decay(10 ** 6) == 0.999
+    sd = ema.state_dict()
+    assert set(sd) == {"decay", "ema_parameters"} and sd["decay"] == 0.999
+    with torch.no_grad():
+        for p in ps:
+            p.add_(1.0)
+    ema.copy_ema_to(ps, store_temp=True)
+    assert torch.equal(ps[0].data, ema.ema_parameters[0])
+    ema.copy_temp_to(ps)
+    assert ema.temp_stored_parameters is None        # (on CPU `.cpu()` aliases, exactly as in the reference)
+    with pytest.raises(ValueError):
+        ema.step(ps[:1], 4)                                                # strict zip, as the reference
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ema.step(ps, 4)                                                    # same-device EMA needs the CUDA kernel
+
+
+def test_adam_scalars_narrowing_matches_oracle():
+    from onetrainer_b200 import ops
+    from oracle import otb_oracle as O
+    for step in (1.0, 2.0, 1000.0):
+        a = ops.adam_scalars(3e-4, 0.9, 0.999, 1e-8, 1e-2, step, True)
+        b = O.adam_scalars(3e-4, 0.9, 0.999, 1e-8, 1e-2, step, True)
+        for k in a:
+            assert np.float32(a[k]) == np.float32(getattr(b, k)), k
+    l2 = ops.adam_scalars(1e-3, 0.9, 0.99, 1e-8, 0.05, 3.0, False)
+    assert l2["decay_mul"] == 1.0 and l2["l2"] == np.float32(0.05)
+
+
+def test_patch_adamw_contract_and_unsupported_options():
+    from onetrainer_b200.modules.util.optimizer.adam_extensions import patch_adam
+    from onetrainer_b200.modules.util.optimizer.adamw_extensions import patch_adamw
+    p = nn.Parameter(torch.zeros(8))
+    opt = torch.optim.AdamW([p], lr=1e-3)
+    patch_adamw(opt, True)
+    assert opt.stochastic_rounding is True and callable(opt.step_parameter)
+    assert opt.step() is None                                              # nothing has a gradient: no launch, no error
+    assert opt.step(lambda: 1.5) == 1.5                                    # closure contract
+    p.grad = torch.ones(8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        opt.step()
+    opt2 = torch.optim.Adam([nn.Parameter(torch.zeros(8))], amsgrad=True)
+    patch_adam(opt2, False)
+    opt2.param_groups[0]["params"][0].grad = torch.ones(8)
+    with pytest.raises(NotImplementedError, match="amsgrad"):
+        opt2.step()
+
+
+def test_timestep_kernel_args_follow_python_semantics():
+    from onetrainer_b200.modules.modelSetup.mixin.ModelSetupNoiseMixin import timestep_kernel_args, timestep_shift
+    cfg = TrainConfig(min_noising_strength=0.1234, max_noising_strength=0.9, timestep_shift=3.0)
+    kw = timestep_kernel_args(1000, False, cfg)
+    assert kw["min_timestep"] == int(1000 * 0.1234) == 123 and kw["max_timestep"] == 900 and kw["shift"] == 3.0
+    dyn = TrainConfig(dynamic_timestep_shifting=True)
+    with pytest.raises(NotImplementedError, match="Dynamic timestep shifting"):
+        timestep_shift(dyn, None, None)
+    mu = 4096 * ((1.15 - 0.5) / (4096 - 256)) + (0.5 - ((1.15 - 0.5) / (4096 - 256)) * 256)
+    assert timestep_shift(dyn, 128, 128) == pytest.approx(math.exp(mu)) == pytest.approx(math.exp(1.15))
+    assert timestep_kernel_args(1000, True, cfg)["ts_mode"] == 3
+
+
+def test_loss_mixin_rejects_out_of_scope_terms():
+    from onetrainer_b200.modules.modelSetup.mixin.ModelSetupDiffusionLossMixin import ModelSetupDiffusionLossMixin
+
+    class S(ModelSetupDiffusionLossMixin):
+        pass
+
+    data = {"loss_type": "target", "predicted": torch.zeros(1, 4, 2, 2), "target": torch.zeros(1, 4, 2, 2)}
+    batch = {"loss_weight": torch.ones(1)}
+    with pytest.raises(NotImplementedError, match="log-cosh"):
+        S()._diffusion_losses(batch, data, TrainConfig(log_cosh_strength=0.5), torch.device("cpu"))
+    with pytest.raises(NotImplementedError, match="VB loss"):
+        S()._diffusion_losses(batch, dict(data, predicted_var_values=torch.zeros(1)), TrainConfig(), torch.device("cpu"))
+    with pytest.raises(NotImplementedError, match="alphas_cumprod_fun"):
+        S()._diffusion_losses(batch, dict(data, timestep=torch.zeros(1, dtype=torch.int32)),
+                              TrainConfig(loss_weight_fn=LossWeight.MIN_SNR_GAMMA), torch.device("cpu"), alphas_cumprod_fun=lambda t, d: t)

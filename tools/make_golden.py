@@ -1,0 +1,344 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (sangoi-exe/OneTrainer) on CPU.
+
+Runs only in the build container (needs /root/reference); the fixtures it writes are committed and
+are what travels to the GPU box.  Two shims make the reference's hot-path modules importable here
+(SURVEY.md F7): a `sys.modules["accelerate"]` stub and an alias for the renamed
+`Optimizer._cuda_graph_capture_health_check`; a `diffusers` stub satisfies one type-hint import.
+No reference arithmetic is rewritten.
+
+Where the reference draws random numbers, the draws are REPLACED by this repo's Philox stream
+(torch.rand / torch.normal / torch.randint_like patched for the duration of one call), so the
+fixtures pin the deterministic transforms after the draw — the part that has to match bit for bit.
+
+    python tools/make_golden.py            # writes tests/golden/
+"""
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+
+import transformers  # noqa: E402,F401  (must be imported before the accelerate stub)
+import torch  # noqa: E402
+
+acc = types.ModuleType("accelerate")
+
+
+class _Accelerator:
+    def __init__(self, *a, **k):
+        self.device = torch.device("cpu")
+
+
+acc.Accelerator = _Accelerator
+sys.modules["accelerate"] = acc
+dif = types.ModuleType("diffusers")
+dif.DDIMScheduler = object
+sys.modules.setdefault("diffusers", dif)
+sys.path.insert(0, "/root/reference")
+if not hasattr(torch.optim.Optimizer, "_cuda_graph_capture_health_check"):
+    torch.optim.Optimizer._cuda_graph_capture_health_check = torch.optim.Optimizer._accelerator_graph_capture_health_check
+
+from modules.modelSetup.mixin.ModelSetupDiffusionLossMixin import ModelSetupDiffusionLossMixin  # noqa: E402
+from modules.modelSetup.mixin.ModelSetupDiffusionMixin import ModelSetupDiffusionMixin  # noqa: E402
+from modules.modelSetup.mixin.ModelSetupFlowMatchingMixin import ModelSetupFlowMatchingMixin  # noqa: E402
+from modules.modelSetup.mixin.ModelSetupNoiseMixin import ModelSetupNoiseMixin  # noqa: E402
+from modules.module.EMAModule import EMAModuleWrapper  # noqa: E402
+from modules.module.LoRAModule import LoRAModule  # noqa: E402
+from modules.util.bf16_stochastic_rounding import copy_stochastic_  # noqa: E402,F401
+from modules.util.config.TrainConfig import TrainConfig  # noqa: E402
+from modules.util.convert.rescale_noise_scheduler_to_zero_terminal_snr import rescale_noise_scheduler_to_zero_terminal_snr  # noqa: E402
+from modules.util.DiffusionScheduleCoefficients import DiffusionScheduleCoefficients  # noqa: E402
+from modules.util.enum.LossScaler import LossScaler  # noqa: E402
+from modules.util.enum.LossWeight import LossWeight  # noqa: E402
+from modules.util.enum.TimestepDistribution import TimestepDistribution  # noqa: E402
+from modules.util.optimizer.adam_extensions import patch_adam  # noqa: E402
+from modules.util.optimizer.adamw_extensions import patch_adamw  # noqa: E402
+
+from oracle import otb_oracle as O  # noqa: E402
+
+OUT = REPO / "tests" / "golden"
+OUT.mkdir(parents=True, exist_ok=True)
+torch.set_num_threads(1)
+
+
+def bits16(t: torch.Tensor) -> np.ndarray:
+    return t.detach().contiguous().view(torch.int16).numpy().view(np.uint16).copy()
+
+
+def scaled_linear_betas():
+    return torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2
+
+
+# ------------------------------------------------------------------------------------ schedule
+def gen_schedule():
+    betas = scaled_linear_betas()
+    co = DiffusionScheduleCoefficients.from_betas(betas)
+
+    class Sched:
+        pass
+
+    s = Sched()
+    s.alphas_cumprod = torch.cumprod(1 - betas, 0)
+    zt_betas = rescale_noise_scheduler_to_zero_terminal_snr(s)
+    np.savez(OUT / "schedule.npz", betas=betas.numpy(), alphas_cumprod=co.alphas_cumprod.numpy(),
+             sqrt_ac=co.sqrt_alphas_cumprod.numpy(), sqrt_1mac=co.sqrt_one_minus_alphas_cumprod.numpy(),
+             zt_betas=zt_betas.numpy(), zt_alphas_cumprod=s.alphas_cumprod.numpy())
+
+
+# ------------------------------------------------------------------------------------ optimizer
+def gen_optimizer():
+    out = {}
+    n = 4099                      # not a multiple of 8: exercises the SR tail lanes
+    lr, betas, eps, wd = 3e-4, (0.9, 0.999), 1e-8, 1e-2
+    for name, dtype, sr, patch, cls in (("adamw_f32", torch.float32, False, patch_adamw, torch.optim.AdamW),
+                                        ("adamw_bf16", torch.bfloat16, False, patch_adamw, torch.optim.AdamW),
+                                        ("adamw_bf16_sr", torch.bfloat16, True, patch_adamw, torch.optim.AdamW),
+                                        ("adam_f32", torch.float32, False, patch_adam, torch.optim.Adam),
+                                        ("adam_bf16_sr", torch.bfloat16, True, patch_adam, torch.optim.Adam)):
+        g = torch.Generator().manual_seed(11)
+        p = torch.nn.Parameter((torch.randn(n, generator=g) * 0.02).to(dtype))
+        opt = cls([p], lr=lr, betas=betas, eps=eps, weight_decay=wd)
+        patch(opt, sr)
+        seed, rng_base = 0xC0FFEE, 24
+        out[f"{name}_p0"] = bits16(p) if dtype == torch.bfloat16 else p.detach().numpy().copy()
+        for step in range(1, 4):
+            grad = (torch.randn(n, generator=g) * 1e-3).to(dtype)
+            p.grad = grad.clone()
+            out[f"{name}_g{step}"] = bits16(grad) if dtype == torch.bfloat16 else grad.numpy().copy()
+            orig = torch.randint_like
+            if sr:
+                def fake_randint_like(src, dtype=None, low=0, high=0, _step=step):
+                    assert low == 0 and high == (1 << 16) and dtype == torch.int32
+                    return torch.from_numpy(O.sr_bits(seed, _step, rng_base, src.numel()).copy()).view(src.shape)
+                torch.randint_like = fake_randint_like
+            try:
+                opt.step_parameter(p, opt.param_groups[0], 0)
+            finally:
+                torch.randint_like = orig
+            st = opt.state[p]
+            for key, t in (("p", p), ("m", st["exp_avg"]), ("v", st["exp_avg_sq"])):
+                out[f"{name}_{key}{step}"] = bits16(t) if dtype == torch.bfloat16 else t.detach().numpy().copy()
+        out[f"{name}_meta"] = np.array([lr, betas[0], betas[1], eps, wd, seed, rng_base], dtype=np.float64)
+    # the KAT of SURVEY.md §8c: 1e5 copies of 1 + 2^-10 through the reference's own copy_stochastic_
+    torch.manual_seed(0)
+    src = torch.full((100000,), 1 + 2 ** -10, dtype=torch.float32)
+    tgt = torch.empty(100000, dtype=torch.bfloat16)
+    copy_stochastic_(tgt, src)
+    out["sr_kat_mean"] = np.array([tgt.float().mean().item()])
+    np.savez(OUT / "optimizer.npz", **out)
+
+
+# ------------------------------------------------------------------------------------ EMA
+def gen_ema():
+    out = {}
+    for name, dtype in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+        g = torch.Generator().manual_seed(5)
+        p = torch.nn.Parameter((torch.randn(1003, generator=g) * 0.05).to(dtype))
+        ema = EMAModuleWrapper([p], decay=0.999, update_step_interval=2, device=torch.device("cpu"))
+        enc = bits16 if dtype == torch.bfloat16 else (lambda t: t.detach().numpy().copy())
+        out[f"{name}_ema0"] = enc(ema.ema_parameters[0])
+        for step in range(6):
+            with torch.no_grad():
+                p.add_((torch.randn(1003, generator=g) * 0.01).to(dtype))
+            out[f"{name}_p{step}"] = enc(p)
+            ema.step([p], step)
+            out[f"{name}_ema{step + 1}"] = enc(ema.ema_parameters[0])
+            out[f"{name}_decay{step}"] = np.array([ema.get_current_decay(step)])
+    np.savez(OUT / "ema.npz", **out)
+
+
+# ------------------------------------------------------------------------------------ timesteps
+class _Noise(ModelSetupNoiseMixin):
+    pass
+
+
+def gen_timesteps():
+    out = {}
+    B = 64
+    cases = [
+        ("uniform", TimestepDistribution.UNIFORM, dict()),
+        ("uniform_range_shift3", TimestepDistribution.UNIFORM, dict(min_noising_strength=0.1, max_noising_strength=0.9, timestep_shift=3.0)),
+        ("logit_normal", TimestepDistribution.LOGIT_NORMAL, dict()),
+        ("logit_normal_biased", TimestepDistribution.LOGIT_NORMAL, dict(noising_weight=0.5, noising_bias=-0.3, timestep_shift=2.0)),
+        ("logit_normal_dynamic", TimestepDistribution.LOGIT_NORMAL, dict(dynamic_timestep_shifting=True)),
+        ("heavy_tail", TimestepDistribution.HEAVY_TAIL, dict(noising_weight=1.2)),
+    ]
+    for name, dist, kw in cases:
+        cfg = TrainConfig.default_values()
+        cfg.timestep_distribution = dist
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        seed, offset = 77, 4
+        # the draws this repo's kernel would make for global samples 0..B-1
+        u = np.zeros(B, dtype=np.float32)
+        for b in range(B):
+            r = O.philox(seed, offset, 3, b)
+            if dist == TimestepDistribution.LOGIT_NORMAL:
+                u1 = (float(r[0] >> 8) + 0.5) * 2.0 ** -24
+                th = (float(np.int32(r[1]) >> 8) + 0.5) * 2.0 ** -23 * np.pi
+                z = np.float32(np.sqrt(-2.0 * np.log(u1)) * np.cos(th))
+                scale = np.float32(cfg.noising_weight) + np.float32(1.0)
+                u[b] = np.float32(z * scale) + np.float32(cfg.noising_bias)
+            else:
+                u[b] = np.float32(r[0] >> 8) * np.float32(2.0 ** -24)
+        draws = torch.from_numpy(u.copy())
+        orig_rand, orig_normal = torch.rand, torch.normal
+        torch.rand = lambda *a, **k: draws.clone()
+        torch.normal = lambda *a, **k: draws.clone()
+        try:
+            gen = torch.Generator().manual_seed(0)
+            ts = _Noise()._get_timestep_discrete(1000, False, gen, B, cfg, latent_width=128, latent_height=128)
+        finally:
+            torch.rand, torch.normal = orig_rand, orig_normal
+        out[f"{name}_draws"] = u
+        out[f"{name}_t"] = ts.numpy().astype(np.int32)
+        out[f"{name}_cfg"] = np.array([cfg.min_noising_strength, cfg.max_noising_strength, cfg.noising_weight, cfg.noising_bias,
+                                       cfg.timestep_shift, float(cfg.dynamic_timestep_shifting), seed, offset], dtype=np.float64)
+    det = _Noise()._get_timestep_discrete(1000, True, torch.Generator(), 4, TrainConfig.default_values())
+    out["deterministic_t"] = det.numpy()
+    np.savez(OUT / "timesteps.npz", **out)
+
+
+# ------------------------------------------------------------------------------------ add noise
+class _Diff(ModelSetupDiffusionMixin):
+    pass
+
+
+class _Flow(ModelSetupFlowMatchingMixin):
+    pass
+
+
+def gen_addnoise():
+    g = torch.Generator().manual_seed(3)
+    B, Cc, H, W = 4, 4, 16, 16
+    latent = torch.randn(B, Cc, H, W, generator=g) * 0.8
+    noise = torch.randn(B, Cc, H, W, generator=g)
+    t = torch.tensor([0, 499, 731, 999], dtype=torch.int32)
+    betas = scaled_linear_betas()
+    scale = 0.13025
+    x0 = latent * scale
+    noisy = _Diff()._add_noise_discrete(x0, noise, t, betas)
+    ac = torch.cumprod(1 - betas, 0)
+    a = (ac[t.long()] ** 0.5).view(-1, 1, 1, 1)
+    b = ((1 - ac[t.long()]) ** 0.5).view(-1, 1, 1, 1)
+    velocity = a * noise - b * x0                       # diffusers DDIMScheduler.get_velocity @5873377 (not vendored)
+    # flow: FLUX scaling (latent - shift) * scale, BaseFluxSetup.py:230
+    fshift, fscale = 0.1159, 0.3611
+    fx0 = (latent - fshift) * fscale
+    fnoisy, sigmas = _Flow()._add_noise_discrete(fx0, noise, t, torch.zeros(1000))
+    np.savez(OUT / "addnoise.npz", latent=latent.numpy(), noise=noise.numpy(), t=t.numpy(), scale=np.array([scale]),
+             x0=x0.numpy(), noisy=noisy.numpy(), velocity=velocity.numpy(), flow_shift_scale=np.array([fshift, fscale]),
+             flow_x0=fx0.numpy(), flow_noisy=fnoisy.numpy(), flow_sigmas=sigmas.flatten().numpy(),
+             flow_target=(noise - fx0).numpy())
+
+
+# ------------------------------------------------------------------------------------ losses
+class _Loss(ModelSetupDiffusionLossMixin):
+    pass
+
+
+def gen_losses():
+    out = {}
+    g = torch.Generator().manual_seed(9)
+    B, Cc, H, W = 4, 4, 16, 16
+    pred32 = torch.randn(B, Cc, H, W, generator=g)
+    target = torch.randn(B, Cc, H, W, generator=g)
+    prior = torch.randn(B, Cc, H, W, generator=g)
+    mask = (torch.rand(B, 1, H, W, generator=g) > 0.5).float()
+    mask[0, 0, :2] = 0.37                                # non-binary values go through the clamp too
+    lw = torch.tensor([1.0, 0.5, 2.0, 1.25])
+    t = torch.tensor([3, 499, 640, 999], dtype=torch.int32)
+    betas = scaled_linear_betas()
+    out.update(pred=pred32.numpy(), target=target.numpy(), prior=prior.numpy(), mask=mask.numpy(), loss_weight=lw.numpy(), t=t.numpy())
+    cases = {
+        "mse": dict(),
+        "mse_minsnr_eps": dict(loss_weight_fn=LossWeight.MIN_SNR_GAMMA),
+        "mse_minsnr_v": dict(loss_weight_fn=LossWeight.MIN_SNR_GAMMA, _v=True),
+        "mse_debiased_eps": dict(loss_weight_fn=LossWeight.DEBIASED_ESTIMATION),
+        "mse_debiased_v": dict(loss_weight_fn=LossWeight.DEBIASED_ESTIMATION, _v=True),
+        "mse_p2": dict(loss_weight_fn=LossWeight.P2, loss_weight_strength=1.0),
+        "mse_mae": dict(mae_strength=0.5, mse_strength=0.7),
+        "masked": dict(masked_training=True),
+        "masked_norm": dict(masked_training=True, normalize_masked_area_loss=True, unmasked_weight=0.2),
+        "masked_norm_prior_mae": dict(masked_training=True, normalize_masked_area_loss=True, masked_prior_preservation_weight=0.4,
+                                      mae_strength=0.3, _prior=True),
+        "masked_prior": dict(masked_training=True, masked_prior_preservation_weight=0.25, _prior=True),
+        "scaler_both": dict(loss_scaler=LossScaler.BOTH, batch_size=4, gradient_accumulation_steps=2),
+        "flow_sigma": dict(loss_weight_fn=LossWeight.SIGMA, _flow=True),
+        "flow_const": dict(_flow=True),
+    }
+    for name, kw in cases.items():
+        for ptag, pdtype in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+            cfg = TrainConfig.default_values()
+            flags = {k: v for k, v in kw.items() if k.startswith("_")}
+            for k, v in kw.items():
+                if not k.startswith("_"):
+                    setattr(cfg, k, v)
+            pred = pred32.to(pdtype).requires_grad_(True)
+            data = {"loss_type": "target", "predicted": pred, "target": target.clone(), "timestep": t,
+                    "prediction_type": "v_prediction" if flags.get("_v") else "epsilon"}
+            if flags.get("_prior"):
+                data["prior_target"] = prior
+            batch = {"latent_mask": mask, "loss_weight": lw}
+            mix = _Loss()
+            if flags.get("_flow"):
+                losses = mix._flow_matching_losses(batch, data, cfg, torch.device("cpu"), sigmas=torch.zeros(1000))
+            else:
+                losses = mix._diffusion_losses(batch, data, cfg, torch.device("cpu"), betas=betas)
+            total = losses.mean() / cfg.gradient_accumulation_steps
+            (grad,) = torch.autograd.grad(total, pred)
+            out[f"{name}_{ptag}_losses"] = losses.detach().numpy()
+            out[f"{name}_{ptag}_grad"] = bits16(grad) if pdtype == torch.bfloat16 else grad.numpy()
+    np.savez(OUT / "losses.npz", **out)
+
+
+# ------------------------------------------------------------------------------------ LoRA
+def gen_lora():
+    out = {}
+    torch.manual_seed(21)
+    for name, base, xshape in (("linear", torch.nn.Linear(72, 40), (3, 10, 72)),
+                               ("linear_nobias", torch.nn.Linear(64, 48, bias=False), (5, 64)),
+                               ("conv1x1", torch.nn.Conv2d(24, 32, 1), (2, 24, 6, 6))):
+        mod = LoRAModule("lora_unet.x", base, 16, 8.0)
+        torch.nn.init.normal_(mod.lora_up.weight, std=0.05)
+        base.requires_grad_(False)
+        mod.hook_to_module()
+        x = torch.randn(*xshape, requires_grad=True)
+        y = base(x)
+        dy = torch.randn_like(y)
+        dx, dA, dB = torch.autograd.grad(y, [x, mod.lora_down.weight, mod.lora_up.weight], dy)
+        out.update({f"{name}_x": x.detach().numpy(), f"{name}_w": base.weight.detach().numpy(),
+                    f"{name}_bias": base.bias.detach().numpy() if base.bias is not None else np.zeros(0, np.float32),
+                    f"{name}_A": mod.lora_down.weight.detach().numpy(), f"{name}_B": mod.lora_up.weight.detach().numpy(),
+                    f"{name}_y": y.detach().numpy(), f"{name}_dy": dy.numpy(), f"{name}_dx": dx.numpy(),
+                    f"{name}_dA": dA.numpy(), f"{name}_dB": dB.numpy(),
+                    f"{name}_scale": np.array([float(mod.alpha) / mod.rank])})
+        out[f"{name}_keys"] = np.array(sorted(mod.state_dict(prefix=mod.prefix).keys()))
+    np.savez(OUT / "lora.npz", **out)
+
+
+# ------------------------------------------------------------------------------------ clip
+def gen_clip():
+    g = torch.Generator().manual_seed(31)
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (1000, 37, 4096)]
+    out = {}
+    for tag, scale in (("big", 1.0), ("small", 1e-3)):
+        for i, p in enumerate(params):
+            p.grad = torch.randn(p.numel(), generator=g) * scale
+            out[f"{tag}_g{i}"] = p.grad.numpy().copy()
+        norm = torch.nn.utils.clip_grad_norm_(params, 1.0)
+        out[f"{tag}_norm"] = np.array([norm.item()], dtype=np.float32)
+        for i, p in enumerate(params):
+            out[f"{tag}_clipped{i}"] = p.grad.numpy().copy()
+    np.savez(OUT / "clip.npz", **out)
+
+
+if __name__ == "__main__":
+    for fn in (gen_schedule, gen_optimizer, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_clip):
+        fn()
+        print("wrote", fn.__name__)
+    for f in sorted(OUT.glob("*.npz")):
+        print(f.name, f.stat().st_size)

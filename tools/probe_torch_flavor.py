@@ -80,6 +80,15 @@ print("bf16 addcdiv fma(a,m/d,p):", mism16(ref, fma(af, mb.float() / db.float(),
       " p+(a*m)/d:", mism16(ref, (pb.float() + (af * mb.float()) / db.float()).bfloat16()))
 ref = mb.clone().lerp_(gb, w)
 print("bf16 lerp fma:", mism16(ref, fma(wf, gb.float() - mb.float(), mb.float()).bfloat16()))
+ref = gb.add(pb, alpha=wd)
+wb = torch.tensor(wd, dtype=torch.bfloat16, device=dev).float()
+print("bf16 add alpha: fma(wd_f32):", mism16(ref, fma(wdf, pb.float(), gb.float()).bfloat16()),
+      " fma(wd_bf16):", mism16(ref, fma(wb, pb.float(), gb.float()).bfloat16()))
+# candidates for div by python scalar
+import numpy as np
+inv_a = torch.tensor(float(np.float32(1.0) / np.float32(c)), dtype=f32, device=dev)
+inv_b = torch.tensor(float(np.float32(1.0 / c)), dtype=f32, device=dev)
+print("div scalar: s*(1f/float(c)):", mism(s / c, s * inv_a), " s*float(1/c):", mism(s / c, s * inv_b), " inv equal:", bool(inv_a == inv_b))
 # the SR path: result = p.float(); result.addcdiv_(m_bf16, d_bf16, value)
 ref = pb.float().addcdiv_(mb, db, value=alpha)
 print("sr-path addcdiv fma(a,m/d,p):", mism(ref, fma(af, mb.float() / db.float(), pb.float())),
