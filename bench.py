@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline benchmark (contract in the task brief).
+
+    python bench.py --gpus N --steps K --warmup W            # own arm (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N ...             # the reference's CPU path (oracle port), rank 0 only
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on; it fits one GPU):
+SDXL LoRA rank 32, bf16, 1024 px (4x128x128 latents), batch 4 per GPU, min-SNR-5 weighting, AdamW,
+global-norm clip 1.0, data parallel (weak scaling).  A step is ONE pass of the hot path over one synthetic
+batch: fused noise/timestep/add-noise -> the 722 hooked LoRA leaves of an SDXL-topology stand-in forward
+-> fused loss fwd+bwd -> leaves backward -> [NCCL allreduce of the LoRA gradient arena] -> grad-norm ->
+fused clip+AdamW -> bf16 shadow refresh.  Synthetic data, random-init weights (no network access).
+
+One JSON line on stdout (rank 0).  `value`: device-timed throughput with inputs resident in HBM;
+`e2e`: the same loop through the public API with HOST batches (pinned H2D copy + D2H loss read per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+WORKLOAD = "sdxl_lora_r32_bf16_1024px_b4_minsnr"
+METRIC = "sdxl_lora_train_steps_per_sec"
+UNIT = "steps/s (batch-4 steps, summed over ranks)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["own", "reference"], default="own")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
+    return ap.parse_args()
+
+
+def measured_peaks() -> tuple[dict, str]:
+    f = REPO / "MEASURED_PEAKS.json"
+    if f.exists():
+        return json.loads(f.read_text()), "measured"
+    # fallback stated in /opt/skills/guides/B200_PROFILING.md
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def reference_arm(args) -> None:
+    """The reference's CPU implementation of the path on the host cores (oracle port), rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import cpu_baseline
+    for _ in range(args.warmup):
+        cpu_baseline.run_sample()
+    t0 = time.perf_counter()
+    samples = [cpu_baseline.run_sample() for _ in range(max(args.steps, 1))]
+    wall = time.perf_counter() - t0
+    step_s = statistics.median(s["step_seconds"] for s in samples)
+    value = 1.0 / step_s
+    s0 = samples[0]
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "note": "bounded CPU sample extrapolated to one full step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": s0["threads"], "kind": "port", "sample": s0["sample"],
+                         "sample_seconds": s0["sample_seconds"], "parts_seconds": s0["parts"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_seconds": wall,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------
+def leaf_flops(model, recompute: bool = False) -> tuple[float, int, list]:
+    """Algorithmic FLOPs of the fused LoRA GEMMs in one step: per leaf 4MKN + 6Mr(K+N)."""
+    total, launches, shapes = 0.0, 0, []
+    for m in model.unet_lora.lora_modules.values():
+        M = getattr(m, "_last_rows", 0)
+        w = m.orig_module.weight
+        N, K, r = w.shape[0], w[0].numel(), m.rank
+        total += 4.0 * M * K * N + 6.0 * M * r * (K + N)
+        launches += 3
+        shapes.append((M, N, K, r))
+    return total, launches, shapes
+
+
+def time_leaf_kernels(model, dev, reps: int = 3) -> tuple[float, float, int]:
+    """Replay every K-a launch of one step (forward, dX, dA/dB per leaf) back to back with CUDA events on the
+    launching stream: returns (seconds per step spent in K-a, algorithmic flops per step, launches per step)."""
+    import torch
+    from onetrainer_b200 import ops
+    flops, launches, shapes = leaf_flops(model)
+    uniq = {}
+    for s in shapes:
+        uniq[s] = uniq.get(s, 0) + 1
+    bufs = {}
+    g = torch.Generator(device=dev).manual_seed(0)
+    for (M, N, K, r) in uniq:
+        mk = lambda *sh: (torch.randn(*sh, device=dev, generator=g) * 0.05).bfloat16()  # noqa: E731
+        bufs[(M, N, K, r)] = dict(x=mk(M, K), w=mk(N, K), wt=mk(K, N), a=mk(r, K), at=mk(K, r), b=mk(N, r), bt=mk(r, N), dy=mk(M, N),
+                                  bias=mk(N), dA=torch.zeros(r, K, device=dev), dB=torch.zeros(N, r, device=dev))
+
+    def one_step():
+        for key, cnt in uniq.items():
+            b = bufs[key]
+            for _ in range(cnt):
+                _, ts = ops.lora_linear(b["x"], b["w"], b["a"], b["b"], b["bias"], 1 / 32)
+                _, gs = ops.lora_linear(b["dy"], b["wt"], b["bt"], b["at"], None, 1 / 32)
+                ops.lora_grad_ab(b["x"], b["dy"], gs, ts, b["dA"], b["dB"])
+
+    one_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 1e3 / reps, flops, launches
+
+
+def own_arm(args) -> None:
+    import torch
+    import torch.distributed as dist
+    from onetrainer_b200 import dp, ops
+    from onetrainer_b200.harness import trainer
+    from onetrainer_b200.modules.util.config.TrainConfig import TrainConfig
+    from onetrainer_b200.modules.util.enum import LossWeight
+
+    rank, local_rank, world = dp.init_from_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (own arm) needs a B200: there is no CPU fallback for this path")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B = 4
+    cfg = TrainConfig(train_device=str(dev), batch_size=B, lora_rank=32, lora_alpha=1.0, loss_weight_fn=LossWeight.MIN_SNR_GAMMA,
+                      clip_grad_norm=1.0)
+    model, setup = trainer.build_model("sdxl", cfg, dev, ema=False, stochastic_rounding=True, lora_up_std=0.02)
+    host_batch = {k: ([t.pin_memory() for t in v] if isinstance(v, list) else v.pin_memory())
+                  for k, v in trainer.synthetic_batch("sdxl", B, dev).items()}
+    dev_batch = trainer.batch_to_device(host_batch, dev)
+    bucket = dp.GradientBucket(None)
+    h2d = sum(sum(t.numel() * t.element_size() for t in v) if isinstance(v, list) else v.numel() * v.element_size()
+              for v in host_batch.values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return trainer.train_step(setup, model, dev_batch, cfg, bucket)
+
+    def step_e2e():
+        b = trainer.batch_to_device(host_batch, dev, non_blocking=True)
+        return trainer.train_step(setup, model, b, cfg, bucket).item()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.LAUNCHES
+        e0.record()
+        for _ in range(k):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / 1e3, ops.LAUNCHES - l0, out
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    with ClockSampler(local_rank) as clk:
+        sec, launches, last_loss = timed(step_resident, args.steps)
+    clocks = clk.summary()
+    for _ in range(2):
+        step_e2e()
+    sec_e2e, _, loss_e2e = timed(step_e2e, args.steps)
+
+    peaks, peak_kind = measured_peaks()
+    ka_sec, ka_flops, ka_launches = time_leaf_kernels(model, dev)
+    achieved = ka_flops / ka_sec / 1e12
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline
+        s = cpu_baseline.run_sample()
+        cpu = {"value": 1.0 / s["step_seconds"], "unit": UNIT, "cores": s["threads"], "kind": "port", "sample": s["sample"],
+               "sample_seconds": s["sample_seconds"], "parts_seconds": s["parts"]}
+    if rank == 0:
+        value = world * args.steps / sec
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "lora_rank": 32, "hooked_leaves": 722,
+                       "lora_params": sum(p.numel() for p in model.parameters), "parallelism": f"dp{world}",
+                       "l2": "inputs larger than L2 (4.4 GB of frozen weights + 0.68 GB LoRA/optimizer state stream every step)"},
+            "samples_per_sec": value * B, "optimizer_steps_per_sec": args.steps / sec,
+            "e2e": {"value": world * args.steps / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": sec_e2e / args.steps * 1e3},
+            "gpu_launches": launches, "loss": float(last_loss), "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "lora_linear_kernel (+ lora_grad_kernel)", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": f"{peak_kind} bf16_tflops_sustained",
+                         "algorithmic_flops_per_step": ka_flops, "launches_per_step": ka_launches,
+                         "seconds_per_step_in_kernel": ka_sec, "share_of_step": ka_sec / (sec / args.steps)},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        own_arm(a)

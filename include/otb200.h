@@ -108,7 +108,7 @@ typedef struct otb_optim_tensor {
     float       beta2;
     float       one_minus_beta2;
     float       bc2_sqrt;     /* sqrt(1 - beta2^step)                                       */
-    float       inv_bc2_sqrt; /* 1 / bc2_sqrt (used under OTB_FLAVOR_DIV_RECIPROCAL)        */
+    float       inv_bc2_sqrt; /* (float)(1.0 / bc2_sqrt_double): torch CUDA divides by a python scalar as a * (float)(1/b) */
     float       eps;
     float       neg_step_size;/* -lr / (1 - beta1^step)                                     */
     int32_t     p_dtype;      /* OTB_F32 | OTB_BF16                                         */

@@ -15,6 +15,52 @@ void otb_set_error(const char* fmt, ...) {
 extern "C" const char* otb_last_error(void) { return g_err; }
 extern "C" int otb_abi_version(void) { return OTB_ABI_VERSION; }
 
+#include <cuda.h>
+
+namespace {
+template <typename F>
+F driver_fn(const char* name) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return (F)p;
+}
+}  // namespace
+
+int otb_bind_context(const void* device_ptr) {
+    typedef CUresult (*GetCur)(CUcontext*);
+    typedef CUresult (*PtrAttr)(void*, CUpointer_attribute, CUdeviceptr);
+    typedef CUresult (*Retain)(CUcontext*, CUdevice);
+    typedef CUresult (*SetCur)(CUcontext);
+    static GetCur get_cur = driver_fn<GetCur>("cuCtxGetCurrent");
+    static PtrAttr ptr_attr = driver_fn<PtrAttr>("cuPointerGetAttribute");
+    static Retain retain = driver_fn<Retain>("cuDevicePrimaryCtxRetain");
+    static SetCur set_cur = driver_fn<SetCur>("cuCtxSetCurrent");
+    if (!get_cur || !ptr_attr || !retain || !set_cur) {
+        otb_set_error("CUDA driver entry points not available");
+        return OTB_ECUDA;
+    }
+    CUcontext ctx = nullptr;
+    if (get_cur(&ctx) == CUDA_SUCCESS && ctx != nullptr) return OTB_OK;
+    if (device_ptr == nullptr) {
+        otb_set_error("no CUDA context is current on this thread and no device pointer to find one from");
+        return OTB_ECUDA;
+    }
+    int ordinal = -1;
+    CUresult r = ptr_attr(&ordinal, CU_POINTER_ATTRIBUTE_DEVICE_ORDINAL, (CUdeviceptr)(uintptr_t)device_ptr);
+    if (r != CUDA_SUCCESS || ordinal < 0) {
+        otb_set_error("cuPointerGetAttribute(%p) failed with CUresult %d: not a device pointer?", device_ptr, (int)r);
+        return OTB_EINVAL;
+    }
+    r = retain(&ctx, (CUdevice)ordinal);
+    if (r == CUDA_SUCCESS) r = set_cur(ctx);
+    if (r != CUDA_SUCCESS) {
+        otb_set_error("binding the primary context of device %d failed with CUresult %d", ordinal, (int)r);
+        return OTB_ECUDA;
+    }
+    return OTB_OK;
+}
+
 int otb_sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
     int dev = 0;
@@ -67,6 +113,7 @@ extern "C" int otb_philox_dump(uint64_t seed, uint64_t offset, uint32_t stream_i
                                int64_t n_groups, uint32_t* out4, void* stream) {
     OTB_CHECK_ARG(out4 != nullptr && n_groups >= 0, "bad philox dump args");
     if (n_groups == 0) return OTB_OK;
+    OTB_BIND(out4);
     philox_dump_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, offset, stream_id, first_group, n_groups, out4);
     OTB_LAUNCH_CHECK("philox_dump_kernel");
     return OTB_OK;

@@ -49,6 +49,17 @@ void otb_set_error(const char* fmt, ...);
 
 int otb_sm_count();   // cached; 148 on B200
 
+// Make sure the calling thread has a current CUDA context: the one that owns `device_ptr`.
+// autograd's backward thread may reach this library before torch has bound a context to it; driver
+// entry points (cuTensorMapEncodeTiled) then fail with CUDA_ERROR_INVALID_CONTEXT, and a runtime call
+// would silently create a context on device 0.  No-op when a context is already current.
+int otb_bind_context(const void* device_ptr);
+#define OTB_BIND(ptr)                                             \
+    do {                                                          \
+        int rc__ = otb_bind_context(ptr);                         \
+        if (rc__ != OTB_OK) return rc__;                          \
+    } while (0)
+
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Restated bit-for-bit in oracle/otb_oracle.c.
 // counter = (group_lo, group_hi, offset_lo, stream<<24 | offset_hi[0:24)), key = seed.

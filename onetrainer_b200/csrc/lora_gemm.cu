@@ -393,6 +393,7 @@ extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
     OTB_CHECK_ARG(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "dropout_p must be in [0,1)");
     OTB_CHECK_ARG((((uintptr_t)a->x | (uintptr_t)a->w | (uintptr_t)a->y | (uintptr_t)a->down | (uintptr_t)a->up |
                     (uintptr_t)a->t_out) & 15) == 0, "all tensor pointers must be 16-byte aligned");
+    OTB_BIND(a->x);
     int sms = otb_sm_count();
     GemmParams p;
     p.M = a->M; p.N = a->N; p.K = a->K; p.R = a->R;

@@ -167,6 +167,7 @@ extern "C" int otb_lora_grad_ab(const otb_lora_grad_args* a, void* stream) {
     if (doB) OTB_CHECK_ARG(a->ts && a->dy && a->N > 0 && a->N % 8 == 0, "dB needs ts, dy and N %% 8 == 0");
     OTB_CHECK_ARG((((uintptr_t)a->x | (uintptr_t)a->dy | (uintptr_t)a->gs | (uintptr_t)a->ts) & 15) == 0,
                   "all operand pointers must be 16-byte aligned");
+    OTB_BIND(doA ? a->x : a->dy);
     GradParams p;
     p.M = a->M; p.R = a->R; p.Rp = (a->R + 15) / 16 * 16;
     p.pr[0].U = (const uint16_t*)a->gs; p.pr[0].V = (const uint16_t*)a->x; p.pr[0].out = doA ? a->dA : nullptr;

@@ -437,6 +437,7 @@ int check_launch(const otb_optim_launch* a) {
     if (a->n_chunks == 0) return 1;
     OTB_CHECK_ARG(a->tensors && a->chunk_tensor && a->chunk_index, "null table pointer");
     OTB_CHECK_ARG(a->chunk_elems > 0 && a->chunk_elems % 2048 == 0, "chunk_elems must be a positive multiple of 2048");
+    OTB_BIND(a->tensors);
     return 0;
 }
 
@@ -461,6 +462,7 @@ extern "C" int otb_ema_multi(const otb_optim_launch* a, void* stream) {
 extern "C" int otb_grad_norm_multi(const otb_optim_launch* a, float max_norm, float grad_prescale,
                                    float* partials, float* out, void* stream) {
     OTB_CHECK_ARG(out != nullptr, "null output");
+    OTB_BIND(out);
     int c = check_launch(a);
     if (c < 0) return c;
     if (c == 0) {
@@ -485,6 +487,7 @@ extern "C" int otb_grad_scale_multi(const otb_optim_launch* a, const float* coef
 extern "C" int otb_shadow_refresh_multi(const otb_shadow_tensor* tensors, int32_t n_tensors, int32_t n_tiles, void* stream) {
     if (n_tensors == 0 || n_tiles == 0) return OTB_OK;
     OTB_CHECK_ARG(tensors != nullptr && n_tensors > 0 && n_tiles > 0, "bad shadow table");
+    OTB_BIND(tensors);
     shadow_refresh_kernel<<<n_tiles, 256, 0, (cudaStream_t)stream>>>(tensors, n_tensors);
     OTB_LAUNCH_CHECK("shadow_refresh_kernel");
     return OTB_OK;

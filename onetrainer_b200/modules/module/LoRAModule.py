@@ -367,6 +367,7 @@ class LoRAModule(PeftBase):
         if x2.dtype != torch.bfloat16:
             x2 = x2.to(torch.bfloat16)
         x2 = x2.contiguous()
+        self._last_rows = x2.shape[0]          # read by bench.py to replay the step's GEMM shapes
         y2 = _LoraLinearFn.apply(x2, A, B, self)
         if isinstance(om, nn.Conv2d):
             return y2.view(b_, h_, w_, -1).permute(0, 3, 1, 2)
@@ -460,15 +461,14 @@ class LoRAModuleWrapper:
         self.refresh_shadows()
 
     def _grad_views(self, idx: int, A: Tensor, B: Tensor, need_a: bool, need_b: bool):
-        mods = self._trainable()
-        key = tuple((tuple(m.lora_down.weight.shape), tuple(m.lora_up.weight.shape)) for m in mods) + (str(A.device),)
-        if self._arena is None or key != self._arena_key:
+        if self._arena is None or self._arena_key != A.device:
+            mods = self._trainable()
             shapes = []
             for m in mods:
                 a, b = m.lora_down.weight, m.lora_up.weight
                 shapes += [(a.shape[0], a[0].numel()), (b.shape[0], b[0].numel())]
             self._arena = GradArena(shapes, A.device)
-            self._arena_key = key
+            self._arena_key = A.device
             self._written_gen = {}
         arena = self._arena
         va, vb = arena.view(2 * idx), arena.view(2 * idx + 1)
@@ -516,6 +516,7 @@ class LoRAModuleWrapper:
         for m in self.lora_modules.values():
             m.to(device, dtype)
         self._shadow = None
+        self._arena = None
         return self
 
     def load_state_dict(self, state_dict: dict[str, Tensor]):
@@ -565,6 +566,8 @@ class LoRAModuleWrapper:
 
     def prune(self):
         self.lora_modules = {k: v for k, v in self.lora_modules.items() if not isinstance(v, self.dummy_klass)}
+        self._shadow = self._arena = None
+        self._bind()
 
     def set_dropout(self, dropout_probability: float):
         if dropout_probability < 0 or dropout_probability > 1:

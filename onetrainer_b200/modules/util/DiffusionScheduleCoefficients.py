@@ -23,6 +23,16 @@ class DiffusionScheduleCoefficients:
         self.sqrt_one_minus_alphas_cumprod = torch.sqrt(1 - alphas_cumprod).contiguous()
 
     @staticmethod
+    def from_tables(betas: Tensor, alphas_cumprod: Tensor, sqrt_alphas_cumprod: Tensor,
+                    sqrt_one_minus_alphas_cumprod: Tensor) -> "DiffusionScheduleCoefficients":
+        """Adopt tables computed elsewhere (e.g. loaded from a backup, or a fixture) without recomputing them."""
+        co = DiffusionScheduleCoefficients.__new__(DiffusionScheduleCoefficients)
+        co.num_timesteps, co.betas, co.alphas_cumprod = betas.shape[0], betas, alphas_cumprod
+        co.sqrt_alphas_cumprod = sqrt_alphas_cumprod.contiguous()
+        co.sqrt_one_minus_alphas_cumprod = sqrt_one_minus_alphas_cumprod.contiguous()
+        return co
+
+    @staticmethod
     def from_betas(betas: Tensor) -> "DiffusionScheduleCoefficients":
         betas = betas.to(dtype=torch.float32)
         return DiffusionScheduleCoefficients(betas, torch.cumprod(1 - betas, dim=0))

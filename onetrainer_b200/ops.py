@@ -18,6 +18,14 @@ _SHADOW_DTYPE = np.dtype(N.ShadowTensor)
 
 CHUNK_ELEMS = 16384          # elements of one tensor handled by one CTA of the multi-tensor kernels
 
+# number of libotb200 kernels launched by this process (bench.py reports it as `gpu_launches`)
+LAUNCHES = 0
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -59,6 +67,7 @@ def lora_linear(x: torch.Tensor, w: torch.Tensor, down: torch.Tensor | None, up:
         scale=float(scale), dropout_p=float(dropout_p), seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1),
         tile_n=int(tile_n), stages=int(stages))
     N.check(N.lib().otb_lora_linear(C.byref(a), _stream()), "otb_lora_linear")
+    _count()
     return y, t
 
 
@@ -73,6 +82,7 @@ def lora_grad_ab(x, dy, gs, ts, dA: torch.Tensor | None, dB: torch.Tensor | None
     a = N.LoraGradArgs(x=N.ptr(x), dy=N.ptr(dy), gs=N.ptr(gs), ts=N.ptr(ts), dA=N.ptr(dA), dB=N.ptr(dB),
                        M=M, N=dy.shape[1] if dy is not None else 0, K=x.shape[1] if x is not None else 0, R=R)
     N.check(N.lib().otb_lora_grad_ab(C.byref(a), _stream()), "otb_lora_grad_ab")
+    _count()
 
 
 # --------------------------------------------------------------------------------------
@@ -125,6 +135,7 @@ def noise_addnoise(*, latent=None, noise_in=None, coef_x0=None, coef_noise=None,
         shift_c1=float(T * shift), shift_c2=float(shift - 1),
         seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1), sample_base=int(sample_base))
     N.check(N.lib().otb_noise_addnoise(C.byref(a), _stream()), "otb_noise_addnoise")
+    _count()
     out.update(x0=x0, noise=noise, noisy=noisy, noisy_cast=noisy_cast, target=tgt, timestep=ts, sigma=sigma)
     return out
 
@@ -158,7 +169,7 @@ def loss_fwd_bwd(predicted, target, *, prior_target=None, mask=None, loss_weight
                  mse_strength=1.0, mae_strength=0.0, unmasked_weight=0.1, masked_prior_preservation_weight=0.0,
                  loss_scale=1.0, loss_weight_strength=5.0, upstream=1.0, want_grad=True):
     """Per-sample losses [B] (fp32) and d(sum_b upstream*losses[b])/d(predicted) in one pass."""
-    N.require_cuda(predicted, target, prior_target, mask, loss_weight, timestep, sqrt_ac, sqrt_1mac, sigmas)
+    N.require_cuda(predicted, target, prior_target, mask, timestep, sqrt_ac, sqrt_1mac, sigmas)
     if predicted.shape != target.shape:
         raise ValueError("loss_fwd_bwd: predicted / target shapes differ")
     predicted = predicted.contiguous()
@@ -199,6 +210,7 @@ def loss_fwd_bwd(predicted, target, *, prior_target=None, mask=None, loss_weight
         masked_prior_preservation_weight=float(masked_prior_preservation_weight), loss_scale=float(loss_scale),
         loss_weight_strength=float(loss_weight_strength), upstream=float(upstream))
     N.check(N.lib().otb_loss_fwd_bwd(C.byref(a), _stream()), "otb_loss_fwd_bwd")
+    _count(2 if (normalize_masked_area_loss and mask is not None) else 1)
     return losses, dpred
 
 
@@ -207,6 +219,7 @@ def loss_bwd_rescale(dpred: torch.Tensor, grad_out: torch.Tensor, assumed: float
     go = grad_out.to(dtype=torch.float32).contiguous()
     N.check(N.lib().otb_loss_bwd_rescale(dpred.data_ptr(), N.dtype_code(dpred.dtype), go.data_ptr(), float(assumed),
                                          B, dpred[0].numel(), _stream()), "otb_loss_bwd_rescale")
+    _count()
 
 
 # --------------------------------------------------------------------------------------
@@ -319,17 +332,19 @@ def adam_scalars(lr: float, beta1: float, beta2: float, eps: float, weight_decay
         decay_mul=f(1 - lr * weight_decay) if decoupled else f(1.0),
         l2=f(0.0) if decoupled else f(weight_decay),
         lerp_w=f(1 - beta1), beta2=f(beta2), one_minus_beta2=f(1 - beta2),
-        bc2_sqrt=f(bc2_sqrt), inv_bc2_sqrt=f(1.0) / f(bc2_sqrt), eps=f(eps), neg_step_size=f(-step_size))
+        bc2_sqrt=f(bc2_sqrt), inv_bc2_sqrt=f(1.0 / bc2_sqrt), eps=f(eps), neg_step_size=f(-step_size))
 
 
 def adamw_sr_ema_multi(table: OptimTable, **kw) -> None:
     a = table.launch_args(**kw)
     N.check(N.lib().otb_adamw_sr_ema_multi(C.byref(a), _stream()), "otb_adamw_sr_ema_multi")
+    _count()
 
 
 def ema_multi(table: OptimTable, one_minus_decay: float) -> None:
     a = table.launch_args(ema_one_minus_decay=one_minus_decay, do_ema=True)
     N.check(N.lib().otb_ema_multi(C.byref(a), _stream()), "otb_ema_multi")
+    _count()
 
 
 def grad_norm_multi(table: OptimTable, max_norm: float, grad_prescale: float = 1.0) -> torch.Tensor:
@@ -337,12 +352,14 @@ def grad_norm_multi(table: OptimTable, max_norm: float, grad_prescale: float = 1
     a = table.launch_args()
     N.check(N.lib().otb_grad_norm_multi(C.byref(a), float(max_norm), float(grad_prescale), table.partials.data_ptr(),
                                         table.norm_coef.data_ptr(), _stream()), "otb_grad_norm_multi")
+    _count(2)
     return table.norm_coef
 
 
 def grad_scale_multi(table: OptimTable, coef: torch.Tensor) -> None:
     a = table.launch_args()
     N.check(N.lib().otb_grad_scale_multi(C.byref(a), coef.data_ptr(), _stream()), "otb_grad_scale_multi")
+    _count()
 
 
 class ShadowTable:
@@ -393,6 +410,7 @@ class ShadowTable:
             self.sync_pointers()
         N.check(N.lib().otb_shadow_refresh_multi(self.dev.data_ptr(), len(self.masters), self.n_tiles, _stream()),
                 "otb_shadow_refresh_multi")
+        _count()
 
 
 def philox_dump(seed: int, offset: int, stream_id: int, first_group: int, n_groups: int, device) -> torch.Tensor:

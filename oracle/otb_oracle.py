@@ -108,7 +108,7 @@ def adam_scalars(lr, beta1, beta2, eps, weight_decay, step, decoupled=True) -> A
     f = np.float32
     return AdamScalars(float(f(1 - lr * weight_decay)) if decoupled else 1.0, 0.0 if decoupled else float(f(weight_decay)),
                        float(f(1 - beta1)), float(f(beta2)), float(f(1 - beta2)), float(f(bc2_sqrt)),
-                       float(f(1.0) / f(bc2_sqrt)), float(f(eps)), float(f(-step_size)))
+                       float(f(1.0 / bc2_sqrt)), float(f(eps)), float(f(-step_size)))
 
 
 def adam_step(p, g, m, v, dt, scalars: AdamScalars, flavor=FLAVOR_TORCH_CPU, sr=False, maximize=False, seed=0, offset=0,
