@@ -21,6 +21,7 @@
 // output once — fewer roundings than the reference's five.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -323,6 +324,277 @@ lora_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     }
 }
 
+// =====================================================================================
+// v2: persistent, thread-block-cluster TMA multicast, double-buffered TMEM accumulators
+// =====================================================================================
+// What v1 left on the table (ncu, profiles/r01_ka_v1.txt): one tile per CTA means the epilogue
+// (TMEM -> registers -> HBM) and the bf16 T hand-off never overlap the next tile's MMAs, and every
+// CTA pulls its own copy of the x and w tiles through L2: 48 KB per 64-wide k-block per CTA is
+// ~27 TB/s of L2->SMEM traffic at the tensor peak — the kernel was L2-bound at 32 % tensor-pipe
+// utilisation.  v2:
+//   * clusters of CM x CN CTAs work on CM x CN neighbouring tiles; each CTA TMA-loads 1/CN of its
+//     x tile and 1/CM of its [w; down] tile and MULTICASTS it to the peers that need it, so L2
+//     traffic per CTA drops from (x + w) to (x/CN + w/CM);
+//   * CTAs are persistent: the smem ring keeps streaming across tiles, the accumulator lives in one
+//     of two TMEM stages, and the 4 epilogue warps drain tile i while the MMA warp runs tile i+1;
+//   * the rank-R hand-off (T: TMEM -> bf16 -> smem -> UMMA) of tile i is issued two k-blocks INTO
+//     tile i+1's mainloop, so the tensor pipe does not idle while the epilogue converts T.
+struct GemmParams2 {
+    GemmParams g;
+    int cm, cn;            // cluster shape (tiles along M, along N)
+    int super_m, super_n;  // number of super-tiles (cluster-sized tile groups)
+    int m_tiles;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctaid_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+// arrive (once the preceding tcgen05 ops retire) on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"(mask) : "memory");
+}
+
+struct SmemLayout2 {
+    uint32_t stage_bytes, x_off, w_off, up_off, up_bytes, t_off, bar_off, total;
+};
+__host__ __device__ inline SmemLayout2 make_layout2(int tile_n, int Rp, int stages) {
+    SmemLayout2 L;
+    L.x_off = 0;
+    L.w_off = BM * 128;
+    L.stage_bytes = (uint32_t)(BM + tile_n + Rp) * 128;
+    L.up_off = L.stage_bytes * stages;
+    L.up_bytes = Rp ? (uint32_t)tile_n * 128 : 0;
+    L.t_off = L.up_off + 2 * L.up_bytes;                 // up tile is double-buffered across tiles
+    L.bar_off = L.t_off + (Rp ? BM * 128 : 0);
+    L.total = L.bar_off + 512;
+    return L;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lora_linear_kernel_v2(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                      const __grid_constant__ CUtensorMap tm_dn, const __grid_constant__ CUtensorMap tm_up,
+                      const GemmParams2 q) {
+    const GemmParams& p = q.g;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const SmemLayout2 L = make_layout2(p.tile_n, p.Rp, p.stages);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool lora = p.Rp > 0;
+    const int csize = q.cm * q.cn;
+    const uint32_t crank = csize > 1 ? cluster_ctarank() : 0;
+    const int rm = (int)crank % q.cm, rn = (int)crank / q.cm;      // position of this CTA's tile inside the super-tile
+    const uint32_t cid = csize > 1 ? cluster_id_x() : blockIdx.x;
+    const uint32_t ncl = csize > 1 ? cluster_nctaid_x() : gridDim.x;
+    const int total_super = q.super_m * q.super_n;
+
+    const uint32_t bar_base = smem_base + L.bar_off;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+    auto misc = [&](int i) { return bar_base + 8u * (2 * MAX_STAGES + i); };
+    // misc: 0,1 up_full  2,3 up_empty  4,5 t_full  6 t_ready  8,9 d_full  10,11 acc_empty  12 tmem slot
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bar_off + 8u * (2 * MAX_STAGES + 12));
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
+        if (lora) { prefetch_tmap(&tm_dn); prefetch_tmap(&tm_up); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), (uint32_t)csize); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(misc(0 + i), 1); mbar_init(misc(2 + i), 1); mbar_init(misc(4 + i), 1);
+            mbar_init(misc(8 + i), 1); mbar_init(misc(10 + i), 128);
+        }
+        mbar_init(misc(6), 128);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(misc(12), 512u);
+    tc_fence_before();
+    __syncthreads();
+    if (csize > 1) cluster_sync_all();          // peers' barriers must exist before any multicast / remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+    constexpr uint32_t ACC_STRIDE = 256;        // TMEM columns per accumulator stage
+
+    const uint16_t all_mask = (uint16_t)((1u << csize) - 1u);
+    // CTAs that share my x tile: same rm, all rn ;  CTAs that share my [w; down] tile: same rn, all rm
+    uint16_t x_mask = 0, w_mask = 0;
+    for (int j = 0; j < q.cn; ++j) x_mask |= (uint16_t)(1u << (rm + j * q.cm));
+    for (int j = 0; j < q.cm; ++j) w_mask |= (uint16_t)(1u << (j + rn * q.cm));
+    const int x_rows = BM / q.cn, w_rows = p.tile_n / q.cm, d_rows = lora ? p.Rp / q.cm : 0;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            int it = 0;
+            for (uint32_t st = cid; st < (uint32_t)total_super; st += ncl, ++it) {
+                const int sm_i = st / q.super_n, sn_i = st % q.super_n;
+                const int m0 = (sm_i * q.cm + rm) * BM, n0 = (sn_i * q.cn + rn) * p.tile_n;
+                if (lora) {
+                    const int ub = it & 1;
+                    mbar_wait(misc(2 + ub), ((it >> 1) & 1) ^ 1);
+                    mbar_expect_tx(misc(0 + ub), L.up_bytes);
+                    tma_load_2d(smem_base + L.up_off + ub * L.up_bytes, &tm_up, misc(0 + ub), 0, n0);
+                }
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    const uint32_t stg = smem_base + L.stage_bytes * s;
+                    mbar_expect_tx(full_bar(s), L.stage_bytes);
+                    if (csize == 1) {
+                        tma_load_2d(stg + L.x_off, &tm_x, full_bar(s), kb * BK, m0);
+                        tma_load_2d(stg + L.w_off, &tm_w, full_bar(s), kb * BK, n0);
+                        if (lora) tma_load_2d(stg + L.w_off + (uint32_t)p.tile_n * 128, &tm_dn, full_bar(s), kb * BK, 0);
+                    } else {
+                        // my slice of each shared tile, delivered to every CTA that needs it
+                        tma_load_2d_mc(stg + L.x_off + (uint32_t)(rn * x_rows) * 128, &tm_x, full_bar(s), kb * BK, m0 + rn * x_rows, x_mask);
+                        tma_load_2d_mc(stg + L.w_off + (uint32_t)(rm * w_rows) * 128, &tm_w, full_bar(s), kb * BK, n0 + rm * w_rows, w_mask);
+                        if (lora)
+                            tma_load_2d_mc(stg + L.w_off + (uint32_t)(p.tile_n + rm * d_rows) * 128, &tm_dn, full_bar(s), kb * BK, rm * d_rows, w_mask);
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc_main = umma_idesc_bf16(BM, p.tile_n + p.Rp);
+            const uint32_t idesc_up = umma_idesc_bf16(BM, p.tile_n);
+            int s = 0; uint32_t ph = 0;
+            int it = 0, pending = -1;
+            auto issue_up = [&](int j) {      // D[j&1] += T(j) . up(j)^T, then hand the accumulator to the epilogue
+                const int as = j & 1;
+                mbar_wait(misc(6), (uint32_t)(j & 1));                     // t_ready: epilogue parked bf16 T(j) in smem
+                mbar_wait(misc(0 + as), (uint32_t)((j >> 1) & 1));         // up_full
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_sw128(smem_base + L.t_off);
+                const uint64_t bdesc = umma_desc_sw128(smem_base + L.up_off + as * L.up_bytes);
+                for (int k = 0; k < p.Rp / UMMA_K; ++k)
+                    umma_bf16(tmem_base + as * ACC_STRIDE, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_up, 1u);
+                umma_commit(misc(8 + as));                                  // d_full
+                umma_commit(misc(2 + as));                                  // up_empty
+            };
+            for (uint32_t st = cid; st < (uint32_t)total_super; st += ncl, ++it) {
+                const int as = it & 1;
+                mbar_wait(misc(10 + as), ((it >> 1) & 1) ^ 1);             // acc_empty: epilogue drained tile it-2
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+                const int lookahead = p.num_kb < 2 ? p.num_kb : 2;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t stg = smem_base + L.stage_bytes * s;
+                    const uint64_t adesc = umma_desc_sw128(stg + L.x_off);
+                    const uint64_t bdesc = umma_desc_sw128(stg + L.w_off);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_main, (kb | k) != 0);
+                    if (csize == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), all_mask);
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                    if (pending >= 0 && kb == lookahead - 1) { issue_up(pending); pending = -1; }
+                }
+                if (lora) { umma_commit(misc(4 + as)); pending = it; }     // t_full
+                else umma_commit(misc(8 + as));                            // d_full
+            }
+            if (pending >= 0) issue_up(pending);
+        }
+    } else {
+        // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =================
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const float keep_scale = p.dropout_p > 0.0f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+        uint8_t* t_row = smem_gen + L.t_off + row * 128;
+        int it = 0;
+        for (uint32_t st = cid; st < (uint32_t)total_super; st += ncl, ++it) {
+            const int as = it & 1;
+            const uint32_t par = (uint32_t)((it >> 1) & 1);
+            const int sm_i = st / q.super_n, sn_i = st % q.super_n;
+            const int m_tile = sm_i * q.cm + rm, n_tile = sn_i * q.cn + rn;
+            const int m0 = m_tile * BM, n0 = n_tile * p.tile_n;
+            const int m = m0 + row;
+            const uint32_t t_lane = tmem_base + as * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+            if (lora) {
+                mbar_wait(misc(4 + as), par);                               // t_full
+                tc_fence_after();
+                for (int c = 0; c < p.Rp; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(t_lane + (uint32_t)(p.tile_n + c), v);
+                    tmem_ld_wait();
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.scale;
+                    if (p.dropout_p > 0.0f) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const uint64_t e = (uint64_t)m * (uint64_t)p.Rp + (uint64_t)(c + j);
+                            Philox4 r = otb_rng(p.seed, p.offset, OTB_STREAM_DROPOUT, e >> 2);
+                            f[j + 0] = otb_u01(r.x) >= p.dropout_p ? f[j + 0] * keep_scale : 0.0f;
+                            f[j + 1] = otb_u01(r.y) >= p.dropout_p ? f[j + 1] * keep_scale : 0.0f;
+                            f[j + 2] = otb_u01(r.z) >= p.dropout_p ? f[j + 2] * keep_scale : 0.0f;
+                            f[j + 3] = otb_u01(r.w) >= p.dropout_p ? f[j + 3] * keep_scale : 0.0f;
+                        }
+                    }
+                    uint4 lo = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                    uint4 hi = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+                    const int j0 = c >> 3;
+                    *reinterpret_cast<uint4*>(t_row + (((j0 + 0) ^ (row & 7)) << 4)) = lo;
+                    *reinterpret_cast<uint4*>(t_row + (((j0 + 1) ^ (row & 7)) << 4)) = hi;
+                    if (p.t_out != nullptr && n_tile == 0 && m < p.M) {
+                        uint16_t* dst = p.t_out + (size_t)m * p.R + c;
+                        if (c + 8 <= p.R) *reinterpret_cast<uint4*>(dst) = lo;
+                        if (c + 16 <= p.R) *reinterpret_cast<uint4*>(dst + 8) = hi;
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(misc(6));                                       // t_ready
+            }
+            mbar_wait(misc(8 + as), par);                                   // d_full
+            tc_fence_after();
+            const bool tile_live = m_tile < q.m_tiles && n0 < p.N;
+            for (int c = 0; c < p.tile_n && tile_live; c += 16) {
+                const int n = n0 + c;
+                if (n >= p.N) break;
+                uint32_t v[16];
+                tmem_ld16(t_lane + (uint32_t)c, v);
+                tmem_ld_wait();
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n + j < p.N) f[j] += load_as_float(p.bias, n + j, p.bias_dtype);
+                }
+                if (m < p.M) {
+                    uint16_t* dst = p.y + (size_t)m * p.N + n;
+                    if (n + 8 <= p.N)
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                    if (n + 16 <= p.N)
+                        *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(misc(10 + as));                                     // acc_empty
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (csize > 1) cluster_sync_all();          // nobody exits while a peer may still multicast into it
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 512u);
+    }
+}
+
 // ------------------------------- host side ------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -382,6 +654,118 @@ int choose_tile_n(int M, int N, int K, int Rp, int sms) {
 
 }  // namespace
 
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// persistent variant of the tile-width choice: `ctas` CTAs each run ceil(tiles / ctas) tiles back to back;
+// the epilogue overlaps the next mainloop, so a tile costs max(mainloop, epilogue) + the T hand-off.
+int choose_tile_n_v2(int M, int N, int K, int Rp, int ctas, int cm, int cn) {
+    const int m_tiles = ((M + BM - 1) / BM + cm - 1) / cm * cm;
+    const int kb4 = ((K + BK - 1) / BK) * 4;
+    double best = 1e30; int best_tn = 64;
+    for (int tn = 32; tn + Rp <= 256; tn += 16) {
+        int n_tiles = ((N + tn - 1) / tn + cn - 1) / cn * cn;
+        int64_t tiles = (int64_t)m_tiles * n_tiles;
+        int64_t rounds = (tiles + ctas - 1) / ctas;
+        int np = tn + Rp;
+        // operand bytes per k-step that this CTA pulls through L2 (x/cn + [w;down]/cm), at ~64 B/clk/SM sustained
+        double l2 = (BM * 32.0 / cn + np * 32.0 / cm) / 64.0;
+        double kstep = np / 2.0;
+        if (kstep < 32 + np / 4.0) kstep = 32 + np / 4.0;
+        if (kstep < l2) kstep = l2;
+        double mainloop = kb4 * kstep;
+        double epi = 14.0 * tn + 400.0;
+        double tile_time = (mainloop > epi ? mainloop : epi) + 300.0;
+        double t = rounds * tile_time;
+        if (t < best - 1e-9) { best = t; best_tn = tn; }
+    }
+    return best_tn;
+}
+
+int launch_v2(const otb_lora_linear_args* a, void* stream) {
+    GemmParams2 q;
+    GemmParams& p = q.g;
+    int cm = env_int("OTB_KA_CM", 2), cn = env_int("OTB_KA_CN", 1);
+    if (cm != 1 && cm != 2) cm = 2;
+    if (cn != 1 && cn != 2) cn = 1;
+    p.M = a->M; p.N = a->N; p.K = a->K; p.R = a->R;
+    p.Rp = (a->R + 15) / 16 * 16;
+    const int sms = otb_sm_count();
+    const int m_tiles = (a->M + BM - 1) / BM;
+    if (m_tiles < cm) cm = 1;                                   // nothing to share along M
+    p.tile_n = a->tile_n > 0 ? a->tile_n : choose_tile_n_v2(a->M, a->N, a->K, p.Rp, sms / (cm * cn) * (cm * cn), cm, cn);
+    OTB_CHECK_ARG(p.tile_n % 16 == 0 && p.tile_n >= 16 && p.tile_n + p.Rp <= 256, "tile_n %d invalid (multiple of 16, tile_n + rank <= 256)", p.tile_n);
+    p.num_kb = (a->K + BK - 1) / BK;
+    p.n_tiles = (a->N + p.tile_n - 1) / p.tile_n;
+    if (p.n_tiles < cn) cn = 1;
+    q.cm = cm; q.cn = cn; q.m_tiles = m_tiles;
+    q.super_m = (m_tiles + cm - 1) / cm;
+    q.super_n = (p.n_tiles + cn - 1) / cn;
+    p.tmem_cols = 512;
+    int stages = a->stages > 0 ? a->stages : MAX_STAGES;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    while (stages > 1 && (int)make_layout2(p.tile_n, p.Rp, stages).total + 1024 > SMEM_LIMIT) --stages;
+    p.stages = stages;
+    const SmemLayout2 L = make_layout2(p.tile_n, p.Rp, stages);
+    OTB_CHECK_ARG((int)L.total + 1024 <= SMEM_LIMIT, "tile does not fit shared memory");
+    p.scale = a->scale; p.dropout_p = a->dropout_p; p.seed = a->seed; p.offset = a->offset;
+    p.bias = a->bias; p.bias_dtype = a->bias_dtype;
+    p.y = (uint16_t*)a->y; p.t_out = (uint16_t*)a->t_out;
+
+    CUtensorMap tm_x, tm_w, tm_dn, tm_up;
+    int rc;
+    if ((rc = make_tmap(&tm_x, a->x, a->M, a->K, BM / cn, "x")) != OTB_OK) return rc;
+    if ((rc = make_tmap(&tm_w, a->w, a->N, a->K, p.tile_n / cm, "w")) != OTB_OK) return rc;
+    if (p.Rp > 0) {
+        if ((rc = make_tmap(&tm_dn, a->down, a->R, a->K, p.Rp / cm, "down")) != OTB_OK) return rc;
+        if ((rc = make_tmap(&tm_up, a->up, a->N, a->R, p.tile_n, "up")) != OTB_OK) return rc;
+    } else {
+        tm_dn = tm_x; tm_up = tm_x;
+    }
+    static thread_local int smem_set_for_dev = -1;
+    int dev = 0;
+    OTB_CUDA(cudaGetDevice(&dev));
+    if (smem_set_for_dev != dev) {
+        OTB_CUDA(cudaFuncSetAttribute(lora_linear_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        smem_set_for_dev = dev;
+    }
+    const int csize = cm * cn;
+    const int total_super = q.super_m * q.super_n;
+    int clusters = sms / csize;
+    if (clusters > total_super) clusters = total_super;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * csize));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = L.total + 1024;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (csize > 1) {
+        // not every SM can host a cluster member (GPC granularity): size the persistent grid to what is co-resident
+        static thread_local int max_clusters[5] = {0, 0, 0, 0, 0};
+        if (max_clusters[csize] == 0) {
+            int n = 0;
+            cudaLaunchConfig_t probe = cfg;
+            probe.gridDim = dim3((unsigned)(sms / csize * csize));
+            if (cudaOccupancyMaxActiveClusters(&n, lora_linear_kernel_v2, &probe) != cudaSuccess || n <= 0) n = sms / csize;
+            max_clusters[csize] = n;
+            (void)cudaGetLastError();
+        }
+        if (clusters > max_clusters[csize]) { clusters = max_clusters[csize]; cfg.gridDim = dim3((unsigned)(clusters * csize)); }
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lora_linear_kernel_v2, tm_x, tm_w, tm_dn, tm_up, q);
+    if (e != cudaSuccess) {
+        otb_set_error("launch of lora_linear_kernel_v2 (cluster %dx%d, tile_n %d, %d stages) failed: %s", cm, cn, p.tile_n, stages,
+                      cudaGetErrorString(e));
+        return OTB_ECUDA;
+    }
+    return OTB_OK;
+}
+
 extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
     OTB_CHECK_ARG(a != nullptr, "null args");
     OTB_CHECK_ARG(a->x && a->w && a->y, "null x / w / y");
@@ -394,6 +778,7 @@ extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
     OTB_CHECK_ARG((((uintptr_t)a->x | (uintptr_t)a->w | (uintptr_t)a->y | (uintptr_t)a->down | (uintptr_t)a->up |
                     (uintptr_t)a->t_out) & 15) == 0, "all tensor pointers must be 16-byte aligned");
     OTB_BIND(a->x);
+    if (env_int("OTB_KA_V1", 0) == 0) return launch_v2(a, stream);
     int sms = otb_sm_count();
     GemmParams p;
     p.M = a->M; p.N = a->N; p.K = a->K; p.R = a->R;

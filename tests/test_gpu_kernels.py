@@ -473,7 +473,8 @@ def test_loss_full_size_properties(K, dev):
         assert torch.allclose(g4.float(), 4 * g1.float(), rtol=2 ** -7)
         h = B // 2
         la, _ = K.ops.loss_fwd_bwd(pred[:h], tgt[:h], timestep=t[:h], sqrt_ac=sa, sqrt_1mac=s1, loss_weight_fn=1, upstream=1 / B)
-        assert torch.equal(la, l1[:h])                               # per-sample values do not depend on the batch
+        # per-sample values do not depend on the batch (the block split, hence the fp32 summation order, does)
+        assert torch.allclose(la, l1[:h], rtol=2e-6, atol=0)
 
 
 # ----------------------------------------------------------------------------------------------- K-a
