@@ -138,38 +138,53 @@ def leaf_flops(model, recompute: bool = False) -> tuple[float, int, list]:
 
 
 def time_leaf_kernels(model, dev, reps: int = 3) -> tuple[float, float, int]:
-    """Replay every K-a launch of one step (forward, dX, dA/dB per leaf) back to back with CUDA events on the
-    launching stream: returns (seconds per step spent in K-a, algorithmic flops per step, launches per step)."""
+    """Replay every K-a launch of one step (forward, dX, dA/dB of each of the 722 leaves, with that leaf's own
+    frozen weight / shadows, so the 4.4 GB of weights stream from HBM as in the real step) back to back with
+    CUDA events on the launching stream.  Returns (seconds per step spent in K-a, algorithmic flops per step,
+    launches per step)."""
     import torch
     from onetrainer_b200 import ops
     flops, launches, shapes = leaf_flops(model)
-    uniq = {}
-    for s in shapes:
-        uniq[s] = uniq.get(s, 0) + 1
-    bufs = {}
     g = torch.Generator(device=dev).manual_seed(0)
-    for (M, N, K, r) in uniq:
-        mk = lambda *sh: (torch.randn(*sh, device=dev, generator=g) * 0.05).bfloat16()  # noqa: E731
-        bufs[(M, N, K, r)] = dict(x=mk(M, K), w=mk(N, K), wt=mk(K, N), a=mk(r, K), at=mk(K, r), b=mk(N, r), bt=mk(r, N), dy=mk(M, N),
-                                  bias=mk(N), dA=torch.zeros(r, K, device=dev), dB=torch.zeros(N, r, device=dev))
+    acts = {}
+    mods = list(model.unet_lora.lora_modules.values())
+    plan = []
+    for m, (M, N, K, r) in zip(mods, shapes):
+        if (M, K) not in acts:
+            acts[(M, K)] = (torch.randn(M, K, device=dev, generator=g) * 0.05).bfloat16()
+        if (M, N) not in acts:
+            acts[(M, N)] = (torch.randn(M, N, device=dev, generator=g) * 0.05).bfloat16()
+        sh = m._operands()
+        plan.append((acts[(M, K)], acts[(M, N)], sh, m._scale(), torch.zeros(r, K, device=dev), torch.zeros(N, r, device=dev)))
 
     def one_step():
-        for key, cnt in uniq.items():
-            b = bufs[key]
-            for _ in range(cnt):
-                _, ts = ops.lora_linear(b["x"], b["w"], b["a"], b["b"], b["bias"], 1 / 32)
-                _, gs = ops.lora_linear(b["dy"], b["wt"], b["bt"], b["at"], None, 1 / 32)
-                ops.lora_grad_ab(b["x"], b["dy"], gs, ts, b["dA"], b["dB"])
+        for x, dy, sh, sc, dA, dB in plan:
+            _, ts = ops.lora_linear(x, sh["w"], sh["a"], sh["b"], sh["bias"], sc)
+            _, gs = ops.lora_linear(dy, sh["wt"], sh["bt"], sh["at"], None, sc)
+            ops.lora_grad_ab(x, dy, gs, ts, dA, dB)
 
-    one_step()
+    # captured once and replayed, so the CUDA events bracket device time only (eager launches of 10-30 us kernels
+    # are host-bound and would under-report the kernel)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        one_step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        one_step()
+    graph.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        one_step()
+        graph.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / 1e3 / reps, flops, launches
+    sec = e0.elapsed_time(e1) / 1e3 / reps
+    del graph
+    return sec, flops, launches
 
 
 def own_arm(args) -> None:
@@ -201,10 +216,19 @@ def own_arm(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphed = None
+    if not args.no_graph:
+        graphed = trainer.GraphedTrainStep(setup, model, cfg, host_batch)
+        launches_per_step = None
+
     def step_resident():
+        if graphed is not None:
+            return graphed.step()                      # batch already staged; device-side work only
         return trainer.train_step(setup, model, dev_batch, cfg, bucket)
 
     def step_e2e():
+        if graphed is not None:
+            return graphed.step(host_batch).item()     # host batch -> pinned staging -> H2D inside the graph -> D2H loss
         b = trainer.batch_to_device(host_batch, dev, non_blocking=True)
         return trainer.train_step(setup, model, b, cfg, bucket).item()
 
@@ -222,10 +246,16 @@ def own_arm(args) -> None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / 1e3, ops.LAUNCHES - l0, out
 
+    l_before = ops.LAUNCHES
+    if graphed is None:
+        trainer.train_step(setup, model, dev_batch, cfg, bucket)
+    launches_eager_step = ops.LAUNCHES - l_before     # kernels of ours per step (a graph replays exactly these)
     for _ in range(max(args.warmup, 3)):
         step_resident()
     with ClockSampler(local_rank) as clk:
         sec, launches, last_loss = timed(step_resident, args.steps)
+    if graphed is not None:
+        launches = graphed.launches_per_step * args.steps
     clocks = clk.summary()
     for _ in range(2):
         step_e2e()
@@ -253,7 +283,7 @@ def own_arm(args) -> None:
             "samples_per_sec": value * B, "optimizer_steps_per_sec": args.steps / sec,
             "e2e": {"value": world * args.steps / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": sec_e2e / args.steps * 1e3},
-            "gpu_launches": launches, "loss": float(last_loss), "clocks": clocks,
+            "gpu_launches": launches, "cuda_graph": graphed is not None, "loss": float(last_loss), "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "lora_linear_kernel (+ lora_grad_kernel)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": f"{peak_kind} bf16_tflops_sustained",
                          "algorithmic_flops_per_step": ka_flops, "launches_per_step": ka_launches,

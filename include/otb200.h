@@ -115,6 +115,13 @@ typedef struct otb_optim_tensor {
     int32_t     flags;        /* bit0: stochastic rounding of p; bit1: maximize (g = -g)    */
 } otb_optim_tensor;
 
+/* per-step values a captured CUDA graph must re-read on every replay (device memory) */
+typedef struct otb_optim_dyn {
+    uint64_t seed, offset;             /* SR Philox key / step number                        */
+    float    ema_one_minus_decay;
+    int32_t  do_ema;
+} otb_optim_dyn;
+
 typedef struct otb_optim_launch {
     const otb_optim_tensor* tensors;   /* device array [n_tensors]                          */
     const int32_t* chunk_tensor;       /* device [n_chunks] tensor index of each chunk      */
@@ -128,6 +135,7 @@ typedef struct otb_optim_launch {
     float    ema_one_minus_decay;      /* 1 - min((1+s)/(10+s), decay); used iff do_ema     */
     int32_t  do_ema;                   /* 1 on EMA update steps ((s+1) % interval == 0)     */
     const float* clip_coef;            /* device scalar: g is scaled by it first, or NULL   */
+    const otb_optim_dyn* dyn;          /* optional device override of seed/offset/ema_*     */
 } otb_optim_launch;
 
 int otb_adamw_sr_ema_multi(const otb_optim_launch* args, void* stream);
@@ -220,6 +228,8 @@ typedef struct otb_noise_args {
     /* RNG */
     uint64_t seed, offset;
     int64_t  sample_base;          /* global index of sample 0 of this rank's batch (DP invariance)   */
+    const uint64_t* rng_dev;       /* optional device {seed, offset}: overrides the two scalars above so a
+                                      captured CUDA graph draws fresh noise on every replay              */
 } otb_noise_args;
 
 int otb_noise_addnoise(const otb_noise_args* args, void* stream);

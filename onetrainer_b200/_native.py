@@ -54,8 +54,12 @@ class OptimLaunch(C.Structure):
         ("n_tensors", _i32), ("n_chunks", _i32), ("chunk_elems", _i32), ("flavor", _u32),
         ("seed", _u64), ("offset", _u64),
         ("ema_one_minus_decay", _f32), ("do_ema", _i32),
-        ("clip_coef", _vp),
+        ("clip_coef", _vp), ("dyn", _vp),
     ]
+
+
+class OptimDyn(C.Structure):
+    _fields_ = [("seed", _u64), ("offset", _u64), ("ema_one_minus_decay", _f32), ("do_ema", _i32)]
 
 
 class ShadowTensor(C.Structure):
@@ -79,7 +83,7 @@ class NoiseArgs(C.Structure):
         ("min_timestep", _i32), ("max_timestep", _i32),
         ("noising_weight", _f32), ("noising_bias", _f32),
         ("shift_c1", _f32), ("shift_c2", _f32),
-        ("seed", _u64), ("offset", _u64), ("sample_base", _i64),
+        ("seed", _u64), ("offset", _u64), ("sample_base", _i64), ("rng_dev", _vp),
     ]
 
 

@@ -110,6 +110,7 @@ __device__ __forceinline__ float normal1(const otb_noise_args& a, uint32_t strea
 // LD: compile-time latent dtype (-1 = read a.latent_dtype)
 template <int U, int LD>
 __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_args a) {
+    if (a.rng_dev != nullptr) { a.seed = a.rng_dev[0]; a.offset = a.rng_dev[1]; }
     const int b = blockIdx.y;
     const int64_t chw = (int64_t)a.C * a.hw;
     const int64_t gs = a.sample_base + b;

@@ -189,3 +189,103 @@ def train_step(setup: DiffusionSetup, model: StandInModel, batch: dict, config, 
         model.ema.step(model.parameters, model.train_progress.global_step // config.gradient_accumulation_steps)
     model.train_progress.next_step(config.batch_size)
     return loss.detach()
+
+
+class GraphedTrainStep:
+    """The whole step as ONE CUDA graph (streams and graphs instead of a tracing compiler).
+
+    The step launches ~11 k kernels (722 leaves x 3 fused launches, plus the stand-in's attention /
+    norm / GEGLU glue); eager python dispatch of those costs more than the GPU work.  Capturing the
+    step once removes the host from the loop: per step the host only (1) copies the next batch into
+    pinned staging buffers, (2) rewrites a few pinned words — Philox keys, EMA schedule, per-tensor
+    AdamW scalars (onetrainer_b200/step_state.py, FusedAdamDriver.host_prepare) — and (3) replays.
+    The H2D batch copy, the noise/loss kernels, every leaf, the NCCL allreduce, grad-norm, AdamW and
+    the shadow refresh are all inside the graph, on one stream.
+    """
+
+    def __init__(self, setup: DiffusionSetup, model: StandInModel, config, example_batch: dict, warmup: int = 3):
+        from .. import step_state
+        self.setup, self.model, self.config = setup, model, config
+        dev = setup.train_device
+        self.state = step_state.DeviceStepState(dev)
+        self.host_batch = {k: ([torch.empty_like(t).pin_memory() for t in v] if isinstance(v, list) else torch.empty_like(v).pin_memory())
+                           for k, v in example_batch.items()}
+        self.dev_batch = {k: ([torch.empty_like(t, device=dev) for t in v] if isinstance(v, list) else torch.empty_like(v, device=dev))
+                          for k, v in example_batch.items()}
+        self.bucket = dp.GradientBucket(None)
+        self.driver = model.optimizer.otb_driver
+        self.loss = None
+        self.graph = None
+        self.set_batch(example_batch)
+        step_state.activate(self.state)
+        # warm-up on a side stream (allocator, lazy tables, cuBLAS/SDPA workspaces) as torch's capture rules require
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._device_part(first=True)
+                self._after_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.driver.freeze_for_graph()
+        self._host_part()
+        from .. import ops
+        before = ops.LAUNCHES
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._device_part(first=False)
+        self.launches_per_step = ops.LAUNCHES - before      # libotb200 kernels inside one replay
+        self._after_step()
+
+    # host-side work that must precede every replay
+    def _host_part(self) -> None:
+        step = self.model.train_progress.global_step
+        self.state.set_noise_key(step, 0)           # predict(): generator.manual_seed(global_step), first draw
+        self.driver.host_prepare()
+
+    def _device_part(self, first: bool) -> None:
+        if first:
+            self._host_part()                       # eager warm-up: host and device parts interleave as in train_step
+        self.state.upload()
+        for k, v in self.host_batch.items():
+            if isinstance(v, list):
+                for d, h in zip(self.dev_batch[k], v):
+                    d.copy_(h, non_blocking=True)
+            else:
+                self.dev_batch[k].copy_(v, non_blocking=True)
+        model, cfg = self.model, self.config
+        data = self.setup.predict(model, self.dev_batch, cfg, model.train_progress)
+        loss = self.setup.calculate_loss(model, self.dev_batch, data, cfg) / cfg.gradient_accumulation_steps
+        loss.backward()
+        if dp.world_size() > 1:
+            if self.bucket.arena is None:
+                self.bucket.arena = model.unet_lora.grad_arena
+            self.driver.grad_prescale = self.bucket.allreduce([p.grad for p in model.parameters if p.grad is not None])
+        self.driver.device_step()
+        model.optimizer.zero_grad(set_to_none=True)
+        self.loss = loss.detach()
+
+    def _after_step(self) -> None:
+        self.model.train_progress.next_step(self.config.batch_size)
+
+    def set_batch(self, batch: dict) -> None:
+        """Stage the next batch in pinned memory (host memcpy); the H2D copy happens inside the graph."""
+        for k, v in batch.items():
+            if isinstance(v, list):
+                for h, t in zip(self.host_batch[k], v):
+                    h.copy_(t)
+            else:
+                self.host_batch[k].copy_(v)
+
+    def step(self, batch: dict | None = None) -> torch.Tensor:
+        """One optimisation step; returns the loss as a device scalar (read it with .item() when needed)."""
+        if batch is not None:
+            self.set_batch(batch)
+        self._host_part()
+        self.graph.replay()
+        self._after_step()
+        return self.loss
+
+    def close(self) -> None:
+        from .. import step_state
+        step_state.activate(None)

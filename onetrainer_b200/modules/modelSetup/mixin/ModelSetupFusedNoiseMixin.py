@@ -14,7 +14,7 @@ from abc import ABCMeta
 import torch
 from torch import Generator, Tensor
 
-from .... import dp, ops
+from .... import dp, ops, step_state
 from .... import _native as N
 from ....rng import draw_key
 from ....util_shapes import flatten_chw
@@ -48,6 +48,11 @@ class ModelSetupFusedNoiseMixin(metaclass=ABCMeta):
         coef_x0, coef_noise = self.__tables
         B, C, hw = flatten_chw(latent_image.shape)
         seed, offset = draw_key(generator, dev)
+        state = step_state.active()
+        rng_dev = None
+        if state is not None:                      # CUDA-graph mode: the key lives in device memory
+            state.set_noise_key(seed, offset)
+            rng_dev = state.noise_ptr
         kw = timestep_kernel_args(num_train_timesteps, deterministic, config, latent_width, latent_height)
         out = ops.noise_addnoise(
             latent=latent_image.contiguous(), coef_x0=coef_x0, coef_noise=coef_noise, B=B, C_=C, hw=hw,
@@ -55,7 +60,8 @@ class ModelSetupFusedNoiseMixin(metaclass=ABCMeta):
             cast_dtype=train_dtype or latent_image.dtype, target=_TARGETS["flow" if flow else prediction_type],
             latent_scale=latent_scale, latent_shift=latent_shift,
             offset_noise_weight=config.offset_noise_weight, perturbation_noise_weight=config.perturbation_noise_weight,
-            seed=seed, offset=offset, sample_base=dp.global_sample_base(B), want_sigma=flow, shape=latent_image.shape, **kw)
+            seed=seed, offset=offset, sample_base=dp.global_sample_base(B), want_sigma=flow, shape=latent_image.shape,
+            rng_dev=rng_dev, **kw)
         res = {"timestep": out["timestep"], "noisy": out["noisy_cast"], "target": out["target"]}
         if flow:
             res["sigma"] = out["sigma"].view(B, *([1] * (latent_image.dim() - 1)))

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import torch
 
-from .... import ops
+from .... import ops, step_state
 from .... import _native as N
 
 
@@ -59,6 +59,9 @@ class FusedAdamDriver:
         self.step_count = 0             # SR Philox offset
         self.last_norm_coef: torch.Tensor | None = None
         self._single = {}               # id(p) -> one-entry table for step_parameter
+        self._frozen_active = None
+        self._last_active = []
+        self._dyn = (0, 0, 0.0, False)
         self._prescale_dev, self._prescale_val = None, None
 
     # -- table construction ---------------------------------------------------------------
@@ -136,14 +139,41 @@ class FusedAdamDriver:
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        if self.host_prepare():
+            self.device_step()
+        return loss
+
+    def host_prepare(self) -> bool:
+        """Everything `step()` does on the HOST: state init, step counters, per-tensor scalars into the
+        pinned table, the per-step dynamic words.  Under a captured CUDA graph this runs before every
+        replay; the graph itself contains only `device_step()`."""
         for group in self.opt.param_groups:
             _check_group(group)
-        active = self._active()
-        if not active:
-            return loss
-        table = self._ensure_table(active)
-        table.set_grad_pointers([p.grad for p, _ in active])
+        if self._frozen_active is not None:
+            active = self._frozen_active          # graph mode: same tensors every step, gradients live in static memory
+        else:
+            active = self._active()
+            if not active:
+                return False
+            table = self._ensure_table(active)
+            table.set_grad_pointers([p.grad for p, _ in active])
+        table = self.table
         self._fill_scalars(table, active)
+        do_ema, omd = False, 0.0
+        if self.ema is not None and self.ema_step_fn is not None:
+            do_ema, omd = self.ema.fused_schedule(int(self.ema_step_fn()))
+        self.step_count += 1
+        self._dyn = (torch.initial_seed(), self.step_count, omd, do_ema)
+        state = step_state.active()
+        if state is not None:
+            state.set_optim(*self._dyn)
+        self._last_active = active
+        return True
+
+    @torch.no_grad()
+    def device_step(self) -> None:
+        """The DEVICE side of `step()`: table upload, [grad-norm], fused clip+AdamW(+SR)(+EMA)."""
+        table = self.table
         table.upload()
         clip = None
         if self.clip_max_norm is not None:
@@ -154,17 +184,17 @@ class FusedAdamDriver:
                 self._prescale_dev = torch.full((1,), self.grad_prescale, dtype=torch.float32, device=table.device)
                 self._prescale_val = self.grad_prescale
             clip = self._prescale_dev
-        do_ema, omd = False, 0.0
-        if self.ema is not None and self.ema_step_fn is not None:
-            s = int(self.ema_step_fn())
-            do_ema, omd = self.ema.fused_schedule(s)
-        self.step_count += 1
-        ops.adamw_sr_ema_multi(table, flavor=self.flavor, seed=torch.initial_seed(), offset=self.step_count,
-                               ema_one_minus_decay=omd, do_ema=do_ema, clip_coef=clip)
-        _bump_versions([p for p, _ in active])
+        seed, offset, omd, do_ema = self._dyn
+        state = step_state.active()
+        ops.adamw_sr_ema_multi(table, flavor=self.flavor, seed=seed, offset=offset, ema_one_minus_decay=omd, do_ema=do_ema,
+                               clip_coef=clip, dyn=state.dyn_ptr if state is not None else None)
+        _bump_versions([p for p, _ in self._last_active])
         for hook in self.post_step_hooks:
             hook()
-        return loss
+
+    def freeze_for_graph(self) -> None:
+        """Pin the current parameter/gradient set: later host_prepare() calls skip rediscovery."""
+        self._frozen_active = self._last_active
 
     @torch.no_grad()
     def step_parameter(self, p, group, i):

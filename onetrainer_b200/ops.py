@@ -97,7 +97,7 @@ def noise_addnoise(*, latent=None, noise_in=None, coef_x0=None, coef_noise=None,
                    offset_noise_weight: float = 0.0, perturbation_noise_weight: float = 0.0,
                    min_timestep: int = 0, max_timestep: int = 1000, noising_weight: float = 0.0,
                    noising_bias: float = 0.0, shift: float = 1.0, seed: int = 0, offset: int = 0,
-                   sample_base: int = 0, want_sigma: bool = False, shape=None) -> dict:
+                   sample_base: int = 0, want_sigma: bool = False, shape=None, rng_dev: torch.Tensor | None = None) -> dict:
     """One launch of the pre-network half of the step kernel; returns the requested tensors."""
     N.require_cuda(latent, noise_in, coef_x0, coef_noise, timestep)
     shape = tuple(shape) if shape is not None else (B, C_ * hw)
@@ -133,7 +133,7 @@ def noise_addnoise(*, latent=None, noise_in=None, coef_x0=None, coef_noise=None,
         min_timestep=int(min_timestep), max_timestep=int(max_timestep),
         noising_weight=float(noising_weight), noising_bias=float(noising_bias),
         shift_c1=float(T * shift), shift_c2=float(shift - 1),
-        seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1), sample_base=int(sample_base))
+        seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1), sample_base=int(sample_base), rng_dev=N.ptr(rng_dev))
     N.check(N.lib().otb_noise_addnoise(C.byref(a), _stream()), "otb_noise_addnoise")
     _count()
     out.update(x0=x0, noise=noise, noisy=noisy, noisy_cast=noisy_cast, target=tgt, timestep=ts, sigma=sigma)
@@ -311,12 +311,12 @@ class OptimTable:
             self.dev[: raw.size].copy_(torch.from_numpy(raw.copy()))
 
     def launch_args(self, *, flavor=N.FLAVOR_TORCH_CUDA, seed=0, offset=0, ema_one_minus_decay=0.0, do_ema=False,
-                    clip_coef: torch.Tensor | None = None) -> N.OptimLaunch:
+                    clip_coef: torch.Tensor | None = None, dyn: torch.Tensor | None = None) -> N.OptimLaunch:
         return N.OptimLaunch(
             tensors=self.dev.data_ptr(), chunk_tensor=self.chunk_tensor.data_ptr(), chunk_index=self.chunk_index.data_ptr(),
             n_tensors=self.n, n_chunks=self.n_chunks, chunk_elems=self.chunk_elems, flavor=int(flavor),
             seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1),
-            ema_one_minus_decay=float(ema_one_minus_decay), do_ema=1 if do_ema else 0, clip_coef=N.ptr(clip_coef))
+            ema_one_minus_decay=float(ema_one_minus_decay), do_ema=1 if do_ema else 0, clip_coef=N.ptr(clip_coef), dyn=N.ptr(dyn))
 
 
 def adam_scalars(lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, step: float,

@@ -310,9 +310,14 @@ def test_add_noise_mixins_vs_golden(P, dev, golden):
     noisy_dev = D()._add_noise_discrete(x0, noise, t, _sched_betas())
     np.testing.assert_allclose(noisy_dev.cpu().numpy(), g["noisy"], rtol=3e-7, atol=1e-7)
     fx0 = torch.from_numpy(g["flow_x0"]).to(dev)
-    fnoisy, sig = F()._add_noise_discrete(fx0, noise, t, torch.zeros(1000))
+    from onetrainer_b200.modules.util.DiffusionScheduleCoefficients import flow_sigmas
+    f = F()
+    f._ModelSetupFlowMatchingMixin__sigma, f._ModelSetupFlowMatchingMixin__one_minus_sigma = (x.to(dev) for x in flow_sigmas(1000, "cpu"))
+    fnoisy, sig = f._add_noise_discrete(fx0, noise, t, torch.zeros(1000))
     assert np.array_equal(fnoisy.cpu().numpy(), g["flow_noisy"]) and sig.shape == (4, 1, 1, 1)
     assert np.array_equal(sig.flatten().cpu().numpy(), g["flow_sigmas"])
+    fnoisy_dev, _ = F()._add_noise_discrete(fx0, noise, t, torch.zeros(1000))      # tables built on the GPU: fp32-rounding close
+    np.testing.assert_allclose(fnoisy_dev.cpu().numpy(), g["flow_noisy"], rtol=3e-7, atol=1e-7)
     with pytest.raises(NotImplementedError):
         D()._add_noise_continuous(x0, noise, t, None)
 
