@@ -12,7 +12,8 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .. import dp
+from .. import dp, step_state
+from ..rng import PhiloxKey
 from ..modules.module.EMAModule import EMAModuleWrapper
 from ..modules.module.LoRAModule import LoRAModuleWrapper
 from ..modules.modelSetup.mixin.ModelSetupDiffusionLossMixin import ModelSetupDiffusionLossMixin
@@ -60,8 +61,11 @@ class DiffusionSetup(ModelSetupFusedNoiseMixin, ModelSetupNoiseMixin, ModelSetup
     def predict(self, model: StandInModel, batch: dict, config, train_progress: TrainProgress, *, deterministic: bool = False) -> dict:
         with model.autocast_context:
             batch_seed = 0 if deterministic else train_progress.global_step
-            generator = torch.Generator(device=config.train_device)
-            generator.manual_seed(batch_seed)
+            if step_state.active() is not None:      # inside a CUDA-graph capture torch cannot build a CUDA generator
+                generator = PhiloxKey(batch_seed, config.train_device)
+            else:
+                generator = torch.Generator(device=config.train_device)
+                generator.manual_seed(batch_seed)
             latent_image = batch["latent_image"]
             T = model.noise_scheduler.config["num_train_timesteps"]
             ptype = model.noise_scheduler.config["prediction_type"]
@@ -108,7 +112,7 @@ def build_model(kind: str, config, device, *, train_dtype=torch.bfloat16, lora_w
     unet = unet.to(dtype=train_dtype)
     unet.requires_grad_(False)
     unet.train()
-    sched = standin.StandInScheduler(standin_betas(), prediction_type)
+    sched = standin.StandInScheduler(standin_betas().to(device), prediction_type)   # device-resident: `.to()` is then a no-op under capture
     model = StandInModel(unet, sched, 0.13025 if kind == "sdxl" else 0.18215, train_dtype, sdxl=(kind == "sdxl"))
     model.unet_lora = LoRAModuleWrapper(unet, "lora_unet", config, ["attentions"])
     model.unet_lora.set_dropout(config.dropout_probability)
@@ -244,8 +248,8 @@ class GraphedTrainStep:
         self.driver.host_prepare()
 
     def _device_part(self, first: bool) -> None:
-        if first:
-            self._host_part()                       # eager warm-up: host and device parts interleave as in train_step
+        if first:                                   # eager warm-up: the optimizer's host part runs after backward (below)
+            self.state.set_noise_key(self.model.train_progress.global_step, 0)
         self.state.upload()
         for k, v in self.host_batch.items():
             if isinstance(v, list):
@@ -261,6 +265,9 @@ class GraphedTrainStep:
             if self.bucket.arena is None:
                 self.bucket.arena = model.unet_lora.grad_arena
             self.driver.grad_prescale = self.bucket.allreduce([p.grad for p in model.parameters if p.grad is not None])
+        if first:
+            self.driver.host_prepare()              # discovers the gradients, builds the table, fills the scalars
+            self.state.upload()                     # the optimizer's dynamic words were written just now
         self.driver.device_step()
         model.optimizer.zero_grad(set_to_none=True)
         self.loss = loss.detach()

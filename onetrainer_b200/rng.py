@@ -11,6 +11,28 @@ from __future__ import annotations
 import torch
 
 
+class PhiloxKey:
+    """A stand-in for `torch.Generator` carrying just what the kernels consume (seed, offset, device).
+    torch refuses to construct a CUDA generator while a CUDA graph is being captured; a captured step
+    uses this instead — the draws are identical because only (seed, offset) ever reach the kernels."""
+
+    def __init__(self, seed: int, device):
+        self._seed, self._offset, self.device = int(seed), 0, torch.device(device)
+
+    def manual_seed(self, seed: int):
+        self._seed, self._offset = int(seed), 0
+        return self
+
+    def initial_seed(self) -> int:
+        return self._seed
+
+    def get_offset(self) -> int:
+        return self._offset
+
+    def set_offset(self, offset: int) -> None:
+        self._offset = int(offset)
+
+
 def draw_key(generator: torch.Generator | None, device=None) -> tuple[int, int]:
     """Returns (seed, offset) and consumes one tick of the generator."""
     if generator is None:
