@@ -42,7 +42,32 @@ for name, M, N, K, cnt in shapes:
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / 5 / nrep
         fl = 2.0 * m * n * k + 2.0 * m * R * (k + n)
+        ref_us = 0.0
+        if len(sys.argv) > 3 and sys.argv[3] == "ref":
+            # the reference's op sequence (LoRAModule.py:322-323) through torch/cuBLAS on the same operands
+            import torch.nn.functional as F
+
+            def run_ref():
+                for i in range(nrep):
+                    F.linear(xs[i & 1], ws[i], bias) + F.linear(F.linear(xs[i & 1], a), b) * (1 / 32)
+            with torch.cuda.stream(s):
+                run_ref()
+            torch.cuda.synchronize()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                run_ref()
+            g2.replay(); torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                g2.replay()
+            e1.record(); torch.cuda.synchronize()
+            ref_us = e0.elapsed_time(e1) * 1e3 / 5 / nrep
+            del g2
         tot_t += us * cnt; tot_f += fl * cnt
-        print(f"{name:16s} {role} M={m:6d} N={n:6d} K={k:5d}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  x{cnt}", flush=True)
+        print(f"{name:16s} {role} M={m:6d} N={n:6d} K={k:5d}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  x{cnt}"
+              + (f"   torch 3-GEMM path {ref_us:8.1f} us ({ref_us / us:.2f}x)" if ref_us else ""), flush=True)
+        tot_ref = globals().get("tot_ref", 0.0) + ref_us * cnt
+        globals()["tot_ref"] = tot_ref
         del g
-print(f"weighted over one step (fwd+dX): {tot_t / 1e3:.2f} ms, {tot_f / tot_t / 1e6:.1f} TFLOP/s")
+print(f"weighted over one step (fwd+dX): {tot_t / 1e3:.2f} ms, {tot_f / tot_t / 1e6:.1f} TFLOP/s"
+      + (f"; torch 3-GEMM path {globals().get('tot_ref', 0.0) / 1e3:.2f} ms" if globals().get("tot_ref") else ""))
