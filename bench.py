@@ -291,10 +291,16 @@ def own_arm(args) -> None:
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # Leave without tearing the communicator down: with the NCCL allreduce captured inside a live CUDA graph,
+        # destroy_process_group() blocked for minutes on the B200 box (gpurun_out/bench_n2.err, round 1).  Every
+        # collective this process will ever issue has completed (the timed regions end on an allreduce + sync),
+        # so the ranks can exit independently.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -107,16 +107,19 @@ __host__ __device__ __forceinline__ float otb_u01(uint32_t x) {
 // Box-Muller on two 32-bit words -> two N(0,1) fp32 values.
 //   u1 = ((a>>8)+0.5) * 2^-24  in (0,1);   th = (((int)b>>8)+0.5) * 2^-23 * pi  in (-pi,pi)
 //   r  = sqrt(-2 ln u1);  z0 = r cos th;  z1 = r sin th
-// The bulk-noise kernel uses the MUFU fast paths (__logf/__sincosf, abs err ~1e-6, see
-// DESIGN.md); the oracle evaluates the same definition with libm.
+// The bulk-noise kernel evaluates this with one MUFU op per transcendental (lg2 / sqrt / sin / cos
+// .approx, abs err ~1e-6) and single-rounding FMAs for the affine maps; the oracle
+// evaluates the same definition with libm in fp64 (tests: 2e-5 absolute).
+__device__ __forceinline__ float otb_mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float otb_mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float otb_mufu_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float otb_mufu_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void otb_box_muller_fast(uint32_t a, uint32_t b, float& z0, float& z1) {
-    float u1 = ((float)(a >> 8) + 0.5f) * 5.9604644775390625e-08f;
-    float th = ((float)((int32_t)b >> 8) + 0.5f) * 1.1920928955078125e-07f * 3.14159265358979323846f;
-    float r = sqrtf(-2.0f * __logf(u1));
-    float s, c;
-    __sincosf(th, &s, &c);
-    z0 = r * c;
-    z1 = r * s;
+    const float u1 = fmaf((float)(a >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);          // (v + 0.5) * 2^-24
+    const float th = fmaf((float)((int32_t)b >> 8), 3.7450702829239286e-07f, 1.8725351414619643e-07f);   // (v + 0.5) * 2^-23 * pi
+    const float r = otb_mufu_sqrt(otb_mufu_lg2(u1) * -1.3862943611198906f);                               // sqrt(-2 ln u1)
+    z0 = r * otb_mufu_cos(th);
+    z1 = r * otb_mufu_sin(th);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -125,6 +128,12 @@ __device__ __forceinline__ void otb_box_muller_fast(uint32_t a, uint32_t b, floa
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
 __device__ __forceinline__ uint16_t float_to_bf16_bits_rn(float f) {
     return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+// two floats -> packed bf16x2 (lo in bits [0,16)), round-to-nearest-even, ONE F2FP.BF16.PACK_AB
+__device__ __forceinline__ uint32_t pack2_bf16_rn(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 // round a float to the nearest bf16 and return it as float (emulates a bf16 store+load)
 __device__ __forceinline__ float round_bf16(float f) { return bf16_bits_to_float(float_to_bf16_bits_rn(f)); }

@@ -141,7 +141,7 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    return (uint32_t)float_to_bf16_bits_rn(a) | ((uint32_t)float_to_bf16_bits_rn(b) << 16);
+    return pack2_bf16_rn(a, b);
 }
 
 // smem carve-up (all tile bases stay 1024 B aligned because tile_n and Rp are multiples of 16)
@@ -595,6 +595,319 @@ lora_linear_kernel_v2(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     }
 }
 
+// =====================================================================================
+// v3: CTA pairs — tcgen05.mma.cta_group::2, 256-row tiles
+// =====================================================================================
+// What v2 left on the table (profiles/r01_ncu_ka_v2.md): with 128 x (256+32) tiles every SM has to ingest
+// 52 KB of operands per 64-wide k-block for 576 tensor-pipe cycles — 90 B/clk, but an SM receives
+// only ~42.5 B/clk from L2 (the 6300 B/clk chip-wide LTS cap / 148; cuBLAS tops out against the same
+// wall).  ncu shows the tensor pipe 47 % active, exactly 42.5 / 90.  TMA multicast does not help: the
+// tile still has to LAND in each SM.  What helps is making each SM ingest less per flop:
+//   * two CTAs on the two SMs of a TPC form ONE 256 x tile_n tile.  Each CTA stages its own 128 rows
+//     of x but only HALF of the [w; down] rows; tcgen05.mma.cta_group::2 reads both halves, each CTA's
+//     TMEM receives the accumulators of its own 128 rows.  Ingest per SM per k-block drops from
+//     (128 + N')·128 B to (128 + N'/2)·128 B;
+//   * tile_n may exceed 256 (two N-chunks per k-step, one 512-column accumulator) when that turns
+//     a 2-round problem into a 1-round one (e.g. M=4096, N=1280: 16 x 4 tiles of 256 x 320 on 74 pairs);
+//   * otherwise two accumulator stages as in v2: the epilogue of tile i overlaps the mainloop of i+1.
+// Roles per CTA: warp 0 TMA producer (both CTAs, each loads its halves, completion is signalled on the
+// LEADER's mbarrier), warp 1 MMA issuer (leader CTA only; commits are multicast to both CTAs), warps 2-5
+// epilogue (both CTAs; the rank-R hand-off and the accumulator release arrive on the leader's barriers).
+struct GemmParams3 {
+    GemmParams g;          // g.tile_n: width of the pair tile; g.n_tiles; g.stages
+    int chunks;            // N-chunks per k-step (1 or 2), each tile_n / chunks <= 256 wide
+    int acc_stages;        // 2 when tile_n + Rp <= 256, else 1
+    int pair_m_tiles;      // ceil(M / 256)
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+// wait on an own barrier whose arrivals come from the peer CTA as well
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    long long t0 = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if ((++spins & 1023u) == 0) {
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > WAIT_LIMIT_CYCLES) __trap();
+        }
+    }
+}
+// TMA load issued by either CTA of a pair; the bytes complete on `bar`, a shared::cluster address that may
+// live in the peer (leader) CTA
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once the preceding tcgen05 ops retire
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+struct SmemLayout3 {
+    uint32_t stage_bytes, x_off, w_off, dn_off, up_off, up_bytes, t_off, bar_off, total;
+};
+__host__ __device__ inline SmemLayout3 make_layout3(int tile_n, int Rp, int stages, int up_bufs) {
+    SmemLayout3 L;
+    L.x_off = 0;
+    L.w_off = BM * 128;
+    L.dn_off = L.w_off + (uint32_t)(tile_n / 2) * 128;
+    L.stage_bytes = L.dn_off + (uint32_t)(Rp / 2) * 128;
+    L.up_off = L.stage_bytes * stages;
+    L.up_bytes = Rp ? (uint32_t)(tile_n / 2) * 128 : 0;
+    L.t_off = L.up_off + up_bufs * L.up_bytes;
+    L.bar_off = L.t_off + (Rp ? BM * 128 : 0);
+    L.total = L.bar_off + 512;
+    return L;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                      const __grid_constant__ CUtensorMap tm_dn, const __grid_constant__ CUtensorMap tm_up,
+                      const GemmParams3 q) {
+    const GemmParams& p = q.g;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int up_bufs = q.acc_stages;
+    const SmemLayout3 L = make_layout3(p.tile_n, p.Rp, p.stages, up_bufs);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool lora = p.Rp > 0;
+    const uint32_t crank = cluster_ctarank();          // 0 = leader
+    const bool leader = crank == 0;
+    const uint32_t cid = cluster_id_x(), ncl = cluster_nctaid_x();
+    const int total_tiles = q.pair_m_tiles * p.n_tiles;
+    const int wc = p.tile_n / q.chunks;                // chunk width (columns of the pair tile)
+    const int wch = wc / 2;                            // rows of w / up per CTA per chunk
+    const int acc_stride = q.acc_stages == 2 ? 256 : 512;
+
+    const uint32_t bar_base = smem_base + L.bar_off;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+    auto misc = [&](int i) { return bar_base + 8u * (2 * MAX_STAGES + i); };
+    // misc: 0,1 up_full(leader)  2,3 up_empty  4,5 t_full  6 t_ready(leader)  8,9 d_full  10,11 acc_empty(leader)  12 tmem slot
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bar_off + 8u * (2 * MAX_STAGES + 12));
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
+        if (lora) { prefetch_tmap(&tm_dn); prefetch_tmap(&tm_up); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(misc(0 + i), 1); mbar_init(misc(2 + i), 1); mbar_init(misc(4 + i), 1);
+            mbar_init(misc(8 + i), 1); mbar_init(misc(10 + i), 256);
+        }
+        mbar_init(misc(6), 256);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(misc(12), 512u);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                         // the peer's barriers and TMEM exist before anything crosses CTAs
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            int it = 0;
+            const uint32_t stage_tx = 2u * L.stage_bytes, up_tx = 2u * L.up_bytes;
+            for (uint32_t st = cid; st < (uint32_t)total_tiles; st += ncl, ++it) {
+                const int mt = st / p.n_tiles, nt = st % p.n_tiles;
+                const int m0 = mt * 2 * BM + (int)crank * BM, n0 = nt * p.tile_n;
+                if (lora) {
+                    const int ub = it % up_bufs;
+                    mbar_wait(misc(2 + ub), (uint32_t)((it / up_bufs) & 1) ^ 1);                 // up_empty (own)
+                    if (leader) mbar_expect_tx(misc(0 + ub), up_tx);
+                    const uint32_t bar = mapa_u32(misc(0 + ub), 0);
+                    for (int c = 0; c < q.chunks; ++c)
+                        tma_load_2d_2sm(smem_base + L.up_off + ub * L.up_bytes + (uint32_t)(c * wch) * 128, &tm_up, bar, 0,
+                                        n0 + c * wc + (int)crank * wch);
+                }
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    const uint32_t stg = smem_base + L.stage_bytes * s;
+                    if (leader) mbar_expect_tx(full_bar(s), stage_tx);
+                    const uint32_t bar = mapa_u32(full_bar(s), 0);
+                    tma_load_2d_2sm(stg + L.x_off, &tm_x, bar, kb * BK, m0);
+                    for (int c = 0; c < q.chunks; ++c)
+                        tma_load_2d_2sm(stg + L.w_off + (uint32_t)(c * wch) * 128, &tm_w, bar, kb * BK, n0 + c * wc + (int)crank * wch);
+                    if (lora) tma_load_2d_2sm(stg + L.dn_off, &tm_dn, bar, kb * BK, (int)crank * (p.Rp / 2));
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (lane == 0 && leader) {
+            const uint32_t idesc_w = umma_idesc_bf16(2 * BM, wc);
+            const uint32_t idesc_dn = umma_idesc_bf16(2 * BM, p.Rp);
+            int s = 0; uint32_t ph = 0;
+            int it = 0, pending = -1;
+            auto issue_up = [&](int j) {      // D += T(j) . up(j)^T, then hand the accumulator to the epilogue
+                const int as = j % q.acc_stages, ub = j % up_bufs;
+                mbar_wait_cluster(misc(6), (uint32_t)(j & 1));                              // t_ready: both CTAs parked T(j)
+                mbar_wait(misc(0 + ub), (uint32_t)((j / up_bufs) & 1));                     // up_full
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_sw128(smem_base + L.t_off);
+                for (int c = 0; c < q.chunks; ++c) {
+                    const uint64_t bdesc = umma_desc_sw128(smem_base + L.up_off + ub * L.up_bytes + (uint32_t)(c * wch) * 128);
+                    for (int k = 0; k < p.Rp / UMMA_K; ++k)
+                        umma_bf16_2sm(tmem_base + as * acc_stride + c * wc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_w, 1u);
+                }
+                umma_commit_2sm(misc(8 + as));                                               // d_full
+                umma_commit_2sm(misc(2 + ub));                                               // up_empty
+            };
+            for (uint32_t st = cid; st < (uint32_t)total_tiles; st += ncl, ++it) {
+                const int as = it % q.acc_stages;
+                mbar_wait_cluster(misc(10 + as), (uint32_t)((it / q.acc_stages) & 1) ^ 1); // acc_empty
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * acc_stride;
+                const int lookahead = p.num_kb < 2 ? p.num_kb : 2;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t stg = smem_base + L.stage_bytes * s;
+                    const uint64_t adesc = umma_desc_sw128(stg + L.x_off);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t acc = (kb | k) != 0;
+                        for (int c = 0; c < q.chunks; ++c)
+                            umma_bf16_2sm(d_tmem + c * wc, adesc + (uint64_t)(k * 2),
+                                          umma_desc_sw128(stg + L.w_off + (uint32_t)(c * wch) * 128) + (uint64_t)(k * 2), idesc_w, acc);
+                        if (lora)
+                            umma_bf16_2sm(d_tmem + p.tile_n, adesc + (uint64_t)(k * 2), umma_desc_sw128(stg + L.dn_off) + (uint64_t)(k * 2), idesc_dn, acc);
+                    }
+                    umma_commit_2sm(empty_bar(s));
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                    if (pending >= 0 && kb == lookahead - 1) { issue_up(pending); pending = -1; }
+                }
+                if (lora) {
+                    umma_commit_2sm(misc(4 + as));                                           // t_full
+                    if (q.acc_stages == 2) pending = it; else issue_up(it);
+                } else {
+                    umma_commit_2sm(misc(8 + as));                                           // d_full
+                }
+            }
+            if (pending >= 0) issue_up(pending);
+        }
+    } else {
+        // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1; both CTAs) =================
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const float keep_scale = p.dropout_p > 0.0f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+        uint8_t* t_row = smem_gen + L.t_off + row * 128;
+        const uint32_t t_ready_leader = mapa_u32(misc(6), 0);
+        int it = 0;
+        for (uint32_t st = cid; st < (uint32_t)total_tiles; st += ncl, ++it) {
+            const int as = it % q.acc_stages;
+            const uint32_t par = (uint32_t)((it / q.acc_stages) & 1);
+            const int mt = st / p.n_tiles, n_tile = st % p.n_tiles;
+            const int m0 = mt * 2 * BM + (int)crank * BM, n0 = n_tile * p.tile_n;
+            const int m = m0 + row;
+            const uint32_t t_lane = tmem_base + as * acc_stride + ((uint32_t)(quad * 32) << 16);
+            if (lora) {
+                mbar_wait(misc(4 + as), par);                               // t_full
+                tc_fence_after();
+                for (int c = 0; c < p.Rp; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(t_lane + (uint32_t)(p.tile_n + c), v);
+                    tmem_ld_wait();
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.scale;
+                    if (p.dropout_p > 0.0f) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const uint64_t e = (uint64_t)m * (uint64_t)p.Rp + (uint64_t)(c + j);
+                            Philox4 r = otb_rng(p.seed, p.offset, OTB_STREAM_DROPOUT, e >> 2);
+                            f[j + 0] = otb_u01(r.x) >= p.dropout_p ? f[j + 0] * keep_scale : 0.0f;
+                            f[j + 1] = otb_u01(r.y) >= p.dropout_p ? f[j + 1] * keep_scale : 0.0f;
+                            f[j + 2] = otb_u01(r.z) >= p.dropout_p ? f[j + 2] * keep_scale : 0.0f;
+                            f[j + 3] = otb_u01(r.w) >= p.dropout_p ? f[j + 3] * keep_scale : 0.0f;
+                        }
+                    }
+                    uint4 lo = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                    uint4 hi = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+                    const int j0 = c >> 3;
+                    *reinterpret_cast<uint4*>(t_row + (((j0 + 0) ^ (row & 7)) << 4)) = lo;
+                    *reinterpret_cast<uint4*>(t_row + (((j0 + 1) ^ (row & 7)) << 4)) = hi;
+                    if (p.t_out != nullptr && n_tile == 0 && m < p.M) {
+                        uint16_t* dst = p.t_out + (size_t)m * p.R + c;
+                        if (c + 8 <= p.R) *reinterpret_cast<uint4*>(dst) = lo;
+                        if (c + 16 <= p.R) *reinterpret_cast<uint4*>(dst + 8) = hi;
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive_cluster(t_ready_leader);                        // t_ready (leader's barrier, 256 arrivals)
+            }
+            mbar_wait(misc(8 + as), par);                                   // d_full
+            tc_fence_after();
+            for (int c = 0; c < p.tile_n; c += 16) {
+                const int n = n0 + c;
+                if (n >= p.N) break;
+                uint32_t v[16];
+                tmem_ld16(t_lane + (uint32_t)c, v);
+                tmem_ld_wait();
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n + j < p.N) f[j] += load_as_float(p.bias, n + j, p.bias_dtype);
+                }
+                if (m < p.M) {
+                    uint16_t* dst = p.y + (size_t)m * p.N + n;
+                    if (n + 8 <= p.N)
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                    if (n + 16 <= p.N)
+                        *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(mapa_u32(misc(10 + as), 0));                // acc_empty (leader's barrier, 256 arrivals)
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                         // neither CTA exits (or frees TMEM) while the pair still works
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc_2sm(tmem_base, 512u);
+    }
+}
+
 // ------------------------------- host side ------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -766,6 +1079,136 @@ int launch_v2(const otb_lora_linear_args* a, void* stream) {
     return OTB_OK;
 }
 
+// ---- v3 planning -----------------------------------------------------------------------------------
+// One cost model for both variants, in SM cycles.  A k-block (64 of K) costs the slower of the tensor pipe
+// (N'/2 cycles per 16-wide k-step for a 128-row CTA tile, the same per CTA of a 256-row pair tile) and the
+// operand ingest of ONE SM at ~42.5 B/clk (see the v3 header).  The epilogue drains ~14 cycles per output
+// column and overlaps the next mainloop when there are two accumulator stages.
+constexpr double INGEST_B_PER_CLK = 42.5;
+
+struct KaPlan {
+    int version;     // 2 or 3
+    int tile_n, chunks, acc_stages;
+    double cycles;
+};
+
+double plan_cost(int rounds, int num_kb, double ingest_bytes, double mma_cycles_per_kb, int tile_n, bool overlapped) {
+    double kb = ingest_bytes / INGEST_B_PER_CLK;
+    if (kb < mma_cycles_per_kb) kb = mma_cycles_per_kb;
+    const double mainloop = num_kb * kb, epi = 14.0 * tile_n + 400.0;
+    if (overlapped) return rounds * ((mainloop > epi ? mainloop : epi) + 300.0) + epi + 1500.0;
+    return rounds * (mainloop + epi + 600.0) + 1500.0;
+}
+
+KaPlan plan_v2(int M, int N, int K, int Rp, int ctas) {
+    const int m_tiles = (M + BM - 1) / BM, num_kb = (K + BK - 1) / BK;
+    KaPlan best{2, 64, 1, 2, 1e30};
+    for (int tn = 32; tn + Rp <= 256; tn += 16) {
+        const int n_tiles = (N + tn - 1) / tn;
+        const int rounds = (int)(((int64_t)m_tiles * n_tiles + ctas - 1) / ctas);
+        const int np = tn + Rp;
+        const double c = plan_cost(rounds, num_kb, (BM + np) * 128.0, 4.0 * (np / 2.0 > 32 + np / 4.0 ? np / 2.0 : 32 + np / 4.0), tn, true);
+        if (c < best.cycles - 1e-9) { best.cycles = c; best.tile_n = tn; }
+    }
+    return best;
+}
+
+KaPlan plan_v3(int M, int N, int K, int Rp, int pairs) {
+    const int m_tiles = (M + 2 * BM - 1) / (2 * BM), num_kb = (K + BK - 1) / BK;
+    KaPlan best{3, 64, 1, 2, 1e30};
+    for (int tn = 32; tn + Rp <= 512; tn += 16) {
+        const int chunks = tn > 256 ? 2 : 1;
+        if (tn % (16 * chunks) != 0) continue;
+        const int acc_stages = tn + Rp <= 256 ? 2 : 1;
+        const int stages_fit = (SMEM_LIMIT - 1024 - 512 - (Rp ? BM * 128 : 0) - (Rp ? acc_stages * (tn / 2) * 128 : 0)) /
+                               ((BM + tn / 2 + Rp / 2) * 128);
+        if (stages_fit < 3) continue;
+        const int n_tiles = (N + tn - 1) / tn;
+        const int rounds = (int)(((int64_t)m_tiles * n_tiles + pairs - 1) / pairs);
+        // per CTA per 16-wide k-step: tn/2 cycles for the w chunks + a floor of 16 for the rank-R MMA
+        const double mma = 4.0 * (tn / 2.0 + (Rp ? (Rp / 2.0 > 16 ? Rp / 2.0 : 16.0) : 0.0));
+        const double c = plan_cost(rounds, num_kb, (BM + tn / 2 + Rp / 2) * 128.0, mma, tn, acc_stages == 2);
+        if (c < best.cycles - 1e-9) { best = KaPlan{3, tn, chunks, acc_stages, c}; }
+    }
+    return best;
+}
+
+int launch_v3(const otb_lora_linear_args* a, void* stream, const KaPlan& plan, int max_pairs) {
+    GemmParams3 q;
+    GemmParams& p = q.g;
+    p.M = a->M; p.N = a->N; p.K = a->K; p.R = a->R;
+    p.Rp = (a->R + 15) / 16 * 16;
+    p.tile_n = plan.tile_n;
+    q.chunks = plan.chunks; q.acc_stages = plan.acc_stages;
+    OTB_CHECK_ARG(p.tile_n % (16 * q.chunks) == 0 && p.tile_n / q.chunks <= 256 && p.tile_n + p.Rp <= (q.acc_stages == 2 ? 256 : 512),
+                  "pair tile_n %d invalid (chunks %d, rank %d)", p.tile_n, q.chunks, p.Rp);
+    p.num_kb = (a->K + BK - 1) / BK;
+    p.n_tiles = (a->N + p.tile_n - 1) / p.tile_n;
+    q.pair_m_tiles = (a->M + 2 * BM - 1) / (2 * BM);
+    p.tmem_cols = 512;
+    int stages = a->stages > 0 ? a->stages : MAX_STAGES;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    while (stages > 1 && (int)make_layout3(p.tile_n, p.Rp, stages, q.acc_stages).total + 1024 > SMEM_LIMIT) --stages;
+    p.stages = stages;
+    const SmemLayout3 L = make_layout3(p.tile_n, p.Rp, stages, q.acc_stages);
+    OTB_CHECK_ARG((int)L.total + 1024 <= SMEM_LIMIT, "pair tile does not fit shared memory");
+    p.scale = a->scale; p.dropout_p = a->dropout_p; p.seed = a->seed; p.offset = a->offset;
+    p.bias = a->bias; p.bias_dtype = a->bias_dtype;
+    p.y = (uint16_t*)a->y; p.t_out = (uint16_t*)a->t_out;
+
+    const int wch = p.tile_n / q.chunks / 2;
+    CUtensorMap tm_x, tm_w, tm_dn, tm_up;
+    int rc;
+    if ((rc = make_tmap(&tm_x, a->x, a->M, a->K, BM, "x")) != OTB_OK) return rc;
+    if ((rc = make_tmap(&tm_w, a->w, a->N, a->K, wch, "w")) != OTB_OK) return rc;
+    if (p.Rp > 0) {
+        if ((rc = make_tmap(&tm_dn, a->down, a->R, a->K, p.Rp / 2, "down")) != OTB_OK) return rc;
+        if ((rc = make_tmap(&tm_up, a->up, a->N, a->R, wch, "up")) != OTB_OK) return rc;
+    } else {
+        tm_dn = tm_x; tm_up = tm_x;
+    }
+    const int total_tiles = q.pair_m_tiles * p.n_tiles;
+    int clusters = max_pairs < total_tiles ? max_pairs : total_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * 2));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = L.total + 1024;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lora_linear_kernel_v3, tm_x, tm_w, tm_dn, tm_up, q);
+    if (e != cudaSuccess) {
+        otb_set_error("launch of lora_linear_kernel_v3 (pair tile 256x%d, %d chunks, %d stages) failed: %s", p.tile_n, q.chunks, stages,
+                      cudaGetErrorString(e));
+        return OTB_ECUDA;
+    }
+    return OTB_OK;
+}
+
+// how many CTA pairs can be co-resident (GPC granularity may strand a few SMs); cached per device
+int v3_max_pairs(int sms) {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return sms / 2;
+    if (cached_dev == dev) return cached;
+    (void)cudaFuncSetAttribute(lora_linear_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    cudaLaunchConfig_t probe = {};
+    probe.gridDim = dim3((unsigned)(sms / 2 * 2));
+    probe.blockDim = dim3(NUM_THREADS);
+    probe.dynamicSmemBytes = SMEM_LIMIT;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    probe.attrs = attr; probe.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, lora_linear_kernel_v3, &probe) != cudaSuccess || n <= 0) n = sms / 2;
+    (void)cudaGetLastError();
+    cached_dev = dev; cached = n;
+    return n;
+}
+
 extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
     OTB_CHECK_ARG(a != nullptr, "null args");
     OTB_CHECK_ARG(a->x && a->w && a->y, "null x / w / y");
@@ -778,7 +1221,24 @@ extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
     OTB_CHECK_ARG((((uintptr_t)a->x | (uintptr_t)a->w | (uintptr_t)a->y | (uintptr_t)a->down | (uintptr_t)a->up |
                     (uintptr_t)a->t_out) & 15) == 0, "all tensor pointers must be 16-byte aligned");
     OTB_BIND(a->x);
-    if (env_int("OTB_KA_V1", 0) == 0) return launch_v2(a, stream);
+    if (env_int("OTB_KA_V1", 0) == 0) {
+        // variant choice: the cost model picks between single-CTA tiles (v2) and CTA-pair tiles (v3);
+        // OTB_KA_VER=2|3 forces one (A/B runs), an explicit tile_n > 256 needs v3
+        const int sms = otb_sm_count();
+        const int Rp = (a->R + 15) / 16 * 16;
+        const int force = env_int("OTB_KA_VER", 2);   // TODO(v3 bring-up): default to the cost model once v3 is validated on the GPU
+        const int pairs = v3_max_pairs(sms);
+        KaPlan p3 = plan_v3(a->M, a->N, a->K, Rp, pairs);
+        if (a->tile_n > 0) {
+            p3.tile_n = a->tile_n; p3.chunks = a->tile_n > 256 ? 2 : 1; p3.acc_stages = a->tile_n + Rp <= 256 ? 2 : 1;
+        }
+        bool use3;
+        if (force == 3 || a->tile_n > 256) use3 = true;
+        else if (force == 2 || a->M <= BM) use3 = false;
+        else use3 = p3.cycles < plan_v2(a->M, a->N, a->K, Rp, sms).cycles;
+        if (use3) return launch_v3(a, stream, p3, pairs);
+        return launch_v2(a, stream);
+    }
     int sms = otb_sm_count();
     GemmParams p;
     p.M = a->M; p.N = a->N; p.K = a->K; p.R = a->R;

@@ -79,9 +79,7 @@ __device__ __forceinline__ void store4(void* p, int64_t i, int dtype, const floa
     if (dtype == OTB_F32) {
         st_stream_u4((float*)p + i, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
     } else if (dtype == OTB_BF16) {
-        uint32_t lo = (uint32_t)float_to_bf16_bits_rn(f[0]) | ((uint32_t)float_to_bf16_bits_rn(f[1]) << 16);
-        uint32_t hi = (uint32_t)float_to_bf16_bits_rn(f[2]) | ((uint32_t)float_to_bf16_bits_rn(f[3]) << 16);
-        st_stream_u2((uint16_t*)p + i, make_uint2(lo, hi));
+        st_stream_u2((uint16_t*)p + i, make_uint2(pack2_bf16_rn(f[0], f[1]), pack2_bf16_rn(f[2], f[3])));
     } else {
         __half2 a = __floats2half2_rn(f[0], f[1]), b = __floats2half2_rn(f[2], f[3]);
         st_stream_u2((__half*)p + i, make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b)));
@@ -108,8 +106,14 @@ __device__ __forceinline__ float normal1(const otb_noise_args& a, uint32_t strea
 
 // grid = (blocks_per_sample, B); each thread owns groups of 4 consecutive elements.
 // LD: compile-time latent dtype (-1 = read a.latent_dtype)
-template <int U, int LD>
+// FT: fast-path target kind (OTB_TARGET_*), or -1 for the generic kernel that reads every option at run time.
+//     FT >= 0 is the training configuration — draw the noise, no offset / perturbation noise, add-noise on,
+//     latent given, no latent shift — with every option a compile-time constant, so the loop body is the
+//     Philox rounds, four MUFU ops per pair of draws and the affine maps (profiles/: 57 -> ~27 thread
+//     instructions per element; the generic kernel was issue-bound at 58 % of the HBM roofline).
+template <int U, int LD, int FT>
 __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_args a) {
+    constexpr bool FAST = FT >= 0;
     if (a.rng_dev != nullptr) { a.seed = a.rng_dev[0]; a.offset = a.rng_dev[1]; }
     const int b = blockIdx.y;
     const int64_t chw = (int64_t)a.C * a.hw;
@@ -125,14 +129,16 @@ __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_ar
     }
     __syncthreads();
     const int32_t t = s_t;
-    const bool add = a.do_add_noise != 0;
+    const bool add = FAST ? true : a.do_add_noise != 0;
     const float cx = add ? a.coef_x0[t] : 0.0f;
     const float cn = add ? a.coef_noise[t] : 0.0f;
     const int ldt = LD >= 0 ? LD : a.latent_dtype;
-    const bool need_noise = a.generate_noise || a.noise_in;
+    const bool need_noise = FAST ? true : (a.generate_noise || a.noise_in);
+    const bool generate = FAST ? true : a.generate_noise != 0;
+    const int target = FAST ? FT : a.target;
     const int64_t base = (int64_t)b * chw;
 
-    if ((chw & 3) == 0) {
+    if (FAST || (chw & 3) == 0) {
         const int64_t ngroups = chw >> 2;
         for (int64_t g0 = (int64_t)blockIdx.x * (NL_THREADS * U) + threadIdx.x; g0 < ngroups; g0 += (int64_t)gridDim.x * (NL_THREADS * U)) {
             float x[U][4], n[U][4];
@@ -145,20 +151,20 @@ __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_ar
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { x[u][k] = 0.0f; n[u][k] = 0.0f; }
                 if (live[u]) {
-                    if (a.latent) load4(a.latent, base + i, ldt, x[u]);
-                    if (!a.generate_noise && a.noise_in) load4(a.noise_in, base + i, ldt, n[u]);
+                    if (FAST || a.latent) load4(a.latent, base + i, ldt, x[u]);
+                    if (!FAST && !a.generate_noise && a.noise_in) load4(a.noise_in, base + i, ldt, n[u]);
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (!live[u]) continue;
                 const int64_t i = (g0 + (int64_t)u * NL_THREADS) << 2;
-                if (a.generate_noise) {
+                if (generate) {
                     const uint64_t ge = (uint64_t)(gs * chw + i);
                     normal4(a, OTB_STREAM_NOISE, ge >> 2, n[u]);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) n[u][k] = rnd_dt(n[u][k], ldt);
-                    if (a.offset_noise_weight > 0.0f) {
+                    if (!FAST && a.offset_noise_weight > 0.0f) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             int c = (int)((uint32_t)(i + k) / (uint32_t)a.hw);
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_ar
                             n[u][k] = rnd_dt(__fadd_rn(n[u][k], rnd_dt(__fmul_rn(a.offset_noise_weight, on), ldt)), ldt);
                         }
                     }
-                    if (a.perturbation_noise_weight > 0.0f) {
+                    if (!FAST && a.perturbation_noise_weight > 0.0f) {
                         float pn[4];
                         normal4(a, OTB_STREAM_PERTURB, ge >> 2, pn);
 #pragma unroll
@@ -175,10 +181,10 @@ __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_ar
                     }
                 }
                 if (a.noise_out && need_noise) store4(a.noise_out, base + i, ldt, n[u]);
-                if (!a.latent) continue;
+                if (!FAST && !a.latent) continue;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    x[u][k] = rnd_dt(__fmul_rn(rnd_dt(__fsub_rn(x[u][k], a.latent_shift), ldt), a.latent_scale), ldt);
+                for (int k = 0; k < 4; ++k)      // FAST: shift == 0 and x - 0 == x exactly
+                    x[u][k] = rnd_dt(__fmul_rn(FAST ? x[u][k] : rnd_dt(__fsub_rn(x[u][k], a.latent_shift), ldt), a.latent_scale), ldt);
                 if (a.x0_out) store4(a.x0_out, base + i, ldt, x[u]);
                 if (add) {
                     float y[4];
@@ -191,19 +197,19 @@ __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_ar
                         store4(a.noisy_cast_out, base + i, a.cast_dtype, y);
                     }
                 }
-                if (a.target_out && a.target != OTB_TARGET_NONE) {
+                if (a.target_out && target != OTB_TARGET_NONE) {
                     float tg[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (a.target == OTB_TARGET_EPSILON) tg[k] = n[u][k];
-                        else if (a.target == OTB_TARGET_V) tg[k] = __fsub_rn(__fmul_rn(cx, n[u][k]), __fmul_rn(cn, x[u][k]));
+                        if (target == OTB_TARGET_EPSILON) tg[k] = n[u][k];
+                        else if (target == OTB_TARGET_V) tg[k] = __fsub_rn(__fmul_rn(cx, n[u][k]), __fmul_rn(cn, x[u][k]));
                         else tg[k] = __fsub_rn(n[u][k], x[u][k]);
                     }
                     store4(a.target_out, base + i, ldt, tg);
                 }
             }
         }
-    } else {
+    } else if constexpr (!FAST) {
         // ragged tail path (chw not a multiple of 4): one element per thread, same RNG indexing
         for (int64_t i = (int64_t)blockIdx.x * NL_THREADS + threadIdx.x; i < chw; i += (int64_t)gridDim.x * NL_THREADS) {
             float n = 0.0f;
@@ -298,17 +304,22 @@ __device__ float timestep_weight(const otb_loss_args& a, int b) {
 }
 
 // grid = (blocks_per_sample, B).  PD / TD: compile-time predicted / target dtype (-1 = read a.*_dtype)
-template <int U, int PD, int TD>
+// FEAT: -1 = every option read at run time; otherwise a compile-time feature set — bit 0 masked, bit 1 prior
+// preservation term, bit 2 MAE term — so the training configurations (FEAT 0: plain MSE, FEAT 1: masked MSE,
+// FEAT 3: masked MSE + prior) carry no dead branches or dead registers.
+template <int U, int PD, int TD, int FEAT>
 __global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args a) {
     const int pred_dt = PD >= 0 ? PD : a.pred_dtype;
     const int tgt_dt = TD >= 0 ? TD : a.target_dtype;
+    constexpr bool FIXED = FEAT >= 0;
     __shared__ float sm[NL_THREADS / 32];
     __shared__ bool s_last;
     const int b = blockIdx.y;
     const int64_t chw = (int64_t)a.C * a.hw;
     const int64_t base = (int64_t)b * chw;
-    const bool masked = a.masked != 0 && a.mask != nullptr;
-    const bool prior = masked && a.prior_target != nullptr && a.masked_prior_preservation_weight != 0.0f;
+    const bool masked = FIXED ? (FEAT & 1) != 0 : (a.masked != 0 && a.mask != nullptr);
+    const bool prior = FIXED ? (FEAT & 2) != 0 : (masked && a.prior_target != nullptr && a.masked_prior_preservation_weight != 0.0f);
+    const bool mae = FIXED ? (FEAT & 4) != 0 : a.mae_strength != 0.0f;
     // per-sample constants
     float inv_mm = 1.0f, inv_mp = 1.0f;
     if (a.normalize_masked_area_loss && a.mask != nullptr) {
@@ -365,7 +376,7 @@ __global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args 
                     const float wm = mk * k_main;
                     float term = a.mse_strength * (d * d) * wm;
                     float gr = a.mse_strength * 2.0f * d * wm;
-                    if (a.mae_strength != 0.0f) {
+                    if (mae) {
                         term += a.mae_strength * fabsf(d) * wm;
                         gr += a.mae_strength * (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * wm;
                     }
@@ -374,7 +385,7 @@ __global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args 
                         const float wp = __fsub_rn(1.0f, mk) * k_prior;
                         term += a.mse_strength * (dp * dp) * wp;
                         gr += a.mse_strength * 2.0f * dp * wp;
-                        if (a.mae_strength != 0.0f) {
+                        if (mae) {
                             term += a.mae_strength * fabsf(dp) * wp;
                             gr += a.mae_strength * (dp > 0.0f ? 1.0f : (dp < 0.0f ? -1.0f : 0.0f)) * wp;
                         }
@@ -395,7 +406,7 @@ __global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args 
             const float wm = m * k_main;
             float term = a.mse_strength * (d * d) * wm;
             float gr = a.mse_strength * 2.0f * d * wm;
-            if (a.mae_strength != 0.0f) {
+            if (mae) {
                 term += a.mae_strength * fabsf(d) * wm;
                 gr += a.mae_strength * (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * wm;
             }
@@ -404,7 +415,7 @@ __global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args 
                 const float wp = __fsub_rn(1.0f, m) * k_prior;
                 term += a.mse_strength * (dp * dp) * wp;
                 gr += a.mse_strength * 2.0f * dp * wp;
-                if (a.mae_strength != 0.0f) {
+                if (mae) {
                     term += a.mae_strength * fabsf(dp) * wp;
                     gr += a.mae_strength * (dp > 0.0f ? 1.0f : (dp < 0.0f ? -1.0f : 0.0f)) * wp;
                 }
@@ -455,11 +466,14 @@ int tuning_unroll(const char* env, int dflt) {
 }
 
 int blocks_per_sample_for(int64_t chw, int B, int unroll) {
-    // 4*unroll elements per thread per iteration; aim at >= 4 waves of 148 SMs x 8 resident blocks when
-    // the problem is large, never more blocks than there are slabs of one block-iteration.
+    // One block-iteration (a "slab") is 4*unroll elements per thread.  A block that loops over several slabs
+    // serialises their memory latency (load -> math -> store -> next load), which is what bounded the first
+    // version at ~60 % of the HBM roofline (profiles/r01_ncu_kb2.md: 21 long-scoreboard stalls per issue), so
+    // every slab gets its own block and the block scheduler provides the pipelining; only beyond ~64 waves of
+    // resident blocks do blocks start to loop.
     int64_t slabs = (chw / 4 + NL_THREADS * unroll - 1) / (NL_THREADS * unroll);
     if (slabs < 1) slabs = 1;
-    int64_t want = (int64_t)otb_sm_count() * 8 * 4 / (B > 0 ? B : 1);
+    int64_t want = (int64_t)otb_sm_count() * 8 * 64 / (B > 0 ? B : 1);
     if (want < 1) want = 1;
     int64_t bps = slabs < want ? slabs : want;
     if (bps > 65535) bps = 65535;
@@ -487,15 +501,30 @@ extern "C" int otb_noise_addnoise(const otb_noise_args* a, void* stream) {
                       "bad timestep range [%d,%d)", a->min_timestep, a->max_timestep);
     const int64_t chw = (int64_t)a->C * a->hw;
     OTB_BIND(a->timestep ? (const void*)a->timestep : (a->latent ? a->latent : a->noise_out));
-    dim3 grid(blocks_per_sample_for(chw, a->B, tuning_unroll("OTB_NB1_UNROLL", NB1_UNROLL)), a->B);
+    const int u = tuning_unroll("OTB_NB1_UNROLL", NB1_UNROLL);
+    dim3 grid(blocks_per_sample_for(chw, a->B, u), a->B);
+    cudaStream_t st = (cudaStream_t)stream;
+    // the training configuration takes the specialised kernel (see the template comment)
+    const bool fast = a->latent_dtype == OTB_F32 && a->generate_noise && a->latent && a->do_add_noise && !a->noise_in &&
+                      a->offset_noise_weight <= 0.0f && a->perturbation_noise_weight <= 0.0f && a->latent_shift == 0.0f &&
+                      (chw & 3) == 0 && a->target != OTB_TARGET_NONE && getenv("OTB_NB1_GENERIC") == nullptr;
+#define OTB_NB1_LAUNCH(UU, FT) noise_addnoise_kernel<UU, OTB_F32, FT><<<grid, NL_THREADS, 0, st>>>(*a)
+#define OTB_NB1_BY_TARGET(UU)                                                   \
+    do {                                                                        \
+        if (!fast) OTB_NB1_LAUNCH(UU, -1);                                      \
+        else if (a->target == OTB_TARGET_EPSILON) OTB_NB1_LAUNCH(UU, OTB_TARGET_EPSILON); \
+        else if (a->target == OTB_TARGET_V) OTB_NB1_LAUNCH(UU, OTB_TARGET_V);   \
+        else OTB_NB1_LAUNCH(UU, OTB_TARGET_FLOW);                               \
+    } while (0)
     if (a->latent_dtype == OTB_F32) {
-        const int u = tuning_unroll("OTB_NB1_UNROLL", NB1_UNROLL);
-        if (u == 1) noise_addnoise_kernel<1, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
-        else if (u == 4) noise_addnoise_kernel<4, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
-        else noise_addnoise_kernel<2, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+        if (u == 1) OTB_NB1_BY_TARGET(1);
+        else if (u == 4) OTB_NB1_BY_TARGET(4);
+        else OTB_NB1_BY_TARGET(2);
+    } else {
+        noise_addnoise_kernel<NB1_UNROLL, -1, -1><<<grid, NL_THREADS, 0, st>>>(*a);
     }
-    else
-        noise_addnoise_kernel<NB1_UNROLL, -1><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+#undef OTB_NB1_BY_TARGET
+#undef OTB_NB1_LAUNCH
     OTB_LAUNCH_CHECK("noise_addnoise_kernel");
     return OTB_OK;
 }
@@ -515,16 +544,31 @@ extern "C" int otb_loss_fwd_bwd(const otb_loss_args* a, void* stream) {
         OTB_LAUNCH_CHECK("mask_stats_kernel");
     }
     dim3 grid(a->blocks_per_sample, a->B);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool masked = a->masked != 0 && a->mask != nullptr;
+    const bool prior = masked && a->prior_target != nullptr && a->masked_prior_preservation_weight != 0.0f;
+    int feat = (masked ? 1 : 0) | (prior ? 2 : 0) | (a->mae_strength != 0.0f ? 4 : 0);
+    if ((feat != 0 && feat != 1 && feat != 3) || getenv("OTB_NB2_GENERIC") != nullptr) feat = -1;
     if (a->pred_dtype == OTB_BF16 && a->target_dtype == OTB_F32) {     // the training configuration
         const int u = tuning_unroll("OTB_NB2_UNROLL", NB2_UNROLL);
-        if (u == 1) loss_fwd_bwd_kernel<1, OTB_BF16, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
-        else if (u == 2) loss_fwd_bwd_kernel<2, OTB_BF16, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
-        else loss_fwd_bwd_kernel<4, OTB_BF16, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+#define OTB_NB2_LAUNCH(UU, FF) loss_fwd_bwd_kernel<UU, OTB_BF16, OTB_F32, FF><<<grid, NL_THREADS, 0, st>>>(*a)
+#define OTB_NB2_BY_FEAT(UU)                          \
+    do {                                             \
+        if (feat == 0) OTB_NB2_LAUNCH(UU, 0);        \
+        else if (feat == 1) OTB_NB2_LAUNCH(UU, 1);   \
+        else if (feat == 3) OTB_NB2_LAUNCH(UU, 3);   \
+        else OTB_NB2_LAUNCH(UU, -1);                 \
+    } while (0)
+        if (u == 1) OTB_NB2_BY_FEAT(1);
+        else if (u == 2) OTB_NB2_BY_FEAT(2);
+        else OTB_NB2_BY_FEAT(4);
+#undef OTB_NB2_BY_FEAT
+#undef OTB_NB2_LAUNCH
     }
     else if (a->pred_dtype == OTB_F32 && a->target_dtype == OTB_F32)
-        loss_fwd_bwd_kernel<NB2_UNROLL, OTB_F32, OTB_F32><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+        loss_fwd_bwd_kernel<NB2_UNROLL, OTB_F32, OTB_F32, -1><<<grid, NL_THREADS, 0, st>>>(*a);
     else
-        loss_fwd_bwd_kernel<NB2_UNROLL, -1, -1><<<grid, NL_THREADS, 0, (cudaStream_t)stream>>>(*a);
+        loss_fwd_bwd_kernel<NB2_UNROLL, -1, -1, -1><<<grid, NL_THREADS, 0, st>>>(*a);
     OTB_LAUNCH_CHECK("loss_fwd_bwd_kernel");
     return OTB_OK;
 }
