@@ -121,6 +121,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+// 32 lanes x 32 consecutive fp32 columns into r[o .. o+32)
+template <int o>
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7]), "=r"(r[o + 8]), "=r"(r[o + 9]), "=r"(r[o + 10]), "=r"(r[o + 11]), "=r"(r[o + 12]), "=r"(r[o + 13]), "=r"(r[o + 14]), "=r"(r[o + 15]), "=r"(r[o + 16]), "=r"(r[o + 17]), "=r"(r[o + 18]), "=r"(r[o + 19]), "=r"(r[o + 20]), "=r"(r[o + 21]), "=r"(r[o + 22]), "=r"(r[o + 23]), "=r"(r[o + 24]), "=r"(r[o + 25]), "=r"(r[o + 26]), "=r"(r[o + 27]), "=r"(r[o + 28]), "=r"(r[o + 29]), "=r"(r[o + 30]), "=r"(r[o + 31])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile whose rows are 128 B apart and whose 8-row groups are
@@ -613,11 +622,32 @@ lora_linear_kernel_v2(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 // Roles per CTA: warp 0 TMA producer (both CTAs, each loads its halves, completion is signalled on the
 // LEADER's mbarrier), warp 1 MMA issuer (leader CTA only; commits are multicast to both CTAs), warps 2-5
 // epilogue (both CTAs; the rank-R hand-off and the accumulator release arrive on the leader's barriers).
+// exactly one lane of a converged warp (the compiler keeps warp-uniform operands in uniform registers inside)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// same descriptor as umma_desc_sw128, from a shared-memory address already in 16-byte units (< 2^14)
+__device__ __forceinline__ uint64_t umma_desc16(uint32_t addr16) {
+    return ((uint64_t)0x40004040u << 32) | (uint64_t)(addr16 | 0x10000u);
+}
+// TMA store of one swizzled smem box; completion is tracked per issuing thread in bulk async-groups
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
+
 struct GemmParams3 {
     GemmParams g;          // g.tile_n: width of the pair tile; g.n_tiles; g.stages
-    int chunks;            // N-chunks per k-step (1 or 2), each tile_n / chunks <= 256 wide
-    int acc_stages;        // 2 when tile_n + Rp <= 256, else 1
+    int chunks;            // MMAs per 16-wide k-step over the fused [w; down] rows (NB = tile_n + Rp, NB / chunks <= 256)
+    int up_chunks;         // MMAs per k-step of the rank-R GEMM (tile_n / up_chunks <= 256)
+    int acc_stages;        // 2 when NB <= 256, else 1
     int pair_m_tiles;      // ceil(M / 256)
+    int debug;             // bring-up only (OTB_KA_DEBUG): bit 0 skip the TMA loads, bit 1 skip the MMAs, bit 2 skip the epilogue
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
@@ -673,26 +703,29 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
                  :: "r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+constexpr uint32_t YSTAGE_WARP_BYTES = 2 * 32 * 128;     // two 32-row x 64-column bf16 staging boxes per epilogue warp
+
 struct SmemLayout3 {
-    uint32_t stage_bytes, x_off, w_off, dn_off, up_off, up_bytes, t_off, bar_off, total;
+    uint32_t stage_bytes, x_off, b_off, up_off, up_bytes, t_off, y_off, bar_off, total;
 };
 __host__ __device__ inline SmemLayout3 make_layout3(int tile_n, int Rp, int stages, int up_bufs) {
     SmemLayout3 L;
     L.x_off = 0;
-    L.w_off = BM * 128;
-    L.dn_off = L.w_off + (uint32_t)(tile_n / 2) * 128;
-    L.stage_bytes = L.dn_off + (uint32_t)(Rp / 2) * 128;
+    L.b_off = BM * 128;                                   // this CTA's half of the fused [w; down] rows
+    L.stage_bytes = L.b_off + (uint32_t)((tile_n + Rp) / 2) * 128;
     L.up_off = L.stage_bytes * stages;
     L.up_bytes = Rp ? (uint32_t)(tile_n / 2) * 128 : 0;
     L.t_off = L.up_off + up_bufs * L.up_bytes;
-    L.bar_off = L.t_off + (Rp ? BM * 128 : 0);
+    L.y_off = L.t_off + (Rp ? BM * 128 : 0);
+    L.bar_off = L.y_off + 4 * YSTAGE_WARP_BYTES;
     L.total = L.bar_off + 512;
     return L;
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                      const __grid_constant__ CUtensorMap tm_dn, const __grid_constant__ CUtensorMap tm_up,
+                      const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_dn,
+                      const __grid_constant__ CUtensorMap tm_up, const __grid_constant__ CUtensorMap tm_y,
                       const GemmParams3 q) {
     const GemmParams& p = q.g;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -706,8 +739,9 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const bool leader = crank == 0;
     const uint32_t cid = cluster_id_x(), ncl = cluster_nctaid_x();
     const int total_tiles = q.pair_m_tiles * p.n_tiles;
-    const int wc = p.tile_n / q.chunks;                // chunk width (columns of the pair tile)
-    const int wch = wc / 2;                            // rows of w / up per CTA per chunk
+    const int NB = p.tile_n + p.Rp;                    // fused B rows: [w tile ; down]
+    const int nbc = NB / q.chunks, nbh = nbc / 2;      // MMA N per chunk; rows of it held by each CTA
+    const int wc = p.tile_n / q.up_chunks, wch = wc / 2;   // same for the rank-R GEMM's `up` operand
     const int acc_stride = q.acc_stages == 2 ? 256 : 512;
 
     const uint32_t bar_base = smem_base + L.bar_off;
@@ -718,8 +752,8 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bar_off + 8u * (2 * MAX_STAGES + 12));
 
     if (threadIdx.x == 0) {
-        prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
-        if (lora) { prefetch_tmap(&tm_dn); prefetch_tmap(&tm_up); }
+        prefetch_tmap(&tm_x); prefetch_tmap(&tm_w); prefetch_tmap(&tm_y);
+        if (lora) { prefetch_tmap(&tm_w2); prefetch_tmap(&tm_dn); prefetch_tmap(&tm_up); }
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(misc(0 + i), 1); mbar_init(misc(2 + i), 1); mbar_init(misc(4 + i), 1);
@@ -737,40 +771,62 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            int it = 0;
-            const uint32_t stage_tx = 2u * L.stage_bytes, up_tx = 2u * L.up_bytes;
-            for (uint32_t st = cid; st < (uint32_t)total_tiles; st += ncl, ++it) {
-                const int mt = st / p.n_tiles, nt = st % p.n_tiles;
-                const int m0 = mt * 2 * BM + (int)crank * BM, n0 = nt * p.tile_n;
-                if (lora) {
-                    const int ub = it % up_bufs;
-                    mbar_wait(misc(2 + ub), (uint32_t)((it / up_bufs) & 1) ^ 1);                 // up_empty (own)
+        // The whole warp runs the loop (warp-uniform control flow and values, so addresses and coordinates stay in
+        // uniform registers); one elected lane issues.  A lone `if (lane == 0)` thread pays an ELECT + R2UR sequence
+        // per UTMALDG / UTCHMMA — measured ~350 cycles per MMA on the issuing thread, 2.7x the tensor pipe's 128.
+        int s = 0; uint32_t ph = 0;
+        int it = 0;
+        const uint32_t stage_tx = 2u * L.stage_bytes, up_tx = 2u * L.up_bytes;
+        for (uint32_t st = cid; st < (uint32_t)total_tiles; st += ncl, ++it) {
+            const int mt = st / p.n_tiles, nt = st % p.n_tiles;
+            const int m0 = mt * 2 * BM + (int)crank * BM, n0 = nt * p.tile_n;
+            if (lora) {
+                const int ub = it % up_bufs;
+                mbar_wait(misc(2 + ub), (uint32_t)((it / up_bufs) & 1) ^ 1);                 // up_empty (own)
+                if (elect_one()) {
                     if (leader) mbar_expect_tx(misc(0 + ub), up_tx);
                     const uint32_t bar = mapa_u32(misc(0 + ub), 0);
-                    for (int c = 0; c < q.chunks; ++c)
+                    for (int c = 0; c < q.up_chunks; ++c)
                         tma_load_2d_2sm(smem_base + L.up_off + ub * L.up_bytes + (uint32_t)(c * wch) * 128, &tm_up, bar, 0,
                                         n0 + c * wc + (int)crank * wch);
                 }
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(empty_bar(s), ph ^ 1);
+                __syncwarp();
+            }
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(empty_bar(s), ph ^ 1);
+                if (elect_one()) {
                     const uint32_t stg = smem_base + L.stage_bytes * s;
-                    if (leader) mbar_expect_tx(full_bar(s), stage_tx);
-                    const uint32_t bar = mapa_u32(full_bar(s), 0);
-                    tma_load_2d_2sm(stg + L.x_off, &tm_x, bar, kb * BK, m0);
-                    for (int c = 0; c < q.chunks; ++c)
-                        tma_load_2d_2sm(stg + L.w_off + (uint32_t)(c * wch) * 128, &tm_w, bar, kb * BK, n0 + c * wc + (int)crank * wch);
-                    if (lora) tma_load_2d_2sm(stg + L.dn_off, &tm_dn, bar, kb * BK, (int)crank * (p.Rp / 2));
-                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                    if (q.debug & 1) {
+                        if (leader) mbar_arrive(full_bar(s));
+                    } else {
+                        if (leader) mbar_expect_tx(full_bar(s), stage_tx);
+                        const uint32_t bar = mapa_u32(full_bar(s), 0);
+                        tma_load_2d_2sm(stg + L.x_off, &tm_x, bar, kb * BK, m0);
+                        // my half of every chunk of the fused [w; down] rows; only the very last half (peer CTA, last
+                        // chunk) reaches into `down`, and it holds all Rp rows of it
+                        for (int c = 0; c < q.chunks; ++c) {
+                            const uint32_t dst = stg + L.b_off + (uint32_t)(c * nbh) * 128;
+                            const int row = c * nbc + (int)crank * nbh;      // first fused row of this half
+                            if (lora && c == q.chunks - 1 && !leader) {
+                                if (nbh > p.Rp) tma_load_2d_2sm(dst, &tm_w2, bar, kb * BK, n0 + row);
+                                tma_load_2d_2sm(dst + (uint32_t)(nbh - p.Rp) * 128, &tm_dn, bar, kb * BK, 0);
+                            } else {
+                                tma_load_2d_2sm(dst, &tm_w, bar, kb * BK, n0 + row);
+                            }
+                        }
+                    }
                 }
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (leader CTA only) =================
-        if (lane == 0 && leader) {
-            const uint32_t idesc_w = umma_idesc_bf16(2 * BM, wc);
-            const uint32_t idesc_dn = umma_idesc_bf16(2 * BM, p.Rp);
+        // ================= MMA issuer (leader CTA only; warp-uniform, one elected lane issues) =================
+        if (leader) {
+            const uint32_t idesc_main = umma_idesc_bf16(2 * BM, nbc);
+            const uint32_t idesc_up = umma_idesc_bf16(2 * BM, wc);
+            const uint32_t sb16 = smem_base >> 4;                     // descriptor address unit: 16 B
+            const uint32_t stage16 = L.stage_bytes >> 4, b16off = L.b_off >> 4, chunk16 = (uint32_t)(nbh * 128) >> 4;
             int s = 0; uint32_t ph = 0;
             int it = 0, pending = -1;
             auto issue_up = [&](int j) {      // D += T(j) . up(j)^T, then hand the accumulator to the epilogue
@@ -778,14 +834,16 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 mbar_wait_cluster(misc(6), (uint32_t)(j & 1));                              // t_ready: both CTAs parked T(j)
                 mbar_wait(misc(0 + ub), (uint32_t)((j / up_bufs) & 1));                     // up_full
                 tc_fence_after();
-                const uint64_t adesc = umma_desc_sw128(smem_base + L.t_off);
-                for (int c = 0; c < q.chunks; ++c) {
-                    const uint64_t bdesc = umma_desc_sw128(smem_base + L.up_off + ub * L.up_bytes + (uint32_t)(c * wch) * 128);
-                    for (int k = 0; k < p.Rp / UMMA_K; ++k)
-                        umma_bf16_2sm(tmem_base + as * acc_stride + c * wc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_w, 1u);
+                if (elect_one()) {
+                    const uint32_t a16 = sb16 + (L.t_off >> 4), b16 = sb16 + ((L.up_off + ub * L.up_bytes) >> 4);
+                    for (int c = 0; c < q.up_chunks; ++c)
+                        for (int k = 0; k < p.Rp / UMMA_K; ++k)
+                            umma_bf16_2sm(tmem_base + as * acc_stride + c * wc, umma_desc16(a16 + k * 2),
+                                          umma_desc16(b16 + c * ((uint32_t)(wch * 128) >> 4) + k * 2), idesc_up, 1u);
+                    umma_commit_2sm(misc(8 + as));                                           // d_full
+                    umma_commit_2sm(misc(2 + ub));                                           // up_empty
                 }
-                umma_commit_2sm(misc(8 + as));                                               // d_full
-                umma_commit_2sm(misc(2 + ub));                                               // up_empty
+                __syncwarp();
             };
             for (uint32_t st = cid; st < (uint32_t)total_tiles; st += ncl, ++it) {
                 const int as = it % q.acc_stages;
@@ -796,26 +854,34 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
-                    const uint32_t stg = smem_base + L.stage_bytes * s;
-                    const uint64_t adesc = umma_desc_sw128(stg + L.x_off);
+                    if (elect_one()) {
+                        const uint32_t a16 = sb16 + stage16 * s, b16 = a16 + b16off;
+                        if (!(q.debug & 2)) {
+                            if (q.chunks == 1) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint32_t acc = (kb | k) != 0;
-                        for (int c = 0; c < q.chunks; ++c)
-                            umma_bf16_2sm(d_tmem + c * wc, adesc + (uint64_t)(k * 2),
-                                          umma_desc_sw128(stg + L.w_off + (uint32_t)(c * wch) * 128) + (uint64_t)(k * 2), idesc_w, acc);
-                        if (lora)
-                            umma_bf16_2sm(d_tmem + p.tile_n, adesc + (uint64_t)(k * 2), umma_desc_sw128(stg + L.dn_off) + (uint64_t)(k * 2), idesc_dn, acc);
+                                for (int k = 0; k < BK / UMMA_K; ++k)
+                                    umma_bf16_2sm(d_tmem, umma_desc16(a16 + k * 2), umma_desc16(b16 + k * 2), idesc_main, (kb | k) != 0);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < BK / UMMA_K; ++k) {
+                                    umma_bf16_2sm(d_tmem, umma_desc16(a16 + k * 2), umma_desc16(b16 + k * 2), idesc_main, (kb | k) != 0);
+                                    umma_bf16_2sm(d_tmem + nbc, umma_desc16(a16 + k * 2), umma_desc16(b16 + chunk16 + k * 2), idesc_main, (kb | k) != 0);
+                                }
+                            }
+                        }
+                        umma_commit_2sm(empty_bar(s));
                     }
-                    umma_commit_2sm(empty_bar(s));
+                    __syncwarp();
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                     if (pending >= 0 && kb == lookahead - 1) { issue_up(pending); pending = -1; }
                 }
                 if (lora) {
-                    umma_commit_2sm(misc(4 + as));                                           // t_full
+                    if (elect_one()) umma_commit_2sm(misc(4 + as));                          // t_full
+                    __syncwarp();
                     if (q.acc_stages == 2) pending = it; else issue_up(it);
                 } else {
-                    umma_commit_2sm(misc(8 + as));                                           // d_full
+                    if (elect_one()) umma_commit_2sm(misc(8 + as));                          // d_full
+                    __syncwarp();
                 }
             }
             if (pending >= 0) issue_up(pending);
@@ -827,6 +893,12 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const float keep_scale = p.dropout_p > 0.0f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
         uint8_t* t_row = smem_gen + L.t_off + row * 128;
         const uint32_t t_ready_leader = mapa_u32(misc(6), 0);
+        // output staging: accumulator -> registers -> bf16 -> 128B-swizzled smem box -> TMA store (coalesced, clipped
+        // at the M / N edges by the tensor map); two boxes per warp so a store drains while the next box is packed
+        const uint32_t ybox = smem_base + L.y_off + (uint32_t)quad * YSTAGE_WARP_BYTES;
+        uint8_t* ybox_gen = smem_gen + L.y_off + (uint32_t)quad * YSTAGE_WARP_BYTES;
+        const bool bias_vec = p.bias != nullptr && (p.bias_dtype == OTB_BF16 || p.bias_dtype == OTB_F32) && (((uintptr_t)p.bias) & 15) == 0;
+        uint32_t ybuf = 0;
         int it = 0;
         for (uint32_t st = cid; st < (uint32_t)total_tiles; st += ncl, ++it) {
             const int as = it % q.acc_stages;
@@ -873,31 +945,88 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             }
             mbar_wait(misc(8 + as), par);                                   // d_full
             tc_fence_after();
-            for (int c = 0; c < p.tile_n; c += 16) {
-                const int n = n0 + c;
-                if (n >= p.N) break;
-                uint32_t v[16];
-                tmem_ld16(t_lane + (uint32_t)c, v);
-                tmem_ld_wait();
-                float f[16];
+            for (int c0 = 0; c0 < p.tile_n; c0 += 64) {
+                const int nb0 = n0 + c0;
+                if (nb0 >= p.N || (q.debug & 4)) break;
+                const int cols = p.tile_n - c0 < 64 ? p.tile_n - c0 : 64;
+                if (cols == 64 && nb0 + 64 <= p.N && (p.bias == nullptr || bias_vec)) {
+                    // ---- full 64-column block: one swizzled box, one TMA store ----
+                    uint32_t v[64];
+                    tmem_ld32<0>(t_lane + (uint32_t)(c0 + 0), v);
+                    tmem_ld32<32>(t_lane + (uint32_t)(c0 + 32), v);
+                    tmem_ld_wait();
+                    if (p.bias != nullptr) {                                // same address in every lane: L1 broadcast
+                        if (p.bias_dtype == OTB_BF16) {
+                            const uint4* bp = reinterpret_cast<const uint4*>((const uint16_t*)p.bias + nb0);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-                if (p.bias != nullptr) {
+                            for (int g = 0; g < 8; ++g) {
+                                const uint4 b = __ldg(bp + g);
+                                const uint32_t w[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n + j < p.N) f[j] += load_as_float(p.bias, n + j, p.bias_dtype);
-                }
-                if (m < p.M) {
-                    uint16_t* dst = p.y + (size_t)m * p.N + n;
-                    if (n + 8 <= p.N)
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-                    if (n + 16 <= p.N)
-                        *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+                                for (int e = 0; e < 4; ++e) {
+                                    v[g * 8 + e * 2 + 0] = __float_as_uint(__uint_as_float(v[g * 8 + e * 2 + 0]) + __uint_as_float(w[e] << 16));
+                                    v[g * 8 + e * 2 + 1] = __float_as_uint(__uint_as_float(v[g * 8 + e * 2 + 1]) + __uint_as_float(w[e] & 0xFFFF0000u));
+                                }
+                            }
+                        } else {
+                            const float4* bp = reinterpret_cast<const float4*>((const float*)p.bias + nb0);
+#pragma unroll
+                            for (int g = 0; g < 16; ++g) {
+                                const float4 b = __ldg(bp + g);
+                                v[g * 4 + 0] = __float_as_uint(__uint_as_float(v[g * 4 + 0]) + b.x);
+                                v[g * 4 + 1] = __float_as_uint(__uint_as_float(v[g * 4 + 1]) + b.y);
+                                v[g * 4 + 2] = __float_as_uint(__uint_as_float(v[g * 4 + 2]) + b.z);
+                                v[g * 4 + 3] = __float_as_uint(__uint_as_float(v[g * 4 + 3]) + b.w);
+                            }
+                        }
+                    }
+                    if (lane == 0) bulk_wait_read<1>();                    // the box written two blocks ago has left smem
+                    __syncwarp();
+                    uint8_t* brow = ybox_gen + ybuf * (32 * 128) + lane * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)                              // 16-byte chunk j of row r lives at chunk j ^ (r & 7)
+                        *reinterpret_cast<uint4*>(brow + ((j ^ (lane & 7)) << 4)) =
+                            make_uint4(pack_bf16x2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1])),
+                                       pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3])),
+                                       pack_bf16x2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5])),
+                                       pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7])));
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tm_y, ybox + ybuf * (32 * 128), nb0, m0 + quad * 32);
+                        bulk_commit();
+                    }
+                    ybuf ^= 1;
+                } else {
+                    // ---- ragged block (N edge, narrow remainder, odd bias): direct predicated stores ----
+                    for (int c = c0; c < c0 + cols; c += 16) {
+                        const int n = n0 + c;
+                        if (n >= p.N) break;
+                        uint32_t v[16];
+                        tmem_ld16(t_lane + (uint32_t)c, v);
+                        tmem_ld_wait();
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                        if (p.bias != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (n + j < p.N) f[j] += load_as_float(p.bias, n + j, p.bias_dtype);
+                        }
+                        if (m < p.M) {
+                            uint16_t* dst = p.y + (size_t)m * p.N + n;
+                            if (n + 8 <= p.N)
+                                *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                            if (n + 16 <= p.N)
+                                *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+                        }
+                    }
                 }
             }
             tc_fence_before();
             mbar_arrive_cluster(mapa_u32(misc(10 + as), 0));                // acc_empty (leader's barrier, 256 arrivals)
         }
+        if (lane == 0) bulk_wait<0>();            // every TMA store of this thread has been written before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -1084,7 +1213,7 @@ int launch_v2(const otb_lora_linear_args* a, void* stream) {
 // (N'/2 cycles per 16-wide k-step for a 128-row CTA tile, the same per CTA of a 256-row pair tile) and the
 // operand ingest of ONE SM at ~42.5 B/clk (see the v3 header).  The epilogue drains ~14 cycles per output
 // column and overlaps the next mainloop when there are two accumulator stages.
-constexpr double INGEST_B_PER_CLK = 42.5;
+constexpr double INGEST_B_PER_CLK = 37.6;   // 42.5 x the ~88 % the TMA ring sustains (fit to tools/ka_sweep.py, gpurun_out/ka_sweep3.log)
 
 struct KaPlan {
     int version;     // 2 or 3
@@ -1092,12 +1221,13 @@ struct KaPlan {
     double cycles;
 };
 
-double plan_cost(int rounds, int num_kb, double ingest_bytes, double mma_cycles_per_kb, int tile_n, bool overlapped) {
+// epi_per_col: epilogue cycles per output column of the tile (v3's staged TMA store ~27, v2's direct stores ~45)
+double plan_cost(int rounds, int num_kb, double ingest_bytes, double mma_cycles_per_kb, int tile_n, bool overlapped, double epi_per_col) {
     double kb = ingest_bytes / INGEST_B_PER_CLK;
     if (kb < mma_cycles_per_kb) kb = mma_cycles_per_kb;
-    const double mainloop = num_kb * kb, epi = 14.0 * tile_n + 400.0;
-    if (overlapped) return rounds * ((mainloop > epi ? mainloop : epi) + 300.0) + epi + 1500.0;
-    return rounds * (mainloop + epi + 600.0) + 1500.0;
+    const double mainloop = num_kb * kb, epi = epi_per_col * tile_n + 500.0;
+    if (overlapped) return rounds * ((mainloop > epi ? mainloop : epi) + 300.0) + epi + 3000.0;
+    return rounds * (mainloop + epi + 1500.0) + 3000.0;
 }
 
 KaPlan plan_v2(int M, int N, int K, int Rp, int ctas) {
@@ -1107,41 +1237,53 @@ KaPlan plan_v2(int M, int N, int K, int Rp, int ctas) {
         const int n_tiles = (N + tn - 1) / tn;
         const int rounds = (int)(((int64_t)m_tiles * n_tiles + ctas - 1) / ctas);
         const int np = tn + Rp;
-        const double c = plan_cost(rounds, num_kb, (BM + np) * 128.0, 4.0 * (np / 2.0 > 32 + np / 4.0 ? np / 2.0 : 32 + np / 4.0), tn, true);
+        const double c = plan_cost(rounds, num_kb, (BM + np) * 128.0, 4.0 * (np / 2.0 > 80.0 ? np / 2.0 : 80.0), tn, true, 45.0);
         if (c < best.cycles - 1e-9) { best.cycles = c; best.tile_n = tn; }
     }
     return best;
+}
+
+// legal pair-tile widths: fused rows NB = tn + Rp split into `chunks` MMAs of NB/chunks (multiple of 16, <= 256),
+// the rank-R GEMM into `up_chunks` MMAs of tn/up_chunks; the last half-chunk must be able to hold all of `down`
+bool v3_shape_ok(int tn, int Rp, int* chunks, int* up_chunks, int* acc_stages) {
+    const int NB = tn + Rp;
+    if (tn < 16 || NB > 512) return false;
+    const int ch = NB > 256 ? 2 : 1, uch = tn > 256 ? 2 : 1;
+    if (NB % (16 * ch) != 0 || tn % (16 * uch) != 0) return false;
+    if (Rp > NB / ch / 2) return false;
+    *chunks = ch; *up_chunks = uch; *acc_stages = NB <= 256 ? 2 : 1;
+    return true;
 }
 
 KaPlan plan_v3(int M, int N, int K, int Rp, int pairs) {
     const int m_tiles = (M + 2 * BM - 1) / (2 * BM), num_kb = (K + BK - 1) / BK;
     KaPlan best{3, 64, 1, 2, 1e30};
     for (int tn = 32; tn + Rp <= 512; tn += 16) {
-        const int chunks = tn > 256 ? 2 : 1;
-        if (tn % (16 * chunks) != 0) continue;
-        const int acc_stages = tn + Rp <= 256 ? 2 : 1;
-        const int stages_fit = (SMEM_LIMIT - 1024 - 512 - (Rp ? BM * 128 : 0) - (Rp ? acc_stages * (tn / 2) * 128 : 0)) /
-                               ((BM + tn / 2 + Rp / 2) * 128);
-        if (stages_fit < 3) continue;
+        int chunks, up_chunks, acc_stages;
+        if (!v3_shape_ok(tn, Rp, &chunks, &up_chunks, &acc_stages)) continue;
+        int stages = MAX_STAGES;
+        while (stages > 0 && (int)make_layout3(tn, Rp, stages, acc_stages).total + 1024 > SMEM_LIMIT) --stages;
+        if (stages < 3) continue;
         const int n_tiles = (N + tn - 1) / tn;
         const int rounds = (int)(((int64_t)m_tiles * n_tiles + pairs - 1) / pairs);
-        // per CTA per 16-wide k-step: tn/2 cycles for the w chunks + a floor of 16 for the rank-R MMA
-        const double mma = 4.0 * (tn / 2.0 + (Rp ? (Rp / 2.0 > 16 ? Rp / 2.0 : 16.0) : 0.0));
-        const double c = plan_cost(rounds, num_kb, (BM + tn / 2 + Rp / 2) * 128.0, mma, tn, acc_stages == 2);
+        const int NB = tn + Rp, nbc = NB / chunks;
+        // per CTA per 16-wide k-step: nbc/2 tensor-pipe cycles per chunk, with a measured floor of ~80 per instruction
+        const double mma = 4.0 * chunks * (nbc / 2.0 > 80.0 ? nbc / 2.0 : 80.0);
+        const double c = plan_cost(rounds, num_kb, (BM + NB / 2) * 128.0, mma, tn, acc_stages == 2, 27.0);
         if (c < best.cycles - 1e-9) { best = KaPlan{3, tn, chunks, acc_stages, c}; }
     }
     return best;
 }
 
-int launch_v3(const otb_lora_linear_args* a, void* stream, const KaPlan& plan, int max_pairs) {
+int launch_v3(const otb_lora_linear_args* a, void* stream, int tile_n, int max_pairs) {
     GemmParams3 q;
     GemmParams& p = q.g;
     p.M = a->M; p.N = a->N; p.K = a->K; p.R = a->R;
     p.Rp = (a->R + 15) / 16 * 16;
-    p.tile_n = plan.tile_n;
-    q.chunks = plan.chunks; q.acc_stages = plan.acc_stages;
-    OTB_CHECK_ARG(p.tile_n % (16 * q.chunks) == 0 && p.tile_n / q.chunks <= 256 && p.tile_n + p.Rp <= (q.acc_stages == 2 ? 256 : 512),
-                  "pair tile_n %d invalid (chunks %d, rank %d)", p.tile_n, q.chunks, p.Rp);
+    p.tile_n = tile_n;
+    OTB_CHECK_ARG(v3_shape_ok(tile_n, p.Rp, &q.chunks, &q.up_chunks, &q.acc_stages),
+                  "pair tile_n %d invalid for rank %d (tile_n + rank a multiple of 16 (32 above 256), <= 512)", tile_n, p.Rp);
+    q.debug = env_int("OTB_KA_DEBUG", 0);
     p.num_kb = (a->K + BK - 1) / BK;
     p.n_tiles = (a->N + p.tile_n - 1) / p.tile_n;
     q.pair_m_tiles = (a->M + 2 * BM - 1) / (2 * BM);
@@ -1156,16 +1298,17 @@ int launch_v3(const otb_lora_linear_args* a, void* stream, const KaPlan& plan, i
     p.bias = a->bias; p.bias_dtype = a->bias_dtype;
     p.y = (uint16_t*)a->y; p.t_out = (uint16_t*)a->t_out;
 
-    const int wch = p.tile_n / q.chunks / 2;
-    CUtensorMap tm_x, tm_w, tm_dn, tm_up;
+    const int nbh = (p.tile_n + p.Rp) / q.chunks / 2, wch = p.tile_n / q.up_chunks / 2;
+    CUtensorMap tm_x, tm_w, tm_w2, tm_dn, tm_up, tm_y;
     int rc;
     if ((rc = make_tmap(&tm_x, a->x, a->M, a->K, BM, "x")) != OTB_OK) return rc;
-    if ((rc = make_tmap(&tm_w, a->w, a->N, a->K, wch, "w")) != OTB_OK) return rc;
+    if ((rc = make_tmap(&tm_w, a->w, a->N, a->K, nbh, "w")) != OTB_OK) return rc;
+    if ((rc = make_tmap(&tm_y, a->y, a->M, a->N, 32, "y")) != OTB_OK) return rc;
+    tm_w2 = tm_w; tm_dn = tm_x; tm_up = tm_x;
     if (p.Rp > 0) {
-        if ((rc = make_tmap(&tm_dn, a->down, a->R, a->K, p.Rp / 2, "down")) != OTB_OK) return rc;
+        if (nbh > p.Rp && (rc = make_tmap(&tm_w2, a->w, a->N, a->K, nbh - p.Rp, "w (last half)")) != OTB_OK) return rc;
+        if ((rc = make_tmap(&tm_dn, a->down, a->R, a->K, p.Rp, "down")) != OTB_OK) return rc;
         if ((rc = make_tmap(&tm_up, a->up, a->N, a->R, wch, "up")) != OTB_OK) return rc;
-    } else {
-        tm_dn = tm_x; tm_up = tm_x;
     }
     const int total_tiles = q.pair_m_tiles * p.n_tiles;
     int clusters = max_pairs < total_tiles ? max_pairs : total_tiles;
@@ -1178,7 +1321,7 @@ int launch_v3(const otb_lora_linear_args* a, void* stream, const KaPlan& plan, i
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, lora_linear_kernel_v3, tm_x, tm_w, tm_dn, tm_up, q);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lora_linear_kernel_v3, tm_x, tm_w, tm_w2, tm_dn, tm_up, tm_y, q);
     if (e != cudaSuccess) {
         otb_set_error("launch of lora_linear_kernel_v3 (pair tile 256x%d, %d chunks, %d stages) failed: %s", p.tile_n, q.chunks, stages,
                       cudaGetErrorString(e));
@@ -1226,17 +1369,16 @@ extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
         // OTB_KA_VER=2|3 forces one (A/B runs), an explicit tile_n > 256 needs v3
         const int sms = otb_sm_count();
         const int Rp = (a->R + 15) / 16 * 16;
-        const int force = env_int("OTB_KA_VER", 2);   // TODO(v3 bring-up): default to the cost model once v3 is validated on the GPU
+        const int force = env_int("OTB_KA_VER", 0);
         const int pairs = v3_max_pairs(sms);
         KaPlan p3 = plan_v3(a->M, a->N, a->K, Rp, pairs);
-        if (a->tile_n > 0) {
-            p3.tile_n = a->tile_n; p3.chunks = a->tile_n > 256 ? 2 : 1; p3.acc_stages = a->tile_n + Rp <= 256 ? 2 : 1;
-        }
+        int ch, uch, as;
+        const bool explicit3 = a->tile_n > 0 && v3_shape_ok(a->tile_n, Rp, &ch, &uch, &as);
         bool use3;
         if (force == 3 || a->tile_n > 256) use3 = true;
-        else if (force == 2 || a->M <= BM) use3 = false;
+        else if (force == 2 || a->M <= BM || (a->tile_n > 0 && !explicit3)) use3 = false;
         else use3 = p3.cycles < plan_v2(a->M, a->N, a->K, Rp, sms).cycles;
-        if (use3) return launch_v3(a, stream, p3, pairs);
+        if (use3) return launch_v3(a, stream, a->tile_n > 0 ? a->tile_n : p3.tile_n, pairs);
         return launch_v2(a, stream);
     }
     int sms = otb_sm_count();

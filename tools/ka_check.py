@@ -11,7 +11,8 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 shapes = [  # M, N, K, R, tile_n, bias
     (256, 64, 64, 16, 0, True), (256, 256, 128, 32, 0, True), (128, 64, 64, 16, 0, False), (300, 328, 136, 8, 0, True),
-    (4096, 1280, 1280, 32, 0, True), (4096, 1280, 1280, 32, 224, True), (4096, 1280, 1280, 32, 320, True),
+    (4096, 1280, 1280, 32, 0, True), (4096, 1280, 1280, 32, 224, True), (4096, 1280, 1280, 32, 320, True), (4096, 1280, 1280, 32, 160, True),
+    (4096, 1280, 1280, 32, 192, False), (4000, 1272, 1280, 32, 224, True), (4096, 1280, 1280, 16, 240, True),
     (4096, 1280, 1280, 32, 64, False), (308, 1280, 2048, 32, 0, False), (16384, 640, 640, 32, 0, True),
     (4096, 10240, 1280, 32, 0, True), (4096, 1280, 5120, 32, 0, True), (1000, 1288, 72, 64, 0, True), (4096, 1280, 1280, 0, 0, True),
     (777, 200, 264, 24, 0, True), (4096, 1280, 1280, 32, 448, True),
