@@ -137,43 +137,19 @@ def leaf_flops(model, recompute: bool = False) -> tuple[float, int, list]:
     return total, launches, shapes
 
 
-def time_leaf_kernels(model, dev, reps: int = 3) -> tuple[float, float, int]:
-    """Replay every K-a launch of one step (forward, dX, dA/dB of each of the 722 leaves, with that leaf's own
-    frozen weight / shadows, so the 4.4 GB of weights stream from HBM as in the real step) back to back with
-    CUDA events on the launching stream.  Returns (seconds per step spent in K-a, algorithmic flops per step,
-    launches per step)."""
+def _graph_time(fn, dev, reps: int = 3) -> float:
+    """Device seconds of one call of `fn` (a launch sequence), captured once and replayed so that CUDA events bracket
+    device time only (eager launches of 10-30 us kernels are host-bound and would under-report the kernel)."""
     import torch
-    from onetrainer_b200 import ops
-    flops, launches, shapes = leaf_flops(model)
-    g = torch.Generator(device=dev).manual_seed(0)
-    acts = {}
-    mods = list(model.unet_lora.lora_modules.values())
-    plan = []
-    for m, (M, N, K, r) in zip(mods, shapes):
-        if (M, K) not in acts:
-            acts[(M, K)] = (torch.randn(M, K, device=dev, generator=g) * 0.05).bfloat16()
-        if (M, N) not in acts:
-            acts[(M, N)] = (torch.randn(M, N, device=dev, generator=g) * 0.05).bfloat16()
-        sh = m._operands()
-        plan.append((acts[(M, K)], acts[(M, N)], sh, m._scale(), torch.zeros(r, K, device=dev), torch.zeros(N, r, device=dev)))
-
-    def one_step():
-        for x, dy, sh, sc, dA, dB in plan:
-            _, ts = ops.lora_linear(x, sh["w"], sh["a"], sh["b"], sh["bias"], sc)
-            _, gs = ops.lora_linear(dy, sh["wt"], sh["bt"], sh["at"], None, sc)
-            ops.lora_grad_ab(x, dy, gs, ts, dA, dB)
-
-    # captured once and replayed, so the CUDA events bracket device time only (eager launches of 10-30 us kernels
-    # are host-bound and would under-report the kernel)
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        one_step()
+        fn()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
-        one_step()
+        fn()
     graph.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -184,7 +160,93 @@ def time_leaf_kernels(model, dev, reps: int = 3) -> tuple[float, float, int]:
     torch.cuda.synchronize()
     sec = e0.elapsed_time(e1) / 1e3 / reps
     del graph
-    return sec, flops, launches
+    return sec
+
+
+def time_leaf_kernels(model, dev) -> dict:
+    """Replay every K-a launch of one step — forward and dX GEMMs (`lora_linear_kernel*`), then the dA/dB kernel
+    (`lora_grad_kernel`) — each leaf with its own frozen weight / shadows, so the 4.4 GB of weights stream from HBM as
+    in the real step.  Returns device seconds and algorithmic work of both families."""
+    import torch
+    from onetrainer_b200 import ops
+    _, _, shapes = leaf_flops(model)
+    g = torch.Generator(device=dev).manual_seed(0)
+    acts = {}
+    mods = list(model.unet_lora.lora_modules.values())
+    plan = []
+    gemm_flops, grad_flops, grad_bytes = 0.0, 0.0, 0.0
+    for m, (M, N, K, r) in zip(mods, shapes):
+        if (M, K) not in acts:
+            acts[(M, K)] = (torch.randn(M, K, device=dev, generator=g) * 0.05).bfloat16()
+        if (M, N) not in acts:
+            acts[(M, N)] = (torch.randn(M, N, device=dev, generator=g) * 0.05).bfloat16()
+        sh = m._operands()
+        plan.append((acts[(M, K)], acts[(M, N)], sh, m._scale(), torch.zeros(r, K, device=dev), torch.zeros(N, r, device=dev),
+                     torch.zeros(M, r, device=dev, dtype=torch.bfloat16)))
+        gemm_flops += 4.0 * M * K * N + 4.0 * M * r * (K + N)      # forward + dX, each 2MKN + 2Mr(K+N)
+        grad_flops += 2.0 * M * r * (K + N)                        # dA + dB
+        grad_bytes += 2.0 * M * (K + N) + 4.0 * M * r + 8.0 * r * (K + N)   # stream x, dY, Gs, Ts once; fp32 RMW of dA, dB
+
+    def gemms():
+        for x, dy, sh, sc, dA, dB, t in plan:
+            ops.lora_linear(x, sh["w"], sh["a"], sh["b"], sh["bias"], sc)
+            ops.lora_linear(dy, sh["wt"], sh["bt"], sh["at"], None, sc)
+
+    def grads():
+        for x, dy, sh, sc, dA, dB, t in plan:
+            ops.lora_grad_ab(x, dy, t, t, dA, dB)
+
+    return {"gemm_sec": _graph_time(gemms, dev), "gemm_flops": gemm_flops, "gemm_launches": 2 * len(plan),
+            "grad_sec": _graph_time(grads, dev), "grad_flops": grad_flops, "grad_bytes": grad_bytes, "grad_launches": len(plan)}
+
+
+def time_hbm_kernels(dev, hbm_peak: float) -> list:
+    """The memory-bound kernels at their roofline size (2^28 elements; SURVEY.md §8d: at the training configuration they
+    move 1-10 MB and are latency-bound), CUDA events around 5 launches after 3 warm-ups.  Algorithmic bytes per element:
+    K-b1 10 (read fp32 latent, write bf16 noisy + fp32 target), K-b2 8 (read bf16 prediction + fp32 target, write bf16
+    gradient), K-c bf16+SR+EMA 18."""
+    import torch
+    from onetrainer_b200 import _native as N, ops
+    out = []
+
+    def timed(fn, iters=5):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3 / iters
+
+    T = 1000
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, T, dtype=torch.float32) ** 2
+    ac = torch.cumprod(1 - betas, 0)
+    sa, s1 = ac.sqrt().to(dev), (1 - ac).sqrt().to(dev)
+    Bb = 4096
+    lat = torch.randn(Bb, 4, 128, 128, device=dev)
+    sec = timed(lambda: ops.noise_addnoise(latent=lat, coef_x0=sa, coef_noise=s1, B=Bb, C_=4, hw=128 * 128, latent_dtype=torch.float32,
+                                           device=dev, cast_dtype=torch.bfloat16, target=N.TARGET_EPSILON, ts_mode=N.TS_UNIFORM, seed=1,
+                                           shape=lat.shape))
+    out.append(("noise_addnoise_kernel (K-b1)", lat.numel() * 10 / sec / 1e9))
+    pred = torch.randn(Bb, 4, 128, 128, device=dev, dtype=torch.bfloat16)
+    ts = torch.randint(0, 1000, (Bb,), device=dev, dtype=torch.int32)
+    sec = timed(lambda: ops.loss_fwd_bwd(pred, lat, timestep=ts, sqrt_ac=sa, sqrt_1mac=s1, loss_weight_fn=N.LW_MIN_SNR, upstream=1 / Bb))
+    out.append(("loss_fwd_bwd_kernel (K-b2)", pred.numel() * 8 / sec / 1e9))
+    del lat, pred
+    n = 1 << 28
+    p = torch.zeros(n, device=dev, dtype=torch.bfloat16); g = torch.full_like(p, 1e-3); m = torch.zeros_like(p); v = torch.ones_like(p); e = torch.zeros_like(p)
+    tab = ops.OptimTable([dict(p=p, g=g, exp_avg=m, exp_avg_sq=v, ema=e)], dev)
+    tab.host["flags"][:] |= N.OPT_FLAG_SR
+    for k, val in ops.adam_scalars(3e-4, 0.9, 0.999, 1e-8, 1e-2, 1.0, True).items():
+        tab.host[k][:] = val
+    tab.upload()
+    sec = timed(lambda: ops.adamw_sr_ema_multi(tab, do_ema=True, ema_one_minus_decay=0.001, seed=1, offset=2))
+    out.append(("adamw_sr_ema_kernel (K-c, bf16 + SR + EMA)", n * 18 / sec / 1e9))
+    return [{"kernel": k, "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak, "elements": 1 << 28}
+            for k, a in out]
 
 
 def own_arm(args) -> None:
@@ -262,9 +324,15 @@ def own_arm(args) -> None:
     sec_e2e, _, loss_e2e = timed(step_e2e, args.steps)
 
     peaks, peak_kind = measured_peaks()
-    ka_sec, ka_flops, ka_launches = time_leaf_kernels(model, dev)
-    achieved = ka_flops / ka_sec / 1e12
+    ka = time_leaf_kernels(model, dev)
+    achieved = ka["gemm_flops"] / ka["gemm_sec"] / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    hbm_peak = float(peaks["hbm_gbs"])
+    hbm_kernels = time_hbm_kernels(dev, hbm_peak) if rank == 0 else []
+    grad_gbs = ka["grad_bytes"] / ka["grad_sec"] / 1e9
+    hbm_kernels.insert(0, {"kernel": "lora_grad_kernel (K-a', dA/dB; all 722 leaves of one step)", "bound": "hbm", "achieved": grad_gbs,
+                           "peak": hbm_peak, "unit": "GB/s", "frac": grad_gbs / hbm_peak, "seconds_per_step_in_kernel": ka["grad_sec"],
+                           "launches_per_step": ka["grad_launches"]})
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_baseline
@@ -284,10 +352,12 @@ def own_arm(args) -> None:
             "e2e": {"value": world * args.steps / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": sec_e2e / args.steps * 1e3},
             "gpu_launches": launches, "cuda_graph": graphed is not None, "loss": float(last_loss), "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "lora_linear_kernel (+ lora_grad_kernel)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "tensor", "kernel": "lora_linear_kernel_v3 / _v2 (K-a: forward + dX launches of all 722 leaves)",
+                         "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": f"{peak_kind} bf16_tflops_sustained",
-                         "algorithmic_flops_per_step": ka_flops, "launches_per_step": ka_launches,
-                         "seconds_per_step_in_kernel": ka_sec, "share_of_step": ka_sec / (sec / args.steps)},
+                         "algorithmic_flops_per_step": ka["gemm_flops"], "launches_per_step": ka["gemm_launches"],
+                         "seconds_per_step_in_kernel": ka["gemm_sec"], "share_of_step": ka["gemm_sec"] / (sec / args.steps)},
+            "hbm_kernels": hbm_kernels, "hbm_peak_source": f"{peak_kind} hbm_gbs",
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[1024] = "";
 
@@ -13,6 +14,15 @@ void otb_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* otb_last_error(void) { return g_err; }
+
+int otb_pdl_enabled() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* v = getenv("OTB_PDL");
+        cached = (v && v[0] == '0') ? 0 : 1;
+    }
+    return cached;
+}
 extern "C" int otb_abi_version(void) { return OTB_ABI_VERSION; }
 
 #include <cuda.h>

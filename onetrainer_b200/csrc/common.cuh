@@ -123,6 +123,18 @@ __device__ __forceinline__ void otb_box_muller_fast(uint32_t a, uint32_t b, floa
 }
 
 // ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still draining; otb_pdl_wait() blocks until that predecessor has completed and
+// its writes are visible, so everything BEFORE it (barrier init, TMEM allocation, tensor-map
+// prefetch) overlaps the predecessor's tail.  otb_pdl_trigger() lets the successor do the
+// same to us.  Both are no-ops for a launch without the attribute.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void otb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void otb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+int otb_pdl_enabled();   // OTB_PDL=0 disables the launch attribute (A/B runs)
+
+// ---------------------------------------------------------------------------------------
 // dtype helpers
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }

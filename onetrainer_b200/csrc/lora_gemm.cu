@@ -393,6 +393,7 @@ lora_linear_kernel_v2(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                       const __grid_constant__ CUtensorMap tm_dn, const __grid_constant__ CUtensorMap tm_up,
                       const GemmParams2 q) {
     const GemmParams& p = q.g;
+    otb_pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -431,6 +432,7 @@ lora_linear_kernel_v2(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
     constexpr uint32_t ACC_STRIDE = 256;        // TMEM columns per accumulator stage
+    otb_pdl_wait();
 
     const uint16_t all_mask = (uint16_t)((1u << csize) - 1u);
     // CTAs that share my x tile: same rm, all rn ;  CTAs that share my [w; down] tile: same rn, all rm
@@ -703,7 +705,9 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
                  :: "r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-constexpr uint32_t YSTAGE_WARP_BYTES = 2 * 32 * 128;     // two 32-row x 64-column bf16 staging boxes per epilogue warp
+constexpr uint32_t YSTAGE_WARP_BYTES = 32 * 128;         // one 32-row x 64-column bf16 staging box per epilogue warp
+constexpr int V3_EPI_WARPS = 8;                          // two warps per TMEM lane quadrant, alternating 64-column blocks
+constexpr int V3_THREADS = 64 + 32 * V3_EPI_WARPS;
 
 struct SmemLayout3 {
     uint32_t stage_bytes, x_off, b_off, up_off, up_bytes, t_off, y_off, bar_off, total;
@@ -717,17 +721,18 @@ __host__ __device__ inline SmemLayout3 make_layout3(int tile_n, int Rp, int stag
     L.up_bytes = Rp ? (uint32_t)(tile_n / 2) * 128 : 0;
     L.t_off = L.up_off + up_bufs * L.up_bytes;
     L.y_off = L.t_off + (Rp ? BM * 128 : 0);
-    L.bar_off = L.y_off + 4 * YSTAGE_WARP_BYTES;
+    L.bar_off = L.y_off + V3_EPI_WARPS * YSTAGE_WARP_BYTES;
     L.total = L.bar_off + 512;
     return L;
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(V3_THREADS, 1)
 lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                       const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_dn,
                       const __grid_constant__ CUtensorMap tm_up, const __grid_constant__ CUtensorMap tm_y,
                       const GemmParams3 q) {
     const GemmParams& p = q.g;
+    otb_pdl_trigger();                           // the next kernel in the stream may begin its own prologue
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -757,9 +762,9 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(misc(0 + i), 1); mbar_init(misc(2 + i), 1); mbar_init(misc(4 + i), 1);
-            mbar_init(misc(8 + i), 1); mbar_init(misc(10 + i), 256);
+            mbar_init(misc(8 + i), 1); mbar_init(misc(10 + i), 2 * 32 * V3_EPI_WARPS);
         }
-        mbar_init(misc(6), 256);
+        mbar_init(misc(6), 2 * 32 * V3_EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_2sm(misc(12), 512u);
@@ -768,6 +773,7 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     cluster_sync_all();                         // the peer's barriers and TMEM exist before anything crosses CTAs
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    otb_pdl_wait();                             // everything above overlapped the previous kernel's tail; its outputs are visible now
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
@@ -887,18 +893,18 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             if (pending >= 0) issue_up(pending);
         }
     } else {
-        // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1; both CTAs) =================
-        const int quad = warp & 3;
+        // ================= epilogue (warps 2..9 -> TMEM lane quadrant warp % 4; both CTAs) =================
+        // two warps share a lane quadrant: `half` 0 takes the even 64-column blocks (and 16-column T chunks), 1 the odd ones
+        const int quad = warp & 3, half = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
         const float keep_scale = p.dropout_p > 0.0f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
         uint8_t* t_row = smem_gen + L.t_off + row * 128;
         const uint32_t t_ready_leader = mapa_u32(misc(6), 0);
         // output staging: accumulator -> registers -> bf16 -> 128B-swizzled smem box -> TMA store (coalesced, clipped
         // at the M / N edges by the tensor map); two boxes per warp so a store drains while the next box is packed
-        const uint32_t ybox = smem_base + L.y_off + (uint32_t)quad * YSTAGE_WARP_BYTES;
-        uint8_t* ybox_gen = smem_gen + L.y_off + (uint32_t)quad * YSTAGE_WARP_BYTES;
+        const uint32_t ybox = smem_base + L.y_off + (uint32_t)(warp - 2) * YSTAGE_WARP_BYTES;
+        uint8_t* ybox_gen = smem_gen + L.y_off + (uint32_t)(warp - 2) * YSTAGE_WARP_BYTES;
         const bool bias_vec = p.bias != nullptr && (p.bias_dtype == OTB_BF16 || p.bias_dtype == OTB_F32) && (((uintptr_t)p.bias) & 15) == 0;
-        uint32_t ybuf = 0;
         int it = 0;
         for (uint32_t st = cid; st < (uint32_t)total_tiles; st += ncl, ++it) {
             const int as = it % q.acc_stages;
@@ -910,7 +916,7 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             if (lora) {
                 mbar_wait(misc(4 + as), par);                               // t_full
                 tc_fence_after();
-                for (int c = 0; c < p.Rp; c += 16) {
+                for (int c = half * 16; c < p.Rp; c += 32) {
                     uint32_t v[16];
                     tmem_ld16(t_lane + (uint32_t)(p.tile_n + c), v);
                     tmem_ld_wait();
@@ -941,11 +947,11 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 }
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive_cluster(t_ready_leader);                        // t_ready (leader's barrier, 256 arrivals)
+                mbar_arrive_cluster(t_ready_leader);                        // t_ready (leader's barrier, every epilogue thread of the pair)
             }
             mbar_wait(misc(8 + as), par);                                   // d_full
             tc_fence_after();
-            for (int c0 = 0; c0 < p.tile_n; c0 += 64) {
+            for (int c0 = half * 64; c0 < p.tile_n; c0 += 128) {
                 const int nb0 = n0 + c0;
                 if (nb0 >= p.N || (q.debug & 4)) break;
                 const int cols = p.tile_n - c0 < 64 ? p.tile_n - c0 : 64;
@@ -980,9 +986,9 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                             }
                         }
                     }
-                    if (lane == 0) bulk_wait_read<1>();                    // the box written two blocks ago has left smem
+                    if (lane == 0) bulk_wait_read<0>();                    // this warp's previous box has left smem
                     __syncwarp();
-                    uint8_t* brow = ybox_gen + ybuf * (32 * 128) + lane * 128;
+                    uint8_t* brow = ybox_gen + lane * 128;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)                              // 16-byte chunk j of row r lives at chunk j ^ (r & 7)
                         *reinterpret_cast<uint4*>(brow + ((j ^ (lane & 7)) << 4)) =
@@ -993,10 +999,9 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&tm_y, ybox + ybuf * (32 * 128), nb0, m0 + quad * 32);
+                        tma_store_2d(&tm_y, ybox, nb0, m0 + quad * 32);
                         bulk_commit();
                     }
-                    ybuf ^= 1;
                 } else {
                     // ---- ragged block (N edge, narrow remainder, odd bias): direct predicated stores ----
                     for (int c = c0; c < c0 + cols; c += 16) {
@@ -1024,7 +1029,7 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 }
             }
             tc_fence_before();
-            mbar_arrive_cluster(mapa_u32(misc(10 + as), 0));                // acc_empty (leader's barrier, 256 arrivals)
+            mbar_arrive_cluster(mapa_u32(misc(10 + as), 0));                // acc_empty (leader's barrier, every epilogue thread of the pair)
         }
         if (lane == 0) bulk_wait<0>();            // every TMA store of this thread has been written before the CTA exits
     }
@@ -1182,10 +1187,12 @@ int launch_v2(const otb_lora_linear_args* a, void* stream) {
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = L.total + 1024;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = otb_pdl_enabled() ? 2 : 1;
     if (csize > 1) {
         // not every SM can host a cluster member (GPC granularity): size the persistent grid to what is co-resident
         static thread_local int max_clusters[5] = {0, 0, 0, 0, 0};
@@ -1221,7 +1228,7 @@ struct KaPlan {
     double cycles;
 };
 
-// epi_per_col: epilogue cycles per output column of the tile (v3's staged TMA store ~27, v2's direct stores ~45)
+// epi_per_col: epilogue cycles per output column of the tile (v3's staged TMA store with 8 warps ~15, v2's direct stores ~45)
 double plan_cost(int rounds, int num_kb, double ingest_bytes, double mma_cycles_per_kb, int tile_n, bool overlapped, double epi_per_col) {
     double kb = ingest_bytes / INGEST_B_PER_CLK;
     if (kb < mma_cycles_per_kb) kb = mma_cycles_per_kb;
@@ -1269,7 +1276,7 @@ KaPlan plan_v3(int M, int N, int K, int Rp, int pairs) {
         const int NB = tn + Rp, nbc = NB / chunks;
         // per CTA per 16-wide k-step: nbc/2 tensor-pipe cycles per chunk, with a measured floor of ~80 per instruction
         const double mma = 4.0 * chunks * (nbc / 2.0 > 80.0 ? nbc / 2.0 : 80.0);
-        const double c = plan_cost(rounds, num_kb, (BM + NB / 2) * 128.0, mma, tn, acc_stages == 2, 27.0);
+        const double c = plan_cost(rounds, num_kb, (BM + NB / 2) * 128.0, mma, tn, acc_stages == 2, 15.0);
         if (c < best.cycles - 1e-9) { best = KaPlan{3, tn, chunks, acc_stages, c}; }
     }
     return best;
@@ -1314,13 +1321,15 @@ int launch_v3(const otb_lora_linear_args* a, void* stream, int tile_n, int max_p
     int clusters = max_pairs < total_tiles ? max_pairs : total_tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * 2));
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(V3_THREADS);
     cfg.dynamicSmemBytes = L.total + 1024;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = otb_pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, lora_linear_kernel_v3, tm_x, tm_w, tm_w2, tm_dn, tm_up, tm_y, q);
     if (e != cudaSuccess) {
         otb_set_error("launch of lora_linear_kernel_v3 (pair tile 256x%d, %d chunks, %d stages) failed: %s", p.tile_n, q.chunks, stages,
@@ -1339,7 +1348,7 @@ int v3_max_pairs(int sms) {
     (void)cudaFuncSetAttribute(lora_linear_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     cudaLaunchConfig_t probe = {};
     probe.gridDim = dim3((unsigned)(sms / 2 * 2));
-    probe.blockDim = dim3(NUM_THREADS);
+    probe.blockDim = dim3(V3_THREADS);
     probe.dynamicSmemBytes = SMEM_LIMIT;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -16,7 +16,7 @@ namespace {
 
 constexpr int GQ = 128;        // output columns (of V) per CTA
 constexpr int GM = 64;         // rows of M per pipeline stage
-constexpr int G_STAGES = 3;
+constexpr int G_STAGES = 5;     // 4 steps (88 KB) of loads in flight per CTA: the kernel is latency-, not bandwidth-bound
 constexpr int G_THREADS = 256; // 8 warps x 16 columns
 constexpr int V_PITCH = GQ * 2 + 16;   // bytes; +16 keeps ldmatrix rows on distinct bank groups
 
@@ -51,9 +51,16 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// one 16-byte fp32 vector reduction (sm_90+): four atomic adds, one lane-level operation
+__device__ __forceinline__ void red_add_v4(float* addr, const float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // grid = (max q_tiles, m_splits, 2)
 __global__ void __launch_bounds__(G_THREADS) lora_grad_kernel(const GradParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    otb_pdl_trigger();
+    otb_pdl_wait();          // Gs / Ts come from the dX / forward launches just before this one
     const GradProblem pr = p.pr[blockIdx.z];
     if ((int)blockIdx.x >= pr.q_tiles || pr.out == nullptr) return;
     const int q0 = blockIdx.x * GQ;
@@ -136,8 +143,15 @@ __global__ void __launch_bounds__(G_THREADS) lora_grad_kernel(const GradParams p
             }
         }
     }
-    // partial sums -> global (fp32 reductions)
+    // partial sums -> global.  The fragments are staged through shared memory (the pipeline buffers are free now) so
+    // that every lane issues ONE 16-byte vector reduction on consecutive addresses — a quarter of the lane-level
+    // atomic operations of a per-element red, and full 128-byte lines per warp instruction.
+    cp_async_wait<0>();
+    __syncthreads();
+    float* stage = reinterpret_cast<float*>(smem);
     const int g = lane >> 2, t4 = lane & 3;
+    // dA: out[R, Q] -> stage[r][q] (pitch GQ + 4);  dB: out[Q, R] -> stage[q][r] (pitch Rp + 4)
+    const int pitch = pr.transposed_out ? p.Rp + 4 : GQ + 4;
 #pragma unroll
     for (int rt = 0; rt < 4; ++rt) {
         if (rt >= r_tiles) continue;
@@ -146,11 +160,30 @@ __global__ void __launch_bounds__(G_THREADS) lora_grad_kernel(const GradParams p
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int r = rt * 16 + g + (k >> 1) * 8;
-                const int q = q0 + warp * 16 + nt * 8 + t4 * 2 + (k & 1);
-                if (r < p.R && q < pr.Q) {
-                    float* dst = pr.transposed_out ? pr.out + (size_t)q * p.R + r : pr.out + (size_t)r * pr.Q + q;
-                    atomicAdd(dst, acc[rt][nt][k]);
-                }
+                const int ql = warp * 16 + nt * 8 + t4 * 2 + (k & 1);
+                stage[pr.transposed_out ? ql * pitch + r : r * pitch + ql] = acc[rt][nt][k];
+            }
+        }
+    }
+    __syncthreads();
+    if (!pr.transposed_out) {
+        // rows of R, 128 columns each: one warp instruction covers one full row (32 lanes x 4 floats)
+        for (int r = warp; r < p.R; r += G_THREADS / 32) {
+            const int q = q0 + lane * 4;
+            if (q < pr.Q) {
+                const float4 v = *reinterpret_cast<const float4*>(stage + r * pitch + lane * 4);
+                red_add_v4(pr.out + (size_t)r * pr.Q + q, v);
+            }
+        }
+    } else {
+        // 128 rows of R floats, contiguous in memory as a whole when the tile is interior
+        const int vec_per_row = p.R >> 2;
+        for (int i = threadIdx.x; i < GQ * vec_per_row; i += G_THREADS) {
+            const int ql = i / vec_per_row, r4 = (i % vec_per_row) * 4;
+            const int q = q0 + ql;
+            if (q < pr.Q) {
+                const float4 v = *reinterpret_cast<const float4*>(stage + ql * pitch + r4);
+                red_add_v4(pr.out + (size_t)q * p.R + r4, v);
             }
         }
     }
@@ -176,9 +209,10 @@ extern "C" int otb_lora_grad_ab(const otb_lora_grad_args* a, void* stream) {
     p.pr[1].Q = a->N; p.pr[1].q_tiles = doB ? (a->N + GQ - 1) / GQ : 0; p.pr[1].transposed_out = 1;
     const int q_tiles_total = p.pr[0].q_tiles + p.pr[1].q_tiles;
     const int q_tiles_max = p.pr[0].q_tiles > p.pr[1].q_tiles ? p.pr[0].q_tiles : p.pr[1].q_tiles;
-    // split M so that the launch fills ~2 waves of the chip, but keep >= GM rows per CTA
+    // split M so that the launch is ONE wave of co-resident CTAs (2 per SM with 110 KB of pipeline buffers each),
+    // but keep >= GM rows per CTA
     const int sms = otb_sm_count();
-    int splits = (2 * sms + q_tiles_total - 1) / q_tiles_total;
+    int splits = (2 * sms) / q_tiles_total;
     const int max_splits = (a->M + GM - 1) / GM;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -192,11 +226,22 @@ extern "C" int otb_lora_grad_ab(const otb_lora_grad_args* a, void* stream) {
     int dev = 0;
     OTB_CUDA(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        OTB_CUDA(cudaFuncSetAttribute(lora_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        OTB_CUDA(cudaFuncSetAttribute(lora_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_dev = dev;
     }
-    dim3 grid((unsigned)q_tiles_max, (unsigned)splits, 2);
-    lora_grad_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(p);
-    OTB_LAUNCH_CHECK("lora_grad_kernel");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)q_tiles_max, (unsigned)splits, 2);
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = otb_pdl_enabled() ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lora_grad_kernel, p);
+    if (e != cudaSuccess) {
+        otb_set_error("launch of lora_grad_kernel failed: %s", cudaGetErrorString(e));
+        return OTB_ECUDA;
+    }
     return OTB_OK;
 }

@@ -1,11 +1,12 @@
-"""Bring-up experiments on K-a v3: which side of the pipeline bounds a k-block (OTB_KA_DEBUG bits)."""
+"""Bring-up experiments on K-a v3: which part of a launch costs what (OTB_KA_DEBUG bits: 1 no TMA, 2 no MMA, 4 no epilogue).
+Graph-timed (8 launches per replay).  usage: python tools/ka_dbg.py M N K"""
 import os
 import sys
 import torch
 sys.path.insert(0, ".")
 from onetrainer_b200 import ops
 dev = torch.device("cuda:0")
-M, N, K = 4096, 10240, 1280
+M, N, K = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (4096, 1280, 1280)
 
 
 def bench(R, tile_n, stages):
@@ -14,21 +15,29 @@ def bench(R, tile_n, stages):
     ws = [(torch.randn(N, K, device=dev) / K ** 0.5).bfloat16() for _ in range(nrep)]
     a = (torch.randn(R, K, device=dev) / K ** 0.5).bfloat16() if R else None
     b = torch.randn(N, R, device=dev).bfloat16() if R else None
+    bias = torch.randn(N, device=dev).bfloat16()
 
     def run():
         for i in range(nrep):
-            ops.lora_linear(xs[i & 1], ws[i], a, b, None, 1 / 32, tile_n=tile_n, stages=stages)
-    run(); torch.cuda.synchronize()
+            ops.lora_linear(xs[i & 1], ws[i], a, b, bias, 1 / 32, tile_n=tile_n, stages=stages)
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        run()
+    torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        run()
+    g.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(3):
-        run()
+    for _ in range(5):
+        g.replay()
     e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / 3 / nrep
+    return e0.elapsed_time(e1) * 1e3 / 5 / nrep
 
 
-for ver, dbg, R, tn, st in [(3, 0, 0, 256, 0), (3, 1, 0, 256, 0), (3, 5, 0, 256, 0), (3, 9, 0, 256, 0), (3, 4, 0, 256, 0), (3, 8, 0, 256, 0), (3, 6, 0, 256, 0),
-                            (3, 7, 0, 256, 0), (2, 0, 0, 224, 0)]:
-    os.environ["OTB_KA_VER"] = str(ver); os.environ["OTB_KA_DEBUG"] = str(dbg)
-    us = bench(R, tn, st)
-    print(f"v{ver} debug={dbg} R={R} tile_n={tn} stages={st}: {us:.1f} us  {2.0 * M * N * K / us / 1e6:.0f} TFLOP/s-equivalent", flush=True)
+for R, tn in [(32, 0), (32, 224), (0, 0)]:
+    for dbg in (0, 1, 2, 4, 3, 5, 6, 7):
+        os.environ["OTB_KA_VER"] = "3"; os.environ["OTB_KA_DEBUG"] = str(dbg)
+        us = bench(R, tn, 0)
+        print(f"M={M} N={N} K={K} R={R} tile_n={tn} debug={dbg} ({'-TMA ' if dbg & 1 else ''}{'-MMA ' if dbg & 2 else ''}{'-EPI' if dbg & 4 else ''}): {us:.1f} us", flush=True)
