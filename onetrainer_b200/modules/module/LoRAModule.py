@@ -96,7 +96,16 @@ class _LoraLinearFn(torch.autograd.Function):
         need_a, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dA, dB, ret_a, ret_b = mod._grad_buffers(need_a, need_b)
         if dA is not None or dB is not None:
-            ops.lora_grad_ab(x2, dy, gs, ts, dA, dB)
+            # autograd only ADOPTS the returned arena slices (or gets None when the kernel accumulates in place), so
+            # nothing on this stream reads dA/dB before the side stream is joined; a foreign p.grad (someone replaced
+            # it) makes autograd add the returned tensor on this stream, so that case stays in order
+            foreign = (ret_a is not None and ret_a.data_ptr() != dA.data_ptr()) or (ret_b is not None and ret_b.data_ptr() != dB.data_ptr()) \
+                or (ret_a is not None and mod.lora_down.weight.grad is not None) or (ret_b is not None and mod.lora_up.weight.grad is not None) \
+                or mod._wrapper_slot is None
+            if ops.side_grads.enabled and not foreign:
+                ops.side_grads.launch(lambda: ops.lora_grad_ab(x2, dy, gs, ts, dA, dB), dy.device, (x2, dy, gs, ts, dA, dB))
+            else:
+                ops.lora_grad_ab(x2, dy, gs, ts, dA, dB)
         if ret_a is not None and ret_a.dtype != mod.lora_down.weight.dtype:
             ret_a = ret_a.to(mod.lora_down.weight.dtype)
         if ret_b is not None and ret_b.dtype != mod.lora_up.weight.dtype:

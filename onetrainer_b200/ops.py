@@ -31,6 +31,69 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# --------------------------------------------------------------------------------------
+# side stream for the weight-gradient kernel
+# --------------------------------------------------------------------------------------
+class SideGrads:
+    """Runs K-a' (dA/dB) on a second stream so that it overlaps whatever backward launches next.
+
+    dA/dB of a leaf feed nothing until the optimizer, but the kernel that computes them (a 10-30 us,
+    latency-bound streaming pass) sat on the critical path between that leaf's dX GEMM and the next
+    backward kernel.  Forked after the dX launch (it needs Gs) and joined (a) every `JOIN_EVERY` leaves, which
+    bounds the extra lifetime of the operands it reads, and (b) by an autograd-engine callback when the backward
+    pass ends — so when `.backward()` returns, every gradient is ordered on the caller's stream exactly as before.
+    Works the same under CUDA-graph capture (a fork/join inside the captured stream).  OTB_SIDE_GRADS=0 disables it.
+    """
+    JOIN_EVERY = 8
+
+    def __init__(self):
+        import os
+        self.enabled = os.environ.get("OTB_SIDE_GRADS", "1") != "0"
+        self._streams = {}
+        self._pending = {}      # device index -> list of tensors kept alive until the join
+        self._callback_armed = False
+
+    def stream(self, device: torch.device) -> torch.cuda.Stream:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        st = self._streams.get(idx)
+        if st is None:
+            st = self._streams[idx] = torch.cuda.Stream(device=device)
+        return st
+
+    def launch(self, fn, device: torch.device, keep_alive: tuple) -> None:
+        """Run `fn()` (which launches on the current stream) on the side stream, ordered after everything
+        already queued on the current stream."""
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        side = self.stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            fn()
+        held = self._pending.setdefault(idx, [])
+        held.append(keep_alive)
+        if not self._callback_armed:
+            self._callback_armed = True
+            torch.autograd.Variable._execution_engine.queue_callback(self.join_all)
+        if len(held) >= self.JOIN_EVERY:
+            self.join(device)
+
+    def join(self, device: torch.device) -> None:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if self._pending.get(idx):
+            torch.cuda.current_stream(device).wait_stream(self._streams[idx])
+            self._pending[idx] = []
+
+    def join_all(self) -> None:
+        self._callback_armed = False
+        for idx, held in self._pending.items():
+            if held:
+                dev = torch.device("cuda", idx)
+                torch.cuda.current_stream(dev).wait_stream(self._streams[idx])
+                self._pending[idx] = []
+
+
+side_grads = SideGrads()
+
+
 def _aligned16(*tensors) -> bool:
     return all(t is None or (t.data_ptr() & 15) == 0 for t in tensors)
 
