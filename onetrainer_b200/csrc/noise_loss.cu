@@ -108,7 +108,7 @@ __device__ __forceinline__ float normal1(const otb_noise_args& a, uint32_t strea
 // LD: compile-time latent dtype (-1 = read a.latent_dtype)
 // FT: fast-path target kind (OTB_TARGET_*), or -1 for the generic kernel that reads every option at run time.
 //     FT >= 0 is the training configuration — draw the noise, no offset / perturbation noise, add-noise on,
-//     latent given, no latent shift — with every option a compile-time constant, so the loop body is the
+//     latent given — with every option a compile-time constant, so the loop body is the
 //     Philox rounds, four MUFU ops per pair of draws and the affine maps (profiles/: 57 -> ~27 thread
 //     instructions per element; the generic kernel was issue-bound at 58 % of the HBM roofline).
 template <int U, int LD, int FT>
@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_ar
                 if (a.noise_out && need_noise) store4(a.noise_out, base + i, ldt, n[u]);
                 if (!FAST && !a.latent) continue;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)      // FAST: shift == 0 and x - 0 == x exactly
-                    x[u][k] = rnd_dt(__fmul_rn(FAST ? x[u][k] : rnd_dt(__fsub_rn(x[u][k], a.latent_shift), ldt), a.latent_scale), ldt);
+                for (int k = 0; k < 4; ++k)
+                    x[u][k] = rnd_dt(__fmul_rn(rnd_dt(__fsub_rn(x[u][k], a.latent_shift), ldt), a.latent_scale), ldt);
                 if (a.x0_out) store4(a.x0_out, base + i, ldt, x[u]);
                 if (add) {
                     float y[4];
@@ -506,7 +506,7 @@ extern "C" int otb_noise_addnoise(const otb_noise_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     // the training configuration takes the specialised kernel (see the template comment)
     const bool fast = a->latent_dtype == OTB_F32 && a->generate_noise && a->latent && a->do_add_noise && !a->noise_in &&
-                      a->offset_noise_weight <= 0.0f && a->perturbation_noise_weight <= 0.0f && a->latent_shift == 0.0f &&
+                      a->offset_noise_weight <= 0.0f && a->perturbation_noise_weight <= 0.0f &&
                       (chw & 3) == 0 && a->target != OTB_TARGET_NONE && getenv("OTB_NB1_GENERIC") == nullptr;
 #define OTB_NB1_LAUNCH(UU, FT) noise_addnoise_kernel<UU, OTB_F32, FT><<<grid, NL_THREADS, 0, st>>>(*a)
 #define OTB_NB1_BY_TARGET(UU)                                                   \

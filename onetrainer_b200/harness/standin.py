@@ -193,6 +193,165 @@ def tiny_unet(dim: int = 64, ctx_dim: int = 64) -> StandInUNet:
     return StandInUNet(4, [(dim, 2, 1, 1)], (dim, 1), ctx_dim=ctx_dim, linear_proj=True)
 
 
+# ---------------------------------------------------------------------------------------------
+# FLUX.1 DiT stand-in (config C5)
+# ---------------------------------------------------------------------------------------------
+class _FluxAttention(nn.Module):
+    """diffusers `Attention` as used by FluxTransformerBlock (joint, `added_kv`) and FluxSingleTransformerBlock."""
+
+    def __init__(self, dim: int, head_dim: int, joint: bool):
+        super().__init__()
+        self.heads = dim // head_dim
+        self.to_q, self.to_k, self.to_v = nn.Linear(dim, dim), nn.Linear(dim, dim), nn.Linear(dim, dim)
+        if joint:
+            self.add_q_proj, self.add_k_proj, self.add_v_proj = nn.Linear(dim, dim), nn.Linear(dim, dim), nn.Linear(dim, dim)
+            self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
+            self.to_add_out = nn.Linear(dim, dim)
+
+    def _heads(self, t):
+        B, L, _ = t.shape
+        return t.view(B, L, self.heads, -1).transpose(1, 2)
+
+    def forward(self, x, ctx=None):
+        B, L, D = x.shape
+        q, k, v = self._heads(self.to_q(x)), self._heads(self.to_k(x)), self._heads(self.to_v(x))
+        if ctx is not None:
+            Lc = ctx.shape[1]
+            q = torch.cat([self._heads(self.add_q_proj(ctx)), q], dim=2)
+            k = torch.cat([self._heads(self.add_k_proj(ctx)), k], dim=2)
+            v = torch.cat([self._heads(self.add_v_proj(ctx)), v], dim=2)
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, -1, D)
+        if ctx is not None:
+            return self.to_out[0](o[:, Lc:]), self.to_add_out(o[:, :Lc])
+        return o
+
+
+class _GELUProj(nn.Module):
+    def __init__(self, dim: int, inner: int):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner)
+
+    def forward(self, x):
+        return F.gelu(self.proj(x), approximate="tanh")
+
+
+class _FluxFeedForward(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.net = nn.ModuleList([_GELUProj(dim, dim * 4), nn.Dropout(0.0), nn.Linear(dim * 4, dim)])
+
+    def forward(self, x):
+        return self.net[2](self.net[0](x))
+
+
+class _AdaNorm(nn.Module):
+    """AdaLayerNormZero-style modulation: `linear` is NOT matched by the attn-mlp filter."""
+
+    def __init__(self, dim: int, n: int):
+        super().__init__()
+        self.linear = nn.Linear(dim, n * dim)
+        self.norm = nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
+        self.n = n
+
+    def forward(self, x, vec):
+        return self.norm(x), self.linear(F.silu(vec))[:, None, :].chunk(self.n, dim=-1)
+
+
+class FluxTransformerBlock(nn.Module):
+    def __init__(self, dim: int, head_dim: int):
+        super().__init__()
+        self.norm1, self.norm1_context = _AdaNorm(dim, 6), _AdaNorm(dim, 6)
+        self.attn = _FluxAttention(dim, head_dim, joint=True)
+        self.norm2 = nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
+        self.ff = _FluxFeedForward(dim)
+        self.norm2_context = nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
+        self.ff_context = _FluxFeedForward(dim)
+
+    def forward(self, x, ctx, vec):
+        xn, (sh1, sc1, g1, sh2, sc2, g2) = self.norm1(x, vec)
+        cn, (csh1, csc1, cg1, csh2, csc2, cg2) = self.norm1_context(ctx, vec)
+        ao, co = self.attn(xn * (1 + sc1) + sh1, cn * (1 + csc1) + csh1)
+        x = x + g1 * ao
+        x = x + g2 * self.ff(self.norm2(x) * (1 + sc2) + sh2)
+        ctx = ctx + cg1 * co
+        ctx = ctx + cg2 * self.ff_context(self.norm2_context(ctx) * (1 + csc2) + csh2)
+        return x, ctx
+
+
+class FluxSingleTransformerBlock(nn.Module):
+    def __init__(self, dim: int, head_dim: int):
+        super().__init__()
+        self.norm = _AdaNorm(dim, 3)
+        self.proj_mlp = nn.Linear(dim, dim * 4)
+        self.attn = _FluxAttention(dim, head_dim, joint=False)
+        self.proj_out = nn.Linear(dim * 5, dim)
+
+    def forward(self, x, vec):
+        xn, (sh, sc, g) = self.norm(x, vec)
+        h = xn * (1 + sc) + sh
+        return x + g * self.proj_out(torch.cat([self.attn(h), F.gelu(self.proj_mlp(h), approximate="tanh")], dim=-1))
+
+
+class StandInFluxTransformer(nn.Module):
+    """FluxTransformer2DModel-shaped stand-in: `transformer(hidden_states, timestep, guidance, pooled_projections,
+    encoder_hidden_states, txt_ids, img_ids, joint_attention_kwargs, return_dict).sample` on PACKED latents
+    [B, (H/2)(W/2), 64].  Same hooked-leaf names, counts and shapes as FLUX.1-dev under the reference's `attn-mlp`
+    preset (`["attn", "ff.net"]`, FluxLoRASetup.py:12-16): per double block attn.{to_q,to_k,to_v,to_out.0,add_q_proj,
+    add_k_proj,add_v_proj,to_add_out} + ff.net.{0.proj,2} (ff_context does not match the filter), per single block
+    attn.{to_q,to_k,to_v}: 19*10 + 38*3 = 304 leaves, 35.5 M LoRA parameters at rank 16.
+    Rotary embeddings are omitted (they do not touch the hooked leaves)."""
+
+    def __init__(self, dim: int = 3072, head_dim: int = 128, n_double: int = 19, n_single: int = 38, in_ch: int = 64,
+                 ctx_dim: int = 4096, pooled_dim: int = 768, guidance_embeds: bool = True):
+        super().__init__()
+        self.config = {"guidance_embeds": guidance_embeds, "in_channels": in_ch}
+        self.x_embedder = nn.Linear(in_ch, dim)
+        self.context_embedder = nn.Linear(ctx_dim, dim)
+        self.time_text_embed = nn.ModuleDict({"time": nn.Linear(256, dim), "guidance": nn.Linear(256, dim), "pooled": nn.Linear(pooled_dim, dim)})
+        self.transformer_blocks = nn.ModuleList([FluxTransformerBlock(dim, head_dim) for _ in range(n_double)])
+        self.single_transformer_blocks = nn.ModuleList([FluxSingleTransformerBlock(dim, head_dim) for _ in range(n_single)])
+        self.norm_out = _AdaNorm(dim, 2)
+        self.proj_out = nn.Linear(dim, in_ch)
+
+    def forward(self, hidden_states, timestep, guidance=None, pooled_projections=None, encoder_hidden_states=None,
+                txt_ids=None, img_ids=None, joint_attention_kwargs=None, return_dict=True):
+        dt = hidden_states.dtype
+        vec = self.time_text_embed["time"](StandInUNet._sinusoid(timestep * 1000.0).to(dt)) + self.time_text_embed["pooled"](pooled_projections.to(dt))
+        if guidance is not None:
+            vec = vec + self.time_text_embed["guidance"](StandInUNet._sinusoid(guidance.float() * 1000.0).to(dt))
+        x = self.x_embedder(hidden_states)
+        ctx = self.context_embedder(encoder_hidden_states)
+        for blk in self.transformer_blocks:
+            x, ctx = blk(x, ctx, vec)
+        Lc = ctx.shape[1]
+        h = torch.cat([ctx, x], dim=1)
+        for blk in self.single_transformer_blocks:
+            h = blk(h, vec)
+        x = h[:, Lc:]
+        xn, (sh, sc) = self.norm_out(x, vec)
+        return _Output(self.proj_out(xn * (1 + sc) + sh))
+
+
+def flux_transformer() -> StandInFluxTransformer:
+    """FLUX.1-dev: 19 double + 38 single blocks, D = 3072, 24 heads x 128, T5 context 4096, 304 hooked leaves."""
+    return StandInFluxTransformer()
+
+
+def tiny_flux(dim: int = 128, ctx_dim: int = 64) -> StandInFluxTransformer:
+    """A 2 + 2 block network of the same shape for tests."""
+    return StandInFluxTransformer(dim=dim, head_dim=32, n_double=2, n_single=2, in_ch=64, ctx_dim=ctx_dim, pooled_dim=32)
+
+
+class StandInFlowScheduler:
+    """What the hot path reads from diffusers' FlowMatchEulerDiscreteScheduler: only the LENGTH of `timesteps` / `sigmas`
+    (ModelSetupFlowMatchingMixin.py:22-25, ModelSetupDiffusionLossMixin.py:297-300)."""
+
+    def __init__(self, num_train_timesteps: int = 1000, device=None):
+        self.config = {"num_train_timesteps": num_train_timesteps}
+        self.timesteps = torch.arange(num_train_timesteps, 0, -1, dtype=torch.float32, device=device)
+        self.sigmas = self.timesteps / num_train_timesteps
+
+
 class StandInScheduler:
     """The three things the hot path reads from a diffusers DDIMScheduler."""
 

@@ -18,6 +18,7 @@ from ..modules.module.EMAModule import EMAModuleWrapper
 from ..modules.module.LoRAModule import LoRAModuleWrapper
 from ..modules.modelSetup.mixin.ModelSetupDiffusionLossMixin import ModelSetupDiffusionLossMixin
 from ..modules.modelSetup.mixin.ModelSetupDiffusionMixin import ModelSetupDiffusionMixin
+from ..modules.modelSetup.mixin.ModelSetupFlowMatchingMixin import ModelSetupFlowMatchingMixin
 from ..modules.modelSetup.mixin.ModelSetupFusedNoiseMixin import ModelSetupFusedNoiseMixin
 from ..modules.modelSetup.mixin.ModelSetupNoiseMixin import ModelSetupNoiseMixin
 from ..modules.util.optimizer.adamw_extensions import patch_adamw
@@ -100,6 +101,120 @@ class DiffusionSetup(ModelSetupFusedNoiseMixin, ModelSetupNoiseMixin, ModelSetup
                                       betas=model.noise_scheduler.betas.to(device=self.train_device)).mean()
 
 
+class StandInFluxModel:
+    """The fields of the reference's FluxModel the step touches (modules/model/FluxModel.py)."""
+
+    def __init__(self, transformer: nn.Module, scheduler, train_dtype: torch.dtype):
+        self.transformer = transformer
+        self.unet = transformer                       # the harness' generic name for "the wrapped network"
+        self.noise_scheduler = scheduler
+        self.vae_scaling_factor, self.vae_shift_factor = 0.3611, 0.1159      # FLUX.1 VAE config
+        self.train_dtype = train_dtype
+        self.sdxl = False
+        self.unet_lora: LoRAModuleWrapper | None = None
+        self.transformer_lora = None
+        self.optimizer = None
+        self.ema: EMAModuleWrapper | None = None
+        self.parameters: list[nn.Parameter] = []
+        self.train_progress = TrainProgress()
+        self.autocast_context = torch.autocast(device_type="cuda", dtype=train_dtype)
+
+    # FluxModel.pack_latents / unpack_latents, modules/model/FluxModel.py:319-344 (pure views + one copy each)
+    @staticmethod
+    def pack_latents(latents, batch_size, num_channels_latents, height, width):
+        latents = latents.view(batch_size, num_channels_latents, height // 2, 2, width // 2, 2)
+        latents = latents.permute(0, 2, 4, 1, 3, 5)
+        return latents.reshape(batch_size, (height // 2) * (width // 2), num_channels_latents * 4)
+
+    @staticmethod
+    def unpack_latents(latents, height, width):
+        batch_size, num_patches, channels = latents.shape
+        height, width = height // 2, width // 2
+        latents = latents.view(batch_size, height, width, channels // 4, 2, 2)
+        latents = latents.permute(0, 3, 1, 4, 2, 5)
+        return latents.reshape(batch_size, channels // 4, height * 2, width * 2)
+
+
+class FlowSetup(ModelSetupFusedNoiseMixin, ModelSetupNoiseMixin, ModelSetupFlowMatchingMixin, ModelSetupDiffusionLossMixin):
+    """FLUX-flavoured setup (rectified flow): restates BaseFluxSetup.predict :202-313 and calculate_loss :377-390
+    with cached text-encoder outputs in the batch."""
+
+    def __init__(self, train_device: torch.device, fused_noise: bool = True, guidance_scale: float = 1.0):
+        super().__init__()
+        self.train_device = train_device
+        self.fused_noise = fused_noise
+        self.guidance_scale = guidance_scale
+
+    def predict(self, model: StandInFluxModel, batch: dict, config, train_progress: TrainProgress, *, deterministic: bool = False) -> dict:
+        with model.autocast_context:
+            batch_seed = 0 if deterministic else train_progress.global_step
+            if step_state.active() is not None:
+                generator = PhiloxKey(batch_seed, config.train_device)
+            else:
+                generator = torch.Generator(device=config.train_device)
+                generator.manual_seed(batch_seed)
+            latent_image = batch["latent_image"]
+            T = model.noise_scheduler.config["num_train_timesteps"]
+            H, W = latent_image.shape[-2], latent_image.shape[-1]
+            if self.fused_noise:
+                st = self._noise_timestep_addnoise(
+                    latent_image, config, generator, num_train_timesteps=T, deterministic=deterministic, prediction_type="flow",
+                    flow=True, latent_scale=model.vae_scaling_factor, latent_shift=model.vae_shift_factor,
+                    train_dtype=model.train_dtype, latent_height=H, latent_width=W)
+                timestep, latent_input, flow = st["timestep"], st["noisy"], st["target"]
+            else:   # the reference's call-by-call sequence
+                scaled_latent_image = (latent_image - model.vae_shift_factor) * model.vae_scaling_factor
+                latent_noise = self._create_noise(scaled_latent_image, config, generator)
+                timestep = self._get_timestep_discrete(T, deterministic, generator, scaled_latent_image.shape[0], config,
+                                                       latent_height=H, latent_width=W)
+                noisy, _sigma = self._add_noise_discrete(scaled_latent_image, latent_noise, timestep, model.noise_scheduler.timesteps)
+                latent_input = noisy.to(dtype=model.train_dtype)
+                flow = latent_noise - scaled_latent_image
+            B, C = latent_input.shape[0], latent_input.shape[1]
+            guidance = None
+            if model.transformer.config["guidance_embeds"]:
+                guidance = torch.full((B,), float(self.guidance_scale), device=latent_input.device, dtype=model.train_dtype)
+            packed = model.pack_latents(latent_input, B, C, H, W)
+            packed_predicted_flow = model.transformer(
+                hidden_states=packed.to(dtype=model.train_dtype), timestep=timestep / 1000, guidance=guidance,
+                pooled_projections=batch["text_encoder_1_pooled_state"].to(dtype=model.train_dtype),
+                encoder_hidden_states=batch["text_encoder_2_hidden_state"].to(dtype=model.train_dtype),
+                txt_ids=None, img_ids=None, joint_attention_kwargs=None, return_dict=True).sample
+            predicted_flow = model.unpack_latents(packed_predicted_flow, H, W)
+            data = {"loss_type": "target", "timestep": timestep, "predicted": predicted_flow, "target": flow}
+        return data
+
+    def calculate_loss(self, model: StandInFluxModel, batch: dict, data: dict, config) -> torch.Tensor:
+        return self._flow_matching_losses(batch=batch, data=data, config=config, train_device=self.train_device,
+                                          sigmas=model.noise_scheduler.sigmas.to(device=self.train_device)).mean()
+
+
+def build_flux_model(kind: str, config, device, *, train_dtype=torch.bfloat16, lora_weight_dtype=torch.float32,
+                     stochastic_rounding: bool = True, fused_clip: bool = True, seed: int = 1234, lr: float = 3e-4,
+                     lora_up_std: float = 0.0) -> tuple[StandInFluxModel, FlowSetup]:
+    """Random-init FLUX stand-in + LoRA wrapper (`attn-mlp` preset) + patched AdamW, as FluxLoRASetup.setup_model :105-161."""
+    torch.manual_seed(seed)
+    with torch.device(device):
+        net = {"flux": standin.flux_transformer, "tiny_flux": standin.tiny_flux}[kind]()
+    net = net.to(dtype=train_dtype)
+    net.requires_grad_(False)
+    net.train()
+    model = StandInFluxModel(net, standin.StandInFlowScheduler(1000, device), train_dtype)
+    model.unet_lora = model.transformer_lora = LoRAModuleWrapper(net, "lora_transformer", config, ["attn", "ff.net"])
+    model.unet_lora.set_dropout(config.dropout_probability)
+    model.unet_lora.to(dtype=lora_weight_dtype)
+    if lora_up_std > 0:
+        g = torch.Generator(device=device).manual_seed(seed + 1)
+        for m in model.unet_lora.lora_modules.values():
+            m.lora_up.weight.data.normal_(0.0, lora_up_std, generator=g)
+    model.unet_lora.hook_to_module()
+    model.unet_lora.requires_grad_(True)
+    model.parameters = model.unet_lora.parameters()
+    model.optimizer = torch.optim.AdamW(model.parameters, lr=lr, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    patch_adamw(model.optimizer, stochastic_rounding, clip_grad_norm=config.clip_grad_norm if fused_clip else None)
+    return model, FlowSetup(torch.device(device))
+
+
 def build_model(kind: str, config, device, *, train_dtype=torch.bfloat16, lora_weight_dtype=torch.float32,
                 prediction_type: str = "epsilon", ema: bool = False, stochastic_rounding: bool = True,
                 fused_clip: bool = True, fused_ema: bool = True, seed: int = 1234, lr: float = 3e-4,
@@ -144,6 +259,15 @@ def standin_betas():
 def synthetic_batch(kind: str, batch_size: int, device, seed: int = 1234, latent_hw: int | None = None, masked: bool = False) -> dict:
     """Seeded synthetic batch with the dataloader's keys."""
     g = torch.Generator(device="cpu").manual_seed(seed + dp.rank())
+    if kind in ("flux", "tiny_flux"):          # FLUX.1: 16-channel latents, T5 states [B,512,4096], CLIP pooled [B,768] (SURVEY.md §8d)
+        hw = latent_hw or (128 if kind == "flux" else 16)
+        ctx, pooled, n_txt = (4096, 768, 512) if kind == "flux" else (64, 32, 8)
+        return {
+            "latent_image": torch.randn(batch_size, 16, hw, hw, generator=g) * 0.8,
+            "loss_weight": torch.ones(batch_size),
+            "text_encoder_2_hidden_state": torch.randn(batch_size, n_txt, ctx, generator=g),
+            "text_encoder_1_pooled_state": torch.randn(batch_size, pooled, generator=g),
+        }
     hw = latent_hw or (128 if kind == "sdxl" else 64)
     ctx = {"sdxl": 2048, "sd15": 768, "tiny": 64}[kind]
     b = {

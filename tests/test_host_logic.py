@@ -240,3 +240,16 @@ def test_loss_mixin_rejects_out_of_scope_terms():
     with pytest.raises(NotImplementedError, match="alphas_cumprod_fun"):
         S()._diffusion_losses(batch, dict(data, timestep=torch.zeros(1, dtype=torch.int32)),
                               TrainConfig(loss_weight_fn=LossWeight.MIN_SNR_GAMMA), torch.device("cpu"), alphas_cumprod_fun=lambda t, d: t)
+
+
+def test_flux_standin_has_the_reference_leaf_set():
+    """`attn-mlp` on the FLUX stand-in selects 304 leaves / 35.5 M rank-16 parameters —
+    ff_context and the AdaLN `linear`s do not match the reference's substring filter (FluxLoRASetup.py:12-16)."""
+    from onetrainer_b200.harness import standin
+    with torch.device("meta"):
+        net = standin.flux_transformer()
+    names = [n for n, m in net.named_modules() if isinstance(m, nn.Linear) and any(f in n for f in ["attn", "ff.net"])]
+    assert len(names) == 304
+    assert not any("ff_context" in n or "norm" in n for n in names)
+    params = sum(16 * (m.in_features + m.out_features) for n, m in net.named_modules() if n in set(names))
+    assert params == 35_487_744
