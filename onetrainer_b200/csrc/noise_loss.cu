@@ -308,7 +308,7 @@ __device__ float timestep_weight(const otb_loss_args& a, int b) {
 // preservation term, bit 2 MAE term — so the training configurations (FEAT 0: plain MSE, FEAT 1: masked MSE,
 // FEAT 3: masked MSE + prior) carry no dead branches or dead registers.
 template <int U, int PD, int TD, int FEAT>
-__global__ void __launch_bounds__(NL_THREADS) loss_fwd_bwd_kernel(otb_loss_args a) {
+__global__ void __launch_bounds__(NL_THREADS, (FEAT >= 0 && U <= 2) ? 6 : 1) loss_fwd_bwd_kernel(otb_loss_args a) {
     const int pred_dt = PD >= 0 ? PD : a.pred_dtype;
     const int tgt_dt = TD >= 0 ? TD : a.target_dtype;
     constexpr bool FIXED = FEAT >= 0;

@@ -240,7 +240,7 @@ __device__ __forceinline__ void adam_chunk(const otb_optim_tensor& t, const OptS
     }
 }
 
-__global__ void __launch_bounds__(OPT_THREADS, 3) adamw_sr_ema_kernel(otb_optim_launch a) {
+__global__ void __launch_bounds__(OPT_THREADS, 4) adamw_sr_ema_kernel(otb_optim_launch a) {
     if (a.dyn != nullptr) {
         a.seed = a.dyn->seed; a.offset = a.dyn->offset;
         a.ema_one_minus_decay = a.dyn->ema_one_minus_decay; a.do_ema = a.dyn->do_ema;
