@@ -522,6 +522,30 @@ def test_lora_linear_tile_and_stage_choices_agree(K, dev):
         assert torch.equal(y, ref), (tn, st)
 
 
+@pytest.mark.parametrize("M,N,K_,R,bias_dtype", [
+    (4096, 1280, 1280, 32, torch.bfloat16), (1000, 1288, 200, 64, torch.float32), (300, 328, 136, 8, torch.bfloat16),
+    (2048, 640, 640, 24, None), (513, 1096, 264, 16, torch.float16)])
+def test_lora_linear_pair_tiles_equal_single_cta_tiles(K, dev, oracle, monkeypatch, M, N, K_, R, bias_dtype):
+    """The two K-a variants — single-CTA tiles (v2) and CTA-pair tiles with tcgen05.mma.cta_group::2, the fused
+    [w; down] operand split across the pair and the TMA-store epilogue (v3) — are the same function BIT FOR BIT
+    (same fp32 accumulation order along K), for one- and two-chunk pair tiles, ragged M / N / K, every bias dtype
+    (bf16 / fp32 take the vector path, fp16 the scalar one) and no bias; and both match the oracle."""
+    x, w, down, up, b = (t.to(dev) for t in _lora_case(dev, M, N, K_, R, seed=M ^ N))
+    bias = None if bias_dtype is None else b.to(bias_dtype)
+    monkeypatch.setenv("OTB_KA_VER", "2")
+    y2, t2 = K.ops.lora_linear(x, w, down, up, bias, 0.5)
+    monkeypatch.setenv("OTB_KA_VER", "3")
+    Rp = (R + 15) // 16 * 16          # two-chunk pair tiles (tile_n > 256 - Rp) need tile_n and tile_n + Rp multiples of 32
+    for tn in ((0, 96, 224, 320, 448) if Rp % 32 == 0 else (0, 96, 224, 240)):
+        y3, t3 = K.ops.lora_linear(x, w, down, up, bias, 0.5, tile_n=tn)
+        assert torch.equal(t3, t2), tn
+        assert torch.equal(y3, y2), (tn, (y3.float() - y2.float()).abs().max().item())
+    f = lambda a: None if a is None else a.float().cpu().numpy()  # noqa: E731
+    yr, _ = oracle.lora_linear(f(x), f(w), f(down), f(up), f(bias), 0.5, round_t_bf16=True)
+    y = y2.float().cpu().numpy()
+    assert (np.abs(y - yr) <= np.abs(yr) * (2.0 ** -8 + 1e-3) + 2e-2).all()
+
+
 def test_lora_linear_rejects_unsupported_shapes(K, dev):
     x, w, down, up, b = (t.to(dev) for t in _lora_case(dev, 64, 64, 64, 16))
     with pytest.raises(NotImplementedError):
