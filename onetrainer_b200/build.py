@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
     obj_dir = PKG_DIR / "build"
     obj_dir.mkdir(exist_ok=True)
-    headers = [CSRC / "common.cuh", REPO_DIR / "include" / "otb200.h"]
+    headers = [CSRC / "common.cuh", CSRC / "tc_ptx.cuh", REPO_DIR / "include" / "otb200.h"]
     objs = []
     for src in SOURCES:
         s = CSRC / src
