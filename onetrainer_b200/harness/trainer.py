@@ -218,9 +218,11 @@ def build_flux_model(kind: str, config, device, *, train_dtype=torch.bfloat16, l
 def build_model(kind: str, config, device, *, train_dtype=torch.bfloat16, lora_weight_dtype=torch.float32,
                 prediction_type: str = "epsilon", ema: bool = False, stochastic_rounding: bool = True,
                 fused_clip: bool = True, fused_ema: bool = True, seed: int = 1234, lr: float = 3e-4,
-                lora_up_std: float = 0.0) -> tuple[StandInModel, DiffusionSetup]:
+                lora_up_std: float = 0.0, full_finetune: bool = False) -> tuple[StandInModel, DiffusionSetup]:
     """Random-init stand-in + LoRA wrapper + patched AdamW (+EMA), as StableDiffusionXLLoRASetup.setup_model
-    (:103-158) and init_model_parameters (optimizer_util.py:50-65) wire them."""
+    (:103-158) and init_model_parameters (optimizer_util.py:50-65) wire them.  `full_finetune=True` is config C4
+    (StableDiffusionXLFineTuneSetup.setup_model :90-113): no adapters, every UNet tensor trainable in the train
+    dtype, AdamW state and EMA in that dtype too — the path is then K-b1, K-b2 and the multi-tensor SR-AdamW + EMA."""
     torch.manual_seed(seed)
     with torch.device(device):
         unet = {"sdxl": standin.sdxl_unet, "sd15": standin.sd15_unet, "tiny": standin.tiny_unet}[kind]()
@@ -229,6 +231,19 @@ def build_model(kind: str, config, device, *, train_dtype=torch.bfloat16, lora_w
     unet.train()
     sched = standin.StandInScheduler(standin_betas().to(device), prediction_type)   # device-resident: `.to()` is then a no-op under capture
     model = StandInModel(unet, sched, 0.13025 if kind == "sdxl" else 0.18215, train_dtype, sdxl=(kind == "sdxl"))
+    if full_finetune:
+        unet.requires_grad_(True)
+        model.parameters = list(unet.parameters())
+        model.optimizer = torch.optim.AdamW(model.parameters, lr=lr, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+        if ema:
+            model.ema = EMAModuleWrapper(model.parameters, decay=config.ema_decay,
+                                         update_step_interval=config.ema_update_step_interval, device=torch.device(device))
+        progress = model.train_progress
+        patch_adamw(model.optimizer, stochastic_rounding,
+                    ema=model.ema if (ema and fused_ema) else None,
+                    ema_step_fn=(lambda: progress.global_step // config.gradient_accumulation_steps) if (ema and fused_ema) else None,
+                    clip_grad_norm=config.clip_grad_norm if fused_clip else None)
+        return model, DiffusionSetup(torch.device(device))
     model.unet_lora = LoRAModuleWrapper(unet, "lora_unet", config, ["attentions"])
     model.unet_lora.set_dropout(config.dropout_probability)
     model.unet_lora.to(dtype=lora_weight_dtype)
@@ -306,7 +321,7 @@ def train_step(setup: DiffusionSetup, model: StandInModel, batch: dict, config, 
     loss.backward()
     driver = model.optimizer.otb_driver
     if dp.world_size() > 1:
-        bucket = bucket or dp.GradientBucket(model.unet_lora.grad_arena)
+        bucket = bucket or dp.GradientBucket(model.unet_lora.grad_arena if model.unet_lora is not None else None)
         driver.grad_prescale = bucket.allreduce([p.grad for p in model.parameters if p.grad is not None])
     if config.clip_grad_norm is not None and driver.clip_max_norm is None:
         from ..modules.util.grad_clip import clip_grad_norm_

@@ -580,3 +580,33 @@ def test_flux_training_loop_tracks_torch_restatement(P, dev):
     for a, b in zip(mine, ref):
         assert a == pytest.approx(b, rel=2e-2), (mine, ref)
     assert np.mean(mine[-4:]) < np.mean(mine[:4]) and np.mean(ref[-4:]) < np.mean(ref[:4])
+
+
+# ------------------------------------------------------------------------------------------ full fine-tune (config C4)
+def test_full_finetune_sr_adamw_ema_loop_is_reproducible(P, dev):
+    """Config C4 on the tiny stand-in: every tensor trainable in bf16, bf16 AdamW state, stochastic rounding, fused
+    EMA + global-norm clip (StableDiffusionXLFineTuneSetup.py:90-113, adamw_extensions.py:17-150, EMAModule.py:37-54).
+    The loss falls; parameters / state / EMA stay bf16; and — because the SR bits are a function of (seed, step,
+    global element index) only — two runs from the same seed are BIT-identical, while round-to-nearest differs."""
+    B = 4
+
+    def run(sr: bool, steps: int = 16):
+        cfg = P.TrainConfig(train_device=str(dev), batch_size=B, ema_decay=0.99, ema_update_step_interval=2)
+        model, setup = P.trainer.build_model("tiny", cfg, dev, ema=True, stochastic_rounding=sr, lr=2e-3, full_finetune=True)
+        batch = P.trainer.batch_to_device(P.trainer.synthetic_batch("tiny", B, dev, latent_hw=32), dev)
+        losses = [P.trainer.train_step(setup, model, batch, cfg).item() for _ in range(steps)]
+        return model, losses
+
+    m1, l1 = run(True)
+    m2, l2 = run(True)
+    m3, l3 = run(False)
+    assert l1 == l2 and all(torch.equal(a, b) for a, b in zip(m1.parameters, m2.parameters))
+    assert all(torch.equal(a, b) for a, b in zip(m1.ema.ema_parameters, m2.ema.ema_parameters))
+    assert any(not torch.equal(a, b) for a, b in zip(m1.parameters, m3.parameters))          # SR really rounds differently
+    assert np.mean(l1[-4:]) < np.mean(l1[:4]) and np.mean(l3[-4:]) < np.mean(l3[:4])
+    p0 = m1.parameters[0]
+    st = m1.optimizer.state[p0]
+    assert p0.dtype == torch.bfloat16 and st["exp_avg"].dtype == torch.bfloat16 and st["exp_avg_sq"].dtype == torch.bfloat16
+    assert all(e.dtype == torch.bfloat16 and torch.isfinite(e.float()).all() for e in m1.ema.ema_parameters)
+    assert any(not torch.equal(e, p) for e, p in zip(m1.ema.ema_parameters, m1.parameters))  # the average lags the weights
+    assert st["step"].item() == 16

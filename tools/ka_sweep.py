@@ -7,10 +7,14 @@ sys.path.insert(0, ".")
 from onetrainer_b200 import ops
 
 dev = torch.device("cuda:0")
-shapes = [("c1280 qkvo", 4096, 1280, 1280), ("c1280 ff0", 4096, 10240, 1280), ("c1280 ff2", 4096, 1280, 5120), ("c640 qkvo", 16384, 640, 640)]
-if len(sys.argv) > 1:
-    shapes = [s for s in shapes if s[0] in sys.argv[1:]]
+shapes = [("ctx kv", 308, 1280, 2048), ("ctx kv dX", 308, 2048, 1280), ("c640 ctx kv", 308, 640, 2048), ("c640 ctx dX", 308, 2048, 640),
+          ("c1280 qkvo", 4096, 1280, 1280), ("c1280 ff0", 4096, 10240, 1280), ("c1280 ff2", 4096, 1280, 5120), ("c640 qkvo", 16384, 640, 640)]
 cfgs = [(2, 0), (2, 128), (2, 224), (3, 0), (3, 96), (3, 128), (3, 160), (3, 192), (3, 224), (3, 256), (3, 320), (3, 448)]
+if len(sys.argv) > 1 and sys.argv[1] == "ctx":
+    cfgs = [(2, 0), (2, 16), (2, 32), (2, 48), (2, 64), (2, 96), (3, 0), (3, 32), (3, 48), (3, 64), (3, 96), (3, 128), (3, 160)]
+    shapes = [s for s in shapes if "ctx" in s[0]]
+elif len(sys.argv) > 1:
+    shapes = [s for s in shapes if s[0] in sys.argv[1:]]
 
 
 def bench(m, n, k, R, tile_n):
@@ -43,7 +47,7 @@ def bench(m, n, k, R, tile_n):
 
 
 for name, M, N, K in shapes:
-    for R in (32, 0):
+    for R in ((32,) if "ctx" in name else (32, 0)):
         for ver, tn in cfgs:
             if ver == 2 and tn + R > 256:
                 continue
