@@ -90,6 +90,39 @@ class GradientBucket:
         return 1.0 / n
 
 
+class FlatGradArena:
+    """Persistent, flat gradient storage for a parameter list (full fine-tuning, config C4).
+
+    `p.grad` of every parameter becomes a view of ONE buffer in the parameter dtype and stays that view for the whole
+    run (autograd accumulates into an existing `.grad` in place).  That gives the data-parallel exchange the same
+    zero-copy in-place allreduce the LoRA arena has, and it gives a captured CUDA graph gradient addresses that do
+    not move between replays — with `zero_grad(set_to_none=True)` autograd allocates new gradient tensors every step.
+    After the optimizer step call `zero()` (one memset) instead of `optimizer.zero_grad(set_to_none=True)`.
+    """
+
+    def __init__(self, parameters: list[torch.Tensor]):
+        if not parameters:
+            raise ValueError("FlatGradArena: empty parameter list")
+        dt, dev = parameters[0].dtype, parameters[0].device
+        if any(p.dtype != dt or p.device != dev for p in parameters):
+            raise ValueError("FlatGradArena: parameters must share dtype and device")
+        align = 16 // parameters[0].element_size()
+        total, offsets = 0, []
+        for p in parameters:
+            offsets.append(total)
+            total += (p.numel() + align - 1) // align * align           # every slice 16-byte aligned
+        self.flat = torch.zeros((total,), dtype=dt, device=dev)
+        self.parameters = list(parameters)
+        for p, off in zip(parameters, offsets):
+            p.grad = self.flat[off:off + p.numel()].view(p.shape)
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def grads(self) -> list[torch.Tensor]:
+        return [p.grad for p in self.parameters]
+
+
 def _is_view_of(t: torch.Tensor, base: torch.Tensor) -> bool:
     lo = base.data_ptr()
     hi = lo + base.numel() * base.element_size()

@@ -44,6 +44,7 @@ class StandInModel:
         self.train_dtype = train_dtype
         self.sdxl = sdxl
         self.unet_lora: LoRAModuleWrapper | None = None
+        self.full_grad_arena: dp.FlatGradArena | None = None      # full fine-tuning: persistent flat gradients
         self.optimizer = None
         self.ema: EMAModuleWrapper | None = None
         self.parameters: list[nn.Parameter] = []
@@ -234,6 +235,7 @@ def build_model(kind: str, config, device, *, train_dtype=torch.bfloat16, lora_w
     if full_finetune:
         unet.requires_grad_(True)
         model.parameters = list(unet.parameters())
+        model.full_grad_arena = dp.FlatGradArena(model.parameters)
         model.optimizer = torch.optim.AdamW(model.parameters, lr=lr, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
         if ema:
             model.ema = EMAModuleWrapper(model.parameters, decay=config.ema_decay,
@@ -321,17 +323,28 @@ def train_step(setup: DiffusionSetup, model: StandInModel, batch: dict, config, 
     loss.backward()
     driver = model.optimizer.otb_driver
     if dp.world_size() > 1:
-        bucket = bucket or dp.GradientBucket(model.unet_lora.grad_arena if model.unet_lora is not None else None)
+        arena = model.unet_lora.grad_arena if model.unet_lora is not None else getattr(model, "full_grad_arena", None)
+        bucket = bucket or dp.GradientBucket(arena.flat if isinstance(arena, dp.FlatGradArena) else arena)
         driver.grad_prescale = bucket.allreduce([p.grad for p in model.parameters if p.grad is not None])
     if config.clip_grad_norm is not None and driver.clip_max_norm is None:
         from ..modules.util.grad_clip import clip_grad_norm_
         clip_grad_norm_(model.parameters, config.clip_grad_norm, driver.grad_prescale)
     model.optimizer.step()
-    model.optimizer.zero_grad(set_to_none=True)
+    _zero_grads(model)
     if model.ema is not None:
         model.ema.step(model.parameters, model.train_progress.global_step // config.gradient_accumulation_steps)
     model.train_progress.next_step(config.batch_size)
     return loss.detach()
+
+
+def _zero_grads(model) -> None:
+    """`optimizer.zero_grad(set_to_none=True)` (GenericTrainer.py:717), or one memset when the gradients are the
+    persistent views of a FlatGradArena."""
+    arena = getattr(model, "full_grad_arena", None)
+    if arena is not None:
+        arena.zero()
+    else:
+        model.optimizer.zero_grad(set_to_none=True)
 
 
 class GraphedTrainStep:
@@ -340,10 +353,10 @@ class GraphedTrainStep:
     The step launches ~11 k kernels (722 leaves x 3 fused launches, plus the stand-in's attention /
     norm / GEGLU glue); eager python dispatch of those costs more than the GPU work.  Capturing the
     step once removes the host from the loop: per step the host only (1) copies the next batch into
-    pinned staging buffers, (2) rewrites a few pinned words — Philox keys, EMA schedule, per-tensor
-    AdamW scalars (onetrainer_b200/step_state.py, FusedAdamDriver.host_prepare) — and (3) replays.
-    The H2D batch copy, the noise/loss kernels, every leaf, the NCCL allreduce, grad-norm, AdamW and
-    the shadow refresh are all inside the graph, on one stream.
+    pinned staging buffers, (2) prepares a few words — Philox keys, EMA schedule, per-tensor AdamW scalars
+    (onetrainer_b200/step_state.py, FusedAdamDriver.host_prepare) — and uploads them with two small async copies
+    from ring-buffered pinned slots, and (3) replays.  The H2D batch copy, the noise/loss kernels, every leaf,
+    the NCCL allreduce, grad-norm, AdamW and the shadow refresh are all inside the graph, on one stream.
     """
 
     def __init__(self, setup: DiffusionSetup, model: StandInModel, config, example_batch: dict, warmup: int = 3):
@@ -359,6 +372,7 @@ class GraphedTrainStep:
         self.driver = model.optimizer.otb_driver
         self.loss = None
         self.graph = None
+        self._replayed = None
         self.set_batch(example_batch)
         step_state.activate(self.state)
         # warm-up on a side stream (allocator, lazy tables, cuBLAS/SDPA workspaces) as torch's capture rules require
@@ -371,6 +385,8 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.driver.freeze_for_graph()
+        self._frozen_params = [p for p, _ in self.driver._frozen_active]
+        self._frozen_grad_ptrs = [int(v) for v in self.driver.table.host["g"]]
         self._host_part()
         from .. import ops
         before = ops.LAUNCHES
@@ -378,6 +394,9 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self._device_part(first=False)
         self.launches_per_step = ops.LAUNCHES - before      # libotb200 kernels inside one replay
+        # capture records but does not execute; the host side of this step (Philox keys, AdamW step counters and
+        # bias corrections) has been prepared, so run it now — otherwise the step would be counted but never taken
+        self.graph.replay()
         self._after_step()
 
     # host-side work that must precede every replay
@@ -385,11 +404,15 @@ class GraphedTrainStep:
         step = self.model.train_progress.global_step
         self.state.set_noise_key(step, 0)           # predict(): generator.manual_seed(global_step), first draw
         self.driver.host_prepare()
+        # this step's words and per-tensor AdamW scalars go to the device now, on the stream the replay follows on
+        # (ring-buffered pinned sources: the host may be a step ahead of the GPU)
+        self.state.upload()
+        self.driver.upload_table()
 
     def _device_part(self, first: bool) -> None:
         if first:                                   # eager warm-up: the optimizer's host part runs after backward (below)
             self.state.set_noise_key(self.model.train_progress.global_step, 0)
-        self.state.upload()
+            self.state.upload()
         for k, v in self.host_batch.items():
             if isinstance(v, list):
                 for d, h in zip(self.dev_batch[k], v):
@@ -402,20 +425,30 @@ class GraphedTrainStep:
         loss.backward()
         if dp.world_size() > 1:
             if self.bucket.arena is None:
-                self.bucket.arena = model.unet_lora.grad_arena
+                self.bucket.arena = model.unet_lora.grad_arena if model.unet_lora is not None else model.full_grad_arena.flat
             self.driver.grad_prescale = self.bucket.allreduce([p.grad for p in model.parameters if p.grad is not None])
         if first:
             self.driver.host_prepare()              # discovers the gradients, builds the table, fills the scalars
             self.state.upload()                     # the optimizer's dynamic words were written just now
-        self.driver.device_step()
-        model.optimizer.zero_grad(set_to_none=True)
+        if not first:
+            # the captured optimizer launch reads gradients through a pointer table frozen after the warm-up steps: refuse
+            # to capture (nothing has executed yet) if autograd handed out gradient tensors at other addresses
+            moved = [p for p, g in zip(self._frozen_params, self._frozen_grad_ptrs) if p.grad is None or p.grad.data_ptr() != g]
+            if moved:
+                raise RuntimeError(f"GraphedTrainStep: {len(moved)} gradient tensors do not live at stable addresses; give the "
+                                   "parameters persistent gradients (LoRA: the wrapper's arena; full fine-tuning: dp.FlatGradArena)")
+        self.driver.device_step(upload=first)       # captured: the table was uploaded by _host_part()
+        _zero_grads(model)
         self.loss = loss.detach()
 
     def _after_step(self) -> None:
         self.model.train_progress.next_step(self.config.batch_size)
 
     def set_batch(self, batch: dict) -> None:
-        """Stage the next batch in pinned memory (host memcpy); the H2D copy happens inside the graph."""
+        """Stage the next batch in pinned memory (host memcpy); the H2D copy happens inside the graph.  The previous
+        replay must have consumed the staging buffers first."""
+        if self._replayed is not None:
+            self._replayed.synchronize()
         for k, v in batch.items():
             if isinstance(v, list):
                 for h, t in zip(self.host_batch[k], v):
@@ -429,6 +462,9 @@ class GraphedTrainStep:
             self.set_batch(batch)
         self._host_part()
         self.graph.replay()
+        if self._replayed is None:
+            self._replayed = torch.cuda.Event()
+        self._replayed.record()
         self._after_step()
         return self.loss
 

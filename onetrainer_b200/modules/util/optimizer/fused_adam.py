@@ -171,10 +171,12 @@ class FusedAdamDriver:
         return True
 
     @torch.no_grad()
-    def device_step(self) -> None:
-        """The DEVICE side of `step()`: table upload, [grad-norm], fused clip+AdamW(+SR)(+EMA)."""
+    def device_step(self, upload: bool = True) -> None:
+        """The DEVICE side of `step()`: table upload, [grad-norm], fused clip+AdamW(+SR)(+EMA).  A captured step passes
+        `upload=False` and uploads the table before each replay instead (`upload_table`)."""
         table = self.table
-        table.upload()
+        if upload:
+            table.upload()
         clip = None
         if self.clip_max_norm is not None:
             self.last_norm_coef = ops.grad_norm_multi(table, self.clip_max_norm, self.grad_prescale)
@@ -191,6 +193,10 @@ class FusedAdamDriver:
         _bump_versions([p for p, _ in self._last_active])
         for hook in self.post_step_hooks:
             hook()
+
+    def upload_table(self) -> None:
+        """Graph mode: the per-tensor scalars written by host_prepare() go to the device before the replay."""
+        self.table.upload()
 
     def freeze_for_graph(self) -> None:
         """Pin the current parameter/gradient set: later host_prepare() calls skip rediscovery."""

@@ -31,6 +31,29 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class PinnedRing:
+    """Slot bookkeeping for pinned staging buffers that feed asynchronous H2D copies."""
+    SLOTS = 3
+
+    def __init__(self):
+        self._events = [None] * self.SLOTS
+        self._next = 0
+
+    def acquire(self) -> int:
+        slot = self._next
+        self._next = (slot + 1) % self.SLOTS
+        ev = self._events[slot]
+        if ev is not None:
+            ev.synchronize()            # the copy that read this slot SLOTS uploads ago (normally long done)
+        return slot
+
+    def release(self, slot: int) -> None:
+        ev = self._events[slot]
+        if ev is None:
+            ev = self._events[slot] = torch.cuda.Event()
+        ev.record()                     # on the current stream, right after the copy
+
+
 # --------------------------------------------------------------------------------------
 # side stream for the weight-gradient kernel
 # --------------------------------------------------------------------------------------
@@ -302,8 +325,13 @@ class OptimTable:
         self.n = len(entries)
         self.chunk_elems = chunk_elems
         self.host = np.zeros(self.n, dtype=_OPT_DTYPE)
-        self._pinned = torch.empty((max(self.n, 1) * _OPT_DTYPE.itemsize,), dtype=torch.uint8).pin_memory() \
+        # ring of pinned staging buffers: an async H2D copy reads its source when the GPU gets to it, by which time a
+        # host running ahead may already be writing the NEXT step's scalars — each upload takes the next slot and a
+        # slot is rewritten only after the copy that last read it has completed
+        nbytes = max(self.n, 1) * _OPT_DTYPE.itemsize
+        self._pinned = [torch.empty((nbytes,), dtype=torch.uint8).pin_memory() for _ in range(PinnedRing.SLOTS)] \
             if torch.cuda.is_available() else None
+        self._ring = PinnedRing()
         self.dev = torch.empty((max(self.n, 1) * _OPT_DTYPE.itemsize,), dtype=torch.uint8, device=self.device)
         chunk_tensor, chunk_index = [], []
         rng_base = 0
@@ -366,10 +394,17 @@ class OptimTable:
         return range(0, len(grads), max(1, len(grads) // 8))
 
     def upload(self) -> None:
+        """Host table -> device, asynchronously on the current stream.  NOT capturable: the host->pinned memcpy
+        happens now, in python — a captured step uploads before the replay (harness/trainer.py)."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("OptimTable.upload() inside a CUDA-graph capture would freeze this step's scalars into every "
+                               "replay; upload before graph.replay()")
         raw = self.host.view(np.uint8).reshape(-1)
         if self._pinned is not None:
-            self._pinned[: raw.size].numpy()[:] = raw
-            self.dev[: raw.size].copy_(self._pinned[: raw.size], non_blocking=True)
+            slot = self._ring.acquire()
+            self._pinned[slot][: raw.size].numpy()[:] = raw
+            self.dev[: raw.size].copy_(self._pinned[slot][: raw.size], non_blocking=True)
+            self._ring.release(slot)
         else:
             self.dev[: raw.size].copy_(torch.from_numpy(raw.copy()))
 

@@ -2,9 +2,9 @@
 
 A CUDA graph bakes kernel arguments in at capture time.  The hot path has four values that change
 every step — the noise Philox key, the stochastic-rounding key, the EMA decay and the EMA on/off
-flag — so, while a `DeviceStepState` is active, the host code writes them into a pinned staging
-buffer and the kernels read them from device memory (`rng_dev` / `dyn` in include/otb200.h).  The
-staging->device copy is part of the captured graph; the host only rewrites the pinned words.
+flag — so, while a `DeviceStepState` is active, the host code writes them into a working copy, uploads
+it through a ring of pinned slots right before each replay, and the kernels read them from device
+memory (`rng_dev` / `dyn` in include/otb200.h).
 """
 from __future__ import annotations
 
@@ -23,9 +23,11 @@ class DeviceStepState:
     DYN = 2          # words 2..4: otb_optim_dyn {seed, offset, (float omd | int32 do_ema << 32)}
 
     def __init__(self, device):
-        self.host = torch.zeros(8, dtype=torch.int64).pin_memory()
+        from .ops import PinnedRing
+        self._np = np.zeros(8, dtype=np.int64)          # the host's working copy
+        self._hosts = [torch.zeros(8, dtype=torch.int64).pin_memory() for _ in range(PinnedRing.SLOTS)]
+        self._ring = PinnedRing()
         self.dev = torch.zeros(8, dtype=torch.int64, device=device)
-        self._np = self.host.numpy()
         assert C.sizeof(N.OptimDyn) == 24
 
     def set_noise_key(self, seed: int, offset: int) -> None:
@@ -39,8 +41,14 @@ class DeviceStepState:
         self._np[4] = packed.astype(np.int64)
 
     def upload(self) -> None:
-        """Captured once; on replay it re-reads whatever the host wrote into the pinned words."""
-        self.dev.copy_(self.host, non_blocking=True)
+        """Working copy -> device on the current stream, through a ring of pinned slots (the host may already be
+        preparing the next step when the GPU executes the copy).  Issued BEFORE the graph replay, not captured."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("DeviceStepState.upload() must run before graph.replay(), not inside the capture")
+        slot = self._ring.acquire()
+        self._hosts[slot].numpy()[:] = self._np
+        self.dev.copy_(self._hosts[slot], non_blocking=True)
+        self._ring.release(slot)
 
     @property
     def noise_ptr(self) -> torch.Tensor:

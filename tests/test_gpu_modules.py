@@ -610,3 +610,37 @@ def test_full_finetune_sr_adamw_ema_loop_is_reproducible(P, dev):
     assert all(e.dtype == torch.bfloat16 and torch.isfinite(e.float()).all() for e in m1.ema.ema_parameters)
     assert any(not torch.equal(e, p) for e, p in zip(m1.ema.ema_parameters, m1.parameters))  # the average lags the weights
     assert st["step"].item() == 16
+
+
+def test_graphed_step_matches_eager_for_lora_and_full_finetune(P, dev):
+    """The CUDA-graph step replays exactly the eager step: same losses (LoRA: up to the order of the fp32 gradient atomics), bit-identical parameters for full fine-tuning — for
+    the LoRA path (gradients in the wrapper's arena) and for full fine-tuning (gradients in a dp.FlatGradArena); and
+    capture refuses parameters whose gradients would move between replays instead of reading stale addresses."""
+    B = 2
+    for full in (False, True):
+        def make():
+            cfg = P.TrainConfig(train_device=str(dev), batch_size=B, lora_rank=16, lora_alpha=8.0)
+            model, setup = P.trainer.build_model("tiny", cfg, dev, ema=full, stochastic_rounding=True, lora_up_std=0.05, lr=1e-3,
+                                                 full_finetune=full)
+            return cfg, model, setup
+        host_batch = P.trainer.synthetic_batch("tiny", B, dev, latent_hw=32)
+        cfg, m_e, s_e = make()
+        dev_batch = P.trainer.batch_to_device(host_batch, dev)
+        eager = [P.trainer.train_step(s_e, m_e, dev_batch, cfg).item() for _ in range(10)]
+        cfg, m_g, s_g = make()
+        g = P.trainer.GraphedTrainStep(s_g, m_g, cfg, host_batch, warmup=3)      # runs steps 0-2 eagerly and step 3 as the first replay
+        try:
+            graphed = [g.step().item() for _ in range(6)]
+        finally:
+            g.close()
+        assert graphed == pytest.approx(eager[4:], rel=2e-3 if not full else 1e-6), (full, eager, graphed)
+        if full:       # full fine-tuning has no atomics anywhere: bit-identical weights
+            assert all(torch.equal(a, b) for a, b in zip(m_e.parameters, m_g.parameters))
+    # gradients that are re-allocated every step cannot be captured
+    cfg = P.TrainConfig(train_device=str(dev), batch_size=B)
+    model, setup = P.trainer.build_model("tiny", cfg, dev, full_finetune=True, lr=1e-3)
+    for p in model.parameters:
+        p.grad = None
+    model.full_grad_arena = None
+    with pytest.raises(RuntimeError, match="stable addresses"):
+        P.trainer.GraphedTrainStep(setup, model, cfg, P.trainer.synthetic_batch("tiny", B, dev, latent_hw=32), warmup=3)
