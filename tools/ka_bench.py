@@ -1,11 +1,13 @@
 """Device-time microbenchmark of K-a per SDXL leaf shape (CUDA-graph replay, so no host launch gaps).
-usage: python tools/ka_bench.py [tile_n] ; env OTB_KA_CM / OTB_KA_CN / OTB_KA_V1 select the variant."""
+usage: python tools/ka_bench.py [flux] [tile_n] [stages] [ref] ; env OTB_KA_VER=2|3 selects the variant."""
 import sys
 import torch
 sys.path.insert(0, ".")
 from onetrainer_b200 import ops
 
 dev = torch.device("cuda:0")
+FLUX = "flux" in sys.argv[1:]
+sys.argv = [a for a in sys.argv if a not in ("flux",)]
 tile_n = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 stages = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 # (name, M, N, K, count per step) for SDXL B=4: forward shapes; dX swaps N and K
@@ -13,6 +15,11 @@ shapes = [("c1280 qkvo/proj", 4096, 1280, 1280, 6 * 60 + 12), ("c1280 kv(ctx)", 
           ("c1280 ff2", 4096, 1280, 5120, 60), ("c640 qkvo/proj", 16384, 640, 640, 6 * 10 + 10), ("c640 kv(ctx)", 308, 640, 2048, 2 * 10),
           ("c640 ff0", 16384, 5120, 640, 10), ("c640 ff2", 16384, 640, 2560, 10)]
 R = 32
+if FLUX:      # FLUX.1-dev at B=1 (config C5): 19 double + 38 single blocks, rank 16
+    R = 16
+    shapes = [("flux img qkvo", 4096, 3072, 3072, 4 * 19), ("flux txt qkvo", 512, 3072, 3072, 4 * 19), ("flux ff0", 4096, 12288, 3072, 19),
+              ("flux ff2", 4096, 3072, 12288, 19), ("flux single qkv", 4608, 3072, 3072, 3 * 38)]
+    tile_n = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 tot_t, tot_f = 0.0, 0.0
 for name, M, N, K, cnt in shapes:
     for role, (m, n, k) in (("fwd", (M, N, K)), ("dX ", (M, K, N))):
