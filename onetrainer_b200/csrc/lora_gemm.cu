@@ -6,7 +6,8 @@
 // dropout, scale and add as separate ATen launches) and, called with the transposed shadows,
 // the dX half of its autograd backward.
 //
-// sm_100a design (one CTA per 128 x tile_n output tile, 192 threads, warp-specialised):
+// sm_100a design, common to both variants below (warp-specialised; v2: one CTA per 128 x tile_n tile, v3: a CTA pair
+// per 256 x tile_n tile):
 //   warp 0     TMA producer: x / w / down tiles (64-wide K slabs, 128B swizzle) into a
 //              multi-stage smem ring, mbarrier full/empty pairs
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer.  The w tile and the down
@@ -49,190 +50,10 @@ struct GemmParams {
     uint16_t* t_out;
 };
 
-// smem carve-up (all tile bases stay 1024 B aligned because tile_n and Rp are multiples of 16)
-struct SmemLayout {
-    uint32_t stage_bytes, x_off, w_off, up_off, t_off, bar_off, total;
-};
-__host__ __device__ inline SmemLayout make_layout(int tile_n, int Rp, int stages) {
-    SmemLayout L;
-    L.x_off = 0;
-    L.w_off = BM * 128;
-    L.stage_bytes = (uint32_t)(BM + tile_n + Rp) * 128;
-    L.up_off = L.stage_bytes * stages;
-    L.t_off = L.up_off + (Rp ? (uint32_t)tile_n * 128 : 0);
-    L.bar_off = L.t_off + (Rp ? BM * 128 : 0);
-    L.total = L.bar_off + 256;
-    return L;
-}
-
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-lora_linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                   const __grid_constant__ CUtensorMap tm_dn, const __grid_constant__ CUtensorMap tm_up,
-                   const GemmParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // dynamic smem is only guaranteed 16 B aligned by the ABI; align by hand (host adds 1 KiB of slack)
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const SmemLayout L = make_layout(p.tile_n, p.Rp, p.stages);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x / p.n_tiles, n_tile = blockIdx.x % p.n_tiles;
-    const int m0 = m_tile * BM, n0 = n_tile * p.tile_n;
-    const bool lora = p.Rp > 0;
-
-    const uint32_t bar_base = smem_base + L.bar_off;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
-    const uint32_t up_full = bar_base + 8u * (2 * MAX_STAGES + 0);
-    const uint32_t t_full = bar_base + 8u * (2 * MAX_STAGES + 1);
-    const uint32_t t_ready = bar_base + 8u * (2 * MAX_STAGES + 2);
-    const uint32_t d_full = bar_base + 8u * (2 * MAX_STAGES + 3);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bar_off + 8u * (2 * MAX_STAGES + 4));
-
-    if (threadIdx.x == 0) {
-        prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
-        if (lora) { prefetch_tmap(&tm_dn); prefetch_tmap(&tm_up); }
-        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(up_full, 1); mbar_init(t_full, 1); mbar_init(t_ready, 128); mbar_init(d_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_gen;
-
-    if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            if (lora) {
-                mbar_expect_tx(up_full, (uint32_t)p.tile_n * 128);
-                tma_load_2d(smem_base + L.up_off, &tm_up, up_full, 0, n0);
-            }
-            int s = 0; uint32_t ph = 0;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                mbar_wait(empty_bar(s), ph ^ 1);
-                const uint32_t st = smem_base + L.stage_bytes * s;
-                mbar_expect_tx(full_bar(s), L.stage_bytes);
-                tma_load_2d(st + L.x_off, &tm_x, full_bar(s), kb * BK, m0);
-                tma_load_2d(st + L.w_off, &tm_w, full_bar(s), kb * BK, n0);
-                if (lora) tma_load_2d(st + L.w_off + (uint32_t)p.tile_n * 128, &tm_dn, full_bar(s), kb * BK, 0);
-                if (++s == p.stages) { s = 0; ph ^= 1; }
-            }
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc_main = umma_idesc_bf16(BM, p.tile_n + p.Rp);
-            int s = 0; uint32_t ph = 0;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                mbar_wait(full_bar(s), ph);
-                tc_fence_after();
-                const uint32_t st = smem_base + L.stage_bytes * s;
-                const uint64_t adesc = umma_desc_sw128(st + L.x_off);
-                const uint64_t bdesc = umma_desc_sw128(st + L.w_off);
-#pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)   // +32 B per k-step inside the swizzle row
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_main, (kb | k) != 0);
-                umma_commit(empty_bar(s));               // frees the smem stage once these MMAs retire
-                if (++s == p.stages) { s = 0; ph ^= 1; }
-            }
-            if (lora) {
-                umma_commit(t_full);                     // T = x.down^T complete (and the base GEMM with it)
-                mbar_wait(t_ready, 0);                   // epilogue parked bf16 T in smem
-                mbar_wait(up_full, 0);
-                tc_fence_after();
-                const uint32_t idesc_up = umma_idesc_bf16(BM, p.tile_n);
-                const uint64_t adesc = umma_desc_sw128(smem_base + L.t_off);
-                const uint64_t bdesc = umma_desc_sw128(smem_base + L.up_off);
-                for (int k = 0; k < p.Rp / UMMA_K; ++k)
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_up, 1u);
-            }
-            umma_commit(d_full);
-        }
-    } else {
-        // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =================
-        const int quad = warp & 3;
-        const int row = quad * 32 + lane;                // row inside the 128-row tile == TMEM lane
-        const int m = m0 + row;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        if (lora) {
-            mbar_wait(t_full, 0);
-            tc_fence_after();
-            const float keep_scale = p.dropout_p > 0.0f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
-            uint8_t* t_row = smem_gen + L.t_off + row * 128;
-            for (int c = 0; c < p.Rp; c += 16) {
-                uint32_t v[16];
-                tmem_ld16(t_lane + (uint32_t)(p.tile_n + c), v);
-                tmem_ld_wait();
-                float f[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.scale;
-                if (p.dropout_p > 0.0f) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const uint64_t e = (uint64_t)m * (uint64_t)p.Rp + (uint64_t)(c + j);
-                        Philox4 r = otb_rng(p.seed, p.offset, OTB_STREAM_DROPOUT, e >> 2);
-                        f[j + 0] = otb_u01(r.x) >= p.dropout_p ? f[j + 0] * keep_scale : 0.0f;
-                        f[j + 1] = otb_u01(r.y) >= p.dropout_p ? f[j + 1] * keep_scale : 0.0f;
-                        f[j + 2] = otb_u01(r.z) >= p.dropout_p ? f[j + 2] * keep_scale : 0.0f;
-                        f[j + 3] = otb_u01(r.w) >= p.dropout_p ? f[j + 3] * keep_scale : 0.0f;
-                    }
-                }
-                uint4 lo = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-                uint4 hi = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
-                // canonical SW128 K-major: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
-                const int j0 = c >> 3;
-                *reinterpret_cast<uint4*>(t_row + (((j0 + 0) ^ (row & 7)) << 4)) = lo;
-                *reinterpret_cast<uint4*>(t_row + (((j0 + 1) ^ (row & 7)) << 4)) = hi;
-                if (p.t_out != nullptr && n_tile == 0 && m < p.M) {
-                    uint16_t* dst = p.t_out + (size_t)m * p.R + c;
-                    if (c + 8 <= p.R) *reinterpret_cast<uint4*>(dst) = lo;
-                    if (c + 16 <= p.R) *reinterpret_cast<uint4*>(dst + 8) = hi;
-                }
-            }
-            fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            tc_fence_before();
-            mbar_arrive(t_ready);
-        }
-        mbar_wait(d_full, 0);
-        tc_fence_after();
-        for (int c = 0; c < p.tile_n; c += 16) {
-            const int n = n0 + c;
-            if (n >= p.N) break;                         // warp-uniform
-            uint32_t v[16];
-            tmem_ld16(t_lane + (uint32_t)c, v);
-            tmem_ld_wait();
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-            if (p.bias != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (n + j < p.N) f[j] += load_as_float(p.bias, n + j, p.bias_dtype);
-            }
-            if (m < p.M) {
-                uint16_t* dst = p.y + (size_t)m * p.N + n;
-                if (n + 8 <= p.N)
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-                if (n + 16 <= p.N)
-                    *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        __syncwarp();
-        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-    }
-}
-
 // =====================================================================================
 // v2: persistent, thread-block-cluster TMA multicast, double-buffered TMEM accumulators
 // =====================================================================================
-// What v1 left on the table (ncu, profiles/r01_ka_v1.txt): one tile per CTA means the epilogue
+// What the first, one-tile-per-CTA version left on the table: one tile per CTA means the epilogue
 // (TMEM -> registers -> HBM) and the bf16 T hand-off never overlap the next tile's MMAs, and every
 // CTA pulls its own copy of the x and w tiles through L2: 48 KB per 64-wide k-block per CTA is
 // ~27 TB/s of L2->SMEM traffic at the tensor peak — the kernel was L2-bound at 32 % tensor-pipe
@@ -935,26 +756,6 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 // ------------------------------- host side ------------------------------------------
 constexpr int SMEM_LIMIT = 227 * 1024;
 
-// Pick the tile width that minimises (waves x per-tile time) on `sms` SMs.  Per 16-wide k-step a
-// tile costs max(N'/2, 32 + N'/4) cycles (tensor pipe vs 128 B/clk of smem operand fetch,
-// N' = tile_n + Rp); the epilogue adds ~12 cycles per output column.
-int choose_tile_n(int M, int N, int K, int Rp, int sms) {
-    const int m_tiles = (M + BM - 1) / BM;
-    const int kb4 = ((K + BK - 1) / BK) * 4;
-    double best = 1e30; int best_tn = 64;
-    for (int tn = 32; tn + Rp <= 256; tn += 16) {
-        int n_tiles = (N + tn - 1) / tn;
-        int64_t tiles = (int64_t)m_tiles * n_tiles;
-        int64_t waves = (tiles + sms - 1) / sms;
-        int np = tn + Rp;
-        double kstep = np / 2.0 > 32 + np / 4.0 ? np / 2.0 : 32 + np / 4.0;
-        double tile_time = kb4 * kstep + 12.0 * tn + 1500.0;
-        double t = waves * tile_time;
-        if (t < best - 1e-9) { best = t; best_tn = tn; }
-    }
-    return best_tn;
-}
-
 }  // namespace
 
 int env_int(const char* name, int dflt) {
@@ -1229,7 +1030,7 @@ extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
     OTB_CHECK_ARG((((uintptr_t)a->x | (uintptr_t)a->w | (uintptr_t)a->y | (uintptr_t)a->down | (uintptr_t)a->up |
                     (uintptr_t)a->t_out) & 15) == 0, "all tensor pointers must be 16-byte aligned");
     OTB_BIND(a->x);
-    if (env_int("OTB_KA_V1", 0) == 0) {
+    {
         // variant choice: the cost model picks between single-CTA tiles (v2) and CTA-pair tiles (v3);
         // OTB_KA_VER=2|3 forces one (A/B runs), an explicit tile_n > 256 needs v3
         const int sms = otb_sm_count();
@@ -1246,48 +1047,5 @@ extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
         if (use3) return launch_v3(a, stream, a->tile_n > 0 ? a->tile_n : p3.tile_n, pairs);
         return launch_v2(a, stream);
     }
-    int sms = otb_sm_count();
-    GemmParams p;
-    p.M = a->M; p.N = a->N; p.K = a->K; p.R = a->R;
-    p.Rp = (a->R + 15) / 16 * 16;
-    p.tile_n = a->tile_n > 0 ? a->tile_n : choose_tile_n(a->M, a->N, a->K, p.Rp, sms);
-    OTB_CHECK_ARG(p.tile_n % 16 == 0 && p.tile_n >= 16 && p.tile_n + p.Rp <= 256, "tile_n %d invalid (multiple of 16, tile_n + rank <= 256)", p.tile_n);
-    p.num_kb = (a->K + BK - 1) / BK;
-    p.n_tiles = (a->N + p.tile_n - 1) / p.tile_n;
-    int cols = 32;
-    while (cols < p.tile_n + p.Rp) cols <<= 1;
-    p.tmem_cols = cols;
-    int stages = a->stages > 0 ? a->stages : MAX_STAGES;
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (stages > p.num_kb) stages = p.num_kb;
-    while (stages > 1 && (int)make_layout(p.tile_n, p.Rp, stages).total + 1024 > SMEM_LIMIT) --stages;
-    p.stages = stages;
-    const SmemLayout L = make_layout(p.tile_n, p.Rp, stages);
-    OTB_CHECK_ARG((int)L.total + 1024 <= SMEM_LIMIT, "tile does not fit shared memory");
-    p.scale = a->scale; p.dropout_p = a->dropout_p; p.seed = a->seed; p.offset = a->offset;
-    p.bias = a->bias; p.bias_dtype = a->bias_dtype;
-    p.y = (uint16_t*)a->y; p.t_out = (uint16_t*)a->t_out;
 
-    CUtensorMap tm_x, tm_w, tm_dn, tm_up;
-    int rc;
-    if ((rc = make_tmap(&tm_x, a->x, a->M, a->K, BM, "x")) != OTB_OK) return rc;
-    if ((rc = make_tmap(&tm_w, a->w, a->N, a->K, p.tile_n, "w")) != OTB_OK) return rc;
-    if (p.Rp > 0) {
-        if ((rc = make_tmap(&tm_dn, a->down, a->R, a->K, p.Rp, "down")) != OTB_OK) return rc;
-        if ((rc = make_tmap(&tm_up, a->up, a->N, a->R, p.tile_n, "up")) != OTB_OK) return rc;
-    } else {
-        tm_dn = tm_x; tm_up = tm_x;
-    }
-    static thread_local int smem_set_for_dev = -1;
-    int dev = 0;
-    OTB_CUDA(cudaGetDevice(&dev));
-    if (smem_set_for_dev != dev) {
-        OTB_CUDA(cudaFuncSetAttribute(lora_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        smem_set_for_dev = dev;
-    }
-    const int m_tiles = (a->M + BM - 1) / BM;
-    dim3 grid((unsigned)(m_tiles * p.n_tiles));
-    lora_linear_kernel<<<grid, NUM_THREADS, L.total + 1024, (cudaStream_t)stream>>>(tm_x, tm_w, tm_dn, tm_up, p);
-    OTB_LAUNCH_CHECK("lora_linear_kernel");
-    return OTB_OK;
 }
