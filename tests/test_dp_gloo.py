@@ -41,6 +41,22 @@ def _worker(rank, world, port, out_dir):
     t1, t2 = torch.full((5,), float(rank)), torch.full((2, 3), 2.0 + rank)
     pre = dp.GradientBucket(None).allreduce([t1, t2])
     assert pre == 0.5 and torch.equal(t1, torch.full((5,), 1.0)) and torch.equal(t2, torch.full((2, 3), 5.0))
+    # (2b) full fine-tuning: persistent flat gradients (dp.FlatGradArena) -> autograd accumulates into the views in
+    # place, the exchange runs in place on the arena, and one memset replaces zero_grad(set_to_none=True)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(6, 3)
+    fa = dp.FlatGradArena(list(lin.parameters()))
+    ptrs = [p.grad.data_ptr() for p in lin.parameters()]
+    for _ in range(2):                                   # two micro-batches accumulate
+        lin(torch.full((4, 6), float(rank + 1))).sum().backward()
+    assert [p.grad.data_ptr() for p in lin.parameters()] == ptrs
+    assert all(dp._is_view_of(p.grad, fa.flat) for p in lin.parameters())
+    pre = dp.GradientBucket(fa.flat).allreduce(fa.grads())
+    assert pre == 0.5
+    assert torch.equal(lin.bias.grad, torch.full((3,), 2 * 4.0 * world))                    # sum over ranks of 2 x 4 ones
+    assert torch.equal(lin.weight.grad, torch.full((3, 6), 2 * 4.0 * (1.0 + 2.0)))
+    fa.zero()
+    assert all(not p.grad.any() for p in lin.parameters()) and [p.grad.data_ptr() for p in lin.parameters()] == ptrs
     # (3) loss averaging for logging
     assert dp.average_scalar(torch.tensor(float(rank))).item() == 0.5
     # (4) DP-invariant draws: this rank's samples of the global batch, through the oracle's stream definition
