@@ -473,9 +473,9 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(misc(0 + i), 1); mbar_init(misc(2 + i), 1); mbar_init(misc(4 + i), 1);
-            mbar_init(misc(8 + i), 1); mbar_init(misc(10 + i), 2 * 32 * V3_EPI_WARPS);
+            mbar_init(misc(8 + i), 1); mbar_init(misc(10 + i), 2 * V3_EPI_WARPS);     // one arrival per epilogue warp of the pair
         }
-        mbar_init(misc(6), 2 * 32 * V3_EPI_WARPS);
+        mbar_init(misc(6), 2 * V3_EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_2sm(misc(12), 512u);
@@ -656,9 +656,10 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                         if (c + 16 <= p.R) *reinterpret_cast<uint4*>(dst + 8) = hi;
                     }
                 }
-                fence_proxy_async();
+                fence_proxy_async();                                        // every lane: its T rows are visible to the tensor core
                 tc_fence_before();
-                mbar_arrive_cluster(t_ready_leader);                        // t_ready (leader's barrier, every epilogue thread of the pair)
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(t_ready_leader);         // t_ready: ONE remote arrival per warp (16 per pair, not 512)
             }
             mbar_wait(misc(8 + as), par);                                   // d_full
             tc_fence_after();
@@ -740,7 +741,8 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 }
             }
             tc_fence_before();
-            mbar_arrive_cluster(mapa_u32(misc(10 + as), 0));                // acc_empty (leader's barrier, every epilogue thread of the pair)
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(misc(10 + as), 0));  // acc_empty: one remote arrival per warp
         }
         if (lane == 0) bulk_wait<0>();            // every TMA store of this thread has been written before the CTA exits
     }
