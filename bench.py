@@ -172,32 +172,63 @@ def time_leaf_kernels(model, dev) -> dict:
     _, _, shapes = leaf_flops(model)
     g = torch.Generator(device=dev).manual_seed(0)
     acts = {}
+
+    def act(M, C, i=0):
+        if (M, C, i) not in acts:
+            acts[(M, C, i)] = (torch.randn(M, C, device=dev, generator=g) * 0.05).bfloat16()
+        return acts[(M, C, i)]
+
     mods = list(model.unet_lora.lora_modules.values())
+    shape_of = {id(m): s for m, s in zip(mods, shapes)}
+    # launch units exactly as the step issues them: sibling groups (q/k/v of a self-attention, k/v of a cross-attention)
+    # are ONE grouped launch forward and one for their dX GEMMs; every other leaf is launched singly
+    grouped = {}
+    for grp in getattr(model.unet_lora, "sibling_groups", []):
+        if grp.enabled:
+            for m in grp.members:
+                grouped[id(m)] = grp
+    units, seen = [], set()
+    for m in mods:
+        grp = grouped.get(id(m))
+        if grp is None:
+            units.append([m])
+        elif id(grp) not in seen:
+            seen.add(id(grp))
+            units.append(list(grp.members))
     plan = []
     gemm_flops, grad_flops, grad_bytes = 0.0, 0.0, 0.0
-    for m, (M, N, K, r) in zip(mods, shapes):
-        if (M, K) not in acts:
-            acts[(M, K)] = (torch.randn(M, K, device=dev, generator=g) * 0.05).bfloat16()
-        if (M, N) not in acts:
-            acts[(M, N)] = (torch.randn(M, N, device=dev, generator=g) * 0.05).bfloat16()
-        sh = m._operands()
-        plan.append((acts[(M, K)], acts[(M, N)], sh, m._scale(), torch.zeros(r, K, device=dev), torch.zeros(N, r, device=dev),
-                     torch.zeros(M, r, device=dev, dtype=torch.bfloat16)))
-        gemm_flops += 4.0 * M * K * N + 4.0 * M * r * (K + N)      # forward + dX, each 2MKN + 2Mr(K+N)
-        grad_flops += 2.0 * M * r * (K + N)                        # dA + dB
-        grad_bytes += 2.0 * M * (K + N) + 4.0 * M * r + 8.0 * r * (K + N)   # stream x, dY, Gs, Ts once; fp32 RMW of dA, dB
+    for unit in units:
+        M, N, K, r = shape_of[id(unit[0])]
+        entry = []
+        for i, m in enumerate(unit):
+            sh = m._operands()
+            entry.append((act(M, K), act(M, N, i), sh, m._scale(), torch.zeros(r, K, device=dev), torch.zeros(N, r, device=dev),
+                          torch.zeros(M, r, device=dev, dtype=torch.bfloat16)))
+            gemm_flops += 4.0 * M * K * N + 4.0 * M * r * (K + N)      # forward + dX, each 2MKN + 2Mr(K+N)
+            grad_flops += 2.0 * M * r * (K + N)                        # dA + dB
+            grad_bytes += 2.0 * M * (K + N) + 4.0 * M * r + 8.0 * r * (K + N)   # stream x, dY, Gs, Ts once; fp32 RMW of dA, dB
+        plan.append(entry)
+    n_leaves = sum(len(e) for e in plan)
 
     def gemms():
-        for x, dy, sh, sc, dA, dB, t in plan:
-            ops.lora_linear(x, sh["w"], sh["a"], sh["b"], sh["bias"], sc)
-            ops.lora_linear(dy, sh["wt"], sh["bt"], sh["at"], None, sc)
+        for e in plan:
+            if len(e) == 1:
+                x, dy, sh, sc, dA, dB, t = e[0]
+                ops.lora_linear(x, sh["w"], sh["a"], sh["b"], sh["bias"], sc)
+                ops.lora_linear(dy, sh["wt"], sh["bt"], sh["at"], None, sc)
+            else:
+                ops.lora_linear_grouped([m[0] for m in e], [m[2]["w"] for m in e], [m[2]["a"] for m in e], [m[2]["b"] for m in e],
+                                        [m[2]["bias"] for m in e], [m[3] for m in e])
+                ops.lora_linear_grouped([m[1] for m in e], [m[2]["wt"] for m in e], [m[2]["bt"] for m in e], [m[2]["at"] for m in e],
+                                        [None] * len(e), [m[3] for m in e])
 
     def grads():
-        for x, dy, sh, sc, dA, dB, t in plan:
-            ops.lora_grad_ab(x, dy, t, t, dA, dB)
+        for e in plan:
+            for x, dy, sh, sc, dA, dB, t in e:
+                ops.lora_grad_ab(x, dy, t, t, dA, dB)
 
     return {"gemm_sec": _graph_time(gemms, dev), "gemm_flops": gemm_flops, "gemm_launches": 2 * len(plan),
-            "grad_sec": _graph_time(grads, dev), "grad_flops": grad_flops, "grad_bytes": grad_bytes, "grad_launches": len(plan)}
+            "grad_sec": _graph_time(grads, dev), "grad_flops": grad_flops, "grad_bytes": grad_bytes, "grad_launches": n_leaves}
 
 
 def time_hbm_kernels(dev, hbm_peak: float) -> list:
@@ -352,7 +383,7 @@ def own_arm(args) -> None:
             "e2e": {"value": world * args.steps / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": sec_e2e / args.steps * 1e3},
             "gpu_launches": launches, "cuda_graph": graphed is not None, "loss": float(last_loss), "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "lora_linear_kernel_v3 / _v2 (K-a: forward + dX launches of all 722 leaves)",
+            "roofline": {"bound": "tensor", "kernel": "lora_linear_kernel_v3 / _v2 (K-a: the forward + dX launches of all 722 leaves; q/k/v siblings grouped)",
                          "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": f"{peak_kind} bf16_tflops_sustained",
                          "algorithmic_flops_per_step": ka["gemm_flops"], "launches_per_step": ka["gemm_launches"],

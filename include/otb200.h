@@ -320,6 +320,13 @@ typedef struct otb_lora_linear_args {
 
 int otb_lora_linear(const otb_lora_linear_args* args, void* stream);
 
+/* Up to three problems of the SAME shape (M, N, K, rank, dropout_p) as ONE launch: members[i] is an ordinary
+ * otb_lora_linear_args (own x, w, down, up, bias, y, t_out, scale, dropout key).  The reference calls the q / k / v
+ * projections of an attention as three separate module forwards (diffusers Attention -> LoRAModule.forward
+ * modules/module/LoRAModule.py:319-323, three times) and autograd runs their three dX GEMMs one after another;
+ * batched, the tiles of all members share one persistent grid.  Results are bit-identical to `count` single calls. */
+int otb_lora_linear_grouped(const otb_lora_linear_args* members, int32_t count, void* stream);
+
 /* dA[R,K] (+)= Gs[M,R]^T x[M,K] ;  dB[N,R] (+)= dy[M,N]^T Ts[M,R]   (fp32 accumulate via
  * split-M partial sums; outputs must be zero or hold the running accumulation). */
 typedef struct otb_lora_grad_args {

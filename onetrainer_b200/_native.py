@@ -134,6 +134,7 @@ SYMBOLS = {
     "otb_loss_blocks_per_sample": (C.c_int, [_i32, _i32, _i32]),
     "otb_loss_bwd_rescale": (C.c_int, [_vp, _i32, _vp, _f32, _i32, _i64, _vp]),
     "otb_lora_linear": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
+    "otb_lora_linear_grouped": (C.c_int, [C.POINTER(LoraLinearArgs), C.c_int32, _vp]),
     "otb_lora_grad_ab": (C.c_int, [C.POINTER(LoraGradArgs), _vp]),
     "otb_philox_dump": (C.c_int, [_u64, _u64, _u32, _i64, _i64, _vp, _vp]),
     "otb_struct_sizes": (C.c_int, [C.POINTER(C.c_int32)]),

@@ -354,8 +354,26 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
 
+// Up to three same-shape problems in ONE launch (a "group": the q/k/v projections of a self-attention, the k/v
+// projections of a cross-attention — or their three dX GEMMs).  Single-leaf launches leave a third of the chip idle
+// on the most frequent SDXL shape (64 tiles of 256 x 320 on 74 CTA pairs, no second tile to hide the epilogue
+// behind); a group of three is 288 tiles over 74 pairs in ~4 full rounds with the epilogue overlapped.
+constexpr int V3_MAX_GROUP = 3;
+struct V3Member {
+    const void* bias;
+    uint16_t* y;
+    uint16_t* t_out;
+    uint64_t seed, offset;
+    float scale;
+    int bias_dtype;
+};
+struct V3Maps {            // one tensor-map set per member of the group
+    CUtensorMap x[V3_MAX_GROUP], w[V3_MAX_GROUP], w2[V3_MAX_GROUP], dn[V3_MAX_GROUP], up[V3_MAX_GROUP], y[V3_MAX_GROUP];
+};
 struct GemmParams3 {
-    GemmParams g;          // g.tile_n: width of the pair tile; g.n_tiles; g.stages
+    GemmParams g;          // g.tile_n: width of the pair tile; g.n_tiles (per member); g.stages; shapes common to the group
+    int groups;            // members in this launch (1..3)
+    V3Member mem[V3_MAX_GROUP];
     int chunks;            // MMAs per 16-wide k-step over the fused [w; down] rows (NB = tile_n + Rp, NB / chunks <= 256)
     int up_chunks;         // MMAs per k-step of the rank-R GEMM (tile_n / up_chunks <= 256)
     int acc_stages;        // 2 when NB <= 256, else 1
@@ -438,10 +456,7 @@ __host__ __device__ inline SmemLayout3 make_layout3(int tile_n, int Rp, int stag
 }
 
 __global__ void __launch_bounds__(V3_THREADS, 1)
-lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                      const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_dn,
-                      const __grid_constant__ CUtensorMap tm_up, const __grid_constant__ CUtensorMap tm_y,
-                      const GemmParams3 q) {
+lora_linear_kernel_v3(const __grid_constant__ V3Maps maps, const GemmParams3 q) {
     const GemmParams& p = q.g;
     otb_pdl_trigger();                           // the next kernel in the stream may begin its own prologue
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -454,7 +469,8 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const uint32_t crank = cluster_ctarank();          // 0 = leader
     const bool leader = crank == 0;
     const uint32_t cid = cluster_id_x(), ncl = cluster_nctaid_x();
-    const int total_tiles = q.pair_m_tiles * p.n_tiles;
+    const int tiles_per_row = q.groups * p.n_tiles;       // tiles of one 256-row block: members side by side, so a shared x stays hot in L2
+    const int total_tiles = q.pair_m_tiles * tiles_per_row;
     const int NB = p.tile_n + p.Rp;                    // fused B rows: [w tile ; down]
     const int nbc = NB / q.chunks, nbh = nbc / 2;      // MMA N per chunk; rows of it held by each CTA
     const int wc = p.tile_n / q.up_chunks, wch = wc / 2;   // same for the rank-R GEMM's `up` operand
@@ -468,8 +484,10 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bar_off + 8u * (2 * MAX_STAGES + 12));
 
     if (threadIdx.x == 0) {
-        prefetch_tmap(&tm_x); prefetch_tmap(&tm_w); prefetch_tmap(&tm_y);
-        if (lora) { prefetch_tmap(&tm_w2); prefetch_tmap(&tm_dn); prefetch_tmap(&tm_up); }
+        for (int g = 0; g < q.groups; ++g) {
+            prefetch_tmap(&maps.x[g]); prefetch_tmap(&maps.w[g]); prefetch_tmap(&maps.y[g]);
+            if (lora) { prefetch_tmap(&maps.w2[g]); prefetch_tmap(&maps.dn[g]); prefetch_tmap(&maps.up[g]); }
+        }
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(misc(0 + i), 1); mbar_init(misc(2 + i), 1); mbar_init(misc(4 + i), 1);
@@ -495,8 +513,10 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         int it = 0;
         const uint32_t stage_tx = 2u * L.stage_bytes, up_tx = 2u * L.up_bytes;
         for (uint32_t st = cid; st < (uint32_t)total_tiles; st += ncl, ++it) {
-            const int mt = st / p.n_tiles, nt = st % p.n_tiles;
+            const int mt = st / tiles_per_row, gm = (st % tiles_per_row) / p.n_tiles, nt = st % p.n_tiles;
             const int m0 = mt * 2 * BM + (int)crank * BM, n0 = nt * p.tile_n;
+            const CUtensorMap* tm_x = &maps.x[gm]; const CUtensorMap* tm_w = &maps.w[gm]; const CUtensorMap* tm_w2 = &maps.w2[gm];
+            const CUtensorMap* tm_dn = &maps.dn[gm]; const CUtensorMap* tm_up = &maps.up[gm];
             if (lora) {
                 const int ub = it % up_bufs;
                 mbar_wait(misc(2 + ub), (uint32_t)((it / up_bufs) & 1) ^ 1);                 // up_empty (own)
@@ -504,7 +524,7 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     if (leader) mbar_expect_tx(misc(0 + ub), up_tx);
                     const uint32_t bar = mapa_u32(misc(0 + ub), 0);
                     for (int c = 0; c < q.up_chunks; ++c)
-                        tma_load_2d_2sm(smem_base + L.up_off + ub * L.up_bytes + (uint32_t)(c * wch) * 128, &tm_up, bar, 0,
+                        tma_load_2d_2sm(smem_base + L.up_off + ub * L.up_bytes + (uint32_t)(c * wch) * 128, tm_up, bar, 0,
                                         n0 + c * wc + (int)crank * wch);
                 }
                 __syncwarp();
@@ -518,17 +538,17 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     } else {
                         if (leader) mbar_expect_tx(full_bar(s), stage_tx);
                         const uint32_t bar = mapa_u32(full_bar(s), 0);
-                        tma_load_2d_2sm(stg + L.x_off, &tm_x, bar, kb * BK, m0);
+                        tma_load_2d_2sm(stg + L.x_off, tm_x, bar, kb * BK, m0);
                         // my half of every chunk of the fused [w; down] rows; only the very last half (peer CTA, last
                         // chunk) reaches into `down`, and it holds all Rp rows of it
                         for (int c = 0; c < q.chunks; ++c) {
                             const uint32_t dst = stg + L.b_off + (uint32_t)(c * nbh) * 128;
                             const int row = c * nbc + (int)crank * nbh;      // first fused row of this half
                             if (lora && c == q.chunks - 1 && !leader) {
-                                if (nbh > p.Rp) tma_load_2d_2sm(dst, &tm_w2, bar, kb * BK, n0 + row);
-                                tma_load_2d_2sm(dst + (uint32_t)(nbh - p.Rp) * 128, &tm_dn, bar, kb * BK, 0);
+                                if (nbh > p.Rp) tma_load_2d_2sm(dst, tm_w2, bar, kb * BK, n0 + row);
+                                tma_load_2d_2sm(dst + (uint32_t)(nbh - p.Rp) * 128, tm_dn, bar, kb * BK, 0);
                             } else {
-                                tma_load_2d_2sm(dst, &tm_w, bar, kb * BK, n0 + row);
+                                tma_load_2d_2sm(dst, tm_w, bar, kb * BK, n0 + row);
                             }
                         }
                     }
@@ -615,14 +635,15 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         // at the M / N edges by the tensor map); two boxes per warp so a store drains while the next box is packed
         const uint32_t ybox = smem_base + L.y_off + (uint32_t)(warp - 2) * YSTAGE_WARP_BYTES;
         uint8_t* ybox_gen = smem_gen + L.y_off + (uint32_t)(warp - 2) * YSTAGE_WARP_BYTES;
-        const bool bias_vec = p.bias != nullptr && (p.bias_dtype == OTB_BF16 || p.bias_dtype == OTB_F32) && (((uintptr_t)p.bias) & 15) == 0;
         int it = 0;
         for (uint32_t st = cid; st < (uint32_t)total_tiles; st += ncl, ++it) {
             const int as = it % q.acc_stages;
             const uint32_t par = (uint32_t)((it / q.acc_stages) & 1);
-            const int mt = st / p.n_tiles, n_tile = st % p.n_tiles;
+            const int mt = st / tiles_per_row, gm = (st % tiles_per_row) / p.n_tiles, n_tile = st % p.n_tiles;
             const int m0 = mt * 2 * BM + (int)crank * BM, n0 = n_tile * p.tile_n;
             const int m = m0 + row;
+            const V3Member& me = q.mem[gm];
+            const bool bias_vec = me.bias != nullptr && (me.bias_dtype == OTB_BF16 || me.bias_dtype == OTB_F32) && (((uintptr_t)me.bias) & 15) == 0;
             const uint32_t t_lane = tmem_base + as * acc_stride + ((uint32_t)(quad * 32) << 16);
             if (lora) {
                 mbar_wait(misc(4 + as), par);                               // t_full
@@ -633,12 +654,12 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     tmem_ld_wait();
                     float f[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.scale;
+                    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * me.scale;
                     if (p.dropout_p > 0.0f) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
                             const uint64_t e = (uint64_t)m * (uint64_t)p.Rp + (uint64_t)(c + j);
-                            Philox4 r = otb_rng(p.seed, p.offset, OTB_STREAM_DROPOUT, e >> 2);
+                            Philox4 r = otb_rng(me.seed, me.offset, OTB_STREAM_DROPOUT, e >> 2);
                             f[j + 0] = otb_u01(r.x) >= p.dropout_p ? f[j + 0] * keep_scale : 0.0f;
                             f[j + 1] = otb_u01(r.y) >= p.dropout_p ? f[j + 1] * keep_scale : 0.0f;
                             f[j + 2] = otb_u01(r.z) >= p.dropout_p ? f[j + 2] * keep_scale : 0.0f;
@@ -650,8 +671,8 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     const int j0 = c >> 3;
                     *reinterpret_cast<uint4*>(t_row + (((j0 + 0) ^ (row & 7)) << 4)) = lo;
                     *reinterpret_cast<uint4*>(t_row + (((j0 + 1) ^ (row & 7)) << 4)) = hi;
-                    if (p.t_out != nullptr && n_tile == 0 && m < p.M) {
-                        uint16_t* dst = p.t_out + (size_t)m * p.R + c;
+                    if (me.t_out != nullptr && n_tile == 0 && m < p.M) {
+                        uint16_t* dst = me.t_out + (size_t)m * p.R + c;
                         if (c + 8 <= p.R) *reinterpret_cast<uint4*>(dst) = lo;
                         if (c + 16 <= p.R) *reinterpret_cast<uint4*>(dst + 8) = hi;
                     }
@@ -667,15 +688,15 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 const int nb0 = n0 + c0;
                 if (nb0 >= p.N || (q.debug & 4)) break;
                 const int cols = p.tile_n - c0 < 64 ? p.tile_n - c0 : 64;
-                if (cols == 64 && nb0 + 64 <= p.N && (p.bias == nullptr || bias_vec)) {
+                if (cols == 64 && nb0 + 64 <= p.N && (me.bias == nullptr || bias_vec)) {
                     // ---- full 64-column block: one swizzled box, one TMA store ----
                     uint32_t v[64];
                     tmem_ld32<0>(t_lane + (uint32_t)(c0 + 0), v);
                     tmem_ld32<32>(t_lane + (uint32_t)(c0 + 32), v);
                     tmem_ld_wait();
-                    if (p.bias != nullptr) {                                // same address in every lane: L1 broadcast
-                        if (p.bias_dtype == OTB_BF16) {
-                            const uint4* bp = reinterpret_cast<const uint4*>((const uint16_t*)p.bias + nb0);
+                    if (me.bias != nullptr) {                               // same address in every lane: L1 broadcast
+                        if (me.bias_dtype == OTB_BF16) {
+                            const uint4* bp = reinterpret_cast<const uint4*>((const uint16_t*)me.bias + nb0);
 #pragma unroll
                             for (int g = 0; g < 8; ++g) {
                                 const uint4 b = __ldg(bp + g);
@@ -687,7 +708,7 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                                 }
                             }
                         } else {
-                            const float4* bp = reinterpret_cast<const float4*>((const float*)p.bias + nb0);
+                            const float4* bp = reinterpret_cast<const float4*>((const float*)me.bias + nb0);
 #pragma unroll
                             for (int g = 0; g < 16; ++g) {
                                 const float4 b = __ldg(bp + g);
@@ -711,7 +732,7 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&tm_y, ybox, nb0, m0 + quad * 32);
+                        tma_store_2d(&maps.y[gm], ybox, nb0, m0 + quad * 32);
                         bulk_commit();
                     }
                 } else {
@@ -725,13 +746,13 @@ lora_linear_kernel_v3(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                         float f[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-                        if (p.bias != nullptr) {
+                        if (me.bias != nullptr) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
-                                if (n + j < p.N) f[j] += load_as_float(p.bias, n + j, p.bias_dtype);
+                                if (n + j < p.N) f[j] += load_as_float(me.bias, n + j, me.bias_dtype);
                         }
                         if (m < p.M) {
-                            uint16_t* dst = p.y + (size_t)m * p.N + n;
+                            uint16_t* dst = me.y + (size_t)m * p.N + n;
                             if (n + 8 <= p.N)
                                 *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
                             if (n + 16 <= p.N)
@@ -921,7 +942,7 @@ bool v3_shape_ok(int tn, int Rp, int* chunks, int* up_chunks, int* acc_stages) {
     return true;
 }
 
-KaPlan plan_v3(int M, int N, int K, int Rp, int pairs) {
+KaPlan plan_v3(int M, int N, int K, int Rp, int pairs, int groups = 1) {
     const int m_tiles = (M + 2 * BM - 1) / (2 * BM), num_kb = (K + BK - 1) / BK;
     KaPlan best{3, 64, 1, 2, 1e30};
     for (int tn = 32; tn + Rp <= 512; tn += 16) {
@@ -931,7 +952,7 @@ KaPlan plan_v3(int M, int N, int K, int Rp, int pairs) {
         while (stages > 0 && (int)make_layout3(tn, Rp, stages, acc_stages).total + 1024 > SMEM_LIMIT) --stages;
         if (stages < 3) continue;
         const int n_tiles = (N + tn - 1) / tn;
-        const int rounds = (int)(((int64_t)m_tiles * n_tiles + pairs - 1) / pairs);
+        const int rounds = (int)(((int64_t)m_tiles * n_tiles * groups + pairs - 1) / pairs);
         const int NB = tn + Rp, nbc = NB / chunks;
         // per CTA per 16-wide k-step: nbc/2 tensor-pipe cycles per chunk, with a measured floor of ~80 per instruction
         const double mma = 4.0 * chunks * (nbc / 2.0 > 80.0 ? nbc / 2.0 : 80.0);
@@ -941,12 +962,14 @@ KaPlan plan_v3(int M, int N, int K, int Rp, int pairs) {
     return best;
 }
 
-int launch_v3(const otb_lora_linear_args* a, void* stream, int tile_n, int max_pairs) {
+// `count` same-shape problems (count == 1: the plain call) as one v3 launch
+int launch_v3(const otb_lora_linear_args* a, int count, void* stream, int tile_n, int max_pairs) {
     GemmParams3 q;
     GemmParams& p = q.g;
     p.M = a->M; p.N = a->N; p.K = a->K; p.R = a->R;
     p.Rp = (a->R + 15) / 16 * 16;
     p.tile_n = tile_n;
+    q.groups = count;
     OTB_CHECK_ARG(v3_shape_ok(tile_n, p.Rp, &q.chunks, &q.up_chunks, &q.acc_stages),
                   "pair tile_n %d invalid for rank %d (tile_n + rank a multiple of 16 (32 above 256), <= 512)", tile_n, p.Rp);
     q.debug = env_int("OTB_KA_DEBUG", 0);
@@ -965,18 +988,26 @@ int launch_v3(const otb_lora_linear_args* a, void* stream, int tile_n, int max_p
     p.y = (uint16_t*)a->y; p.t_out = (uint16_t*)a->t_out;
 
     const int nbh = (p.tile_n + p.Rp) / q.chunks / 2, wch = p.tile_n / q.up_chunks / 2;
-    CUtensorMap tm_x, tm_w, tm_w2, tm_dn, tm_up, tm_y;
+    V3Maps maps;
     int rc;
-    if ((rc = make_tmap(&tm_x, a->x, a->M, a->K, BM, "x")) != OTB_OK) return rc;
-    if ((rc = make_tmap(&tm_w, a->w, a->N, a->K, nbh, "w")) != OTB_OK) return rc;
-    if ((rc = make_tmap(&tm_y, a->y, a->M, a->N, 32, "y")) != OTB_OK) return rc;
-    tm_w2 = tm_w; tm_dn = tm_x; tm_up = tm_x;
-    if (p.Rp > 0) {
-        if (nbh > p.Rp && (rc = make_tmap(&tm_w2, a->w, a->N, a->K, nbh - p.Rp, "w (last half)")) != OTB_OK) return rc;
-        if ((rc = make_tmap(&tm_dn, a->down, a->R, a->K, p.Rp, "down")) != OTB_OK) return rc;
-        if ((rc = make_tmap(&tm_up, a->up, a->N, a->R, wch, "up")) != OTB_OK) return rc;
+    for (int g = 0; g < V3_MAX_GROUP; ++g) {
+        const otb_lora_linear_args* m = &a[g < count ? g : 0];         // unused slots mirror member 0
+        q.mem[g] = V3Member{m->bias, (uint16_t*)m->y, (uint16_t*)m->t_out, m->seed, m->offset, m->scale, m->bias_dtype};
+        if (g >= count) {
+            maps.x[g] = maps.x[0]; maps.w[g] = maps.w[0]; maps.w2[g] = maps.w2[0]; maps.dn[g] = maps.dn[0]; maps.up[g] = maps.up[0]; maps.y[g] = maps.y[0];
+            continue;
+        }
+        if ((rc = make_tmap(&maps.x[g], m->x, m->M, m->K, BM, "x")) != OTB_OK) return rc;
+        if ((rc = make_tmap(&maps.w[g], m->w, m->N, m->K, nbh, "w")) != OTB_OK) return rc;
+        if ((rc = make_tmap(&maps.y[g], m->y, m->M, m->N, 32, "y")) != OTB_OK) return rc;
+        maps.w2[g] = maps.w[g]; maps.dn[g] = maps.x[g]; maps.up[g] = maps.x[g];
+        if (p.Rp > 0) {
+            if (nbh > p.Rp && (rc = make_tmap(&maps.w2[g], m->w, m->N, m->K, nbh - p.Rp, "w (last half)")) != OTB_OK) return rc;
+            if ((rc = make_tmap(&maps.dn[g], m->down, m->R, m->K, p.Rp, "down")) != OTB_OK) return rc;
+            if ((rc = make_tmap(&maps.up[g], m->up, m->N, m->R, wch, "up")) != OTB_OK) return rc;
+        }
     }
-    const int total_tiles = q.pair_m_tiles * p.n_tiles;
+    const int total_tiles = q.pair_m_tiles * p.n_tiles * count;
     int clusters = max_pairs < total_tiles ? max_pairs : total_tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * 2));
@@ -989,10 +1020,10 @@ int launch_v3(const otb_lora_linear_args* a, void* stream, int tile_n, int max_p
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = otb_pdl_enabled() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, lora_linear_kernel_v3, tm_x, tm_w, tm_w2, tm_dn, tm_up, tm_y, q);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lora_linear_kernel_v3, maps, q);
     if (e != cudaSuccess) {
-        otb_set_error("launch of lora_linear_kernel_v3 (pair tile 256x%d, %d chunks, %d stages) failed: %s", p.tile_n, q.chunks, stages,
-                      cudaGetErrorString(e));
+        otb_set_error("launch of lora_linear_kernel_v3 (%d x pair tile 256x%d, %d chunks, %d stages) failed: %s", count, p.tile_n, q.chunks,
+                      stages, cudaGetErrorString(e));
         return OTB_ECUDA;
     }
     return OTB_OK;
@@ -1020,7 +1051,7 @@ int v3_max_pairs(int sms) {
     return n;
 }
 
-extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
+static int check_lora_linear_args(const otb_lora_linear_args* a) {
     OTB_CHECK_ARG(a != nullptr, "null args");
     OTB_CHECK_ARG(a->x && a->w && a->y, "null x / w / y");
     OTB_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
@@ -1031,6 +1062,12 @@ extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
     OTB_CHECK_ARG(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "dropout_p must be in [0,1)");
     OTB_CHECK_ARG((((uintptr_t)a->x | (uintptr_t)a->w | (uintptr_t)a->y | (uintptr_t)a->down | (uintptr_t)a->up |
                     (uintptr_t)a->t_out) & 15) == 0, "all tensor pointers must be 16-byte aligned");
+    return OTB_OK;
+}
+
+extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
+    int rc = check_lora_linear_args(a);
+    if (rc != OTB_OK) return rc;
     OTB_BIND(a->x);
     {
         // variant choice: the cost model picks between single-CTA tiles (v2) and CTA-pair tiles (v3);
@@ -1046,8 +1083,25 @@ extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
         if (force == 3 || a->tile_n > 256) use3 = true;
         else if (force == 2 || a->M <= BM || (a->tile_n > 0 && !explicit3)) use3 = false;
         else use3 = p3.cycles < plan_v2(a->M, a->N, a->K, Rp, sms).cycles;
-        if (use3) return launch_v3(a, stream, a->tile_n > 0 ? a->tile_n : p3.tile_n, pairs);
+        if (use3) return launch_v3(a, 1, stream, a->tile_n > 0 ? a->tile_n : p3.tile_n, pairs);
         return launch_v2(a, stream);
     }
 
+}
+
+extern "C" int otb_lora_linear_grouped(const otb_lora_linear_args* members, int32_t count, void* stream) {
+    OTB_CHECK_ARG(members != nullptr && count >= 1 && count <= V3_MAX_GROUP, "group of %d (1..%d members)", count, V3_MAX_GROUP);
+    for (int g = 0; g < count; ++g) {
+        int rc = check_lora_linear_args(&members[g]);
+        if (rc != OTB_OK) return rc;
+        const otb_lora_linear_args& a = members[g], &b = members[0];
+        OTB_CHECK_ARG(a.M == b.M && a.N == b.N && a.K == b.K && a.R == b.R && a.dropout_p == b.dropout_p,
+                      "members of a group must share M, N, K, rank and dropout_p");
+    }
+    if (count == 1) return otb_lora_linear(members, stream);
+    OTB_BIND(members[0].x);
+    const int Rp = (members[0].R + 15) / 16 * 16;
+    const int pairs = v3_max_pairs(otb_sm_count());
+    const KaPlan plan = plan_v3(members[0].M, members[0].N, members[0].K, Rp, pairs, count);
+    return launch_v3(members, count, stream, members[0].tile_n > 0 ? members[0].tile_n : plan.tile_n, pairs);
 }

@@ -96,21 +96,156 @@ class _LoraLinearFn(torch.autograd.Function):
         need_a, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dA, dB, ret_a, ret_b = mod._grad_buffers(need_a, need_b)
         if dA is not None or dB is not None:
-            # autograd only ADOPTS the returned arena slices (or gets None when the kernel accumulates in place), so
-            # nothing on this stream reads dA/dB before the side stream is joined; a foreign p.grad (someone replaced
-            # it) makes autograd add the returned tensor on this stream, so that case stays in order
-            foreign = (ret_a is not None and ret_a.data_ptr() != dA.data_ptr()) or (ret_b is not None and ret_b.data_ptr() != dB.data_ptr()) \
-                or (ret_a is not None and mod.lora_down.weight.grad is not None) or (ret_b is not None and mod.lora_up.weight.grad is not None) \
-                or mod._wrapper_slot is None
-            if ops.side_grads.enabled and not foreign:
-                ops.side_grads.launch(lambda: ops.lora_grad_ab(x2, dy, gs, ts, dA, dB), dy.device, (x2, dy, gs, ts, dA, dB))
-            else:
-                ops.lora_grad_ab(x2, dy, gs, ts, dA, dB)
+            _launch_grad_ab(mod, x2, dy, gs, ts, dA, dB, ret_a, ret_b)
         if ret_a is not None and ret_a.dtype != mod.lora_down.weight.dtype:
             ret_a = ret_a.to(mod.lora_down.weight.dtype)
         if ret_b is not None and ret_b.dtype != mod.lora_up.weight.dtype:
             ret_b = ret_b.to(mod.lora_up.weight.dtype)
         return (dx if ctx.needs_input_grad[0] else None), ret_a, ret_b, None
+
+
+class _LoraGroupFn(torch.autograd.Function):
+    """The same contract as _LoraLinearFn for up to three sibling leaves that share their input (the q/k/v projections
+    of a self-attention, the k/v of a cross-attention): ONE grouped launch forward, ONE for the dX GEMMs."""
+
+    @staticmethod
+    def forward(ctx, mods: tuple, x2: Tensor, *ab: Tensor):
+        ctx.set_materialize_grads(False)             # an output nobody consumed arrives as None in backward
+        ops_ = [m._operands() for m in mods]
+        p = mods[0].dropout.p if mods[0].training else 0.0
+        keys = [(0, 0)] * len(mods)
+        if p > 0.0:
+            gen = torch.cuda.default_generators[x2.device.index]
+            keys = []
+            for _ in mods:
+                seed, offset = gen.initial_seed(), gen.get_offset()
+                gen.set_offset(offset + 4)
+                keys.append((seed, offset))
+        ys, ts = ops.lora_linear_grouped([x2] * len(mods), [o["w"] for o in ops_], [o["a"] for o in ops_], [o["b"] for o in ops_],
+                                         [o["bias"] for o in ops_], [m._scale() for m in mods], dropout_p=p, keys=keys,
+                                         want_t=any(ctx.needs_input_grad[1:]))
+        ctx.mods, ctx.p, ctx.keys = mods, p, keys
+        ctx.save_for_backward(x2, *[t for t in ts if t is not None])
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        mods = ctx.mods
+        x2, *ts = ctx.saved_tensors
+        live = [i for i, dy in enumerate(dys) if dy is not None]
+        grads = [None] * (2 * len(mods))
+        dx = None
+        if live:
+            dyc = []
+            for i in live:
+                dy = dys[i].contiguous()
+                dyc.append(dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16))
+            ops_ = [mods[i]._operands() for i in live]
+            dxs, gss = ops.lora_linear_grouped(dyc, [o["wt"] for o in ops_], [o["bt"] for o in ops_], [o["at"] for o in ops_],
+                                               [None] * len(live), [mods[i]._scale() for i in live], dropout_p=ctx.p,
+                                               keys=[ctx.keys[i] for i in live], want_t=True)
+            for j, i in enumerate(live):
+                mod = mods[i]
+                need_a, need_b = ctx.needs_input_grad[2 + 2 * i], ctx.needs_input_grad[3 + 2 * i]
+                dA, dB, ret_a, ret_b = mod._grad_buffers(need_a, need_b)
+                if dA is not None or dB is not None:
+                    _launch_grad_ab(mod, x2, dyc[j], gss[j], ts[i], dA, dB, ret_a, ret_b)
+                if ret_a is not None and ret_a.dtype != mod.lora_down.weight.dtype:
+                    ret_a = ret_a.to(mod.lora_down.weight.dtype)
+                if ret_b is not None and ret_b.dtype != mod.lora_up.weight.dtype:
+                    ret_b = ret_b.to(mod.lora_up.weight.dtype)
+                grads[2 * i], grads[2 * i + 1] = ret_a, ret_b
+            if ctx.needs_input_grad[1]:
+                dx = dxs[0]
+                for d in dxs[1:]:
+                    dx = dx + d
+        return (None, dx, *grads)
+
+
+def _launch_grad_ab(mod, x2, dy, gs, ts, dA, dB, ret_a, ret_b) -> None:
+    """dA / dB of one leaf on the side stream (see ops.SideGrads) unless autograd will READ the returned tensor on
+    this stream: it only ADOPTS the arena slices (or gets None when the kernel accumulates in place); a foreign
+    p.grad (someone replaced it) makes autograd add the returned tensor here, so that case stays in order."""
+    foreign = (ret_a is not None and ret_a.data_ptr() != dA.data_ptr()) or (ret_b is not None and ret_b.data_ptr() != dB.data_ptr()) \
+        or (ret_a is not None and mod.lora_down.weight.grad is not None) or (ret_b is not None and mod.lora_up.weight.grad is not None) \
+        or mod._wrapper_slot is None
+    if ops.side_grads.enabled and not foreign:
+        ops.side_grads.launch(lambda: ops.lora_grad_ab(x2, dy, gs, ts, dA, dB), dy.device, (x2, dy, gs, ts, dA, dB))
+    else:
+        ops.lora_grad_ab(x2, dy, gs, ts, dA, dB)
+
+
+class SiblingGroup:
+    """Leaves that the wrapped network calls back to back on the SAME input: {to_q, to_k, to_v} of a self-attention,
+    {to_k, to_v} of a cross-attention, {add_q_proj, add_k_proj, add_v_proj} of a joint attention.
+
+    The plugin seam is one forward per leaf, so the batching is speculative: the first member called with input x
+    computes every member on x in one grouped launch and parks the siblings' outputs; a sibling called next with the
+    same tensor (same storage, same version, same shape) takes its parked output.  A sibling called with anything else
+    proves the guess wrong: the group switches itself off for good and its members go back to single launches."""
+
+    def __init__(self, members: list["LoRAModule"]):
+        self.members = members
+        self.enabled = True
+        self._key = None
+        self._parked: dict[int, Tensor] = {}
+        self._drew_keys = False
+        for i, m in enumerate(members):
+            m._group = (self, i)
+
+    @staticmethod
+    def _key_of(x2: Tensor):
+        return (x2.data_ptr(), x2._version, tuple(x2.shape), x2.dtype)
+
+    def forward(self, idx: int, x_rows: Tensor) -> Tensor | None:
+        """The member's output from a grouped launch, or None when the caller should launch singly.  `x_rows` is the
+        member's input as the network passed it (flattened to rows, BEFORE the bf16 cast, so siblings fed the same fp32
+        tensor are recognised and the cast happens once)."""
+        key = self._key_of(x_rows)
+        if idx in self._parked:
+            if key == self._key:
+                y = self._parked.pop(idx)
+                if not self._parked:
+                    self._key = None
+                return y
+            # same member, different input: not siblings after all.  Give back the dropout keys drawn for the members
+            # that never consumed their output, so the single launches that follow draw what they would have drawn.
+            if len(self.members) == 3 and idx == 1:
+                # q read one tensor, k another: a cross-attention whose context happens to have the query's width.
+                # k and v still share their input: carry on as a pair.
+                self.members[0]._group = None
+                self.members = self.members[1:]
+                for i, m in enumerate(self.members):
+                    m._group = (self, i)
+            else:
+                self.enabled = False
+            if self._drew_keys:
+                gen = torch.cuda.default_generators[x_rows.device.index]
+                gen.set_offset(gen.get_offset() - 4 * len(self._parked))
+            self._parked.clear()
+            self._key = None
+            return None
+        if idx != 0:
+            # only the first member starts a grouped launch (the network calls it first); a sibling that finds nothing
+            # parked — its leader ran singly, or was not called in this pass — launches singly.  This also keeps a stale
+            # parked output (a pass that ended early) from ever being served: the leader's next call replaces it.
+            return None
+        mods = tuple(self.members)
+        x2 = x_rows if x_rows.dtype == torch.bfloat16 else x_rows.to(torch.bfloat16)
+        x2 = x2.contiguous()
+        ab = []
+        for m in mods:
+            ab += [m.lora_down.weight, m.lora_up.weight]
+        self._drew_keys = mods[0].training and mods[0].dropout.p > 0.0
+        ys = _LoraGroupFn.apply(mods, x2, *ab)
+        self._key = key
+        self._parked = {i: y for i, y in enumerate(ys) if i != idx}
+        for m in mods:
+            m._last_rows = x2.shape[0]
+        return ys[idx]
+
+
+SIBLING_SETS = (("to_q", "to_k", "to_v"), ("add_q_proj", "add_k_proj", "add_v_proj"))
 
 
 # ---------------------------------------------------------------------------------------
@@ -373,11 +508,15 @@ class LoRAModule(PeftBase):
             x2 = x.permute(0, 2, 3, 1).reshape(-1, c_)
         else:
             x2 = x.reshape(-1, x.shape[-1])
-        if x2.dtype != torch.bfloat16:
-            x2 = x2.to(torch.bfloat16)
-        x2 = x2.contiguous()
         self._last_rows = x2.shape[0]          # read by bench.py to replay the step's GEMM shapes
-        y2 = _LoraLinearFn.apply(x2, A, B, self)
+        y2 = None
+        grp = getattr(self, "_group", None)
+        if grp is not None and grp[0].enabled and not isinstance(om, nn.Conv2d):
+            y2 = grp[0].forward(grp[1], x2)
+        if y2 is None:
+            if x2.dtype != torch.bfloat16:
+                x2 = x2.to(torch.bfloat16)
+            y2 = _LoraLinearFn.apply(x2.contiguous(), A, B, self)
         if isinstance(om, nn.Conv2d):
             return y2.view(b_, h_, w_, -1).permute(0, 3, 1, 2)
         return y2.view(*x.shape[:-1], y2.shape[-1])
@@ -438,6 +577,37 @@ class LoRAModuleWrapper:
     def _bind(self) -> None:
         for i, m in enumerate(self._trainable()):
             m._wrapper_slot = (self, i)
+        self._build_sibling_groups()
+
+    def _build_sibling_groups(self) -> None:
+        """Group the q/k/v-style projections that share a parent module and a shape (SiblingGroup).  With equal in_features
+        all three are taken to read the same tensor (self- / joint attention); otherwise only k and v (cross-attention)."""
+        import os
+        self.sibling_groups: list[SiblingGroup] = []
+        for m in self._trainable():
+            m._group = None
+        if os.environ.get("OTB_GROUP_SIBLINGS", "1") == "0":
+            return
+        by_parent: dict[str, dict[str, LoRAModule]] = {}
+        for name, m in self.lora_modules.items():
+            if isinstance(m, LoRAModule) and not isinstance(m, self.dummy_klass) and isinstance(m.orig_module, nn.Linear) and "." in name:
+                parent, leaf = name.rsplit(".", 1)
+                by_parent.setdefault(parent, {})[leaf] = m
+
+        def same(ms):
+            a = ms[0]
+            return all(b.orig_module.in_features == a.orig_module.in_features and b.orig_module.out_features == a.orig_module.out_features
+                       and b.rank == a.rank and float(b.alpha) == float(a.alpha) and b.lora_down.weight.dtype == a.lora_down.weight.dtype
+                       for b in ms[1:])
+        for leaves in by_parent.values():
+            for names in SIBLING_SETS:
+                ms = [leaves[n] for n in names if n in leaves]
+                if len(ms) == 3 and same(ms):
+                    self.sibling_groups.append(SiblingGroup(ms))
+                elif len(ms) == 3 and same(ms[1:]):
+                    self.sibling_groups.append(SiblingGroup(ms[1:]))
+                elif len(ms) == 2 and names[0] not in leaves and same(ms):
+                    self.sibling_groups.append(SiblingGroup(ms))
 
     def refresh_shadows(self) -> None:
         """Re-emit the bf16 (and transposed) shadows of every A/B in ONE launch.  Called after each

@@ -157,6 +157,42 @@ def lora_linear(x: torch.Tensor, w: torch.Tensor, down: torch.Tensor | None, up:
     return y, t
 
 
+def lora_linear_grouped(xs: list[torch.Tensor], ws: list[torch.Tensor], downs: list[torch.Tensor], ups: list[torch.Tensor],
+                        biases: list[torch.Tensor | None], scales: list[float], *, dropout_p: float = 0.0,
+                        keys: list[tuple[int, int]] | None = None, want_t: bool = True, tile_n: int = 0):
+    """`len(xs)` (1..3) same-shape lora_linear problems as ONE launch (otb_lora_linear_grouped): the q/k/v projections of
+    a self-attention (pass the same x three times), the k/v projections of a cross-attention, or their dX GEMMs.
+    Returns ([y_i], [t_i]); bit-identical to the single calls."""
+    g = len(xs)
+    if not (1 <= g <= 3 and len(ws) == len(downs) == len(ups) == len(biases) == len(scales) == g):
+        raise ValueError("lora_linear_grouped: 1..3 members, one entry per member in every list")
+    M, K = xs[0].shape
+    Nn, R = ws[0].shape[0], downs[0].shape[0]
+    arr = (N.LoraLinearArgs * g)()
+    ys, ts = [], []
+    for i in range(g):
+        x, w, down, up, bias = xs[i], ws[i], downs[i], ups[i], biases[i]
+        N.require_cuda(x, w, down, up, bias)
+        for name, t in (("x", x), ("w", w), ("down", down), ("up", up)):
+            if t.dtype != torch.bfloat16 or not t.is_contiguous() or t.dim() != 2:
+                raise ValueError(f"lora_linear_grouped: {name}[{i}] must be a contiguous 2-D bf16 tensor")
+        if tuple(x.shape) != (M, K) or tuple(w.shape) != (Nn, K) or tuple(down.shape) != (R, K) or tuple(up.shape) != (Nn, R):
+            raise ValueError("lora_linear_grouped: members must share M, N, K and rank")
+        y = torch.empty((M, Nn), dtype=torch.bfloat16, device=x.device)
+        t = torch.empty((M, R), dtype=torch.bfloat16, device=x.device) if want_t else None
+        seed, offset = keys[i] if keys is not None else (0, 0)
+        arr[i] = N.LoraLinearArgs(
+            x=x.data_ptr(), w=w.data_ptr(), down=down.data_ptr(), up=up.data_ptr(), bias=N.ptr(bias), y=y.data_ptr(), t_out=N.ptr(t),
+            M=M, N=Nn, K=K, R=R, bias_dtype=N.dtype_code(bias.dtype) if bias is not None else N.F32, scale=float(scales[i]),
+            dropout_p=float(dropout_p), seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1), tile_n=int(tile_n), stages=0)
+        ys.append(y)
+        ts.append(t)
+    if M > 0:
+        N.check(N.lib().otb_lora_linear_grouped(arr, g, _stream()), "otb_lora_linear_grouped")
+        _count()
+    return ys, ts
+
+
 def lora_grad_ab(x, dy, gs, ts, dA: torch.Tensor | None, dB: torch.Tensor | None) -> None:
     """dA[R,K] += gs^T x ; dB[N,R] += dy^T ts  (fp32 accumulation into the given buffers)."""
     N.require_cuda(x, dy, gs, ts, dA, dB)

@@ -611,3 +611,27 @@ def test_lora_linear_full_size_linearity(K, dev):
     _, t = K.ops.lora_linear(x1, w, down, up, None, 0.03125)
     lora = t.float() @ up.float().t()
     assert torch.allclose((y1.float() - yb.float()), lora, atol=0.06, rtol=2 ** -6)
+
+
+@pytest.mark.parametrize("M,N,K_,R,g", [(4096, 1280, 1280, 32, 3), (308, 640, 2048, 32, 2), (1000, 328, 136, 16, 3), (513, 1096, 264, 8, 2)])
+def test_lora_linear_grouped_equals_single_launches(K, dev, M, N, K_, R, g):
+    """otb_lora_linear_grouped: up to three same-shape problems in one launch (members' tiles share one persistent grid) —
+    bit-identical to the single launches, with a shared input (forward of sibling projections) and with distinct inputs
+    (their dX GEMMs), with and without bias, with dropout keyed per member."""
+    cases = [_lora_case(dev, M, N, K_, R, seed=10 * i + M) for i in range(g)]
+    xs = [c[0].to(dev) for c in cases]
+    ws, downs, ups = ([c[j].to(dev) for c in cases] for j in (1, 2, 3))
+    biases = [cases[0][4].to(dev), None, cases[2][4].to(dev).float() if g == 3 else None][:g]
+    for shared in (True, False):
+        xin = [xs[0]] * g if shared else xs
+        ys, ts = K.ops.lora_linear_grouped(xin, ws, downs, ups, biases, [0.5, 0.25, 1.0][:g])
+        for i in range(g):
+            y1, t1 = K.ops.lora_linear(xin[i], ws[i], downs[i], ups[i], biases[i], [0.5, 0.25, 1.0][i])
+            assert torch.equal(ys[i], y1) and torch.equal(ts[i], t1), (shared, i)
+    keys = [(7, 4 * i) for i in range(g)]
+    ys, ts = K.ops.lora_linear_grouped(xs, ws, downs, ups, [None] * g, [1.0] * g, dropout_p=0.25, keys=keys)
+    for i in range(g):
+        y1, t1 = K.ops.lora_linear(xs[i], ws[i], downs[i], ups[i], None, 1.0, dropout_p=0.25, seed=7, offset=4 * i)
+        assert torch.equal(ys[i], y1) and torch.equal(ts[i], t1)
+    with pytest.raises(ValueError):
+        K.ops.lora_linear_grouped(xs[:1] + [xs[0][:-8].contiguous()], ws[:2], downs[:2], ups[:2], [None, None], [1.0, 1.0])

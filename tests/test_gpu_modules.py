@@ -644,3 +644,56 @@ def test_graphed_step_matches_eager_for_lora_and_full_finetune(P, dev):
     model.full_grad_arena = None
     with pytest.raises(RuntimeError, match="stable addresses"):
         P.trainer.GraphedTrainStep(setup, model, cfg, P.trainer.synthetic_batch("tiny", B, dev, latent_hw=32), warmup=3)
+
+
+def test_sibling_groups_batch_qkv_and_match_single_launches(P, dev, monkeypatch):
+    """The wrapper batches the q/k/v projections of a self-attention and the k/v of a cross-attention into grouped
+    launches (speculatively: the plugin seam is one forward per leaf).  Predictions and losses equal the ungrouped run
+    bit for bit, LoRA gradients up to the bf16 summation order of the siblings' dX; a group whose members turn out to
+    read different tensors shrinks to the k/v pair or switches itself off, and still computes the right thing."""
+    B = 2
+    from onetrainer_b200 import ops
+
+    def run(group: bool):
+        monkeypatch.setenv("OTB_GROUP_SIBLINGS", "1" if group else "0")
+        cfg = P.TrainConfig(train_device=str(dev), batch_size=B, lora_rank=16, lora_alpha=8.0)
+        model, setup = P.trainer.build_model("tiny", cfg, dev, stochastic_rounding=False, lora_up_std=0.05, lr=1e-3)
+        batch = P.trainer.batch_to_device(P.trainer.synthetic_batch("tiny", B, dev, latent_hw=32), dev)
+        for _ in range(2):          # the first pass lets speculative groups settle (tiny: ctx width == query width)
+            for p in model.parameters:
+                p.grad = None
+            before = ops.LAUNCHES
+            data = setup.predict(model, batch, cfg, model.train_progress)
+            loss = setup.calculate_loss(model, batch, data, cfg)
+            loss.backward()
+            torch.cuda.synchronize()
+        return model, loss.item(), data["predicted"].detach().clone(), ops.LAUNCHES - before
+
+    m_g, l_g, pred_g, n_g = run(True)
+    m_s, l_s, pred_s, n_s = run(False)
+    groups = m_g.unet_lora.sibling_groups
+    assert len(groups) > 0 and all(g.enabled for g in groups) and len(m_s.unet_lora.sibling_groups) == 0
+    assert {len(g.members) for g in groups} == {2, 3}                       # self-attention q/k/v and cross-attention k/v
+    saved = sum(len(g.members) - 1 for g in groups)
+    assert n_s - n_g == 2 * saved                                           # one launch fewer per extra member, forward and dX
+    assert torch.equal(pred_g, pred_s) and l_g == l_s
+    for a, b in zip(m_g.parameters, m_s.parameters):
+        # dX of a group is (dq + dk) + dv rounded to bf16 in that order; autograd sums the single launches in its own
+        # order, so upstream gradients differ by bf16 roundings (~0.4 % each)
+        assert torch.allclose(a.grad, b.grad, rtol=3e-2, atol=1e-2 * b.grad.abs().max().item())
+    # mis-speculation: a q/k/v group whose k reads another tensor shrinks to the k/v pair; a pair whose v reads another
+    # tensor switches itself off; either way the member is computed by a single launch on ITS input
+    grp = next(g for g in groups if len(g.members) == 3)
+    ma, mb, mc = grp.members
+    xa, xb, xc = (torch.randn(64, ma.orig_module.in_features, device=dev).bfloat16() for _ in range(3))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ma.orig_module(xa)                # hooked forward: starts the group on xa
+        yb = mb.orig_module(xb)           # sibling called on another tensor
+    assert grp.enabled and grp.members == [mb, mc] and ma._group is None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        mb.orig_module(xb)                # the pair's leader starts it on xb
+        yc = mc.orig_module(xc)
+    assert not grp.enabled
+    for m, x, y in ((mb, xb, yb), (mc, xc, yc)):
+        ref, _ = ops.lora_linear(x, *(m._operands()[k] for k in ("w", "a", "b", "bias")), m._scale())
+        assert torch.equal(y, ref)
