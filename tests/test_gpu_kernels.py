@@ -635,3 +635,66 @@ def test_lora_linear_grouped_equals_single_launches(K, dev, M, N, K_, R, g):
         assert torch.equal(ys[i], y1) and torch.equal(ts[i], t1)
     with pytest.raises(ValueError):
         K.ops.lora_linear_grouped(xs[:1] + [xs[0][:-8].contiguous()], ws[:2], downs[:2], ups[:2], [None, None], [1.0, 1.0])
+
+
+def test_lora_linear_random_shapes_vs_fp32_torch(K, dev):
+    """Differential sweep: 32 seeded random problems (ragged M / N / K, every legal rank, with and without bias, single
+    and grouped launches, whatever variant / tile width the planner picks) against an fp32 torch restatement with the
+    kernel's two rounding points (T to bf16, output to bf16).  Catches planner / edge-tile mistakes the fixed cases miss."""
+    rng = np.random.default_rng(1234)
+    for case in range(32):
+        M = int(rng.choice([1, 37, 128, 129, 255, 256, 300, 777, 1024, 2049, 4096]))
+        N = int(rng.integers(1, 200)) * 8
+        K_ = int(rng.integers(1, 160)) * 8
+        R = int(rng.choice([8, 16, 24, 32, 64]))
+        g = int(rng.choice([1, 1, 2, 3]))
+        gen = torch.Generator(device=dev).manual_seed(case)
+        xs = [torch.randn(M, K_, device=dev, generator=gen).bfloat16() for _ in range(g)]
+        ws = [(torch.randn(N, K_, device=dev, generator=gen) / math.sqrt(K_)).bfloat16() for _ in range(g)]
+        downs = [(torch.randn(R, K_, device=dev, generator=gen) / math.sqrt(K_)).bfloat16() for _ in range(g)]
+        ups = [(torch.randn(N, R, device=dev, generator=gen) * 0.5).bfloat16() for _ in range(g)]
+        biases = [torch.randn(N, device=dev, generator=gen).bfloat16() if rng.random() < 0.6 else None for _ in range(g)]
+        scale = 0.37
+        if g == 1:
+            y, t = K.ops.lora_linear(xs[0], ws[0], downs[0], ups[0], biases[0], scale)
+            ys, ts = [y], [t]
+        else:
+            ys, ts = K.ops.lora_linear_grouped(xs, ws, downs, ups, biases, [scale] * g)
+        for i in range(g):
+            t_ref = ((xs[i].float() @ downs[i].float().T) * scale)
+            assert torch.allclose(ts[i].float(), t_ref, rtol=2 ** -7, atol=1e-5), (case, M, N, K_, R, g, "t")
+            ref = xs[i].float() @ ws[i].float().T + ts[i].float() @ ups[i].float().T      # the kernel's own bf16 T feeds the up-projection
+            if biases[i] is not None:
+                ref = ref + biases[i].float()
+            err = (ys[i].float() - ref).abs()
+            tol = ref.abs() * 2.0 ** -8 + 2e-3 * ref.abs().max() + 1e-3
+            assert (err <= tol).all(), (case, M, N, K_, R, g, err.max().item())
+
+
+def test_lora_grad_ab_random_shapes_vs_fp32_torch(K, dev, monkeypatch):
+    """Differential sweep of K-a' (tcgen05, MN-major operands read straight from TMA boxes): 24 seeded random problems
+    against fp32 torch, both kernels (tcgen05 default and the mma.sync one behind OTB_KGRAD_TC=0), including dA-only /
+    dB-only calls, rows that end inside a 128-row stage and ranks from 8 to 64; a second call accumulates."""
+    rng = np.random.default_rng(99)
+    for case in range(24):
+        M = int(rng.choice([1, 64, 127, 128, 129, 300, 1000, 2048, 4097]))
+        N = int(rng.integers(1, 180)) * 8
+        K_ = int(rng.integers(1, 180)) * 8
+        R = int(rng.choice([8, 16, 24, 32, 64]))
+        gen = torch.Generator(device=dev).manual_seed(1000 + case)
+        x = torch.randn(M, K_, device=dev, generator=gen).bfloat16()
+        dy = torch.randn(M, N, device=dev, generator=gen).bfloat16()
+        gs = torch.randn(M, R, device=dev, generator=gen).bfloat16()
+        ts = torch.randn(M, R, device=dev, generator=gen).bfloat16()
+        rA, rB = gs.float().T @ x.float(), dy.float().T @ ts.float()
+        which = case % 3                       # 0: both, 1: dA only, 2: dB only
+        for tc in ("1", "0"):
+            monkeypatch.setenv("OTB_KGRAD_TC", tc)
+            dA = torch.zeros(R, K_, device=dev) if which != 2 else None
+            dB = torch.zeros(N, R, device=dev) if which != 1 else None
+            K.ops.lora_grad_ab(x, dy, gs, ts, dA, dB)
+            K.ops.lora_grad_ab(x, dy, gs, ts, dA, dB)
+            if dA is not None:
+                assert torch.allclose(dA, 2 * rA, rtol=1e-4, atol=2e-3 * rA.abs().max().item() + 1e-5), (case, tc, M, N, K_, R)
+            if dB is not None:
+                assert torch.allclose(dB, 2 * rB, rtol=1e-4, atol=2e-3 * rB.abs().max().item() + 1e-5), (case, tc, M, N, K_, R)
