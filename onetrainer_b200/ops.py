@@ -72,6 +72,7 @@ class SideGrads:
     def __init__(self):
         import os
         self.enabled = os.environ.get("OTB_SIDE_GRADS", "1") != "0"
+        self.JOIN_EVERY = int(os.environ.get("OTB_SIDE_JOIN_EVERY", self.JOIN_EVERY))
         self._streams = {}
         self._pending = {}      # device index -> list of tensors kept alive until the join
         self._callback_armed = False
