@@ -75,7 +75,6 @@ class SideGrads:
         self.JOIN_EVERY = int(os.environ.get("OTB_SIDE_JOIN_EVERY", self.JOIN_EVERY))
         self._streams = {}
         self._pending = {}      # device index -> list of tensors kept alive until the join
-        self._callback_armed = False
 
     def stream(self, device: torch.device) -> torch.cuda.Stream:
         idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -94,8 +93,9 @@ class SideGrads:
             fn()
         held = self._pending.setdefault(idx, [])
         held.append(keep_alive)
-        if not self._callback_armed:
-            self._callback_armed = True
+        if len(held) == 1:
+            # first pending launch since the last join: make sure this backward pass ends with one (stateless on purpose —
+            # a backward that raises never runs its callbacks, and must not leave a flag behind that disarms the next one)
             torch.autograd.Variable._execution_engine.queue_callback(self.join_all)
         if len(held) >= self.JOIN_EVERY:
             self.join(device)
@@ -107,7 +107,6 @@ class SideGrads:
             self._pending[idx] = []
 
     def join_all(self) -> None:
-        self._callback_armed = False
         for idx, held in self._pending.items():
             if held:
                 dev = torch.device("cuda", idx)
