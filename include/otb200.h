@@ -230,6 +230,9 @@ typedef struct otb_noise_args {
     int64_t  sample_base;          /* global index of sample 0 of this rank's batch (DP invariance)   */
     const uint64_t* rng_dev;       /* optional device {seed, offset}: overrides the two scalars above so a
                                       captured CUDA graph draws fresh noise on every replay              */
+    int32_t pack_w;                /* 0: noisy_cast_out is [B, C, H, W].  W > 0 (the latent width; H = hw / W): it is
+                                      written in FLUX's packed layout [B, (H/2)(W/2), 4C] — FluxModel.pack_latents,
+                                      modules/model/FluxModel.py:319-331 — so the network input needs no permute copy  */
 } otb_noise_args;
 
 int otb_noise_addnoise(const otb_noise_args* args, void* stream);
@@ -280,6 +283,9 @@ typedef struct otb_loss_args {
     float loss_scale;           /* batch_size_scale * gradient_accumulation_steps_scale    */
     float loss_weight_strength; /* gamma                                                   */
     float upstream;             /* assumed d(total)/d(losses[b]); 1/(B*GA)                 */
+    int32_t pred_pack_w;        /* 0: predicted / dpred are [B, C, H, W].  W > 0: both are in FLUX's packed layout
+                                   [B, (H/2)(W/2), 4C] (the transformer's output, before FluxModel.unpack_latents
+                                   modules/model/FluxModel.py:333-344); target / mask stay [B, C, H, W]           */
 } otb_loss_args;
 
 int otb_loss_fwd_bwd(const otb_loss_args* args, void* stream);

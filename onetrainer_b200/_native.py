@@ -83,7 +83,7 @@ class NoiseArgs(C.Structure):
         ("min_timestep", _i32), ("max_timestep", _i32),
         ("noising_weight", _f32), ("noising_bias", _f32),
         ("shift_c1", _f32), ("shift_c2", _f32),
-        ("seed", _u64), ("offset", _u64), ("sample_base", _i64), ("rng_dev", _vp),
+        ("seed", _u64), ("offset", _u64), ("sample_base", _i64), ("rng_dev", _vp), ("pack_w", _i32),
     ]
 
 
@@ -98,7 +98,7 @@ class LossArgs(C.Structure):
         ("num_train_timesteps", _i32), ("blocks_per_sample", _i32),
         ("mse_strength", _f32), ("mae_strength", _f32),
         ("unmasked_weight", _f32), ("masked_prior_preservation_weight", _f32),
-        ("loss_scale", _f32), ("loss_weight_strength", _f32), ("upstream", _f32),
+        ("loss_scale", _f32), ("loss_weight_strength", _f32), ("upstream", _f32), ("pred_pack_w", _i32),
     ]
 
 

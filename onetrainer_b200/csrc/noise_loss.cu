@@ -92,6 +92,42 @@ __device__ __forceinline__ float rnd_dt(float x, int dtype) {
     return x;
 }
 
+// FLUX packed layout (FluxModel.pack_latents, modules/model/FluxModel.py:319-331): element (c, h, w) of a sample lives
+// at token (h/2)(W/2) + w/2, channel 4c + 2(h&1) + (w&1) of [L, 4C].  A group of 4 consecutive w (w % 4 == 0) is two
+// adjacent channel PAIRS of two adjacent tokens.  Returns the element offset of the first pair inside the sample; the
+// second pair is 4C elements further.
+__device__ __forceinline__ int64_t packed_pair_offset(uint32_t i, int C, int hw, int W) {
+    const uint32_t c = i / (uint32_t)hw, rem = i - c * (uint32_t)hw;
+    const uint32_t h = rem / (uint32_t)W, w = rem - h * (uint32_t)W;
+    const uint32_t token = (h >> 1) * ((uint32_t)W >> 1) + (w >> 1);
+    return (int64_t)token * (4 * C) + (int64_t)(4 * c + 2 * (h & 1));
+}
+__device__ __forceinline__ void load_packed4(const void* p, int64_t off, int C, int dtype, float (&f)[4]) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int64_t o = off + (int64_t)half * 4 * C;
+        if (dtype == OTB_BF16) {
+            const uint32_t r = *reinterpret_cast<const uint32_t*>((const uint16_t*)p + o);
+            f[2 * half] = __uint_as_float(r << 16); f[2 * half + 1] = __uint_as_float(r & 0xFFFF0000u);
+        } else if (dtype == OTB_F32) {
+            const float2 r = *reinterpret_cast<const float2*>((const float*)p + o);
+            f[2 * half] = r.x; f[2 * half + 1] = r.y;
+        } else {
+            const __half2 r = *reinterpret_cast<const __half2*>((const __half*)p + o);
+            f[2 * half] = __low2float(r); f[2 * half + 1] = __high2float(r);
+        }
+    }
+}
+__device__ __forceinline__ void store_packed4(void* p, int64_t off, int C, int dtype, const float (&f)[4]) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int64_t o = off + (int64_t)half * 4 * C;
+        if (dtype == OTB_BF16) *reinterpret_cast<uint32_t*>((uint16_t*)p + o) = pack2_bf16_rn(f[2 * half], f[2 * half + 1]);
+        else if (dtype == OTB_F32) *reinterpret_cast<float2*>((float*)p + o) = make_float2(f[2 * half], f[2 * half + 1]);
+        else *reinterpret_cast<__half2*>((__half*)p + o) = __floats2half2_rn(f[2 * half], f[2 * half + 1]);
+    }
+}
+
 // four N(0,1) draws for global element group `grp` of stream `stream`
 __device__ __forceinline__ void normal4(const otb_noise_args& a, uint32_t stream, uint64_t grp, float (&z)[4]) {
     Philox4 r = otb_rng(a.seed, a.offset, stream, grp);
@@ -194,7 +230,8 @@ __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_ar
                     if (a.noisy_cast_out) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) y[k] = rnd_dt(y[k], ldt);
-                        store4(a.noisy_cast_out, base + i, a.cast_dtype, y);
+                        if (a.pack_w > 0) store_packed4(a.noisy_cast_out, base + packed_pair_offset((uint32_t)i, a.C, a.hw, a.pack_w), a.C, a.cast_dtype, y);
+                        else store4(a.noisy_cast_out, base + i, a.cast_dtype, y);
                     }
                 }
                 if (a.target_out && target != OTB_TARGET_NONE) {
@@ -350,7 +387,8 @@ __global__ void __launch_bounds__(NL_THREADS, (FEAT >= 0 && U <= 2) ? 6 : 1) los
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { p[u][k] = 0.0f; t[u][k] = 0.0f; pt[u][k] = 0.0f; m[u][k] = 1.0f; }
                 if (!live[u]) continue;
-                load4(a.predicted, base + i, pred_dt, p[u]);
+                if (a.pred_pack_w > 0) load_packed4(a.predicted, base + packed_pair_offset((uint32_t)i, a.C, a.hw, a.pred_pack_w), a.C, pred_dt, p[u]);
+                else load4(a.predicted, base + i, pred_dt, p[u]);
                 load4(a.target, base + i, tgt_dt, t[u]);
                 if (prior) load4(a.prior_target, base + i, tgt_dt, pt[u]);
                 if (masked) {
@@ -393,7 +431,10 @@ __global__ void __launch_bounds__(NL_THREADS, (FEAT >= 0 && U <= 2) ? 6 : 1) los
                     acc += term;
                     g[k] = gr * gfac;
                 }
-                if (want_grad) store4(a.dpred, base + i, pred_dt, g);
+                if (want_grad) {
+                    if (a.pred_pack_w > 0) store_packed4(a.dpred, base + packed_pair_offset((uint32_t)i, a.C, a.hw, a.pred_pack_w), a.C, pred_dt, g);
+                    else store4(a.dpred, base + i, pred_dt, g);
+                }
             }
         }
     } else {
@@ -500,6 +541,11 @@ extern "C" int otb_noise_addnoise(const otb_noise_args* a, void* stream) {
         OTB_CHECK_ARG(a->max_timestep >= a->min_timestep && a->min_timestep >= 0 && a->max_timestep <= a->num_train_timesteps,
                       "bad timestep range [%d,%d)", a->min_timestep, a->max_timestep);
     const int64_t chw = (int64_t)a->C * a->hw;
+    if (a->pack_w != 0) {
+        OTB_CHECK_ARG(a->pack_w > 0 && a->hw % a->pack_w == 0 && a->pack_w % 4 == 0 && (a->hw / a->pack_w) % 2 == 0,
+                      "pack_w %d: the latent must be H x W with W %% 4 == 0 and H even (hw = %d)", a->pack_w, a->hw);
+        OTB_CHECK_ARG(a->noisy_cast_out != nullptr, "pack_w applies to noisy_cast_out, which is null");
+    }
     OTB_BIND(a->timestep ? (const void*)a->timestep : (a->latent ? a->latent : a->noise_out));
     const int u = tuning_unroll("OTB_NB1_UNROLL", NB1_UNROLL);
     dim3 grid(blocks_per_sample_for(chw, a->B, u), a->B);
@@ -535,6 +581,9 @@ extern "C" int otb_loss_fwd_bwd(const otb_loss_args* a, void* stream) {
     OTB_CHECK_ARG(a->predicted && a->target && a->losses && a->partials && a->counters, "null tensor");
     OTB_CHECK_ARG(a->blocks_per_sample > 0 && a->blocks_per_sample <= 65535, "bad blocks_per_sample");
     OTB_CHECK_ARG(!(a->masked && !a->mask), "masked loss needs a mask");
+    if (a->pred_pack_w != 0)
+        OTB_CHECK_ARG(a->pred_pack_w > 0 && a->hw % a->pred_pack_w == 0 && a->pred_pack_w % 4 == 0 && (a->hw / a->pred_pack_w) % 2 == 0,
+                      "pred_pack_w %d: the latent must be H x W with W %% 4 == 0 and H even (hw = %d)", a->pred_pack_w, a->hw);
     if (a->loss_weight_fn == OTB_LW_MIN_SNR || a->loss_weight_fn == OTB_LW_DEBIASED || a->loss_weight_fn == OTB_LW_P2)
         OTB_CHECK_ARG(a->timestep == nullptr || (a->sqrt_ac && a->sqrt_1mac), "snr weighting needs the schedule tables");
     OTB_BIND(a->predicted);

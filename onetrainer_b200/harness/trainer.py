@@ -140,11 +140,14 @@ class FlowSetup(ModelSetupFusedNoiseMixin, ModelSetupNoiseMixin, ModelSetupFlowM
     """FLUX-flavoured setup (rectified flow): restates BaseFluxSetup.predict :202-313 and calculate_loss :377-390
     with cached text-encoder outputs in the batch."""
 
-    def __init__(self, train_device: torch.device, fused_noise: bool = True, guidance_scale: float = 1.0):
+    def __init__(self, train_device: torch.device, fused_noise: bool = True, guidance_scale: float = 1.0, fold_pack: bool = True):
         super().__init__()
         self.train_device = train_device
         self.fused_noise = fused_noise
         self.guidance_scale = guidance_scale
+        # SURVEY §8f rank 2: K-b1 writes the network input in packed layout and K-b2 reads the packed prediction, so
+        # pack_latents / unpack_latents (and the unpack's backward) disappear from the step
+        self.fold_pack = fold_pack and fused_noise
 
     def predict(self, model: StandInFluxModel, batch: dict, config, train_progress: TrainProgress, *, deterministic: bool = False) -> dict:
         with model.autocast_context:
@@ -161,7 +164,7 @@ class FlowSetup(ModelSetupFusedNoiseMixin, ModelSetupNoiseMixin, ModelSetupFlowM
                 st = self._noise_timestep_addnoise(
                     latent_image, config, generator, num_train_timesteps=T, deterministic=deterministic, prediction_type="flow",
                     flow=True, latent_scale=model.vae_scaling_factor, latent_shift=model.vae_shift_factor,
-                    train_dtype=model.train_dtype, latent_height=H, latent_width=W)
+                    train_dtype=model.train_dtype, latent_height=H, latent_width=W, pack_latents=self.fold_pack)
                 timestep, latent_input, flow = st["timestep"], st["noisy"], st["target"]
             else:   # the reference's call-by-call sequence
                 scaled_latent_image = (latent_image - model.vae_shift_factor) * model.vae_scaling_factor
@@ -171,18 +174,22 @@ class FlowSetup(ModelSetupFusedNoiseMixin, ModelSetupNoiseMixin, ModelSetupFlowM
                 noisy, _sigma = self._add_noise_discrete(scaled_latent_image, latent_noise, timestep, model.noise_scheduler.timesteps)
                 latent_input = noisy.to(dtype=model.train_dtype)
                 flow = latent_noise - scaled_latent_image
-            B, C = latent_input.shape[0], latent_input.shape[1]
+            B, C = latent_image.shape[0], latent_image.shape[1]
             guidance = None
             if model.transformer.config["guidance_embeds"]:
                 guidance = torch.full((B,), float(self.guidance_scale), device=latent_input.device, dtype=model.train_dtype)
-            packed = model.pack_latents(latent_input, B, C, H, W)
+            packed = latent_input if self.fold_pack else model.pack_latents(latent_input, B, C, H, W)
             packed_predicted_flow = model.transformer(
                 hidden_states=packed.to(dtype=model.train_dtype), timestep=timestep / 1000, guidance=guidance,
                 pooled_projections=batch["text_encoder_1_pooled_state"].to(dtype=model.train_dtype),
                 encoder_hidden_states=batch["text_encoder_2_hidden_state"].to(dtype=model.train_dtype),
                 txt_ids=None, img_ids=None, joint_attention_kwargs=None, return_dict=True).sample
-            predicted_flow = model.unpack_latents(packed_predicted_flow, H, W)
-            data = {"loss_type": "target", "timestep": timestep, "predicted": predicted_flow, "target": flow}
+            if self.fold_pack:
+                data = {"loss_type": "target", "timestep": timestep, "predicted": packed_predicted_flow, "target": flow,
+                        "predicted_packed_width": W}
+            else:
+                predicted_flow = model.unpack_latents(packed_predicted_flow, H, W)
+                data = {"loss_type": "target", "timestep": timestep, "predicted": predicted_flow, "target": flow}
         return data
 
     def calculate_loss(self, model: StandInFluxModel, batch: dict, data: dict, config) -> torch.Tensor:

@@ -89,7 +89,9 @@ class ModelSetupDiffusionLossMixin(metaclass=ABCMeta):
             masked_prior_preservation_weight=config.masked_prior_preservation_weight,
             loss_scale=float(batch_scale * ga_scale), loss_weight_strength=config.loss_weight_strength,
             # what `.mean()` over B then `/ gradient_accumulation_steps` hands back to us
-            upstream=1.0 / (B * config.gradient_accumulation_steps), **tables)
+            upstream=1.0 / (B * config.gradient_accumulation_steps),
+            # opt-in: data['predicted'] is the transformer's PACKED output (FluxModel.unpack_latents skipped)
+            pred_pack_w=int(data.get("predicted_packed_width", 0)), **tables)
         return _FusedLoss.apply(predicted, kw)
 
     # ---- reference API -------------------------------------------------------------------

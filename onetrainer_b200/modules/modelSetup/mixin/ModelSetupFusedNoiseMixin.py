@@ -35,8 +35,11 @@ class ModelSetupFusedNoiseMixin(metaclass=ABCMeta):
                                  betas: Tensor | None = None, flow: bool = False, latent_scale: float = 1.0,
                                  latent_shift: float = 0.0, train_dtype: torch.dtype | None = None,
                                  latent_width: int | None = None, latent_height: int | None = None,
-                                 want_noise: bool = False, want_scaled_latent: bool = False) -> dict:
-        """Returns {'timestep' int32[B], 'noisy' (train dtype), 'target', ['sigma'], ['noise'], ['scaled_latent']}."""
+                                 want_noise: bool = False, want_scaled_latent: bool = False,
+                                 pack_latents: bool = False) -> dict:
+        """Returns {'timestep' int32[B], 'noisy' (train dtype), 'target', ['sigma'], ['noise'], ['scaled_latent']}.
+        `pack_latents=True` writes 'noisy' directly in FLUX's packed layout [B, (H/2)(W/2), 4C]
+        (FluxModel.pack_latents, modules/model/FluxModel.py:319-331) — no permute copy before the transformer."""
         dev = latent_image.device
         if self.__tables is None:
             if flow:
@@ -61,7 +64,7 @@ class ModelSetupFusedNoiseMixin(metaclass=ABCMeta):
             latent_scale=latent_scale, latent_shift=latent_shift,
             offset_noise_weight=config.offset_noise_weight, perturbation_noise_weight=config.perturbation_noise_weight,
             seed=seed, offset=offset, sample_base=dp.global_sample_base(B), want_sigma=flow, shape=latent_image.shape,
-            rng_dev=rng_dev, **kw)
+            rng_dev=rng_dev, pack_w=latent_image.shape[-1] if pack_latents else 0, **kw)
         res = {"timestep": out["timestep"], "noisy": out["noisy_cast"], "target": out["target"]}
         if flow:
             res["sigma"] = out["sigma"].view(B, *([1] * (latent_image.dim() - 1)))

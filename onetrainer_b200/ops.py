@@ -219,7 +219,8 @@ def noise_addnoise(*, latent=None, noise_in=None, coef_x0=None, coef_noise=None,
                    offset_noise_weight: float = 0.0, perturbation_noise_weight: float = 0.0,
                    min_timestep: int = 0, max_timestep: int = 1000, noising_weight: float = 0.0,
                    noising_bias: float = 0.0, shift: float = 1.0, seed: int = 0, offset: int = 0,
-                   sample_base: int = 0, want_sigma: bool = False, shape=None, rng_dev: torch.Tensor | None = None) -> dict:
+                   sample_base: int = 0, want_sigma: bool = False, shape=None, rng_dev: torch.Tensor | None = None,
+                   pack_w: int = 0) -> dict:
     """One launch of the pre-network half of the step kernel; returns the requested tensors."""
     N.require_cuda(latent, noise_in, coef_x0, coef_noise, timestep)
     shape = tuple(shape) if shape is not None else (B, C_ * hw)
@@ -233,6 +234,8 @@ def noise_addnoise(*, latent=None, noise_in=None, coef_x0=None, coef_noise=None,
     noise = new(latent_dtype) if want_noise else None
     noisy = new(latent_dtype) if want_noisy else None
     noisy_cast = new(cast_dtype) if cast_dtype is not None else None
+    if pack_w and noisy_cast is not None:          # FLUX packed layout [B, (H/2)(W/2), 4C] (FluxModel.pack_latents)
+        noisy_cast = noisy_cast.view(B, hw // 4, 4 * C_)
     tgt = new(latent_dtype) if target != N.TARGET_NONE else None
     if ts_mode == N.TS_GIVEN:
         if timestep is None:
@@ -255,7 +258,8 @@ def noise_addnoise(*, latent=None, noise_in=None, coef_x0=None, coef_noise=None,
         min_timestep=int(min_timestep), max_timestep=int(max_timestep),
         noising_weight=float(noising_weight), noising_bias=float(noising_bias),
         shift_c1=float(T * shift), shift_c2=float(shift - 1),
-        seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1), sample_base=int(sample_base), rng_dev=N.ptr(rng_dev))
+        seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1), sample_base=int(sample_base), rng_dev=N.ptr(rng_dev),
+        pack_w=int(pack_w))
     N.check(N.lib().otb_noise_addnoise(C.byref(a), _stream()), "otb_noise_addnoise")
     _count()
     out.update(x0=x0, noise=noise, noisy=noisy, noisy_cast=noisy_cast, target=tgt, timestep=ts, sigma=sigma)
@@ -289,16 +293,21 @@ def loss_fwd_bwd(predicted, target, *, prior_target=None, mask=None, loss_weight
                  sqrt_ac=None, sqrt_1mac=None, sigmas=None, masked=False, normalize_masked_area_loss=False,
                  loss_weight_fn=N.LW_CONSTANT, v_prediction=False, num_train_timesteps=1000,
                  mse_strength=1.0, mae_strength=0.0, unmasked_weight=0.1, masked_prior_preservation_weight=0.0,
-                 loss_scale=1.0, loss_weight_strength=5.0, upstream=1.0, want_grad=True):
-    """Per-sample losses [B] (fp32) and d(sum_b upstream*losses[b])/d(predicted) in one pass."""
+                 loss_scale=1.0, loss_weight_strength=5.0, upstream=1.0, want_grad=True, pred_pack_w: int = 0):
+    """Per-sample losses [B] (fp32) and d(sum_b upstream*losses[b])/d(predicted) in one pass.  With `pred_pack_w` = W the
+    prediction (and its gradient) are in FLUX's packed layout [B, (H/2)(W/2), 4C]; the target stays [B, C, H, W]."""
     N.require_cuda(predicted, target, prior_target, mask, timestep, sqrt_ac, sqrt_1mac, sigmas)
-    if predicted.shape != target.shape:
+    if pred_pack_w:
+        if target.dim() != 4 or predicted.dim() != 3 or predicted.numel() != target.numel() or target.shape[-1] != pred_pack_w \
+                or tuple(predicted.shape[1:]) != (target.shape[2] * target.shape[3] // 4, 4 * target.shape[1]):
+            raise ValueError(f"loss_fwd_bwd: packed prediction {tuple(predicted.shape)} does not match target {tuple(target.shape)}")
+    elif predicted.shape != target.shape:
         raise ValueError("loss_fwd_bwd: predicted / target shapes differ")
     predicted = predicted.contiguous()
     target = target.contiguous()
-    B = predicted.shape[0]
-    Cc = predicted.shape[1] if predicted.dim() > 2 else 1
-    hw = predicted[0].numel() // Cc
+    B = target.shape[0]
+    Cc = target.shape[1] if target.dim() > 2 else 1
+    hw = target[0].numel() // Cc
     dev = predicted.device
     if prior_target is not None:
         prior_target = prior_target.to(dtype=target.dtype).contiguous()
@@ -330,7 +339,7 @@ def loss_fwd_bwd(predicted, target, *, prior_target=None, mask=None, loss_weight
         num_train_timesteps=int(num_train_timesteps), blocks_per_sample=bps,
         mse_strength=float(mse_strength), mae_strength=float(mae_strength), unmasked_weight=float(unmasked_weight),
         masked_prior_preservation_weight=float(masked_prior_preservation_weight), loss_scale=float(loss_scale),
-        loss_weight_strength=float(loss_weight_strength), upstream=float(upstream))
+        loss_weight_strength=float(loss_weight_strength), upstream=float(upstream), pred_pack_w=int(pred_pack_w))
     N.check(N.lib().otb_loss_fwd_bwd(C.byref(a), _stream()), "otb_loss_fwd_bwd")
     _count(2 if (normalize_masked_area_loss and mask is not None) else 1)
     return losses, dpred

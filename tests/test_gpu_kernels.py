@@ -698,3 +698,40 @@ def test_lora_grad_ab_random_shapes_vs_fp32_torch(K, dev, monkeypatch):
                 assert torch.allclose(dA, 2 * rA, rtol=1e-4, atol=2e-3 * rA.abs().max().item() + 1e-5), (case, tc, M, N, K_, R)
             if dB is not None:
                 assert torch.allclose(dB, 2 * rB, rtol=1e-4, atol=2e-3 * rB.abs().max().item() + 1e-5), (case, tc, M, N, K_, R)
+
+
+def _flux_pack(t, C, H, W):
+    """FluxModel.pack_latents (modules/model/FluxModel.py:319-331) in torch."""
+    B = t.shape[0]
+    return t.view(B, C, H // 2, 2, W // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, (H // 2) * (W // 2), C * 4)
+
+
+@pytest.mark.parametrize("C,H,W", [(16, 32, 48), (4, 8, 8), (16, 128, 128)])
+def test_flux_pack_unpack_folded_into_the_kernels(K, dev, C, H, W):
+    """K-b1 writes the network input directly in FLUX's packed layout and K-b2 reads the packed
+    prediction / writes the packed gradient — pure permutations, so everything is BIT-identical to packing the plain
+    results with the reference's pack_latents; the loss values do not change at all."""
+    from onetrainer_b200.modules.util.DiffusionScheduleCoefficients import flow_sigmas
+    B = 3
+    gen = torch.Generator(device=dev).manual_seed(C * H + W)
+    lat = torch.randn(B, C, H, W, device=dev, generator=gen)
+    sigma, one_minus = flow_sigmas(1000, dev)
+    common = dict(latent=lat, coef_x0=one_minus, coef_noise=sigma, B=B, C_=C, hw=H * W, latent_dtype=torch.float32, device=dev,
+                  cast_dtype=torch.bfloat16, target=K.N.TARGET_FLOW, ts_mode=K.N.TS_LOGIT_NORMAL, latent_scale=0.3611, latent_shift=0.1159,
+                  seed=5, offset=0, shape=lat.shape)
+    plain = K.ops.noise_addnoise(**common)
+    packed = K.ops.noise_addnoise(pack_w=W, **common)
+    assert packed["noisy_cast"].shape == (B, H * W // 4, 4 * C)
+    assert torch.equal(packed["noisy_cast"], _flux_pack(plain["noisy_cast"], C, H, W))
+    assert torch.equal(packed["target"], plain["target"]) and torch.equal(packed["timestep"], plain["timestep"])
+    # loss on a packed prediction
+    pred = torch.randn(B, C, H, W, device=dev, generator=gen).bfloat16()
+    mask = (torch.rand(B, 1, H, W, device=dev, generator=gen) > 0.5).float()
+    for kw in (dict(), dict(mask=mask, masked=True, normalize_masked_area_loss=True, mae_strength=0.5)):
+        l0, g0 = K.ops.loss_fwd_bwd(pred, plain["target"], timestep=plain["timestep"], sigmas=sigma, loss_weight_fn=K.N.LW_SIGMA, upstream=1 / B, **kw)
+        l1, g1 = K.ops.loss_fwd_bwd(_flux_pack(pred, C, H, W).contiguous(), plain["target"], timestep=plain["timestep"], sigmas=sigma,
+                                    loss_weight_fn=K.N.LW_SIGMA, upstream=1 / B, pred_pack_w=W, **kw)
+        assert torch.equal(l0, l1)
+        assert g1.shape == (B, H * W // 4, 4 * C) and torch.equal(g1, _flux_pack(g0, C, H, W))
+    with pytest.raises(ValueError):
+        K.ops.noise_addnoise(pack_w=W - 2, **common)
