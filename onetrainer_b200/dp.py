@@ -123,6 +123,90 @@ class FlatGradArena:
         return [p.grad for p in self.parameters]
 
 
+class OverlappedArenaReducer:
+    """The one exchange step of a FlatGradArena, overlapped with backward (full fine-tuning, config C4).
+
+    The 4.4 GB bf16 gradient arena of SDXL costs ~9 ms of allreduce on 2 GPUs and more on 8 when it runs after
+    backward.  Gradients become final in (roughly) reverse parameter order, so the arena is cut into contiguous buckets;
+    a post-accumulate-grad hook counts each bucket's parameters down and, when the last one lands, issues that bucket's
+    in-place allreduce on a communication stream forked from the backward stream.  `finish()` joins the streams and
+    returns the 1/n prescale.  Works the same inside a CUDA-graph capture (fork / join of captured streams).
+    With gradient accumulation, `arm(last_micro_step=False)` keeps the hooks quiet until the last micro-batch.
+    """
+
+    def __init__(self, arena: FlatGradArena, n_buckets: int | None = None):
+        if n_buckets is None:
+            n_buckets = int(os.environ.get("OTB_REDUCE_BUCKETS", "12"))
+        self.arena = arena
+        params = arena.parameters
+        total = arena.flat.numel()
+        bounds, self._bucket_of, counts = [0], {}, []
+        target = max(1, total // max(1, n_buckets))
+        start_ptr = arena.flat.data_ptr()
+        esz = arena.flat.element_size()
+        cur = 0
+        for i, p in enumerate(params):
+            off = (p.grad.data_ptr() - start_ptr) // esz
+            if off - bounds[-1] >= target and cur > 0:
+                bounds.append(off)
+                counts.append(cur)
+                cur = 0
+            self._bucket_of[id(p)] = len(bounds) - 1
+            cur += 1
+        bounds.append(total)
+        counts.append(cur)
+        self._slices = [arena.flat[bounds[b]:bounds[b + 1]] for b in range(len(counts))]
+        self._counts = counts
+        self._left = list(counts)
+        self._armed = False
+        self._comm = None
+        self._issued = 0
+        for p in params:
+            p.register_post_accumulate_grad_hook(self._on_grad)
+
+    def arm(self, last_micro_step: bool = True) -> None:
+        self._left = list(self._counts)
+        self._armed = last_micro_step and world_size() > 1
+        self._issued = 0
+
+    def _on_grad(self, p: torch.Tensor) -> None:
+        if not self._armed:
+            return
+        b = self._bucket_of[id(p)]
+        self._left[b] -= 1
+        if self._left[b] == 0:
+            self._reduce(b)
+
+    def _reduce(self, b: int) -> None:
+        if not self.arena.flat.is_cuda:                   # host tensors (gloo tests): no streams to fork
+            dist.all_reduce(self._slices[b], op=dist.ReduceOp.SUM)
+            self._issued += 1
+            return
+        main = torch.cuda.current_stream(self.arena.flat.device)
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=self.arena.flat.device)
+        self._comm.wait_stream(main)                      # the kernels that produced this bucket's gradients
+        with torch.cuda.stream(self._comm):
+            dist.all_reduce(self._slices[b], op=dist.ReduceOp.SUM)
+        self._issued += 1
+
+    def finish(self) -> float:
+        """Reduce whatever has not been reduced (parameters without a gradient this step), join, return the prescale."""
+        n = world_size()
+        if n == 1:
+            return 1.0
+        if not self._armed:
+            return 1.0
+        for b, left in enumerate(self._left):
+            if left > 0:
+                self._left[b] = 0
+                self._reduce(b)
+        if self._comm is not None and self.arena.flat.is_cuda:
+            torch.cuda.current_stream(self.arena.flat.device).wait_stream(self._comm)
+        self._armed = False
+        return 1.0 / n
+
+
 def _is_view_of(t: torch.Tensor, base: torch.Tensor) -> bool:
     lo = base.data_ptr()
     hi = lo + base.numel() * base.element_size()

@@ -45,6 +45,7 @@ class StandInModel:
         self.sdxl = sdxl
         self.unet_lora: LoRAModuleWrapper | None = None
         self.full_grad_arena: dp.FlatGradArena | None = None      # full fine-tuning: persistent flat gradients
+        self.grad_reducer: dp.OverlappedArenaReducer | None = None  # ... and their allreduce, overlapped with backward
         self.optimizer = None
         self.ema: EMAModuleWrapper | None = None
         self.parameters: list[nn.Parameter] = []
@@ -243,6 +244,7 @@ def build_model(kind: str, config, device, *, train_dtype=torch.bfloat16, lora_w
         unet.requires_grad_(True)
         model.parameters = list(unet.parameters())
         model.full_grad_arena = dp.FlatGradArena(model.parameters)
+        model.grad_reducer = dp.OverlappedArenaReducer(model.full_grad_arena) if dp.world_size() > 1 else None
         model.optimizer = torch.optim.AdamW(model.parameters, lr=lr, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
         if ema:
             model.ema = EMAModuleWrapper(model.parameters, decay=config.ema_decay,
@@ -327,9 +329,14 @@ def train_step(setup: DiffusionSetup, model: StandInModel, batch: dict, config, 
     data = setup.predict(model, batch, config, model.train_progress)
     loss = setup.calculate_loss(model, batch, data, config)
     loss = loss / config.gradient_accumulation_steps
+    reducer = getattr(model, "grad_reducer", None)
+    if reducer is not None:
+        reducer.arm()
     loss.backward()
     driver = model.optimizer.otb_driver
-    if dp.world_size() > 1:
+    if reducer is not None:
+        driver.grad_prescale = reducer.finish()
+    elif dp.world_size() > 1:
         arena = model.unet_lora.grad_arena if model.unet_lora is not None else getattr(model, "full_grad_arena", None)
         bucket = bucket or dp.GradientBucket(arena.flat if isinstance(arena, dp.FlatGradArena) else arena)
         driver.grad_prescale = bucket.allreduce([p.grad for p in model.parameters if p.grad is not None])
@@ -429,8 +436,13 @@ class GraphedTrainStep:
         model, cfg = self.model, self.config
         data = self.setup.predict(model, self.dev_batch, cfg, model.train_progress)
         loss = self.setup.calculate_loss(model, self.dev_batch, data, cfg) / cfg.gradient_accumulation_steps
+        reducer = getattr(model, "grad_reducer", None)
+        if reducer is not None:
+            reducer.arm()
         loss.backward()
-        if dp.world_size() > 1:
+        if reducer is not None:
+            self.driver.grad_prescale = reducer.finish()
+        elif dp.world_size() > 1:
             if self.bucket.arena is None:
                 self.bucket.arena = model.unet_lora.grad_arena if model.unet_lora is not None else model.full_grad_arena.flat
             self.driver.grad_prescale = self.bucket.allreduce([p.grad for p in model.parameters if p.grad is not None])

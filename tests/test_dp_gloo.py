@@ -57,6 +57,23 @@ def _worker(rank, world, port, out_dir):
     assert torch.equal(lin.weight.grad, torch.full((3, 6), 2 * 4.0 * (1.0 + 2.0)))
     fa.zero()
     assert all(not p.grad.any() for p in lin.parameters()) and [p.grad.data_ptr() for p in lin.parameters()] == ptrs
+    # (2c) the same exchange issued bucket by bucket from post-accumulate-grad hooks while backward is still running
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(*[torch.nn.Linear(8, 8) for _ in range(5)])
+    fa2 = dp.FlatGradArena(list(net.parameters()))
+    red = dp.OverlappedArenaReducer(fa2, n_buckets=3)
+    assert len(red._slices) == 3 and sum(sl.numel() for sl in red._slices) == fa2.flat.numel()
+    red.arm(last_micro_step=False)                       # first micro-batch of two: accumulate only
+    net(torch.full((2, 8), 0.5 + rank)).sum().backward()
+    assert red.finish() == 1.0 and red._issued == 0
+    local = fa2.flat.clone()
+    red.arm()
+    net(torch.full((2, 8), 0.5 + rank)).sum().backward()
+    assert red._issued >= 2                              # buckets went out during backward, before finish()
+    assert red.finish() == 0.5 and red._issued == 3
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    torch.distributed.all_gather(gathered, 2 * local)    # what each rank held locally after both micro-batches
+    assert torch.allclose(fa2.flat, sum(gathered), rtol=1e-6, atol=1e-6)
     # (3) loss averaging for logging
     assert dp.average_scalar(torch.tensor(float(rank))).item() == 0.5
     # (4) DP-invariant draws: this rank's samples of the global batch, through the oracle's stream definition
