@@ -34,7 +34,9 @@ class EMAModuleWrapper:
         self._fused_step = None             # optimization_step already applied inside the optimizer launch
 
     def get_current_decay(self, optimization_step) -> float:
-        return min((1 + optimization_step) / (10 + optimization_step), self.decay)
+        """Warm-up schedule of the reference (:31-35): (1 + s) / (10 + s), capped by the configured decay."""
+        warm_up = (optimization_step + 1) / (optimization_step + 10)
+        return warm_up if warm_up < self.decay else self.decay
 
     # ---- fusion with the patched optimizer ------------------------------------------------
     def attach_fused_driver(self, driver) -> None:
@@ -78,29 +80,39 @@ class EMAModuleWrapper:
                 e.add_(delta)
 
     def to(self, device: torch.device = None, dtype: torch.dtype = None) -> None:
-        self.device = device
-        self.ema_parameters = [p.to(device=device, dtype=dtype) if p.is_floating_point() else p.to(device=device)
-                               for p in self.ema_parameters]
-        self._table = None
+        """Move (and for floating tensors, cast) the averages; integer buffers keep their dtype (:56-61)."""
+        moved = []
+        for avg in self.ema_parameters:
+            kwargs = {"device": device}
+            if avg.is_floating_point():
+                kwargs["dtype"] = dtype
+            moved.append(avg.to(**kwargs))
+        self.ema_parameters, self.device = moved, device
+        self._table = None                   # pointer tables refer to the old storage
         if self._driver is not None:
             self._driver.table = None
 
+    def _write_into(self, sources, parameters) -> None:
+        for src, dst in zip(sources, list(parameters), strict=True):
+            dst.data.copy_(src.to(dst.device).data)
+
     def copy_ema_to(self, parameters: Iterable[torch.nn.Parameter], store_temp: bool = True) -> None:
-        parameters = list(parameters)
-        if store_temp:
-            self.temp_stored_parameters = [p.detach().cpu() for p in parameters]
-        for e, p in zip(self.ema_parameters, parameters, strict=True):
-            p.data.copy_(e.to(p.device).data)
+        """Swap the averages in for sampling / saving (:63-69), optionally parking the live weights on the host."""
+        live = list(parameters)
+        self.temp_stored_parameters = [w.detach().cpu() for w in live] if store_temp else self.temp_stored_parameters
+        self._write_into(self.ema_parameters, live)
 
     def copy_temp_to(self, parameters: Iterable[torch.nn.Parameter]) -> None:
-        for t, p in zip(self.temp_stored_parameters, parameters, strict=True):
-            p.data.copy_(t.data)
+        """Put the parked live weights back (:71-75)."""
+        self._write_into(self.temp_stored_parameters, parameters)
         self.temp_stored_parameters = None
 
+    def state_dict(self) -> dict:
+        return dict(decay=self.decay, ema_parameters=self.ema_parameters)
+
     def load_state_dict(self, state_dict: dict) -> None:
-        self.decay = self.decay if self.decay else state_dict.get("decay", self.decay)
+        """A configured decay wins over the saved one, as in the reference (:80-86)."""
+        if not self.decay:
+            self.decay = state_dict.get("decay", self.decay)
         self.ema_parameters = state_dict.get("ema_parameters")
         self.to(self.device)
-
-    def state_dict(self) -> dict:
-        return {"decay": self.decay, "ema_parameters": self.ema_parameters}
