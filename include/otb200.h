@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OTB_ABI_VERSION 1
+#define OTB_ABI_VERSION 2   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs */
 
 /* error codes */
 #define OTB_OK            0

@@ -12,6 +12,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "libotb200.so"
 
 # ---- enums (include/otb200.h) ---------------------------------------------------------
+ABI_VERSION = 2          # include/otb200.h: OTB_ABI_VERSION
 OTB_OK, OTB_EINVAL, OTB_EUNSUPPORTED, OTB_ECUDA, OTB_EARCH = 0, -1, -2, -3, -4
 F32, BF16, F16 = 0, 1, 2
 
@@ -158,8 +159,8 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.otb_abi_version() != 1:
-            raise RuntimeError(f"{LIB_PATH}: ABI version {handle.otb_abi_version()} != 1; rebuild the library")
+        if handle.otb_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{LIB_PATH}: ABI version {handle.otb_abi_version()} != {ABI_VERSION}; rebuild the library")
         sizes = (C.c_int32 * 7)()
         handle.otb_struct_sizes(sizes)
         for got, st in zip(sizes, _STRUCTS):
