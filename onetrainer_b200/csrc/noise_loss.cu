@@ -147,7 +147,9 @@ __device__ __forceinline__ float normal1(const otb_noise_args& a, uint32_t strea
 //     latent given — with every option a compile-time constant, so the loop body is the
 //     Philox rounds, four MUFU ops per pair of draws and the affine maps (profiles/: 57 -> ~27 thread
 //     instructions per element; the generic kernel was issue-bound at 58 % of the HBM roofline).
-template <int U, int LD, int FT>
+// PACK: noisy_cast_out is written in FLUX's packed layout (a.pack_w = latent width); compile-time so that the plain
+// kernels carry none of the index arithmetic (as a run-time branch it cost K-b2 20 % of its bandwidth)
+template <int U, int LD, int FT, bool PACK>
 __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_args a) {
     constexpr bool FAST = FT >= 0;
     if (a.rng_dev != nullptr) { a.seed = a.rng_dev[0]; a.offset = a.rng_dev[1]; }
@@ -220,7 +222,8 @@ __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_ar
                 if (!FAST && !a.latent) continue;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    x[u][k] = rnd_dt(__fmul_rn(rnd_dt(__fsub_rn(x[u][k], a.latent_shift), ldt), a.latent_scale), ldt);
+                    x[u][k] = rnd_dt(__fmul_rn((FAST && FT != OTB_TARGET_FLOW) ? x[u][k]      // eps / v fast paths: shift == 0, x - 0 == x
+                                                                              : rnd_dt(__fsub_rn(x[u][k], a.latent_shift), ldt), a.latent_scale), ldt);
                 if (a.x0_out) store4(a.x0_out, base + i, ldt, x[u]);
                 if (add) {
                     float y[4];
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(NL_THREADS) noise_addnoise_kernel(otb_noise_ar
                     if (a.noisy_cast_out) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) y[k] = rnd_dt(y[k], ldt);
-                        if (a.pack_w > 0) store_packed4(a.noisy_cast_out, base + packed_pair_offset((uint32_t)i, a.C, a.hw, a.pack_w), a.C, a.cast_dtype, y);
+                        if constexpr (PACK) store_packed4(a.noisy_cast_out, base + packed_pair_offset((uint32_t)i, a.C, a.hw, a.pack_w), a.C, a.cast_dtype, y);
                         else store4(a.noisy_cast_out, base + i, a.cast_dtype, y);
                     }
                 }
@@ -344,8 +347,9 @@ __device__ float timestep_weight(const otb_loss_args& a, int b) {
 // FEAT: -1 = every option read at run time; otherwise a compile-time feature set — bit 0 masked, bit 1 prior
 // preservation term, bit 2 MAE term — so the training configurations (FEAT 0: plain MSE, FEAT 1: masked MSE,
 // FEAT 3: masked MSE + prior) carry no dead branches or dead registers.
-template <int U, int PD, int TD, int FEAT>
-__global__ void __launch_bounds__(NL_THREADS, (FEAT >= 0 && U <= 2) ? 6 : 1) loss_fwd_bwd_kernel(otb_loss_args a) {
+// PACK: predicted / dpred are in FLUX's packed layout (a.pred_pack_w = latent width), compile-time like the features
+template <int U, int PD, int TD, int FEAT, bool PACK>
+__global__ void __launch_bounds__(NL_THREADS, (FEAT >= 0 && U <= 2 && !PACK) ? 6 : 1) loss_fwd_bwd_kernel(otb_loss_args a) {
     const int pred_dt = PD >= 0 ? PD : a.pred_dtype;
     const int tgt_dt = TD >= 0 ? TD : a.target_dtype;
     constexpr bool FIXED = FEAT >= 0;
@@ -387,7 +391,7 @@ __global__ void __launch_bounds__(NL_THREADS, (FEAT >= 0 && U <= 2) ? 6 : 1) los
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { p[u][k] = 0.0f; t[u][k] = 0.0f; pt[u][k] = 0.0f; m[u][k] = 1.0f; }
                 if (!live[u]) continue;
-                if (a.pred_pack_w > 0) load_packed4(a.predicted, base + packed_pair_offset((uint32_t)i, a.C, a.hw, a.pred_pack_w), a.C, pred_dt, p[u]);
+                if constexpr (PACK) load_packed4(a.predicted, base + packed_pair_offset((uint32_t)i, a.C, a.hw, a.pred_pack_w), a.C, pred_dt, p[u]);
                 else load4(a.predicted, base + i, pred_dt, p[u]);
                 load4(a.target, base + i, tgt_dt, t[u]);
                 if (prior) load4(a.prior_target, base + i, tgt_dt, pt[u]);
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(NL_THREADS, (FEAT >= 0 && U <= 2) ? 6 : 1) los
                     g[k] = gr * gfac;
                 }
                 if (want_grad) {
-                    if (a.pred_pack_w > 0) store_packed4(a.dpred, base + packed_pair_offset((uint32_t)i, a.C, a.hw, a.pred_pack_w), a.C, pred_dt, g);
+                    if constexpr (PACK) store_packed4(a.dpred, base + packed_pair_offset((uint32_t)i, a.C, a.hw, a.pred_pack_w), a.C, pred_dt, g);
                     else store4(a.dpred, base + i, pred_dt, g);
                 }
             }
@@ -553,8 +557,9 @@ extern "C" int otb_noise_addnoise(const otb_noise_args* a, void* stream) {
     // the training configuration takes the specialised kernel (see the template comment)
     const bool fast = a->latent_dtype == OTB_F32 && a->generate_noise && a->latent && a->do_add_noise && !a->noise_in &&
                       a->offset_noise_weight <= 0.0f && a->perturbation_noise_weight <= 0.0f &&
+                      (a->latent_shift == 0.0f || a->target == OTB_TARGET_FLOW) &&
                       (chw & 3) == 0 && a->target != OTB_TARGET_NONE && getenv("OTB_NB1_GENERIC") == nullptr;
-#define OTB_NB1_LAUNCH(UU, FT) noise_addnoise_kernel<UU, OTB_F32, FT><<<grid, NL_THREADS, 0, st>>>(*a)
+#define OTB_NB1_LAUNCH(UU, FT) noise_addnoise_kernel<UU, OTB_F32, FT, false><<<grid, NL_THREADS, 0, st>>>(*a)
 #define OTB_NB1_BY_TARGET(UU)                                                   \
     do {                                                                        \
         if (!fast) OTB_NB1_LAUNCH(UU, -1);                                      \
@@ -562,12 +567,17 @@ extern "C" int otb_noise_addnoise(const otb_noise_args* a, void* stream) {
         else if (a->target == OTB_TARGET_V) OTB_NB1_LAUNCH(UU, OTB_TARGET_V);   \
         else OTB_NB1_LAUNCH(UU, OTB_TARGET_FLOW);                               \
     } while (0)
-    if (a->latent_dtype == OTB_F32) {
+    if (a->pack_w > 0) {
+        // packed network input: the FLUX training configuration (fp32 latents, flow target) or the generic kernel
+        OTB_UNSUPPORTED((chw & 3) != 0, "pack_w needs C*H*W to be a multiple of 4");
+        if (fast && a->target == OTB_TARGET_FLOW) noise_addnoise_kernel<NB1_UNROLL, OTB_F32, OTB_TARGET_FLOW, true><<<grid, NL_THREADS, 0, st>>>(*a);
+        else noise_addnoise_kernel<NB1_UNROLL, -1, -1, true><<<grid, NL_THREADS, 0, st>>>(*a);
+    } else if (a->latent_dtype == OTB_F32) {
         if (u == 1) OTB_NB1_BY_TARGET(1);
         else if (u == 4) OTB_NB1_BY_TARGET(4);
         else OTB_NB1_BY_TARGET(2);
     } else {
-        noise_addnoise_kernel<NB1_UNROLL, -1, -1><<<grid, NL_THREADS, 0, st>>>(*a);
+        noise_addnoise_kernel<NB1_UNROLL, -1, -1, false><<<grid, NL_THREADS, 0, st>>>(*a);
     }
 #undef OTB_NB1_BY_TARGET
 #undef OTB_NB1_LAUNCH
@@ -598,9 +608,15 @@ extern "C" int otb_loss_fwd_bwd(const otb_loss_args* a, void* stream) {
     const bool prior = masked && a->prior_target != nullptr && a->masked_prior_preservation_weight != 0.0f;
     int feat = (masked ? 1 : 0) | (prior ? 2 : 0) | (a->mae_strength != 0.0f ? 4 : 0);
     if ((feat != 0 && feat != 1 && feat != 3) || getenv("OTB_NB2_GENERIC") != nullptr) feat = -1;
-    if (a->pred_dtype == OTB_BF16 && a->target_dtype == OTB_F32) {     // the training configuration
+    if (a->pred_pack_w > 0) {                  // packed prediction (FLUX): plain MSE specialisation or the generic kernel
+        if (feat == 0 && a->pred_dtype == OTB_BF16 && a->target_dtype == OTB_F32)
+            loss_fwd_bwd_kernel<NB2_UNROLL, OTB_BF16, OTB_F32, 0, true><<<grid, NL_THREADS, 0, st>>>(*a);
+        else
+            loss_fwd_bwd_kernel<NB2_UNROLL, -1, -1, -1, true><<<grid, NL_THREADS, 0, st>>>(*a);
+    }
+    else if (a->pred_dtype == OTB_BF16 && a->target_dtype == OTB_F32) {     // the training configuration
         const int u = tuning_unroll("OTB_NB2_UNROLL", NB2_UNROLL);
-#define OTB_NB2_LAUNCH(UU, FF) loss_fwd_bwd_kernel<UU, OTB_BF16, OTB_F32, FF><<<grid, NL_THREADS, 0, st>>>(*a)
+#define OTB_NB2_LAUNCH(UU, FF) loss_fwd_bwd_kernel<UU, OTB_BF16, OTB_F32, FF, false><<<grid, NL_THREADS, 0, st>>>(*a)
 #define OTB_NB2_BY_FEAT(UU)                          \
     do {                                             \
         if (feat == 0) OTB_NB2_LAUNCH(UU, 0);        \
@@ -615,9 +631,9 @@ extern "C" int otb_loss_fwd_bwd(const otb_loss_args* a, void* stream) {
 #undef OTB_NB2_LAUNCH
     }
     else if (a->pred_dtype == OTB_F32 && a->target_dtype == OTB_F32)
-        loss_fwd_bwd_kernel<NB2_UNROLL, OTB_F32, OTB_F32, -1><<<grid, NL_THREADS, 0, st>>>(*a);
+        loss_fwd_bwd_kernel<NB2_UNROLL, OTB_F32, OTB_F32, -1, false><<<grid, NL_THREADS, 0, st>>>(*a);
     else
-        loss_fwd_bwd_kernel<NB2_UNROLL, -1, -1, -1><<<grid, NL_THREADS, 0, st>>>(*a);
+        loss_fwd_bwd_kernel<NB2_UNROLL, -1, -1, -1, false><<<grid, NL_THREADS, 0, st>>>(*a);
     OTB_LAUNCH_CHECK("loss_fwd_bwd_kernel");
     return OTB_OK;
 }
