@@ -280,6 +280,21 @@ def time_hbm_kernels(dev, hbm_peak: float) -> list:
             for k, a in out]
 
 
+def profiled_traffic() -> tuple[float | None, str | None]:
+    """DRAM bytes (read + write) of ONE launch of the dominant kernel from the committed `ncu --set full` summary
+    (profiles/r01b_ncu_ka_v3.md: M=4096, N=10240, K=1280, r=32) — per launch, not per step."""
+    import re
+    f = REPO / "profiles" / "r01b_ncu_ka_v3.md"
+    if not f.exists():
+        return None, None
+    m = re.search(r"traffic = read \+ write = ([0-9.]+) (\w+) \+ ([0-9.]+) (\w+)", f.read_text())
+    if not m:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    return float(m.group(1)) * unit[m.group(2)] + float(m.group(3)) * unit[m.group(4)], \
+        "one launch at M=4096 N=10240 K=1280 r=32 (profiles/r01b_ncu_ka_v3.md); algorithmic 120.7 MB incl. the output write"
+
+
 def own_arm(args) -> None:
     import torch
     import torch.distributed as dist
@@ -370,6 +385,7 @@ def own_arm(args) -> None:
         s = cpu_baseline.run_sample()
         cpu = {"value": 1.0 / s["step_seconds"], "unit": UNIT, "cores": s["threads"], "kind": "port", "sample": s["sample"],
                "sample_seconds": s["sample_seconds"], "parts_seconds": s["parts"]}
+    traffic, traffic_of = profiled_traffic()
     if rank == 0:
         value = world * args.steps / sec
         line = {
@@ -385,7 +401,8 @@ def own_arm(args) -> None:
             "gpu_launches": launches, "cuda_graph": graphed is not None, "loss": float(last_loss), "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "lora_linear_kernel_v3 / _v2 (K-a: the forward + dX launches of all 722 leaves; q/k/v siblings grouped)",
                          "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": f"{peak_kind} bf16_tflops_sustained",
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_of": traffic_of,
+                         "peak_source": f"{peak_kind} bf16_tflops_sustained",
                          "algorithmic_flops_per_step": ka["gemm_flops"], "launches_per_step": ka["gemm_launches"],
                          "seconds_per_step_in_kernel": ka["gemm_sec"], "share_of_step": ka["gemm_sec"] / (sec / args.steps)},
             "hbm_kernels": hbm_kernels, "hbm_peak_source": f"{peak_kind} hbm_gbs",
