@@ -125,13 +125,15 @@ def reference_arm(args) -> None:
 
 # ---------------------------------------------------------------------------------------------------
 def leaf_flops(model, recompute: bool = False) -> tuple[float, int, list]:
-    """Algorithmic FLOPs of the fused LoRA GEMMs in one step: per leaf 4MKN + 6Mr(K+N)."""
+    """Algorithmic FLOPs of the fused LoRA GEMMs in one step: per leaf 4MKN + 6Mr(K+N); a leaf whose
+    input takes no gradient (context K/V) has no dX GEMM, here as in the reference's autograd: 2MKN + 4Mr(K+N) + 2MrN."""
     total, launches, shapes = 0.0, 0, []
     for m in model.unet_lora.lora_modules.values():
         M = getattr(m, "_last_rows", 0)
         w = m.orig_module.weight
         N, K, r = w.shape[0], w[0].numel(), m.rank
-        total += 4.0 * M * K * N + 6.0 * M * r * (K + N)
+        total += 2.0 * M * K * N + 4.0 * M * r * (K + N)              # forward, dA, dB
+        total += 2.0 * M * K * N + 2.0 * M * r * (K + N) if getattr(m, "_last_input_grad", True) else 2.0 * M * r * N
         launches += 3
         shapes.append((M, N, K, r))
     return total, launches, shapes
@@ -169,6 +171,7 @@ def time_leaf_kernels(model, dev) -> dict:
     in the real step.  Returns device seconds and algorithmic work of both families."""
     import torch
     from onetrainer_b200 import ops
+    from onetrainer_b200.modules.module.LoRAModule import _gs_only
     _, _, shapes = leaf_flops(model)
     g = torch.Generator(device=dev).manual_seed(0)
     acts = {}
@@ -199,31 +202,32 @@ def time_leaf_kernels(model, dev) -> dict:
     gemm_flops, grad_flops, grad_bytes = 0.0, 0.0, 0.0
     for unit in units:
         M, N, K, r = shape_of[id(unit[0])]
+        # a leaf whose input took no gradient in the real step (context K/V): no dX GEMM is issued, only Gs (see _gs_only)
+        no_dx = not getattr(unit[0], "_last_input_grad", True)
         entry = []
         for i, m in enumerate(unit):
             sh = m._operands()
             entry.append((act(M, K), act(M, N, i), sh, m._scale(), torch.zeros(r, K, device=dev), torch.zeros(N, r, device=dev),
                           torch.zeros(M, r, device=dev, dtype=torch.bfloat16)))
-            gemm_flops += 4.0 * M * K * N + 4.0 * M * r * (K + N)      # forward + dX, each 2MKN + 2Mr(K+N)
+            gemm_flops += 2.0 * M * K * N + 2.0 * M * r * (K + N)      # forward
+            gemm_flops += 2.0 * M * r * N if no_dx else 2.0 * M * K * N + 2.0 * M * r * (K + N)   # Gs only, or dX (+ Gs)
             grad_flops += 2.0 * M * r * (K + N)                        # dA + dB
             grad_bytes += 2.0 * M * (K + N) + 4.0 * M * r + 8.0 * r * (K + N)   # stream x, dY, Gs, Ts once; fp32 RMW of dA, dB
-        plan.append(entry)
-    n_leaves = sum(len(e) for e in plan)
+        plan.append((entry, no_dx))
+    n_leaves = sum(len(e) for e, _ in plan)
 
     def gemms():
-        for e in plan:
-            if len(e) == 1:
-                x, dy, sh, sc, dA, dB, t = e[0]
-                ops.lora_linear(x, sh["w"], sh["a"], sh["b"], sh["bias"], sc)
-                ops.lora_linear(dy, sh["wt"], sh["bt"], sh["at"], None, sc)
+        for e, no_dx in plan:
+            ops.lora_linear_grouped([m[0] for m in e], [m[2]["w"] for m in e], [m[2]["a"] for m in e], [m[2]["b"] for m in e],
+                                    [m[2]["bias"] for m in e], [m[3] for m in e])
+            if no_dx:
+                _gs_only([m[1] for m in e], [m[2] for m in e], [m[3] for m in e], 0.0, [(0, 0)] * len(e))
             else:
-                ops.lora_linear_grouped([m[0] for m in e], [m[2]["w"] for m in e], [m[2]["a"] for m in e], [m[2]["b"] for m in e],
-                                        [m[2]["bias"] for m in e], [m[3] for m in e])
                 ops.lora_linear_grouped([m[1] for m in e], [m[2]["wt"] for m in e], [m[2]["bt"] for m in e], [m[2]["at"] for m in e],
                                         [None] * len(e), [m[3] for m in e])
 
     def grads():
-        for e in plan:
+        for e, _ in plan:
             for x, dy, sh, sc, dA, dB, t in e:
                 ops.lora_grad_ab(x, dy, t, t, dA, dB)
 

@@ -90,10 +90,15 @@ class _LoraLinearFn(torch.autograd.Function):
         dy = dy.contiguous()
         if dy.dtype != torch.bfloat16:
             dy = dy.to(torch.bfloat16)
-        # dX = dY W + drop(s * dY B) A  — same kernel, transposed shadows; also parks Gs = drop(s * dY B)
-        dx, gs = ops.lora_linear(dy, sh["wt"], sh["bt"], sh["at"], None, mod._scale(), dropout_p=ctx.p,
-                                 seed=ctx.key[0], offset=ctx.key[1], want_t=True)
         need_a, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        mod._last_input_grad = ctx.needs_input_grad[0]      # read by bench.py to replay the step's launches
+        # dX = dY W + drop(s * dY B) A  — same kernel, transposed shadows; also parks Gs = drop(s * dY B)
+        dx = gs = None
+        if ctx.needs_input_grad[0]:
+            dx, gs = ops.lora_linear(dy, sh["wt"], sh["bt"], sh["at"], None, mod._scale(), dropout_p=ctx.p,
+                                     seed=ctx.key[0], offset=ctx.key[1], want_t=True)
+        elif need_a:
+            gs = _gs_only([dy], [sh], [mod._scale()], ctx.p, [ctx.key])[0]
         dA, dB, ret_a, ret_b = mod._grad_buffers(need_a, need_b)
         if dA is not None or dB is not None:
             _launch_grad_ab(mod, x2, dy, gs, ts, dA, dB, ret_a, ret_b)
@@ -101,7 +106,21 @@ class _LoraLinearFn(torch.autograd.Function):
             ret_a = ret_a.to(mod.lora_down.weight.dtype)
         if ret_b is not None and ret_b.dtype != mod.lora_up.weight.dtype:
             ret_b = ret_b.to(mod.lora_up.weight.dtype)
-        return (dx if ctx.needs_input_grad[0] else None), ret_a, ret_b, None
+        return dx, ret_a, ret_b, None
+
+
+NO_DX_ROWS = 64
+
+
+def _gs_only(dys: list, shs: list, scales: list, p: float, keys: list) -> list:
+    """Gs = drop(s * dY B) of leaves whose input takes no gradient (the K/V projections of the text context, the first
+    layer after the latents): autograd would not form dX there and neither does this path.  K-a produces T alongside
+    any output tile, so the launch is cut down to the first NO_DX_ROWS output columns of dX (discarded) and streams
+    dY once; the full dX GEMM of such a leaf (M x K x N) is never issued."""
+    rows = min(NO_DX_ROWS, shs[0]["wt"].shape[0])
+    _, gss = ops.lora_linear_grouped(dys, [sh["wt"][:rows] for sh in shs], [sh["bt"] for sh in shs], [sh["at"][:rows] for sh in shs],
+                                     [None] * len(dys), scales, dropout_p=p, keys=keys, want_t=True)
+    return gss
 
 
 class _LoraGroupFn(torch.autograd.Function):
@@ -141,11 +160,18 @@ class _LoraGroupFn(torch.autograd.Function):
                 dy = dys[i].contiguous()
                 dyc.append(dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16))
             ops_ = [mods[i]._operands() for i in live]
-            dxs, gss = ops.lora_linear_grouped(dyc, [o["wt"] for o in ops_], [o["bt"] for o in ops_], [o["at"] for o in ops_],
-                                               [None] * len(live), [mods[i]._scale() for i in live], dropout_p=ctx.p,
-                                               keys=[ctx.keys[i] for i in live], want_t=True)
+            dxs = None
+            if ctx.needs_input_grad[1]:
+                dxs, gss = ops.lora_linear_grouped(dyc, [o["wt"] for o in ops_], [o["bt"] for o in ops_], [o["at"] for o in ops_],
+                                                   [None] * len(live), [mods[i]._scale() for i in live], dropout_p=ctx.p,
+                                                   keys=[ctx.keys[i] for i in live], want_t=True)
+            elif any(ctx.needs_input_grad[2 + 2 * i] for i in live):
+                gss = _gs_only(dyc, ops_, [mods[i]._scale() for i in live], ctx.p, [ctx.keys[i] for i in live])
+            else:
+                gss = [None] * len(live)
             for j, i in enumerate(live):
                 mod = mods[i]
+                mod._last_input_grad = ctx.needs_input_grad[1]
                 need_a, need_b = ctx.needs_input_grad[2 + 2 * i], ctx.needs_input_grad[3 + 2 * i]
                 dA, dB, ret_a, ret_b = mod._grad_buffers(need_a, need_b)
                 if dA is not None or dB is not None:
@@ -155,7 +181,7 @@ class _LoraGroupFn(torch.autograd.Function):
                 if ret_b is not None and ret_b.dtype != mod.lora_up.weight.dtype:
                     ret_b = ret_b.to(mod.lora_up.weight.dtype)
                 grads[2 * i], grads[2 * i + 1] = ret_a, ret_b
-            if ctx.needs_input_grad[1]:
+            if dxs is not None:
                 dx = dxs[0]
                 for d in dxs[1:]:
                     dx = dx + d
@@ -427,10 +453,14 @@ class LoRAModule(PeftBase):
         if type(om) not in (nn.Linear, nn.Conv2d) and type(om).__name__ in ("LinearNf4", "LinearFp8", "Linear4bit", "Linear8bitLt"):
             raise NotImplementedError(f"quantized base layer {type(om).__name__} is not supported by the fused LoRA kernel")
         if isinstance(om, nn.Conv2d):
-            if om.kernel_size != (1, 1) or om.stride != (1, 1) or om.padding not in ((0, 0), 0) or om.dilation != (1, 1) or om.groups != 1:
+            if om.groups != 1 or isinstance(om.padding, str) or om.padding_mode != "zeros":
                 raise NotImplementedError(
-                    "fused LoRA supports Linear and 1x1/stride-1/groups-1 Conv2d leaves; "
-                    f"got Conv2d(kernel={om.kernel_size}, stride={om.stride}, padding={om.padding}, groups={om.groups})")
+                    "fused LoRA supports Linear and groups-1, zero-padded Conv2d leaves; "
+                    f"got Conv2d(kernel={om.kernel_size}, padding={om.padding}, padding_mode={om.padding_mode}, groups={om.groups})")
+
+    @staticmethod
+    def _is_pointwise(om: nn.Conv2d) -> bool:
+        return om.kernel_size == (1, 1) and om.stride == (1, 1) and tuple(om.padding) == (0, 0)
 
     def initialize_weights(self):
         self._initialized = True
@@ -505,7 +535,17 @@ class LoRAModule(PeftBase):
         A, B = self.lora_down.weight, self.lora_up.weight
         if isinstance(om, nn.Conv2d):
             b_, c_, h_, w_ = x.shape
-            x2 = x.permute(0, 2, 3, 1).reshape(-1, c_)
+            if self._is_pointwise(om):
+                x2 = x.permute(0, 2, 3, 1).reshape(-1, c_)
+            else:
+                # k x k leaf (create_layer, reference :142-155): one row per output pixel, columns (c, ki, kj) in the
+                # order of weight.reshape(Cout, -1); base and down then share the row matrix like a Linear leaf.
+                # The rows are formed in bf16 (the kernel's operand type), so the 9x copy costs 2 B per element.
+                (kh, kw), (sh, sw), (ph, pw), (dh, dw) = om.kernel_size, om.stride, om.padding, om.dilation
+                h_ = (h_ + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+                w_ = (w_ + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+                cols = nn.functional.unfold(x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16), om.kernel_size, om.dilation, om.padding, om.stride)
+                x2 = cols.transpose(1, 2).reshape(-1, cols.shape[1])
         else:
             x2 = x.reshape(-1, x.shape[-1])
         self._last_rows = x2.shape[0]          # read by bench.py to replay the step's GEMM shapes

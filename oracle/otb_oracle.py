@@ -217,3 +217,35 @@ def lora_backward(x, dy, w, down, up, scale, round_bf16=True):
     dA = g.T @ x64
     dB = dy64.T @ t
     return dx.astype(np.float32), dA.astype(np.float32), dB.astype(np.float32)
+
+
+# ---- k x k convolution leaves as row/column matrices ---------------------------------------------
+def conv_rows(x, kernel, stride=(1, 1), padding=(0, 0), dilation=(1, 1)):
+    """NCHW -> one row per output pixel, columns ordered (c, ki, kj) like `weight.reshape(Cout, -1)`, zero padded:
+    the k x k leaves of LoRAModule.create_layer (LoRAModule.py:142-155) then read as the Linear arithmetic above."""
+    x = np.asarray(x)
+    Bn, Cc, H, W = x.shape
+    (kh, kw), (sh, sw), (ph, pw), (dh, dw) = kernel, stride, padding, dilation
+    Ho = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+    Wo = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+    xp = np.zeros((Bn, Cc, H + 2 * ph, W + 2 * pw), dtype=x.dtype)
+    xp[:, :, ph:ph + H, pw:pw + W] = x
+    rows = np.empty((Bn, Ho, Wo, Cc, kh, kw), dtype=x.dtype)
+    for i in range(kh):
+        for j in range(kw):
+            rows[:, :, :, :, i, j] = xp[:, :, i * dh:i * dh + sh * (Ho - 1) + 1:sh, j * dw:j * dw + sw * (Wo - 1) + 1:sw].transpose(0, 2, 3, 1)
+    return rows.reshape(Bn * Ho * Wo, Cc * kh * kw), (Ho, Wo)
+
+
+def conv_rows_adjoint(drows, xshape, kernel, stride=(1, 1), padding=(0, 0), dilation=(1, 1)):
+    """Transpose of conv_rows: scatter-add the row gradients back onto the NCHW input (fp64 accumulate)."""
+    Bn, Cc, H, W = xshape
+    (kh, kw), (sh, sw), (ph, pw), (dh, dw) = kernel, stride, padding, dilation
+    Ho = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+    Wo = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+    d = np.asarray(drows, dtype=np.float64).reshape(Bn, Ho, Wo, Cc, kh, kw)
+    dxp = np.zeros((Bn, Cc, H + 2 * ph, W + 2 * pw), dtype=np.float64)
+    for i in range(kh):
+        for j in range(kw):
+            dxp[:, :, i * dh:i * dh + sh * (Ho - 1) + 1:sh, j * dw:j * dw + sw * (Wo - 1) + 1:sw] += d[:, :, :, :, i, j].transpose(0, 3, 1, 2)
+    return dxp[:, :, ph:ph + H, pw:pw + W].astype(np.float32)

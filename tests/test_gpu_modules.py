@@ -63,16 +63,16 @@ class TorchLoRA(nn.Module):
         return self.base(x) + ld * self.scale
 
 
-@pytest.mark.parametrize("name", ["linear", "linear_nobias", "conv1x1"])
+@pytest.mark.parametrize("name", ["linear", "linear_nobias", "conv1x1", "conv3x3", "conv3x3_s2"])
 def test_lora_module_vs_reference_golden(P, dev, golden, name):
     """The reference's CPU fp32 forward/backward (config C1 arithmetic) vs the hooked fused module in bf16.
     Tolerance: inputs and weights are rounded to bf16 (2^-9 relative each) and the contraction runs over
-    K <= 72 terms: 2 bf16 ulp of the output magnitude + 1 % of the tensor's scale."""
+    K <= 216 terms: 2 bf16 ulp of the output magnitude + 1 % of the tensor's scale."""
     g = golden("lora")
     x = torch.from_numpy(g[f"{name}_x"]).to(dev)
     w, bias = torch.from_numpy(g[f"{name}_w"]), g[f"{name}_bias"]
-    if name == "conv1x1":
-        base = nn.Conv2d(w.shape[1], w.shape[0], 1, bias=bias.size > 0)
+    if name.startswith("conv"):
+        base = nn.Conv2d(w.shape[1], w.shape[0], w.shape[2], stride=2 if name.endswith("_s2") else 1, padding=w.shape[2] // 2, bias=bias.size > 0)
     else:
         base = nn.Linear(w.shape[1], w.shape[0], bias=bias.size > 0)
     with torch.no_grad():
@@ -107,9 +107,36 @@ def test_lora_module_vs_reference_golden(P, dev, golden, name):
     mod.remove_hook_from_module()
     with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
         y0 = base(x)
-    ref0 = nn.functional.conv2d(x.bfloat16(), base.weight.bfloat16(), base.bias.bfloat16() if bias.size else None) if name == "conv1x1" \
-        else nn.functional.linear(x.bfloat16(), base.weight.bfloat16(), base.bias.bfloat16() if bias.size else None)
+    ref0 = nn.functional.conv2d(x.bfloat16(), base.weight.bfloat16(), base.bias.bfloat16() if bias.size else None, base.stride, base.padding) \
+        if name.startswith("conv") else nn.functional.linear(x.bfloat16(), base.weight.bfloat16(), base.bias.bfloat16() if bias.size else None)
     assert torch.equal(y0, ref0)
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.25])
+def test_leaf_without_input_grad_skips_dx_and_keeps_dA_dB(P, dev, dropout):
+    """A leaf fed by a tensor that takes no gradient (context K/V): autograd forms no dX, and the fused path issues
+    only the Gs part of that launch.  dA / dB must equal the ones of the full launch (same Gs: same k order, same
+    dropout key) to within one bf16 ulp of Gs propagated through the fp32 dA sum."""
+    torch.manual_seed(5)
+    base = nn.Linear(256, 192).to(dev).to(torch.bfloat16).requires_grad_(False)
+    mod = P.L.LoRAModule("lora_unet.kv", base, 16, 8.0).to(dev)
+    mod.dropout.p = dropout
+    with torch.no_grad():
+        mod.lora_up.weight.normal_(0, 0.05)
+    mod.hook_to_module()
+    x = torch.randn(308, 256, device=dev).bfloat16()
+    dy = torch.randn(308, 192, device=dev).bfloat16()
+    out = {}
+    for needs in (True, False):
+        torch.cuda.manual_seed(11)                      # same dropout key for both passes
+        xin = x.clone().requires_grad_(needs)
+        y = base(xin)
+        grads = torch.autograd.grad(y, ([xin] if needs else []) + [mod.lora_down.weight, mod.lora_up.weight], dy)
+        out[needs] = grads[-2:]
+        assert mod._last_input_grad is needs
+    for full, cut, what in zip(out[True], out[False], ("dA", "dB")):
+        tol = 2.0 ** -8 * full.abs().max().item()      # (dB does not involve Gs: only the order of its fp32 reds differs)
+        assert (full - cut).abs().max().item() <= tol, what
 
 
 def test_fp32_compute_is_refused_not_emulated(P, dev):

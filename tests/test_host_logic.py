@@ -102,8 +102,14 @@ def test_wrapper_selects_leaves_by_substring_and_keeps_state_dict_keys(golden):
 
 def test_empty_filter_selects_everything_supported_and_unsupported_layers_raise():
     cfg = TrainConfig()
-    with pytest.raises(NotImplementedError, match="1x1"):
-        LoRAModuleWrapper(_net(), "lora_unet", cfg, [""])                   # "" matches the 3x3 conv too
+    w = LoRAModuleWrapper(_net(), "lora_unet", cfg, [""])                   # "" matches the 3x3 conv too (`full` preset)
+    k3 = w.lora_modules["attentions.0.conv3"]
+    assert tuple(k3.lora_down.weight.shape) == (cfg.lora_rank, 8, 3, 3) and tuple(k3.lora_up.weight.shape) == (8, cfg.lora_rank, 1, 1)
+    assert k3.lora_down.padding == (1, 1) and k3.lora_down.stride == (1, 1)
+    with pytest.raises(NotImplementedError, match="groups-1"):
+        LoRAModule("p", nn.Conv2d(8, 8, 3, padding=1, groups=2), 8, 1.0)
+    with pytest.raises(NotImplementedError, match="zero-padded"):
+        LoRAModule("p", nn.Conv2d(8, 8, 3, padding=1, padding_mode="reflect"), 8, 1.0)
     with pytest.raises(NotImplementedError):
         LoRAModuleWrapper(_net(), "lora_unet", TrainConfig(lora_decompose=True), ["to_q"])     # DoRA
     with pytest.raises(NotImplementedError):

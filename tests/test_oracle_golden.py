@@ -168,7 +168,10 @@ def test_losses_vs_reference(oracle, golden, name):
     np.testing.assert_allclose(grad, ref_grad, rtol=2e-5, atol=1e-6 * np.abs(ref_grad).max())
 
 
-@pytest.mark.parametrize("name", ["linear", "linear_nobias", "conv1x1"])
+CONV_GEOMETRY = {"conv3x3": dict(kernel=(3, 3), stride=(1, 1), padding=(1, 1)), "conv3x3_s2": dict(kernel=(3, 3), stride=(2, 2), padding=(1, 1))}
+
+
+@pytest.mark.parametrize("name", ["linear", "linear_nobias", "conv1x1", "conv3x3", "conv3x3_s2"])
 def test_lora_linear_vs_reference(oracle, golden, name):
     """LoRAModule.forward (LoRAModule.py:319-323) and its autograd backward on CPU fp32 (config C1's arithmetic).
     fp32 tolerance (north_star): 1e-3 relative; fp64-accumulated oracle lands within 1e-5."""
@@ -176,8 +179,13 @@ def test_lora_linear_vs_reference(oracle, golden, name):
     x, w, A, B, dy = g[f"{name}_x"], g[f"{name}_w"], g[f"{name}_A"], g[f"{name}_B"], g[f"{name}_dy"]
     bias = g[f"{name}_bias"]
     s = float(g[f"{name}_scale"][0])
-    if name == "conv1x1":      # NCHW 1x1 conv == Linear over pixels
-        to2d = lambda t: np.ascontiguousarray(t.transpose(0, 2, 3, 1).reshape(-1, t.shape[1]))  # noqa: E731
+    to2d = lambda t: np.ascontiguousarray(t.transpose(0, 2, 3, 1).reshape(-1, t.shape[1]))  # noqa: E731
+    geo = CONV_GEOMETRY.get(name)
+    if geo is not None:        # k x k conv == Linear over the unfolded patches (create_layer, LoRAModule.py:142-155)
+        x2, (ho, wo) = oracle.conv_rows(x, **geo)
+        assert (ho, wo) == dy.shape[2:]
+        dy2, y_ref, dx_ref = to2d(dy), to2d(g[f"{name}_y"]), None
+    elif name == "conv1x1":    # NCHW 1x1 conv == Linear over pixels
         x2, dy2, y_ref, dx_ref = to2d(x), to2d(dy), to2d(g[f"{name}_y"]), to2d(g[f"{name}_dx"])
     else:
         x2, dy2 = x.reshape(-1, x.shape[-1]), dy.reshape(-1, dy.shape[-1])
@@ -186,6 +194,8 @@ def test_lora_linear_vs_reference(oracle, golden, name):
     y, _ = oracle.lora_linear(x2, w2, A2, B2, bias if bias.size else None, s, round_t_bf16=False)
     np.testing.assert_allclose(y, y_ref, rtol=1e-5, atol=1e-5)
     dx, dA, dB = oracle.lora_backward(x2, dy2, w2, A2, B2, s, round_bf16=False)
+    if geo is not None:
+        dx, dx_ref = oracle.conv_rows_adjoint(dx, x.shape, **geo), g[f"{name}_dx"]
     np.testing.assert_allclose(dx, dx_ref, rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(dA, g[f"{name}_dA"].reshape(A2.shape), rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(dB, g[f"{name}_dB"].reshape(B2.shape), rtol=1e-5, atol=1e-5)

@@ -298,25 +298,33 @@ def gen_losses():
 # ------------------------------------------------------------------------------------ LoRA
 def gen_lora():
     out = {}
+
+    def run(cases):
+        for name, base, xshape in cases:
+            mod = LoRAModule("lora_unet.x", base, 16, 8.0)
+            torch.nn.init.normal_(mod.lora_up.weight, std=0.05)
+            base.requires_grad_(False)
+            mod.hook_to_module()
+            x = torch.randn(*xshape, requires_grad=True)
+            y = base(x)
+            dy = torch.randn_like(y)
+            dx, dA, dB = torch.autograd.grad(y, [x, mod.lora_down.weight, mod.lora_up.weight], dy)
+            out.update({f"{name}_x": x.detach().numpy(), f"{name}_w": base.weight.detach().numpy(),
+                        f"{name}_bias": base.bias.detach().numpy() if base.bias is not None else np.zeros(0, np.float32),
+                        f"{name}_A": mod.lora_down.weight.detach().numpy(), f"{name}_B": mod.lora_up.weight.detach().numpy(),
+                        f"{name}_y": y.detach().numpy(), f"{name}_dy": dy.numpy(), f"{name}_dx": dx.numpy(),
+                        f"{name}_dA": dA.numpy(), f"{name}_dB": dB.numpy(),
+                        f"{name}_scale": np.array([float(mod.alpha) / mod.rank])})
+            out[f"{name}_keys"] = np.array(sorted(mod.state_dict(prefix=mod.prefix).keys()))
+
     torch.manual_seed(21)
-    for name, base, xshape in (("linear", torch.nn.Linear(72, 40), (3, 10, 72)),
-                               ("linear_nobias", torch.nn.Linear(64, 48, bias=False), (5, 64)),
-                               ("conv1x1", torch.nn.Conv2d(24, 32, 1), (2, 24, 6, 6))):
-        mod = LoRAModule("lora_unet.x", base, 16, 8.0)
-        torch.nn.init.normal_(mod.lora_up.weight, std=0.05)
-        base.requires_grad_(False)
-        mod.hook_to_module()
-        x = torch.randn(*xshape, requires_grad=True)
-        y = base(x)
-        dy = torch.randn_like(y)
-        dx, dA, dB = torch.autograd.grad(y, [x, mod.lora_down.weight, mod.lora_up.weight], dy)
-        out.update({f"{name}_x": x.detach().numpy(), f"{name}_w": base.weight.detach().numpy(),
-                    f"{name}_bias": base.bias.detach().numpy() if base.bias is not None else np.zeros(0, np.float32),
-                    f"{name}_A": mod.lora_down.weight.detach().numpy(), f"{name}_B": mod.lora_up.weight.detach().numpy(),
-                    f"{name}_y": y.detach().numpy(), f"{name}_dy": dy.numpy(), f"{name}_dx": dx.numpy(),
-                    f"{name}_dA": dA.numpy(), f"{name}_dB": dB.numpy(),
-                    f"{name}_scale": np.array([float(mod.alpha) / mod.rank])})
-        out[f"{name}_keys"] = np.array(sorted(mod.state_dict(prefix=mod.prefix).keys()))
+    run((("linear", torch.nn.Linear(72, 40), (3, 10, 72)),
+         ("linear_nobias", torch.nn.Linear(64, 48, bias=False), (5, 64)),
+         ("conv1x1", torch.nn.Conv2d(24, 32, 1), (2, 24, 6, 6))))
+    # k x k leaves of the `full` preset (LoRAModule.py:142-155): own seed, so the fixtures above keep their draws
+    torch.manual_seed(22)
+    run((("conv3x3", torch.nn.Conv2d(24, 32, 3, padding=1), (2, 24, 6, 6)),
+         ("conv3x3_s2", torch.nn.Conv2d(16, 40, 3, stride=2, padding=1, bias=False), (2, 16, 9, 8))))
     np.savez(OUT / "lora.npz", **out)
 
 
@@ -337,7 +345,10 @@ def gen_clip():
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])              # e.g. `python tools/make_golden.py gen_lora` rewrites one fixture file
     for fn in (gen_schedule, gen_optimizer, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_clip):
+        if only and fn.__name__ not in only:
+            continue
         fn()
         print("wrote", fn.__name__)
     for f in sorted(OUT.glob("*.npz")):
