@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OTB_ABI_VERSION 2   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs */
+#define OTB_ABI_VERSION 3   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs.  3: otb_grad_exchange, otb_grad_norm_from_partials */
 
 /* error codes */
 #define OTB_OK            0
@@ -155,8 +155,44 @@ int otb_ema_multi(const otb_optim_launch* args, void* stream);
  * ---------------------------------------------------------------------------------- */
 int otb_grad_norm_multi(const otb_optim_launch* args, float max_norm, float grad_prescale,
                         float* partials, float* out_norm_coef, void* stream);
+/* the same finish step over squared-norm partials produced elsewhere (otb_grad_exchange) */
+int otb_grad_norm_from_partials(const float* partials, int32_t n_partials, float max_norm, float grad_prescale,
+                                float* out_norm_coef, void* stream);
 /* in-place g *= coef for callers that want the reference's two-pass behaviour */
 int otb_grad_scale_multi(const otb_optim_launch* args, const float* coef, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K-r  data-parallel gradient exchange fused with the squared gradient norm, over NVLink
+ *      peer memory ("one exchange step"; the reference has no multi-GPU
+ *      code, so this replaces what a DDP wrapper around GenericTrainer.py:692-714 would do
+ *      with ncclAllReduce + nn.utils.clip_grad_norm_'s norm pass).
+ * The flat fp32 gradient arena is symmetric memory: every replica is mapped into every
+ * process and (optionally) all of them as one NVLS multicast object.  Rank r sums slice r
+ * over all replicas (P2P loads in rank order, or multimem.ld_reduce inside the switch),
+ * accumulates (grad_prescale * sum)^2, and writes the sum back into every replica in place
+ * (P2P stores, or multimem.st); block partials of the squared norm land in
+ * float[world * blocks] on every rank (feed them to otb_grad_norm_from_partials).  Peer
+ * barriers on flag words (uint32[2 * OTB_MAX_RANKS] per rank, zero-initialised,
+ * peer-mapped) bracket the kernel; every rank must make the same call in the same order.
+ * No NCCL, no host sync; capturable in a CUDA graph.
+ * ---------------------------------------------------------------------------------- */
+#define OTB_MAX_RANKS 16
+#define OTB_EXCHANGE_P2P  0    /* world in {2, 4, 8}: (n-1)/n of the arena per NVLink direction   */
+#define OTB_EXCHANGE_NVLS 1    /* any world <= OTB_MAX_RANKS: (1 + 1/n) of the arena per direction */
+typedef struct otb_grad_exchange_args {
+    float*    peer_grads[OTB_MAX_RANKS];    /* arena of rank i as mapped into THIS process         */
+    float*    peer_partials[OTB_MAX_RANKS]; /* float[world * blocks] of rank i, likewise           */
+    uint32_t* peer_flags[OTB_MAX_RANKS];    /* flag words of rank i, likewise                      */
+    void*     mc_grads;                     /* NVLS only: multicast address of the arena           */
+    float*    mc_partials;                  /* NVLS only: multicast address of the partial table   */
+    int64_t   n_elems;                      /* floats in the arena, multiple of 4                  */
+    int32_t   rank, world;
+    int32_t   blocks;                       /* otb_grad_exchange_blocks(n_elems, world)            */
+    int32_t   mode;                         /* OTB_EXCHANGE_*                                      */
+    float     grad_prescale;                /* folded into the norm only; the arena holds the SUM  */
+} otb_grad_exchange_args;
+int otb_grad_exchange_blocks(int64_t n_elems, int32_t world);
+int otb_grad_exchange(const otb_grad_exchange_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * bf16 shadow refresh: for every LoRA tensor (fp32 or bf16 master, [rows, cols])
@@ -350,8 +386,8 @@ int otb_lora_grad_ab(const otb_lora_grad_args* args, void* stream);
 /* Utility used by tests and the data-parallel bucket path: fp32 <-> bf16 casts with
  * round-to-nearest-even, and a device-side Philox dump for known-answer tests. */
 /* sizeof() of every argument struct, in declaration order: optim_tensor, optim_launch, shadow_tensor,
- * noise_args, loss_args, lora_linear_args, lora_grad_args.  Bindings assert these at load time. */
-int otb_struct_sizes(int32_t* out7);
+ * noise_args, loss_args, lora_linear_args, lora_grad_args, grad_exchange_args.  Bindings assert these at load time. */
+int otb_struct_sizes(int32_t* out8);
 
 int otb_philox_dump(uint64_t seed, uint64_t offset, uint32_t stream_id, int64_t first_group,
                     int64_t n_groups, uint32_t* out4, void* stream);

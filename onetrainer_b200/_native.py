@@ -12,7 +12,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "libotb200.so"
 
 # ---- enums (include/otb200.h) ---------------------------------------------------------
-ABI_VERSION = 2          # include/otb200.h: OTB_ABI_VERSION
+ABI_VERSION = 3          # include/otb200.h: OTB_ABI_VERSION
 OTB_OK, OTB_EINVAL, OTB_EUNSUPPORTED, OTB_ECUDA, OTB_EARCH = 0, -1, -2, -3, -4
 F32, BF16, F16 = 0, 1, 2
 
@@ -120,6 +120,20 @@ class LoraGradArgs(C.Structure):
     ]
 
 
+MAX_RANKS = 16           # OTB_MAX_RANKS
+
+
+class GradExchangeArgs(C.Structure):
+    _fields_ = [
+        ("peer_grads", _vp * MAX_RANKS), ("peer_partials", _vp * MAX_RANKS), ("peer_flags", _vp * MAX_RANKS),
+        ("mc_grads", _vp), ("mc_partials", _vp), ("n_elems", _i64),
+        ("rank", _i32), ("world", _i32), ("blocks", _i32), ("mode", _i32), ("grad_prescale", _f32),
+    ]
+
+
+EXCHANGE_P2P, EXCHANGE_NVLS = 0, 1
+
+
 # every symbol include/otb200.h declares: (name, restype, argtypes)
 SYMBOLS = {
     "otb_last_error": (C.c_char_p, []),
@@ -128,7 +142,10 @@ SYMBOLS = {
     "otb_adamw_sr_ema_multi": (C.c_int, [C.POINTER(OptimLaunch), _vp]),
     "otb_ema_multi": (C.c_int, [C.POINTER(OptimLaunch), _vp]),
     "otb_grad_norm_multi": (C.c_int, [C.POINTER(OptimLaunch), _f32, _f32, _vp, _vp, _vp]),
+    "otb_grad_norm_from_partials": (C.c_int, [_vp, _i32, _f32, _f32, _vp, _vp]),
     "otb_grad_scale_multi": (C.c_int, [C.POINTER(OptimLaunch), _vp, _vp]),
+    "otb_grad_exchange_blocks": (C.c_int, [_i64, _i32]),
+    "otb_grad_exchange": (C.c_int, [C.POINTER(GradExchangeArgs), _vp]),
     "otb_shadow_refresh_multi": (C.c_int, [_vp, _i32, _i32, _vp]),
     "otb_noise_addnoise": (C.c_int, [C.POINTER(NoiseArgs), _vp]),
     "otb_loss_fwd_bwd": (C.c_int, [C.POINTER(LossArgs), _vp]),
@@ -140,7 +157,7 @@ SYMBOLS = {
     "otb_philox_dump": (C.c_int, [_u64, _u64, _u32, _i64, _i64, _vp, _vp]),
     "otb_struct_sizes": (C.c_int, [C.POINTER(C.c_int32)]),
 }
-_STRUCTS = (OptimTensor, OptimLaunch, ShadowTensor, NoiseArgs, LossArgs, LoraLinearArgs, LoraGradArgs)
+_STRUCTS = (OptimTensor, OptimLaunch, ShadowTensor, NoiseArgs, LossArgs, LoraLinearArgs, LoraGradArgs, GradExchangeArgs)
 
 _lib = None
 
@@ -161,7 +178,7 @@ def lib() -> C.CDLL:
             fn.argtypes = args
         if handle.otb_abi_version() != ABI_VERSION:
             raise RuntimeError(f"{LIB_PATH}: ABI version {handle.otb_abi_version()} != {ABI_VERSION}; rebuild the library")
-        sizes = (C.c_int32 * 7)()
+        sizes = (C.c_int32 * len(_STRUCTS))()
         handle.otb_struct_sizes(sizes)
         for got, st in zip(sizes, _STRUCTS):
             if got != C.sizeof(st):

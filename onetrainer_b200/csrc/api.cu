@@ -109,6 +109,7 @@ extern "C" int otb_struct_sizes(int32_t* out) {
     out[4] = (int32_t)sizeof(otb_loss_args);
     out[5] = (int32_t)sizeof(otb_lora_linear_args);
     out[6] = (int32_t)sizeof(otb_lora_grad_args);
+    out[7] = (int32_t)sizeof(otb_grad_exchange_args);
     return OTB_OK;
 }
 

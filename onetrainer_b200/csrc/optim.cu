@@ -479,6 +479,15 @@ extern "C" int otb_grad_norm_multi(const otb_optim_launch* a, float max_norm, fl
     return OTB_OK;
 }
 
+extern "C" int otb_grad_norm_from_partials(const float* partials, int32_t n_partials, float max_norm, float grad_prescale,
+                                           float* out, void* stream) {
+    OTB_CHECK_ARG(out != nullptr && partials != nullptr && n_partials > 0, "null output / partials");
+    OTB_BIND(out);
+    grad_norm_finish_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, n_partials, max_norm, grad_prescale, out);
+    OTB_LAUNCH_CHECK("grad_norm_finish_kernel");
+    return OTB_OK;
+}
+
 extern "C" int otb_grad_scale_multi(const otb_optim_launch* a, const float* coef, void* stream) {
     OTB_CHECK_ARG(coef != nullptr, "null coef");
     int c = check_launch(a);

@@ -68,14 +68,23 @@ class GradientBucket:
     def __init__(self, arena: torch.Tensor | None = None):
         self.arena = arena
         self._flat = None
+        self._exchange: GradExchange | None = None
+        self.norm_partials: torch.Tensor | None = None      # squared-norm partials of the last exchange (K-r path only)
 
     def allreduce(self, grads: list[torch.Tensor]) -> float:
         """Sum gradients over ranks in place.  Returns the prescale (1/world_size) to apply."""
         n = world_size()
+        self.norm_partials = None
         if n == 1:
             return 1.0
         if self.arena is not None and all(_is_view_of(g, self.arena) for g in grads):
-            dist.all_reduce(self.arena, op=dist.ReduceOp.SUM)
+            if is_symmetric(self.arena):
+                # K-r: reduce-scatter + all-gather + squared norm in one kernel over NVLink peer memory (csrc/exchange.cu)
+                if self._exchange is None:
+                    self._exchange = GradExchange(self.arena)
+                self.norm_partials = self._exchange.exchange(1.0 / n)
+            else:
+                dist.all_reduce(self.arena, op=dist.ReduceOp.SUM)
             return 1.0 / n
         total = sum(g.numel() for g in grads)
         if self._flat is None or self._flat.numel() != total or self._flat.dtype != grads[0].dtype:
@@ -88,6 +97,95 @@ class GradientBucket:
         dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
         torch._foreach_copy_(grads, views)
         return 1.0 / n
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# symmetric (peer-mapped + NVLS multicast) memory for the exchange kernel
+# ---------------------------------------------------------------------------------------------------------------
+_symmetric: dict[int, int] = {}        # data_ptr -> bytes of every live symmetric_zeros() allocation
+
+
+def peer_exchange_wanted() -> bool:
+    """OTB_PEER_EXCHANGE=0 keeps the LoRA gradient exchange on ncclAllReduce (A/B runs); default on for GPU ranks."""
+    return world_size() > 1 and torch.cuda.is_available() and os.environ.get("OTB_PEER_EXCHANGE", "1") != "0"
+
+
+def symmetric_zeros(numel: int, dtype: torch.dtype, device) -> torch.Tensor:
+    """A zero-filled flat buffer from torch's symmetric-memory allocator: the same allocation exists on every rank and,
+    after the rendezvous, is peer-mapped (NVLink loads/stores) and mapped as one NVLS multicast object.  Every rank
+    must allocate the same sizes in the same order.  Plumbing only: the kernels that use it are ours."""
+    import torch.distributed._symmetric_memory as symm
+    t = symm.empty(int(numel), dtype=dtype, device=torch.device(device))
+    t.zero_()
+    _symmetric[t.data_ptr()] = t.numel() * t.element_size()
+    return t
+
+
+def is_symmetric(t: torch.Tensor) -> bool:
+    return t.is_cuda and _symmetric.get(t.data_ptr(), 0) >= t.numel() * t.element_size()
+
+
+class GradExchange:
+    """Host side of K-r (include/otb200.h: otb_grad_exchange) for one flat fp32 gradient arena.
+
+    Construction is collective (three rendezvous + one barrier) and happens once, outside any graph capture;
+    `exchange()` is three launches on the current stream, capturable, and returns the squared-norm partials
+    (float[world * blocks], identical on every rank) for otb_grad_norm_from_partials.
+    mode: "p2p" (peer loads / stores; 2, 4 or 8 ranks) or "nvls" (multimem through the switch); default from
+    OTB_KR_MODE, else p2p where it is instantiated."""
+
+    def __init__(self, arena: torch.Tensor, group=None, mode: str | None = None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _native as N
+        if arena.dtype != torch.float32 or arena.numel() % 4 != 0 or not is_symmetric(arena):
+            raise ValueError("GradExchange: the arena must be a symmetric_zeros() fp32 buffer with a multiple of 4 elements")
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("GradExchange: the rendezvous cannot be captured; run one eager step first")
+        group = group if group is not None else dist.group.WORLD
+        rk, ws = dist.get_rank(group), dist.get_world_size(group)
+        if not 2 <= ws <= N.MAX_RANKS:
+            raise ValueError(f"GradExchange: world size {ws} outside 2..{N.MAX_RANKS}")
+        mode = mode or os.environ.get("OTB_KR_MODE") or ("p2p" if ws in (2, 4, 8) else "nvls")
+        if mode not in ("p2p", "nvls"):
+            raise ValueError(f"GradExchange: unknown mode {mode!r}")
+        dev = arena.device
+        self.arena, self.mode = arena, mode
+        self.blocks = int(N.lib().otb_grad_exchange_blocks(arena.numel(), ws))
+        self.partials = symmetric_zeros(ws * self.blocks, torch.float32, dev)
+        self.flags = symmetric_zeros(2 * N.MAX_RANKS, torch.int32, dev)
+        tensors = (arena, self.partials, self.flags)
+        handles = [symm.rendezvous(t, group) for t in tensors]
+
+        def peers(t, h):
+            arr = (C.c_void_p * N.MAX_RANKS)()
+            for r in range(ws):
+                arr[r] = h.buffer_ptrs[r] + (t.data_ptr() - h.buffer_ptrs[rk])
+            return arr
+
+        def multicast(t, h):
+            if mode != "nvls":
+                return None
+            if not h.multicast_ptr:
+                raise RuntimeError("GradExchange: this allocation has no NVLS multicast mapping (no NVSwitch multicast support "
+                                   "on this node); use OTB_KR_MODE=p2p, or OTB_PEER_EXCHANGE=0 for ncclAllReduce")
+            return h.multicast_ptr + (t.data_ptr() - h.buffer_ptrs[rk])
+
+        self._handles = handles                     # keep the mappings alive
+        self._args = N.GradExchangeArgs(
+            peer_grads=peers(arena, handles[0]), peer_partials=peers(self.partials, handles[1]), peer_flags=peers(self.flags, handles[2]),
+            mc_grads=multicast(arena, handles[0]), mc_partials=multicast(self.partials, handles[1]), n_elems=arena.numel(),
+            rank=rk, world=ws, blocks=self.blocks, mode=N.EXCHANGE_NVLS if mode == "nvls" else N.EXCHANGE_P2P, grad_prescale=1.0)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)                         # every rank's flag words are zero before anyone raises one
+
+    def exchange(self, grad_prescale: float) -> torch.Tensor:
+        import ctypes as C
+        from . import _native as N, ops
+        self._args.grad_prescale = float(grad_prescale)
+        N.check(N.lib().otb_grad_exchange(C.byref(self._args), ops._stream()), "otb_grad_exchange")
+        ops._count(3)
+        return self.partials
 
 
 class FlatGradArena:

@@ -15,7 +15,7 @@ from torch import nn
 from .. import dp, step_state
 from ..rng import PhiloxKey
 from ..modules.module.EMAModule import EMAModuleWrapper
-from ..modules.module.LoRAModule import LoRAModuleWrapper
+from ..modules.module.LoRAModule import GradArena, LoRAModuleWrapper
 from ..modules.modelSetup.mixin.ModelSetupDiffusionLossMixin import ModelSetupDiffusionLossMixin
 from ..modules.modelSetup.mixin.ModelSetupDiffusionMixin import ModelSetupDiffusionMixin
 from ..modules.modelSetup.mixin.ModelSetupFlowMatchingMixin import ModelSetupFlowMatchingMixin
@@ -209,6 +209,7 @@ def build_flux_model(kind: str, config, device, *, train_dtype=torch.bfloat16, l
     net.requires_grad_(False)
     net.train()
     model = StandInFluxModel(net, standin.StandInFlowScheduler(1000, device), train_dtype)
+    GradArena.allocator = dp.symmetric_zeros if dp.peer_exchange_wanted() else None    # K-r needs a peer-mapped arena
     model.unet_lora = model.transformer_lora = LoRAModuleWrapper(net, "lora_transformer", config, ["attn", "ff.net"])
     model.unet_lora.set_dropout(config.dropout_probability)
     model.unet_lora.to(dtype=lora_weight_dtype)
@@ -255,6 +256,7 @@ def build_model(kind: str, config, device, *, train_dtype=torch.bfloat16, lora_w
                     ema_step_fn=(lambda: progress.global_step // config.gradient_accumulation_steps) if (ema and fused_ema) else None,
                     clip_grad_norm=config.clip_grad_norm if fused_clip else None)
         return model, DiffusionSetup(torch.device(device))
+    GradArena.allocator = dp.symmetric_zeros if dp.peer_exchange_wanted() else None    # K-r needs a peer-mapped arena
     model.unet_lora = LoRAModuleWrapper(unet, "lora_unet", config, ["attentions"])
     model.unet_lora.set_dropout(config.dropout_probability)
     model.unet_lora.to(dtype=lora_weight_dtype)
@@ -340,6 +342,7 @@ def train_step(setup: DiffusionSetup, model: StandInModel, batch: dict, config, 
         arena = model.unet_lora.grad_arena if model.unet_lora is not None else getattr(model, "full_grad_arena", None)
         bucket = bucket or dp.GradientBucket(arena.flat if isinstance(arena, dp.FlatGradArena) else arena)
         driver.grad_prescale = bucket.allreduce([p.grad for p in model.parameters if p.grad is not None])
+        driver.norm_partials = bucket.norm_partials
     if config.clip_grad_norm is not None and driver.clip_max_norm is None:
         from ..modules.util.grad_clip import clip_grad_norm_
         clip_grad_norm_(model.parameters, config.clip_grad_norm, driver.grad_prescale)
@@ -446,6 +449,7 @@ class GraphedTrainStep:
             if self.bucket.arena is None:
                 self.bucket.arena = model.unet_lora.grad_arena if model.unet_lora is not None else model.full_grad_arena.flat
             self.driver.grad_prescale = self.bucket.allreduce([p.grad for p in model.parameters if p.grad is not None])
+            self.driver.norm_partials = self.bucket.norm_partials
         if first:
             self.driver.host_prepare()              # discovers the gradients, builds the table, fills the scalars
             self.state.upload()                     # the optimizer's dynamic words were written just now

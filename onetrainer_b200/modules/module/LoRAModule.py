@@ -45,6 +45,8 @@ class GradArena:
     allreduce then runs in place on the arena with no gather/scatter (onetrainer_b200/dp.py).
     """
 
+    allocator = None        # (numel, dtype, device) -> zeroed flat tensor; dp.symmetric_zeros under data parallelism
+
     def __init__(self, shapes: list[tuple[int, ...]], device):
         total = 0
         self.offsets = []
@@ -52,7 +54,9 @@ class GradArena:
             n = math.prod(s)
             self.offsets.append((total, n, s))
             total += (n + 3) // 4 * 4           # keep every slice 16-byte aligned
-        self.flat = torch.zeros((max(total, 1),), dtype=torch.float32, device=device)
+        total = max(total, 4)
+        self.flat = GradArena.allocator(total, torch.float32, device) if GradArena.allocator is not None \
+            else torch.zeros((total,), dtype=torch.float32, device=device)
         self.generation = 0
 
     def view(self, i: int) -> Tensor:

@@ -55,6 +55,7 @@ class FusedAdamDriver:
         self.ema_step_fn = None         # () -> optimization_step the trainer will pass to ema.step
         self.clip_max_norm: float | None = None
         self.grad_prescale = 1.0        # 1/world_size under data parallel
+        self.norm_partials = None       # squared-norm partials of ALL active gradients, when the exchange kernel made them
         self.post_step_hooks = []       # e.g. LoRAModuleWrapper.refresh_shadows
         self.step_count = 0             # SR Philox offset
         self.last_norm_coef: torch.Tensor | None = None
@@ -179,7 +180,10 @@ class FusedAdamDriver:
             table.upload()
         clip = None
         if self.clip_max_norm is not None:
-            self.last_norm_coef = ops.grad_norm_multi(table, self.clip_max_norm, self.grad_prescale)
+            if self.norm_partials is not None:     # the data-parallel exchange kernel already accumulated the squared norm
+                self.last_norm_coef = ops.grad_norm_from_partials(table, self.norm_partials, self.clip_max_norm, self.grad_prescale)
+            else:
+                self.last_norm_coef = ops.grad_norm_multi(table, self.clip_max_norm, self.grad_prescale)
             clip = self.last_norm_coef[1:2]
         elif self.grad_prescale != 1.0:                         # data parallel without clipping: g * 1/n only
             if self._prescale_dev is None or self._prescale_val != self.grad_prescale:

@@ -499,6 +499,15 @@ def grad_norm_multi(table: OptimTable, max_norm: float, grad_prescale: float = 1
     return table.norm_coef
 
 
+def grad_norm_from_partials(table: OptimTable, partials: torch.Tensor, max_norm: float, grad_prescale: float = 1.0) -> torch.Tensor:
+    """[total_norm, clip_coef] from squared-norm partials another kernel produced (the NVLS gradient exchange)."""
+    N.require_cuda(partials)
+    N.check(N.lib().otb_grad_norm_from_partials(partials.data_ptr(), partials.numel(), float(max_norm), float(grad_prescale),
+                                                table.norm_coef.data_ptr(), _stream()), "otb_grad_norm_from_partials")
+    _count()
+    return table.norm_coef
+
+
 def grad_scale_multi(table: OptimTable, coef: torch.Tensor) -> None:
     a = table.launch_args()
     N.check(N.lib().otb_grad_scale_multi(C.byref(a), coef.data_ptr(), _stream()), "otb_grad_scale_multi")

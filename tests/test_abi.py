@@ -31,10 +31,10 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header():
     from onetrainer_b200 import _native as N
-    sizes = (C.c_int32 * 7)()
+    sizes = (C.c_int32 * len(N._STRUCTS))()
     assert N.lib().otb_struct_sizes(sizes) == 0
     assert [int(s) for s in sizes] == [C.sizeof(s) for s in N._STRUCTS]
-    assert N.lib().otb_abi_version() == N.ABI_VERSION == 2
+    assert N.lib().otb_abi_version() == N.ABI_VERSION == 3
 
 
 def test_flavor_constants_agree_across_header_binding_and_oracle():
