@@ -132,7 +132,7 @@ class GradExchange:
     `exchange()` is three launches on the current stream, capturable, and returns the squared-norm partials
     (float[world * blocks], identical on every rank) for otb_grad_norm_from_partials.
     mode: "p2p" (peer loads / stores; 2, 4 or 8 ranks) or "nvls" (multimem through the switch); default from
-    OTB_KR_MODE, else p2p where it is instantiated."""
+    OTB_KR_MODE, else the faster one measured for the world size (p2p on 2 ranks, nvls from 4)."""
 
     def __init__(self, arena: torch.Tensor, group=None, mode: str | None = None):
         import ctypes as C
@@ -146,7 +146,9 @@ class GradExchange:
         rk, ws = dist.get_rank(group), dist.get_world_size(group)
         if not 2 <= ws <= N.MAX_RANKS:
             raise ValueError(f"GradExchange: world size {ws} outside 2..{N.MAX_RANKS}")
-        mode = mode or os.environ.get("OTB_KR_MODE") or ("p2p" if ws in (2, 4, 8) else "nvls")
+        # measured on B200 / NVSwitch, 340 MB arena (profiles/r01d_logs/nvls_check*.log): 2 ranks p2p 524 us, nvls 889 us,
+        # ncclAllReduce 650 us; 4 ranks 806 / 780 / 855 us; 8 ranks 961 / 757 / 885 us
+        mode = mode or os.environ.get("OTB_KR_MODE") or ("p2p" if ws == 2 else "nvls")
         if mode not in ("p2p", "nvls"):
             raise ValueError(f"GradExchange: unknown mode {mode!r}")
         dev = arena.device
