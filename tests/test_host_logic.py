@@ -259,3 +259,22 @@ def test_flux_standin_has_the_reference_leaf_set():
     assert not any("ff_context" in n or "norm" in n for n in names)
     params = sum(16 * (m.in_features + m.out_features) for n, m in net.named_modules() if n in set(names))
     assert params == 35_487_744
+
+
+@pytest.mark.parametrize("name", ["cos_map", "cos_map_range_shift3", "sigmoid"])
+def test_multinomial_timestep_distributions_vs_reference(golden, name):
+    """COS_MAP / SIGMOID (ModelSetupNoiseMixin.py:122-153) stay on torch ops over B elements: with the reference's own
+    CPU generator stream the samples and the cached weight table must be the reference's."""
+    from onetrainer_b200.modules.modelSetup.mixin.ModelSetupNoiseMixin import ModelSetupNoiseMixin
+
+    class S(ModelSetupNoiseMixin):
+        pass
+
+    g = golden("timesteps")
+    lo, hi, weight, bias, shift, _, seed, _ = g[f"{name}_cfg"]
+    cfg = TrainConfig(timestep_distribution=TimestepDistribution.SIGMOID if name == "sigmoid" else TimestepDistribution.COS_MAP,
+                      min_noising_strength=lo, max_noising_strength=hi, noising_weight=weight, noising_bias=bias, timestep_shift=shift)
+    s = S()
+    t = s._get_timestep_discrete(1000, False, torch.Generator().manual_seed(int(seed)), 64, cfg)
+    assert t.dtype == torch.int32 and t.tolist() == g[f"{name}_t"].tolist()
+    np.testing.assert_allclose(s._ModelSetupNoiseMixin__weights.numpy(), g[f"{name}_weights"], rtol=1e-6)

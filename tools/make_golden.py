@@ -197,6 +197,21 @@ def gen_timesteps():
         out[f"{name}_t"] = ts.numpy().astype(np.int32)
         out[f"{name}_cfg"] = np.array([cfg.min_noising_strength, cfg.max_noising_strength, cfg.noising_weight, cfg.noising_bias,
                                        cfg.timestep_shift, float(cfg.dynamic_timestep_shifting), seed, offset], dtype=np.float64)
+    # COS_MAP / SIGMOID: a multinomial over a cached weight table (ModelSetupNoiseMixin.py:122-153).  torch's own CPU
+    # generator draws (the repo keeps this distribution on torch ops too), so the samples themselves are pinned
+    for name, dist, kw in (("cos_map", TimestepDistribution.COS_MAP, dict()),
+                           ("cos_map_range_shift3", TimestepDistribution.COS_MAP, dict(min_noising_strength=0.1, max_noising_strength=0.9, timestep_shift=3.0)),
+                           ("sigmoid", TimestepDistribution.SIGMOID, dict(noising_weight=2.0, noising_bias=0.1, timestep_shift=2.0))):
+        cfg = TrainConfig.default_values()
+        cfg.timestep_distribution = dist
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        mix = _Noise()
+        ts = mix._get_timestep_discrete(1000, False, torch.Generator().manual_seed(5), B, cfg)
+        out[f"{name}_t"] = ts.numpy().astype(np.int32)
+        out[f"{name}_weights"] = mix._ModelSetupNoiseMixin__weights.numpy()
+        out[f"{name}_cfg"] = np.array([cfg.min_noising_strength, cfg.max_noising_strength, cfg.noising_weight, cfg.noising_bias,
+                                       cfg.timestep_shift, 0.0, 5, 0], dtype=np.float64)
     det = _Noise()._get_timestep_discrete(1000, True, torch.Generator(), 4, TrainConfig.default_values())
     out["deterministic_t"] = det.numpy()
     np.savez(OUT / "timesteps.npz", **out)
