@@ -249,3 +249,30 @@ def conv_rows_adjoint(drows, xshape, kernel, stride=(1, 1), padding=(0, 0), dila
         for j in range(kw):
             dxp[:, :, i * dh:i * dh + sh * (Ho - 1) + 1:sh, j * dw:j * dw + sw * (Wo - 1) + 1:sw] += d[:, :, :, :, i, j].transpose(0, 3, 1, 2)
     return dxp[:, :, ph:ph + H, pw:pw + W].astype(np.float32)
+
+
+# ---- DoRA (oracle ahead of the kernel: the fused path still raises for it) -----------------------
+def dora(x2, dy2, w, down, up, m, bias, scale, norm_epsilon=False, decompose_output_axis=False):
+    """DoRAModule.forward (LoRAModule.py:385-419) and its backward with the norm detached (:396-400), fp64 accumulate.
+    x2 / dy2 are row matrices ([M, Cin*kh*kw] via conv_rows for a conv leaf, [M, Cout]); w, down, up, m keep the module's
+    own shapes.  Returns y2, dx2, d_down, d_up, d_m."""
+    w64 = np.asarray(w, dtype=np.float64)
+    a2 = np.asarray(down, dtype=np.float64).reshape(down.shape[0], -1)
+    b2 = np.asarray(up, dtype=np.float64).reshape(up.shape[0], -1)
+    x64, dy64, m64 = (np.asarray(t, dtype=np.float64) for t in (x2, dy2, m))
+    v = w64 + scale * (b2 @ a2).reshape(w64.shape)                       # make_weight(A, B) * alpha / rank  (:76-91, :389)
+    axes = tuple(range(1, v.ndim)) if decompose_output_axis else (0,) + tuple(range(2, v.ndim))
+    norm = np.sqrt((v * v).sum(axis=axes, keepdims=True)) + (float(np.finfo(np.float32).eps) if norm_epsilon else 0.0)
+    wp = m64 * (v / norm)
+    wp2 = wp.reshape(w64.shape[0], -1)
+    y = x64 @ wp2.T
+    if bias is not None and np.size(bias):
+        y = y + np.asarray(bias, dtype=np.float64)
+    g = (dy64.T @ x64).reshape(w64.shape)                                # dL/dWP
+    d_m = (g * v / norm).sum(axis=axes, keepdims=True)
+    dv2 = (g * m64 / norm).reshape(w64.shape[0], -1)                     # the norm is a constant for backpropagation
+    d_up = scale * (dv2 @ a2.T)
+    d_down = scale * (b2.T @ dv2)
+    dx = dy64 @ wp2
+    f32 = lambda t: t.astype(np.float32)  # noqa: E731
+    return f32(y), f32(dx), f32(d_down).reshape(down.shape), f32(d_up).reshape(up.shape), f32(d_m)

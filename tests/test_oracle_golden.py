@@ -201,6 +201,32 @@ def test_lora_linear_vs_reference(oracle, golden, name):
     np.testing.assert_allclose(dB, g[f"{name}_dB"].reshape(B2.shape), rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("name", ["linear", "linear_outaxis_eps", "conv3x3"])
+def test_dora_vs_reference(oracle, golden, name):
+    """DoRAModule.forward (LoRAModule.py:385-419) + autograd backward, CPU fp32.  Oracle only: the fused path raises for
+    DoRA until its kernel exists; this pins the restatement that kernel will be checked against."""
+    g = golden("dora")
+    x, dy = g[f"{name}_x"], g[f"{name}_dy"]
+    eps_flag, out_axis = (bool(v) for v in g[f"{name}_flags"])
+    to2d = lambda t: np.ascontiguousarray(t.transpose(0, 2, 3, 1).reshape(-1, t.shape[1]))  # noqa: E731
+    geo = dict(kernel=(3, 3), stride=(1, 1), padding=(1, 1)) if name == "conv3x3" else None
+    if geo is not None:
+        x2, _ = oracle.conv_rows(x, **geo)
+        dy2, y_ref = to2d(dy), to2d(g[f"{name}_y"])
+    else:
+        x2, dy2 = x.reshape(-1, x.shape[-1]), dy.reshape(-1, dy.shape[-1])
+        y_ref = g[f"{name}_y"].reshape(dy2.shape)
+    y, dx, dA, dB, dm = oracle.dora(x2, dy2, g[f"{name}_w"], g[f"{name}_A"], g[f"{name}_B"], g[f"{name}_m"], g[f"{name}_bias"],
+                                    float(g[f"{name}_scale"][0]), norm_epsilon=eps_flag, decompose_output_axis=out_axis)
+    dx = oracle.conv_rows_adjoint(dx, x.shape, **geo) if geo is not None else dx.reshape(x.shape)
+    np.testing.assert_allclose(y, y_ref, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dx, g[f"{name}_dx"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dA, g[f"{name}_dA"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(dB, g[f"{name}_dB"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(dm, g[f"{name}_dm"], rtol=1e-4, atol=1e-5)
+    assert list(g[f"{name}_keys"]) == ["lora_unet.x.alpha", "lora_unet.x.dora_scale", "lora_unet.x.lora_down.weight", "lora_unet.x.lora_up.weight"]
+
+
 @pytest.mark.parametrize("tag", ["big", "small"])
 def test_clip_grad_norm_vs_torch(oracle, golden, tag):
     """nn.utils.clip_grad_norm_(params, 1.0) as called at GenericTrainer.py:712-713."""

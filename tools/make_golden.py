@@ -46,7 +46,7 @@ from modules.modelSetup.mixin.ModelSetupDiffusionMixin import ModelSetupDiffusio
 from modules.modelSetup.mixin.ModelSetupFlowMatchingMixin import ModelSetupFlowMatchingMixin  # noqa: E402
 from modules.modelSetup.mixin.ModelSetupNoiseMixin import ModelSetupNoiseMixin  # noqa: E402
 from modules.module.EMAModule import EMAModuleWrapper  # noqa: E402
-from modules.module.LoRAModule import LoRAModule  # noqa: E402
+from modules.module.LoRAModule import DoRAModule, LoRAModule  # noqa: E402
 from modules.util.bf16_stochastic_rounding import copy_stochastic_  # noqa: E402,F401
 from modules.util.config.TrainConfig import TrainConfig  # noqa: E402
 from modules.util.convert.rescale_noise_scheduler_to_zero_terminal_snr import rescale_noise_scheduler_to_zero_terminal_snr  # noqa: E402
@@ -343,6 +343,37 @@ def gen_lora():
     np.savez(OUT / "lora.npz", **out)
 
 
+# ------------------------------------------------------------------------------------ DoRA (oracle only so far)
+def gen_dora():
+    """DoRAModule.forward (LoRAModule.py:385-419) and its autograd backward, CPU fp32.  Pins the ORACLE's restatement;
+    the fused path still raises for DoRA."""
+    out = {}
+    torch.manual_seed(41)
+    for name, base, xshape, kw in (("linear", torch.nn.Linear(48, 40), (3, 7, 48), dict()),
+                                   ("linear_outaxis_eps", torch.nn.Linear(32, 24, bias=False), (5, 32), dict(norm_epsilon=True, decompose_output_axis=True)),
+                                   ("conv3x3", torch.nn.Conv2d(8, 16, 3, padding=1), (2, 8, 5, 5), dict())):
+        mod = DoRAModule("lora_unet.x", base, 8, 4.0, train_device=torch.device("cpu"), **kw)
+        torch.nn.init.normal_(mod.lora_up.weight, std=0.05)
+        with torch.no_grad():
+            mod.dora_scale.mul_(1.0 + 0.1 * torch.randn_like(mod.dora_scale))
+        base.requires_grad_(False)
+        mod.hook_to_module()
+        x = torch.randn(*xshape, requires_grad=True)
+        y = base(x)
+        dy = torch.randn_like(y)
+        dx, dA, dB, dm = torch.autograd.grad(y, [x, mod.lora_down.weight, mod.lora_up.weight, mod.dora_scale], dy)
+        out.update({f"{name}_x": x.detach().numpy(), f"{name}_w": base.weight.detach().numpy(),
+                    f"{name}_bias": base.bias.detach().numpy() if base.bias is not None else np.zeros(0, np.float32),
+                    f"{name}_A": mod.lora_down.weight.detach().numpy(), f"{name}_B": mod.lora_up.weight.detach().numpy(),
+                    f"{name}_m": mod.dora_scale.detach().numpy(),
+                    f"{name}_y": y.detach().numpy(), f"{name}_dy": dy.numpy(), f"{name}_dx": dx.numpy(),
+                    f"{name}_dA": dA.numpy(), f"{name}_dB": dB.numpy(), f"{name}_dm": dm.numpy(),
+                    f"{name}_scale": np.array([float(mod.alpha) / mod.rank]),
+                    f"{name}_flags": np.array([int(kw.get("norm_epsilon", False)), int(kw.get("decompose_output_axis", False))])})
+        out[f"{name}_keys"] = np.array(sorted(mod.state_dict(prefix=mod.prefix).keys()))
+    np.savez(OUT / "dora.npz", **out)
+
+
 # ------------------------------------------------------------------------------------ clip
 def gen_clip():
     g = torch.Generator().manual_seed(31)
@@ -361,7 +392,7 @@ def gen_clip():
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])              # e.g. `python tools/make_golden.py gen_lora` rewrites one fixture file
-    for fn in (gen_schedule, gen_optimizer, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_clip):
+    for fn in (gen_schedule, gen_optimizer, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_dora, gen_clip):
         if only and fn.__name__ not in only:
             continue
         fn()
