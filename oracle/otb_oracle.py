@@ -276,3 +276,64 @@ def dora(x2, dy2, w, down, up, m, bias, scale, norm_epsilon=False, decompose_out
     dx = dy64 @ wp2
     f32 = lambda t: t.astype(np.float32)  # noqa: E731
     return f32(y), f32(dx), f32(d_down).reshape(down.shape), f32(d_up).reshape(up.shape), f32(d_m)
+
+
+# ---- Adafactor (oracle ahead of the kernel: the fused optimizer covers AdamW / Adam) -------------
+def adafactor_step(p, grad, state, *, lr=None, eps=(1e-30, 1e-3), clip_threshold=1.0, decay_rate=-0.8, beta1=None,
+                   weight_decay=0.0, scale_parameter=True, relative_step=True, warmup_init=False, bf16=False):
+    """One step_adafactor_parameter (adafactor_extensions.py:17-93) over transformers' Adafactor helpers (_get_lr,
+    _rms, _approx_sq_grad; transformers pinned by requirements-global.txt).  `p` / `grad` are fp32 arrays holding the
+    tensor's values (bf16 tensors: the widened values, `bf16=True`); `state` is the per-tensor dict, {} before the first
+    step.  Elementwise work in fp32 like the reference, reductions accumulated in fp64.  Returns the new parameter.
+    The reference's bf16 tail overwrites copy_stochastic_'s result with p.copy_(fp32) (:88-91), i.e. round-to-nearest
+    whether or not stochastic rounding is on; that is what this does."""
+    f32 = np.float32
+    p32 = np.asarray(p, dtype=f32).copy()
+    g = np.asarray(grad, dtype=f32)
+    factored, use_first_moment = g.ndim >= 2, beta1 is not None                       # _get_options
+    if not state:
+        state["step"] = 0
+        if use_first_moment:
+            state["exp_avg"] = np.zeros_like(g)
+        if factored:
+            state["exp_avg_sq_row"] = np.zeros(g.shape[:-1], dtype=f32)
+            state["exp_avg_sq_col"] = np.zeros(g.shape[:-2] + g.shape[-1:], dtype=f32)
+        else:
+            state["exp_avg_sq"] = np.zeros_like(g)
+    rms = lambda t: f32(np.sqrt((t.astype(np.float64) ** 2).sum()) / (t.size ** 0.5))  # noqa: E731  (_rms)
+    mean = lambda t, axis, keep=False: (t.astype(np.float64).mean(axis=axis, keepdims=keep)).astype(f32)  # noqa: E731
+    state["step"] += 1
+    state["RMS"] = rms(p32)
+    step_size = lr                                                                     # _get_lr
+    if relative_step:
+        min_step = 1e-6 * state["step"] if warmup_init else 1e-2
+        step_size = min(min_step, 1.0 / math.sqrt(state["step"]))
+    param_scale = max(eps[1], float(state["RMS"])) if scale_parameter else 1.0
+    lr_t = f32(param_scale * step_size)
+    beta2t = 1.0 - math.pow(state["step"], decay_rate)
+    update = g * g + f32(eps[0])
+    if factored:
+        row, col = state["exp_avg_sq_row"], state["exp_avg_sq_col"]
+        row *= f32(beta2t)
+        row += f32(1.0 - beta2t) * mean(update, -1)
+        col *= f32(beta2t)
+        col += f32(1.0 - beta2t) * mean(update, -2)
+        r_factor = (f32(1.0) / np.sqrt(row / mean(row, -1, keep=True)))[..., None]     # _approx_sq_grad
+        c_factor = (f32(1.0) / np.sqrt(col))[..., None, :]
+        update = (r_factor * c_factor) * g
+    else:
+        v = state["exp_avg_sq"]
+        v *= f32(beta2t)
+        v += f32(1.0 - beta2t) * update
+        update = (f32(1.0) / np.sqrt(v)) * g
+    update = update / max(f32(rms(update) / f32(clip_threshold)), f32(1.0))
+    update = update * lr_t
+    if use_first_moment:
+        m = state["exp_avg"]
+        m *= f32(beta1)
+        m += f32(1.0 - beta1) * update
+        update = m
+    if weight_decay != 0:
+        p32 = p32 + p32 * f32(-weight_decay * float(lr_t))
+    p32 = p32 - update
+    return bf16_bits_to_f32(f32_to_bf16_bits(p32)) if bf16 else p32

@@ -227,6 +227,36 @@ def test_dora_vs_reference(oracle, golden, name):
     assert list(g[f"{name}_keys"]) == ["lora_unet.x.alpha", "lora_unet.x.dora_scale", "lora_unet.x.lora_down.weight", "lora_unet.x.lora_up.weight"]
 
 
+@pytest.mark.parametrize("name", ["matrix_f32_relative", "vector_f32_relative", "matrix_f32_fixed_lr_beta1_wd", "conv_f32_warmup", "matrix_bf16_sr"])
+def test_adafactor_vs_reference(oracle, golden, name):
+    """step_adafactor_parameter (adafactor_extensions.py:17-93), three steps.  Oracle only: the fused optimizer kernel
+    covers AdamW / Adam.  fp32 elementwise + fp64 reductions against torch's fp32 reductions:
+    1e-5 relative on the parameter and the factored states; the bf16 case may differ by one bf16 ulp where the fp32
+    value sits on a rounding boundary."""
+    g = golden("adafactor")
+    lr, eps0, eps1, clip, decay, beta1, wd, scale_p, rel, warm = g[f"{name}_meta"]
+    kw = dict(lr=None if np.isnan(lr) else float(lr), eps=(float(eps0), float(eps1)), clip_threshold=float(clip), decay_rate=float(decay),
+              beta1=None if np.isnan(beta1) else float(beta1), weight_decay=float(wd), scale_parameter=bool(scale_p),
+              relative_step=bool(rel), warmup_init=bool(warm))
+    bf16 = name.endswith("bf16_sr")
+    dec = (lambda a: oracle.bf16_bits_to_f32(a)) if bf16 else (lambda a: a)
+    p, state = dec(g[f"{name}_p0"]), {}
+    for step in (1, 2, 3):
+        p = oracle.adafactor_step(p, dec(g[f"{name}_g{step}"]), state, bf16=bf16, **kw)
+        ref = dec(g[f"{name}_p{step}"])
+        if bf16:
+            ulp = np.abs(ref) * 2.0 ** -7
+            assert (np.abs(p - ref) <= ulp).all() and (p != ref).mean() < 0.02
+            p = ref                                    # continue from the reference's values: boundary cases do not compound
+        else:
+            np.testing.assert_allclose(p, ref, rtol=1e-5, atol=1e-8)
+        np.testing.assert_allclose(float(state["RMS"]), float(g[f"{name}_rms{step}"][0]), rtol=1e-6)
+        for key in ("exp_avg", "exp_avg_sq", "exp_avg_sq_row", "exp_avg_sq_col"):
+            if f"{name}_{key}{step}" in g:
+                ref_state = g[f"{name}_{key}{step}"]        # near-cancelling first-moment entries: tolerance on the tensor's scale
+                np.testing.assert_allclose(state[key], ref_state, rtol=2e-5, atol=1e-6 * np.abs(ref_state).max())
+
+
 @pytest.mark.parametrize("tag", ["big", "small"])
 def test_clip_grad_norm_vs_torch(oracle, golden, tag):
     """nn.utils.clip_grad_norm_(params, 1.0) as called at GenericTrainer.py:712-713."""

@@ -131,6 +131,46 @@ def gen_optimizer():
     np.savez(OUT / "optimizer.npz", **out)
 
 
+# ------------------------------------------------------------------------------------ Adafactor (oracle only so far)
+def gen_adafactor():
+    """step_adafactor_parameter (adafactor_extensions.py:17-93) on transformers' Adafactor, three steps per case.
+    Pins the ORACLE's restatement; the fused optimizer kernel covers AdamW/Adam only.
+    Note the reference's bf16 tail (:88-91): copy_stochastic_ is followed by an unconditional p.copy_(fp32), so the
+    stochastic rounding is overwritten by round-to-nearest — the fixtures record exactly that."""
+    from transformers import Adafactor
+    from modules.util.optimizer.adafactor_extensions import patch_adafactor
+    out = {}
+    cases = (("matrix_f32_relative", (24, 40), torch.float32, False, dict()),
+             ("vector_f32_relative", (301,), torch.float32, False, dict()),
+             ("matrix_f32_fixed_lr_beta1_wd", (24, 40), torch.float32, False,
+              dict(lr=1e-3, relative_step=False, scale_parameter=False, beta1=0.9, weight_decay=0.01)),
+             ("conv_f32_warmup", (8, 6, 3, 3), torch.float32, False, dict(warmup_init=True)),
+             ("matrix_bf16_sr", (24, 40), torch.bfloat16, True, dict()))
+    for name, shape, dtype, sr, kw in cases:
+        g = torch.Generator().manual_seed(13)
+        p = torch.nn.Parameter((torch.randn(*shape, generator=g) * 0.05).to(dtype))
+        opt = Adafactor([p], **kw)
+        patch_adafactor(opt, sr)
+        enc = bits16 if dtype == torch.bfloat16 else (lambda t: t.detach().numpy().copy())
+        out[f"{name}_p0"] = enc(p)
+        for step in range(1, 4):
+            grad = (torch.randn(*shape, generator=g) * 1e-2).to(dtype)
+            p.grad = grad.clone()
+            out[f"{name}_g{step}"] = enc(grad)
+            opt.step_parameter(p, opt.param_groups[0], 0)
+            out[f"{name}_p{step}"] = enc(p)
+            st = opt.state[p]
+            for key in ("exp_avg", "exp_avg_sq", "exp_avg_sq_row", "exp_avg_sq_col"):
+                if key in st:
+                    out[f"{name}_{key}{step}"] = st[key].detach().float().numpy().copy()
+            out[f"{name}_rms{step}"] = np.array([float(st["RMS"])])
+        grp = opt.param_groups[0]
+        out[f"{name}_meta"] = np.array([grp["lr"] if grp["lr"] is not None else np.nan, grp["eps"][0], grp["eps"][1], grp["clip_threshold"],
+                                        grp["decay_rate"], grp["beta1"] if grp["beta1"] is not None else np.nan, grp["weight_decay"],
+                                        float(grp["scale_parameter"]), float(grp["relative_step"]), float(grp["warmup_init"])], dtype=np.float64)
+    np.savez(OUT / "adafactor.npz", **out)
+
+
 # ------------------------------------------------------------------------------------ EMA
 def gen_ema():
     out = {}
@@ -392,7 +432,7 @@ def gen_clip():
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])              # e.g. `python tools/make_golden.py gen_lora` rewrites one fixture file
-    for fn in (gen_schedule, gen_optimizer, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_dora, gen_clip):
+    for fn in (gen_schedule, gen_optimizer, gen_adafactor, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_dora, gen_clip):
         if only and fn.__name__ not in only:
             continue
         fn()
