@@ -337,3 +337,73 @@ def adafactor_step(p, grad, state, *, lr=None, eps=(1e-30, 1e-3), clip_threshold
         p32 = p32 + p32 * f32(-weight_decay * float(lr_t))
     p32 = p32 - update
     return bf16_bits_to_f32(f32_to_bf16_bits(p32)) if bf16 else p32
+
+
+# ---- CAME (oracle ahead of the kernel) -------------------------------------------------------------
+def _factored_rsqrt(row, col):
+    """_approx_sq_grad of Adafactor / CAME: rsqrt(row / mean(row)) x rsqrt(col)."""
+    f32 = np.float32
+    r = (f32(1.0) / np.sqrt(row / row.astype(np.float64).mean(axis=-1, keepdims=True).astype(f32)))[..., None]
+    c = (f32(1.0) / np.sqrt(col))[..., None, :]
+    return r * c
+
+
+def stochastic_round_bf16(x32, bits):
+    """copy_stochastic_ (bf16_stochastic_rounding.py:5-30): int32 view + 16 random bits, low half masked off."""
+    u = np.ascontiguousarray(x32, dtype=np.float32).view(np.int32) + np.asarray(bits, dtype=np.int32).reshape(np.shape(x32))
+    return (u & np.int32(-65536)).view(np.float32)
+
+
+def came_step(p, grad, state, *, lr, eps=(1e-30, 1e-16), clip_threshold=1.0, betas=(0.9, 0.999, 0.9999), weight_decay=0.0,
+              sr_draws=None):
+    """One CAME.step_parameter (modules/util/optimizer/CAME.py:80-176).  `p` / `grad`: fp32 arrays with the tensor's
+    values; `state`: per-tensor dict, {} before the first step.  `sr_draws` (bf16 parameter with stochastic rounding):
+    a callable n -> int32[n] of 16-bit draws, called once per add_stochastic_ in the reference's order (weight decay
+    first, then the update); None = fp32 parameter, plain adds.  Returns the new parameter values."""
+    f32 = np.float32
+    p32 = np.asarray(p, dtype=f32).copy()
+    g = np.asarray(grad, dtype=f32)
+    factored = g.ndim >= 2
+    if not state:
+        state["step"] = 0
+        state["exp_avg"] = np.zeros_like(g)
+        if factored:
+            for key in ("exp_avg_sq_row", "exp_avg_res_row"):
+                state[key] = np.zeros(g.shape[:-1], dtype=f32)
+            for key in ("exp_avg_sq_col", "exp_avg_res_col"):
+                state[key] = np.zeros(g.shape[:-2] + g.shape[-1:], dtype=f32)
+        else:
+            state["exp_avg_sq"] = np.zeros_like(g)
+    mean = lambda t, axis: t.astype(np.float64).mean(axis=axis).astype(f32)  # noqa: E731
+    rms = lambda t: f32(np.sqrt((t.astype(np.float64) ** 2).sum()) / (t.size ** 0.5))  # noqa: E731
+    state["step"] += 1
+    state["RMS"] = rms(p32)
+
+    def ema_(buf, value, beta):
+        buf *= f32(beta)
+        buf += f32(1.0 - beta) * value
+
+    update = g * g + f32(eps[0])
+    if factored:
+        ema_(state["exp_avg_sq_row"], mean(update, -1), betas[1])
+        ema_(state["exp_avg_sq_col"], mean(update, -2), betas[1])
+        update = _factored_rsqrt(state["exp_avg_sq_row"], state["exp_avg_sq_col"]) * g
+    else:
+        ema_(state["exp_avg_sq"], update, betas[1])
+        update = (f32(1.0) / np.sqrt(state["exp_avg_sq"])) * g
+    update = update / max(f32(rms(update) / f32(clip_threshold)), f32(1.0))
+    exp_avg = state["exp_avg"]
+    ema_(exp_avg, update, betas[0])
+    res = (update - exp_avg) ** 2 + f32(eps[1])                         # instability (:137-139)
+    if factored:
+        ema_(state["exp_avg_res_row"], mean(res, -1), betas[2])
+        ema_(state["exp_avg_res_col"], mean(res, -2), betas[2])
+        update = _factored_rsqrt(state["exp_avg_res_row"], state["exp_avg_res_col"]) * exp_avg
+    else:
+        update = exp_avg.copy()
+    if weight_decay != 0:
+        decayed = p32 + f32(-weight_decay * lr) * p32
+        p32 = stochastic_round_bf16(decayed, sr_draws(p32.size)) if sr_draws is not None else decayed
+    update = update * f32(lr)
+    stepped = -update + p32                                            # add_stochastic_: result = (-update).clone(); result.add_(p)
+    return stochastic_round_bf16(stepped, sr_draws(p32.size)) if sr_draws is not None else stepped

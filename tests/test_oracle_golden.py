@@ -257,6 +257,38 @@ def test_adafactor_vs_reference(oracle, golden, name):
                 np.testing.assert_allclose(state[key], ref_state, rtol=2e-5, atol=1e-6 * np.abs(ref_state).max())
 
 
+@pytest.mark.parametrize("name", ["matrix_f32", "vector_f32_wd", "conv_f32", "matrix_bf16_sr_wd"])
+def test_came_vs_reference(oracle, golden, name):
+    """CAME.step_parameter (modules/util/optimizer/CAME.py:80-176), three steps; the bf16 case with stochastic rounding
+    fed the same 16-bit draws as the reference run (one Philox call per add_stochastic_).  Oracle only (SURVEY.md §8f
+    rank 4).  fp32: 1e-5 relative; bf16 + SR: identical except where the fp32 sum lands within an ulp of a draw's
+    carry boundary (< 2 % of elements, one bf16 ulp)."""
+    g = golden("came")
+    lr, eps0, eps1, clip, b0, b1, b2, wd, seed, rng_base = g[f"{name}_meta"]
+    kw = dict(lr=float(lr), eps=(float(eps0), float(eps1)), clip_threshold=float(clip), betas=(float(b0), float(b1), float(b2)), weight_decay=float(wd))
+    bf16 = "bf16" in name
+    dec = (lambda a: oracle.bf16_bits_to_f32(a)) if bf16 else (lambda a: a)
+    p, state, calls = dec(g[f"{name}_p0"]), {}, [0]
+
+    def draws(n):
+        calls[0] += 1
+        return oracle.sr_bits(int(seed), calls[0], int(rng_base), n)
+
+    for step in (1, 2, 3):
+        p = oracle.came_step(p, dec(g[f"{name}_g{step}"]), state, sr_draws=draws if bf16 else None, **kw)
+        ref = dec(g[f"{name}_p{step}"])
+        if bf16:
+            assert (np.abs(p - ref) <= np.abs(ref) * 2.0 ** -7).all() and (p != ref).mean() < 0.02
+            p = ref
+        else:
+            np.testing.assert_allclose(p, ref, rtol=1e-5, atol=1e-8)
+        for key in ("exp_avg", "exp_avg_sq", "exp_avg_sq_row", "exp_avg_sq_col", "exp_avg_res_row", "exp_avg_res_col"):
+            if f"{name}_{key}{step}" in g:
+                ref_state = g[f"{name}_{key}{step}"]
+                np.testing.assert_allclose(state[key], ref_state, rtol=5e-5, atol=1e-6 * np.abs(ref_state).max())
+    assert calls[0] == (6 if bf16 else 0)
+
+
 @pytest.mark.parametrize("tag", ["big", "small"])
 def test_clip_grad_norm_vs_torch(oracle, golden, tag):
     """nn.utils.clip_grad_norm_(params, 1.0) as called at GenericTrainer.py:712-713."""

@@ -171,6 +171,51 @@ def gen_adafactor():
     np.savez(OUT / "adafactor.npz", **out)
 
 
+# ------------------------------------------------------------------------------------ CAME (oracle only so far)
+def gen_came():
+    """CAME.step_parameter (modules/util/optimizer/CAME.py:80-176), three steps per case; in the bf16 + SR case the
+    reference's randint_like draws are replaced by this repo's Philox SR bits (one draw per add_stochastic_ call)."""
+    from modules.util.optimizer.CAME import CAME
+    out = {}
+    seed, rng_base = 0xCA3E, 8
+    cases = (("matrix_f32", (24, 40), torch.float32, False, dict(lr=2e-4)),
+             ("vector_f32_wd", (301,), torch.float32, False, dict(lr=2e-4, weight_decay=0.01)),
+             ("conv_f32", (8, 6, 3, 3), torch.float32, False, dict(lr=1e-4, betas=(0.8, 0.99, 0.999), clip_threshold=0.5)),
+             ("matrix_bf16_sr_wd", (24, 40), torch.bfloat16, True, dict(lr=2e-4, weight_decay=0.01)))
+    for name, shape, dtype, sr, kw in cases:
+        g = torch.Generator().manual_seed(17)
+        p = torch.nn.Parameter((torch.randn(*shape, generator=g) * 0.05).to(dtype))
+        opt = CAME([p], stochastic_rounding=sr, **kw)
+        enc = bits16 if dtype == torch.bfloat16 else (lambda t: t.detach().numpy().copy())
+        out[f"{name}_p0"] = enc(p)
+        calls = [0]
+        for step in range(1, 4):
+            grad = (torch.randn(*shape, generator=g) * 1e-2).to(dtype)
+            p.grad = grad.clone()
+            out[f"{name}_g{step}"] = enc(grad)
+            orig = torch.randint_like
+
+            def fake_randint_like(src, dtype=None, low=0, high=0):
+                assert low == 0 and high == (1 << 16) and dtype == torch.int32
+                calls[0] += 1
+                return torch.from_numpy(O.sr_bits(seed, calls[0], rng_base, src.numel()).copy()).view(src.shape)
+            if sr:
+                torch.randint_like = fake_randint_like
+            try:
+                opt.step_parameter(p, opt.param_groups[0], 0)
+            finally:
+                torch.randint_like = orig
+            out[f"{name}_p{step}"] = enc(p)
+            st = opt.state[p]
+            for key in ("exp_avg", "exp_avg_sq", "exp_avg_sq_row", "exp_avg_sq_col", "exp_avg_res_row", "exp_avg_res_col"):
+                if key in st:
+                    out[f"{name}_{key}{step}"] = st[key].detach().float().numpy().copy()
+        grp = opt.param_groups[0]
+        out[f"{name}_meta"] = np.array([grp["lr"], grp["eps"][0], grp["eps"][1], grp["clip_threshold"], *grp["betas"], grp["weight_decay"],
+                                        seed, rng_base], dtype=np.float64)
+    np.savez(OUT / "came.npz", **out)
+
+
 # ------------------------------------------------------------------------------------ EMA
 def gen_ema():
     out = {}
@@ -432,7 +477,7 @@ def gen_clip():
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])              # e.g. `python tools/make_golden.py gen_lora` rewrites one fixture file
-    for fn in (gen_schedule, gen_optimizer, gen_adafactor, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_dora, gen_clip):
+    for fn in (gen_schedule, gen_optimizer, gen_adafactor, gen_came, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_dora, gen_clip):
         if only and fn.__name__ not in only:
             continue
         fn()
