@@ -2,6 +2,16 @@
 
 TEST INFRASTRUCTURE ONLY — see the header of otb_oracle.c.  Only tests/, __graft_entry__.smoke()
 and bench.py's cpu_baseline / --impl reference legs may import this module.
+
+Besides the ctypes wrappers of the C restatement, this file holds the numpy restatements (fp64 accumulation) of:
+  lora_backward        LoRAModule.forward's autograd backward           modules/module/LoRAModule.py:319-323
+  conv_rows / _adjoint k x k conv leaves as row matrices                 modules/module/LoRAModule.py:142-155
+  dora                 DoRAModule.forward + backward                     modules/module/LoRAModule.py:385-419
+  adafactor_step       step_adafactor_parameter                          modules/util/optimizer/adafactor_extensions.py:17-93
+  came_step            CAME.step_parameter                               modules/util/optimizer/CAME.py:80-176
+  stochastic_round_bf16  copy_stochastic_                                modules/util/bf16_stochastic_rounding.py:5-30
+all pinned on outputs of the unmodified reference (tests/golden/, tools/make_golden.py).  The last four have no kernel
+yet: the oracle is in place first (task order: oracle, boundary, kernel).
 """
 from __future__ import annotations
 
