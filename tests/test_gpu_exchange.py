@@ -33,7 +33,7 @@ def test_two_rank_exchange_equals_nccl_allreduce_and_norm():
         pytest.skip("needs two GPUs")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                          "--master-port", "29547", str(REPO / "tools" / "nvls_check.py"), str((1 << 22) + 4 * 37)],
+                          "--master-port", "29547", str(REPO / "tools" / "exchange_check.py"), str((1 << 22) + 4 * 37)],
                          cwd=REPO, env=env, capture_output=True, text=True, timeout=240)
-    assert "nvls_check: ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "exchange_check: ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("equal_to_nccl=True") == 4

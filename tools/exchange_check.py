@@ -1,5 +1,5 @@
 """K-r (otb_grad_exchange, both modes) against ncclAllReduce on the LoRA arena size: correctness, then CUDA-event timing.
-usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29541 tools/nvls_check.py [n_elems]"""
+usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29541 tools/exchange_check.py [n_elems]"""
 import os
 import sys
 import torch
@@ -53,6 +53,6 @@ if rank == 0:
     mb = n * 4 / 1e6
     print(f"{world} GPUs, {mb:.0f} MB fp32: ncclAllReduce {t_nccl * 1e3:.0f} us | K-r (exchange + squared norm) "
           + " | ".join(f"{mode} {v * 1e3:.0f} us = {2 * (world - 1) / world * mb / 1e3 / (v / 1e3):.0f} GB/s bus" for mode, v in t.items()), flush=True)
-    print("nvls_check:", "ok" if ok else "MISMATCH", flush=True)
+    print("exchange_check:", "ok" if ok else "MISMATCH", flush=True)
 torch.cuda.synchronize()
 os._exit(0 if ok else 1)
