@@ -8,7 +8,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
-from ..enum import LossScaler, LossWeight, PeftType, TimestepDistribution
+from ..enum import EMAMode, LearningRateScaler, LossScaler, LossWeight, Optimizer, PeftType, TimestepDistribution
 
 
 class _ModelTypeStub:
@@ -23,6 +23,25 @@ class _ModelTypeStub:
 
     def has_mask_input(self) -> bool:
         return self._mask
+
+
+@dataclass
+class TrainOptimizerConfig:
+    """The fields of the reference's TrainOptimizerConfig (TrainConfig.py:34-262) that `create_optimizer` reads for
+    ADAM / ADAMW (create.py:481-534); None means "use the optimizer's default", as there."""
+    optimizer: object = Optimizer.ADAMW
+    beta1: float | None = None
+    beta2: float | None = None
+    eps: float | None = None
+    weight_decay: float | None = None
+    amsgrad: bool | None = False
+    foreach: bool | None = False
+    fused: bool | None = False
+    maximize: bool | None = False
+    capturable: bool | None = False
+    differentiable: bool | None = False
+    fused_back_pass: bool = False
+    stochastic_rounding: bool = False
 
 
 @dataclass
@@ -60,7 +79,11 @@ class TrainConfig:
     loss_weight_fn: object = LossWeight.CONSTANT
     loss_weight_strength: float = 5.0
     loss_scaler: object = LossScaler.NONE
-    # optimizer / ema (consumed by the harness, not by kernels)
+    # optimizer / ema (consumed by the trainer glue, not by kernels)
+    learning_rate: float = 3e-6
+    learning_rate_scaler: object = LearningRateScaler.NONE
+    optimizer: TrainOptimizerConfig = field(default_factory=TrainOptimizerConfig)
+    ema: object = EMAMode.OFF
     clip_grad_norm: float | None = 1.0
     ema_decay: float = 0.999
     ema_update_step_interval: int = 5

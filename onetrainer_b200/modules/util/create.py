@@ -1,0 +1,58 @@
+"""Optimizer and EMA construction for the fused step.
+
+Mirror of the ADAM / ADAMW branches of `create_optimizer` (/root/reference/modules/util/create.py:481-534) and of
+`create_ema` (:1089-1111): same argument meaning, same defaults, same RuntimeErrors.  Differences, all loud:
+every other optimizer raises NotImplementedError (SURVEY.md §8f rank 4 — their oracle restatements exist, their
+kernels do not); the optimizer is always patched, because the fused launch IS the step here; EMA on the CPU raises
+(the fused EMA lives next to the parameters in HBM).
+"""
+from __future__ import annotations
+
+import torch
+
+from ..module.EMAModule import EMAModuleWrapper
+from .enum import enum_name
+from .NamedParameterGroup import NamedParameterGroupCollection
+from .optimizer.adam_extensions import patch_adam
+from .optimizer.adamw_extensions import patch_adamw
+
+
+def _or(value, default):
+    return default if value is None else value
+
+
+def create_optimizer(parameter_group_collection: NamedParameterGroupCollection, state_dict: dict | None, config,
+                     ema: EMAModuleWrapper | None = None, ema_step_fn=None, clip_grad_norm: float | None = None):
+    """torch.optim.AdamW / Adam over `parameters_for_optimizer(config)`, step rebound to the fused launch.
+    `ema` / `ema_step_fn` / `clip_grad_norm` optionally fold EMA and the global-norm clip into that launch."""
+    oc = config.optimizer
+    name = enum_name(oc.optimizer)
+    if name not in ("ADAMW", "ADAM"):
+        raise NotImplementedError(f"optimizer {name} has no fused step on the B200 path (AdamW and Adam do)")
+    if oc.stochastic_rounding and (oc.fused or oc.foreach):
+        raise RuntimeError('"stochastic_rounding" is only allowed when "fused" and "foreach" are disabled')
+    if oc.fused_back_pass and (oc.fused or oc.foreach):
+        raise RuntimeError('"fused_back_pass" is only allowed when "fused" and "foreach" are disabled')
+    cls, patch, default_decay = (torch.optim.AdamW, patch_adamw, 1e-2) if name == "ADAMW" else (torch.optim.Adam, patch_adam, 0)
+    optimizer = cls(
+        params=parameter_group_collection.parameters_for_optimizer(config), lr=config.learning_rate,
+        betas=(_or(oc.beta1, 0.9), _or(oc.beta2, 0.999)), weight_decay=_or(oc.weight_decay, default_decay), eps=_or(oc.eps, 1e-8),
+        amsgrad=_or(oc.amsgrad, False), foreach=_or(oc.foreach, False), maximize=_or(oc.maximize, False),
+        capturable=_or(oc.capturable, False), differentiable=_or(oc.differentiable, False), fused=_or(oc.fused, False))
+    patch(optimizer, oc.stochastic_rounding, ema=ema, ema_step_fn=ema_step_fn, clip_grad_norm=clip_grad_norm)
+    if state_dict is not None:
+        optimizer.load_state_dict(state_dict)
+    return optimizer
+
+
+def create_ema(parameters, state_dict: dict | None, config) -> EMAModuleWrapper | None:
+    mode = enum_name(config.ema)
+    if mode == "OFF":
+        return None
+    if mode == "CPU":
+        raise NotImplementedError("EMA on the CPU is outside the B200 path: the fused EMA update reads the parameters in HBM")
+    ema = EMAModuleWrapper(parameters=parameters, decay=config.ema_decay, update_step_interval=config.ema_update_step_interval,
+                           device=torch.device(config.train_device))
+    if state_dict is not None:
+        ema.load_state_dict(state_dict)
+    return ema

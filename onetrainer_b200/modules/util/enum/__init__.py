@@ -16,6 +16,9 @@ TimestepDistribution = _StrEnum("TimestepDistribution", {k: k for k in ("UNIFORM
 LossWeight = _StrEnum("LossWeight", {k: k for k in ("CONSTANT", "P2", "MIN_SNR_GAMMA", "DEBIASED_ESTIMATION", "SIGMA")})
 LossScaler = _StrEnum("LossScaler", {k: k for k in ("NONE", "BATCH", "GRADIENT_ACCUMULATION", "BOTH")})
 PeftType = _StrEnum("PeftType", {k: k for k in ("LORA", "LOHA")})
+LearningRateScaler = _StrEnum("LearningRateScaler", {k: k for k in ("NONE", "BATCH", "GRADIENT_ACCUMULATION", "BOTH")})
+EMAMode = _StrEnum("EMAMode", {k: k for k in ("OFF", "GPU", "CPU")})
+Optimizer = _StrEnum("Optimizer", {k: k for k in ("ADAM", "ADAMW")})     # the two the fused step covers
 
 
 def enum_name(x) -> str:

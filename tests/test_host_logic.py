@@ -278,3 +278,65 @@ def test_multinomial_timestep_distributions_vs_reference(golden, name):
     t = s._get_timestep_discrete(1000, False, torch.Generator().manual_seed(int(seed)), 64, cfg)
     assert t.dtype == torch.int32 and t.tolist() == g[f"{name}_t"].tolist()
     np.testing.assert_allclose(s._ModelSetupNoiseMixin__weights.numpy(), g[f"{name}_weights"], rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ A15 trainer glue
+def _collection():
+    from onetrainer_b200.modules.util.NamedParameterGroup import NamedParameterGroup, NamedParameterGroupCollection
+    col = NamedParameterGroupCollection()
+    col.add_group(NamedParameterGroup("unet_lora", [nn.Parameter(torch.zeros(3)), nn.Parameter(torch.zeros(2))], None, "UNet LoRA"))
+    col.add_group(NamedParameterGroup("te_lora", [nn.Parameter(torch.zeros(5))], 1e-5))
+    return col
+
+
+@pytest.mark.parametrize("scaler", ["NONE", "BATCH", "GRADIENT_ACCUMULATION", "BOTH"])
+def test_parameter_groups_for_optimizer_vs_reference(golden, scaler):
+    """NamedParameterGroupCollection.parameters_for_optimizer (NamedParameterGroup.py:36-61): the same dicts, bit for bit."""
+    from onetrainer_b200.modules.util.enum import LearningRateScaler
+    g = golden("param_groups")
+    cfg = TrainConfig(learning_rate=3e-4, learning_rate_scaler=LearningRateScaler[scaler], batch_size=4, gradient_accumulation_steps=2)
+    col = _collection()
+    groups = col.parameters_for_optimizer(cfg)
+    assert [grp["lr"] for grp in groups] == g[f"{scaler}_lr"].tolist()
+    assert [grp["initial_lr"] for grp in groups] == g[f"{scaler}_initial_lr"].tolist()
+    assert [len(grp["params"]) for grp in groups] == g[f"{scaler}_counts"].tolist() and sorted(groups[0]) == list(g[f"{scaler}_keys"])
+    assert col.unique_name_mapping == list(g["unique_names"]) and col.display_name_mapping == list(g["display_names"])
+    assert len(col.parameters()) == int(g["n_parameters"][0]) and col.parameters()[0] is groups[0]["params"][0]
+
+
+def test_create_optimizer_and_ema_keep_the_reference_contract():
+    """create_optimizer ADAM / ADAMW branches (create.py:481-534), create_ema (:1089-1111), init_model_parameters
+    (optimizer_util.py:50-65): defaults, errors, and the attributes the trainer and the savers read afterwards."""
+    from onetrainer_b200.modules.util import create
+    from onetrainer_b200.modules.util.config.TrainConfig import TrainOptimizerConfig
+    from onetrainer_b200.modules.util.enum import EMAMode, Optimizer
+    from onetrainer_b200.modules.util.optimizer_util import init_model_parameters
+    cfg = TrainConfig(learning_rate=3e-4, train_device="cpu", optimizer=TrainOptimizerConfig(stochastic_rounding=True))
+    opt = create.create_optimizer(_collection(), None, cfg)
+    assert type(opt) is torch.optim.AdamW and opt.stochastic_rounding and callable(opt.step_parameter)
+    g0, g1 = opt.param_groups
+    assert (g0["lr"], g1["lr"], g0["betas"], g0["eps"], g0["weight_decay"]) == (3e-4, 1e-5, (0.9, 0.999), 1e-8, 1e-2)
+    adam = create.create_optimizer(_collection(), None, TrainConfig(optimizer=TrainOptimizerConfig(optimizer=Optimizer.ADAM, beta2=0.99)))
+    assert type(adam) is torch.optim.Adam and adam.param_groups[0]["weight_decay"] == 0 and adam.param_groups[0]["betas"] == (0.9, 0.99)
+    with pytest.raises(RuntimeError, match='"stochastic_rounding" is only allowed'):
+        create.create_optimizer(_collection(), None, TrainConfig(optimizer=TrainOptimizerConfig(stochastic_rounding=True, foreach=True)))
+    with pytest.raises(RuntimeError, match='"fused_back_pass" is only allowed'):
+        create.create_optimizer(_collection(), None, TrainConfig(optimizer=TrainOptimizerConfig(fused_back_pass=True, fused=True)))
+    with pytest.raises(NotImplementedError, match="ADAFACTOR"):
+        create.create_optimizer(_collection(), None, TrainConfig(optimizer=TrainOptimizerConfig(optimizer="ADAFACTOR")))
+    assert create.create_ema(_collection().parameters(), None, cfg) is None
+    with pytest.raises(NotImplementedError, match="CPU"):
+        create.create_ema(_collection().parameters(), None, TrainConfig(ema=EMAMode.CPU))
+    ema = create.create_ema(_collection().parameters(), None, TrainConfig(ema=EMAMode.GPU, train_device="cpu", ema_decay=0.99))
+    assert isinstance(ema, EMAModuleWrapper) and ema.decay == 0.99 and len(ema.ema_parameters) == 3
+
+    class Model:
+        pass
+
+    model = Model()
+    model.train_config = TrainConfig(ema=EMAMode.GPU, train_device="cpu")
+    model.optimizer_state_dict = model.ema_state_dict = None
+    init_model_parameters(model, _collection(), torch.device("cpu"))
+    assert model.param_group_mapping == ["unet_lora", "te_lora"] and model.optimizer_state_dict is None and model.ema_state_dict is None
+    assert isinstance(model.optimizer, torch.optim.AdamW) and isinstance(model.ema, EMAModuleWrapper)
+    assert len(model.parameters.parameters()) == 3

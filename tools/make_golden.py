@@ -459,6 +459,28 @@ def gen_dora():
     np.savez(OUT / "dora.npz", **out)
 
 
+# ------------------------------------------------------------------------------------ parameter groups
+def gen_param_groups():
+    """NamedParameterGroupCollection.parameters_for_optimizer (NamedParameterGroup.py:36-61) for every scaler."""
+    from modules.util.enum.LearningRateScaler import LearningRateScaler
+    from modules.util.NamedParameterGroup import NamedParameterGroup, NamedParameterGroupCollection
+    out = {}
+    for scaler in LearningRateScaler:
+        cfg = TrainConfig.default_values()
+        cfg.learning_rate, cfg.learning_rate_scaler, cfg.batch_size, cfg.gradient_accumulation_steps = 3e-4, scaler, 4, 2
+        col = NamedParameterGroupCollection()
+        col.add_group(NamedParameterGroup("unet_lora", [torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(2))], None, "UNet LoRA"))
+        col.add_group(NamedParameterGroup("te_lora", [torch.nn.Parameter(torch.zeros(5))], 1e-5))
+        groups = col.parameters_for_optimizer(cfg)
+        out[f"{scaler}_lr"] = np.array([g["lr"] for g in groups], dtype=np.float64)
+        out[f"{scaler}_initial_lr"] = np.array([g["initial_lr"] for g in groups], dtype=np.float64)
+        out[f"{scaler}_counts"] = np.array([len(g["params"]) for g in groups])
+        out[f"{scaler}_keys"] = np.array(sorted(groups[0].keys()))
+        out["unique_names"], out["display_names"] = np.array(col.unique_name_mapping), np.array(col.display_name_mapping)
+        out["n_parameters"] = np.array([len(col.parameters())])
+    np.savez(OUT / "param_groups.npz", **out)
+
+
 # ------------------------------------------------------------------------------------ clip
 def gen_clip():
     g = torch.Generator().manual_seed(31)
@@ -477,7 +499,7 @@ def gen_clip():
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])              # e.g. `python tools/make_golden.py gen_lora` rewrites one fixture file
-    for fn in (gen_schedule, gen_optimizer, gen_adafactor, gen_came, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_dora, gen_clip):
+    for fn in (gen_schedule, gen_optimizer, gen_adafactor, gen_came, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_dora, gen_param_groups, gen_clip):
         if only and fn.__name__ not in only:
             continue
         fn()
