@@ -26,7 +26,7 @@ namespace {
 
 constexpr int EX_THREADS = 256;
 constexpr int EX_UNROLL_DEFAULT = 4;
-constexpr long long PEER_WAIT_LIMIT_CYCLES = 40000000000ll;    // ~20 s: a missing rank traps instead of hanging the GPU
+constexpr long long PEER_WAIT_LIMIT_CYCLES = 120000000000ll;   // ~60 s: a missing rank traps instead of hanging the GPU
 
 struct PeerFlags {
     uint32_t* ptr[OTB_MAX_RANKS];
