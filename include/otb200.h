@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-#define OTB_ABI_VERSION 3   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs.  3: otb_grad_exchange, otb_grad_norm_from_partials */
+#define OTB_ABI_VERSION 4   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs.  3: otb_grad_exchange, otb_grad_norm_from_partials.
+                               4: OTB_TS_TABLE (ts_cdf / ts_cdf_len appended to otb_noise_args) */
 
 /* error codes */
 #define OTB_OK            0
@@ -216,7 +217,9 @@ int otb_shadow_refresh_multi(const otb_shadow_tensor* tensors, int32_t n_tensors
  *       memory-bound step kernel.
  * Replaces: _create_noise           ModelSetupNoiseMixin.py:18-49
  *           _get_timestep_discrete  ModelSetupNoiseMixin.py:51-155 (UNIFORM, LOGIT_NORMAL,
- *                                   HEAVY_TAIL, static + dynamic shift, deterministic)
+ *                                   HEAVY_TAIL, static + dynamic shift, deterministic;
+ *                                   COS_MAP / SIGMOID :122-153 as an inverse-CDF draw over
+ *                                   the reference's weight table)
  *           _add_noise_discrete     ModelSetupDiffusionMixin.py:15-38 (DDPM tables)
  *                                   ModelSetupFlowMatchingMixin.py:14-39 (rectified flow)
  *           latent scaling          BaseStableDiffusionXLSetup.py:215, BaseFluxSetup.py:230
@@ -227,6 +230,9 @@ int otb_shadow_refresh_multi(const otb_shadow_tensor* tensors, int32_t n_tensors
 #define OTB_TS_HEAVY_TAIL    2
 #define OTB_TS_DETERMINISTIC 3   /* int(T*0.5)-1 */
 #define OTB_TS_GIVEN         4   /* timesteps supplied by the caller in `timestep` */
+#define OTB_TS_TABLE         5   /* COS_MAP / SIGMOID: t = min_timestep + first i with ts_cdf[i] > u, u ~ U[0,1) from the
+                                    timestep stream at the GLOBAL sample index (the reference calls torch.multinomial
+                                    on the same weights; ts_cdf is their normalised running sum)           */
 
 #define OTB_TARGET_NONE    0
 #define OTB_TARGET_EPSILON 1     /* target = noise                               */
@@ -269,6 +275,8 @@ typedef struct otb_noise_args {
     int32_t pack_w;                /* 0: noisy_cast_out is [B, C, H, W].  W > 0 (the latent width; H = hw / W): it is
                                       written in FLUX's packed layout [B, (H/2)(W/2), 4C] — FluxModel.pack_latents,
                                       modules/model/FluxModel.py:319-331 — so the network input needs no permute copy  */
+    const float* ts_cdf;           /* OTB_TS_TABLE: [ts_cdf_len] non-decreasing, last entry 1.0 (device memory)          */
+    int32_t ts_cdf_len;            /* max_timestep - min_timestep                                                        */
 } otb_noise_args;
 
 int otb_noise_addnoise(const otb_noise_args* args, void* stream);

@@ -12,7 +12,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "libotb200.so"
 
 # ---- enums (include/otb200.h) ---------------------------------------------------------
-ABI_VERSION = 3          # include/otb200.h: OTB_ABI_VERSION
+ABI_VERSION = 4          # include/otb200.h: OTB_ABI_VERSION
 OTB_OK, OTB_EINVAL, OTB_EUNSUPPORTED, OTB_ECUDA, OTB_EARCH = 0, -1, -2, -3, -4
 F32, BF16, F16 = 0, 1, 2
 
@@ -30,7 +30,7 @@ FLAVOR_TORCH_CUDA = (FLAVOR_DIV_RECIPROCAL | FLAVOR_ADDCDIV_MUL_LAST | FLAVOR_FM
 
 STREAM_NOISE, STREAM_OFFSET, STREAM_PERTURB, STREAM_TIMESTEP, STREAM_SR, STREAM_DROPOUT = range(6)
 
-TS_UNIFORM, TS_LOGIT_NORMAL, TS_HEAVY_TAIL, TS_DETERMINISTIC, TS_GIVEN = range(5)
+TS_UNIFORM, TS_LOGIT_NORMAL, TS_HEAVY_TAIL, TS_DETERMINISTIC, TS_GIVEN, TS_TABLE = range(6)
 TARGET_NONE, TARGET_EPSILON, TARGET_V, TARGET_FLOW = range(4)
 LW_CONSTANT, LW_MIN_SNR, LW_DEBIASED, LW_P2, LW_SIGMA = range(5)
 
@@ -85,6 +85,7 @@ class NoiseArgs(C.Structure):
         ("noising_weight", _f32), ("noising_bias", _f32),
         ("shift_c1", _f32), ("shift_c2", _f32),
         ("seed", _u64), ("offset", _u64), ("sample_base", _i64), ("rng_dev", _vp), ("pack_w", _i32),
+        ("ts_cdf", _vp), ("ts_cdf_len", _i32),
     ]
 
 

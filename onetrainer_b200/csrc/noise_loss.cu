@@ -30,6 +30,17 @@ __device__ int32_t sample_timestep(const otb_noise_args& a, int64_t gs) {
     const int T = a.num_train_timesteps;
     if (a.ts_mode == OTB_TS_DETERMINISTIC) return (int)((double)T * 0.5) - 1;
     Philox4 r = otb_rng(a.seed, a.offset, OTB_STREAM_TIMESTEP, (uint64_t)gs);
+    if (a.ts_mode == OTB_TS_TABLE) {
+        // inverse CDF over the reference's weight table (ModelSetupNoiseMixin.py:122-153: multinomial, with replacement):
+        // first index whose running sum exceeds u; the shift is already inside the weights
+        const float u = otb_u01(r.x);
+        int lo = 0, hi = a.ts_cdf_len - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (a.ts_cdf[mid] > u) hi = mid; else lo = mid + 1;
+        }
+        return a.min_timestep + lo;
+    }
     const float num_t = (float)(a.max_timestep - a.min_timestep);
     const float min_t = (float)a.min_timestep;
     float ts;
@@ -532,7 +543,8 @@ extern "C" int otb_noise_addnoise(const otb_noise_args* a, void* stream) {
     OTB_CHECK_ARG(a->B > 0 && a->C > 0 && a->hw > 0 && (int64_t)a->C * a->hw < (1ll << 31), "bad shape B=%d C=%d hw=%d", a->B, a->C, a->hw);
     OTB_CHECK_ARG(a->B <= 65535, "batch %d too large for one launch", a->B);
     OTB_CHECK_ARG(a->latent_dtype >= OTB_F32 && a->latent_dtype <= OTB_F16, "bad latent dtype");
-    OTB_CHECK_ARG(a->ts_mode >= OTB_TS_UNIFORM && a->ts_mode <= OTB_TS_GIVEN, "bad timestep mode %d", a->ts_mode);
+    OTB_CHECK_ARG(a->ts_mode >= OTB_TS_UNIFORM && a->ts_mode <= OTB_TS_TABLE, "bad timestep mode %d", a->ts_mode);
+    OTB_CHECK_ARG(a->ts_mode != OTB_TS_TABLE || (a->ts_cdf != nullptr && a->ts_cdf_len > 0), "OTB_TS_TABLE needs ts_cdf / ts_cdf_len");
     OTB_CHECK_ARG(a->timestep != nullptr || (!a->do_add_noise && a->ts_mode != OTB_TS_GIVEN && a->target != OTB_TARGET_V),
                   "timestep buffer required");
     if (a->do_add_noise || a->target == OTB_TARGET_V) {

@@ -73,7 +73,10 @@ class ModelSetupDiffusionLossMixin(metaclass=ABCMeta):
         B = predicted.shape[0]
         # LossScaler (ModelSetupDiffusionLossMixin.py:243-248)
         scaler = enum_name(config.loss_scaler)
-        batch_scale = 1 if scaler in ("NONE", "GRADIENT_ACCUMULATION") else config.batch_size
+        # "batch" is the GLOBAL batch under data parallelism (as in NamedParameterGroup's LR scaler), so that an N-rank run
+        # at per-rank batch b reproduces the 1-rank run at batch N*b
+        from .... import dp
+        batch_scale = 1 if scaler in ("NONE", "GRADIENT_ACCUMULATION") else config.batch_size * dp.world_size()
         ga_scale = 1 if scaler in ("NONE", "BATCH") else config.gradient_accumulation_steps
         masked = bool(config.masked_training) and not config.model_type.has_conditioning_image_input()
         use_mask_mean_only = (not masked) and bool(config.masked_training) and bool(config.normalize_masked_area_loss)

@@ -56,7 +56,7 @@ class ModelSetupFusedNoiseMixin(metaclass=ABCMeta):
         if state is not None:                      # CUDA-graph mode: the key lives in device memory
             state.set_noise_key(seed, offset)
             rng_dev = state.noise_ptr
-        kw = timestep_kernel_args(num_train_timesteps, deterministic, config, latent_width, latent_height)
+        kw = timestep_kernel_args(num_train_timesteps, deterministic, config, latent_width, latent_height, device=dev)
         out = ops.noise_addnoise(
             latent=latent_image.contiguous(), coef_x0=coef_x0, coef_noise=coef_noise, B=B, C_=C, hw=hw,
             latent_dtype=latent_image.dtype, device=dev, want_x0=want_scaled_latent, want_noise=want_noise,

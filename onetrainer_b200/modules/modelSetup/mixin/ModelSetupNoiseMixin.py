@@ -40,27 +40,65 @@ def timestep_shift(config, latent_width: int | None, latent_height: int | None) 
     return shift
 
 
-def timestep_kernel_args(num_train_timesteps: int, deterministic: bool, config, latent_width=None, latent_height=None) -> dict:
+def timestep_weights(num_train_timesteps: int, config, latent_width=None, latent_height=None) -> Tensor:
+    """The reference's multinomial weight table for COS_MAP / SIGMOID (ModelSetupNoiseMixin.py:122-153), op for op, on
+    the CPU as the reference builds it (its `linspace` has no device argument)."""
+    min_timestep = int(num_train_timesteps * config.min_noising_strength)
+    max_timestep = int(num_train_timesteps * config.max_noising_strength)
+    num_timestep = max_timestep - min_timestep
+    shift = timestep_shift(config, latent_width, latent_height)
+    lin = torch.linspace(0, 1, num_timestep)
+    lin = lin / (shift - shift * lin + lin)
+    derivative = torch.linspace(0, 1, num_timestep)
+    derivative = shift / (shift + derivative - (derivative * shift)).pow(2)
+    if enum_name(config.timestep_distribution) == "COS_MAP":
+        weights = 2.0 / (math.pi - 2.0 * math.pi * lin + 2.0 * math.pi * lin ** 2.0)
+    else:
+        bias, weight = config.noising_bias + 0.5, config.noising_weight
+        weights = lin / (shift - shift * lin + lin)
+        weights = 1 / (1 + torch.exp(-weight * (weights - bias)))
+    weights *= derivative
+    return weights
+
+
+def timestep_cdf(weights: Tensor) -> Tensor:
+    """Normalised running sum of the weight table (fp64 accumulate, one rounding to fp32, last entry exactly 1): what
+    the kernel's inverse-CDF draw (OTB_TS_TABLE) searches.  Restated in oracle/otb_oracle.py: timestep_cdf."""
+    c = torch.cumsum(weights.detach().to("cpu", torch.float64), 0)
+    c = (c / c[-1]).to(torch.float32)
+    c[-1] = 1.0
+    return c
+
+
+_cdf_cache: dict = {}
+
+
+def timestep_kernel_args(num_train_timesteps: int, deterministic: bool, config, latent_width=None, latent_height=None,
+                         device=None) -> dict:
     """Host-side reduction of the config to the scalars the kernel takes — python ints/doubles
     exactly where the reference computes in python (ModelSetupNoiseMixin.py:69-71,91-121)."""
     if deterministic:
         return dict(ts_mode=N.TS_DETERMINISTIC, num_train_timesteps=num_train_timesteps)
     dist_name = enum_name(config.timestep_distribution)
+    min_t, max_t = int(num_train_timesteps * config.min_noising_strength), int(num_train_timesteps * config.max_noising_strength)
+    if dist_name in ("COS_MAP", "SIGMOID"):
+        shift = timestep_shift(config, latent_width, latent_height)
+        key = (dist_name, num_train_timesteps, min_t, max_t, float(shift), float(config.noising_weight), float(config.noising_bias), str(device))
+        cdf = _cdf_cache.get(key)
+        if cdf is None:
+            if len(_cdf_cache) > 16:
+                _cdf_cache.clear()
+            cdf = _cdf_cache[key] = timestep_cdf(timestep_weights(num_train_timesteps, config, latent_width, latent_height)).to(device)
+        return dict(ts_mode=N.TS_TABLE, num_train_timesteps=num_train_timesteps, min_timestep=min_t, max_timestep=max_t, ts_cdf=cdf)
     if dist_name not in _TS_MODES:
-        raise NotImplementedError(f"timestep distribution {dist_name} is sampled on the host path")
+        raise NotImplementedError(f"timestep distribution {dist_name} is not implemented on the B200 path")
     return dict(
-        ts_mode=_TS_MODES[dist_name], num_train_timesteps=num_train_timesteps,
-        min_timestep=int(num_train_timesteps * config.min_noising_strength),
-        max_timestep=int(num_train_timesteps * config.max_noising_strength),
+        ts_mode=_TS_MODES[dist_name], num_train_timesteps=num_train_timesteps, min_timestep=min_t, max_timestep=max_t,
         noising_weight=config.noising_weight, noising_bias=config.noising_bias,
         shift=timestep_shift(config, latent_width, latent_height))
 
 
 class ModelSetupNoiseMixin(metaclass=ABCMeta):
-
-    def __init__(self):
-        super().__init__()
-        self.__weights = None
 
     def _create_noise(self, source_tensor: Tensor, config, generator: Generator) -> Tensor:
         B, C, hw = flatten_chw(source_tensor.shape)
@@ -78,36 +116,12 @@ class ModelSetupNoiseMixin(metaclass=ABCMeta):
         if deterministic:
             # -1 is for zero-based indexing; shape [1], int64 — as the reference returns it
             return torch.tensor(int(num_train_timesteps * 0.5) - 1, dtype=torch.long, device=generator.device).unsqueeze(0)
-        dist_name = enum_name(config.timestep_distribution)
-        if dist_name in ("COS_MAP", "SIGMOID"):
-            return self.__multinomial_timesteps(num_train_timesteps, generator, batch_size, config, latent_width, latent_height)
-        kw = timestep_kernel_args(num_train_timesteps, False, config, latent_width, latent_height)
+        kw = timestep_kernel_args(num_train_timesteps, False, config, latent_width, latent_height, device=generator.device)
         seed, offset = draw_key(generator, generator.device)
         out = ops.noise_addnoise(B=batch_size, C_=1, hw=4, latent_dtype=torch.float32, device=generator.device,
                                  generate_noise=False, do_add_noise=False, seed=seed, offset=offset,
                                  sample_base=dp.global_sample_base(batch_size), **kw)
         return out["timestep"]
-
-    def __multinomial_timesteps(self, num_train_timesteps, generator, batch_size, config, latent_width, latent_height):
-        """COS_MAP / SIGMOID: a B-element multinomial over a cached 1000-entry weight table
-        (ModelSetupNoiseMixin.py:122-153).  Off the kernel path: torch ops on B elements."""
-        min_timestep = int(num_train_timesteps * config.min_noising_strength)
-        max_timestep = int(num_train_timesteps * config.max_noising_strength)
-        num_timestep = max_timestep - min_timestep
-        shift = timestep_shift(config, latent_width, latent_height)
-        if self.__weights is None:
-            lin = torch.linspace(0, 1, num_timestep)
-            derivative = shift / (shift + lin - (lin * shift)).pow(2)
-            lin = lin / (shift - shift * lin + lin)
-            if enum_name(config.timestep_distribution) == "COS_MAP":
-                weights = 2.0 / (math.pi - 2.0 * math.pi * lin + 2.0 * math.pi * lin ** 2.0)
-            else:
-                bias, weight = config.noising_bias + 0.5, config.noising_weight
-                weights = lin / (shift - shift * lin + lin)
-                weights = 1 / (1 + torch.exp(-weight * (weights - bias)))
-            self.__weights = (weights * derivative).to(device=generator.device)
-        samples = torch.multinomial(self.__weights, num_samples=batch_size, replacement=True, generator=generator) + min_timestep
-        return samples.to(dtype=torch.long, device=generator.device).int()
 
     def _get_timestep_continuous(self, deterministic: bool, generator: Generator, batch_size: int, config) -> Tensor:
         if deterministic:

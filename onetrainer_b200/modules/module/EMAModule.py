@@ -56,14 +56,20 @@ class EMAModuleWrapper:
     @torch.no_grad()
     def step(self, parameters: Iterable[torch.nn.Parameter], optimization_step) -> None:
         parameters = list(parameters)
+        covered: set = set()
         if self._fused_step is not None and self._fused_step == optimization_step:
-            self._fused_step = None          # the optimizer launch already did this step's update
-            return
+            # the optimizer launch already updated the averages of the tensors it stepped; whatever it did not cover
+            # (no gradient this step, an EMA kept in another dtype) still gets the reference's update below (:37-54
+            # updates EVERY requires_grad parameter)
+            self._fused_step = None
+            covered = self._driver.ema_covered_ids() if self._driver is not None else set()
         one_minus_decay = 1 - self.get_current_decay(optimization_step)
         if (optimization_step + 1) % self.update_step_interval != 0:
             return
-        pairs = [(e, p) for e, p in zip(self.ema_parameters, parameters, strict=True) if p.requires_grad]
-        same = [(e, p) for e, p in pairs if e.device == p.device]
+        pairs = [(e, p) for e, p in zip(self.ema_parameters, parameters, strict=True) if p.requires_grad and id(p) not in covered]
+        if not pairs:
+            return
+        same = [(e, p) for e, p in pairs if e.device == p.device and e.dtype == p.dtype]
         if same:
             N.require_cuda(*[p for _, p in same])
             key = tuple((e.data_ptr(), p.data_ptr()) for e, p in same)
@@ -73,8 +79,9 @@ class EMAModuleWrapper:
                 self._table_key = key
             ops.ema_multi(self._table, one_minus_decay)
         for e, p in pairs:
-            if e.device != p.device:         # EMA kept on another device (EMAMode.CPU): host-side, as the reference
-                delta = p.detach().to(e.device)
+            if e.device != p.device or e.dtype != p.dtype:
+                # EMA kept on another device (EMAMode.CPU) or in another dtype: the reference's three ops, in e's dtype
+                delta = p.detach().to(device=e.device, dtype=e.dtype)
                 delta.sub_(e)
                 delta.mul_(one_minus_decay)
                 e.add_(delta)
@@ -93,8 +100,13 @@ class EMAModuleWrapper:
             self._driver.table = None
 
     def _write_into(self, sources, parameters) -> None:
-        for src, dst in zip(sources, list(parameters), strict=True):
+        live = list(parameters)
+        for src, dst in zip(sources, live, strict=True):
             dst.data.copy_(src.to(dst.device).data)
+        # `.data.copy_` leaves Parameter._version alone, and the fused LoRA path keys its bf16 shadows on it: without the
+        # bump a forward after the swap would still run the old weights (sampling "with EMA" on non-EMA weights)
+        from ..util.optimizer.fused_adam import _bump_versions
+        _bump_versions(live)
 
     def copy_ema_to(self, parameters: Iterable[torch.nn.Parameter], store_temp: bool = True) -> None:
         """Swap the averages in for sampling / saving (:63-69), optionally parking the live weights on the host."""

@@ -196,9 +196,11 @@ def _launch_grad_ab(mod, x2, dy, gs, ts, dA, dB, ret_a, ret_b) -> None:
     """dA / dB of one leaf on the side stream (see ops.SideGrads) unless autograd will READ the returned tensor on
     this stream: it only ADOPTS the arena slices (or gets None when the kernel accumulates in place); a foreign
     p.grad (someone replaced it) makes autograd add the returned tensor here, so that case stays in order."""
-    foreign = (ret_a is not None and ret_a.data_ptr() != dA.data_ptr()) or (ret_b is not None and ret_b.data_ptr() != dB.data_ptr()) \
-        or (ret_a is not None and mod.lora_down.weight.grad is not None) or (ret_b is not None and mod.lora_up.weight.grad is not None) \
-        or mod._wrapper_slot is None
+    arena = mod._wrapper_slot[0].grad_arena if mod._wrapper_slot is not None else None
+
+    def outside(t) -> bool:
+        return t is not None and (arena is None or not arena.data_ptr() <= t.data_ptr() < arena.data_ptr() + arena.numel() * arena.element_size())
+    foreign = outside(dA) or outside(dB)
     if ops.side_grads.enabled and not foreign:
         ops.side_grads.launch(lambda: ops.lora_grad_ab(x2, dy, gs, ts, dA, dB), dy.device, (x2, dy, gs, ts, dA, dB))
     else:
@@ -382,43 +384,42 @@ class PeftBase(nn.Module):
 
     @classmethod
     def make_dummy(cls):
-        """A holder for state-dict keys that match no trainable layer (reference :162-206): keeps
-        and returns the loaded dict, never hooks, never trains."""
+        """The adapter type's placeholder class for state-dict keys that match no trainable layer (reference :162-206):
+        `Placeholder(prefix, None, *args)` parks a loaded dict and hands it back on save, and refuses everything else."""
+        return type(f"Dummy{cls.__name__}", (_KeyHolder, cls), {})
 
-        class Dummy(cls):
-            def __init__(self, *args, **kwargs):
-                super().__init__(*args, **kwargs)
-                self._state_dict = {}
 
-            def forward(self, *args, **kwargs):
-                raise NotImplementedError("Should never be called on a dummy module.")
+def _refuse(what: str):
+    def method(self, *args, **kwargs):
+        raise NotImplementedError(f"{what}() should never be called on a dummy module.")
+    method.__name__ = what
+    return method
 
-            def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True, assign: bool = False):
-                self._initialized = True
-                self._state_dict = copy.deepcopy(state_dict)
-                return nn.modules.module._IncompatibleKeys([], [])
 
-            def state_dict(self, *args, **kwargs):  # type: ignore
-                if not self._initialized:
-                    raise RuntimeError("A state dict must be loaded before one can be returned.")
-                return self._state_dict
+class _KeyHolder:
+    """Mixed in FRONT of an adapter class by PeftBase.make_dummy: keeps unknown keys alive across load -> save so that a
+    LoRA file with layers this network does not have round-trips unchanged; it never hooks, trains or computes."""
 
-            def initialize_weights(self):
-                raise NotImplementedError("Should never be called on a dummy module.")
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._parked: dict = {}
 
-            def hook_to_module(self):
-                raise NotImplementedError("Should never be called on a dummy module.")
+    def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True, assign: bool = False):
+        self._parked = copy.deepcopy(state_dict)
+        self._initialized = True
+        return nn.modules.module._IncompatibleKeys([], [])
 
-            def remove_hook_from_module(self):
-                raise NotImplementedError("Should never be called on a dummy module.")
+    def state_dict(self, *args, **kwargs):  # type: ignore[override]
+        if not self._initialized:
+            raise RuntimeError("A state dict must be loaded before one can be returned.")
+        return self._parked
 
-            def apply_to_module(self):
-                raise NotImplementedError("Should never be called on a dummy module.")
-
-            def extract_from_module(self, base_module: nn.Module):
-                raise NotImplementedError("Should never be called on a dummy module.")
-
-        return Dummy
+    forward = _refuse("forward")
+    initialize_weights = _refuse("initialize_weights")
+    hook_to_module = _refuse("hook_to_module")
+    remove_hook_from_module = _refuse("remove_hook_from_module")
+    apply_to_module = _refuse("apply_to_module")
+    extract_from_module = _refuse("extract_from_module")
 
 
 # ---------------------------------------------------------------------------------------
@@ -604,6 +605,7 @@ class LoRAModuleWrapper:
         self._arena = None
         self._arena_key = None
         self._written_gen = {}
+        self._written_pass = {}
 
     def __create_modules(self, orig_module: nn.Module | None) -> dict[str, PeftBase]:
         found = {}
@@ -693,6 +695,7 @@ class LoRAModuleWrapper:
             self._arena = GradArena(shapes, A.device)
             self._arena_key = A.device
             self._written_gen = {}
+            self._written_pass = {}
         arena = self._arena
         va, vb = arena.view(2 * idx), arena.view(2 * idx + 1)
 
@@ -702,9 +705,20 @@ class LoRAModuleWrapper:
             return "inplace" if p.grad.data_ptr() == v.data_ptr() else "foreign"
 
         sa, sb = state(A, va) if need_a else "skip", state(B, vb) if need_b else "skip"
-        if "fresh" in (sa, sb) and self._written_gen.get(idx) == arena.generation:
+        # One backward pass may reach the same leaf twice (a shared module, two forwards before one backward): autograd
+        # defers AccumulateGrad, so p.grad is still None the second time and the slice handed out the first time is
+        # still pending.  Do not mistake that for a new step (which would zero every gradient gathered so far) and do not
+        # hand the same slice out twice (autograd would add it to itself): the second use goes through a temporary and
+        # plain autograd accumulation, as the reference's per-use gradients do.
+        pass_id = torch._C._current_graph_task_id()
+        reused = pass_id >= 0 and self._written_pass.get(idx) == pass_id
+        if reused:
+            sa = "foreign" if sa == "fresh" else sa
+            sb = "foreign" if sb == "fresh" else sb
+        elif "fresh" in (sa, sb) and self._written_gen.get(idx) == arena.generation:
             arena.start_new_accumulation()      # first leaf of a new step: one memset for everyone
         self._written_gen[idx] = arena.generation
+        self._written_pass[idx] = pass_id
 
         def pick(st: str, p: Tensor, v: Tensor):
             if st == "skip":

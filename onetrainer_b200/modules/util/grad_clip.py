@@ -24,7 +24,7 @@ def clip_grad_norm_(parameters, max_norm: float, grad_prescale: float = 1.0) -> 
     if not params:
         return torch.tensor(0.0)
     N.require_cuda(*params)
-    key = tuple(id(p) for p in params)
+    key = tuple((id(p), p.data_ptr(), p.numel()) for p in params)     # ids are recycled: the address and size pin the tensor
     table = _tables.get(key)
     if table is None:
         if len(_tables) > 8:

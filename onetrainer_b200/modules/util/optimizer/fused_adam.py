@@ -57,13 +57,15 @@ class FusedAdamDriver:
         self.grad_prescale = 1.0        # 1/world_size under data parallel
         self.norm_partials = None       # squared-norm partials of ALL active gradients, when the exchange kernel made them
         self.post_step_hooks = []       # e.g. LoRAModuleWrapper.refresh_shadows
-        self.step_count = 0             # SR Philox offset
+        self.step_count = 0             # SR Philox offset (persisted as state_dict()["otb_sr_step_count"])
+        self._sr_seed, self._sr_seed_src = None, None
         self.last_norm_coef: torch.Tensor | None = None
         self._single = {}               # id(p) -> one-entry table for step_parameter
         self._frozen_active = None
         self._last_active = []
         self._dyn = (0, 0, 0.0, False)
         self._prescale_dev, self._prescale_val = None, None
+        self._ema_covered: set = set()  # id(p) of the tensors whose EMA rides in the table's launch
 
     # -- table construction ---------------------------------------------------------------
     def _active(self):
@@ -87,10 +89,30 @@ class FusedAdamDriver:
                 _init_state(st, p, group)
             entries.append(dict(p=p.data, g=p.grad, exp_avg=st["exp_avg"], exp_avg_sq=st["exp_avg_sq"],
                                 ema=ema_of.get(id(p))))
+        self._ema_covered = {id(p) for p, _ in active if id(p) in ema_of}
         return entries
 
+    def ema_covered_ids(self) -> set:
+        """Parameters whose EMA update happened inside the last optimizer launch (EMAModuleWrapper.step does the rest)."""
+        return self._ema_covered
+
+    def invalidate(self) -> None:
+        """Forget every cached pointer table (optimizer.load_state_dict replaced the state tensors)."""
+        if self._frozen_active is not None:
+            raise RuntimeError("optimizer state was replaced while a captured CUDA graph still points at the old tensors; "
+                               "re-capture the step after load_state_dict()")
+        self.table, self.table_key = None, None
+        self._single.clear()
+
     def _ensure_table(self, active):
-        key = tuple((id(p), p.data_ptr(), p.dtype) for p, _ in active) + (id(self.ema),)
+        # the key covers everything the device table points at: parameters AND their state tensors (load_state_dict
+        # replaces exp_avg / exp_avg_sq / step; a stale table would keep stepping the old moments)
+        st = self.opt.state
+        for p, group in active:
+            if len(st[p]) == 0:
+                _init_state(st[p], p, group)
+        key = tuple((id(p), p.data_ptr(), p.dtype, st[p]["exp_avg"].data_ptr(), st[p]["exp_avg_sq"].data_ptr())
+                    for p, _ in active) + (id(self.ema),)
         if self.table is None or key != self.table_key:
             if active and not active[0][0].is_cuda:
                 N.require_cuda(active[0][0])
@@ -133,6 +155,25 @@ class FusedAdamDriver:
                 h[k][i:j] = v
             i = j
 
+    def sr_seed(self) -> int:
+        """Key of the stochastic-rounding stream.  Under data parallelism every rank must draw the SAME bits or the bf16
+        replicas drift apart, whatever per-rank seeding the application uses: rank 0's seed is broadcast once."""
+        if self._sr_seed is None:
+            seed = torch.initial_seed()
+            from .... import dp
+            if dp.world_size() > 1:
+                import torch.distributed as dist
+                dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+                t = torch.tensor([seed & (2 ** 63 - 1)], dtype=torch.int64, device=dev)
+                dist.broadcast(t, src=0)
+                seed = int(t.item())
+            self._sr_seed = seed
+            self._sr_seed_src = torch.initial_seed()
+        elif self._sr_seed_src != torch.initial_seed():      # the application re-seeded torch: follow it (single process)
+            self._sr_seed = None
+            return self.sr_seed()
+        return self._sr_seed
+
     # -- entry points ---------------------------------------------------------------------
     @torch.no_grad()
     def step(self, closure=None):
@@ -164,7 +205,7 @@ class FusedAdamDriver:
         if self.ema is not None and self.ema_step_fn is not None:
             do_ema, omd = self.ema.fused_schedule(int(self.ema_step_fn()))
         self.step_count += 1
-        self._dyn = (torch.initial_seed(), self.step_count, omd, do_ema)
+        self._dyn = (self.sr_seed(), self.step_count, omd, do_ema)
         state = step_state.active()
         if state is not None:
             state.set_optim(*self._dyn)
@@ -216,7 +257,7 @@ class FusedAdamDriver:
         st = self.opt.state[p]
         if len(st) == 0:
             _init_state(st, p, group)
-        key = (id(p), p.data_ptr())
+        key = (id(p), p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr())
         tab = self._single.get(key)
         if tab is None:
             tab = ops.OptimTable([dict(p=p.data, g=p.grad, exp_avg=st["exp_avg"], exp_avg_sq=st["exp_avg_sq"])], p.device)
@@ -226,7 +267,7 @@ class FusedAdamDriver:
         self._fill_scalars(tab, [(p, group)])
         tab.upload()
         self.step_count += 1
-        ops.adamw_sr_ema_multi(tab, flavor=self.flavor, seed=torch.initial_seed(), offset=self.step_count)
+        ops.adamw_sr_ema_multi(tab, flavor=self.flavor, seed=self.sr_seed(), offset=self.step_count)
         _bump_versions([p])
 
 
@@ -240,4 +281,24 @@ def install(optimizer, stochastic_rounding: bool, decoupled: bool, ema=None, ema
     optimizer.otb_driver = driver
     optimizer.step = driver.step
     optimizer.step_parameter = driver.step_parameter
+
+    # resume: the SR stream position travels with the optimizer state (a resumed run must not replay offsets 1, 2, ...),
+    # and a load replaces the state tensors the cached pointer tables refer to
+    def _save(opt, state_dict):
+        state_dict["otb_sr_step_count"] = driver.step_count
+        return state_dict
+
+    def _pre_load(opt, state_dict):
+        if "otb_sr_step_count" in state_dict:
+            state_dict = dict(state_dict)
+            driver.step_count = int(state_dict.pop("otb_sr_step_count"))
+            return state_dict
+        return None
+
+    def _post_load(opt):
+        driver.invalidate()
+
+    optimizer.register_state_dict_post_hook(_save)
+    optimizer.register_load_state_dict_pre_hook(_pre_load)
+    optimizer.register_load_state_dict_post_hook(_post_load)
     return driver

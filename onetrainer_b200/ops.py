@@ -220,9 +220,12 @@ def noise_addnoise(*, latent=None, noise_in=None, coef_x0=None, coef_noise=None,
                    min_timestep: int = 0, max_timestep: int = 1000, noising_weight: float = 0.0,
                    noising_bias: float = 0.0, shift: float = 1.0, seed: int = 0, offset: int = 0,
                    sample_base: int = 0, want_sigma: bool = False, shape=None, rng_dev: torch.Tensor | None = None,
-                   pack_w: int = 0) -> dict:
+                   pack_w: int = 0, ts_cdf: torch.Tensor | None = None) -> dict:
     """One launch of the pre-network half of the step kernel; returns the requested tensors."""
-    N.require_cuda(latent, noise_in, coef_x0, coef_noise, timestep)
+    N.require_cuda(latent, noise_in, coef_x0, coef_noise, timestep, ts_cdf)
+    if ts_mode == N.TS_TABLE and (ts_cdf is None or ts_cdf.dtype != torch.float32 or not ts_cdf.is_contiguous()
+                                  or ts_cdf.numel() != max_timestep - min_timestep):
+        raise ValueError("noise_addnoise: TS_TABLE needs a contiguous fp32 ts_cdf of max_timestep - min_timestep entries")
     shape = tuple(shape) if shape is not None else (B, C_ * hw)
     ldt = N.dtype_code(latent_dtype)
 
@@ -259,7 +262,7 @@ def noise_addnoise(*, latent=None, noise_in=None, coef_x0=None, coef_noise=None,
         noising_weight=float(noising_weight), noising_bias=float(noising_bias),
         shift_c1=float(T * shift), shift_c2=float(shift - 1),
         seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1), sample_base=int(sample_base), rng_dev=N.ptr(rng_dev),
-        pack_w=int(pack_w))
+        pack_w=int(pack_w), ts_cdf=N.ptr(ts_cdf), ts_cdf_len=0 if ts_cdf is None else ts_cdf.numel())
     N.check(N.lib().otb_noise_addnoise(C.byref(a), _stream()), "otb_noise_addnoise")
     _count()
     out.update(x0=x0, noise=noise, noisy=noisy, noisy_cast=noisy_cast, target=tgt, timestep=ts, sigma=sigma)

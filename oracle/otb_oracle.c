@@ -245,6 +245,18 @@ int32_t otb_o_timestep(int mode, uint64_t seed, uint64_t offset, int64_t global_
     return otb_o_timestep_from_draw(mode, draw, T, min_t, max_t, noising_weight, noising_bias, shift_c1, shift_c2);
 }
 
+/* COS_MAP / SIGMOID (ModelSetupNoiseMixin.py:122-153): the reference draws torch.multinomial(weights, B, replacement=True)
+ * + min_timestep.  multinomial-with-replacement IS an i.i.d. draw from weights / sum(weights); restated as the inverse
+ * CDF of one U[0,1) draw per GLOBAL sample from the timestep stream: first i with cdf[i] > u. */
+int32_t otb_o_timestep_table(uint64_t seed, uint64_t offset, int64_t global_sample, const float* cdf, int len, int min_t) {
+    uint32_t r[4];
+    otb_o_philox(seed, offset, 3u, (uint64_t)global_sample, r);
+    float u = (float)(r[0] >> 8) * 5.9604644775390625e-08f;
+    int i = 0;
+    while (i < len - 1 && !(cdf[i] > u)) ++i;         /* linear scan: the definition, not the kernel's binary search */
+    return min_t + i;
+}
+
 /* ---------------- noise ---------------- */
 /* N(0,1) draw for global element `elem` of `stream` (ideal evaluation of the kernel's definition) */
 static inline float normal_at(uint64_t seed, uint64_t offset, uint32_t stream, uint64_t elem) {

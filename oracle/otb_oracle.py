@@ -62,6 +62,7 @@ def lib():
         _lib.otb_o_sqsum.restype = C.c_double
         _lib.otb_o_timestep.restype = C.c_int32
         _lib.otb_o_timestep_from_draw.restype = C.c_int32
+        _lib.otb_o_timestep_table.restype = C.c_int32
         _lib.otb_o_timestep_weight.restype = C.c_float
     return _lib
 
@@ -151,6 +152,21 @@ def timestep(mode, seed, offset, global_sample, T=1000, min_t=0, max_t=1000, noi
     return int(lib().otb_o_timestep(C.c_int(mode), C.c_uint64(seed), C.c_uint64(offset), C.c_int64(global_sample), C.c_int(T),
                                     C.c_int(min_t), C.c_int(max_t), C.c_float(noising_weight), C.c_float(noising_bias),
                                     C.c_float(float(T * shift)), C.c_float(float(shift - 1))))
+
+
+def timestep_cdf(weights) -> np.ndarray:
+    """Normalised running sum of the reference's multinomial weight table (fp64 accumulate, one rounding, last entry 1)."""
+    c = np.cumsum(np.asarray(weights, dtype=np.float64))
+    c = (c / c[-1]).astype(np.float32)
+    c[-1] = 1.0
+    return c
+
+
+def timestep_table(seed, offset, global_sample, cdf, min_t=0) -> int:
+    """COS_MAP / SIGMOID draw for one global sample (ModelSetupNoiseMixin.py:122-153 restated as an inverse CDF)."""
+    cdf = np.ascontiguousarray(cdf, dtype=np.float32)
+    return int(lib().otb_o_timestep_table(C.c_uint64(seed), C.c_uint64(offset), C.c_int64(global_sample),
+                                          cdf.ctypes.data_as(C.c_void_p), C.c_int(cdf.size), C.c_int(min_t)))
 
 
 def timestep_from_draw(mode, draw, T=1000, min_t=0, max_t=1000, noising_weight=0.0, noising_bias=0.0, shift=1.0) -> int:

@@ -287,6 +287,32 @@ def test_timesteps_bit_exact_vs_oracle_and_golden(K, dev, oracle, golden, name):
     assert (diff.max() == 0) if MODES[name] == 0 else (diff.max() <= 1 and (diff != 0).sum() <= 1)
 
 
+@pytest.mark.parametrize("name", ["cos_map", "cos_map_range_shift3", "sigmoid"])
+def test_table_timesteps_bit_exact_vs_oracle_and_dp_invariant(K, dev, oracle, golden, name):
+    """COS_MAP / SIGMOID (ModelSetupNoiseMixin.py:122-153) in the kernel: an inverse-CDF draw over the reference's own
+    weight table, keyed by the global sample index.  Integer output: bit-exact vs the oracle's restatement; two ranks
+    of 32 samples draw what one process draws for 64; the histogram follows the table."""
+    g = golden("timesteps")
+    mn, mx = int(1000 * g[f"{name}_cfg"][0]), int(1000 * g[f"{name}_cfg"][1])
+    cdf = oracle.timestep_cdf(g[f"{name}_weights"])
+    dcdf = torch.from_numpy(cdf).to(dev)
+
+    def draw(B, base):
+        return K.ops.noise_addnoise(B=B, C_=1, hw=4, latent_dtype=torch.float32, device=dev, generate_noise=False, do_add_noise=False,
+                                    ts_mode=K.N.TS_TABLE, min_timestep=mn, max_timestep=mx, ts_cdf=dcdf, seed=77, offset=4,
+                                    sample_base=base)["timestep"].cpu().numpy()
+    mine = draw(64, 0)
+    assert np.array_equal(mine, np.array([oracle.timestep_table(77, 4, i, cdf, mn) for i in range(64)]))
+    assert np.array_equal(np.concatenate([draw(32, 0), draw(32, 32)]), mine)
+    big = draw(32768, 0)
+    assert big.min() >= mn and big.max() < mx
+    emp = np.cumsum(np.bincount(big - mn, minlength=mx - mn)) / big.size
+    assert np.abs(emp - cdf).max() < 1.63 / math.sqrt(big.size)
+    with pytest.raises(ValueError, match="ts_cdf"):
+        K.ops.noise_addnoise(B=4, C_=1, hw=4, latent_dtype=torch.float32, device=dev, generate_noise=False, do_add_noise=False,
+                             ts_mode=K.N.TS_TABLE, min_timestep=0, max_timestep=1000, seed=1)
+
+
 def test_noise_matches_oracle_and_is_gaussian(K, dev, oracle):
     """fp32 N(0,1) draws: the kernel uses MUFU log/sincos (abs err ~1e-6); the oracle evaluates the same
     Philox -> Box-Muller definition with libm in fp64.  Tolerance 2e-5 absolute (values reach |z| ~ 5)."""

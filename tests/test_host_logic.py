@@ -262,10 +262,11 @@ def test_flux_standin_has_the_reference_leaf_set():
 
 
 @pytest.mark.parametrize("name", ["cos_map", "cos_map_range_shift3", "sigmoid"])
-def test_multinomial_timestep_distributions_vs_reference(golden, name):
-    """COS_MAP / SIGMOID (ModelSetupNoiseMixin.py:122-153) stay on torch ops over B elements: with the reference's own
-    CPU generator stream the samples and the cached weight table must be the reference's."""
-    from onetrainer_b200.modules.modelSetup.mixin.ModelSetupNoiseMixin import ModelSetupNoiseMixin
+def test_table_timestep_distributions_host_side(golden, name):
+    """COS_MAP / SIGMOID (ModelSetupNoiseMixin.py:122-153): the host reduces the config to the reference's weight table
+    (bit for bit) and its running sum for the kernel's inverse-CDF draw; like every other stage there is no CPU path."""
+    from onetrainer_b200 import _native as N
+    from onetrainer_b200.modules.modelSetup.mixin.ModelSetupNoiseMixin import ModelSetupNoiseMixin, timestep_kernel_args, timestep_weights
 
     class S(ModelSetupNoiseMixin):
         pass
@@ -274,10 +275,13 @@ def test_multinomial_timestep_distributions_vs_reference(golden, name):
     lo, hi, weight, bias, shift, _, seed, _ = g[f"{name}_cfg"]
     cfg = TrainConfig(timestep_distribution=TimestepDistribution.SIGMOID if name == "sigmoid" else TimestepDistribution.COS_MAP,
                       min_noising_strength=lo, max_noising_strength=hi, noising_weight=weight, noising_bias=bias, timestep_shift=shift)
-    s = S()
-    t = s._get_timestep_discrete(1000, False, torch.Generator().manual_seed(int(seed)), 64, cfg)
-    assert t.dtype == torch.int32 and t.tolist() == g[f"{name}_t"].tolist()
-    np.testing.assert_allclose(s._ModelSetupNoiseMixin__weights.numpy(), g[f"{name}_weights"], rtol=1e-6)
+    assert np.array_equal(timestep_weights(1000, cfg).numpy(), g[f"{name}_weights"])
+    kw = timestep_kernel_args(1000, False, cfg, device="cpu")
+    cdf = kw["ts_cdf"]
+    assert kw["ts_mode"] == N.TS_TABLE and cdf.numel() == kw["max_timestep"] - kw["min_timestep"] == int(1000 * hi) - int(1000 * lo)
+    assert cdf.dtype == torch.float32 and cdf[-1].item() == 1.0 and bool((cdf[1:] >= cdf[:-1]).all()) and cdf[0].item() > 0
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        S()._get_timestep_discrete(1000, False, torch.Generator().manual_seed(int(seed)), 64, cfg)
 
 
 # ------------------------------------------------------------------------------------------ A15 trainer glue

@@ -99,6 +99,38 @@ def test_timesteps_vs_reference(oracle, golden, name):
     assert ref.min() >= 0 and ref.max() < 1000
 
 
+@pytest.mark.parametrize("name,dist,kw", [
+    ("cos_map", "COS_MAP", dict()),
+    ("cos_map_range_shift3", "COS_MAP", dict(min_noising_strength=0.1, max_noising_strength=0.9, timestep_shift=3.0)),
+    ("sigmoid", "SIGMOID", dict(noising_weight=2.0, noising_bias=0.1, timestep_shift=2.0))])
+def test_table_timesteps_vs_reference_weights(oracle, golden, name, dist, kw):
+    """COS_MAP / SIGMOID (ModelSetupNoiseMixin.py:122-153): the reference draws torch.multinomial over a cached weight
+    table.  (1) the host builds the SAME table, bit for bit; (2) the oracle's inverse-CDF draw (what the kernel does, per
+    global sample) is distributed as weights / sum(weights); (3) the reference's own 64 recorded draws are consistent
+    with that distribution (two-sample KS)."""
+    from onetrainer_b200.modules.modelSetup.mixin.ModelSetupNoiseMixin import timestep_cdf, timestep_weights
+    from onetrainer_b200.modules.util.config.TrainConfig import TrainConfig
+    from onetrainer_b200.modules.util.enum import TimestepDistribution
+    g = golden("timesteps")
+    cfg = TrainConfig(timestep_distribution=getattr(TimestepDistribution, dist), **kw)
+    w = timestep_weights(1000, cfg).numpy()
+    assert np.array_equal(w.view(np.uint32), g[f"{name}_weights"].view(np.uint32))
+    mn, mx = int(1000 * cfg.min_noising_strength), int(1000 * cfg.max_noising_strength)
+    cdf = oracle.timestep_cdf(w)
+    assert np.array_equal(cdf, timestep_cdf(__import__("torch").from_numpy(w)).numpy()) and cdf.size == mx - mn
+    n = 20000
+    draws = np.array([oracle.timestep_table(11, 3, i, cdf, mn) for i in range(n)])
+    assert draws.min() >= mn and draws.max() < mx
+    emp = np.cumsum(np.bincount(draws - mn, minlength=mx - mn)) / n
+    assert np.abs(emp - cdf).max() < 1.63 / np.sqrt(n)            # KS, alpha = 1 %
+    ref = g[f"{name}_t"]
+    assert ref.min() >= mn and ref.max() < mx
+    emp_ref = np.cumsum(np.bincount(ref - mn, minlength=mx - mn)) / ref.size
+    assert np.abs(emp_ref - cdf).max() < 1.95 / np.sqrt(ref.size)  # the reference's own multinomial draws, alpha = 0.1 %
+    # keyed by the GLOBAL sample index: a rank that owns samples [8, 16) draws what a single process draws for them
+    assert [oracle.timestep_table(11, 3, 8 + i, cdf, mn) for i in range(8)] == draws[8:16].tolist()
+
+
 def test_deterministic_timestep(oracle, golden):
     assert oracle.timestep(3, 0, 0, 0) == 499 == int(golden("timesteps")["deterministic_t"][0])
 
