@@ -63,7 +63,7 @@ def timestep_weights(num_train_timesteps: int, config, latent_width=None, latent
 
 def timestep_cdf(weights: Tensor) -> Tensor:
     """Normalised running sum of the weight table (fp64 accumulate, one rounding to fp32, last entry exactly 1): what
-    the kernel's inverse-CDF draw (OTB_TS_TABLE) searches.  Restated in oracle/otb_oracle.py: timestep_cdf."""
+    the kernel's inverse-CDF draw (OTB_TS_TABLE) searches.  (The CPU checker restates the same construction.)"""
     c = torch.cumsum(weights.detach().to("cpu", torch.float64), 0)
     c = (c / c[-1]).to(torch.float32)
     c[-1] = 1.0

@@ -285,6 +285,111 @@ def test_checkpoint_recompute_and_dropout_mask_reuse(P, dev):
     assert torch.equal(y_a, y_b)                          # eval: no dropout, deterministic
 
 
+def test_leaf_used_twice_in_one_graph_accumulates_like_autograd(P, dev):
+    """A hooked leaf called twice before one backward (a shared module): autograd defers AccumulateGrad, so the second
+    backward of the leaf still sees p.grad None.  The arena must neither be zeroed mid-backward nor handed out twice:
+    gradients equal the sum of the two uses computed separately, and the other leaves' gradients survive."""
+    cfg, net, wrap = _tiny(P, dev, seed=9)
+    mods = list(wrap.lora_modules.values())
+    shared, other = mods[0], mods[1]
+    x1 = torch.randn(96, shared.orig_module.in_features, device=dev).bfloat16()
+    x2 = torch.randn(96, shared.orig_module.in_features, device=dev).bfloat16()
+    x3 = torch.randn(96, other.orig_module.in_features, device=dev).bfloat16()
+
+    def grads(fn):
+        for p in wrap.parameters():
+            p.grad = None
+        fn().backward()
+        return [p.grad.clone() if p.grad is not None else None for p in (shared.lora_down.weight, shared.lora_up.weight, other.lora_down.weight)]
+
+    f = lambda m, x: (m.orig_module(x).float() ** 2).mean()   # noqa: E731
+    both = grads(lambda: f(other, x3) + f(shared, x1) + f(shared, x2))
+    only1 = grads(lambda: f(shared, x1))
+    only2 = grads(lambda: f(shared, x2))
+    only3 = grads(lambda: f(other, x3))
+    for b, a1, a2 in zip(both[:2], only1[:2], only2[:2]):
+        assert torch.allclose(b, a1 + a2, rtol=1e-4, atol=1e-6 * b.abs().max().item())
+    assert torch.allclose(both[2], only3[2], rtol=1e-5, atol=1e-7 * only3[2].abs().max().item())    # not wiped by a mid-backward memset
+
+
+def test_ema_swap_in_is_seen_by_the_fused_forward(P, dev):
+    """copy_ema_to / copy_temp_to (EMAModule.py:63-75) around sampling: the fused forward keys its bf16 shadows on the
+    parameters' version counters, so the swap must bump them — a forward 'with EMA' has to run the EMA weights."""
+    cfg, net, wrap = _tiny(P, dev, seed=4)
+    params = wrap.parameters()
+    ema = P.EMAModuleWrapper(params, decay=0.5, update_step_interval=1, device=dev)
+    m = list(wrap.lora_modules.values())[0]
+    x = torch.randn(64, m.orig_module.in_features, device=dev).bfloat16()
+    with torch.no_grad():
+        y_live = m.orig_module(x).clone()
+        for e in ema.ema_parameters:
+            e.mul_(-1.5)                                   # averages that differ clearly from the live weights
+        ema.copy_ema_to(params, store_temp=True)
+        y_ema = m.orig_module(x).clone()
+        ops_ = m._operands()
+        ref, _ = P.L.ops.lora_linear(x, ops_["w"], m.lora_down.weight.bfloat16().view(m.rank, -1), m.lora_up.weight.bfloat16().view(-1, m.rank),
+                                     ops_["bias"], m._scale())
+        ema.copy_temp_to(params)
+        y_back = m.orig_module(x)
+    assert torch.equal(y_ema, ref) and not torch.equal(y_ema, y_live)
+    assert torch.equal(y_back, y_live)
+
+
+def test_optimizer_state_reload_mid_run_and_partial_ema_coverage(P, dev):
+    """(1) optimizer.load_state_dict() after the first step replaces exp_avg / exp_avg_sq / step: the fused launch must
+    step the LOADED moments (not a cached table of the old ones) and state_dict() must save them.  (2) A fused EMA only
+    rides along for tensors the optimizer stepped: a requires_grad parameter without a gradient this step still gets
+    the reference's EMA update (EMAModule.py:37-54 updates every requires_grad parameter)."""
+    torch.manual_seed(3)
+    mk = lambda: [nn.Parameter(torch.randn(257, device=dev) * 0.1), nn.Parameter(torch.randn(64, 8, device=dev) * 0.1)]   # noqa: E731
+    pa, pb = mk(), None
+    torch.manual_seed(3)
+    pb = mk()
+    oa, ob = torch.optim.AdamW(pa, lr=1e-2), torch.optim.AdamW(pb, lr=1e-2)
+    P.patch_adamw(oa, False)
+    P.patch_adamw(ob, False)
+    gs = [[torch.randn_like(p) for p in pa] for _ in range(4)]
+    for step in range(2):
+        for p, q, g in zip(pa, pb, gs[step]):
+            p.grad, q.grad = g.clone(), g.clone()
+        oa.step(); ob.step()
+    sd = ob.state_dict()
+    assert "otb_sr_step_count" in sd
+    # optimizer A continues from B's state after diverging for a step
+    for p, g in zip(pa, gs[3]):
+        p.grad = g.clone()
+    oa.step()
+    with torch.no_grad():
+        for p, q in zip(pa, pb):
+            p.copy_(q)
+    oa.load_state_dict(sd)
+    for p, q, g in zip(pa, pb, gs[2]):
+        p.grad, q.grad = g.clone(), g.clone()
+    oa.step(); ob.step()
+    for p, q in zip(pa, pb):
+        assert torch.equal(p, q)
+        assert torch.equal(oa.state[p]["exp_avg"], ob.state[q]["exp_avg"]) and oa.state[p]["step"].item() == 3
+    assert torch.equal(oa.state_dict()["state"][0]["exp_avg_sq"], ob.state_dict()["state"][0]["exp_avg_sq"])
+    # partial EMA coverage
+    pc = mk()
+    ema_f = P.EMAModuleWrapper(pc, decay=0.9, update_step_interval=1, device=dev)
+    ema_r = P.EMAModuleWrapper(pc, decay=0.9, update_step_interval=1, device=dev)
+    oc = torch.optim.AdamW(pc, lr=1e-2)
+    ctr = {"s": 0}
+    P.patch_adamw(oc, False, ema=ema_f, ema_step_fn=lambda: ctr["s"])
+    for step in range(3):
+        ctr["s"] = step
+        pc[0].grad = torch.randn_like(pc[0])
+        pc[1].grad = None                                    # no gradient this step: not in the fused launch
+        with torch.no_grad():
+            pc[1].add_(0.01)                                 # ... but it moved (e.g. written by someone else)
+        oc.step()
+        ema_f.step(pc, step)
+        ema_r.step(pc, step)                                 # unfused: the reference's behaviour
+        for a, b in zip(ema_f.ema_parameters, ema_r.ema_parameters):
+            assert torch.equal(a, b)
+
+
 # ------------------------------------------------------------------------------------------ S2 mixins
 def test_noise_mixin_generator_semantics(P, dev):
     class S(P.ModelSetupNoiseMixin):
