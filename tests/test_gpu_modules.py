@@ -291,7 +291,7 @@ def test_leaf_used_twice_in_one_graph_accumulates_like_autograd(P, dev):
     gradients equal the sum of the two uses computed separately, and the other leaves' gradients survive."""
     cfg, net, wrap = _tiny(P, dev, seed=9)
     mods = list(wrap.lora_modules.values())
-    shared, other = mods[0], mods[1]
+    shared, other = mods[0], mods[4]            # proj_in and attn1.to_out.0: plain Linear leaves outside any sibling group
     x1 = torch.randn(96, shared.orig_module.in_features, device=dev).bfloat16()
     x2 = torch.randn(96, shared.orig_module.in_features, device=dev).bfloat16()
     x3 = torch.randn(96, other.orig_module.in_features, device=dev).bfloat16()
