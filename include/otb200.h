@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define OTB_ABI_VERSION 4   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs.  3: otb_grad_exchange, otb_grad_norm_from_partials.
-                               4: OTB_TS_TABLE (ts_cdf / ts_cdf_len appended to otb_noise_args) */
+                               4: OTB_TS_TABLE (ts_cdf / ts_cdf_len appended to otb_noise_args); otb_lora_grad_batched */
 
 /* error codes */
 #define OTB_OK            0
@@ -377,19 +377,32 @@ int otb_lora_linear(const otb_lora_linear_args* args, void* stream);
  * batched, the tiles of all members share one persistent grid.  Results are bit-identical to `count` single calls. */
 int otb_lora_linear_grouped(const otb_lora_linear_args* members, int32_t count, void* stream);
 
-/* dA[R,K] (+)= Gs[M,R]^T x[M,K] ;  dB[N,R] (+)= dy[M,N]^T Ts[M,R]   (fp32 accumulate via
- * split-M partial sums; outputs must be zero or hold the running accumulation). */
+/* dA[R,K] += Gs[M,R]^T x[M,K] ;  dB[N,R] += dy[M,N]^T Ts[M,R]   (fp32; the outputs must hold zero or the running
+ * accumulation of earlier micro-batches).  Two of the ~7 GEMMs autograd runs per leaf for LoRAModule.forward
+ * (modules/module/LoRAModule.py:319-323).  The sum over M is formed in a fixed order: results are bit-identical from
+ * run to run. */
 typedef struct otb_lora_grad_args {
     const void* x;     /* [M, K] bf16 */
     const void* dy;    /* [M, N] bf16 */
     const void* gs;    /* [M, R] bf16 */
     const void* ts;    /* [M, R] bf16 */
-    float*      dA;    /* [R, K] fp32 */
-    float*      dB;    /* [N, R] fp32 */
+    float*      dA;    /* [R, K] fp32, or NULL */
+    float*      dB;    /* [N, R] fp32, or NULL */
     int32_t M, N, K, R;
 } otb_lora_grad_args;
 
+/* one leaf, M not split (one CTA per 128 output columns) */
 int otb_lora_grad_ab(const otb_lora_grad_args* args, void* stream);
+
+/* Up to OTB_GRAD_BATCH_MAX leaves of ANY shapes as ONE persistent launch: dA / dB feed nothing until the optimizer, so
+ * the host queues the leaves of a backward pass and flushes them in batches (722 latency-bound launches per SDXL step
+ * in the first version).  `workspace` (device memory, 256-byte aligned, at least otb_lora_grad_workspace_bytes(leaves,
+ * count) bytes, or NULL) lets small batches and very long M be split over more CTAs; split partial sums are combined
+ * in split order by the last CTA to arrive.  Its first 64 KB are arrival counters: zero before the FIRST use, left
+ * zero by every launch.  Launches that share a workspace must be ordered on one stream. */
+#define OTB_GRAD_BATCH_MAX 32
+int otb_lora_grad_batched(const otb_lora_grad_args* leaves, int32_t count, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t otb_lora_grad_workspace_bytes(const otb_lora_grad_args* leaves, int32_t count);
 
 /* Utility used by tests and the data-parallel bucket path: fp32 <-> bf16 casts with
  * round-to-nearest-even, and a device-side Philox dump for known-answer tests. */

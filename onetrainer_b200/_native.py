@@ -122,6 +122,7 @@ class LoraGradArgs(C.Structure):
 
 
 MAX_RANKS = 16           # OTB_MAX_RANKS
+GRAD_BATCH_MAX = 32      # OTB_GRAD_BATCH_MAX
 
 
 class GradExchangeArgs(C.Structure):
@@ -155,6 +156,8 @@ SYMBOLS = {
     "otb_lora_linear": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
     "otb_lora_linear_grouped": (C.c_int, [C.POINTER(LoraLinearArgs), C.c_int32, _vp]),
     "otb_lora_grad_ab": (C.c_int, [C.POINTER(LoraGradArgs), _vp]),
+    "otb_lora_grad_batched": (C.c_int, [C.POINTER(LoraGradArgs), C.c_int32, _vp, _i64, _vp]),
+    "otb_lora_grad_workspace_bytes": (_i64, [C.POINTER(LoraGradArgs), C.c_int32]),
     "otb_philox_dump": (C.c_int, [_u64, _u64, _u32, _i64, _i64, _vp, _vp]),
     "otb_struct_sizes": (C.c_int, [C.POINTER(C.c_int32)]),
 }

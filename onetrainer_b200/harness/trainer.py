@@ -284,9 +284,11 @@ def standin_betas():
     return scaled_linear_betas()
 
 
-def synthetic_batch(kind: str, batch_size: int, device, seed: int = 1234, latent_hw: int | None = None, masked: bool = False) -> dict:
-    """Seeded synthetic batch with the dataloader's keys."""
-    g = torch.Generator(device="cpu").manual_seed(seed + dp.rank())
+def synthetic_batch(kind: str, batch_size: int, device, seed: int = 1234, latent_hw: int | None = None, masked: bool = False,
+                    rank: int | None = None) -> dict:
+    """Seeded synthetic batch with the dataloader's keys.  `rank` selects another rank's batch
+    (the data-parallel self-check rebuilds the global batch on one GPU)."""
+    g = torch.Generator(device="cpu").manual_seed(seed + (dp.rank() if rank is None else rank))
     if kind in ("flux", "tiny_flux"):          # FLUX.1: 16-channel latents, T5 states [B,512,4096], CLIP pooled [B,768] (SURVEY.md §8d)
         hw = latent_hw or (128 if kind == "flux" else 16)
         ctx, pooled, n_txt = (4096, 768, 512) if kind == "flux" else (64, 32, 8)

@@ -193,18 +193,20 @@ class _LoraGroupFn(torch.autograd.Function):
 
 
 def _launch_grad_ab(mod, x2, dy, gs, ts, dA, dB, ret_a, ret_b) -> None:
-    """dA / dB of one leaf on the side stream (see ops.SideGrads) unless autograd will READ the returned tensor on
-    this stream: it only ADOPTS the arena slices (or gets None when the kernel accumulates in place); a foreign
-    p.grad (someone replaced it) makes autograd add the returned tensor here, so that case stays in order."""
+    """dA / dB of one leaf: queued for the batched launch (ops.GradQueue) unless something will READ the result before
+    the backward pass ends.  Autograd only ADOPTS the arena slices (or gets None when the kernel accumulates in place);
+    a temporary (someone replaced p.grad, or the leaf is used twice in one graph) is added by autograd right away, and
+    a post-accumulate-grad hook (optimizer-in-backward, GenericTrainer.py:550-557) steps the parameter right away — in
+    both cases the kernel runs now."""
     arena = mod._wrapper_slot[0].grad_arena if mod._wrapper_slot is not None else None
 
     def outside(t) -> bool:
         return t is not None and (arena is None or not arena.data_ptr() <= t.data_ptr() < arena.data_ptr() + arena.numel() * arena.element_size())
-    foreign = outside(dA) or outside(dB)
-    if ops.side_grads.enabled and not foreign:
-        ops.side_grads.launch(lambda: ops.lora_grad_ab(x2, dy, gs, ts, dA, dB), dy.device, (x2, dy, gs, ts, dA, dB))
-    else:
+    hooked = any(getattr(p, "_post_accumulate_grad_hooks", None) for p in (mod.lora_down.weight, mod.lora_up.weight))
+    if outside(dA) or outside(dB) or hooked:
         ops.lora_grad_ab(x2, dy, gs, ts, dA, dB)
+    else:
+        ops.grad_queue.push((x2, dy, gs, ts, dA, dB), dy.device)
 
 
 class SiblingGroup:

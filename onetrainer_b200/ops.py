@@ -55,66 +55,53 @@ class PinnedRing:
 
 
 # --------------------------------------------------------------------------------------
-# side stream for the weight-gradient kernel
+# deferred, batched weight gradients
 # --------------------------------------------------------------------------------------
-class SideGrads:
-    """Runs K-a' (dA/dB) on a second stream so that it overlaps whatever backward launches next.
+class GradQueue:
+    """Queues the dA / dB contractions of the leaves of one backward pass and flushes them in batches (K-a').
 
-    dA/dB of a leaf feed nothing until the optimizer, but the kernel that computes them (a 10-30 us,
-    latency-bound streaming pass) sat on the critical path between that leaf's dX GEMM and the next
-    backward kernel.  Forked after the dX launch (it needs Gs) and joined (a) every `JOIN_EVERY` leaves, which
-    bounds the extra lifetime of the operands it reads, and (b) by an autograd-engine callback when the backward
-    pass ends — so when `.backward()` returns, every gradient is ordered on the caller's stream exactly as before.
-    Works the same under CUDA-graph capture (a fork/join inside the captured stream).  OTB_SIDE_GRADS=0 disables it.
-    """
-    JOIN_EVERY = 8
+    dA / dB of a leaf feed nothing until the optimizer, but one launch per leaf (722 per SDXL step) is a 10 us,
+    latency-bound streaming pass.  A leaf's backward therefore only RECORDS its operands here; every `FLUSH_LEAVES`
+    leaves — and, through an autograd-engine callback, when the backward pass ends — the queue is handed to
+    otb_lora_grad_batched, one persistent launch per 32 leaves that keeps every SM streaming.  When `.backward()`
+    returns, every gradient has been launched on the caller's stream, exactly as before.  The queue holds references
+    to the operands until the flush, which bounds their extra lifetime to one batch.  Works the same under CUDA-graph
+    capture.  OTB_GRAD_BATCH=1 launches every leaf by itself (A/B runs)."""
+    FLUSH_LEAVES = 32
 
     def __init__(self):
         import os
-        self.enabled = os.environ.get("OTB_SIDE_GRADS", "1") != "0"
-        self.JOIN_EVERY = int(os.environ.get("OTB_SIDE_JOIN_EVERY", self.JOIN_EVERY))
-        self._streams = {}
-        self._pending = {}      # device index -> list of tensors kept alive until the join
+        self.FLUSH_LEAVES = max(1, int(os.environ.get("OTB_GRAD_BATCH", self.FLUSH_LEAVES)))
+        self._pending: dict[int, list] = {}
 
-    def stream(self, device: torch.device) -> torch.cuda.Stream:
+    def push(self, leaf: tuple, device: torch.device) -> None:
+        """leaf = (x, dy, gs, ts, dA, dB); launched at the latest when the current backward pass ends."""
+        if self.FLUSH_LEAVES == 1 or torch._C._current_graph_task_id() < 0:
+            lora_grad_batched([leaf])           # outside a backward pass nobody would flush the queue
+            return
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        st = self._streams.get(idx)
-        if st is None:
-            st = self._streams[idx] = torch.cuda.Stream(device=device)
-        return st
-
-    def launch(self, fn, device: torch.device, keep_alive: tuple) -> None:
-        """Run `fn()` (which launches on the current stream) on the side stream, ordered after everything
-        already queued on the current stream."""
-        idx = device.index if device.index is not None else torch.cuda.current_device()
-        side = self.stream(device)
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side):
-            fn()
         held = self._pending.setdefault(idx, [])
-        held.append(keep_alive)
+        held.append(leaf)
         if len(held) == 1:
-            # first pending launch since the last join: make sure this backward pass ends with one (stateless on purpose —
-            # a backward that raises never runs its callbacks, and must not leave a flag behind that disarms the next one)
-            torch.autograd.Variable._execution_engine.queue_callback(self.join_all)
-        if len(held) >= self.JOIN_EVERY:
-            self.join(device)
+            # first pending leaf since the last flush: make sure this backward pass ends with one (registered per flush on
+            # purpose — a backward that raises never runs its callbacks and must not leave a flag behind)
+            torch.autograd.Variable._execution_engine.queue_callback(self.flush_all)
+        if len(held) >= self.FLUSH_LEAVES:
+            self.flush(idx)
 
-    def join(self, device: torch.device) -> None:
-        idx = device.index if device.index is not None else torch.cuda.current_device()
-        if self._pending.get(idx):
-            torch.cuda.current_stream(device).wait_stream(self._streams[idx])
+    def flush(self, idx: int) -> None:
+        held = self._pending.get(idx)
+        if held:
             self._pending[idx] = []
+            with torch.cuda.device(idx):
+                lora_grad_batched(held)
 
-    def join_all(self) -> None:
-        for idx, held in self._pending.items():
-            if held:
-                dev = torch.device("cuda", idx)
-                torch.cuda.current_stream(dev).wait_stream(self._streams[idx])
-                self._pending[idx] = []
+    def flush_all(self) -> None:
+        for idx in list(self._pending):
+            self.flush(idx)
 
 
-side_grads = SideGrads()
+grad_queue = GradQueue()
 
 
 def _aligned16(*tensors) -> bool:
@@ -193,18 +180,63 @@ def lora_linear_grouped(xs: list[torch.Tensor], ws: list[torch.Tensor], downs: l
     return ys, ts
 
 
+class _GradWorkspace:
+    """Per-device scratch of the batched weight-gradient kernel: 64 KB of arrival counters (zero before the first use,
+    left zero by every launch) followed by the partial tiles of split problems.  Grown on demand — a new, zeroed buffer;
+    the old one stays alive until every launch that used it has been ordered before the new one's first use, which
+    stream order on the single stream that uses it guarantees."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, device, nbytes: int) -> torch.Tensor:
+        key = str(device)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            size = max(nbytes, 8 << 20) * 3 // 2
+            buf = self._bufs[key] = torch.zeros((size,), dtype=torch.uint8, device=device)
+        return buf
+
+
+_grad_ws = _GradWorkspace()
+
+
+def lora_grad_batched(leaves: list[tuple]) -> None:
+    """dA[R,K] += gs^T x ; dB[N,R] += dy^T ts for a LIST of leaves (x, dy, gs, ts, dA, dB) in as few launches as possible
+    (otb_lora_grad_batched: up to 32 leaves each).  Fixed-order fp32 sums: bit-identical from run to run."""
+    if not leaves:
+        return
+    arr = (N.LoraGradArgs * len(leaves))()
+    for i, (x, dy, gs, ts, dA, dB) in enumerate(leaves):
+        N.require_cuda(x, dy, gs, ts, dA, dB)
+        for t in (dA, dB):
+            if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+                raise ValueError("lora_grad: dA / dB must be contiguous fp32")
+        for t in (x, dy, gs, ts):
+            if t is not None and (t.dtype != torch.bfloat16 or not t.is_contiguous() or t.dim() != 2):
+                raise ValueError("lora_grad: x / dy / gs / ts must be contiguous 2-D bf16 tensors")
+        M = x.shape[0] if x is not None else dy.shape[0]
+        R = gs.shape[1] if gs is not None else ts.shape[1]
+        arr[i] = N.LoraGradArgs(x=N.ptr(x), dy=N.ptr(dy), gs=N.ptr(gs), ts=N.ptr(ts), dA=N.ptr(dA), dB=N.ptr(dB),
+                                M=M, N=dy.shape[1] if dy is not None else 0, K=x.shape[1] if x is not None else 0, R=R)
+    dev = next(t for t in leaves[0] if t is not None).device
+    lib = N.lib()
+    for lo in range(0, len(leaves), N.GRAD_BATCH_MAX):
+        n = min(N.GRAD_BATCH_MAX, len(leaves) - lo)
+        sub = C.cast(C.byref(arr, lo * C.sizeof(N.LoraGradArgs)), C.POINTER(N.LoraGradArgs))
+        need = lib.otb_lora_grad_workspace_bytes(sub, n)
+        if need < 0:
+            N.check(lib.otb_lora_grad_batched(sub, n, None, 0, _stream()), "otb_lora_grad_batched")      # reports the bad argument
+        ws = _grad_ws.get(dev, int(need))
+        N.check(lib.otb_lora_grad_batched(sub, n, ws.data_ptr(), ws.numel(), _stream()), "otb_lora_grad_batched")
+        _count()
+
+
 def lora_grad_ab(x, dy, gs, ts, dA: torch.Tensor | None, dB: torch.Tensor | None) -> None:
-    """dA[R,K] += gs^T x ; dB[N,R] += dy^T ts  (fp32 accumulation into the given buffers)."""
-    N.require_cuda(x, dy, gs, ts, dA, dB)
-    M = x.shape[0] if x is not None else dy.shape[0]
-    R = gs.shape[1] if gs is not None else ts.shape[1]
-    for t in (dA, dB):
-        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
-            raise ValueError("lora_grad_ab: dA / dB must be contiguous fp32")
-    a = N.LoraGradArgs(x=N.ptr(x), dy=N.ptr(dy), gs=N.ptr(gs), ts=N.ptr(ts), dA=N.ptr(dA), dB=N.ptr(dB),
-                       M=M, N=dy.shape[1] if dy is not None else 0, K=x.shape[1] if x is not None else 0, R=R)
-    N.check(N.lib().otb_lora_grad_ab(C.byref(a), _stream()), "otb_lora_grad_ab")
-    _count()
+    """dA[R,K] += gs^T x ; dB[N,R] += dy^T ts  for one leaf (a batch of one)."""
+    if dA is None and dB is None:
+        return
+    lora_grad_batched([(x, dy, gs, ts, dA, dB)])
 
 
 # --------------------------------------------------------------------------------------

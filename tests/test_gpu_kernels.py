@@ -697,33 +697,84 @@ def test_lora_linear_random_shapes_vs_fp32_torch(K, dev):
             assert (err <= tol).all(), (case, M, N, K_, R, g, err.max().item())
 
 
-def test_lora_grad_ab_random_shapes_vs_fp32_torch(K, dev, monkeypatch):
+def _grad_problem(dev, case, M, N, K_, R):
+    gen = torch.Generator(device=dev).manual_seed(1000 + case)
+    x = torch.randn(M, K_, device=dev, generator=gen).bfloat16()
+    dy = torch.randn(M, N, device=dev, generator=gen).bfloat16()
+    gs = torch.randn(M, R, device=dev, generator=gen).bfloat16()
+    ts = torch.randn(M, R, device=dev, generator=gen).bfloat16()
+    return x, dy, gs, ts
+
+
+def test_lora_grad_ab_random_shapes_vs_fp32_torch(K, dev):
     """Differential sweep of K-a' (tcgen05, MN-major operands read straight from TMA boxes): 24 seeded random problems
-    against fp32 torch, both kernels (tcgen05 default and the mma.sync one behind OTB_KGRAD_TC=0), including dA-only /
-    dB-only calls, rows that end inside a 128-row stage and ranks from 8 to 64; a second call accumulates."""
+    against fp32 torch, including dA-only / dB-only calls, rows that end inside a 128-row stage and ranks from 8 to 64;
+    a second call accumulates; and the result is bit-identical from call to call (fixed-order sums, no atomics)."""
     rng = np.random.default_rng(99)
     for case in range(24):
         M = int(rng.choice([1, 64, 127, 128, 129, 300, 1000, 2048, 4097]))
         N = int(rng.integers(1, 180)) * 8
         K_ = int(rng.integers(1, 180)) * 8
         R = int(rng.choice([8, 16, 24, 32, 64]))
-        gen = torch.Generator(device=dev).manual_seed(1000 + case)
-        x = torch.randn(M, K_, device=dev, generator=gen).bfloat16()
-        dy = torch.randn(M, N, device=dev, generator=gen).bfloat16()
-        gs = torch.randn(M, R, device=dev, generator=gen).bfloat16()
-        ts = torch.randn(M, R, device=dev, generator=gen).bfloat16()
+        x, dy, gs, ts = _grad_problem(dev, case, M, N, K_, R)
         rA, rB = gs.float().T @ x.float(), dy.float().T @ ts.float()
         which = case % 3                       # 0: both, 1: dA only, 2: dB only
-        for tc in ("1", "0"):
-            monkeypatch.setenv("OTB_KGRAD_TC", tc)
+        runs = []
+        for _ in range(2):
             dA = torch.zeros(R, K_, device=dev) if which != 2 else None
             dB = torch.zeros(N, R, device=dev) if which != 1 else None
             K.ops.lora_grad_ab(x, dy, gs, ts, dA, dB)
             K.ops.lora_grad_ab(x, dy, gs, ts, dA, dB)
             if dA is not None:
-                assert torch.allclose(dA, 2 * rA, rtol=1e-4, atol=2e-3 * rA.abs().max().item() + 1e-5), (case, tc, M, N, K_, R)
+                assert torch.allclose(dA, 2 * rA, rtol=1e-4, atol=2e-3 * rA.abs().max().item() + 1e-5), (case, M, N, K_, R)
             if dB is not None:
-                assert torch.allclose(dB, 2 * rB, rtol=1e-4, atol=2e-3 * rB.abs().max().item() + 1e-5), (case, tc, M, N, K_, R)
+                assert torch.allclose(dB, 2 * rB, rtol=1e-4, atol=2e-3 * rB.abs().max().item() + 1e-5), (case, M, N, K_, R)
+            runs.append((dA, dB))
+        for a, b in zip(*runs):
+            assert a is None or torch.equal(a, b), (case, "not reproducible")
+
+
+def test_lora_grad_batched_mixed_shapes_split_and_unsplit_agree(K, dev, monkeypatch):
+    """otb_lora_grad_batched: leaves of DIFFERENT shapes in one launch (the queue of a backward pass), more than 32
+    leaves (several launches), M long enough to be split through the workspace, and the single-leaf entry point without
+    a workspace (never split).  All variants compute the same fixed-order fp32 sums per 128-row stage, so they agree to
+    fp32 re-association (1e-6 relative), each one is bit-reproducible, and all match fp32 torch."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    shapes = [(4096, 1280, 1280, 32), (308, 1280, 2048, 32), (16384, 640, 640, 32), (1000, 328, 136, 16), (129, 72, 520, 8), (20000, 64, 192, 64)]
+    shapes += [(int(rng.choice([64, 300, 1024, 2049])), int(rng.integers(1, 60)) * 8, int(rng.integers(1, 60)) * 8, int(rng.choice([8, 16, 32]))) for _ in range(34)]
+    probs = [_grad_problem(dev, 50 + i, *s) for i, s in enumerate(shapes)]
+    refs = [(gs.float().T @ x.float(), dy.float().T @ ts.float()) for x, dy, gs, ts in probs]
+
+    def run_batched():
+        outs = [(torch.zeros(s[3], s[2], device=dev), torch.zeros(s[1], s[3], device=dev)) for s in shapes]
+        K.ops.lora_grad_batched([(*p, dA, dB) for p, (dA, dB) in zip(probs, outs)])
+        return outs
+
+    def run_single_nosplit():
+        outs = [(torch.zeros(s[3], s[2], device=dev), torch.zeros(s[1], s[3], device=dev)) for s in shapes]
+        for (x, dy, gs, ts), (dA, dB), s in zip(probs, outs, shapes):
+            a = K.N.LoraGradArgs(x=x.data_ptr(), dy=dy.data_ptr(), gs=gs.data_ptr(), ts=ts.data_ptr(), dA=dA.data_ptr(), dB=dB.data_ptr(),
+                                 M=s[0], N=s[1], K=s[2], R=s[3])
+            K.N.check(K.N.lib().otb_lora_grad_ab(C.byref(a), torch.cuda.current_stream().cuda_stream), "otb_lora_grad_ab")
+        return outs
+
+    b1, b2 = run_batched(), run_batched()
+    single = run_single_nosplit()
+    monkeypatch.setenv("OTB_KGRAD_SPLIT_ROWS", "512")          # force the workspace path on almost every problem
+    s1, s2 = run_batched(), run_batched()
+    one = [(torch.zeros(s[3], s[2], device=dev), torch.zeros(s[1], s[3], device=dev)) for s in shapes]
+    for p, (dA, dB) in zip(probs, one):
+        K.ops.lora_grad_ab(*p, dA, dB)                         # batch of one WITH a workspace: split to fill the chip
+    for i, ((rA, rB), s) in enumerate(zip(refs, shapes)):
+        for j, r in enumerate((rA, rB)):
+            assert torch.equal(b1[i][j], b2[i][j]) and torch.equal(s1[i][j], s2[i][j]), (i, s, "not reproducible")
+            tol = dict(rtol=2e-5, atol=2e-6 * r.abs().max().item())
+            assert torch.allclose(b1[i][j], single[i][j], **tol) and torch.allclose(s1[i][j], single[i][j], **tol), (i, s)
+            assert torch.allclose(one[i][j], single[i][j], **tol), (i, s)
+            assert torch.allclose(b1[i][j], r, rtol=1e-4, atol=2e-3 * r.abs().max().item() + 1e-5), (i, s)
+    with pytest.raises(ValueError, match="bf16"):
+        K.ops.lora_grad_batched([(probs[0][0].float(), *probs[0][1:], *b1[0])])
 
 
 def _flux_pack(t, C, H, W):

@@ -218,6 +218,35 @@ def test_wrapper_network_grads_vs_torch_restatement(P, dev):
             assert (mine - r).abs().max().item() <= 0.02 * scale + 1e-7, f"{k} {what}: {(mine - r).abs().max().item()} vs scale {scale}"
 
 
+def test_lora_gradients_are_bit_reproducible(P, dev):
+    """dA / dB are fixed-order fp32 sums (no atomics): with the stand-in's attention on its deterministic (math) backend,
+    two forward + backward passes of the whole hooked network give bit-identical LoRA gradients — as cuBLAS does for the
+    reference — both with every leaf launched by itself and with the leaves batched by the queue."""
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    cfg, net, wrap = _tiny(P, dev, seed=12)
+    x, t, ctx = _inputs(dev, seed=4)
+    params = wrap.parameters()
+
+    def run():
+        for p in params:
+            p.grad = None
+        with sdpa_kernel(SDPBackend.MATH), torch.autocast("cuda", dtype=torch.bfloat16):
+            (net(x, t, ctx).sample.float() ** 2).mean().backward()
+        return [p.grad.clone() for p in params]
+
+    g1, g2 = run(), run()
+    assert all(torch.equal(a, b) for a, b in zip(g1, g2))
+    q = P.L.ops.grad_queue
+    saved = q.FLUSH_LEAVES
+    try:
+        q.FLUSH_LEAVES = 1                       # every leaf launched by itself: split over M through the workspace
+        g3 = run()
+    finally:
+        q.FLUSH_LEAVES = saved
+    for a, b in zip(g1, g3):                     # same per-stage sums, re-associated across splits
+        assert torch.allclose(a, b, rtol=2e-5, atol=2e-6 * a.abs().max().item())
+
+
 def test_gradient_accumulation_and_zero_grad_semantics(P, dev):
     """Two micro-batches accumulate in place in the arena (autograd receives None for the second), and a new
     step after zero_grad(set_to_none=True) starts from zero with ONE memset for the whole wrapper."""
