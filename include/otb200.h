@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define OTB_ABI_VERSION 4   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs.  3: otb_grad_exchange, otb_grad_norm_from_partials.
-                               4: OTB_TS_TABLE (ts_cdf / ts_cdf_len appended to otb_noise_args); otb_lora_grad_batched */
+                               4: OTB_TS_TABLE (ts_cdf / ts_cdf_len appended to otb_noise_args); otb_lora_grad_batched; otb_lora_linear_grouped takes up to 32 members */
 
 /* error codes */
 #define OTB_OK            0
@@ -370,11 +370,15 @@ typedef struct otb_lora_linear_args {
 
 int otb_lora_linear(const otb_lora_linear_args* args, void* stream);
 
-/* Up to three problems of the SAME shape (M, N, K, rank, dropout_p) as ONE launch: members[i] is an ordinary
+/* Up to OTB_LORA_GROUP_MAX problems of the SAME shape (M, N, K, rank, dropout_p) as ONE launch: members[i] is an ordinary
  * otb_lora_linear_args (own x, w, down, up, bias, y, t_out, scale, dropout key).  The reference calls the q / k / v
  * projections of an attention as three separate module forwards (diffusers Attention -> LoRAModule.forward
  * modules/module/LoRAModule.py:319-323, three times) and autograd runs their three dX GEMMs one after another;
- * batched, the tiles of all members share one persistent grid.  Results are bit-identical to `count` single calls. */
+ * batched, the tiles of all members share one persistent grid.  The wide form (more than three members) is for the K / V
+ * projections of the text context, which read the SAME tensor in every cross-attention of the network (140 leaves in
+ * SDXL, M = 77 * batch): one launch per 32 of them instead of one 18 us launch per pair.  Results are bit-identical to
+ * `count` single calls. */
+#define OTB_LORA_GROUP_MAX 32
 int otb_lora_linear_grouped(const otb_lora_linear_args* members, int32_t count, void* stream);
 
 /* dA[R,K] += Gs[M,R]^T x[M,K] ;  dB[N,R] += dy[M,N]^T Ts[M,R]   (fp32; the outputs must hold zero or the running

@@ -123,6 +123,7 @@ class LoraGradArgs(C.Structure):
 
 MAX_RANKS = 16           # OTB_MAX_RANKS
 GRAD_BATCH_MAX = 32      # OTB_GRAD_BATCH_MAX
+LORA_GROUP_MAX = 32      # OTB_LORA_GROUP_MAX
 
 
 class GradExchangeArgs(C.Structure):

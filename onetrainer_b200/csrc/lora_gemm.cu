@@ -358,7 +358,8 @@ template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.
 // projections of a cross-attention — or their three dX GEMMs).  Single-leaf launches leave a third of the chip idle
 // on the most frequent SDXL shape (64 tiles of 256 x 320 on 74 CTA pairs, no second tile to hide the epilogue
 // behind); a group of three is 288 tiles over 74 pairs in ~4 full rounds with the epilogue overlapped.
-constexpr int V3_MAX_GROUP = 3;
+constexpr int V3_MAX_GROUP = 3;            // the common launch: a leaf, or the q/k/v (k/v) siblings of one attention
+constexpr int V3_BIG_GROUP = OTB_LORA_GROUP_MAX;   // the wide launch: every context K/V projection of a network at once (same x)
 struct V3Member {
     const void* bias;
     uint16_t* y;
@@ -367,13 +368,15 @@ struct V3Member {
     float scale;
     int bias_dtype;
 };
+template <int G>
 struct V3Maps {            // one tensor-map set per member of the group
-    CUtensorMap x[V3_MAX_GROUP], w[V3_MAX_GROUP], w2[V3_MAX_GROUP], dn[V3_MAX_GROUP], up[V3_MAX_GROUP], y[V3_MAX_GROUP];
+    CUtensorMap x[G], w[G], w2[G], dn[G], up[G], y[G];
 };
+template <int G>
 struct GemmParams3 {
     GemmParams g;          // g.tile_n: width of the pair tile; g.n_tiles (per member); g.stages; shapes common to the group
-    int groups;            // members in this launch (1..3)
-    V3Member mem[V3_MAX_GROUP];
+    int groups;            // members in this launch (1..G)
+    V3Member mem[G];
     int chunks;            // MMAs per 16-wide k-step over the fused [w; down] rows (NB = tile_n + Rp, NB / chunks <= 256)
     int up_chunks;         // MMAs per k-step of the rank-R GEMM (tile_n / up_chunks <= 256)
     int acc_stages;        // 2 when NB <= 256, else 1
@@ -455,8 +458,9 @@ __host__ __device__ inline SmemLayout3 make_layout3(int tile_n, int Rp, int stag
     return L;
 }
 
+template <int G>
 __global__ void __launch_bounds__(V3_THREADS, 1)
-lora_linear_kernel_v3(const __grid_constant__ V3Maps maps, const GemmParams3 q) {
+lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_constant__ GemmParams3<G> q) {
     const GemmParams& p = q.g;
     otb_pdl_trigger();                           // the next kernel in the stream may begin its own prologue
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -484,7 +488,7 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps maps, const GemmParams3 q) 
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bar_off + 8u * (2 * MAX_STAGES + 12));
 
     if (threadIdx.x == 0) {
-        for (int g = 0; g < q.groups; ++g) {
+        for (int g = 0; g < q.groups && g < V3_MAX_GROUP; ++g) {
             prefetch_tmap(&maps.x[g]); prefetch_tmap(&maps.w[g]); prefetch_tmap(&maps.y[g]);
             if (lora) { prefetch_tmap(&maps.w2[g]); prefetch_tmap(&maps.dn[g]); prefetch_tmap(&maps.up[g]); }
         }
@@ -963,8 +967,10 @@ KaPlan plan_v3(int M, int N, int K, int Rp, int pairs, int groups = 1) {
 }
 
 // `count` same-shape problems (count == 1: the plain call) as one v3 launch
+template <int G>
 int launch_v3(const otb_lora_linear_args* a, int count, void* stream, int tile_n, int max_pairs) {
-    GemmParams3 q;
+    static thread_local GemmParams3<G> q;          // the wide instantiation is 27 KB with its maps: keep both off the stack
+    static thread_local V3Maps<G> maps;
     GemmParams& p = q.g;
     p.M = a->M; p.N = a->N; p.K = a->K; p.R = a->R;
     p.Rp = (a->R + 15) / 16 * 16;
@@ -988,9 +994,8 @@ int launch_v3(const otb_lora_linear_args* a, int count, void* stream, int tile_n
     p.y = (uint16_t*)a->y; p.t_out = (uint16_t*)a->t_out;
 
     const int nbh = (p.tile_n + p.Rp) / q.chunks / 2, wch = p.tile_n / q.up_chunks / 2;
-    V3Maps maps;
     int rc;
-    for (int g = 0; g < V3_MAX_GROUP; ++g) {
+    for (int g = 0; g < G; ++g) {
         const otb_lora_linear_args* m = &a[g < count ? g : 0];         // unused slots mirror member 0
         q.mem[g] = V3Member{m->bias, (uint16_t*)m->y, (uint16_t*)m->t_out, m->seed, m->offset, m->scale, m->bias_dtype};
         if (g >= count) {
@@ -1020,7 +1025,7 @@ int launch_v3(const otb_lora_linear_args* a, int count, void* stream, int tile_n
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = otb_pdl_enabled() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, lora_linear_kernel_v3, maps, q);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lora_linear_kernel_v3<G>, maps, q);
     if (e != cudaSuccess) {
         otb_set_error("launch of lora_linear_kernel_v3 (%d x pair tile 256x%d, %d chunks, %d stages) failed: %s", count, p.tile_n, q.chunks,
                       stages, cudaGetErrorString(e));
@@ -1035,7 +1040,8 @@ int v3_max_pairs(int sms) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return sms / 2;
     if (cached_dev == dev) return cached;
-    (void)cudaFuncSetAttribute(lora_linear_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    (void)cudaFuncSetAttribute(lora_linear_kernel_v3<V3_MAX_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    (void)cudaFuncSetAttribute(lora_linear_kernel_v3<V3_BIG_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     cudaLaunchConfig_t probe = {};
     probe.gridDim = dim3((unsigned)(sms / 2 * 2));
     probe.blockDim = dim3(V3_THREADS);
@@ -1045,7 +1051,7 @@ int v3_max_pairs(int sms) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     probe.attrs = attr; probe.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, lora_linear_kernel_v3, &probe) != cudaSuccess || n <= 0) n = sms / 2;
+    if (cudaOccupancyMaxActiveClusters(&n, lora_linear_kernel_v3<V3_MAX_GROUP>, &probe) != cudaSuccess || n <= 0) n = sms / 2;
     (void)cudaGetLastError();
     cached_dev = dev; cached = n;
     return n;
@@ -1083,14 +1089,14 @@ extern "C" int otb_lora_linear(const otb_lora_linear_args* a, void* stream) {
         if (force == 3 || a->tile_n > 256) use3 = true;
         else if (force == 2 || a->M <= BM || (a->tile_n > 0 && !explicit3)) use3 = false;
         else use3 = p3.cycles < plan_v2(a->M, a->N, a->K, Rp, sms).cycles;
-        if (use3) return launch_v3(a, 1, stream, a->tile_n > 0 ? a->tile_n : p3.tile_n, pairs);
+        if (use3) return launch_v3<V3_MAX_GROUP>(a, 1, stream, a->tile_n > 0 ? a->tile_n : p3.tile_n, pairs);
         return launch_v2(a, stream);
     }
 
 }
 
 extern "C" int otb_lora_linear_grouped(const otb_lora_linear_args* members, int32_t count, void* stream) {
-    OTB_CHECK_ARG(members != nullptr && count >= 1 && count <= V3_MAX_GROUP, "group of %d (1..%d members)", count, V3_MAX_GROUP);
+    OTB_CHECK_ARG(members != nullptr && count >= 1 && count <= V3_BIG_GROUP, "group of %d (1..%d members)", count, V3_BIG_GROUP);
     for (int g = 0; g < count; ++g) {
         int rc = check_lora_linear_args(&members[g]);
         if (rc != OTB_OK) return rc;
@@ -1103,5 +1109,7 @@ extern "C" int otb_lora_linear_grouped(const otb_lora_linear_args* members, int3
     const int Rp = (members[0].R + 15) / 16 * 16;
     const int pairs = v3_max_pairs(otb_sm_count());
     const KaPlan plan = plan_v3(members[0].M, members[0].N, members[0].K, Rp, pairs, count);
-    return launch_v3(members, count, stream, members[0].tile_n > 0 ? members[0].tile_n : plan.tile_n, pairs);
+    const int tn = members[0].tile_n > 0 ? members[0].tile_n : plan.tile_n;
+    if (count <= V3_MAX_GROUP) return launch_v3<V3_MAX_GROUP>(members, count, stream, tn, pairs);
+    return launch_v3<V3_BIG_GROUP>(members, count, stream, tn, pairs);
 }

@@ -280,6 +280,41 @@ class SiblingGroup:
 
 
 SIBLING_SETS = (("to_q", "to_k", "to_v"), ("add_q_proj", "add_k_proj", "add_v_proj"))
+CONTEXT_LEAVES = ("attn2.to_k", "attn2.to_v")       # diffusers BasicTransformerBlock: cross-attention over the text context
+CONTEXT_ARG = ("encoder_hidden_states", 2)          # UNet2DConditionModel.forward(sample, timestep, encoder_hidden_states, ...)
+
+
+class ContextLaunch:
+    """The K / V projections of the text context, for EVERY cross-attention of the wrapped network, in a few wide launches.
+
+    All `attn2.to_k` / `attn2.to_v` leaves of a UNet read the same tensor — the `encoder_hidden_states` handed to the
+    network's forward — and there are many of them (SDXL: 140, M = 77 x batch rows each): as leaf-by-leaf launches they
+    are the worst-shaped GEMMs of the step (a long serial K over two or three row tiles, 18 us per k/v pair).  The
+    wrapper therefore hooks the NETWORK's forward (it already owns `orig_module`; the seam stays one forward per leaf):
+    when the network is called, every context leaf of matching width is computed on that tensor, 32 leaves per launch
+    (otb_lora_linear_grouped, wide form), and the outputs are parked on the leaves.  A leaf later called with that very
+    tensor (same storage, version, shape — the input is kept alive so the address cannot be recycled) returns its
+    parked output — also when a checkpointed block is re-run in backward; called with anything else it computes as
+    usual.  Backward is one `Gs` launch per 32 leaves (the context takes no gradient, so there is no dX) plus the
+    queued dA / dB.  OTB_CTX_GROUP=0 switches it off."""
+
+    def __init__(self, members: list["LoRAModule"]):
+        self.members = members
+
+    def run(self, ctx_rows: Tensor) -> None:
+        key = SiblingGroup._key_of(ctx_rows)
+        x2 = ctx_rows if ctx_rows.dtype == torch.bfloat16 else ctx_rows.to(torch.bfloat16)
+        x2 = x2.contiguous()
+        for lo in range(0, len(self.members), ops.N.LORA_GROUP_MAX):
+            mods = tuple(self.members[lo:lo + ops.N.LORA_GROUP_MAX])
+            ab = []
+            for m in mods:
+                ab += [m.lora_down.weight, m.lora_up.weight]
+            ys = _LoraGroupFn.apply(mods, x2, *ab)
+            for m, y in zip(mods, ys):
+                m._ctx_parked = (key, ctx_rows, y)
+
+
 
 
 # ---------------------------------------------------------------------------------------
@@ -447,6 +482,7 @@ class LoRAModule(PeftBase):
         self._own_versions = None
         self._base_cache = None         # (key, w_bf16, wt_bf16)
         self._scale_cache = None
+        self._ctx_parked = None         # output of the wrapper's wide context launch for this leaf (ContextLaunch)
         if orig_module is not None:
             self._check_supported(orig_module)
             self.initialize_weights()
@@ -557,8 +593,11 @@ class LoRAModule(PeftBase):
             x2 = x.reshape(-1, x.shape[-1])
         self._last_rows = x2.shape[0]          # read by bench.py to replay the step's GEMM shapes
         y2 = None
+        parked = self._ctx_parked               # (key, input kept alive, output) from the wrapper's context launch
+        if parked is not None and parked[0] == SiblingGroup._key_of(x2):
+            y2 = parked[2]
         grp = getattr(self, "_group", None)
-        if grp is not None and grp[0].enabled and not isinstance(om, nn.Conv2d):
+        if y2 is None and grp is not None and grp[0].enabled and not isinstance(om, nn.Conv2d):
             y2 = grp[0].forward(grp[1], x2)
         if y2 is None:
             if x2.dtype != torch.bfloat16:
@@ -608,6 +647,8 @@ class LoRAModuleWrapper:
         self._arena_key = None
         self._written_gen = {}
         self._written_pass = {}
+        self._net_hook = None
+        self.context_launches: list[ContextLaunch] = []
 
     def __create_modules(self, orig_module: nn.Module | None) -> dict[str, PeftBase]:
         found = {}
@@ -625,7 +666,42 @@ class LoRAModuleWrapper:
     def _bind(self) -> None:
         for i, m in enumerate(self._trainable()):
             m._wrapper_slot = (self, i)
+        self._build_context_launches()
         self._build_sibling_groups()
+
+    def _build_context_launches(self) -> None:
+        """One ContextLaunch per shape class of `attn2.to_k` / `attn2.to_v` leaves (SDXL: 2048 -> 1280 and 2048 -> 640)."""
+        import os
+        self.context_launches: list[ContextLaunch] = []
+        for m in self._trainable():
+            m._ctx_parked = None
+        if os.environ.get("OTB_CTX_GROUP", "1") == "0":
+            return
+        classes: dict[tuple, list[LoRAModule]] = {}
+        for name, m in self.lora_modules.items():
+            if isinstance(m, LoRAModule) and not isinstance(m, self.dummy_klass) and isinstance(m.orig_module, nn.Linear) \
+                    and name.endswith(CONTEXT_LEAVES):
+                om = m.orig_module
+                k = (om.in_features, om.out_features, m.rank, float(m.alpha), m.lora_down.weight.dtype, om.bias is None)
+                classes.setdefault(k, []).append(m)
+        self.context_launches = [ContextLaunch(ms) for ms in classes.values() if len(ms) >= 4]
+
+    def _on_network_forward(self, module, args, kwargs) -> None:
+        """Forward pre-hook of the wrapped network: start the wide context launches on `encoder_hidden_states`."""
+        if not self.context_launches:
+            return
+        ctx = kwargs.get(CONTEXT_ARG[0])
+        if ctx is None and len(args) > CONTEXT_ARG[1]:
+            ctx = args[CONTEXT_ARG[1]]
+        if not isinstance(ctx, Tensor) or not ctx.is_cuda or ctx.dim() < 2:
+            return
+        compute = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else ctx.dtype
+        if compute != torch.bfloat16:
+            return                              # the leaves will raise their own error for a non-bf16 compute dtype
+        rows = ctx.reshape(-1, ctx.shape[-1])
+        for launch in self.context_launches:
+            if launch.members[0].orig_module.in_features == rows.shape[1]:
+                launch.run(rows)
 
     def _build_sibling_groups(self) -> None:
         """Group the q/k/v-style projections that share a parent module and a shape (SiblingGroup).  With equal in_features
@@ -637,7 +713,10 @@ class LoRAModuleWrapper:
         if os.environ.get("OTB_GROUP_SIBLINGS", "1") == "0":
             return
         by_parent: dict[str, dict[str, LoRAModule]] = {}
+        in_context_launch = {id(m) for cl in self.context_launches for m in cl.members}      # those are batched network-wide
         for name, m in self.lora_modules.items():
+            if id(m) in in_context_launch:
+                continue
             if isinstance(m, LoRAModule) and not isinstance(m, self.dummy_klass) and isinstance(m.orig_module, nn.Linear) and "." in name:
                 parent, leaf = name.rsplit(".", 1)
                 by_parent.setdefault(parent, {})[leaf] = m
@@ -790,10 +869,35 @@ class LoRAModuleWrapper:
         self._bind()
         for m in self.lora_modules.values():
             m.hook_to_module()
+        if self._net_hook is None and isinstance(self.orig_module, nn.Module):
+            self._net_hook = self.orig_module.register_forward_pre_hook(self._on_network_forward, with_kwargs=True)
 
     def remove_hook_from_module(self):
         for m in self.lora_modules.values():
             m.remove_hook_from_module()
+        if self._net_hook is not None:
+            self._net_hook.remove()
+            self._net_hook = None
+        for m in self._trainable():
+            m._ctx_parked = None
+
+    def launch_units(self) -> list[list["LoRAModule"]]:
+        """The leaves grouped as the step launches them: context launches (32 per launch), sibling groups, single leaves —
+        in module discovery order.  bench.py replays exactly these to time K-a."""
+        units, taken = [], set()
+        for cl in getattr(self, "context_launches", []):
+            for lo in range(0, len(cl.members), ops.N.LORA_GROUP_MAX):
+                chunk = cl.members[lo:lo + ops.N.LORA_GROUP_MAX]
+                units.append(list(chunk))
+                taken.update(id(m) for m in chunk)
+        for grp in getattr(self, "sibling_groups", []):
+            if grp.enabled and not any(id(m) in taken for m in grp.members):
+                units.append(list(grp.members))
+                taken.update(id(m) for m in grp.members)
+        for m in self._trainable():
+            if id(m) not in taken:
+                units.append([m])
+        return units
 
     def apply_to_module(self):
         for m in self.lora_modules.values():

@@ -147,12 +147,13 @@ def lora_linear(x: torch.Tensor, w: torch.Tensor, down: torch.Tensor | None, up:
 def lora_linear_grouped(xs: list[torch.Tensor], ws: list[torch.Tensor], downs: list[torch.Tensor], ups: list[torch.Tensor],
                         biases: list[torch.Tensor | None], scales: list[float], *, dropout_p: float = 0.0,
                         keys: list[tuple[int, int]] | None = None, want_t: bool = True, tile_n: int = 0):
-    """`len(xs)` (1..3) same-shape lora_linear problems as ONE launch (otb_lora_linear_grouped): the q/k/v projections of
-    a self-attention (pass the same x three times), the k/v projections of a cross-attention, or their dX GEMMs.
-    Returns ([y_i], [t_i]); bit-identical to the single calls."""
+    """`len(xs)` (1..32) same-shape lora_linear problems as ONE launch (otb_lora_linear_grouped): the q/k/v projections of
+    a self-attention (pass the same x three times), the k/v projections of a cross-attention, their dX GEMMs — or the
+    K/V projections of the text context of up to 16 cross-attentions at once.  Returns ([y_i], [t_i]); bit-identical to
+    the single calls."""
     g = len(xs)
-    if not (1 <= g <= 3 and len(ws) == len(downs) == len(ups) == len(biases) == len(scales) == g):
-        raise ValueError("lora_linear_grouped: 1..3 members, one entry per member in every list")
+    if not (1 <= g <= N.LORA_GROUP_MAX and len(ws) == len(downs) == len(ups) == len(biases) == len(scales) == g):
+        raise ValueError(f"lora_linear_grouped: 1..{N.LORA_GROUP_MAX} members, one entry per member in every list")
     M, K = xs[0].shape
     Nn, R = ws[0].shape[0], downs[0].shape[0]
     arr = (N.LoraLinearArgs * g)()

@@ -419,6 +419,57 @@ def test_optimizer_state_reload_mid_run_and_partial_ema_coverage(P, dev):
             assert torch.equal(a, b)
 
 
+def test_context_launch_serves_every_cross_attention_and_survives_checkpointing(P, dev, monkeypatch):
+    """The K / V projections of the text context are computed for the whole network when the network's forward starts
+    (ContextLaunch, 32 leaves per launch) and parked on the leaves: (1) predictions and LoRA gradients equal the
+    leaf-by-leaf run bit for bit (same kernels, same k order; dA / dB are fixed-order sums); (2) under the reference's
+    default gradient checkpointing (TrainConfig.py:786; non-reentrant, block by block) the re-run blocks are served the
+    same parked tensors and gradients do not change; (3) a context leaf called on ANOTHER tensor computes on that
+    tensor; (4) un-hooking the wrapper removes the network hook."""
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    def build(ctx_group: bool):
+        monkeypatch.setenv("OTB_CTX_GROUP", "1" if ctx_group else "0")
+        return _tiny(P, dev, seed=21)
+
+    x, t, ctx = _inputs(dev, seed=6)
+
+    def run(net, wrap, checkpointing=False):
+        if checkpointing:
+            assert P.standin.enable_checkpointing(net) == 4
+        for p in wrap.parameters():
+            p.grad = None
+        with sdpa_kernel(SDPBackend.MATH), torch.autocast("cuda", dtype=torch.bfloat16):
+            out = net(x, t, ctx).sample
+            (out.float() ** 2).mean().backward()
+        if checkpointing:
+            P.standin.disable_checkpointing(net)
+        return out.detach().clone(), [p.grad.clone() for p in wrap.parameters()]
+
+    _, net_g, wrap_g = build(True)
+    _, net_s, wrap_s = build(False)
+    assert len(wrap_g.context_launches) == 1 and not wrap_s.context_launches
+    before = P.L.ops.LAUNCHES
+    out_g, grads_g = run(net_g, wrap_g)
+    n_g = P.L.ops.LAUNCHES - before
+    before = P.L.ops.LAUNCHES
+    out_s, grads_s = run(net_s, wrap_s)
+    n_s = P.L.ops.LAUNCHES - before
+    assert n_s - n_g == 2 * 7                                 # 8 leaves -> 1 launch, forward and Gs
+    assert torch.equal(out_g, out_s)
+    assert all(torch.equal(a, b) for a, b in zip(grads_g, grads_s))
+    out_c, grads_c = run(net_g, wrap_g, checkpointing=True)
+    assert torch.equal(out_c, out_g) and all(torch.equal(a, b) for a, b in zip(grads_c, grads_g))
+    leaf = wrap_g.context_launches[0].members[0]
+    other = torch.randn(40, leaf.orig_module.in_features, device=dev).bfloat16()
+    y = leaf.orig_module(other)
+    ref, _ = P.L.ops.lora_linear(other, *(leaf._operands()[k] for k in ("w", "a", "b", "bias")), leaf._scale())
+    assert torch.equal(y, ref)
+    wrap_g.remove_hook_from_module()
+    assert wrap_g._net_hook is None and all(m._ctx_parked is None for m in wrap_g.lora_modules.values())
+    assert len(net_g._forward_pre_hooks) == 0
+
+
 # ------------------------------------------------------------------------------------------ S2 mixins
 def test_noise_mixin_generator_semantics(P, dev):
     class S(P.ModelSetupNoiseMixin):
@@ -825,6 +876,7 @@ def test_sibling_groups_batch_qkv_and_match_single_launches(P, dev, monkeypatch)
 
     def run(group: bool):
         monkeypatch.setenv("OTB_GROUP_SIBLINGS", "1" if group else "0")
+        monkeypatch.setenv("OTB_CTX_GROUP", "1" if group else "0")
         cfg = P.TrainConfig(train_device=str(dev), batch_size=B, lora_rank=16, lora_alpha=8.0)
         model, setup = P.trainer.build_model("tiny", cfg, dev, stochastic_rounding=False, lora_up_std=0.05, lr=1e-3)
         batch = P.trainer.batch_to_device(P.trainer.synthetic_batch("tiny", B, dev, latent_hw=32), dev)
@@ -842,9 +894,11 @@ def test_sibling_groups_batch_qkv_and_match_single_launches(P, dev, monkeypatch)
     m_s, l_s, pred_s, n_s = run(False)
     groups = m_g.unet_lora.sibling_groups
     assert len(groups) > 0 and all(g.enabled for g in groups) and len(m_s.unet_lora.sibling_groups) == 0
-    assert {len(g.members) for g in groups} == {2, 3}                       # self-attention q/k/v and cross-attention k/v
-    saved = sum(len(g.members) - 1 for g in groups)
-    assert n_s - n_g == 2 * saved                                           # one launch fewer per extra member, forward and dX
+    ctx_launches = m_g.unet_lora.context_launches
+    assert {len(g.members) for g in groups} == {3}                          # self-attention q/k/v ...
+    assert [len(c.members) for c in ctx_launches] == [8] and not m_s.unet_lora.context_launches   # ... and every cross-attention k/v at once
+    saved = sum(len(g.members) - 1 for g in groups) + sum(len(c.members) - 1 for c in ctx_launches)
+    assert n_s - n_g == 2 * saved                                           # one launch fewer per extra member, forward and dX / Gs
     assert torch.equal(pred_g, pred_s) and l_g == l_s
     for a, b in zip(m_g.parameters, m_s.parameters):
         # dX of a group is (dq + dk) + dv rounded to bf16 in that order; autograd sums the single launches in its own
