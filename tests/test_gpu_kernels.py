@@ -737,8 +737,9 @@ def test_lora_grad_ab_random_shapes_vs_fp32_torch(K, dev):
 def test_lora_grad_batched_mixed_shapes_split_and_unsplit_agree(K, dev, monkeypatch):
     """otb_lora_grad_batched: leaves of DIFFERENT shapes in one launch (the queue of a backward pass), more than 32
     leaves (several launches), M long enough to be split through the workspace, and the single-leaf entry point without
-    a workspace (never split).  All variants compute the same fixed-order fp32 sums per 128-row stage, so they agree to
-    fp32 re-association (1e-6 relative), each one is bit-reproducible, and all match fp32 torch."""
+    a workspace (never split).  Split and unsplit variants re-associate the fp32 accumulation over M (the tensor core
+    accumulates a whole unit in TMEM; splits are then added in split order), so they agree to ~1e-5 of the tensor's
+    scale; each variant is bit-reproducible, and all match fp32 torch."""
     import ctypes as C
     rng = np.random.default_rng(5)
     shapes = [(4096, 1280, 1280, 32), (308, 1280, 2048, 32), (16384, 640, 640, 32), (1000, 328, 136, 16), (129, 72, 520, 8), (20000, 64, 192, 64)]
@@ -769,7 +770,7 @@ def test_lora_grad_batched_mixed_shapes_split_and_unsplit_agree(K, dev, monkeypa
     for i, ((rA, rB), s) in enumerate(zip(refs, shapes)):
         for j, r in enumerate((rA, rB)):
             assert torch.equal(b1[i][j], b2[i][j]) and torch.equal(s1[i][j], s2[i][j]), (i, s, "not reproducible")
-            tol = dict(rtol=2e-5, atol=2e-6 * r.abs().max().item())
+            tol = dict(rtol=1e-4, atol=2e-5 * r.abs().max().item())
             assert torch.allclose(b1[i][j], single[i][j], **tol) and torch.allclose(s1[i][j], single[i][j], **tol), (i, s)
             assert torch.allclose(one[i][j], single[i][j], **tol), (i, s)
             assert torch.allclose(b1[i][j], r, rtol=1e-4, atol=2e-3 * r.abs().max().item() + 1e-5), (i, s)

@@ -428,6 +428,40 @@ def gen_lora():
     np.savez(OUT / "lora.npz", **out)
 
 
+def gen_lora_bf16in():
+    """LoRAModule.forward / backward (LoRAModule.py:319-323) in the reference's fp32 on operands that are EXACTLY
+    representable in bf16 (x, W, bias, A, B, dY rounded once, stored as fp32).  This is the north_star's comparison value
+    for the bf16 kernel — "the value computed from bf16-rounded inputs in fp32" — so the GPU test can hold K-a to 2 bf16
+    ulp instead of budgeting for the input rounding."""
+    out = {}
+    r16 = lambda t: t.detach().bfloat16().float()  # noqa: E731
+    torch.manual_seed(23)
+    for name, base, xshape in (("linear", torch.nn.Linear(264, 136), (4, 50, 264)),
+                               ("linear_nobias", torch.nn.Linear(1280, 320, bias=False), (77, 1280)),
+                               ("conv1x1", torch.nn.Conv2d(64, 96, 1), (2, 64, 12, 12)),
+                               ("conv3x3", torch.nn.Conv2d(24, 32, 3, padding=1), (2, 24, 10, 10))):
+        with torch.no_grad():
+            base.weight.copy_(r16(base.weight))
+            if base.bias is not None:
+                base.bias.copy_(r16(base.bias))
+        mod = LoRAModule("lora_unet.x", base, 16, 8.0)
+        with torch.no_grad():
+            mod.lora_down.weight.copy_(r16(mod.lora_down.weight))
+            mod.lora_up.weight.copy_(r16(torch.randn_like(mod.lora_up.weight) * 0.05))
+        base.requires_grad_(False)
+        mod.hook_to_module()
+        x = r16(torch.randn(*xshape)).requires_grad_(True)
+        y = base(x)
+        dy = r16(torch.randn_like(y))
+        dx, dA, dB = torch.autograd.grad(y, [x, mod.lora_down.weight, mod.lora_up.weight], dy)
+        out.update({f"{name}_x": x.detach().numpy(), f"{name}_w": base.weight.detach().numpy(),
+                    f"{name}_bias": base.bias.detach().numpy() if base.bias is not None else np.zeros(0, np.float32),
+                    f"{name}_A": mod.lora_down.weight.detach().numpy(), f"{name}_B": mod.lora_up.weight.detach().numpy(),
+                    f"{name}_y": y.detach().numpy(), f"{name}_dy": dy.numpy(), f"{name}_dx": dx.numpy(),
+                    f"{name}_dA": dA.numpy(), f"{name}_dB": dB.numpy()})
+    np.savez(OUT / "lora_bf16in.npz", **out)
+
+
 # ------------------------------------------------------------------------------------ DoRA (oracle only so far)
 def gen_dora():
     """DoRAModule.forward (LoRAModule.py:385-419) and its autograd backward, CPU fp32.  Pins the ORACLE's restatement;
@@ -499,7 +533,7 @@ def gen_clip():
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])              # e.g. `python tools/make_golden.py gen_lora` rewrites one fixture file
-    for fn in (gen_schedule, gen_optimizer, gen_adafactor, gen_came, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_dora, gen_param_groups, gen_clip):
+    for fn in (gen_schedule, gen_optimizer, gen_adafactor, gen_came, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_lora_bf16in, gen_dora, gen_param_groups, gen_clip):
         if only and fn.__name__ not in only:
             continue
         fn()
