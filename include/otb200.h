@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define OTB_ABI_VERSION 4   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs.  3: otb_grad_exchange, otb_grad_norm_from_partials.
-                               4: OTB_TS_TABLE (ts_cdf / ts_cdf_len appended to otb_noise_args); otb_lora_grad_batched; otb_lora_linear_grouped takes up to 32 members */
+                               4: OTB_TS_TABLE (ts_cdf / ts_cdf_len appended to otb_noise_args); otb_lora_grad_batched; otb_lora_linear_grouped takes up to 32 members; otb_lora_linear_args.flags */
 
 /* error codes */
 #define OTB_OK            0
@@ -366,7 +366,13 @@ typedef struct otb_lora_linear_args {
     uint64_t seed, offset;/* dropout Philox key (same in fwd and bwd => same mask)          */
     int32_t tile_n;       /* 0 = let the library choose                                     */
     int32_t stages;       /* 0 = let the library choose                                     */
+    int32_t flags;        /* OTB_LINEAR_STATIC_WEIGHTS: w / down / up / bias were NOT written by the launch that
+                             precedes this one on the stream (frozen base weights, shadows refreshed after the last
+                             optimizer step).  The kernel may then fetch its first weight tiles BEFORE the stream
+                             dependency on that launch resolves (programmatic dependent launch), hiding their HBM
+                             latency behind the predecessor's tail; x is always read after it.              */
 } otb_lora_linear_args;
+#define OTB_LINEAR_STATIC_WEIGHTS 1
 
 int otb_lora_linear(const otb_lora_linear_args* args, void* stream);
 
@@ -403,9 +409,12 @@ int otb_lora_grad_ab(const otb_lora_grad_args* args, void* stream);
  * in the first version).  `workspace` (device memory, 256-byte aligned, at least otb_lora_grad_workspace_bytes(leaves,
  * count) bytes, or NULL) lets small batches and very long M be split over more CTAs; split partial sums are combined
  * in split order by the last CTA to arrive.  Its first 64 KB are arrival counters: zero before the FIRST use, left
- * zero by every launch.  Launches that share a workspace must be ordered on one stream. */
+ * zero by every launch.  `chained` != 0 declares that the launch issued immediately before this one on `stream` is
+ * another otb_lora_grad_batched launch whose outputs this one neither reads nor writes and which uses a DIFFERENT
+ * workspace: the two may then overlap (the second fills the SMs the first vacates at its tail). */
 #define OTB_GRAD_BATCH_MAX 32
-int otb_lora_grad_batched(const otb_lora_grad_args* leaves, int32_t count, void* workspace, int64_t workspace_bytes, void* stream);
+int otb_lora_grad_batched(const otb_lora_grad_args* leaves, int32_t count, void* workspace, int64_t workspace_bytes,
+                          int32_t chained, void* stream);
 int64_t otb_lora_grad_workspace_bytes(const otb_lora_grad_args* leaves, int32_t count);
 
 /* Utility used by tests and the data-parallel bucket path: fp32 <-> bf16 casts with

@@ -110,7 +110,7 @@ class LoraLinearArgs(C.Structure):
         ("M", _i32), ("N", _i32), ("K", _i32), ("R", _i32),
         ("bias_dtype", _i32), ("scale", _f32), ("dropout_p", _f32),
         ("seed", _u64), ("offset", _u64),
-        ("tile_n", _i32), ("stages", _i32),
+        ("tile_n", _i32), ("stages", _i32), ("flags", _i32),
     ]
 
 
@@ -124,6 +124,7 @@ class LoraGradArgs(C.Structure):
 MAX_RANKS = 16           # OTB_MAX_RANKS
 GRAD_BATCH_MAX = 32      # OTB_GRAD_BATCH_MAX
 LORA_GROUP_MAX = 32      # OTB_LORA_GROUP_MAX
+LINEAR_STATIC_WEIGHTS = 1
 
 
 class GradExchangeArgs(C.Structure):
@@ -157,7 +158,7 @@ SYMBOLS = {
     "otb_lora_linear": (C.c_int, [C.POINTER(LoraLinearArgs), _vp]),
     "otb_lora_linear_grouped": (C.c_int, [C.POINTER(LoraLinearArgs), C.c_int32, _vp]),
     "otb_lora_grad_ab": (C.c_int, [C.POINTER(LoraGradArgs), _vp]),
-    "otb_lora_grad_batched": (C.c_int, [C.POINTER(LoraGradArgs), C.c_int32, _vp, _i64, _vp]),
+    "otb_lora_grad_batched": (C.c_int, [C.POINTER(LoraGradArgs), C.c_int32, _vp, _i64, C.c_int32, _vp]),
     "otb_lora_grad_workspace_bytes": (_i64, [C.POINTER(LoraGradArgs), C.c_int32]),
     "otb_philox_dump": (C.c_int, [_u64, _u64, _u32, _i64, _i64, _vp, _vp]),
     "otb_struct_sizes": (C.c_int, [C.POINTER(C.c_int32)]),

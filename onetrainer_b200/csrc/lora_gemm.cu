@@ -381,6 +381,7 @@ struct GemmParams3 {
     int up_chunks;         // MMAs per k-step of the rank-R GEMM (tile_n / up_chunks <= 256)
     int acc_stages;        // 2 when NB <= 256, else 1
     int pair_m_tiles;      // ceil(M / 256)
+    int prefetch_w;        // weight tiles of the first k-blocks are fetched before griddepcontrol.wait (OTB_LINEAR_STATIC_WEIGHTS)
     int debug;             // bring-up only (OTB_KA_DEBUG): bit 0 skip the TMA loads, bit 1 skip the MMAs, bit 2 skip the epilogue
 };
 
@@ -506,7 +507,11 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
     cluster_sync_all();                         // the peer's barriers and TMEM exist before anything crosses CTAs
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
-    otb_pdl_wait();                             // everything above overlapped the previous kernel's tail; its outputs are visible now
+    // Everything above overlapped the previous kernel's tail.  griddepcontrol.wait (its outputs are visible afterwards) is
+    // issued per role: the producer first fetches the WEIGHT tiles of its first k-blocks when the caller vouches that the
+    // preceding launch did not write them — the frozen base and the LoRA shadows come cold from HBM (~2 us to the first
+    // byte), the activations x are what the predecessor produced and are read after the wait.
+    if (warp != 0) otb_pdl_wait();
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
@@ -516,6 +521,35 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
         int s = 0; uint32_t ph = 0;
         int it = 0;
         const uint32_t stage_tx = 2u * L.stage_bytes, up_tx = 2u * L.up_bytes;
+        // the [w; down] halves of k-block kb of a tile into stage `stg` (completion on the leader's barrier `bar`)
+        auto load_weights = [&](uint32_t stg, uint32_t bar, int kb, int n0, const CUtensorMap* tm_w, const CUtensorMap* tm_w2, const CUtensorMap* tm_dn) {
+            // my half of every chunk of the fused [w; down] rows; only the very last half (peer CTA, last chunk) reaches
+            // into `down`, and it holds all Rp rows of it
+            for (int c = 0; c < q.chunks; ++c) {
+                const uint32_t dst = stg + L.b_off + (uint32_t)(c * nbh) * 128;
+                const int row = c * nbc + (int)crank * nbh;      // first fused row of this half
+                if (lora && c == q.chunks - 1 && !leader) {
+                    if (nbh > p.Rp) tma_load_2d_2sm(dst, tm_w2, bar, kb * BK, n0 + row);
+                    tma_load_2d_2sm(dst + (uint32_t)(nbh - p.Rp) * 128, tm_dn, bar, kb * BK, 0);
+                } else {
+                    tma_load_2d_2sm(dst, tm_w, bar, kb * BK, n0 + row);
+                }
+            }
+        };
+        int prefetched = 0;            // k-blocks of this CTA's FIRST tile whose weights are already on their way
+        if (q.prefetch_w && !(q.debug & 1) && cid < (uint32_t)total_tiles) {
+            const int gm = ((int)cid % tiles_per_row) / p.n_tiles, nt = (int)cid % p.n_tiles;
+            const int n0 = nt * p.tile_n;
+            prefetched = p.num_kb < p.stages ? p.num_kb : p.stages;
+            if (elect_one()) {
+                for (int kb = 0; kb < prefetched; ++kb) {            // the ring is empty: stages 0 .. prefetched-1, no wait needed
+                    if (leader) mbar_expect_tx(full_bar(kb), stage_tx);
+                    load_weights(smem_base + L.stage_bytes * kb, mapa_u32(full_bar(kb), 0), kb, n0, &maps.w[gm], &maps.w2[gm], &maps.dn[gm]);
+                }
+            }
+            __syncwarp();
+        }
+        otb_pdl_wait();
         for (uint32_t st = cid; st < (uint32_t)total_tiles; st += ncl, ++it) {
             const int mt = st / tiles_per_row, gm = (st % tiles_per_row) / p.n_tiles, nt = st % p.n_tiles;
             const int m0 = mt * 2 * BM + (int)crank * BM, n0 = nt * p.tile_n;
@@ -540,21 +574,11 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
                     if (q.debug & 1) {
                         if (leader) mbar_arrive(full_bar(s));
                     } else {
-                        if (leader) mbar_expect_tx(full_bar(s), stage_tx);
+                        const bool early = it == 0 && kb < prefetched;      // expect_tx and the weight loads were issued before the wait
+                        if (leader && !early) mbar_expect_tx(full_bar(s), stage_tx);
                         const uint32_t bar = mapa_u32(full_bar(s), 0);
                         tma_load_2d_2sm(stg + L.x_off, tm_x, bar, kb * BK, m0);
-                        // my half of every chunk of the fused [w; down] rows; only the very last half (peer CTA, last
-                        // chunk) reaches into `down`, and it holds all Rp rows of it
-                        for (int c = 0; c < q.chunks; ++c) {
-                            const uint32_t dst = stg + L.b_off + (uint32_t)(c * nbh) * 128;
-                            const int row = c * nbc + (int)crank * nbh;      // first fused row of this half
-                            if (lora && c == q.chunks - 1 && !leader) {
-                                if (nbh > p.Rp) tma_load_2d_2sm(dst, tm_w2, bar, kb * BK, n0 + row);
-                                tma_load_2d_2sm(dst + (uint32_t)(nbh - p.Rp) * 128, tm_dn, bar, kb * BK, 0);
-                            } else {
-                                tma_load_2d_2sm(dst, tm_w, bar, kb * BK, n0 + row);
-                            }
-                        }
+                        if (!early) load_weights(stg, bar, kb, n0, tm_w, tm_w2, tm_dn);
                     }
                 }
                 __syncwarp();
@@ -979,6 +1003,10 @@ int launch_v3(const otb_lora_linear_args* a, int count, void* stream, int tile_n
     OTB_CHECK_ARG(v3_shape_ok(tile_n, p.Rp, &q.chunks, &q.up_chunks, &q.acc_stages),
                   "pair tile_n %d invalid for rank %d (tile_n + rank a multiple of 16 (32 above 256), <= 512)", tile_n, p.Rp);
     q.debug = env_int("OTB_KA_DEBUG", 0);
+    q.prefetch_w = 1;
+    for (int g = 0; g < count; ++g)
+        if (!(a[g].flags & OTB_LINEAR_STATIC_WEIGHTS)) q.prefetch_w = 0;
+    if (!otb_pdl_enabled() || env_int("OTB_KA_PREFETCH_W", 1) == 0) q.prefetch_w = 0;
     p.num_kb = (a->K + BK - 1) / BK;
     p.n_tiles = (a->N + p.tile_n - 1) / p.tile_n;
     q.pair_m_tiles = (a->M + 2 * BM - 1) / (2 * BM);

@@ -58,6 +58,7 @@ struct alignas(64) GbProblem {
 struct GbBatch {
     GbProblem pr[GB_MAX_PROBLEMS];
     int32_t n_problems, total_units;
+    int32_t chained;         // the launch before this one on the stream is a sibling batch of the same flush (see the host entry)
 };
 static_assert(sizeof(GbBatch) <= 32 * 1024 - 256, "kernel parameters are limited to 32 KB");
 
@@ -92,7 +93,6 @@ __device__ __forceinline__ int snake_unit(int round, int cta, int ctas) {
 
 __global__ void __launch_bounds__(GB_THREADS, 1)
 lora_grad_batched_kernel(const __grid_constant__ GbBatch batch) {
-    otb_pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -119,7 +119,14 @@ lora_grad_batched_kernel(const __grid_constant__ GbBatch batch) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
-    otb_pdl_wait();          // Gs / Ts / dY come from launches before this one
+    // Stream dependency.  A launch that follows a sibling batch of the same flush reads nothing that sibling writes: it
+    // skips the wait, so its CTAs start on the SMs the sibling's CTAs vacate and fill the tail of that launch (each launch
+    // ends with some CTAs one unit short).  That is only sound because every launch releases its dependents AFTER its own
+    // wait: a chained launch can only be running once the head of the chain has seen everything before the flush complete.
+    // A chained launch still waits for its predecessor — at its END (below), so that "the last launch of the chain has
+    // completed" keeps meaning "the whole chain has", which is what the next kernel on the stream relies on.
+    if (!batch.chained) otb_pdl_wait();          // Gs / Ts / dY come from launches before this flush
+    otb_pdl_trigger();
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -269,6 +276,7 @@ lora_grad_batched_kernel(const __grid_constant__ GbBatch batch) {
         __syncwarp();
         tmem_dealloc(tmem_base, 128u);
     }
+    if (batch.chained) otb_pdl_wait();           // do not complete before the sibling this launch overlapped
 }
 
 // ------------------------------- host side ------------------------------------------
@@ -343,7 +351,7 @@ extern "C" int64_t otb_lora_grad_workspace_bytes(const otb_lora_grad_args* leave
 }
 
 extern "C" int otb_lora_grad_batched(const otb_lora_grad_args* leaves, int32_t count, void* workspace, int64_t workspace_bytes,
-                                     void* stream) {
+                                     int32_t chained, void* stream) {
     OTB_CHECK_ARG(leaves != nullptr && count >= 1 && count <= OTB_GRAD_BATCH_MAX, "batch of %d leaves (1..%d)", count, OTB_GRAD_BATCH_MAX);
     OTB_CHECK_ARG(workspace == nullptr || ((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     HostProblem hp[GB_MAX_PROBLEMS];
@@ -386,6 +394,7 @@ extern "C" int otb_lora_grad_batched(const otb_lora_grad_args* leaves, int32_t c
     }
     batch.n_problems = n;
     batch.total_units = units;
+    batch.chained = (chained && otb_pdl_enabled()) ? 1 : 0;
     static thread_local int attr_dev = -1;
     int dev = 0;
     OTB_CUDA(cudaGetDevice(&dev));
@@ -415,5 +424,5 @@ extern "C" int otb_lora_grad_batched(const otb_lora_grad_args* leaves, int32_t c
 extern "C" int otb_lora_grad_ab(const otb_lora_grad_args* a, void* stream) {
     OTB_CHECK_ARG(a != nullptr, "null args");
     if (a->dA == nullptr && a->dB == nullptr) return OTB_OK;
-    return otb_lora_grad_batched(a, 1, nullptr, 0, stream);
+    return otb_lora_grad_batched(a, 1, nullptr, 0, 0, stream);
 }

@@ -81,7 +81,7 @@ class _LoraLinearFn(torch.autograd.Function):
             seed, offset = gen.initial_seed(), gen.get_offset()
             gen.set_offset(offset + 4)      # checkpoint recompute restores this state -> same mask
         y, ts = ops.lora_linear(x2, sh["w"], sh["a"], sh["b"], sh["bias"], mod._scale(), dropout_p=p,
-                                seed=seed, offset=offset, want_t=any(ctx.needs_input_grad[:3]))
+                                seed=seed, offset=offset, want_t=any(ctx.needs_input_grad[:3]), static_weights=sh["static"])
         ctx.mod, ctx.p, ctx.key = mod, p, (seed, offset)
         ctx.save_for_backward(x2, ts)
         return y
@@ -100,7 +100,7 @@ class _LoraLinearFn(torch.autograd.Function):
         dx = gs = None
         if ctx.needs_input_grad[0]:
             dx, gs = ops.lora_linear(dy, sh["wt"], sh["bt"], sh["at"], None, mod._scale(), dropout_p=ctx.p,
-                                     seed=ctx.key[0], offset=ctx.key[1], want_t=True)
+                                     seed=ctx.key[0], offset=ctx.key[1], want_t=True, static_weights=sh["static"])
         elif need_a:
             gs = _gs_only([dy], [sh], [mod._scale()], ctx.p, [ctx.key])[0]
         dA, dB, ret_a, ret_b = mod._grad_buffers(need_a, need_b)
@@ -113,6 +113,27 @@ class _LoraLinearFn(torch.autograd.Function):
         return dx, ret_a, ret_b, None
 
 
+class _UnfoldRows(torch.autograd.Function):
+    """im2col for a k x k conv leaf: one bf16 row per output pixel, columns (c, ki, kj).  Its adjoint (col2im) adds up to
+    kh*kw overlapping patch gradients per input pixel; torch's own backward would do that in bf16, one rounding per
+    addend — here the sum is formed in fp32 and rounded ONCE, like the fp32-accumulating dgrad of the reference's conv."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, kernel_size, dilation, padding, stride):
+        ctx.geom = (tuple(x.shape[-2:]), kernel_size, dilation, padding, stride)
+        cols = nn.functional.unfold(x, kernel_size, dilation, padding, stride)
+        return cols.transpose(1, 2).reshape(-1, cols.shape[1])
+
+    @staticmethod
+    def backward(ctx, drows: Tensor):
+        hw, kernel_size, dilation, padding, stride = ctx.geom
+        L = ((hw[0] + 2 * padding[0] - dilation[0] * (kernel_size[0] - 1) - 1) // stride[0] + 1) * \
+            ((hw[1] + 2 * padding[1] - dilation[1] * (kernel_size[1] - 1) - 1) // stride[1] + 1)
+        dcols = drows.reshape(-1, L, drows.shape[1]).transpose(1, 2).float()
+        dx = nn.functional.fold(dcols, hw, kernel_size, dilation, padding, stride)
+        return dx.to(drows.dtype), None, None, None, None
+
+
 NO_DX_ROWS = 64
 
 
@@ -123,7 +144,8 @@ def _gs_only(dys: list, shs: list, scales: list, p: float, keys: list) -> list:
     dY once; the full dX GEMM of such a leaf (M x K x N) is never issued."""
     rows = min(NO_DX_ROWS, shs[0]["wt"].shape[0])
     _, gss = ops.lora_linear_grouped(dys, [sh["wt"][:rows] for sh in shs], [sh["bt"] for sh in shs], [sh["at"][:rows] for sh in shs],
-                                     [None] * len(dys), scales, dropout_p=p, keys=keys, want_t=True)
+                                     [None] * len(dys), scales, dropout_p=p, keys=keys, want_t=True,
+                                     static_weights=all(sh.get("static", False) for sh in shs))
     return gss
 
 
@@ -146,7 +168,7 @@ class _LoraGroupFn(torch.autograd.Function):
                 keys.append((seed, offset))
         ys, ts = ops.lora_linear_grouped([x2] * len(mods), [o["w"] for o in ops_], [o["a"] for o in ops_], [o["b"] for o in ops_],
                                          [o["bias"] for o in ops_], [m._scale() for m in mods], dropout_p=p, keys=keys,
-                                         want_t=any(ctx.needs_input_grad[1:]))
+                                         want_t=any(ctx.needs_input_grad[1:]), static_weights=all(o["static"] for o in ops_))
         ctx.mods, ctx.p, ctx.keys = mods, p, keys
         ctx.save_for_backward(x2, *[t for t in ts if t is not None])
         return tuple(ys)
@@ -168,7 +190,7 @@ class _LoraGroupFn(torch.autograd.Function):
             if ctx.needs_input_grad[1]:
                 dxs, gss = ops.lora_linear_grouped(dyc, [o["wt"] for o in ops_], [o["bt"] for o in ops_], [o["at"] for o in ops_],
                                                    [None] * len(live), [mods[i]._scale() for i in live], dropout_p=ctx.p,
-                                                   keys=[ctx.keys[i] for i in live], want_t=True)
+                                                   keys=[ctx.keys[i] for i in live], want_t=True, static_weights=all(o["static"] for o in ops_))
             elif any(ctx.needs_input_grad[2 + 2 * i] for i in live):
                 gss = _gs_only(dyc, ops_, [mods[i]._scale() for i in live], ctx.p, [ctx.keys[i] for i in live])
             else:
@@ -204,6 +226,9 @@ def _launch_grad_ab(mod, x2, dy, gs, ts, dA, dB, ret_a, ret_b) -> None:
         return t is not None and (arena is None or not arena.data_ptr() <= t.data_ptr() < arena.data_ptr() + arena.numel() * arena.element_size())
     hooked = any(getattr(p, "_post_accumulate_grad_hooks", None) for p in (mod.lora_down.weight, mod.lora_up.weight))
     if outside(dA) or outside(dB) or hooked:
+        # whoever reads this result now (autograd adding a second use of the leaf to the first, an optimizer hook) may also
+        # read slices that are still in the queue: launch those first
+        ops.grad_queue.flush_all()
         ops.lora_grad_ab(x2, dy, gs, ts, dA, dB)
     else:
         ops.grad_queue.push((x2, dy, gs, ts, dA, dB), dy.device)
@@ -529,6 +554,7 @@ class LoRAModule(PeftBase):
         w = om.weight
         key = (w.data_ptr(), w._version, w.dtype)
         if self._base_cache is None or self._base_cache[0] != key:
+            self._rebuilt = True
             if w.dtype not in (torch.bfloat16, torch.float32, torch.float16):
                 raise NotImplementedError(f"base weight dtype {w.dtype} is not supported by the fused LoRA kernel")
             w2 = w.detach().reshape(w.shape[0], -1)
@@ -537,6 +563,10 @@ class LoRAModule(PeftBase):
         return self._base_cache[1], self._base_cache[2]
 
     def _operands(self) -> dict:
+        """The bf16 operands of the fused kernels.  'static' says that none of them was (re)written by a launch issued
+        during THIS call — i.e. the launch preceding the GEMM on the stream is not their producer, and the kernel may
+        fetch weight tiles ahead of its stream dependency (OTB_LINEAR_STATIC_WEIGHTS)."""
+        self._rebuilt = False
         w, wt = self._base()
         if self._wrapper_slot is not None:
             wrapper, idx = self._wrapper_slot
@@ -545,12 +575,13 @@ class LoRAModule(PeftBase):
             A, B = self.lora_down.weight, self.lora_up.weight
             vers = (A._version, B._version, A.data_ptr(), B.data_ptr(), A.dtype)
             if self._own_shadow is None or self._own_versions != vers:
+                self._rebuilt = True
                 if self._own_shadow is None or self._own_versions[2:] != vers[2:]:
                     self._own_shadow = ops.ShadowTable([A.detach().view(A.shape[0], -1), B.detach().view(B.shape[0], -1)], A.device)
                 self._own_shadow.refresh()
                 self._own_versions = vers
             (a, b), (at, bt) = self._own_shadow.views, self._own_shadow.views_t
-        return dict(w=w, wt=wt, a=a, at=at, b=b, bt=bt, bias=self.orig_module.bias)
+        return dict(w=w, wt=wt, a=a, at=at, b=b, bt=bt, bias=self.orig_module.bias, static=not self._rebuilt)
 
     def _grad_buffers(self, need_a: bool, need_b: bool):
         """(dA accumulate target, dB accumulate target, value to return for A, for B)."""
@@ -587,8 +618,8 @@ class LoRAModule(PeftBase):
                 (kh, kw), (sh, sw), (ph, pw), (dh, dw) = om.kernel_size, om.stride, om.padding, om.dilation
                 h_ = (h_ + 2 * ph - dh * (kh - 1) - 1) // sh + 1
                 w_ = (w_ + 2 * pw - dw * (kw - 1) - 1) // sw + 1
-                cols = nn.functional.unfold(x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16), om.kernel_size, om.dilation, om.padding, om.stride)
-                x2 = cols.transpose(1, 2).reshape(-1, cols.shape[1])
+                x2 = _UnfoldRows.apply(x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16), om.kernel_size, om.dilation,
+                                       tuple(om.padding), om.stride)
         else:
             x2 = x.reshape(-1, x.shape[-1])
         self._last_rows = x2.shape[0]          # read by bench.py to replay the step's GEMM shapes
@@ -759,6 +790,7 @@ class LoRAModuleWrapper:
                  or self._shadow_key[idx][:2] != (A.data_ptr(), B.data_ptr()))
         if stale:
             self.refresh_shadows()
+            m._rebuilt = True
         v, vt = self._shadow.views, self._shadow.views_t
         return v[2 * idx], vt[2 * idx], v[2 * idx + 1], vt[2 * idx + 1]
 

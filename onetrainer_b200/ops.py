@@ -67,7 +67,7 @@ class GradQueue:
     returns, every gradient has been launched on the caller's stream, exactly as before.  The queue holds references
     to the operands until the flush, which bounds their extra lifetime to one batch.  Works the same under CUDA-graph
     capture.  OTB_GRAD_BATCH=1 launches every leaf by itself (A/B runs)."""
-    FLUSH_LEAVES = 32
+    FLUSH_LEAVES = 96        # three chained launches per flush: only the last one's tail is exposed
 
     def __init__(self):
         import os
@@ -113,9 +113,11 @@ def _aligned16(*tensors) -> bool:
 # --------------------------------------------------------------------------------------
 def lora_linear(x: torch.Tensor, w: torch.Tensor, down: torch.Tensor | None, up: torch.Tensor | None,
                 bias: torch.Tensor | None, scale: float, *, dropout_p: float = 0.0, seed: int = 0,
-                offset: int = 0, want_t: bool = True, tile_n: int = 0, stages: int = 0):
+                offset: int = 0, want_t: bool = True, tile_n: int = 0, stages: int = 0, static_weights: bool = False):
     """y = x w^T + bias + drop(scale * x down^T)_bf16 up^T  on tcgen05.  Returns (y, t) with
-    t = drop(scale * x down^T) in bf16 ([M, R]) or None.  x:[M,K] w:[N,K] down:[R,K] up:[N,R], bf16."""
+    t = drop(scale * x down^T) in bf16 ([M, R]) or None.  x:[M,K] w:[N,K] down:[R,K] up:[N,R], bf16.
+    `static_weights`: w / down / up / bias were not written by the launch preceding this one on the stream
+    (OTB_LINEAR_STATIC_WEIGHTS: the kernel may fetch weight tiles before that launch has finished)."""
     N.require_cuda(x, w, down, up, bias)
     for name, t in (("x", x), ("w", w), ("down", down), ("up", up)):
         if t is not None and (t.dtype != torch.bfloat16 or not t.is_contiguous() or t.dim() != 2):
@@ -138,7 +140,7 @@ def lora_linear(x: torch.Tensor, w: torch.Tensor, down: torch.Tensor | None, up:
         t_out=N.ptr(t), M=M, N=Nn, K=K, R=R,
         bias_dtype=N.dtype_code(bias.dtype) if bias is not None else N.F32,
         scale=float(scale), dropout_p=float(dropout_p), seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1),
-        tile_n=int(tile_n), stages=int(stages))
+        tile_n=int(tile_n), stages=int(stages), flags=N.LINEAR_STATIC_WEIGHTS if static_weights else 0)
     N.check(N.lib().otb_lora_linear(C.byref(a), _stream()), "otb_lora_linear")
     _count()
     return y, t
@@ -146,7 +148,7 @@ def lora_linear(x: torch.Tensor, w: torch.Tensor, down: torch.Tensor | None, up:
 
 def lora_linear_grouped(xs: list[torch.Tensor], ws: list[torch.Tensor], downs: list[torch.Tensor], ups: list[torch.Tensor],
                         biases: list[torch.Tensor | None], scales: list[float], *, dropout_p: float = 0.0,
-                        keys: list[tuple[int, int]] | None = None, want_t: bool = True, tile_n: int = 0):
+                        keys: list[tuple[int, int]] | None = None, want_t: bool = True, tile_n: int = 0, static_weights: bool = False):
     """`len(xs)` (1..32) same-shape lora_linear problems as ONE launch (otb_lora_linear_grouped): the q/k/v projections of
     a self-attention (pass the same x three times), the k/v projections of a cross-attention, their dX GEMMs — or the
     K/V projections of the text context of up to 16 cross-attentions at once.  Returns ([y_i], [t_i]); bit-identical to
@@ -172,7 +174,8 @@ def lora_linear_grouped(xs: list[torch.Tensor], ws: list[torch.Tensor], downs: l
         arr[i] = N.LoraLinearArgs(
             x=x.data_ptr(), w=w.data_ptr(), down=down.data_ptr(), up=up.data_ptr(), bias=N.ptr(bias), y=y.data_ptr(), t_out=N.ptr(t),
             M=M, N=Nn, K=K, R=R, bias_dtype=N.dtype_code(bias.dtype) if bias is not None else N.F32, scale=float(scales[i]),
-            dropout_p=float(dropout_p), seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1), tile_n=int(tile_n), stages=0)
+            dropout_p=float(dropout_p), seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1), tile_n=int(tile_n), stages=0,
+            flags=N.LINEAR_STATIC_WEIGHTS if static_weights else 0)
         ys.append(y)
         ts.append(t)
     if M > 0:
@@ -222,14 +225,21 @@ def lora_grad_batched(leaves: list[tuple]) -> None:
                                 M=M, N=dy.shape[1] if dy is not None else 0, K=x.shape[1] if x is not None else 0, R=R)
     dev = next(t for t in leaves[0] if t is not None).device
     lib = N.lib()
+    chunks = []
     for lo in range(0, len(leaves), N.GRAD_BATCH_MAX):
         n = min(N.GRAD_BATCH_MAX, len(leaves) - lo)
         sub = C.cast(C.byref(arr, lo * C.sizeof(N.LoraGradArgs)), C.POINTER(N.LoraGradArgs))
         need = lib.otb_lora_grad_workspace_bytes(sub, n)
         if need < 0:
-            N.check(lib.otb_lora_grad_batched(sub, n, None, 0, _stream()), "otb_lora_grad_batched")      # reports the bad argument
-        ws = _grad_ws.get(dev, int(need))
-        N.check(lib.otb_lora_grad_batched(sub, n, ws.data_ptr(), ws.numel(), _stream()), "otb_lora_grad_batched")
+            N.check(lib.otb_lora_grad_batched(sub, n, None, 0, 0, _stream()), "otb_lora_grad_batched")      # reports the bad argument
+        chunks.append((sub, n, (int(need) + 255) // 256 * 256))
+    # the launches of one flush are independent of each other (different leaves, different outputs): each gets its own
+    # slice of the workspace and all but the first are chained, so that they overlap instead of each ending in its own tail
+    ws = _grad_ws.get(dev, sum(c[2] for c in chunks))
+    off = 0
+    for i, (sub, n, need) in enumerate(chunks):
+        N.check(lib.otb_lora_grad_batched(sub, n, ws.data_ptr() + off, need, 1 if i > 0 else 0, _stream()), "otb_lora_grad_batched")
+        off += need
         _count()
 
 

@@ -391,7 +391,8 @@ def test_optimizer_state_reload_mid_run_and_partial_ema_coverage(P, dev):
     with torch.no_grad():
         for p, q in zip(pa, pb):
             p.copy_(q)
-    oa.load_state_dict(sd)
+    import copy
+    oa.load_state_dict(copy.deepcopy(sd))                # (torch's load keeps same-dtype tensors by reference: do not alias B's state)
     for p, q, g in zip(pa, pb, gs[2]):
         p.grad, q.grad = g.clone(), g.clone()
     oa.step(); ob.step()
