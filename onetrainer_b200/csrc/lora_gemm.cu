@@ -1006,7 +1006,10 @@ int launch_v3(const otb_lora_linear_args* a, int count, void* stream, int tile_n
     q.prefetch_w = 1;
     for (int g = 0; g < count; ++g)
         if (!(a[g].flags & OTB_LINEAR_STATIC_WEIGHTS)) q.prefetch_w = 0;
-    if (!otb_pdl_enabled() || env_int("OTB_KA_PREFETCH_W", 1) == 0) q.prefetch_w = 0;
+    // Off unless asked for: measured on the B200 over one SDXL step's 894 launches, fetching the weights ahead of the wait
+    // LOST 0.9 ms (37.2 vs 36.3 ms) — the x tile of the first k-block then queues behind up to `stages` weight boxes in the
+    // TMA unit, and the early fetches compete with the predecessor's epilogue stores (profiles/README.md, round 2).
+    if (!otb_pdl_enabled() || env_int("OTB_KA_PREFETCH_W", 0) == 0) q.prefetch_w = 0;
     p.num_kb = (a->K + BK - 1) / BK;
     p.n_tiles = (a->N + p.tile_n - 1) / p.tile_n;
     q.pair_m_tiles = (a->M + 2 * BM - 1) / (2 * BM);

@@ -185,21 +185,24 @@ def lora_linear_grouped(xs: list[torch.Tensor], ws: list[torch.Tensor], downs: l
 
 
 class _GradWorkspace:
-    """Per-device scratch of the batched weight-gradient kernel: 64 KB of arrival counters (zero before the first use,
-    left zero by every launch) followed by the partial tiles of split problems.  Grown on demand — a new, zeroed buffer;
-    the old one stays alive until every launch that used it has been ordered before the new one's first use, which
-    stream order on the single stream that uses it guarantees."""
+    """Per-device scratch of the batched weight-gradient kernel, cut into fixed SLOTS (one per chained launch of a flush).
+    Every slot starts with 64 KB of arrival counters — zero before the first use, left zero by every launch — followed
+    by the partial tiles of split problems.  The slot size and count only ever grow, and growing allocates a new, zeroed
+    buffer: a counter block therefore never lands on memory that held partial sums.  (The old buffer stays alive until
+    every launch that used it has been ordered before the new one's first use — stream order on the one stream using it.)"""
 
     def __init__(self):
         self._bufs = {}
 
-    def get(self, device, nbytes: int) -> torch.Tensor:
+    def get(self, device, slots: int, slot_bytes: int) -> tuple[torch.Tensor, int]:
         key = str(device)
-        buf = self._bufs.get(key)
-        if buf is None or buf.numel() < nbytes:
-            size = max(nbytes, 8 << 20) * 3 // 2
-            buf = self._bufs[key] = torch.zeros((size,), dtype=torch.uint8, device=device)
-        return buf
+        buf, n, size = self._bufs.get(key, (None, 0, 0))
+        if buf is None or n < slots or size < slot_bytes:
+            n = max(n, slots, 3)
+            size = max(size, (max(slot_bytes, 4 << 20) * 3 // 2 + 255) // 256 * 256)
+            buf = torch.zeros((n * size,), dtype=torch.uint8, device=device)
+            self._bufs[key] = (buf, n, size)
+        return buf, size
 
 
 _grad_ws = _GradWorkspace()
@@ -235,11 +238,9 @@ def lora_grad_batched(leaves: list[tuple]) -> None:
         chunks.append((sub, n, (int(need) + 255) // 256 * 256))
     # the launches of one flush are independent of each other (different leaves, different outputs): each gets its own
     # slice of the workspace and all but the first are chained, so that they overlap instead of each ending in its own tail
-    ws = _grad_ws.get(dev, sum(c[2] for c in chunks))
-    off = 0
+    ws, slot = _grad_ws.get(dev, len(chunks), max(c[2] for c in chunks))
     for i, (sub, n, need) in enumerate(chunks):
-        N.check(lib.otb_lora_grad_batched(sub, n, ws.data_ptr() + off, need, 1 if i > 0 else 0, _stream()), "otb_lora_grad_batched")
-        off += need
+        N.check(lib.otb_lora_grad_batched(sub, n, ws.data_ptr() + i * slot, slot, 1 if i > 0 else 0, _stream()), "otb_lora_grad_batched")
         _count()
 
 

@@ -171,7 +171,9 @@ def test_lora_module_vs_reference_golden_bf16_inputs(L, dev, golden, name):
     y = base(x)
     dx, dA, dB = torch.autograd.grad(y, [x, mod.lora_down.weight, mod.lora_up.weight], t("dy").bfloat16())
     assert_within_ulps(y, t("y"), "y", 1 / 8)
-    assert_within_ulps(dx, t("dx"), "dX", 1 / 8)
+    # a k x k leaf forms dX from kh*kw overlapping patch gradients, each a bf16 output of K-a, added in fp32: kh*kw roundings
+    # at the scale of the addends instead of one at the scale of the sum -> small elements are held to the ulp at the rms
+    assert_within_ulps(dx, t("dx"), "dX", 1.0 if name == "conv3x3" else 1 / 8)
     assert_within_ulps(dA, t("dA"), "dA", 1.0)
     assert_within_ulps(dB, t("dB"), "dB", 1.0)
 
