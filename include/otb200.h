@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define OTB_ABI_VERSION 4   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs.  3: otb_grad_exchange, otb_grad_norm_from_partials.
-                               4: OTB_TS_TABLE (ts_cdf / ts_cdf_len appended to otb_noise_args); otb_lora_grad_batched; otb_lora_linear_grouped takes up to 32 members; otb_lora_linear_args.flags */
+                               4: OTB_TS_TABLE (ts_cdf / ts_cdf_len appended to otb_noise_args); otb_lora_grad_batched; otb_lora_linear_grouped takes up to 32 members; otb_lora_linear_args.flags; otb_adafactor_multi / otb_came_multi; otb_dora_compose / otb_dora_backward */
 
 /* error codes */
 #define OTB_OK            0
@@ -161,6 +161,83 @@ int otb_grad_norm_from_partials(const float* partials, int32_t n_partials, float
                                 float* out_norm_coef, void* stream);
 /* in-place g *= coef for callers that want the reference's two-pass behaviour */
 int otb_grad_scale_multi(const otb_optim_launch* args, const float* coef, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * DoRA (weight-decomposed LoRA): the weight-sized part of
+ * DoRAModule.forward  modules/module/LoRAModule.py:385-419  and of its backward.
+ *     V = W + BA * scale ;  norm = ||V|| per input-channel group (or per output row) (+ eps), detached ;
+ *     WP = dora_scale * (V / norm)
+ * The activation-sized GEMMs (y = x WP^T, dX = dY WP) run on otb_lora_linear with rank 0; BA = B A, G = dY^T x and the
+ * rank-r products of the backward are plain library GEMMs on the caller's side.  [N, J] matrices are row-major; column j
+ * belongs to group j / group_size (group_size = kh * kw of a conv leaf, 1 for Linear).
+ * ---------------------------------------------------------------------------------- */
+typedef struct otb_dora_args {
+    const void*  w;           /* [N, J] frozen base weight, w_dtype                                                    */
+    const float* ba;          /* [N, J] fp32: lora_up . lora_down (make_weight, :76-91), unscaled                      */
+    const float* dora_scale;  /* [J / group_size] (input axis) or [N] (output axis), fp32                              */
+    float*       norm;        /* same shape: written by otb_dora_compose, read by otb_dora_backward                     */
+    float*       scratch;     /* max(N, J) floats                                                                      */
+    void*        wp;          /* compose: [N, J] bf16 out                                                              */
+    void*        wpt;         /* compose: [J, N] bf16 out (the K-major operand of the dX launch), or NULL              */
+    const void*  G;           /* backward: [N, J] bf16, dL/dWP                                                         */
+    float*       dV;          /* backward: [N, J] fp32 out, dL/dV with the norm held constant (:396-400)               */
+    float*       d_scale;     /* backward: gradient of dora_scale, fp32 out                                            */
+    int32_t N, J, group_size, out_axis, w_dtype;
+    float scale;              /* alpha / rank                                                                          */
+    float eps;                /* torch.finfo(fp32).eps when norm_epsilon, else 0                                       */
+} otb_dora_args;
+
+int otb_dora_compose(const otb_dora_args* args, void* stream);
+int otb_dora_backward(const otb_dora_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Factored optimizers: multi-tensor Adafactor and CAME, one launch per step,
+ * one CTA per tensor, every reduction in a fixed order, no host read-back.
+ * Replaces: step_adafactor_parameter  modules/util/optimizer/adafactor_extensions.py:17-93
+ *           CAME.step_parameter       modules/util/optimizer/CAME.py:80-176
+ *           add_stochastic_           modules/util/bf16_stochastic_rounding.py:33-45
+ * A tensor with >= 2 dimensions is a batch of [rows, cols] matrices (batch = product of the leading dimensions) with a
+ * row factor [batch, rows] and a column factor [batch, cols]; a 1-D tensor keeps an unfactored second moment
+ * (batch = rows = 1, cols = numel).  State tensors are fp32, as in the reference.
+ * ---------------------------------------------------------------------------------- */
+#define OTB_FACTORED_FACTORED        1   /* sq_row / sq_col (and res_row / res_col) instead of sq                     */
+#define OTB_FACTORED_FIRST_MOMENT    2   /* Adafactor: beta1 is set (exp_avg present); CAME always has one            */
+#define OTB_FACTORED_SCALE_PARAMETER 4   /* Adafactor: lr_t = max(eps1, RMS(p)) * lr                                  */
+#define OTB_FACTORED_SR              8   /* CAME: bf16 parameter written with stochastic rounding (add_stochastic_)   */
+
+typedef struct otb_factored_tensor {
+    void*       p;          /* parameter, p_dtype                                                                     */
+    const void* g;          /* gradient, p_dtype                                                                      */
+    float*      exp_avg;    /* [numel] first moment, or NULL                                                          */
+    float*      sq_row;     /* [batch, rows]  exp_avg_sq_row                                                          */
+    float*      sq_col;     /* [batch, cols]  exp_avg_sq_col                                                          */
+    float*      sq;         /* [numel]        exp_avg_sq (not factored)                                               */
+    float*      res_row;    /* CAME: exp_avg_res_row                                                                  */
+    float*      res_col;    /* CAME: exp_avg_res_col                                                                  */
+    float*      rms_out;    /* optional [1]: RMS(p) of this step (state["RMS"])                                       */
+    int64_t numel;
+    int64_t rng_base;       /* global element index of element 0 in the stochastic-rounding stream                    */
+    int64_t scratch_offset; /* this tensor's `batch` floats inside otb_factored_launch.scratch                        */
+    int32_t batch, rows, cols;
+    int32_t p_dtype, flags;
+    float beta1;            /* Adafactor beta1 / CAME betas[0]                                                        */
+    float beta2;            /* Adafactor beta2t = 1 - step^decay_rate / CAME betas[1]                                 */
+    float beta3;            /* CAME betas[2]                                                                          */
+    float eps0, eps1, clip_threshold;
+    float lr;               /* Adafactor: the (relative) step size before parameter scaling; CAME: lr                 */
+    float weight_decay;
+} otb_factored_tensor;
+
+typedef struct otb_factored_launch {
+    const otb_factored_tensor* tensors;   /* device array                                                             */
+    float*   scratch;                     /* device, sum of `batch` over the tensors                                  */
+    int32_t  n_tensors;
+    uint64_t seed, offset;                /* CAME stochastic rounding: the weight-decay draw uses `offset`, the update
+                                             draw `offset + 1` (`offset` when weight_decay == 0)                      */
+} otb_factored_launch;
+
+int otb_adafactor_multi(const otb_factored_launch* args, void* stream);
+int otb_came_multi(const otb_factored_launch* args, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K-r  data-parallel gradient exchange fused with the squared gradient norm, over NVLink
@@ -420,8 +497,9 @@ int64_t otb_lora_grad_workspace_bytes(const otb_lora_grad_args* leaves, int32_t 
 /* Utility used by tests and the data-parallel bucket path: fp32 <-> bf16 casts with
  * round-to-nearest-even, and a device-side Philox dump for known-answer tests. */
 /* sizeof() of every argument struct, in declaration order: optim_tensor, optim_launch, shadow_tensor,
- * noise_args, loss_args, lora_linear_args, lora_grad_args, grad_exchange_args.  Bindings assert these at load time. */
-int otb_struct_sizes(int32_t* out8);
+ * noise_args, loss_args, lora_linear_args, lora_grad_args, grad_exchange_args, factored_tensor, factored_launch, dora_args.
+ * Bindings assert these at load time. */
+int otb_struct_sizes(int32_t* out11);
 
 int otb_philox_dump(uint64_t seed, uint64_t offset, uint32_t stream_id, int64_t first_group,
                     int64_t n_groups, uint32_t* out4, void* stream);

@@ -121,6 +121,32 @@ class LoraGradArgs(C.Structure):
     ]
 
 
+FACTORED_FACTORED, FACTORED_FIRST_MOMENT, FACTORED_SCALE_PARAMETER, FACTORED_SR = 1, 2, 4, 8
+
+
+class FactoredTensor(C.Structure):
+    _fields_ = [
+        ("p", _vp), ("g", _vp), ("exp_avg", _vp), ("sq_row", _vp), ("sq_col", _vp), ("sq", _vp), ("res_row", _vp), ("res_col", _vp),
+        ("rms_out", _vp),
+        ("numel", _i64), ("rng_base", _i64), ("scratch_offset", _i64),
+        ("batch", _i32), ("rows", _i32), ("cols", _i32), ("p_dtype", _i32), ("flags", _i32),
+        ("beta1", _f32), ("beta2", _f32), ("beta3", _f32), ("eps0", _f32), ("eps1", _f32), ("clip_threshold", _f32),
+        ("lr", _f32), ("weight_decay", _f32),
+    ]
+
+
+class DoraArgs(C.Structure):
+    _fields_ = [
+        ("w", _vp), ("ba", _vp), ("dora_scale", _vp), ("norm", _vp), ("scratch", _vp), ("wp", _vp), ("wpt", _vp), ("G", _vp), ("dV", _vp),
+        ("d_scale", _vp),
+        ("N", _i32), ("J", _i32), ("group_size", _i32), ("out_axis", _i32), ("w_dtype", _i32), ("scale", _f32), ("eps", _f32),
+    ]
+
+
+class FactoredLaunch(C.Structure):
+    _fields_ = [("tensors", _vp), ("scratch", _vp), ("n_tensors", _i32), ("seed", _u64), ("offset", _u64)]
+
+
 MAX_RANKS = 16           # OTB_MAX_RANKS
 GRAD_BATCH_MAX = 32      # OTB_GRAD_BATCH_MAX
 LORA_GROUP_MAX = 32      # OTB_LORA_GROUP_MAX
@@ -160,10 +186,15 @@ SYMBOLS = {
     "otb_lora_grad_ab": (C.c_int, [C.POINTER(LoraGradArgs), _vp]),
     "otb_lora_grad_batched": (C.c_int, [C.POINTER(LoraGradArgs), C.c_int32, _vp, _i64, C.c_int32, _vp]),
     "otb_lora_grad_workspace_bytes": (_i64, [C.POINTER(LoraGradArgs), C.c_int32]),
+    "otb_dora_compose": (C.c_int, [C.POINTER(DoraArgs), _vp]),
+    "otb_dora_backward": (C.c_int, [C.POINTER(DoraArgs), _vp]),
+    "otb_adafactor_multi": (C.c_int, [C.POINTER(FactoredLaunch), _vp]),
+    "otb_came_multi": (C.c_int, [C.POINTER(FactoredLaunch), _vp]),
     "otb_philox_dump": (C.c_int, [_u64, _u64, _u32, _i64, _i64, _vp, _vp]),
     "otb_struct_sizes": (C.c_int, [C.POINTER(C.c_int32)]),
 }
-_STRUCTS = (OptimTensor, OptimLaunch, ShadowTensor, NoiseArgs, LossArgs, LoraLinearArgs, LoraGradArgs, GradExchangeArgs)
+_STRUCTS = (OptimTensor, OptimLaunch, ShadowTensor, NoiseArgs, LossArgs, LoraLinearArgs, LoraGradArgs, GradExchangeArgs,
+            FactoredTensor, FactoredLaunch, DoraArgs)
 
 _lib = None
 

@@ -110,6 +110,9 @@ extern "C" int otb_struct_sizes(int32_t* out) {
     out[5] = (int32_t)sizeof(otb_lora_linear_args);
     out[6] = (int32_t)sizeof(otb_lora_grad_args);
     out[7] = (int32_t)sizeof(otb_grad_exchange_args);
+    out[8] = (int32_t)sizeof(otb_factored_tensor);
+    out[9] = (int32_t)sizeof(otb_factored_launch);
+    out[10] = (int32_t)sizeof(otb_dora_args);
     return OTB_OK;
 }
 

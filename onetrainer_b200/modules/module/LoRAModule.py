@@ -645,7 +645,121 @@ class LoRAModule(PeftBase):
         pass  # not implemented in the reference either (:329-331)
 
 
+# ---------------------------------------------------------------------------------------
+# DoRA
+# ---------------------------------------------------------------------------------------
+class _DoraFn(torch.autograd.Function):
+    """y = x WP^T + bias with WP = dora_scale * (V / ||V||), V = W + (B A) * alpha / rank  (DoRAModule.forward,
+    reference :385-419) and its backward with the norm held constant (:396-400).
+
+    Activation-sized work on K-a (rank 0): y = x WP^T forward, dX = dY WP backward, on the bf16 WP / WP^T the compose
+    kernel emits.  Weight-sized work: B A, G = dY^T x (the bf16 GEMM autocast gives the reference), dV A^T and B^T dV are
+    library GEMMs; norms, WP, dV and d(dora_scale) are otb_dora_compose / otb_dora_backward."""
+
+    @staticmethod
+    def forward(ctx, x2: Tensor, a_param: Tensor, b_param: Tensor, m_param: Tensor, mod: "DoRAModule"):
+        om = mod.orig_module
+        w2 = om.weight.detach().reshape(om.weight.shape[0], -1)
+        A2, B2 = a_param.detach().reshape(a_param.shape[0], -1).float(), b_param.detach().reshape(b_param.shape[0], -1).float()
+        ba = B2 @ A2
+        gsz = 1 if isinstance(om, nn.Linear) else om.kernel_size[0] * om.kernel_size[1]
+        eps = torch.finfo(torch.float32).eps if mod.norm_epsilon else 0.0
+        wp, wpt, norm = ops.dora_compose(w2.contiguous(), ba, m_param, mod._scale(), eps=eps, group_size=gsz, out_axis=mod.decompose_output_axis,
+                                         want_transposed=ctx.needs_input_grad[0])
+        y, _ = ops.lora_linear(x2, wp, None, None, om.bias, 0.0, want_t=False)
+        ctx.mod, ctx.gsz = mod, gsz
+        ctx.save_for_backward(x2, wpt, norm)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        mod: DoRAModule = ctx.mod
+        x2, wpt, norm = ctx.saved_tensors
+        om = mod.orig_module
+        dy = dy.contiguous()
+        if dy.dtype != torch.bfloat16:
+            dy = dy.to(torch.bfloat16)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx, _ = ops.lora_linear(dy, wpt, None, None, None, 0.0, want_t=False)
+        dA = dB = dm = None
+        if any(ctx.needs_input_grad[1:4]):
+            A, B, m = mod.lora_down.weight, mod.lora_up.weight, mod.dora_scale
+            A2, B2 = A.detach().reshape(A.shape[0], -1).float(), B.detach().reshape(B.shape[0], -1).float()
+            w2 = om.weight.detach().reshape(om.weight.shape[0], -1).contiguous()
+            G = dy.t() @ x2                                           # dL/dWP, bf16 as the reference's autocast GEMM leaves it
+            dV, dmf = ops.dora_backward(G.contiguous(), w2, B2 @ A2, m, norm, mod._scale(), group_size=ctx.gsz, out_axis=mod.decompose_output_axis)
+            s = mod._scale()
+            if ctx.needs_input_grad[1]:
+                dA = ((B2.t() @ dV) * s).reshape(A.shape).to(A.dtype)
+            if ctx.needs_input_grad[2]:
+                dB = ((dV @ A2.t()) * s).reshape(B.shape).to(B.dtype)
+            if ctx.needs_input_grad[3]:
+                dm = dmf.reshape(m.shape).to(m.dtype)
+        return dx, dA, dB, dm, None
+
+
+class DoRAModule(LoRAModule):
+    """Weight-decomposed low-rank adaptation (reference DoRAModule, :333-419): same constructor keywords
+    (`norm_epsilon`, `decompose_output_axis`, `train_device`), same `dora_scale` parameter shape and state-dict key."""
+    dora_num_dims: int
+    dora_scale: Tensor | None
+    norm_epsilon: bool
+    decompose_output_axis: bool
+
+    def __init__(self, *args, **kwargs):
+        self.dora_scale = None
+        self.norm_epsilon = kwargs.pop("norm_epsilon", False)
+        self.decompose_output_axis = kwargs.pop("decompose_output_axis", False)
+        self.train_device = kwargs.pop("train_device")
+        super().__init__(*args, **kwargs)
+
+    def initialize_weights(self):
+        super().initialize_weights()
+        w = self.orig_module.weight.detach().to(device=self.train_device, dtype=torch.float)
+        self.dora_num_dims = w.dim() - 1
+        if self.decompose_output_axis:
+            scale = torch.norm(w.reshape(w.shape[0], -1), dim=1, keepdim=True).reshape(w.shape[0], *[1] * self.dora_num_dims)
+        else:
+            scale = torch.norm(w.transpose(1, 0).reshape(w.shape[1], -1), dim=1, keepdim=True) \
+                .reshape(w.shape[1], *[1] * self.dora_num_dims).transpose(1, 0)
+        self.dora_scale = nn.Parameter(scale.contiguous().to(device=self.orig_module.weight.device))
+
+    def check_initialized(self):
+        super().check_initialized()
+        assert self.dora_scale is not None
+
+    def forward(self, x, *args, **kwargs):
+        self.check_initialized()
+        if not x.is_cuda:
+            raise RuntimeError("the fused DoRA path runs on sm_100a CUDA tensors only; there is no CPU fallback")
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+        if out_dtype != torch.bfloat16:
+            raise NotImplementedError(f"the fused DoRA kernel computes in bf16 (tcgen05 kind::f16); got compute dtype {out_dtype}")
+        om = self.orig_module
+        x = self.dropout(x)                      # the DoRA code base drops out the INPUT (reference :413-416)
+        if isinstance(om, nn.Conv2d):
+            b_, c_, h_, w_ = x.shape
+            if self._is_pointwise(om):
+                x2 = x.permute(0, 2, 3, 1).reshape(-1, c_)
+            else:
+                (kh, kw), (sh, sw), (ph, pw), (dh, dw) = om.kernel_size, om.stride, om.padding, om.dilation
+                h_ = (h_ + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+                w_ = (w_ + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+                x2 = _UnfoldRows.apply(x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16), om.kernel_size, om.dilation, tuple(om.padding), om.stride)
+        else:
+            x2 = x.reshape(-1, x.shape[-1])
+        self._last_rows = x2.shape[0]
+        if x2.dtype != torch.bfloat16:
+            x2 = x2.to(torch.bfloat16)
+        y2 = _DoraFn.apply(x2.contiguous(), self.lora_down.weight, self.lora_up.weight, self.dora_scale, self)
+        if isinstance(om, nn.Conv2d):
+            return y2.view(b_, h_, w_, -1).permute(0, 3, 1, 2)
+        return y2.view(*x.shape[:-1], y2.shape[-1])
+
+
 DummyLoRAModule = LoRAModule.make_dummy()
+DummyDoRAModule = DoRAModule.make_dummy()
 
 
 # ---------------------------------------------------------------------------------------
@@ -665,12 +779,17 @@ class LoRAModuleWrapper:
         self.rank = config.lora_rank
         self.alpha = config.lora_alpha
         self.module_filter = [x.strip() for x in module_filter] if module_filter is not None else []
-        if enum_name(self.peft_type) != "LORA" or getattr(config, "lora_decompose", False):
-            raise NotImplementedError("only plain LoRA is implemented on the B200 path (DoRA / LoHa: SURVEY.md §8f rank 4)")
-        self.klass = LoRAModule
-        self.dummy_klass = DummyLoRAModule
+        if enum_name(self.peft_type) != "LORA":
+            raise NotImplementedError("LoRA and DoRA are implemented on the B200 path; LoHa is not (SURVEY.md §2.1)")
         self.additional_args = [self.rank, self.alpha]
-        self.additional_kwargs = {}
+        if getattr(config, "lora_decompose", False):          # reference :448-457
+            self.klass, self.dummy_klass = DoRAModule, DummyDoRAModule
+            self.additional_kwargs = {"norm_epsilon": getattr(config, "lora_decompose_norm_epsilon", False),
+                                      "decompose_output_axis": getattr(config, "lora_decompose_output_axis", False),
+                                      "train_device": torch.device(config.train_device)}
+        else:
+            self.klass, self.dummy_klass = LoRAModule, DummyLoRAModule
+            self.additional_kwargs = {}
         self.lora_modules = self.__create_modules(orig_module)
         self._shadow = None
         self._shadow_key = None
@@ -706,7 +825,7 @@ class LoRAModuleWrapper:
         self.context_launches: list[ContextLaunch] = []
         for m in self._trainable():
             m._ctx_parked = None
-        if os.environ.get("OTB_CTX_GROUP", "1") == "0":
+        if os.environ.get("OTB_CTX_GROUP", "1") == "0" or self.klass is not LoRAModule:      # DoRA leaves compose their own weight
             return
         classes: dict[tuple, list[LoRAModule]] = {}
         for name, m in self.lora_modules.items():
@@ -741,7 +860,7 @@ class LoRAModuleWrapper:
         self.sibling_groups: list[SiblingGroup] = []
         for m in self._trainable():
             m._group = None
-        if os.environ.get("OTB_GROUP_SIBLINGS", "1") == "0":
+        if os.environ.get("OTB_GROUP_SIBLINGS", "1") == "0" or self.klass is not LoRAModule:
             return
         by_parent: dict[str, dict[str, LoRAModule]] = {}
         in_context_launch = {id(m) for cl in self.context_launches for m in cl.members}      # those are batched network-wide
@@ -771,7 +890,7 @@ class LoRAModuleWrapper:
         """Re-emit the bf16 (and transposed) shadows of every A/B in ONE launch.  Called after each
         optimizer step (post-step hook) and whenever a leaf sees its parameters changed."""
         mods = self._trainable()
-        if not mods:
+        if not mods or self.klass is not LoRAModule:       # DoRA reads its fp32 masters directly
             return
         key = tuple((m.lora_down.weight.data_ptr(), m.lora_up.weight.data_ptr(), m.lora_down.weight.dtype) for m in mods)
         if self._shadow is None or key != self._shadow_key:

@@ -28,11 +28,19 @@ class _ModelTypeStub:
 @dataclass
 class TrainOptimizerConfig:
     """The fields of the reference's TrainOptimizerConfig (TrainConfig.py:34-262) that `create_optimizer` reads for
-    ADAM / ADAMW (create.py:481-534); None means "use the optimizer's default", as there."""
+    ADAM / ADAMW (create.py:481-534), ADAFACTOR (:914-936) and CAME (:939-951); None means "use the optimizer's default",
+    as there."""
     optimizer: object = Optimizer.ADAMW
     beta1: float | None = None
     beta2: float | None = None
+    beta3: float | None = None
     eps: float | None = None
+    eps2: float | None = None
+    clip_threshold: float | None = None
+    decay_rate: float | None = None
+    scale_parameter: bool | None = None
+    relative_step: bool | None = None
+    warmup_init: bool | None = None
     weight_decay: float | None = None
     amsgrad: bool | None = False
     foreach: bool | None = False
@@ -55,6 +63,8 @@ class TrainConfig:
     lora_rank: int = 16
     lora_alpha: float = 1.0
     lora_decompose: bool = False
+    lora_decompose_norm_epsilon: bool = True
+    lora_decompose_output_axis: bool = False
     lora_layers: str = ""
     dropout_probability: float = 0.0
     # noise

@@ -27,8 +27,10 @@ def create_optimizer(parameter_group_collection: NamedParameterGroupCollection, 
     `ema` / `ema_step_fn` / `clip_grad_norm` optionally fold EMA and the global-norm clip into that launch."""
     oc = config.optimizer
     name = enum_name(oc.optimizer)
+    if name in ("ADAFACTOR", "CAME"):
+        return _create_factored(name, parameter_group_collection, state_dict, config, ema, clip_grad_norm)
     if name not in ("ADAMW", "ADAM"):
-        raise NotImplementedError(f"optimizer {name} has no fused step on the B200 path (AdamW and Adam do)")
+        raise NotImplementedError(f"optimizer {name} has no fused step on the B200 path (AdamW, Adam, Adafactor and CAME do)")
     if oc.stochastic_rounding and (oc.fused or oc.foreach):
         raise RuntimeError('"stochastic_rounding" is only allowed when "fused" and "foreach" are disabled')
     if oc.fused_back_pass and (oc.fused or oc.foreach):
@@ -40,6 +42,35 @@ def create_optimizer(parameter_group_collection: NamedParameterGroupCollection, 
         amsgrad=_or(oc.amsgrad, False), foreach=_or(oc.foreach, False), maximize=_or(oc.maximize, False),
         capturable=_or(oc.capturable, False), differentiable=_or(oc.differentiable, False), fused=_or(oc.fused, False))
     patch(optimizer, oc.stochastic_rounding, ema=ema, ema_step_fn=ema_step_fn, clip_grad_norm=clip_grad_norm)
+    if state_dict is not None:
+        optimizer.load_state_dict(state_dict)
+    return optimizer
+
+
+def _create_factored(name: str, parameter_group_collection, state_dict, config, ema, clip_grad_norm):
+    """ADAFACTOR (create.py:914-936: transformers' Adafactor + patch_adafactor) and CAME (:939-951), same arguments and
+    defaults.  EMA and the global-norm clip are NOT folded into these launches (`ema` / `clip_grad_norm` are ignored): the
+    trainer's own EMAModuleWrapper.step and clip_grad_norm_ calls do them, one multi-tensor launch each."""
+    oc = config.optimizer
+    parameters = parameter_group_collection.parameters_for_optimizer(config)
+    if name == "ADAFACTOR":
+        from transformers.optimization import Adafactor
+        from .optimizer.adafactor_extensions import patch_adafactor
+        if oc.relative_step:
+            for parameter in parameters:
+                if isinstance(parameter, dict) and "lr" in parameter:
+                    parameter.pop("lr")
+        optimizer = Adafactor(
+            params=parameters, lr=None if oc.relative_step is True else config.learning_rate,
+            eps=(_or(oc.eps, 1e-30), _or(oc.eps2, 1e-3)), clip_threshold=_or(oc.clip_threshold, 1.0), decay_rate=_or(oc.decay_rate, -0.8),
+            beta1=oc.beta1, weight_decay=_or(oc.weight_decay, 0.0), scale_parameter=_or(oc.scale_parameter, True),
+            relative_step=_or(oc.relative_step, True), warmup_init=_or(oc.warmup_init, False))
+        patch_adafactor(optimizer, oc.stochastic_rounding)
+    else:
+        from .optimizer.CAME import CAME
+        optimizer = CAME(params=parameters, lr=config.learning_rate, eps=(_or(oc.eps, 1e-30), _or(oc.eps2, 1e-16)),
+                         betas=(_or(oc.beta1, 0.9), _or(oc.beta2, 0.999), _or(oc.beta3, 0.9999)), weight_decay=_or(oc.weight_decay, 0),
+                         stochastic_rounding=oc.stochastic_rounding)
     if state_dict is not None:
         optimizer.load_state_dict(state_dict)
     return optimizer

@@ -18,7 +18,7 @@ LossScaler = _StrEnum("LossScaler", {k: k for k in ("NONE", "BATCH", "GRADIENT_A
 PeftType = _StrEnum("PeftType", {k: k for k in ("LORA", "LOHA")})
 LearningRateScaler = _StrEnum("LearningRateScaler", {k: k for k in ("NONE", "BATCH", "GRADIENT_ACCUMULATION", "BOTH")})
 EMAMode = _StrEnum("EMAMode", {k: k for k in ("OFF", "GPU", "CPU")})
-Optimizer = _StrEnum("Optimizer", {k: k for k in ("ADAM", "ADAMW")})     # the two the fused step covers
+Optimizer = _StrEnum("Optimizer", {k: k for k in ("ADAM", "ADAMW", "ADAFACTOR", "CAME")})     # the ones with a fused step
 
 
 def enum_name(x) -> str:

@@ -252,6 +252,57 @@ def lora_grad_ab(x, dy, gs, ts, dA: torch.Tensor | None, dB: torch.Tensor | None
 
 
 # --------------------------------------------------------------------------------------
+# DoRA: weight-space kernels
+# --------------------------------------------------------------------------------------
+def _dora_args(w2, ba, dora_scale, norm, scratch, scale, eps, group_size, out_axis, **kw) -> "N.DoraArgs":
+    Nn, J = w2.shape
+    return N.DoraArgs(w=w2.data_ptr(), ba=ba.data_ptr(), dora_scale=dora_scale.data_ptr(), norm=norm.data_ptr(), scratch=scratch.data_ptr(),
+                      N=Nn, J=J, group_size=int(group_size), out_axis=1 if out_axis else 0, w_dtype=N.dtype_code(w2.dtype),
+                      scale=float(scale), eps=float(eps), **{k: N.ptr(v) for k, v in kw.items()})
+
+
+def dora_compose(w2: torch.Tensor, ba: torch.Tensor, dora_scale: torch.Tensor, scale: float, *, eps: float = 0.0, group_size: int = 1,
+                 out_axis: bool = False, want_transposed: bool = True):
+    """WP = dora_scale * (V / ||V||), V = w2 + ba * scale (DoRAModule.forward, LoRAModule.py:389-412): returns
+    (wp [N, J] bf16, wp^T [J, N] bf16 or None, norm fp32).  w2: [N, J] base weight; ba: [N, J] fp32; dora_scale flat fp32."""
+    N.require_cuda(w2, ba, dora_scale)
+    Nn, J = w2.shape
+    if not (w2.is_contiguous() and ba.is_contiguous() and ba.dtype == torch.float32 and tuple(ba.shape) == (Nn, J)):
+        raise ValueError("dora_compose: w2 and ba must be contiguous [N, J], ba fp32")
+    groups = Nn if out_axis else J // group_size
+    m = dora_scale.detach().reshape(-1)
+    if m.numel() != groups or m.dtype != torch.float32 or not m.is_contiguous():
+        raise ValueError(f"dora_compose: dora_scale must be {groups} contiguous fp32 values")
+    dev = w2.device
+    norm = torch.empty((groups,), dtype=torch.float32, device=dev)
+    scratch = torch.empty((max(Nn, J),), dtype=torch.float32, device=dev)
+    wp = torch.empty((Nn, J), dtype=torch.bfloat16, device=dev)
+    wpt = torch.empty((J, Nn), dtype=torch.bfloat16, device=dev) if want_transposed else None
+    a = _dora_args(w2, ba, m, norm, scratch, scale, eps, group_size, out_axis, wp=wp, wpt=wpt)
+    N.check(N.lib().otb_dora_compose(C.byref(a), _stream()), "otb_dora_compose")
+    _count(3)
+    return wp, wpt, norm
+
+
+def dora_backward(G: torch.Tensor, w2: torch.Tensor, ba: torch.Tensor, dora_scale: torch.Tensor, norm: torch.Tensor, scale: float, *,
+                  group_size: int = 1, out_axis: bool = False):
+    """(dV [N, J] fp32, d_dora_scale flat fp32) from G = dL/dWP (bf16), with the norm held constant (LoRAModule.py:396-400)."""
+    N.require_cuda(G, w2, ba, dora_scale, norm)
+    Nn, J = w2.shape
+    if G.dtype != torch.bfloat16 or not G.is_contiguous() or tuple(G.shape) != (Nn, J):
+        raise ValueError("dora_backward: G must be a contiguous bf16 [N, J] tensor")
+    dev = w2.device
+    m = dora_scale.detach().reshape(-1)
+    dV = torch.empty((Nn, J), dtype=torch.float32, device=dev)
+    dm = torch.empty_like(m)
+    scratch = torch.empty((max(Nn, J),), dtype=torch.float32, device=dev)
+    a = _dora_args(w2, ba, m, norm, scratch, scale, 0.0, group_size, out_axis, G=G, dV=dV, d_scale=dm)
+    N.check(N.lib().otb_dora_backward(C.byref(a), _stream()), "otb_dora_backward")
+    _count(2)
+    return dV, dm
+
+
+# --------------------------------------------------------------------------------------
 # K-b1
 # --------------------------------------------------------------------------------------
 def noise_addnoise(*, latent=None, noise_in=None, coef_x0=None, coef_noise=None, timestep=None,
