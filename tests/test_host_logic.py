@@ -110,8 +110,10 @@ def test_empty_filter_selects_everything_supported_and_unsupported_layers_raise(
         LoRAModule("p", nn.Conv2d(8, 8, 3, padding=1, groups=2), 8, 1.0)
     with pytest.raises(NotImplementedError, match="zero-padded"):
         LoRAModule("p", nn.Conv2d(8, 8, 3, padding=1, padding_mode="reflect"), 8, 1.0)
-    with pytest.raises(NotImplementedError):
-        LoRAModuleWrapper(_net(), "lora_unet", TrainConfig(lora_decompose=True), ["to_q"])     # DoRA
+    from onetrainer_b200.modules.module.LoRAModule import DoRAModule
+    dora = LoRAModuleWrapper(_net(), "lora_unet", TrainConfig(train_device="cpu", lora_decompose=True), ["to_q"])     # DoRA (reference :448-457)
+    assert dora.lora_modules and all(isinstance(m, DoRAModule) and m.dora_scale.dtype == torch.float32 for m in dora.lora_modules.values())
+    assert all(k.endswith(("lora_down.weight", "lora_up.weight", "alpha", "dora_scale")) for k in dora.state_dict())
     with pytest.raises(NotImplementedError):
         LoRAModuleWrapper(_net(), "lora_unet", TrainConfig(peft_type=PeftType.LOHA), ["to_q"])
     with pytest.raises(NotImplementedError, match="Only Linear and Conv2d"):
@@ -326,8 +328,19 @@ def test_create_optimizer_and_ema_keep_the_reference_contract():
         create.create_optimizer(_collection(), None, TrainConfig(optimizer=TrainOptimizerConfig(stochastic_rounding=True, foreach=True)))
     with pytest.raises(RuntimeError, match='"fused_back_pass" is only allowed'):
         create.create_optimizer(_collection(), None, TrainConfig(optimizer=TrainOptimizerConfig(fused_back_pass=True, fused=True)))
-    with pytest.raises(NotImplementedError, match="ADAFACTOR"):
-        create.create_optimizer(_collection(), None, TrainConfig(optimizer=TrainOptimizerConfig(optimizer="ADAFACTOR")))
+    with pytest.raises(NotImplementedError, match="LION"):
+        create.create_optimizer(_collection(), None, TrainConfig(optimizer=TrainOptimizerConfig(optimizer="LION")))
+    # ADAFACTOR (create.py:914-936) and CAME (:939-951): the reference's classes and defaults, step rebound to the fused launch
+    af = create.create_optimizer(_collection(), None, TrainConfig(optimizer=TrainOptimizerConfig(optimizer=Optimizer.ADAFACTOR, relative_step=True)))
+    assert type(af).__name__ == "Adafactor" and af.param_groups[0]["relative_step"] and af.param_groups[0]["lr"] is None
+    assert af.param_groups[0]["eps"] == (1e-30, 1e-3) and af.param_groups[0]["decay_rate"] == -0.8 and hasattr(af, "step_parameter")
+    af2 = create.create_optimizer(_collection(), None, TrainConfig(learning_rate=1e-4, optimizer=TrainOptimizerConfig(
+        optimizer=Optimizer.ADAFACTOR, relative_step=False, scale_parameter=False, beta1=0.9)))
+    assert af2.param_groups[0]["lr"] == 1e-4 and af2.param_groups[0]["beta1"] == 0.9 and af2.stochastic_rounding is False
+    came = create.create_optimizer(_collection(), None, TrainConfig(learning_rate=2e-4, optimizer=TrainOptimizerConfig(
+        optimizer=Optimizer.CAME, stochastic_rounding=True)))
+    assert type(came).__name__ == "CAME" and came.defaults["betas"] == (0.9, 0.999, 0.9999) and came.defaults["eps"] == (1e-30, 1e-16)
+    assert came.stochastic_rounding is True and came.param_groups[1]["lr"] == 1e-5
     assert create.create_ema(_collection().parameters(), None, cfg) is None
     with pytest.raises(NotImplementedError, match="CPU"):
         create.create_ema(_collection().parameters(), None, TrainConfig(ema=EMAMode.CPU))
