@@ -223,6 +223,7 @@ typedef struct otb_factored_tensor {
     float beta1;            /* Adafactor beta1 / CAME betas[0]                                                        */
     float beta2;            /* Adafactor beta2t = 1 - step^decay_rate / CAME betas[1]                                 */
     float beta3;            /* CAME betas[2]                                                                          */
+    float one_minus_beta1, one_minus_beta2, one_minus_beta3;   /* formed in double on the host: 1 - (float)0.9999 is off by 1.7e-4 */
     float eps0, eps1, clip_threshold;
     float lr;               /* Adafactor: the (relative) step size before parameter scaling; CAME: lr                 */
     float weight_decay;

@@ -130,7 +130,8 @@ class FactoredTensor(C.Structure):
         ("rms_out", _vp),
         ("numel", _i64), ("rng_base", _i64), ("scratch_offset", _i64),
         ("batch", _i32), ("rows", _i32), ("cols", _i32), ("p_dtype", _i32), ("flags", _i32),
-        ("beta1", _f32), ("beta2", _f32), ("beta3", _f32), ("eps0", _f32), ("eps1", _f32), ("clip_threshold", _f32),
+        ("beta1", _f32), ("beta2", _f32), ("beta3", _f32), ("one_minus_beta1", _f32), ("one_minus_beta2", _f32), ("one_minus_beta3", _f32),
+        ("eps0", _f32), ("eps1", _f32), ("clip_threshold", _f32),
         ("lr", _f32), ("weight_decay", _f32),
     ]
 

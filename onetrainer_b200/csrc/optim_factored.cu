@@ -50,9 +50,8 @@ struct Dims { int batch, rows, cols; int64_t numel; };
 // row / column means of f(i) over every [rows, cols] matrix of the tensor, folded into the running factors:
 //   row[b, r] = row * beta + (1 - beta) * mean_c f ,  col[b, c] = col * beta + (1 - beta) * mean_r f
 template <typename F>
-__device__ void factor_update(const Dims d, float* row, float* col, float beta, F f) {
+__device__ void factor_update(const Dims d, float* row, float* col, float beta, float omb, F f) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float omb = 1.0f - beta;
     const int64_t total_rows = (int64_t)d.batch * d.rows;
     for (int64_t br = warp; br < total_rows; br += FO_WARPS) {                 // one warp per row: coalesced, shuffle reduce
         const int64_t base = br * d.cols;
@@ -130,9 +129,9 @@ adafactor_multi_kernel(const otb_factored_tensor* __restrict__ tensors, float* _
     }
     auto g2 = [&](int64_t i) { const float g = ldf(t.g, i, pdt); return __fmaf_rn(g, g, t.eps0); };
     if (factored) {
-        factor_update(d, t.sq_row, t.sq_col, t.beta2, g2);
+        factor_update(d, t.sq_row, t.sq_col, t.beta2, t.one_minus_beta2, g2);
     } else {
-        const float omb = 1.0f - t.beta2;
+        const float omb = t.one_minus_beta2;
         for (int64_t i = threadIdx.x; i < d.numel; i += FO_THREADS) t.sq[i] = __fmaf_rn(omb, g2(i), __fmul_rn(t.sq[i], t.beta2));
     }
     __syncthreads();
@@ -153,7 +152,7 @@ adafactor_multi_kernel(const otb_factored_tensor* __restrict__ tensors, float* _
     for (int64_t i = threadIdx.x; i < d.numel; i += FO_THREADS) {
         float u = upd(i) / denom * lr_t;
         if (first) {
-            const float m = __fmaf_rn(1.0f - t.beta1, u, __fmul_rn(t.exp_avg[i], t.beta1));
+            const float m = __fmaf_rn(t.one_minus_beta1, u, __fmul_rn(t.exp_avg[i], t.beta1));
             t.exp_avg[i] = m;
             u = m;
         }
@@ -184,9 +183,9 @@ came_multi_kernel(const otb_factored_tensor* __restrict__ tensors, float* __rest
     // ---- A: second moment
     auto g2 = [&](int64_t i) { const float g = ldf(t.g, i, pdt); return __fmaf_rn(g, g, t.eps0); };
     if (factored) {
-        factor_update(d, t.sq_row, t.sq_col, t.beta2, g2);
+        factor_update(d, t.sq_row, t.sq_col, t.beta2, t.one_minus_beta2, g2);
     } else {
-        const float omb = 1.0f - t.beta2;
+        const float omb = t.one_minus_beta2;
         for (int64_t i = threadIdx.x; i < d.numel; i += FO_THREADS) t.sq[i] = __fmaf_rn(omb, g2(i), __fmul_rn(t.sq[i], t.beta2));
     }
     __syncthreads();
@@ -204,11 +203,11 @@ came_multi_kernel(const otb_factored_tensor* __restrict__ tensors, float* __rest
     const float denom = sh[0];
     // ---- C: first moment; instability factors from (u-hat - m)^2 + eps1
     for (int64_t i = threadIdx.x; i < d.numel; i += FO_THREADS)
-        t.exp_avg[i] = __fmaf_rn(1.0f - t.beta1, upd(i) / denom, __fmul_rn(t.exp_avg[i], t.beta1));
+        t.exp_avg[i] = __fmaf_rn(t.one_minus_beta1, upd(i) / denom, __fmul_rn(t.exp_avg[i], t.beta1));
     __syncthreads();
     if (factored) {
         auto res = [&](int64_t i) { const float e = upd(i) / denom - t.exp_avg[i]; return __fmaf_rn(e, e, t.eps1); };
-        factor_update(d, t.res_row, t.res_col, t.beta3, res);
+        factor_update(d, t.res_row, t.res_col, t.beta3, t.one_minus_beta3, res);
         __syncthreads();
         row_means(d, t.res_row, scratch, red);
     }

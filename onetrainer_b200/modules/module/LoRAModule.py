@@ -661,7 +661,8 @@ class _DoraFn(torch.autograd.Function):
         om = mod.orig_module
         w2 = om.weight.detach().reshape(om.weight.shape[0], -1)
         A2, B2 = a_param.detach().reshape(a_param.shape[0], -1).float(), b_param.detach().reshape(b_param.shape[0], -1).float()
-        ba = B2 @ A2
+        with torch.autocast("cuda", enabled=False):       # weight space stays fp32, as the reference builds WP in A's dtype
+            ba = B2 @ A2
         gsz = 1 if isinstance(om, nn.Linear) else om.kernel_size[0] * om.kernel_size[1]
         eps = torch.finfo(torch.float32).eps if mod.norm_epsilon else 0.0
         wp, wpt, norm = ops.dora_compose(w2.contiguous(), ba, m_param, mod._scale(), eps=eps, group_size=gsz, out_axis=mod.decompose_output_axis,
@@ -688,12 +689,13 @@ class _DoraFn(torch.autograd.Function):
             A2, B2 = A.detach().reshape(A.shape[0], -1).float(), B.detach().reshape(B.shape[0], -1).float()
             w2 = om.weight.detach().reshape(om.weight.shape[0], -1).contiguous()
             G = dy.t() @ x2                                           # dL/dWP, bf16 as the reference's autocast GEMM leaves it
-            dV, dmf = ops.dora_backward(G.contiguous(), w2, B2 @ A2, m, norm, mod._scale(), group_size=ctx.gsz, out_axis=mod.decompose_output_axis)
             s = mod._scale()
-            if ctx.needs_input_grad[1]:
-                dA = ((B2.t() @ dV) * s).reshape(A.shape).to(A.dtype)
-            if ctx.needs_input_grad[2]:
-                dB = ((dV @ A2.t()) * s).reshape(B.shape).to(B.dtype)
+            with torch.autocast("cuda", enabled=False):
+                dV, dmf = ops.dora_backward(G.contiguous(), w2, B2 @ A2, m, norm, s, group_size=ctx.gsz, out_axis=mod.decompose_output_axis)
+                if ctx.needs_input_grad[1]:
+                    dA = ((B2.t() @ dV) * s).reshape(A.shape).to(A.dtype)
+                if ctx.needs_input_grad[2]:
+                    dB = ((dV @ A2.t()) * s).reshape(B.shape).to(B.dtype)
             if ctx.needs_input_grad[3]:
                 dm = dmf.reshape(m.shape).to(m.dtype)
         return dx, dA, dB, dm, None

@@ -128,12 +128,14 @@ class FactoredDriver:
                     flags |= N.FACTORED_FIRST_MOMENT
                 if group["scale_parameter"]:
                     flags |= N.FACTORED_SCALE_PARAMETER
-                h["beta1"] = group["beta1"] if group["beta1"] is not None else 0.0
-                h["beta2"] = 1.0 - math.pow(step, group["decay_rate"])
+                b1 = group["beta1"] if group["beta1"] is not None else 0.0
+                b2 = 1.0 - math.pow(step, group["decay_rate"])                 # beta2t
+                h["beta1"], h["beta2"], h["one_minus_beta1"], h["one_minus_beta2"] = b1, b2, 1.0 - b1, 1.0 - b2
                 h["lr"] = step_size
             else:
                 flags |= N.FACTORED_FIRST_MOMENT | (N.FACTORED_SR if sr else 0)
                 h["beta1"], h["beta2"], h["beta3"] = group["betas"]
+                h["one_minus_beta1"], h["one_minus_beta2"], h["one_minus_beta3"] = (1.0 - b for b in group["betas"])     # in double, as python does
                 h["lr"] = group["lr"]
             h["eps0"], h["eps1"] = group["eps"]
             h["clip_threshold"], h["weight_decay"], h["flags"] = group["clip_threshold"], group["weight_decay"], flags

@@ -145,7 +145,7 @@ def test_factored_optimizers_multi_tensor_equals_per_tensor_and_is_reproducible(
         col = NamedParameterGroupCollection()
         w = torch.nn.Parameter(torch.randn(8, 16, device=dev) * 0.05)
         col.add_group(NamedParameterGroup("unet_lora", [w], None))
-        cfg = TrainConfig(train_device=str(dev), learning_rate=1e-4, optimizer=TrainOptimizerConfig(optimizer=which))
+        cfg = TrainConfig(train_device=str(dev), learning_rate=1e-4, optimizer=TrainOptimizerConfig(optimizer=which, relative_step=True))
         opt = create.create_optimizer(col, None, cfg)
         assert type(opt).__name__ == cls_name
         before = w.detach().clone()

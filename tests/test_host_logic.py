@@ -357,3 +357,48 @@ def test_create_optimizer_and_ema_keep_the_reference_contract():
     assert model.param_group_mapping == ["unet_lora", "te_lora"] and model.optimizer_state_dict is None and model.ema_state_dict is None
     assert isinstance(model.optimizer, torch.optim.AdamW) and isinstance(model.ema, EMAModuleWrapper)
     assert len(model.parameters.parameters()) == 3
+
+
+# ------------------------------------------------------------------------------------------ f4: on-disk LoRA key formats
+def test_lora_saver_key_formats_round_trip(tmp_path):
+    """LoRASaverMixin._save (modelSaver/mixin/LoRASaverMixin.py:38-106): legacy diffusers keys (adapter prefix + '_' + the
+    module path with '.' -> '_'), dtype conversion, the INTERNAL layout, and loading a legacy file back into a wrapper."""
+    from safetensors import safe_open
+    from safetensors.torch import load_file
+    from onetrainer_b200.modules.modelSaver.mixin.LoRASaverMixin import (ModelFormat, StandInLoRASaver, convert_legacy_diffusers_to_internal,
+                                                                        convert_to_legacy_diffusers, sdxl_lora_key_sets)
+    net = _net()
+    wrap = LoRAModuleWrapper(net, "lora_unet", TrainConfig(lora_rank=8), ["to_q", "to_out"])
+    for m in wrap.lora_modules.values():
+        nn.init.normal_(m.lora_up.weight, std=0.02)
+
+    class Model:
+        unet_lora, sdxl = wrap, True
+        lora_state_dict = {"bundle_emb.<tok>.clip_l": torch.ones(2, 4)}
+
+    sd = wrap.state_dict()
+    legacy = convert_to_legacy_diffusers(sd, sdxl_lora_key_sets())
+    k_internal = next(k for k in sd if k.endswith("to_q.lora_down.weight"))
+    k_legacy = "lora_unet_" + k_internal[len("lora_unet."):-len(".lora_down.weight")].replace(".", "_") + ".lora_down.weight"
+    assert k_legacy in legacy and "." not in k_legacy[: -len(".lora_down.weight")] and len(legacy) == len(sd)
+    saver = StandInLoRASaver()
+    dst = tmp_path / "out" / "lora.safetensors"
+    saver.save(Model, ModelFormat.SAFETENSORS, str(dst), torch.bfloat16)
+    loaded = load_file(str(dst))
+    assert set(loaded) == set(legacy) | {"bundle_emb.<tok>.clip_l"} and all(v.dtype == torch.bfloat16 for v in loaded.values())
+    with safe_open(str(dst), "pt") as f:
+        assert f.metadata()["ss_base_model_version"] == "sdxl_"
+    saver.save(Model, ModelFormat.LEGACY_SAFETENSORS, str(tmp_path / "legacy.safetensors"), None)
+    assert set(load_file(str(tmp_path / "legacy.safetensors"))) == set(loaded)
+    saver.save(Model, ModelFormat.INTERNAL, str(tmp_path / "backup"), None)
+    internal = load_file(str(tmp_path / "backup" / "lora" / "lora.safetensors"))
+    assert set(internal) == set(sd) | {"bundle_emb.<tok>.clip_l"} and internal[k_internal].dtype == torch.float32
+    with pytest.raises(NotImplementedError):
+        saver.save(Model, ModelFormat.DIFFUSERS, str(tmp_path / "x"), None)
+    with pytest.raises(NotImplementedError, match="omi_model_standards"):
+        saver._save(Model, ModelFormat.SAFETENSORS, str(tmp_path / "omi.safetensors"), None, enable_omi_format=True)
+    # load the legacy file into a fresh wrapper
+    w2 = LoRAModuleWrapper(_net(), "lora_unet", TrainConfig(lora_rank=8), ["to_q", "to_out"])
+    back = convert_legacy_diffusers_to_internal({k: v.float() for k, v in loaded.items()}, w2.state_dict().keys())
+    w2.load_state_dict(back)
+    assert torch.equal(w2.state_dict()[k_internal], sd[k_internal].detach().bfloat16().float())
