@@ -1,5 +1,5 @@
 """Launch one kernel a few times at its roofline size — the target of `ncu --set full`.
-usage: python tools/kprof.py {kc_bf16|kc_fp32|kb1|kb2|ka|kgrad} [iters]"""
+usage: python tools/kprof.py {kc_bf16|kc_fp32|kb1|kb2|ka|ka1280|kaqkv|kgrad|kgradb|adafactor|came|dora} [iters]"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -67,3 +67,53 @@ elif which == "kgrad":
     dA = torch.zeros(R, K, device=dev); dB = torch.zeros(Nn, R, device=dev)
     ms = timed(lambda: ops.lora_grad_ab(x, dy, gs, ts_, dA, dB))
     print(f"kgrad: {ms * 1e3:.1f} us")
+elif which == "ka1280":
+    # the most frequent SDXL leaf: one round of 64 pair tiles
+    M, Nn, K, R = 4096, 1280, 1280, 32
+    x = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(Nn, K, device=dev) / 36).bfloat16()
+    down = (torch.randn(R, K, device=dev) / 36).bfloat16(); up = torch.randn(Nn, R, device=dev).bfloat16()
+    bias = torch.randn(Nn, device=dev).bfloat16()
+    ms = timed(lambda: ops.lora_linear(x, w, down, up, bias, 1 / 32))
+    print(f"ka1280: {ms * 1e3:.1f} us, {(2.0 * M * Nn * K + 2.0 * M * R * (K + Nn)) / ms / 1e9:.1f} TFLOP/s")
+elif which == "kaqkv":
+    M, Nn, K, R = 4096, 1280, 1280, 32
+    x = torch.randn(M, K, device=dev).bfloat16()
+    ws = [(torch.randn(Nn, K, device=dev) / 36).bfloat16() for _ in range(3)]
+    dn = [(torch.randn(R, K, device=dev) / 36).bfloat16() for _ in range(3)]
+    up = [torch.randn(Nn, R, device=dev).bfloat16() for _ in range(3)]
+    ms = timed(lambda: ops.lora_linear_grouped([x] * 3, ws, dn, up, [None] * 3, [1 / 32] * 3))
+    print(f"kaqkv: {ms * 1e3:.1f} us, {3 * (2.0 * M * Nn * K + 2.0 * M * R * (K + Nn)) / ms / 1e9:.1f} TFLOP/s")
+elif which == "kgradb":
+    # one batched launch: 32 leaves of the c1280 shape, each with its own operands (690 MB streamed)
+    M, Nn, K, R = 4096, 1280, 1280, 32
+    leaves = []
+    for i in range(32):
+        leaves.append((torch.randn(M, K, device=dev).bfloat16(), torch.randn(M, Nn, device=dev).bfloat16(), torch.randn(M, R, device=dev).bfloat16(),
+                       torch.randn(M, R, device=dev).bfloat16(), torch.zeros(R, K, device=dev), torch.zeros(Nn, R, device=dev)))
+    ms = timed(lambda: ops.lora_grad_batched(leaves))
+    byts = 32 * (2.0 * M * (K + Nn) + 4.0 * M * R + 8.0 * R * (K + Nn))
+    print(f"kgradb: {ms * 1e3:.1f} us for 32 leaves, {byts / ms / 1e6:.0f} GB/s")
+elif which in ("adafactor", "came"):
+    # 64 matrices of 2048 x 2048 fp32 (268 M elements) through the reference-facing optimizer classes
+    ps = [torch.nn.Parameter(torch.randn(2048, 2048, device=dev) * 0.02) for _ in range(64)]
+    for p in ps:
+        p.grad = torch.randn_like(p) * 1e-3
+    if which == "adafactor":
+        from transformers.optimization import Adafactor
+        from onetrainer_b200.modules.util.optimizer.adafactor_extensions import patch_adafactor
+        opt = Adafactor(ps, lr=1e-4, relative_step=False, scale_parameter=False, warmup_init=False)
+        patch_adafactor(opt, False)
+        bpe = 4 + 4 + 4 + 4           # two passes over g (4+4), p read + write (4+4); factors are O(rows + cols)
+    else:
+        from onetrainer_b200.modules.util.optimizer.CAME import CAME
+        opt = CAME(ps, lr=1e-4)
+        bpe = 4 + 4 + 4 + 4 + 8       # + exp_avg read + write
+    ms = timed(lambda: opt.step())
+    n = sum(p.numel() for p in ps)
+    print(f"{which}: {ms:.3f} ms for {n} fp32 elements, {n * bpe / ms / 1e6:.0f} GB/s at {bpe} B/element (host launch included)")
+elif which == "dora":
+    Nn, J = 10240, 1280
+    w2 = (torch.randn(Nn, J, device=dev) / 36).bfloat16(); ba = torch.randn(Nn, J, device=dev) * 1e-3
+    m = torch.ones(J, device=dev)
+    ms = timed(lambda: ops.dora_compose(w2, ba, m, 1 / 32))
+    print(f"dora_compose: {ms * 1e3:.1f} us, {Nn * J * (2 + 4 + 2 + 2 + 6) / ms / 1e6:.0f} GB/s (two passes over w/ba, two bf16 outputs)")
