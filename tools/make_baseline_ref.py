@@ -32,15 +32,21 @@ ENTRY = [
     "modules.util.NamedParameterGroup", "modules.util.config.TrainConfig",
     "modules.util.convert.rescale_noise_scheduler_to_zero_terminal_snr",
 ]
+# the family callers of SURVEY.md §8 row A16 (predict / calculate_loss of the three Base*Setup classes), run unmodified by
+# baseline/ref_callers.py with a placeholder `diffusers` package
+CALLERS = ["modules.modelSetup.BaseStableDiffusionSetup", "modules.modelSetup.BaseStableDiffusionXLSetup", "modules.modelSetup.BaseFluxSetup"]
 
 
 def closure() -> list[Path]:
     sys.path.insert(0, str(REPO))
-    from baseline import ref_arm
+    from baseline import ref_arm, ref_callers
     ref_arm.install_shims()
     sys.path.insert(0, str(REF))
     import importlib
     for name in ENTRY:
+        importlib.import_module(name)
+    ref_callers.install_caller_shims()
+    for name in CALLERS:
         importlib.import_module(name)
     files = set()
     for mod in list(sys.modules.values()):
