@@ -31,8 +31,9 @@
 extern "C" {
 #endif
 
-#define OTB_ABI_VERSION 4   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs.  3: otb_grad_exchange, otb_grad_norm_from_partials.
-                               4: OTB_TS_TABLE (ts_cdf / ts_cdf_len appended to otb_noise_args); otb_lora_grad_batched; otb_lora_linear_grouped takes up to 32 members; otb_lora_linear_args.flags; otb_adafactor_multi / otb_came_multi; otb_dora_compose / otb_dora_backward */
+#define OTB_ABI_VERSION 5   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs.  3: otb_grad_exchange, otb_grad_norm_from_partials.
+                               4: OTB_TS_TABLE (ts_cdf / ts_cdf_len appended to otb_noise_args); otb_lora_grad_batched; otb_lora_linear_grouped takes up to 32 members; otb_lora_linear_args.flags; otb_adafactor_multi / otb_came_multi; otb_dora_compose / otb_dora_backward.
+                               5: otb_shard_reduce / otb_shard_gather / otb_peer_barrier / otb_peer_signal / otb_peer_wait (K-z) */
 
 /* error codes */
 #define OTB_OK            0
@@ -272,6 +273,48 @@ typedef struct otb_grad_exchange_args {
 } otb_grad_exchange_args;
 int otb_grad_exchange_blocks(int64_t n_elems, int32_t world);
 int otb_grad_exchange(const otb_grad_exchange_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K-z  the SHARDED form of the exchange for full fine-tuning (SURVEY.md §8f rank 3:
+ *      "optimizer-in-backward mode ... with bucketed reduce-scatter"; hook point
+ *      GenericTrainer.py:531-558, optimizer adamw_extensions.py:17-150, EMA EMAModule.py:37-54):
+ *      reduce-scatter -> K-c on the owner's tensors only -> all-gather of the updated
+ *      parameters, all over NVLink peer memory, no NCCL.
+ * The flat gradient arena AND the flat parameter arena are symmetric memory.  A contiguous,
+ * tensor-aligned element range [begin, end) has one owner rank.
+ *   otb_shard_reduce  (owner only) sums the range over every replica — P2P: one 16-byte load
+ *       per peer, added in rank order in fp32; NVLS: multimem.ld_reduce (.acc::f32 for bf16) —
+ *       rounds once, keeps the sum in the OWNER's replica and writes the block partials of
+ *       (grad_prescale * sum)^2 into float[partial_slot + block] of EVERY rank's partial table
+ *       (all tables complete after the following barrier -> otb_grad_norm_from_partials);
+ *   otb_shard_gather  (owner only) copies the range of the owner's replica into every
+ *       replica (P2P stores / one multimem.st stream);
+ *   otb_peer_barrier  all ranks: flag-word barrier, `phase` in [0, OTB_PEER_PHASES) selects the
+ *       word set (uint32[OTB_PEER_PHASES * OTB_MAX_RANKS] per rank, zero-initialised);
+ *   otb_peer_signal / otb_peer_wait  one-directional: a non-owner raises its word in the
+ *       owner's table ("my backward has produced this range"), the owner consumes one word per
+ *       peer — lets the reduce of a bucket overlap the rest of backward.
+ * Bounded spins (trap after ~60 s).  Capturable in a CUDA graph; no host sync.
+ * ---------------------------------------------------------------------------------- */
+#define OTB_PEER_PHASES 4
+typedef struct otb_shard_exchange_args {
+    void*     peer_base[OTB_MAX_RANKS];     /* the arena of rank i as mapped into THIS process       */
+    float*    peer_partials[OTB_MAX_RANKS]; /* partial table of rank i, likewise (reduce, P2P mode)  */
+    void*     mc_base;                      /* NVLS only: multicast address of the arena             */
+    float*    mc_partials;                  /* NVLS only: multicast address of the partial table     */
+    int64_t   begin, end;                   /* element range, whole 16-byte vectors                  */
+    int32_t   dtype;                        /* OTB_BF16 | OTB_F32                                    */
+    int32_t   rank, world;
+    int32_t   mode;                         /* OTB_EXCHANGE_*                                        */
+    int32_t   blocks;                       /* grid size; the launch writes `blocks` partials        */
+    int32_t   partial_slot;                 /* first index of this launch's partials in the table    */
+    float     grad_prescale;                /* folded into the norm only; the arena holds the SUM    */
+} otb_shard_exchange_args;
+int otb_shard_reduce(const otb_shard_exchange_args* args, void* stream);
+int otb_shard_gather(const otb_shard_exchange_args* args, void* stream);
+int otb_peer_barrier(uint32_t* const* peer_flags, int32_t rank, int32_t world, int32_t phase, void* stream);
+int otb_peer_signal(uint32_t* owner_word, void* stream);
+int otb_peer_wait(uint32_t* my_words, int32_t rank, int32_t world, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * bf16 shadow refresh: for every LoRA tensor (fp32 or bf16 master, [rows, cols])

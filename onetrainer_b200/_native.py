@@ -12,7 +12,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "libotb200.so"
 
 # ---- enums (include/otb200.h) ---------------------------------------------------------
-ABI_VERSION = 4          # include/otb200.h: OTB_ABI_VERSION
+ABI_VERSION = 5          # include/otb200.h: OTB_ABI_VERSION
 OTB_OK, OTB_EINVAL, OTB_EUNSUPPORTED, OTB_ECUDA, OTB_EARCH = 0, -1, -2, -3, -4
 F32, BF16, F16 = 0, 1, 2
 
@@ -163,6 +163,15 @@ class GradExchangeArgs(C.Structure):
 
 
 EXCHANGE_P2P, EXCHANGE_NVLS = 0, 1
+PEER_PHASES = 4          # include/otb200.h: OTB_PEER_PHASES
+
+
+class ShardExchangeArgs(C.Structure):
+    _fields_ = [
+        ("peer_base", _vp * MAX_RANKS), ("peer_partials", _vp * MAX_RANKS), ("mc_base", _vp), ("mc_partials", _vp),
+        ("begin", _i64), ("end", _i64), ("dtype", _i32), ("rank", _i32), ("world", _i32), ("mode", _i32), ("blocks", _i32),
+        ("partial_slot", _i32), ("grad_prescale", _f32),
+    ]
 
 
 # every symbol include/otb200.h declares: (name, restype, argtypes)
@@ -177,6 +186,11 @@ SYMBOLS = {
     "otb_grad_scale_multi": (C.c_int, [C.POINTER(OptimLaunch), _vp, _vp]),
     "otb_grad_exchange_blocks": (C.c_int, [_i64, _i32]),
     "otb_grad_exchange": (C.c_int, [C.POINTER(GradExchangeArgs), _vp]),
+    "otb_shard_reduce": (C.c_int, [C.POINTER(ShardExchangeArgs), _vp]),
+    "otb_shard_gather": (C.c_int, [C.POINTER(ShardExchangeArgs), _vp]),
+    "otb_peer_barrier": (C.c_int, [C.POINTER(_vp), _i32, _i32, _i32, _vp]),
+    "otb_peer_signal": (C.c_int, [_vp, _vp]),
+    "otb_peer_wait": (C.c_int, [_vp, _i32, _i32, _vp]),
     "otb_shadow_refresh_multi": (C.c_int, [_vp, _i32, _i32, _vp]),
     "otb_noise_addnoise": (C.c_int, [C.POINTER(NoiseArgs), _vp]),
     "otb_loss_fwd_bwd": (C.c_int, [C.POINTER(LossArgs), _vp]),
@@ -195,7 +209,7 @@ SYMBOLS = {
     "otb_struct_sizes": (C.c_int, [C.POINTER(C.c_int32)]),
 }
 _STRUCTS = (OptimTensor, OptimLaunch, ShadowTensor, NoiseArgs, LossArgs, LoraLinearArgs, LoraGradArgs, GradExchangeArgs,
-            FactoredTensor, FactoredLaunch, DoraArgs)
+            FactoredTensor, FactoredLaunch, DoraArgs, ShardExchangeArgs)
 
 _lib = None
 

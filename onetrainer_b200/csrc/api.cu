@@ -113,6 +113,7 @@ extern "C" int otb_struct_sizes(int32_t* out) {
     out[8] = (int32_t)sizeof(otb_factored_tensor);
     out[9] = (int32_t)sizeof(otb_factored_launch);
     out[10] = (int32_t)sizeof(otb_dora_args);
+    out[11] = (int32_t)sizeof(otb_shard_exchange_args);
     return OTB_OK;
 }
 

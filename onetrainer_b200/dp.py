@@ -110,6 +110,13 @@ def peer_exchange_wanted() -> bool:
     return world_size() > 1 and torch.cuda.is_available() and os.environ.get("OTB_PEER_EXCHANGE", "1") != "0"
 
 
+def sharded_optimizer_wanted() -> bool:
+    """Full fine-tuning under data parallelism: reduce-scatter -> sharded AdamW/EMA -> all-gather with this repo's own
+    kernels (ShardedExchange) instead of the bucketed ncclAllReduce + replicated optimizer.  OTB_SHARDED_OPT=0 keeps the
+    replicated form (A/B runs)."""
+    return world_size() > 1 and torch.cuda.is_available() and os.environ.get("OTB_SHARDED_OPT", "1") != "0"
+
+
 def symmetric_zeros(numel: int, dtype: torch.dtype, device) -> torch.Tensor:
     """A zero-filled flat buffer from torch's symmetric-memory allocator: the same allocation exists on every rank and,
     after the rendezvous, is peer-mapped (NVLink loads/stores) and mapped as one NVLS multicast object.  Every rank
@@ -305,6 +312,244 @@ class OverlappedArenaReducer:
             torch.cuda.current_stream(self.arena.flat.device).wait_stream(self._comm)
         self._armed = False
         return 1.0 / n
+
+
+class ShardedExchange:
+    """K-z, host side: reduce-scatter -> sharded optimizer -> all-gather for full fine-tuning (config C4; SURVEY.md §8f
+    rank 3), over NVLink peer memory with this repo's own kernels (include/otb200.h: otb_shard_reduce / otb_shard_gather).
+
+    Construction (collective, outside any graph capture) re-homes the parameters AND their gradients into two flat
+    symmetric-memory arenas (same offsets in both), cuts them into contiguous tensor-aligned buckets, and gives bucket b
+    to rank b % world.  Per step:
+
+        arm()                 before backward
+        [hooks]               when a bucket's last gradient lands: non-owners signal the owner, the owner waits for every
+                              peer and reduces the bucket on a communication stream while backward goes on (overlap=True)
+        finish() -> 1/n       joins; after it every rank holds the complete table of squared-norm partials
+                              (`norm_partials`) and the owner's replica holds the summed gradients of its buckets
+        optimizer.step()      an optimizer built over `owned_parameters()` only: 1/n of the state, EMA and HBM traffic
+        gather()              the owners push their updated parameter ranges into every replica; barrier
+
+    Same interface as OverlappedArenaReducer (arm / finish), so the trainer treats both alike.  The stochastic-rounding
+    stream stays keyed by the GLOBAL element offset (`rng_base_of`), so the sharded update is bit-identical to the
+    replicated one given the same summed gradients."""
+
+    def __init__(self, parameters: list[torch.Tensor], n_buckets: int | None = None, group=None, mode: str | None = None,
+                 overlap: bool | None = None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _native as N
+        if not parameters:
+            raise ValueError("ShardedExchange: empty parameter list")
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("ShardedExchange: the rendezvous cannot be captured")
+        dt, dev = parameters[0].dtype, parameters[0].device
+        if any(p.dtype != dt or p.device != dev for p in parameters) or dt not in (torch.bfloat16, torch.float32):
+            raise ValueError("ShardedExchange: parameters must share one device and one dtype (bf16 or fp32)")
+        group = group if group is not None else dist.group.WORLD
+        rk, ws = dist.get_rank(group), dist.get_world_size(group)
+        if not 2 <= ws <= N.MAX_RANKS:
+            raise ValueError(f"ShardedExchange: world size {ws} outside 2..{N.MAX_RANKS}")
+        mode = mode or os.environ.get("OTB_KZ_MODE") or ("p2p" if ws == 2 else "nvls")
+        if mode == "p2p" and ws not in (2, 4, 8):
+            mode = "nvls"
+        self.mode, self.rank, self.world = mode, rk, ws
+        self.overlap = (os.environ.get("OTB_KZ_OVERLAP", "1") != "0") if overlap is None else overlap
+        self.parameters = list(parameters)
+        offsets, total, bounds, first_param = self.plan([p.numel() for p in parameters], ws, n_buckets)
+        self.param_flat = symmetric_zeros(total, dt, dev)
+        self.grad_flat = symmetric_zeros(total, dt, dev)
+        with torch.no_grad():
+            for p, off in zip(parameters, offsets):
+                view = self.param_flat[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.grad_flat[off:off + p.numel()].view(p.shape)
+        self.flat = self.grad_flat                      # FlatGradArena's interface (zero(), grads())
+        self.offsets = offsets
+        self.rng_base_of = {id(p): off for p, off in zip(parameters, offsets)}     # 8-aligned (align >= 4; bf16: 8)
+        self.bounds = bounds
+        self.n_buckets = len(bounds) - 1
+        self.owner = [b % ws for b in range(self.n_buckets)]
+        self._bucket_of = {}
+        self._counts = []
+        for b in range(self.n_buckets):
+            for i in range(first_param[b], first_param[b + 1]):
+                self._bucket_of[id(parameters[i])] = b
+            self._counts.append(first_param[b + 1] - first_param[b])
+        self._owned = [p for p in parameters if self.owner[self._bucket_of[id(p)]] == rk]
+        self.blocks = min(4096, max(1, int(os.environ.get("OTB_KZ_BLOCKS", str(2 * torch.cuda.get_device_properties(dev).multi_processor_count)))))
+        self.partials = symmetric_zeros(self.n_buckets * self.blocks, torch.float32, dev)
+        self.flags = symmetric_zeros(N.PEER_PHASES * N.MAX_RANKS, torch.int32, dev)              # barriers
+        self.ready = symmetric_zeros(self.n_buckets * N.MAX_RANKS, torch.int32, dev)             # per-bucket "produced" words
+        tensors = (self.grad_flat, self.param_flat, self.partials, self.flags, self.ready)
+        handles = [symm.rendezvous(t, group) for t in tensors]
+        self._handles = handles
+
+        def peers(t, h):
+            arr = (C.c_void_p * N.MAX_RANKS)()
+            for r in range(ws):
+                arr[r] = h.buffer_ptrs[r] + (t.data_ptr() - h.buffer_ptrs[rk])
+            return arr
+
+        def multicast(t, h):
+            if mode != "nvls":
+                return None
+            if not h.multicast_ptr:
+                raise RuntimeError("ShardedExchange: no NVLS multicast mapping on this node; use OTB_KZ_MODE=p2p")
+            return h.multicast_ptr + (t.data_ptr() - h.buffer_ptrs[rk])
+
+        common = dict(dtype=N.dtype_code(dt), rank=rk, world=ws, mode=N.EXCHANGE_NVLS if mode == "nvls" else N.EXCHANGE_P2P,
+                      blocks=self.blocks, grad_prescale=1.0 / ws)
+        self._reduce_args = N.ShardExchangeArgs(peer_base=peers(self.grad_flat, handles[0]), peer_partials=peers(self.partials, handles[2]),
+                                                mc_base=multicast(self.grad_flat, handles[0]), mc_partials=multicast(self.partials, handles[2]),
+                                                **common)
+        self._gather_args = N.ShardExchangeArgs(peer_base=peers(self.param_flat, handles[1]), peer_partials=(C.c_void_p * N.MAX_RANKS)(),
+                                                mc_base=multicast(self.param_flat, handles[1]), mc_partials=None, **common)
+        self._flag_ptrs = peers(self.flags, handles[3])
+        self._ready_ptrs = peers(self.ready, handles[4])
+        self._my_ready = self.ready.data_ptr()
+        self.norm_partials = self.partials
+        self._left = list(self._counts)
+        self._armed = False
+        self._comm = None
+        self._reduced = [False] * self.n_buckets
+        for p in parameters:
+            p.register_post_accumulate_grad_hook(self._on_grad)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)
+
+    @staticmethod
+    def plan(numels: list[int], world: int, n_buckets: int | None = None):
+        """Arena layout and bucket cut for a parameter list (pure host logic).  Every tensor starts on an 8-element
+        boundary (16-byte vectors for bf16; the 8-element groups of the SR Philox stream, so offsets equal the replicated
+        optimizer table's `rng_base`).  Buckets are contiguous, tensor-aligned, about total / n_buckets elements each, a
+        multiple of the world size of them where the tensor count allows; bucket b belongs to rank b % world.
+        Returns (offsets, total, bounds, first_param): bucket b covers elements [bounds[b], bounds[b+1]) = parameters
+        [first_param[b], first_param[b+1])."""
+        align = 8
+        offsets, total = [], 0
+        for n in numels:
+            offsets.append(total)
+            total += (n + align - 1) // align * align
+        if n_buckets is None:
+            n_buckets = int(os.environ.get("OTB_KZ_BUCKETS", str(3 * world if world > 2 else 8)))
+        n_buckets = max(world, (n_buckets + world - 1) // world * world)
+        if len(numels) >= world:
+            n_buckets = min(n_buckets, max(world, len(numels) // world * world))
+        target = max(1, total // n_buckets)
+        bounds, first_param = [0], [0]
+        for i, off in enumerate(offsets):
+            if off - bounds[-1] >= target and len(bounds) < n_buckets and i > first_param[-1]:
+                bounds.append(off)
+                first_param.append(i)
+        bounds.append(total)
+        first_param.append(len(numels))
+        return offsets, total, bounds, first_param
+
+    # FlatGradArena's interface -----------------------------------------------------------------------------------------
+    def zero(self) -> None:
+        self.grad_flat.zero_()
+
+    def grads(self) -> list[torch.Tensor]:
+        return [p.grad for p in self.parameters]
+
+    def owned_parameters(self) -> list[torch.Tensor]:
+        return list(self._owned)
+
+    def owned_elements(self) -> int:
+        return sum(self.bounds[b + 1] - self.bounds[b] for b in range(self.n_buckets) if self.owner[b] == self.rank)
+
+    # the step ----------------------------------------------------------------------------------------------------------
+    def arm(self, last_micro_step: bool = True) -> None:
+        self._left = list(self._counts)
+        self._reduced = [False] * self.n_buckets
+        self._armed = last_micro_step
+
+    def _on_grad(self, p: torch.Tensor) -> None:
+        if not self._armed or not self.overlap:
+            return
+        b = self._bucket_of[id(p)]
+        self._left[b] -= 1
+        if self._left[b] == 0:
+            main = torch.cuda.current_stream(self.grad_flat.device)
+            if self._comm is None:
+                self._comm = torch.cuda.Stream(device=self.grad_flat.device)
+            self._comm.wait_stream(main)                  # the kernels that produced this bucket's gradients
+            with torch.cuda.stream(self._comm):
+                self._handshake_and_reduce(b)
+
+    def _handshake_and_reduce(self, b: int) -> None:
+        """Per-bucket hand-shake (non-owners raise their word in the owner's table; the owner consumes them) and, on the
+        owner, the reduce of the bucket.  Every rank runs this for every bucket in the same order."""
+        import ctypes as C
+        from . import _native as N, ops
+        lib = N.lib()
+        own = self.owner[b]
+        word = b * N.MAX_RANKS
+        if own == self.rank:
+            N.check(lib.otb_peer_wait(self._my_ready + 4 * word, self.rank, self.world, ops._stream()), "otb_peer_wait")
+            self._launch_reduce(b)
+            ops._count(2)
+        else:
+            N.check(lib.otb_peer_signal(self._ready_ptrs[own] + 4 * (word + self.rank), ops._stream()), "otb_peer_signal")
+            ops._count(1)
+        self._reduced[b] = True
+
+    def _launch_reduce(self, b: int) -> None:
+        import ctypes as C
+        from . import _native as N, ops
+        a = self._reduce_args
+        a.begin, a.end, a.partial_slot = self.bounds[b], self.bounds[b + 1], b * self.blocks
+        N.check(N.lib().otb_shard_reduce(C.byref(a), ops._stream()), "otb_shard_reduce")
+
+    def _barrier(self, phase: int) -> None:
+        from . import _native as N, ops
+        N.check(N.lib().otb_peer_barrier(self._flag_ptrs, self.rank, self.world, phase, ops._stream()), "otb_peer_barrier")
+        ops._count(1)
+
+    def finish(self) -> float:
+        """Reduce what the hooks have not reduced, join the communication stream, make every rank's partial table
+        complete.  Returns the prescale (1/world) for the norm / optimizer."""
+        if not self._armed:
+            return 1.0
+        dev = self.grad_flat.device
+        main = torch.cuda.current_stream(dev)
+        if self._comm is not None and self.overlap:
+            main.wait_stream(self._comm)
+        pending = [b for b in range(self.n_buckets) if not self._reduced[b]]
+        if pending:
+            if len(pending) == self.n_buckets:
+                self._barrier(0)                          # nothing overlapped: ONE barrier says every backward is complete
+                for b in pending:
+                    if self.owner[b] == self.rank:
+                        self._launch_reduce(b)
+                        from . import ops
+                        ops._count(1)
+                    self._reduced[b] = True
+            else:
+                for b in pending:                         # parameters without a gradient this step left a bucket open
+                    self._handshake_and_reduce(b)
+        self._barrier(1)                                  # every owner's partials have landed in every table
+        self._armed = False
+        return 1.0 / self.world
+
+    def gather(self) -> None:
+        """After the optimizer step on the owned tensors: push my parameter ranges into every replica."""
+        import ctypes as C
+        from . import _native as N, ops
+        a = self._gather_args
+        for b in range(self.n_buckets):
+            if self.owner[b] == self.rank:
+                a.begin, a.end, a.partial_slot = self.bounds[b], self.bounds[b + 1], 0
+                N.check(N.lib().otb_shard_gather(C.byref(a), ops._stream()), "otb_shard_gather")
+                ops._count(1)
+        self._barrier(2)                                  # every replica is complete before the next forward reads it
+        try:
+            torch.autograd.graph.increment_version(self.parameters)
+        except TypeError:
+            for p in self.parameters:
+                torch.autograd.graph.increment_version(p)
 
 
 def _is_view_of(t: torch.Tensor, base: torch.Tensor) -> bool:

@@ -244,17 +244,27 @@ def build_model(kind: str, config, device, *, train_dtype=torch.bfloat16, lora_w
     if full_finetune:
         unet.requires_grad_(True)
         model.parameters = list(unet.parameters())
-        model.full_grad_arena = dp.FlatGradArena(model.parameters)
-        model.grad_reducer = dp.OverlappedArenaReducer(model.full_grad_arena) if dp.world_size() > 1 else None
-        model.optimizer = torch.optim.AdamW(model.parameters, lr=lr, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+        opt_params = model.parameters
+        if dp.sharded_optimizer_wanted():
+            # K-z: parameters and gradients in symmetric arenas, every bucket owned by one rank, optimizer state and EMA
+            # only for the owner's tensors (reduce-scatter -> sharded K-c -> all-gather)
+            model.full_grad_arena = model.grad_reducer = dp.ShardedExchange(model.parameters)
+            opt_params = model.grad_reducer.owned_parameters()
+        else:
+            model.full_grad_arena = dp.FlatGradArena(model.parameters)
+            model.grad_reducer = dp.OverlappedArenaReducer(model.full_grad_arena) if dp.world_size() > 1 else None
+        model.optimizer_parameters = opt_params
+        model.optimizer = torch.optim.AdamW(opt_params, lr=lr, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
         if ema:
-            model.ema = EMAModuleWrapper(model.parameters, decay=config.ema_decay,
+            model.ema = EMAModuleWrapper(opt_params, decay=config.ema_decay,
                                          update_step_interval=config.ema_update_step_interval, device=torch.device(device))
         progress = model.train_progress
         patch_adamw(model.optimizer, stochastic_rounding,
                     ema=model.ema if (ema and fused_ema) else None,
                     ema_step_fn=(lambda: progress.global_step // config.gradient_accumulation_steps) if (ema and fused_ema) else None,
                     clip_grad_norm=config.clip_grad_norm if fused_clip else None)
+        if isinstance(model.grad_reducer, dp.ShardedExchange):
+            model.optimizer.otb_driver.rng_base_of = model.grad_reducer.rng_base_of
         return model, DiffusionSetup(torch.device(device))
     GradArena.allocator = dp.symmetric_zeros if dp.peer_exchange_wanted() else None    # K-r needs a peer-mapped arena
     model.unet_lora = LoRAModuleWrapper(unet, "lora_unet", config, ["attentions"])
@@ -340,6 +350,7 @@ def train_step(setup: DiffusionSetup, model: StandInModel, batch: dict, config, 
     driver = model.optimizer.otb_driver
     if reducer is not None:
         driver.grad_prescale = reducer.finish()
+        driver.norm_partials = getattr(reducer, "norm_partials", None)     # K-z: the reduce already accumulated the global norm
     elif dp.world_size() > 1:
         arena = model.unet_lora.grad_arena if model.unet_lora is not None else getattr(model, "full_grad_arena", None)
         bucket = bucket or dp.GradientBucket(arena.flat if isinstance(arena, dp.FlatGradArena) else arena)
@@ -349,9 +360,12 @@ def train_step(setup: DiffusionSetup, model: StandInModel, batch: dict, config, 
         from ..modules.util.grad_clip import clip_grad_norm_
         clip_grad_norm_(model.parameters, config.clip_grad_norm, driver.grad_prescale)
     model.optimizer.step()
+    if hasattr(reducer, "gather"):
+        reducer.gather()                                                    # K-z: the owners' updated ranges -> every replica
     _zero_grads(model)
     if model.ema is not None:
-        model.ema.step(model.parameters, model.train_progress.global_step // config.gradient_accumulation_steps)
+        model.ema.step(getattr(model, "optimizer_parameters", None) or model.parameters,
+                       model.train_progress.global_step // config.gradient_accumulation_steps)
     model.train_progress.next_step(config.batch_size)
     return loss.detach()
 
@@ -447,6 +461,7 @@ class GraphedTrainStep:
         loss.backward()
         if reducer is not None:
             self.driver.grad_prescale = reducer.finish()
+            self.driver.norm_partials = getattr(reducer, "norm_partials", None)
         elif dp.world_size() > 1:
             if self.bucket.arena is None:
                 self.bucket.arena = model.unet_lora.grad_arena if model.unet_lora is not None else model.full_grad_arena.flat
@@ -463,6 +478,8 @@ class GraphedTrainStep:
                 raise RuntimeError(f"GraphedTrainStep: {len(moved)} gradient tensors do not live at stable addresses; give the "
                                    "parameters persistent gradients (LoRA: the wrapper's arena; full fine-tuning: dp.FlatGradArena)")
         self.driver.device_step(upload=first)       # captured: the table was uploaded by _host_part()
+        if hasattr(reducer, "gather"):
+            reducer.gather()
         _zero_grads(model)
         self.loss = loss.detach()
 

@@ -57,6 +57,7 @@ class FusedAdamDriver:
         self.grad_prescale = 1.0        # 1/world_size under data parallel
         self.norm_partials = None       # squared-norm partials of ALL active gradients, when the exchange kernel made them
         self.post_step_hooks = []       # e.g. LoRAModuleWrapper.refresh_shadows
+        self.rng_base_of = None         # id(p) -> global element offset in the SR stream (dp.ShardedExchange), else table order
         self.step_count = 0             # SR Philox offset (persisted as state_dict()["otb_sr_step_count"])
         self._sr_seed, self._sr_seed_src = None, None
         self.last_norm_coef: torch.Tensor | None = None
@@ -88,7 +89,7 @@ class FusedAdamDriver:
             if len(st) == 0:
                 _init_state(st, p, group)
             entries.append(dict(p=p.data, g=p.grad, exp_avg=st["exp_avg"], exp_avg_sq=st["exp_avg_sq"],
-                                ema=ema_of.get(id(p))))
+                                ema=ema_of.get(id(p)), rng_base=None if self.rng_base_of is None else self.rng_base_of[id(p)]))
         self._ema_covered = {id(p) for p, _ in active if id(p) in ema_of}
         return entries
 

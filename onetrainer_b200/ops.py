@@ -485,7 +485,9 @@ class OptimTable:
             self.numels.append(n)
             h = self.host[i]
             h["numel"] = n
-            h["rng_base"] = rng_base
+            # position in the stochastic-rounding stream: by default the running offset inside this table; a sharded
+            # optimizer (dp.ShardedExchange) passes the GLOBAL offset so that its bits equal the replicated run's
+            h["rng_base"] = e.get("rng_base", rng_base) if e.get("rng_base") is not None else rng_base
             rng_base += (n + 7) // 8 * 8
             h["p_dtype"] = N.dtype_code(p.dtype)
             nch = (n + chunk_elems - 1) // chunk_elems

@@ -402,3 +402,32 @@ def test_lora_saver_key_formats_round_trip(tmp_path):
     back = convert_legacy_diffusers_to_internal({k: v.float() for k, v in loaded.items()}, w2.state_dict().keys())
     w2.load_state_dict(back)
     assert torch.equal(w2.state_dict()[k_internal], sd[k_internal].detach().bfloat16().float())
+
+
+def test_sharded_exchange_plan_is_contiguous_tensor_aligned_and_balanced():
+    """dp.ShardedExchange.plan (K-z host logic): every tensor on an 8-element boundary (= the replicated optimizer table's
+    rng_base), buckets contiguous / tensor-aligned / covering everything, owners round-robin, shares balanced."""
+    import random
+    from onetrainer_b200 import dp
+    from onetrainer_b200 import ops
+    rnd = random.Random(0)
+    numels = [rnd.choice([320, 640, 1280, 77, 13, 1280 * 1280, 640 * 640, 10240 * 1280, 5120 * 640, 9]) for _ in range(400)]
+    for world in (2, 4, 8):
+        offsets, total, bounds, first = dp.ShardedExchange.plan(numels, world)
+        assert all(o % 8 == 0 for o in offsets) and total % 8 == 0
+        run = 0
+        for n, o in zip(numels, offsets):           # same running offset as ops.OptimTable (rng_base += ceil8(n))
+            assert o == run
+            run += (n + 7) // 8 * 8
+        assert bounds[0] == 0 and bounds[-1] == total and bounds == sorted(set(bounds))
+        assert all(bounds[b] == offsets[first[b]] for b in range(len(bounds) - 1))
+        assert first[0] == 0 and first[-1] == len(numels) and all(a < b for a, b in zip(first, first[1:]))
+        nb = len(bounds) - 1
+        assert nb >= world
+        share = [0] * world
+        for b in range(nb):
+            share[b % world] += bounds[b + 1] - bounds[b]
+        assert max(share) <= 1.35 * total / world, (world, share)
+    # fewer tensors than buckets asked for: never an empty bucket
+    offsets, total, bounds, first = dp.ShardedExchange.plan([100, 200, 300], 2, n_buckets=8)
+    assert len(bounds) - 1 <= 3 and all(a < b for a, b in zip(bounds, bounds[1:]))

@@ -1,0 +1,157 @@
+"""K-z (dp.ShardedExchange: otb_shard_reduce / otb_shard_gather) on N ranks: kernel-level parity against ncclAllReduce, then
+the sharded optimizer step against the replicated one on the tiny full-fine-tuning stand-in, then CUDA-event timing.
+usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29543 tools/shard_check.py [big]"""
+import os
+import sys
+import torch
+import torch.distributed as dist
+sys.path.insert(0, ".")
+from onetrainer_b200 import dp, ops  # noqa: E402
+
+rank, local, world = dp.init_from_env("nccl")
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
+ok = True
+
+
+def say(*a):
+    print(f"rank {rank}/{world}", *a, flush=True)
+
+
+# ------------------------------------------------------------------ 1. the kernels, both modes, both dtypes
+shapes = [(640, 320), (77,), (1280, 1280), (3, 3, 64, 8), (5120, 640), (13,), (2560, 1280), (320,), (1280, 640), (640,), (1000, 333), (64, 64)] * 2
+for dt in (torch.bfloat16, torch.float32):
+    for mode in (("p2p", "nvls") if world in (2, 4, 8) else ("nvls",)):
+        torch.manual_seed(7)
+        params = [torch.nn.Parameter((torch.randn(s, device=dev) * 0.02).to(dt)) for s in shapes]
+        try:
+            ex = dp.ShardedExchange(params, n_buckets=2 * world, mode=mode, overlap=False)
+        except RuntimeError as e:
+            say(f"{mode} unavailable: {e}")
+            continue
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        ex.grad_flat.copy_((torch.randn(ex.grad_flat.shape, device=dev, generator=g) * 1e-3).to(dt))
+        ref = ex.grad_flat.clone()
+        dist.all_reduce(ref)                                   # the replicated form's exchange
+        ex.arm()
+        pre = ex.finish()
+        torch.cuda.synchronize()
+        mine = [(ex.bounds[b], ex.bounds[b + 1]) for b in range(ex.n_buckets) if ex.owner[b] == rank]
+        if world == 2 or dt == torch.float32 and world == 2:
+            same = all(torch.equal(ex.grad_flat[lo:hi], ref[lo:hi]) for lo, hi in mine)
+        else:   # more than two addends: NCCL's order / intermediate roundings differ from fp32 accumulation in rank order
+            same = all(torch.allclose(ex.grad_flat[lo:hi].float(), ref[lo:hi].float(), rtol=2 ** -7 if dt == torch.bfloat16 else 1e-5, atol=1e-7)
+                       for lo, hi in mine)
+        owned_sum = torch.cat([ex.grad_flat[lo:hi].float() for lo, hi in mine]) if mine else torch.zeros(0, device=dev)
+        sq = (owned_sum.double() * pre).pow(2).sum().reshape(1)
+        dist.all_reduce(sq)
+        norm = ex.partials.double().sum().sqrt().item()
+        norm_ok = abs(norm - sq.sqrt().item()) <= 1e-5 * sq.sqrt().item()
+        tables = [torch.zeros_like(ex.partials) for _ in range(world)]
+        dist.all_gather(tables, ex.partials)
+        tables_same = all(torch.equal(t, tables[0]) for t in tables)
+        # the optimizer "updates" my ranges; gather pushes them everywhere
+        with torch.no_grad():
+            for lo, hi in mine:
+                ex.param_flat[lo:hi] = (torch.arange(lo, hi, device=dev) % 251).to(dt) + rank
+        ex.gather()
+        torch.cuda.synchronize()
+        expect = torch.empty_like(ex.param_flat)
+        for b in range(ex.n_buckets):
+            lo, hi = ex.bounds[b], ex.bounds[b + 1]
+            expect[lo:hi] = (torch.arange(lo, hi, device=dev) % 251).to(dt) + ex.owner[b]
+        gathered = torch.equal(ex.param_flat, expect)
+        views_ok = all(p.data_ptr() == ex.param_flat.data_ptr() + off * p.element_size() for p, off in zip(params, ex.offsets))
+        say(f"{mode} {str(dt).split('.')[-1]}: buckets={ex.n_buckets} owned={len(mine)} reduce_equals_nccl={same} norm_ok={norm_ok} "
+            f"partial_tables_identical={tables_same} gathered={gathered} views_ok={views_ok}")
+        ok = ok and same and norm_ok and tables_same and gathered and views_ok
+        del ex, params
+
+# ------------------------------------------------------------------ 2. sharded step == replicated step
+from onetrainer_b200.harness import trainer  # noqa: E402
+from onetrainer_b200.modules.util.config.TrainConfig import TrainConfig  # noqa: E402
+
+
+def run(sharded: bool, clip, graph: bool, overlap: bool = True):
+    os.environ["OTB_SHARDED_OPT"] = "1" if sharded else "0"
+    os.environ["OTB_KZ_OVERLAP"] = "1" if overlap else "0"
+    torch.manual_seed(1234)
+    cfg = TrainConfig(train_device=str(dev), batch_size=2, clip_grad_norm=clip, ema_decay=0.999, ema_update_step_interval=2)
+    model, setup = trainer.build_model("tiny", cfg, dev, ema=True, stochastic_rounding=True, full_finetune=True, lr=1e-3)
+    batch = trainer.synthetic_batch("tiny", 2, dev, latent_hw=32)
+    losses = []
+    if graph:
+        host = {k: ([t.pin_memory() for t in v] if isinstance(v, list) else v.pin_memory()) for k, v in batch.items()}
+        st = trainer.GraphedTrainStep(setup, model, cfg, host)
+        for _ in range(3):
+            losses.append(st.step().item())
+        st.close()
+    else:
+        b = trainer.batch_to_device(batch, dev)
+        for _ in range(4):
+            losses.append(trainer.train_step(setup, model, b, cfg).item())
+    torch.cuda.synchronize()
+    flat = torch.cat([p.detach().float().flatten() for p in model.parameters])
+    # EMA of the tensors this rank steps (all of them when replicated): compare on the owner
+    ema = {id(p): e.detach().float().clone() for p, e in zip(model.optimizer_parameters, model.ema.ema_parameters)} if model.ema is not None else {}
+    order = {id(p): i for i, p in enumerate(model.parameters)}
+    ema_by_index = {order[k]: v for k, v in ema.items()}
+    return flat, losses, ema_by_index, model
+
+
+for clip in (None, 1.0):
+    for graph in (False, True):
+        ref_flat, ref_losses, ref_ema, _m = run(False, clip, graph)
+        del _m
+        for overlap in (False, True):
+            flat, losses, ema, m = run(True, clip, graph, overlap)
+            r0 = flat.clone()
+            dist.broadcast(r0, 0)
+            replicas = torch.equal(r0, flat)
+            if clip is None and world == 2:
+                same = torch.equal(flat, ref_flat)
+                ema_same = all(torch.equal(v, ref_ema[i]) for i, v in ema.items())
+            else:       # the clip coefficient comes from a differently ordered (still deterministic) sum of the same squares
+                same = torch.allclose(flat, ref_flat, rtol=2 ** -6, atol=1e-6) and (flat != ref_flat).float().mean().item() < 0.05
+                ema_same = all(torch.allclose(v, ref_ema[i], rtol=2 ** -6, atol=1e-6) for i, v in ema.items())
+            owned = len(m.optimizer_parameters)
+            say(f"step clip={clip} graph={graph} overlap={overlap}: params_match_replicated={same} ema_match={ema_same} replicas_identical={replicas} "
+                f"losses {['%.5f' % x for x in losses]} vs {['%.5f' % x for x in ref_losses]} owned_tensors={owned}/{len(m.parameters)}")
+            ok = ok and same and ema_same and replicas and owned < len(m.parameters)
+            del m
+
+# ------------------------------------------------------------------ 3. timing at the C4 size (optional)
+if "big" in sys.argv[1:]:
+    n = 2_222_172_804 // 8 * 8
+    chunk = 16 * 1024 * 1024
+    params = [torch.nn.Parameter(torch.zeros(min(chunk, n - lo), device=dev, dtype=torch.bfloat16)) for lo in range(0, n, chunk)]
+    for mode in (("p2p", "nvls") if world in (2, 4, 8) else ("nvls",)):
+        ex = dp.ShardedExchange(params, mode=mode, overlap=False)
+
+        def timed(fn, iters=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+
+        def red():
+            ex.arm(); ex.finish()
+        t_red, t_gat = timed(red), timed(ex.gather)
+        t_nccl = timed(lambda: dist.all_reduce(ex.grad_flat))
+        gb = n * 2 / 1e9
+        if rank == 0:
+            print(f"{world} GPUs, {gb:.2f} GB bf16, {mode}: shard_reduce {t_red:.2f} ms ({(world - 1) / world * gb / t_red * 1e3:.0f} GB/s in per GPU) | "
+                  f"shard_gather {t_gat:.2f} ms ({(world - 1) / world * gb / t_gat * 1e3:.0f} GB/s out per GPU) | ncclAllReduce {t_nccl:.2f} ms", flush=True)
+        del ex
+
+if rank == 0:
+    print("shard_check:", "ok" if ok else "MISMATCH", flush=True)
+torch.cuda.synchronize()
+os._exit(0 if ok else 1)
