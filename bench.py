@@ -828,12 +828,19 @@ def own_arm(args) -> None:
         for fn in (c2, c4, c5):
             try:
                 rec, m, s = fn()
-                if rec["config"].startswith("C4") and rank == 0:
-                    kc = optimizer_in_step_gbs(m, dev)
-                    rec["kc_in_step"] = {"gbs": kc["gbs"], "frac_of_hbm": kc["gbs"] / hbm_peak, "ms": kc["seconds"] * 1e3, "bytes": kc["bytes"],
-                                         "includes": kc["includes"]}
-                    if world > 1 and getattr(m, "grad_reducer", None) is not None:
-                        rec["exchange"] = f"bucketed ncclAllReduce of the {m.full_grad_arena.flat.numel() * 2 / 2 ** 30:.2f} GiB bf16 gradient arena, overlapped with backward"
+                if rec["config"].startswith("C4"):
+                    red = getattr(m, "grad_reducer", None)
+                    if world > 1 and isinstance(red, dp.ShardedExchange):
+                        # K-z: reduce-scatter -> AdamW + EMA on the owner's tensors only -> all-gather (every rank takes part)
+                        rec["exchange"] = {"kind": "K-z (otb_shard_reduce / otb_shard_gather over NVLink peer memory; optimizer state and EMA sharded "
+                                                   f"1/{world}: {len(m.optimizer_parameters)} of {len(m.parameters)} tensors on this rank)", **red.measure()}
+                    elif world > 1 and red is not None:
+                        rec["exchange"] = {"kind": f"bucketed ncclAllReduce of the {m.full_grad_arena.flat.numel() * 2 / 2 ** 30:.2f} GiB bf16 gradient "
+                                                   "arena, overlapped with backward; replicated optimizer"}
+                    if rank == 0 and not (world > 1 and isinstance(red, dp.ShardedExchange)):
+                        kc = optimizer_in_step_gbs(m, dev)
+                        rec["kc_in_step"] = {"gbs": kc["gbs"], "frac_of_hbm": kc["gbs"] / hbm_peak, "ms": kc["seconds"] * 1e3, "bytes": kc["bytes"],
+                                             "includes": kc["includes"]}
                 subs.append(rec)
                 free_model(m, s)
             except Exception as e:  # noqa: BLE001

@@ -534,6 +534,42 @@ class ShardedExchange:
         self._armed = False
         return 1.0 / self.world
 
+    def measure(self, iters: int = 5) -> dict:
+        """CUDA-event time of the two halves, NOT overlapped with anything (collective: every rank must call it; the
+        gradients are summed in place again and again, so call it only when their values no longer matter): max over ranks."""
+        dev = self.grad_flat.device
+        keep = self.overlap
+        self.overlap = False
+
+        def timed(fn):
+            fn()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+
+        def reduce():
+            self.arm()
+            self.finish()
+        try:
+            red, gat = timed(reduce), timed(self.gather)
+        finally:
+            self.overlap = keep
+        esz = self.grad_flat.element_size()
+        nbytes = self.grad_flat.numel() * esz
+        moved = (self.world - 1) / self.world * nbytes
+        return {"mode": self.mode, "buckets": self.n_buckets, "arena_gb": nbytes / 1e9, "reduce_ms": red, "gather_ms": gat,
+                "reduce_gbs_in_per_gpu": moved / red / 1e6, "gather_gbs_out_per_gpu": moved / gat / 1e6,
+                "note": "reduce-scatter + squared norm / all-gather of the updated parameters, each timed alone with its barriers; "
+                        "in the step the reduce of a bucket overlaps the rest of backward"}
+
     def gather(self) -> None:
         """After the optimizer step on the owned tensors: push my parameter ranges into every replica."""
         import ctypes as C
