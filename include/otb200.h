@@ -177,7 +177,7 @@ typedef struct otb_dora_args {
     const float* ba;          /* [N, J] fp32: lora_up . lora_down (make_weight, :76-91), unscaled                      */
     const float* dora_scale;  /* [J / group_size] (input axis) or [N] (output axis), fp32                              */
     float*       norm;        /* same shape: written by otb_dora_compose, read by otb_dora_backward                     */
-    float*       scratch;     /* max(N, J) floats                                                                      */
+    float*       scratch;     /* max(N, 64 * J) floats (row-slab partials of the column passes)                        */
     void*        wp;          /* compose: [N, J] bf16 out                                                              */
     void*        wpt;         /* compose: [J, N] bf16 out (the K-major operand of the dX launch), or NULL              */
     const void*  G;           /* backward: [N, J] bf16, dL/dWP                                                         */
@@ -234,6 +234,7 @@ typedef struct otb_factored_launch {
     const otb_factored_tensor* tensors;   /* device array                                                             */
     float*   scratch;                     /* device, sum of `batch` over the tensors                                  */
     int32_t  n_tensors;
+    int32_t  cluster;                     /* CTAs per tensor (one thread-block cluster each): 1, 2, 4 or 8; 0 = 1       */
     uint64_t seed, offset;                /* CAME stochastic rounding: the weight-decay draw uses `offset`, the update
                                              draw `offset + 1` (`offset` when weight_decay == 0)                      */
 } otb_factored_launch;

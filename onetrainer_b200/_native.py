@@ -145,7 +145,7 @@ class DoraArgs(C.Structure):
 
 
 class FactoredLaunch(C.Structure):
-    _fields_ = [("tensors", _vp), ("scratch", _vp), ("n_tensors", _i32), ("seed", _u64), ("offset", _u64)]
+    _fields_ = [("tensors", _vp), ("scratch", _vp), ("n_tensors", _i32), ("cluster", _i32), ("seed", _u64), ("offset", _u64)]
 
 
 MAX_RANKS = 16           # OTB_MAX_RANKS

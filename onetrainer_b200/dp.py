@@ -323,8 +323,9 @@ class ShardedExchange:
     to rank b % world.  Per step:
 
         arm()                 before backward
-        [hooks]               when a bucket's last gradient lands: non-owners signal the owner, the owner waits for every
-                              peer and reduces the bucket on a communication stream while backward goes on (overlap=True)
+        [hooks]               overlap=True only (off by default — measured slower, see below): when a bucket's last gradient lands,
+                              non-owners signal the owner, the owner waits for every peer and reduces the bucket on a
+                              communication stream while backward goes on
         finish() -> 1/n       joins; after it every rank holds the complete table of squared-norm partials
                               (`norm_partials`) and the owner's replica holds the summed gradients of its buckets
         optimizer.step()      an optimizer built over `owned_parameters()` only: 1/n of the state, EMA and HBM traffic
@@ -354,7 +355,11 @@ class ShardedExchange:
         if mode == "p2p" and ws not in (2, 4, 8):
             mode = "nvls"
         self.mode, self.rank, self.world = mode, rk, ws
-        self.overlap = (os.environ.get("OTB_KZ_OVERLAP", "1") != "0") if overlap is None else overlap
+        # measured on 2 B200s, C4 (profiles/r02e_logs): 1 GPU 142.0 ms/step; reduce after backward 145.5 ms; reduce per bucket
+        # DURING backward 149.6 ms (296 blocks), 155 / 172 / 235 ms with 32 / 16 / 8 blocks — a reduce fast enough to keep up
+        # takes the SMs backward needs, a small one is latency-bound on peer loads and ends up on the critical path.
+        # Off by default; OTB_KZ_OVERLAP=1 turns the per-bucket hand-shakes on.
+        self.overlap = (os.environ.get("OTB_KZ_OVERLAP", "0") != "0") if overlap is None else overlap
         self.parameters = list(parameters)
         offsets, total, bounds, first_param = self.plan([p.numel() for p in parameters], ws, n_buckets)
         self.param_flat = symmetric_zeros(total, dt, dev)
@@ -378,7 +383,7 @@ class ShardedExchange:
                 self._bucket_of[id(parameters[i])] = b
             self._counts.append(first_param[b + 1] - first_param[b])
         self._owned = [p for p in parameters if self.owner[self._bucket_of[id(p)]] == rk]
-        self.blocks = min(4096, max(1, int(os.environ.get("OTB_KZ_BLOCKS", str(2 * torch.cuda.get_device_properties(dev).multi_processor_count)))))
+        self.blocks = min(4096, max(1, int(os.environ.get("OTB_KZ_BLOCKS", str(4 * torch.cuda.get_device_properties(dev).multi_processor_count)))))
         self.partials = symmetric_zeros(self.n_buckets * self.blocks, torch.float32, dev)
         self.flags = symmetric_zeros(N.PEER_PHASES * N.MAX_RANKS, torch.int32, dev)              # barriers
         self.ready = symmetric_zeros(self.n_buckets * N.MAX_RANKS, torch.int32, dev)             # per-bucket "produced" words

@@ -36,6 +36,8 @@ def _shape3(shape) -> tuple[int, int, int, bool]:
 
 class FactoredDriver:
     """Owns the device table of one Adafactor / CAME optimizer and launches the kernel."""
+    SMALL_NUMEL = 1 << 17        # up to 128 k elements (every rank <= 64 LoRA factor of SD / SDXL / FLUX): one CTA per tensor
+    LARGE_CLUSTER = 8            # larger tensors (full fine-tuning): a cluster of 8 CTAs per tensor
 
     def __init__(self, optimizer, kind: str):
         assert kind in ("adafactor", "came")
@@ -152,11 +154,15 @@ class FactoredDriver:
         entry["event"].record()
         self.step_count += 1
         wd_calls = 2 if any(g["weight_decay"] != 0 for g in self.opt.param_groups) else 1
-        a = N.FactoredLaunch(tensors=entry["dev"].data_ptr(), scratch=entry["scratch"].data_ptr(), n_tensors=n,
-                             seed=torch.initial_seed() & (2 ** 64 - 1), offset=(self.step_count - 1) * wd_calls + 1)
         fn = N.lib().otb_adafactor_multi if self.kind == "adafactor" else N.lib().otb_came_multi
-        N.check(fn(C.byref(a), ops._stream()), f"otb_{self.kind}_multi")
-        ops._count()
+        n_small = int((entry["host"]["numel"][:n] <= self.SMALL_NUMEL).sum())          # the table is sorted: small tensors first
+        for first, count, cluster in ((0, n_small, 1), (n_small, n - n_small, self.LARGE_CLUSTER)):
+            if count == 0:
+                continue
+            a = N.FactoredLaunch(tensors=entry["dev"].data_ptr() + first * _DT.itemsize, scratch=entry["scratch"].data_ptr(), n_tensors=count,
+                                 cluster=cluster, seed=torch.initial_seed() & (2 ** 64 - 1), offset=(self.step_count - 1) * wd_calls + 1)
+            N.check(fn(C.byref(a), ops._stream()), f"otb_{self.kind}_multi")
+            ops._count()
 
     # ---- entry points ------------------------------------------------------------------------
     @torch.no_grad()
@@ -167,6 +173,8 @@ class FactoredDriver:
                 loss = closure()
         active = [(p, g) for g in self.opt.param_groups for p in g["params"] if p.grad is not None]
         if active:
+            # size classes: LoRA-sized tensors get one CTA each, large matrices a cluster of 8 (stable order inside a class)
+            active = [a for a in active if a[0].numel() <= self.SMALL_NUMEL] + [a for a in active if a[0].numel() > self.SMALL_NUMEL]
             N.require_cuda(*[p for p, _ in active])
             for p, g in active:
                 self._init_state(p, g)

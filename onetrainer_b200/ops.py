@@ -275,7 +275,7 @@ def dora_compose(w2: torch.Tensor, ba: torch.Tensor, dora_scale: torch.Tensor, s
         raise ValueError(f"dora_compose: dora_scale must be {groups} contiguous fp32 values")
     dev = w2.device
     norm = torch.empty((groups,), dtype=torch.float32, device=dev)
-    scratch = torch.empty((max(Nn, J),), dtype=torch.float32, device=dev)
+    scratch = torch.empty((max(Nn, 64 * J),), dtype=torch.float32, device=dev)
     wp = torch.empty((Nn, J), dtype=torch.bfloat16, device=dev)
     wpt = torch.empty((J, Nn), dtype=torch.bfloat16, device=dev) if want_transposed else None
     a = _dora_args(w2, ba, m, norm, scratch, scale, eps, group_size, out_axis, wp=wp, wpt=wpt)
@@ -295,7 +295,7 @@ def dora_backward(G: torch.Tensor, w2: torch.Tensor, ba: torch.Tensor, dora_scal
     m = dora_scale.detach().reshape(-1)
     dV = torch.empty((Nn, J), dtype=torch.float32, device=dev)
     dm = torch.empty_like(m)
-    scratch = torch.empty((max(Nn, J),), dtype=torch.float32, device=dev)
+    scratch = torch.empty((max(Nn, 64 * J),), dtype=torch.float32, device=dev)
     a = _dora_args(w2, ba, m, norm, scratch, scale, 0.0, group_size, out_axis, G=G, dV=dV, d_scale=dm)
     N.check(N.lib().otb_dora_backward(C.byref(a), _stream()), "otb_dora_backward")
     _count(2)

@@ -37,11 +37,20 @@ for dt in (torch.bfloat16, torch.float32):
         pre = ex.finish()
         torch.cuda.synchronize()
         mine = [(ex.bounds[b], ex.bounds[b + 1]) for b in range(ex.n_buckets) if ex.owner[b] == rank]
-        if world == 2 or dt == torch.float32 and world == 2:
+        note = ""
+        if world == 2 and not (mode == "nvls" and dt == torch.bfloat16):
             same = all(torch.equal(ex.grad_flat[lo:hi], ref[lo:hi]) for lo, hi in mine)
-        else:   # more than two addends: NCCL's order / intermediate roundings differ from fp32 accumulation in rank order
-            same = all(torch.allclose(ex.grad_flat[lo:hi].float(), ref[lo:hi].float(), rtol=2 ** -7 if dt == torch.bfloat16 else 1e-5, atol=1e-7)
-                       for lo, hi in mine)
+        else:
+            # more than two addends: NCCL's order / intermediate roundings differ from fp32 accumulation in rank order;
+            # NVLS bf16: the switch adds in its own arithmetic (multimem.ld_reduce.add.acc::f32.bf16x2) — bounded by 1 bf16 ulp
+            worst, frac = 0.0, 0.0
+            for lo, hi in mine:
+                a, b = ex.grad_flat[lo:hi].float(), ref[lo:hi].float()
+                ulp = torch.exp2(torch.floor(torch.log2(b.abs().clamp_min(1e-30))) - (7 if dt == torch.bfloat16 else 23))
+                worst = max(worst, float(((a - b).abs() / ulp).max())) if hi > lo else worst
+                frac = max(frac, float((a != b).float().mean())) if hi > lo else frac
+            same = worst <= (1.0 if dt == torch.bfloat16 else 4.0 * world)
+            note = f" (worst {worst:.2f} ulp, {frac * 100:.2f}% of elements differ from NCCL)"
         owned_sum = torch.cat([ex.grad_flat[lo:hi].float() for lo, hi in mine]) if mine else torch.zeros(0, device=dev)
         sq = (owned_sum.double() * pre).pow(2).sum().reshape(1)
         dist.all_reduce(sq)
@@ -62,7 +71,7 @@ for dt in (torch.bfloat16, torch.float32):
             expect[lo:hi] = (torch.arange(lo, hi, device=dev) % 251).to(dt) + ex.owner[b]
         gathered = torch.equal(ex.param_flat, expect)
         views_ok = all(p.data_ptr() == ex.param_flat.data_ptr() + off * p.element_size() for p, off in zip(params, ex.offsets))
-        say(f"{mode} {str(dt).split('.')[-1]}: buckets={ex.n_buckets} owned={len(mine)} reduce_equals_nccl={same} norm_ok={norm_ok} "
+        say(f"{mode} {str(dt).split('.')[-1]}: buckets={ex.n_buckets} owned={len(mine)} reduce_equals_nccl={same}{note} norm_ok={norm_ok} "
             f"partial_tables_identical={tables_same} gathered={gathered} views_ok={views_ok}")
         ok = ok and same and norm_ok and tables_same and gathered and views_ok
         del ex, params
