@@ -382,7 +382,9 @@ struct GemmParams3 {
     int acc_stages;        // 2 when NB <= 256, else 1
     int pair_m_tiles;      // ceil(M / 256)
     int prefetch_w;        // weight tiles of the first k-blocks are fetched before griddepcontrol.wait (OTB_LINEAR_STATIC_WEIGHTS)
-    int debug;             // bring-up only (OTB_KA_DEBUG): bit 0 skip the TMA loads, bit 1 skip the MMAs, bit 2 skip the epilogue
+    int lookahead;         // k-blocks of tile i+1 issued before the rank-R MMAs of tile i (acc_stages == 2); 0 = right after tile i
+    int debug;             // bring-up only (OTB_KA_DEBUG): bit 0 skip the TMA loads, bit 1 skip the MMAs, bit 2 skip the epilogue,
+                           // bit 3 skip the TMA stores, bit 4 skip the accumulator loads, bit 5 skip the async-proxy fence
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
@@ -390,8 +392,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Arrival on a barrier of the peer (leader) CTA.  Default semantics (.release at CTA scope), as CUTLASS's ClusterBarrier
+// does it: what the waiter consumes afterwards is TMEM (read back with tcgen05.ld + wait before the arrive) or this CTA's
+// own shared memory through the async proxy (ordered by fence.proxy.async before the arrive) — nothing that needs a
+// cluster-scope release.  With `.release.cluster` the arrive is a MEMBAR that waits for every earlier global store of the
+// thread: 18 % of the kernel's stall samples on the short-K leaves (`stall_membar`, profiles/r02_ncu_kac640_lines.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
 // wait on an own barrier whose arrivals come from the peer CTA as well
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -615,7 +622,8 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
                 mbar_wait_cluster(misc(10 + as), (uint32_t)((it / q.acc_stages) & 1) ^ 1); // acc_empty
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * acc_stride;
-                const int lookahead = p.num_kb < 2 ? p.num_kb : 2;
+                const int lookahead = p.num_kb < q.lookahead ? p.num_kb : q.lookahead;
+                if (pending >= 0 && lookahead == 0) { issue_up(pending); pending = -1; }
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
@@ -719,15 +727,25 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
                 if (cols == 64 && nb0 + 64 <= p.N && (me.bias == nullptr || bias_vec)) {
                     // ---- full 64-column block: one swizzled box, one TMA store ----
                     uint32_t v[64];
-                    tmem_ld32<0>(t_lane + (uint32_t)(c0 + 0), v);
-                    tmem_ld32<32>(t_lane + (uint32_t)(c0 + 32), v);
-                    tmem_ld_wait();
-                    if (me.bias != nullptr) {                               // same address in every lane: L1 broadcast
+                    uint4 bq[8];                                            // bf16 bias of the block, requested BEFORE the TMEM loads
+                    if (me.bias != nullptr && me.bias_dtype == OTB_BF16) {  // (same address in every lane: L1 broadcast)
+                        const uint4* bp = reinterpret_cast<const uint4*>((const uint16_t*)me.bias + nb0);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) bq[g] = __ldg(bp + g);
+                    }
+                    if (!(q.debug & 16)) {
+                        tmem_ld32<0>(t_lane + (uint32_t)(c0 + 0), v);
+                        tmem_ld32<32>(t_lane + (uint32_t)(c0 + 32), v);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) v[j] = 0u;
+                    }
+                    if (me.bias != nullptr) {
                         if (me.bias_dtype == OTB_BF16) {
-                            const uint4* bp = reinterpret_cast<const uint4*>((const uint16_t*)me.bias + nb0);
 #pragma unroll
                             for (int g = 0; g < 8; ++g) {
-                                const uint4 b = __ldg(bp + g);
+                                const uint4 b = bq[g];
                                 const uint32_t w[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
@@ -757,9 +775,9 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
                                        pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3])),
                                        pack_bf16x2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5])),
                                        pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7])));
-                    fence_proxy_async();
+                    if (!(q.debug & 32)) fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) {
+                    if (lane == 0 && !(q.debug & 8)) {
                         tma_store_2d(&maps.y[gm], ybox, nb0, m0 + quad * 32);
                         bulk_commit();
                     }
@@ -769,12 +787,28 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
                         const int n = n0 + c;
                         if (n >= p.N) break;
                         uint32_t v[16];
+                        // a whole 16-column chunk with an aligned bf16 bias (the 32-column remainder of a 224-wide tile): two
+                        // vector loads, requested before the accumulator load — per-element loads made this path 20 % of the
+                        // kernel's stall samples on the short-K leaves (profiles/r02_ncu_kac640_lines.md)
+                        const bool bias16 = bias_vec && me.bias_dtype == OTB_BF16 && n + 16 <= p.N;
+                        uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
+                        if (bias16) {
+                            const uint4* bp = reinterpret_cast<const uint4*>((const uint16_t*)me.bias + n);
+                            b0 = __ldg(bp); b1 = __ldg(bp + 1);
+                        }
                         tmem_ld16(t_lane + (uint32_t)c, v);
                         tmem_ld_wait();
                         float f[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-                        if (me.bias != nullptr) {
+                        if (bias16) {
+                            const uint32_t w[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                f[2 * e] += __uint_as_float(w[e] << 16);
+                                f[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+                            }
+                        } else if (me.bias != nullptr) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
                                 if (n + j < p.N) f[j] += load_as_float(me.bias, n + j, me.bias_dtype);
@@ -1003,6 +1037,8 @@ int launch_v3(const otb_lora_linear_args* a, int count, void* stream, int tile_n
     OTB_CHECK_ARG(v3_shape_ok(tile_n, p.Rp, &q.chunks, &q.up_chunks, &q.acc_stages),
                   "pair tile_n %d invalid for rank %d (tile_n + rank a multiple of 16 (32 above 256), <= 512)", tile_n, p.Rp);
     q.debug = env_int("OTB_KA_DEBUG", 0);
+    q.lookahead = env_int("OTB_KA_LOOKAHEAD", 2);
+    if (q.lookahead < 0) q.lookahead = 0;
     q.prefetch_w = 1;
     for (int g = 0; g < count; ++g)
         if (!(a[g].flags & OTB_LINEAR_STATIC_WEIGHTS)) q.prefetch_w = 0;

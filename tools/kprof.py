@@ -75,6 +75,14 @@ elif which == "ka1280":
     bias = torch.randn(Nn, device=dev).bfloat16()
     ms = timed(lambda: ops.lora_linear(x, w, down, up, bias, 1 / 32))
     print(f"ka1280: {ms * 1e3:.1f} us, {(2.0 * M * Nn * K + 2.0 * M * R * (K + Nn)) / ms / 1e9:.1f} TFLOP/s")
+elif which == "kac640":
+    # short-K shape of the C=640 level (10 k-blocks per tile): epilogue-bound
+    M, Nn, K, R = 16384, 5120, 640, 32
+    x = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(Nn, K, device=dev) / 25).bfloat16()
+    down = (torch.randn(R, K, device=dev) / 25).bfloat16(); up = torch.randn(Nn, R, device=dev).bfloat16()
+    bias = torch.randn(Nn, device=dev).bfloat16()
+    ms = timed(lambda: ops.lora_linear(x, w, down, up, bias, 1 / 32))
+    print(f"kac640: {ms * 1e3:.1f} us, {(2.0 * M * Nn * K + 2.0 * M * R * (K + Nn)) / ms / 1e9:.1f} TFLOP/s")
 elif which == "kaqkv":
     M, Nn, K, R = 4096, 1280, 1280, 32
     x = torch.randn(M, K, device=dev).bfloat16()

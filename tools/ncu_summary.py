@@ -85,5 +85,49 @@ def launches(path):
         print(f"| `{k}` | {n} | {t:.1f} | {t / total:.3f} |")
 
 
+def lines(path, top=30):
+    """Warp-stall samples per SOURCE line of a capture taken with --import-source on (kernels compiled with -lineinfo)."""
+    import collections
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    agg, stall, total = collections.Counter(), collections.defaultdict(collections.Counter), 0
+    cur, h, ci, kernel = None, None, {}, ""
+
+    def num(x):
+        try:
+            return int(x)
+        except ValueError:
+            return 0
+    for r in rows:
+        if r and r[0] == "File Path":
+            cur = r[1].split("/")[-1]
+            continue
+        if r and r[0] == "Function Name":
+            kernel = r[1]
+            continue
+        if r and r[0] == "Line No":
+            h, ci = r, {}
+            for k, n in enumerate(h):
+                ci.setdefault(n, k)
+            continue
+        if h is None or len(r) < len(h) or r[2] != "-":
+            continue
+        n = num(r[ci["# Samples"]])
+        if n == 0:
+            continue
+        key = (cur, num(r[0]), r[1].strip())
+        agg[key] += n
+        total += n
+        for name, k in ci.items():
+            if name.startswith("stall_") and "Not Issued" not in name and num(r[k]):
+                stall[key][name] += num(r[k])
+    print(f"# warp-stall samples per source line: `{path.split('/')[-1]}`\n\n`{kernel}` — {total} samples\n")
+    print("| samples | share | line | source | top stall reasons |\n|---|---|---|---|---|")
+    for key, n in agg.most_common(top):
+        f, ln, src = key
+        why = ", ".join(f"{a} {b}" for a, b in stall[key].most_common(2))
+        print(f"| {n} | {n / total:.3f} | `{f}:{ln}` | `{src[:110].replace('|', '¦')}` | {why} |")
+
+
 if __name__ == "__main__":
-    {"rep": rep, "list": launches}[sys.argv[1]](sys.argv[2])
+    {"rep": rep, "list": launches, "lines": lines}[sys.argv[1]](sys.argv[2])
