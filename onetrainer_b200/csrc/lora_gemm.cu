@@ -78,6 +78,11 @@ __device__ __forceinline__ uint32_t cluster_nctaid_x() { uint32_t r; asm volatil
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// execution barrier only: what it orders is barrier initialisation (published by fence.mbarrier_init.release.cluster) or
+// the end of all work of the pair — no data; `.release` here is a MEMBAR that waits for every outstanding store
+__device__ __forceinline__ void cluster_sync_relaxed() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
@@ -351,6 +356,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                  :: "l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// L2-only prefetch of one box of a tensor map (no shared-memory slot, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(map), "r"(c0), "r"(c1) : "memory");
+}
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
 
@@ -400,7 +409,8 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
-// wait on an own barrier whose arrivals come from the peer CTA as well
+// wait on an own barrier whose arrivals come from the peer CTA as well, with a cluster-scope acquire (kept for reference:
+// the MMA warp's two waits consume TMEM / async-proxy shared memory only and use the plain CTA-scope wait, as CUTLASS does)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t done = 0, spins = 0;
     long long t0 = 0;
@@ -511,7 +521,7 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
     if (warp == 1) tmem_alloc_2sm(misc(12), 512u);
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                         // the peer's barriers and TMEM exist before anything crosses CTAs
+    cluster_sync_relaxed();                     // the peer's barriers and TMEM exist before anything crosses CTAs
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
     // Everything above overlapped the previous kernel's tail.  griddepcontrol.wait (its outputs are visible afterwards) is
@@ -544,7 +554,25 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
             }
         };
         int prefetched = 0;            // k-blocks of this CTA's FIRST tile whose weights are already on their way
-        if (q.prefetch_w && !(q.debug & 1) && cid < (uint32_t)total_tiles) {
+        if (q.prefetch_w == 2 && !(q.debug & 1) && cid < (uint32_t)total_tiles) {
+            // L2-only variant: the frozen weight tiles of this CTA's first tile are pulled from HBM into L2 while the previous
+            // launch still runs; nothing queues in front of the first x box and no ring slot is taken
+            const int gm = ((int)cid % tiles_per_row) / p.n_tiles, nt = (int)cid % p.n_tiles;
+            const int n0 = nt * p.tile_n;
+            if (elect_one()) {
+                for (int kb = 0; kb < p.num_kb; ++kb)
+                    for (int c = 0; c < q.chunks; ++c) {
+                        const int row = c * nbc + (int)crank * nbh;
+                        if (lora && c == q.chunks - 1 && !leader) {
+                            if (nbh > p.Rp) tma_prefetch_l2_2d(&maps.w2[gm], kb * BK, n0 + row);
+                            tma_prefetch_l2_2d(&maps.dn[gm], kb * BK, 0);
+                        } else {
+                            tma_prefetch_l2_2d(&maps.w[gm], kb * BK, n0 + row);
+                        }
+                    }
+            }
+            __syncwarp();
+        } else if (q.prefetch_w && !(q.debug & 1) && cid < (uint32_t)total_tiles) {
             const int gm = ((int)cid % tiles_per_row) / p.n_tiles, nt = (int)cid % p.n_tiles;
             const int n0 = nt * p.tile_n;
             prefetched = p.num_kb < p.stages ? p.num_kb : p.stages;
@@ -603,7 +631,7 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
             int it = 0, pending = -1;
             auto issue_up = [&](int j) {      // D += T(j) . up(j)^T, then hand the accumulator to the epilogue
                 const int as = j % q.acc_stages, ub = j % up_bufs;
-                mbar_wait_cluster(misc(6), (uint32_t)(j & 1));                              // t_ready: both CTAs parked T(j)
+                mbar_wait(misc(6), (uint32_t)(j & 1));                                      // t_ready: both CTAs parked T(j)
                 mbar_wait(misc(0 + ub), (uint32_t)((j / up_bufs) & 1));                     // up_full
                 tc_fence_after();
                 if (elect_one()) {
@@ -619,7 +647,7 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
             };
             for (uint32_t st = cid; st < (uint32_t)total_tiles; st += ncl, ++it) {
                 const int as = it % q.acc_stages;
-                mbar_wait_cluster(misc(10 + as), (uint32_t)((it / q.acc_stages) & 1) ^ 1); // acc_empty
+                mbar_wait(misc(10 + as), (uint32_t)((it / q.acc_stages) & 1) ^ 1);         // acc_empty
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * acc_stride;
                 const int lookahead = p.num_kb < q.lookahead ? p.num_kb : q.lookahead;
@@ -681,6 +709,19 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
             const V3Member& me = q.mem[gm];
             const bool bias_vec = me.bias != nullptr && (me.bias_dtype == OTB_BF16 || me.bias_dtype == OTB_F32) && (((uintptr_t)me.bias) & 15) == 0;
             const uint32_t t_lane = tmem_base + as * acc_stride + ((uint32_t)(quad * 32) << 16);
+            // bf16 bias of this warp's 64-column blocks, one 4-byte word (two columns) per lane, requested NOW — before the
+            // waits for the MMAs — and broadcast with shuffles in the epilogue: the eight 16-byte loads per block that stood
+            // here before were still 5-6 % of the kernel's stall samples after being hoisted above the accumulator load
+            uint32_t bw[4] = {0u, 0u, 0u, 0u};
+            const bool bias_shfl = bias_vec && me.bias_dtype == OTB_BF16;
+            if (bias_shfl) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c0 = half * 64 + k * 128;
+                    if (c0 + 64 <= p.tile_n && n0 + c0 + 64 <= p.N)
+                        bw[k] = __ldg(reinterpret_cast<const uint32_t*>((const uint16_t*)me.bias + n0 + c0) + lane);
+                }
+            }
             if (lora) {
                 mbar_wait(misc(4 + as), par);                               // t_full
                 tc_fence_after();
@@ -727,12 +768,8 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
                 if (cols == 64 && nb0 + 64 <= p.N && (me.bias == nullptr || bias_vec)) {
                     // ---- full 64-column block: one swizzled box, one TMA store ----
                     uint32_t v[64];
-                    uint4 bq[8];                                            // bf16 bias of the block, requested BEFORE the TMEM loads
-                    if (me.bias != nullptr && me.bias_dtype == OTB_BF16) {  // (same address in every lane: L1 broadcast)
-                        const uint4* bp = reinterpret_cast<const uint4*>((const uint16_t*)me.bias + nb0);
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) bq[g] = __ldg(bp + g);
-                    }
+                    const int bk = c0 >> 7;                                  // (selects, not an indexed array: keeps bw[] in registers)
+                    const uint32_t my_bias = bk == 0 ? bw[0] : bk == 1 ? bw[1] : bk == 2 ? bw[2] : bw[3];   // columns 2*lane, 2*lane + 1
                     if (!(q.debug & 16)) {
                         tmem_ld32<0>(t_lane + (uint32_t)(c0 + 0), v);
                         tmem_ld32<32>(t_lane + (uint32_t)(c0 + 32), v);
@@ -744,14 +781,10 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
                     if (me.bias != nullptr) {
                         if (me.bias_dtype == OTB_BF16) {
 #pragma unroll
-                            for (int g = 0; g < 8; ++g) {
-                                const uint4 b = bq[g];
-                                const uint32_t w[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    v[g * 8 + e * 2 + 0] = __float_as_uint(__uint_as_float(v[g * 8 + e * 2 + 0]) + __uint_as_float(w[e] << 16));
-                                    v[g * 8 + e * 2 + 1] = __float_as_uint(__uint_as_float(v[g * 8 + e * 2 + 1]) + __uint_as_float(w[e] & 0xFFFF0000u));
-                                }
+                            for (int e = 0; e < 32; ++e) {                   // lane e holds the bias of columns 2e, 2e + 1
+                                const uint32_t w = __shfl_sync(0xffffffffu, my_bias, e);
+                                v[2 * e + 0] = __float_as_uint(__uint_as_float(v[2 * e + 0]) + __uint_as_float(w << 16));
+                                v[2 * e + 1] = __float_as_uint(__uint_as_float(v[2 * e + 1]) + __uint_as_float(w & 0xFFFF0000u));
                             }
                         } else {
                             const float4* bp = reinterpret_cast<const float4*>((const float*)me.bias + nb0);
@@ -831,7 +864,7 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                         // neither CTA exits (or frees TMEM) while the pair still works
+    cluster_sync_relaxed();                     // neither CTA exits (or frees TMEM) while the pair still works
     if (warp == 1) {
         __syncwarp();
         tmem_dealloc_2sm(tmem_base, 512u);
@@ -1046,6 +1079,7 @@ int launch_v3(const otb_lora_linear_args* a, int count, void* stream, int tile_n
     // LOST 0.9 ms (37.2 vs 36.3 ms) — the x tile of the first k-block then queues behind up to `stages` weight boxes in the
     // TMA unit, and the early fetches compete with the predecessor's epilogue stores (profiles/README.md, round 2).
     if (!otb_pdl_enabled() || env_int("OTB_KA_PREFETCH_W", 0) == 0) q.prefetch_w = 0;
+    else if (q.prefetch_w) q.prefetch_w = env_int("OTB_KA_PREFETCH_W", 0) == 2 ? 2 : 1;      // 2: into L2 only
     p.num_kb = (a->K + BK - 1) / BK;
     p.n_tiles = (a->N + p.tile_n - 1) / p.tile_n;
     q.pair_m_tiles = (a->M + 2 * BM - 1) / (2 * BM);

@@ -34,7 +34,6 @@
 
 namespace {
 
-__device__ __forceinline__ float ldf(const void* p, int64_t i, int dt) { return load_as_float(p, i, dt); }
 
 // deterministic block sum: strided per-thread partials -> warp shuffle tree -> warp partials summed in warp order
 __device__ float block_sum(float v, float* red) {
@@ -82,9 +81,55 @@ __device__ __forceinline__ void phase_sync() {
 
 struct Dims { int batch, rows, cols; int64_t numel; };
 
+// ---- W consecutive elements at a time (W = 4: 16-byte accesses for fp32, 8-byte for bf16 / fp16; W = 1: any shape)
+template <int W>
+__device__ __forceinline__ void ld_w(const void* p, int64_t i, int dt, float (&f)[W]) {
+    if (W == 4) {
+        if (dt == OTB_F32) {
+            const float4 v = *reinterpret_cast<const float4*>((const float*)p + i);
+            f[0] = v.x; f[1 % W] = v.y; f[2 % W] = v.z; f[3 % W] = v.w;
+        } else {
+            const uint2 v = *reinterpret_cast<const uint2*>((const uint16_t*)p + i);
+            if (dt == OTB_BF16) {
+                f[0] = __uint_as_float(v.x << 16); f[1 % W] = __uint_as_float(v.x & 0xFFFF0000u);
+                f[2 % W] = __uint_as_float(v.y << 16); f[3 % W] = __uint_as_float(v.y & 0xFFFF0000u);
+            } else {
+                const __half2 h0 = *reinterpret_cast<const __half2*>(&v.x), h1 = *reinterpret_cast<const __half2*>(&v.y);
+                f[0] = __low2float(h0); f[1 % W] = __high2float(h0); f[2 % W] = __low2float(h1); f[3 % W] = __high2float(h1);
+            }
+        }
+    } else {
+        f[0] = load_as_float(p, i, dt);
+    }
+}
+template <int W>
+__device__ __forceinline__ void st_w(void* p, int64_t i, int dt, const float (&f)[W]) {
+    if (W == 4 && dt == OTB_F32) {
+        *reinterpret_cast<float4*>((float*)p + i) = make_float4(f[0], f[1 % W], f[2 % W], f[3 % W]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; ++k) store_from_float(p, i + k, dt, f[k]);
+    }
+}
+template <int W>
+__device__ __forceinline__ void ldf_w(const float* p, int64_t i, float (&f)[W]) {
+    if (W == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p + i);
+        f[0] = v.x; f[1 % W] = v.y; f[2 % W] = v.z; f[3 % W] = v.w;
+    } else {
+        f[0] = p[i];
+    }
+}
+template <int W>
+__device__ __forceinline__ void stf_w(float* p, int64_t i, const float (&f)[W]) {
+    if (W == 4) *reinterpret_cast<float4*>(p + i) = make_float4(f[0], f[1 % W], f[2 % W], f[3 % W]);
+    else p[i] = f[0];
+}
+
 // row / column means of f(i) over every [rows, cols] matrix of the tensor, folded into the running factors:
 //   row[b, r] = row * beta + (1 - beta) * mean_c f ,  col[b, c] = col * beta + (1 - beta) * mean_r f
-template <typename F>
+// f(i, out[W]) yields W consecutive elements of one row (W divides cols)
+template <int W, typename F>
 __device__ void factor_update(const Dims d, float* row, float* col, float beta, float omb, F f) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t cr = fo_crank(), cs = fo_csize();
@@ -92,25 +137,45 @@ __device__ void factor_update(const Dims d, float* row, float* col, float beta, 
     for (int64_t br = cr * FO_WARPS + warp; br < total_rows; br += cs * FO_WARPS) {   // one warp per row: coalesced, shuffle reduce
         const int64_t base = br * d.cols;
         float acc = 0.0f;
-        for (int c = lane; c < d.cols; c += 32) acc += f(base + c);
+        for (int c = lane * W; c < d.cols; c += 32 * W) {
+            float v[W];
+            f(base + c, v);
+#pragma unroll
+            for (int k = 0; k < W; ++k) acc += v[k];
+        }
         acc = warp_sum(acc);
         if (lane == 0) row[br] = __fmaf_rn(omb, acc / (float)d.cols, __fmul_rn(row[br], beta));
     }
-    const int64_t total_cols = (int64_t)d.batch * d.cols;
-    for (int64_t bc = cr * FO_THREADS + threadIdx.x; bc < total_cols; bc += cs * FO_THREADS) {   // one thread per column: coalesced across threads
-        const int64_t b = bc / d.cols, c = bc - b * d.cols;
+    const int cw = d.cols / W;                                                  // column groups per matrix
+    const int64_t total_groups = (int64_t)d.batch * cw;
+    for (int64_t bg = cr * FO_THREADS + threadIdx.x; bg < total_groups; bg += cs * FO_THREADS) {   // one thread per W columns
+        const int64_t b = bg / cw;
+        const int c = (int)(bg - b * cw) * W;
         const int64_t base = b * (int64_t)d.rows * d.cols + c;
-        float acc = 0.0f;
+        float acc[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc[k] = 0.0f;
         int r = 0;
-        for (; r + 8 <= d.rows; r += 8) {                                       // eight independent loads in flight, added in row order
-            float v[8];
+        for (; r + 4 <= d.rows; r += 4) {                                       // four independent loads in flight, added in row order
+            float v[4][W];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = f(base + (int64_t)(r + k) * d.cols);
+            for (int q = 0; q < 4; ++q) f(base + (int64_t)(r + q) * d.cols, v[q]);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc += v[k];
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int k = 0; k < W; ++k) acc[k] += v[q][k];
         }
-        for (; r < d.rows; ++r) acc += f(base + (int64_t)r * d.cols);
-        col[bc] = __fmaf_rn(omb, acc / (float)d.rows, __fmul_rn(col[bc], beta));
+        for (; r < d.rows; ++r) {
+            float v[W];
+            f(base + (int64_t)r * d.cols, v);
+#pragma unroll
+            for (int k = 0; k < W; ++k) acc[k] += v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const int64_t bc = b * d.cols + c + k;
+            col[bc] = __fmaf_rn(omb, acc[k] / (float)d.rows, __fmul_rn(col[bc], beta));
+        }
     }
 }
 
@@ -131,14 +196,19 @@ __device__ void row_means(const Dims d, const float* row, float* scratch, float*
     __syncthreads();
 }
 
-// _approx_sq_grad at element i: rsqrt(row / mean(row)) * rsqrt(col)
-__device__ __forceinline__ float approx_factor(const Dims d, const float* row, const float* col, const float* mean, int64_t i) {
-    const int64_t mat = (int64_t)d.rows * d.cols;
-    const int64_t b = i / mat, rem = i - b * mat;
-    const int64_t r = rem / d.cols, c = rem - r * d.cols;
-    const float rf = rsqrtf(row[b * d.rows + r] / mean[b]);
-    const float cf = rsqrtf(col[b * d.cols + c]);
-    return rf * cf;
+// _approx_sq_grad for the W consecutive elements starting at i (one row): rsqrt(row / mean(row)) * rsqrt(col).
+// 32-bit index arithmetic: every tensor is far below 2^31 elements (checked by the host), and a 64-bit division per
+// element was most of the instruction count of these loops.
+template <int W>
+__device__ __forceinline__ void approx_factor(const Dims d, const float* row, const float* col, const float* mean, int64_t i, float (&a)[W]) {
+    const uint32_t mat = (uint32_t)d.rows * (uint32_t)d.cols, ii = (uint32_t)i;
+    const uint32_t b = d.batch == 1 ? 0u : ii / mat, rem = ii - b * mat;
+    const uint32_t r = rem / (uint32_t)d.cols, c = rem - r * (uint32_t)d.cols;
+    const float rf = rsqrtf(row[(int64_t)b * d.rows + r] / mean[b]);
+    float cf[W];
+    ldf_w<W>(col, (int64_t)b * d.cols + c, cf);
+#pragma unroll
+    for (int k = 0; k < W; ++k) a[k] = rf * rsqrtf(cf[k]);
 }
 
 __device__ __forceinline__ uint32_t sr_rand16(uint64_t seed, uint64_t offset, uint64_t elem) {
@@ -152,20 +222,30 @@ __device__ __forceinline__ float stochastic_bf16(float x, uint32_t r16) {
     return __int_as_float((__float_as_int(x) + (int)r16) & (int)0xFFFF0000);
 }
 
-__global__ void __launch_bounds__(FO_THREADS)
-adafactor_multi_kernel(const otb_factored_tensor* __restrict__ tensors, float* __restrict__ scratch_all) {
-    __shared__ float red[FO_WARPS];
-    __shared__ float sh[2];
-    __shared__ float slot[2];
-    const otb_factored_tensor t = tensors[fo_cid()];
+// W = 4 needs: numel and cols multiples of 4 (a group never straddles a row), every pointer 16-byte aligned (8 for 16-bit p / g)
+__device__ __forceinline__ bool can_vec4(const otb_factored_tensor& t) {
+    const uintptr_t f32s = (uintptr_t)t.exp_avg | (uintptr_t)t.sq | (uintptr_t)t.sq_col | (uintptr_t)t.res_col;
+    const uintptr_t pg = (uintptr_t)t.p | (uintptr_t)t.g;
+    return (t.numel & 3) == 0 && (t.cols & 3) == 0 && (f32s & 15) == 0 && (pg & (t.p_dtype == OTB_F32 ? 15 : 7)) == 0 && t.numel < (int64_t)1 << 31;
+}
+
+struct FoShared { float* red; float* sh; float* slot; };
+
+template <int W>
+__device__ void adafactor_body(const otb_factored_tensor& t, float* scratch, const FoShared S) {
+    float* red = S.red; float* sh = S.sh; float* slot = S.slot;
     const Dims d{t.batch, t.rows, t.cols, t.numel};
-    const int64_t e0 = (int64_t)fo_crank() * FO_THREADS + threadIdx.x, estride = (int64_t)fo_csize() * FO_THREADS;
+    const int64_t e0 = ((int64_t)fo_crank() * FO_THREADS + threadIdx.x) * W, estride = (int64_t)fo_csize() * FO_THREADS * W;
     const bool factored = (t.flags & OTB_FACTORED_FACTORED) != 0, first = (t.flags & OTB_FACTORED_FIRST_MOMENT) != 0;
-    float* scratch = scratch_all + t.scratch_offset;
     const int pdt = t.p_dtype;
     // ---- A: RMS(p); second-moment state
     float acc = 0.0f;
-    for (int64_t i = e0; i < d.numel; i += estride) { const float p = ldf(t.p, i, pdt); acc += p * p; }
+    for (int64_t i = e0; i < d.numel; i += estride) {
+        float p[W];
+        ld_w<W>(t.p, i, pdt, p);
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc += p[k] * p[k];
+    }
     const float sum_p2 = cluster_sum(acc, red, &slot[0]);
     if (threadIdx.x == 0) {
         const float rms_p = sqrtf(sum_p2) / sqrtf((float)d.numel);          // _rms: norm(2) / numel ** 0.5
@@ -173,22 +253,46 @@ adafactor_multi_kernel(const otb_factored_tensor* __restrict__ tensors, float* _
         const float scale = (t.flags & OTB_FACTORED_SCALE_PARAMETER) ? fmaxf(t.eps1, rms_p) : 1.0f;
         sh[0] = scale * t.lr;                                                 // _get_lr: param_scale * rel_step_sz
     }
-    auto g2 = [&](int64_t i) { const float g = ldf(t.g, i, pdt); return __fmaf_rn(g, g, t.eps0); };
+    auto g2 = [&](int64_t i, float (&o)[W]) {
+        ld_w<W>(t.g, i, pdt, o);
+#pragma unroll
+        for (int k = 0; k < W; ++k) o[k] = __fmaf_rn(o[k], o[k], t.eps0);
+    };
     if (factored) {
-        factor_update(d, t.sq_row, t.sq_col, t.beta2, t.one_minus_beta2, g2);
+        factor_update<W>(d, t.sq_row, t.sq_col, t.beta2, t.one_minus_beta2, g2);
     } else {
         const float omb = t.one_minus_beta2;
-        for (int64_t i = e0; i < d.numel; i += estride) t.sq[i] = __fmaf_rn(omb, g2(i), __fmul_rn(t.sq[i], t.beta2));
+        for (int64_t i = e0; i < d.numel; i += estride) {
+            float q[W], s2[W];
+            g2(i, q);
+            ldf_w<W>(t.sq, i, s2);
+#pragma unroll
+            for (int k = 0; k < W; ++k) s2[k] = __fmaf_rn(omb, q[k], __fmul_rn(s2[k], t.beta2));
+            stf_w<W>(t.sq, i, s2);
+        }
     }
     phase_sync();                                 // the factors of every row / column are final, whichever CTA formed them
     // ---- B: RMS of the update
     if (factored) row_means(d, t.sq_row, scratch, red);
-    auto upd = [&](int64_t i) {
-        const float g = ldf(t.g, i, pdt);
-        return (factored ? approx_factor(d, t.sq_row, t.sq_col, scratch, i) : rsqrtf(t.sq[i])) * g;
+    auto upd = [&](int64_t i, float (&u)[W]) {
+        float g[W], a[W];
+        ld_w<W>(t.g, i, pdt, g);
+        if (factored) approx_factor<W>(d, t.sq_row, t.sq_col, scratch, i, a);
+        else {
+            ldf_w<W>(t.sq, i, a);
+#pragma unroll
+            for (int k = 0; k < W; ++k) a[k] = rsqrtf(a[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k) u[k] = a[k] * g[k];
     };
     acc = 0.0f;
-    for (int64_t i = e0; i < d.numel; i += estride) { const float u = upd(i); acc += u * u; }
+    for (int64_t i = e0; i < d.numel; i += estride) {
+        float u[W];
+        upd(i, u);
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc += u[k] * u[k];
+    }
     const float sum_u2 = cluster_sum(acc, red, &slot[1]);
     if (threadIdx.x == 0) sh[1] = fmaxf(sqrtf(sum_u2) / sqrtf((float)d.numel) / t.clip_threshold, 1.0f);
     __syncthreads();
@@ -196,16 +300,146 @@ adafactor_multi_kernel(const otb_factored_tensor* __restrict__ tensors, float* _
     const float wd_alpha = -t.weight_decay * lr_t;
     // ---- C: apply
     for (int64_t i = e0; i < d.numel; i += estride) {
-        float u = upd(i) / denom * lr_t;
+        float u[W], p[W];
+        upd(i, u);
+#pragma unroll
+        for (int k = 0; k < W; ++k) u[k] = u[k] / denom * lr_t;
         if (first) {
-            const float m = __fmaf_rn(t.one_minus_beta1, u, __fmul_rn(t.exp_avg[i], t.beta1));
-            t.exp_avg[i] = m;
-            u = m;
+            float m[W];
+            ldf_w<W>(t.exp_avg, i, m);
+#pragma unroll
+            for (int k = 0; k < W; ++k) { m[k] = __fmaf_rn(t.one_minus_beta1, u[k], __fmul_rn(m[k], t.beta1)); u[k] = m[k]; }
+            stf_w<W>(t.exp_avg, i, m);
         }
-        float p = ldf(t.p, i, pdt);
-        if (t.weight_decay != 0.0f) p = __fmaf_rn(wd_alpha, p, p);
-        p = p - u;
-        store_from_float(t.p, i, pdt, p);          // bf16: round to nearest — the reference overwrites its stochastic rounding (:88-91)
+        ld_w<W>(t.p, i, pdt, p);
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            if (t.weight_decay != 0.0f) p[k] = __fmaf_rn(wd_alpha, p[k], p[k]);
+            p[k] = p[k] - u[k];
+        }
+        st_w<W>(t.p, i, pdt, p);                   // bf16: round to nearest — the reference overwrites its stochastic rounding (:88-91)
+    }
+}
+
+__global__ void __launch_bounds__(FO_THREADS)
+adafactor_multi_kernel(const otb_factored_tensor* __restrict__ tensors, float* __restrict__ scratch_all) {
+    __shared__ float red[FO_WARPS];
+    __shared__ float sh[2];
+    __shared__ float slot[2];
+    const otb_factored_tensor t = tensors[fo_cid()];
+    const FoShared S{red, sh, slot};
+    if (can_vec4(t)) adafactor_body<4>(t, scratch_all + t.scratch_offset, S);      // block- (and cluster-) uniform
+    else adafactor_body<1>(t, scratch_all + t.scratch_offset, S);
+}
+
+template <int W>
+__device__ void came_body(const otb_factored_tensor& t, float* scratch, const FoShared S, uint64_t seed, uint64_t offset) {
+    float* red = S.red; float* sh = S.sh; float* slot = S.slot;
+    const Dims d{t.batch, t.rows, t.cols, t.numel};
+    const int64_t e0 = ((int64_t)fo_crank() * FO_THREADS + threadIdx.x) * W, estride = (int64_t)fo_csize() * FO_THREADS * W;
+    const bool factored = (t.flags & OTB_FACTORED_FACTORED) != 0;
+    const bool sr = (t.flags & OTB_FACTORED_SR) != 0 && t.p_dtype == OTB_BF16;
+    const int pdt = t.p_dtype;
+    // ---- RMS(p) is only recorded (state["RMS"], CAME.py:118)
+    if (t.rms_out) {
+        float a0 = 0.0f;
+        for (int64_t i = e0; i < d.numel; i += estride) {
+            float p[W];
+            ld_w<W>(t.p, i, pdt, p);
+#pragma unroll
+            for (int k = 0; k < W; ++k) a0 += p[k] * p[k];
+        }
+        const float s = cluster_sum(a0, red, &slot[0]);
+        if (threadIdx.x == 0 && fo_crank() == 0) *t.rms_out = sqrtf(s) / sqrtf((float)d.numel);
+    }
+    // ---- A: second moment
+    auto g2 = [&](int64_t i, float (&o)[W]) {
+        ld_w<W>(t.g, i, pdt, o);
+#pragma unroll
+        for (int k = 0; k < W; ++k) o[k] = __fmaf_rn(o[k], o[k], t.eps0);
+    };
+    if (factored) {
+        factor_update<W>(d, t.sq_row, t.sq_col, t.beta2, t.one_minus_beta2, g2);
+    } else {
+        const float omb = t.one_minus_beta2;
+        for (int64_t i = e0; i < d.numel; i += estride) {
+            float q[W], s2[W];
+            g2(i, q);
+            ldf_w<W>(t.sq, i, s2);
+#pragma unroll
+            for (int k = 0; k < W; ++k) s2[k] = __fmaf_rn(omb, q[k], __fmul_rn(s2[k], t.beta2));
+            stf_w<W>(t.sq, i, s2);
+        }
+    }
+    phase_sync();
+    // ---- B: RMS of the update
+    if (factored) row_means(d, t.sq_row, scratch, red);
+    auto upd = [&](int64_t i, float (&u)[W]) {
+        float g[W], a[W];
+        ld_w<W>(t.g, i, pdt, g);
+        if (factored) approx_factor<W>(d, t.sq_row, t.sq_col, scratch, i, a);
+        else {
+            ldf_w<W>(t.sq, i, a);
+#pragma unroll
+            for (int k = 0; k < W; ++k) a[k] = rsqrtf(a[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k) u[k] = a[k] * g[k];
+    };
+    float acc = 0.0f;
+    for (int64_t i = e0; i < d.numel; i += estride) {
+        float u[W];
+        upd(i, u);
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc += u[k] * u[k];
+    }
+    const float sum_u2 = cluster_sum(acc, red, &slot[1]);
+    if (threadIdx.x == 0) sh[0] = fmaxf(sqrtf(sum_u2) / sqrtf((float)d.numel) / t.clip_threshold, 1.0f);
+    __syncthreads();
+    const float denom = sh[0];
+    // ---- C: first moment; instability factors from (u-hat - m)^2 + eps1
+    for (int64_t i = e0; i < d.numel; i += estride) {
+        float u[W], m[W];
+        upd(i, u);
+        ldf_w<W>(t.exp_avg, i, m);
+#pragma unroll
+        for (int k = 0; k < W; ++k) m[k] = __fmaf_rn(t.one_minus_beta1, u[k] / denom, __fmul_rn(m[k], t.beta1));
+        stf_w<W>(t.exp_avg, i, m);
+    }
+    phase_sync();                                 // the row / column passes below read first moments other CTAs wrote
+    if (factored) {
+        auto res = [&](int64_t i, float (&o)[W]) {
+            float u[W], m[W];
+            upd(i, u);
+            ldf_w<W>(t.exp_avg, i, m);
+#pragma unroll
+            for (int k = 0; k < W; ++k) { const float e = u[k] / denom - m[k]; o[k] = __fmaf_rn(e, e, t.eps1); }
+        };
+        factor_update<W>(d, t.res_row, t.res_col, t.beta3, t.one_minus_beta3, res);
+        phase_sync();                             // (also: nobody overwrites scratch[] while a peer still forms u-hat with it)
+        row_means(d, t.res_row, scratch, red);
+    }
+    // ---- D: apply (CAME.py:160-176)
+    const float wd_alpha = -t.weight_decay * t.lr;
+    for (int64_t i = e0; i < d.numel; i += estride) {
+        float m[W], a[W], p[W];
+        ldf_w<W>(t.exp_avg, i, m);
+        if (factored) approx_factor<W>(d, t.res_row, t.res_col, scratch, i, a);
+        ld_w<W>(t.p, i, pdt, p);
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const float u = (factored ? a[k] * m[k] : m[k]) * t.lr;
+            float pk = p[k];
+            if (t.weight_decay != 0.0f) {
+                pk = __fmaf_rn(wd_alpha, pk, pk);                                // add_stochastic_(p, p, alpha): p.float() + alpha * p
+                if (sr) pk = stochastic_bf16(pk, sr_rand16(seed, offset, (uint64_t)(t.rng_base + i + k)));
+                else if (pdt == OTB_BF16) pk = round_bf16(pk);
+            }
+            pk = -u + pk;                                                        // add_stochastic_(p, -update)
+            if (sr) pk = stochastic_bf16(pk, sr_rand16(seed, offset + (t.weight_decay != 0.0f ? 1 : 0), (uint64_t)(t.rng_base + i + k)));
+            p[k] = pk;
+        }
+        st_w<W>(t.p, i, pdt, p);
     }
 }
 
@@ -215,65 +449,9 @@ came_multi_kernel(const otb_factored_tensor* __restrict__ tensors, float* __rest
     __shared__ float sh[1];
     __shared__ float slot[2];
     const otb_factored_tensor t = tensors[fo_cid()];
-    const Dims d{t.batch, t.rows, t.cols, t.numel};
-    const int64_t e0 = (int64_t)fo_crank() * FO_THREADS + threadIdx.x, estride = (int64_t)fo_csize() * FO_THREADS;
-    const bool factored = (t.flags & OTB_FACTORED_FACTORED) != 0;
-    const bool sr = (t.flags & OTB_FACTORED_SR) != 0 && t.p_dtype == OTB_BF16;
-    float* scratch = scratch_all + t.scratch_offset;
-    const int pdt = t.p_dtype;
-    // ---- RMS(p) is only recorded (state["RMS"], CAME.py:118)
-    if (t.rms_out) {
-        float a0 = 0.0f;
-        for (int64_t i = e0; i < d.numel; i += estride) { const float p = ldf(t.p, i, pdt); a0 += p * p; }
-        const float s = cluster_sum(a0, red, &slot[0]);
-        if (threadIdx.x == 0 && fo_crank() == 0) *t.rms_out = sqrtf(s) / sqrtf((float)d.numel);
-    }
-    // ---- A: second moment
-    auto g2 = [&](int64_t i) { const float g = ldf(t.g, i, pdt); return __fmaf_rn(g, g, t.eps0); };
-    if (factored) {
-        factor_update(d, t.sq_row, t.sq_col, t.beta2, t.one_minus_beta2, g2);
-    } else {
-        const float omb = t.one_minus_beta2;
-        for (int64_t i = e0; i < d.numel; i += estride) t.sq[i] = __fmaf_rn(omb, g2(i), __fmul_rn(t.sq[i], t.beta2));
-    }
-    phase_sync();
-    // ---- B: RMS of the update
-    if (factored) row_means(d, t.sq_row, scratch, red);
-    auto upd = [&](int64_t i) {
-        const float g = ldf(t.g, i, pdt);
-        return (factored ? approx_factor(d, t.sq_row, t.sq_col, scratch, i) : rsqrtf(t.sq[i])) * g;
-    };
-    float acc = 0.0f;
-    for (int64_t i = e0; i < d.numel; i += estride) { const float u = upd(i); acc += u * u; }
-    const float sum_u2 = cluster_sum(acc, red, &slot[1]);
-    if (threadIdx.x == 0) sh[0] = fmaxf(sqrtf(sum_u2) / sqrtf((float)d.numel) / t.clip_threshold, 1.0f);
-    __syncthreads();
-    const float denom = sh[0];
-    // ---- C: first moment; instability factors from (u-hat - m)^2 + eps1
-    for (int64_t i = e0; i < d.numel; i += estride)
-        t.exp_avg[i] = __fmaf_rn(t.one_minus_beta1, upd(i) / denom, __fmul_rn(t.exp_avg[i], t.beta1));
-    phase_sync();                                 // the row / column passes below read first moments other CTAs wrote
-    if (factored) {
-        auto res = [&](int64_t i) { const float e = upd(i) / denom - t.exp_avg[i]; return __fmaf_rn(e, e, t.eps1); };
-        factor_update(d, t.res_row, t.res_col, t.beta3, t.one_minus_beta3, res);
-        phase_sync();                             // (also: nobody overwrites scratch[] while a peer still forms u-hat with it)
-        row_means(d, t.res_row, scratch, red);
-    }
-    // ---- D: apply (CAME.py:160-176)
-    const float wd_alpha = -t.weight_decay * t.lr;
-    for (int64_t i = e0; i < d.numel; i += estride) {
-        const float m = t.exp_avg[i];
-        const float u = (factored ? approx_factor(d, t.res_row, t.res_col, scratch, i) * m : m) * t.lr;
-        float p = ldf(t.p, i, pdt);
-        if (t.weight_decay != 0.0f) {
-            p = __fmaf_rn(wd_alpha, p, p);                                   // add_stochastic_(p, p, alpha): p.float() + alpha * p
-            if (sr) p = stochastic_bf16(p, sr_rand16(seed, offset, (uint64_t)(t.rng_base + i)));
-            else if (pdt == OTB_BF16) p = round_bf16(p);
-        }
-        p = -u + p;                                                          // add_stochastic_(p, -update)
-        if (sr) p = stochastic_bf16(p, sr_rand16(seed, offset + (t.weight_decay != 0.0f ? 1 : 0), (uint64_t)(t.rng_base + i)));
-        store_from_float(t.p, i, pdt, p);
-    }
+    const FoShared S{red, sh, slot};
+    if (can_vec4(t)) came_body<4>(t, scratch_all + t.scratch_offset, S, seed, offset);
+    else came_body<1>(t, scratch_all + t.scratch_offset, S, seed, offset);
 }
 
 int check_launch(const otb_factored_launch* a) {

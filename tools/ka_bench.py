@@ -6,6 +6,8 @@ sys.path.insert(0, ".")
 from onetrainer_b200 import ops
 
 dev = torch.device("cuda:0")
+import os
+STATIC = bool(int(os.environ.get("KA_STATIC", "0")))      # tell K-a the weights are not written by the preceding launch
 FLUX = "flux" in sys.argv[1:]
 sys.argv = [a for a in sys.argv if a not in ("flux",)]
 tile_n = int(sys.argv[1]) if len(sys.argv) > 1 else 0
@@ -31,7 +33,7 @@ for name, M, N, K, cnt in shapes:
 
         def run():
             for i in range(nrep):
-                ops.lora_linear(xs[i & 1], ws[i], a, b, bias, 1 / 32, tile_n=tile_n, stages=stages)
+                ops.lora_linear(xs[i & 1], ws[i], a, b, bias, 1 / 32, tile_n=tile_n, stages=stages, static_weights=STATIC)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
