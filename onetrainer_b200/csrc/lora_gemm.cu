@@ -392,10 +392,20 @@ struct GemmParams3 {
     int pair_m_tiles;      // ceil(M / 256)
     int prefetch_w;        // weight tiles of the first k-blocks are fetched before griddepcontrol.wait (OTB_LINEAR_STATIC_WEIGHTS)
     int lookahead;         // k-blocks of tile i+1 issued before the rank-R MMAs of tile i (acc_stages == 2); 0 = right after tile i
+    int tail_reorder;      // single-accumulator two-chunk tiles: issue the last k-blocks chunk-major (OTB_KA_TAIL=0 switches it off)
+    unsigned long long* trace;   // bring-up only (OTB_KA_TRACE=<device address>): %globaltimer stamps of the first tile of clusters 0..7
     int debug;             // bring-up only (OTB_KA_DEBUG): bit 0 skip the TMA loads, bit 1 skip the MMAs, bit 2 skip the epilogue,
                            // bit 3 skip the TMA stores, bit 4 skip the accumulator loads, bit 5 skip the async-proxy fence
 };
 
+// bring-up timeline: event e of cluster `cid` (leader CTA, first tile) -> trace[cid * 16 + e], nanoseconds of %globaltimer
+__device__ __forceinline__ void ka_stamp(unsigned long long* trace, uint32_t cid, bool leader, int it, int e) {
+    if (trace != nullptr && leader && cid < 8 && it == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        trace[cid * 16 + e] = t;
+    }
+}
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
@@ -481,6 +491,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1)
 lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_constant__ GemmParams3<G> q) {
     const GemmParams& p = q.g;
     otb_pdl_trigger();                           // the next kernel in the stream may begin its own prologue
+    if (threadIdx.x == 0) ka_stamp(q.trace, cluster_id_x(), cluster_ctarank() == 0, 0, 0);      // 0: kernel entry
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -524,6 +535,7 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
     cluster_sync_relaxed();                     // the peer's barriers and TMEM exist before anything crosses CTAs
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    if (threadIdx.x == 0) ka_stamp(q.trace, cid, leader, 0, 1);                                  // 1: prologue done
     // Everything above overlapped the previous kernel's tail.  griddepcontrol.wait (its outputs are visible afterwards) is
     // issued per role: the producer first fetches the WEIGHT tiles of its first k-blocks when the caller vouches that the
     // preceding launch did not write them — the frozen base and the LoRA shadows come cold from HBM (~2 us to the first
@@ -585,6 +597,7 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
             __syncwarp();
         }
         otb_pdl_wait();
+        if (lane == 0) ka_stamp(q.trace, cid, leader, 0, 2);                                     // 2: previous launch complete
         for (uint32_t st = cid; st < (uint32_t)total_tiles; st += ncl, ++it) {
             const int mt = st / tiles_per_row, gm = (st % tiles_per_row) / p.n_tiles, nt = st % p.n_tiles;
             const int m0 = mt * 2 * BM + (int)crank * BM, n0 = nt * p.tile_n;
@@ -652,9 +665,19 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
                 const uint32_t d_tmem = tmem_base + as * acc_stride;
                 const int lookahead = p.num_kb < q.lookahead ? p.num_kb : q.lookahead;
                 if (pending >= 0 && lookahead == 0) { issue_up(pending); pending = -1; }
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                // One accumulator stage, two N-chunks (tiles wider than 224): nothing overlaps the rank-R hand-off of such a
+                // tile, so its LAST k-blocks are issued chunk-major — first the chunk that holds the `down` columns, then
+                // t_full, then the other chunk — and the epilogue converts T while the tensor pipe still works on the first
+                // chunk (tools/ka_trace.py: 0.9 us between "mainloop complete" and "accumulator complete" before)
+                int tail = 0;
+                if (lora && q.chunks == 2 && q.acc_stages == 1 && q.tail_reorder) {
+                    tail = p.stages - 1 < 3 ? p.stages - 1 : 3;
+                    if (tail > p.num_kb) tail = p.num_kb;
+                }
+                for (int kb = 0; kb < p.num_kb - tail; ++kb) {
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
+                    if (kb == 0 && lane == 0) ka_stamp(q.trace, cid, true, it, 3);               // 3: first operands landed
                     if (elect_one()) {
                         const uint32_t a16 = sb16 + stage16 * s, b16 = a16 + b16off;
                         if (!(q.debug & 2)) {
@@ -676,8 +699,38 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                     if (pending >= 0 && kb == lookahead - 1) { issue_up(pending); pending = -1; }
                 }
+                if (tail > 0) {
+                    const int s0 = s;
+                    auto slot = [&](int j) { const int v = s0 + j; return v >= p.stages ? v - p.stages : v; };
+                    for (int j = 0; j < tail; ++j) {                                         // every tail slot has landed
+                        mbar_wait(full_bar(s), ph);
+                        if (++s == p.stages) { s = 0; ph ^= 1; }
+                    }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const int kb0 = p.num_kb - tail;
+                        for (int j = 0; j < tail && !(q.debug & 2); ++j) {                   // the chunk with the `down` columns first
+                            const uint32_t a16 = sb16 + stage16 * slot(j), b16 = a16 + b16off;
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k)
+                                umma_bf16_2sm(d_tmem + nbc, umma_desc16(a16 + k * 2), umma_desc16(b16 + chunk16 + k * 2), idesc_main, ((kb0 + j) | k) != 0);
+                        }
+                        umma_commit_2sm(misc(4 + as));                                       // t_full: T is complete
+                        for (int j = 0; j < tail; ++j) {
+                            const uint32_t a16 = sb16 + stage16 * slot(j), b16 = a16 + b16off;
+                            if (!(q.debug & 2)) {
+#pragma unroll
+                                for (int k = 0; k < BK / UMMA_K; ++k)
+                                    umma_bf16_2sm(d_tmem, umma_desc16(a16 + k * 2), umma_desc16(b16 + k * 2), idesc_main, ((kb0 + j) | k) != 0);
+                            }
+                            umma_commit_2sm(empty_bar(slot(j)));
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) ka_stamp(q.trace, cid, true, it, 4);                              // 4: last k-block issued
                 if (lora) {
-                    if (elect_one()) umma_commit_2sm(misc(4 + as));                          // t_full
+                    if (tail == 0 && elect_one()) umma_commit_2sm(misc(4 + as));             // t_full
                     __syncwarp();
                     if (q.acc_stages == 2) pending = it; else issue_up(it);
                 } else {
@@ -725,6 +778,7 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
             if (lora) {
                 mbar_wait(misc(4 + as), par);                               // t_full
                 tc_fence_after();
+                if (warp == 2 && lane == 0) ka_stamp(q.trace, cid, leader, it, 5);      // 5: mainloop complete (t_full seen)
                 for (int c = half * 16; c < p.Rp; c += 32) {
                     uint32_t v[16];
                     tmem_ld16(t_lane + (uint32_t)(p.tile_n + c), v);
@@ -758,9 +812,11 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(t_ready_leader);         // t_ready: ONE remote arrival per warp (16 per pair, not 512)
+                if (warp == 2 && lane == 0) ka_stamp(q.trace, cid, leader, it, 6);      // 6: T parked
             }
             mbar_wait(misc(8 + as), par);                                   // d_full
             tc_fence_after();
+            if (warp == 2 && lane == 0) ka_stamp(q.trace, cid, leader, it, 7);          // 7: accumulator complete (d_full seen)
             for (int c0 = half * 64; c0 < p.tile_n; c0 += 128) {
                 const int nb0 = n0 + c0;
                 if (nb0 >= p.N || (q.debug & 4)) break;
@@ -859,12 +915,15 @@ lora_linear_kernel_v3(const __grid_constant__ V3Maps<G> maps, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(misc(10 + as), 0));  // acc_empty: one remote arrival per warp
+            if (warp == 2 && lane == 0) ka_stamp(q.trace, cid, leader, it, 8);          // 8: this warp's blocks packed and handed to TMA
         }
         if (lane == 0) bulk_wait<0>();            // every TMA store of this thread has been written before the CTA exits
+        if (warp == 2 && lane == 0) ka_stamp(q.trace, cid, leader, 0, 9);               // 9: stores written
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_relaxed();                     // neither CTA exits (or frees TMEM) while the pair still works
+    if (threadIdx.x == 0) ka_stamp(q.trace, cid, leader, 0, 10);                                 // 10: pair done
     if (warp == 1) {
         __syncwarp();
         tmem_dealloc_2sm(tmem_base, 512u);
@@ -1071,6 +1130,11 @@ int launch_v3(const otb_lora_linear_args* a, int count, void* stream, int tile_n
                   "pair tile_n %d invalid for rank %d (tile_n + rank a multiple of 16 (32 above 256), <= 512)", tile_n, p.Rp);
     q.debug = env_int("OTB_KA_DEBUG", 0);
     q.lookahead = env_int("OTB_KA_LOOKAHEAD", 2);
+    q.tail_reorder = env_int("OTB_KA_TAIL", 1);
+    {
+        const char* tr = getenv("OTB_KA_TRACE");
+        q.trace = tr ? (unsigned long long*)strtoull(tr, nullptr, 0) : nullptr;
+    }
     if (q.lookahead < 0) q.lookahead = 0;
     q.prefetch_w = 1;
     for (int g = 0; g < count; ++g)
