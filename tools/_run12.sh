@@ -1,0 +1,13 @@
+mkdir -p gpurun_out/r02o
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02o/bench_n2.json 2> gpurun_out/r02o/bench_n2.err; echo "bench n2 rc=$?"
+tail -c 1500 gpurun_out/r02o/bench_n2.err | grep -v Warning | tail -8
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29552 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r02o/bench_ref_n2.json 2> gpurun_out/r02o/bench_ref_n2.err; echo "ref n2 rc=$?"
+timeout 600 python -m pytest tests/test_gpu_exchange.py -m gpu -q 2>&1 | tail -2
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r02o/bench_n2.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'])
+print(d.get('exchange_check'))
+for c in d.get('configs',[]): print({k:c[k] for k in c if k in ('config','ms_per_step','steps_per_sec','exchange','error')})
+print(d.get('checkpointing',{}).get('ms_per_step'))
+PY
