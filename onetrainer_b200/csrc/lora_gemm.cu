@@ -419,25 +419,8 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
-// wait on an own barrier whose arrivals come from the peer CTA as well, with a cluster-scope acquire (kept for reference:
-// the MMA warp's two waits consume TMEM / async-proxy shared memory only and use the plain CTA-scope wait, as CUTLASS does)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0, spins = 0;
-    long long t0 = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) break;
-        if ((++spins & 1023u) == 0) {
-            long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > WAIT_LIMIT_CYCLES) __trap();
-        }
-    }
-}
+// (waits on barriers whose arrivals come from the peer CTA use the plain CTA-scope mbar_wait: what the waiter consumes
+// afterwards is TMEM or async-proxy shared memory, as in CUTLASS's ClusterBarrier::wait)
 // TMA load issued by either CTA of a pair; the bytes complete on `bar`, a shared::cluster address that may
 // live in the peer (leader) CTA
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {

@@ -572,8 +572,8 @@ class ShardedExchange:
         moved = (self.world - 1) / self.world * nbytes
         return {"mode": self.mode, "buckets": self.n_buckets, "arena_gb": nbytes / 1e9, "reduce_ms": red, "gather_ms": gat,
                 "reduce_gbs_in_per_gpu": moved / red / 1e6, "gather_gbs_out_per_gpu": moved / gat / 1e6,
-                "note": "reduce-scatter + squared norm / all-gather of the updated parameters, each timed alone with its barriers; "
-                        "in the step the reduce of a bucket overlaps the rest of backward"}
+                "note": "reduce-scatter + squared norm / all-gather of the updated parameters, each timed alone with its barriers; in the "
+                        "step " + ("the reduce of a bucket overlaps the rest of backward" if keep else "both run after backward / after the optimizer")}
 
     def gather(self) -> None:
         """After the optimizer step on the owned tensors: push my parameter ranges into every replica."""

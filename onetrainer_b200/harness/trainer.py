@@ -392,11 +392,15 @@ class GraphedTrainStep:
     the NCCL allreduce, grad-norm, AdamW and the shadow refresh are all inside the graph, on one stream.
     """
 
-    def __init__(self, setup: DiffusionSetup, model: StandInModel, config, example_batch: dict, warmup: int = 3):
+    def __init__(self, setup: DiffusionSetup, model: StandInModel, config, example_batch: dict, warmup: int = 3, *,
+                 pool=None, state=None, replay_after_capture: bool = True):
+        """`pool` / `state`: a graph memory pool and a DeviceStepState shared with other captures of the same model
+        (BucketedGraphedTrainStep: one capture per batch shape, never replayed concurrently).  `replay_after_capture=False`:
+        the capture itself takes no optimisation step (the host-side step counters it prepared are rolled back)."""
         from .. import step_state
         self.setup, self.model, self.config = setup, model, config
         dev = setup.train_device
-        self.state = step_state.DeviceStepState(dev)
+        self.state = state if state is not None else step_state.DeviceStepState(dev)
         self.host_batch = {k: ([torch.empty_like(t).pin_memory() for t in v] if isinstance(v, list) else torch.empty_like(v).pin_memory())
                            for k, v in example_batch.items()}
         self.dev_batch = {k: ([torch.empty_like(t, device=dev) for t in v] if isinstance(v, list) else torch.empty_like(v, device=dev))
@@ -424,13 +428,16 @@ class GraphedTrainStep:
         from .. import ops
         before = ops.LAUNCHES
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, pool=pool):
             self._device_part(first=False)
         self.launches_per_step = ops.LAUNCHES - before      # libotb200 kernels inside one replay
         # capture records but does not execute; the host side of this step (Philox keys, AdamW step counters and
         # bias corrections) has been prepared, so run it now — otherwise the step would be counted but never taken
-        self.graph.replay()
-        self._after_step()
+        if replay_after_capture:
+            self.graph.replay()
+            self._after_step()
+        else:
+            self.driver.host_rollback()
 
     # host-side work that must precede every replay
     def _host_part(self) -> None:
@@ -502,6 +509,8 @@ class GraphedTrainStep:
         """One optimisation step; returns the loss as a device scalar (read it with .item() when needed)."""
         if batch is not None:
             self.set_batch(batch)
+        from .. import step_state
+        step_state.activate(self.state)
         self._host_part()
         self.graph.replay()
         if self._replayed is None:
@@ -512,4 +521,49 @@ class GraphedTrainStep:
 
     def close(self) -> None:
         from .. import step_state
+        step_state.activate(None)
+
+
+class BucketedGraphedTrainStep:
+    """One captured step per BATCH SHAPE.  The reference trains aspect-ratio buckets — the latent height x width changes
+    from step to step (modules/dataLoader/mixin/DataLoaderText2ImageMixin.py: aspect bucketing) — and a CUDA graph is
+    bound to one shape.  The first batch of a shape is stepped eagerly once (that IS its optimisation step: it also
+    warms the shape-dependent library plans up) and the step is captured for the shapes's later batches; every capture
+    shares one graph memory pool (they never replay concurrently, so the activations of all buckets occupy the memory
+    of the largest one) and one DeviceStepState.  `max_graphs` bounds the cache (least recently used capture dropped)."""
+
+    def __init__(self, setup: DiffusionSetup, model: StandInModel, config, max_graphs: int = 16):
+        from .. import step_state
+        self.setup, self.model, self.config = setup, model, config
+        self.state = step_state.DeviceStepState(setup.train_device)
+        self.max_graphs = max_graphs
+        self._steps: dict[tuple, GraphedTrainStep] = {}
+        self._pool = None
+        self.captures = 0
+
+    @staticmethod
+    def shape_key(batch: dict) -> tuple:
+        return tuple(sorted((k, tuple(tuple(t.shape) for t in v) if isinstance(v, list) else tuple(v.shape)) for k, v in batch.items()))
+
+    def step(self, batch: dict) -> torch.Tensor:
+        key = self.shape_key(batch)
+        st = self._steps.pop(key, None)
+        if st is not None:
+            self._steps[key] = st                       # most recently used last
+            return st.step(batch)
+        while len(self._steps) >= self.max_graphs:
+            old = self._steps.pop(next(iter(self._steps)))
+            old.graph = None
+        # the eager step of this batch (warmup=1) + the capture; the capture itself takes no step
+        st = GraphedTrainStep(self.setup, self.model, self.config, batch, warmup=1, pool=self._pool, state=self.state,
+                              replay_after_capture=False)
+        if self._pool is None:
+            self._pool = st.graph.pool()
+        self._steps[key] = st
+        self.captures += 1
+        return st.loss
+
+    def close(self) -> None:
+        from .. import step_state
+        self._steps.clear()
         step_state.activate(None)

@@ -1,6 +1,6 @@
 """LoRA adapters on the B200 fused kernel — drop-in for the LoRA part of
 /root/reference/modules/module/LoRAModule.py (PeftBase :17-206, LoRAModule :283-331,
-LoRAModuleWrapper :427-587; DoRA/LoHa are outside SURVEY.md §8 and raise).
+LoRAModuleWrapper :427-587; DoRAModule :333-419 — SURVEY.md §8f rank 4 — on K-a with fused weight-space kernels; LoHa raises).
 
 Seam contract kept: `klass(prefix, orig_module, rank, alpha)`;
 `forward(x, *args, **kwargs)`; `hook_to_module()/remove_hook_from_module()` swapping the wrapped

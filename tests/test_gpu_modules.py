@@ -867,6 +867,38 @@ def test_graphed_step_matches_eager_for_lora_and_full_finetune(P, dev):
         P.trainer.GraphedTrainStep(setup, model, cfg, P.trainer.synthetic_batch("tiny", B, dev, latent_hw=32), warmup=3)
 
 
+def test_bucketed_graph_cache_follows_changing_batch_shapes(P, dev):
+    """Aspect-ratio buckets: the latent shape changes from step to step.  BucketedGraphedTrainStep steps the first batch of
+    a shape eagerly (once), captures that shape's step into a pool shared by all captures, and replays it for later
+    batches of the shape — the loss sequence equals the eager trainer's on the same batches, for the LoRA path and for
+    full fine-tuning (bit-identical weights there), and only two captures are taken for two shapes."""
+    B = 2
+    shapes = [32, 16, 32, 16, 16, 32, 32, 16]
+    batches = [P.trainer.synthetic_batch("tiny", B, dev, seed=100 + i, latent_hw=hw) for i, hw in enumerate(shapes)]
+    for full in (False, True):
+        def make():
+            cfg = P.TrainConfig(train_device=str(dev), batch_size=B, lora_rank=16, lora_alpha=8.0)
+            model, setup = P.trainer.build_model("tiny", cfg, dev, ema=full, stochastic_rounding=True, lora_up_std=0.05, lr=1e-3,
+                                                 full_finetune=full)
+            return cfg, model, setup
+        cfg, m_e, s_e = make()
+        eager = [P.trainer.train_step(s_e, m_e, P.trainer.batch_to_device(b, dev), cfg).item() for b in batches]
+        cfg, m_g, s_g = make()
+        g = P.trainer.BucketedGraphedTrainStep(s_g, m_g, cfg)
+        try:
+            graphed = [g.step(b).item() for b in batches]
+        finally:
+            g.close()
+        assert g.captures == 2
+        assert graphed == pytest.approx(eager, rel=2e-3 if not full else 1e-4), (full, eager, graphed)
+        assert m_g.train_progress.global_step == m_e.train_progress.global_step == len(batches)
+        if full:
+            assert _bit_equal_fraction(m_e.parameters, m_g.parameters) >= 0.999
+            steps_e = [float(m_e.optimizer.state[p]["step"]) for p in m_e.parameters[:3]]
+            steps_g = [float(m_g.optimizer.state[p]["step"]) for p in m_g.parameters[:3]]
+            assert steps_e == steps_g == [float(len(batches))] * 3
+
+
 def test_sibling_groups_batch_qkv_and_match_single_launches(P, dev, monkeypatch):
     """The wrapper batches the q/k/v projections of a self-attention and the k/v of a cross-attention into grouped
     launches (speculatively: the plugin seam is one forward per leaf).  Predictions and losses equal the ungrouped run
