@@ -355,11 +355,14 @@ class ShardedExchange:
         if mode == "p2p" and ws not in (2, 4, 8):
             mode = "nvls"
         self.mode, self.rank, self.world = mode, rk, ws
-        # measured on 2 B200s, C4 (profiles/r02e_logs): 1 GPU 142.0 ms/step; reduce after backward 145.5 ms; reduce per bucket
-        # DURING backward 149.6 ms (296 blocks), 155 / 172 / 235 ms with 32 / 16 / 8 blocks — a reduce fast enough to keep up
-        # takes the SMs backward needs, a small one is latency-bound on peer loads and ends up on the critical path.
-        # Off by default; OTB_KZ_OVERLAP=1 turns the per-bucket hand-shakes on.
-        self.overlap = (os.environ.get("OTB_KZ_OVERLAP", "0") != "0") if overlap is None else overlap
+        # Per-bucket reduce DURING backward (hooks) or all buckets after it?  Measured on C4, 142.0 ms/step on one GPU:
+        #   2 B200s, P2P  (profiles/r02e_logs): after backward 145.5 ms; during backward 149.6 ms (296 blocks), 155 / 172 / 235 ms
+        #                 with 32 / 16 / 8 blocks — peer loads need many SMs to keep up, and backward needs the same SMs;
+        #   8 B200s, NVLS (profiles/r02p_logs): after backward 151.8 ms; during backward 148.6 ms — the switch does the adds, the
+        #                 reduce is one request stream and disturbs backward less than it saves.
+        # Default: overlap in NVLS mode, not in P2P mode; OTB_KZ_OVERLAP=0|1 overrides.
+        env = os.environ.get("OTB_KZ_OVERLAP")
+        self.overlap = ((env != "0") if env is not None else mode == "nvls") if overlap is None else overlap
         self.parameters = list(parameters)
         offsets, total, bounds, first_param = self.plan([p.numel() for p in parameters], ws, n_buckets)
         self.param_flat = symmetric_zeros(total, dt, dev)

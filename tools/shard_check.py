@@ -31,6 +31,7 @@ for dt in (torch.bfloat16, torch.float32):
             continue
         g = torch.Generator(device=dev).manual_seed(100 + rank)
         ex.grad_flat.copy_((torch.randn(ex.grad_flat.shape, device=dev, generator=g) * 1e-3).to(dt))
+        src_grads = ex.grad_flat.clone()
         ref = ex.grad_flat.clone()
         dist.all_reduce(ref)                                   # the replicated form's exchange
         ex.arm()
@@ -39,18 +40,30 @@ for dt in (torch.bfloat16, torch.float32):
         mine = [(ex.bounds[b], ex.bounds[b + 1]) for b in range(ex.n_buckets) if ex.owner[b] == rank]
         note = ""
         if world == 2 and not (mode == "nvls" and dt == torch.bfloat16):
-            same = all(torch.equal(ex.grad_flat[lo:hi], ref[lo:hi]) for lo, hi in mine)
+            same = all(torch.equal(ex.grad_flat[lo:hi], ref[lo:hi]) for lo, hi in mine)          # a + b has one rounding
         else:
-            # more than two addends: NCCL's order / intermediate roundings differ from fp32 accumulation in rank order;
-            # NVLS bf16: the switch adds in its own arithmetic (multimem.ld_reduce.add.acc::f32.bf16x2) — bounded by 1 bf16 ulp
-            worst, frac = 0.0, 0.0
-            for lo, hi in mine:
-                a, b = ex.grad_flat[lo:hi].float(), ref[lo:hi].float()
-                ulp = torch.exp2(torch.floor(torch.log2(b.abs().clamp_min(1e-30))) - (7 if dt == torch.bfloat16 else 23))
-                worst = max(worst, float(((a - b).abs() / ulp).max())) if hi > lo else worst
-                frac = max(frac, float((a != b).float().mean())) if hi > lo else frac
-            same = worst <= (1.0 if dt == torch.bfloat16 else 4.0 * world)
-            note = f" (worst {worst:.2f} ulp, {frac * 100:.2f}% of elements differ from NCCL)"
+            # more than two addends: ncclAllReduce rounds its partial sums (bf16) / adds in its own order, K-z accumulates in
+            # fp32 in RANK ORDER and rounds once -> the exact expectation is an emulation of that, not NCCL's result.
+            # NVLS: the switch adds in its own order / arithmetic -> within 1 ulp (bf16) of the fp32 sum
+            parts = [torch.empty_like(src_grads) for _ in range(world)]
+            dist.all_gather(parts, src_grads)
+            acc = parts[0].float()
+            for r in range(1, world):
+                acc = acc + parts[r].float()
+            want = acc.to(dt)
+            if mode == "p2p":
+                same = all(torch.equal(ex.grad_flat[lo:hi], want[lo:hi]) for lo, hi in mine)
+                note = " (bit-equal to the fp32 rank-order sum rounded once)"
+            else:
+                worst = 0.0
+                for lo, hi in mine:
+                    if hi > lo:
+                        a, b = ex.grad_flat[lo:hi].float(), acc[lo:hi]
+                        scale = torch.stack([p[lo:hi].float().abs() for p in parts]).max(0).values.clamp_min(1e-30)     # the addends' magnitude
+                        ulp = torch.exp2(torch.floor(torch.log2(scale)) - (7 if dt == torch.bfloat16 else 23))
+                        worst = max(worst, float(((a - b).abs() / ulp).max()))
+                same = worst <= (2.0 if dt == torch.bfloat16 else float(world))
+                note = f" (worst {worst:.2f} ulp of the largest addend vs the fp32 sum)"
         owned_sum = torch.cat([ex.grad_flat[lo:hi].float() for lo, hi in mine]) if mine else torch.zeros(0, device=dev)
         sq = (owned_sum.double() * pre).pow(2).sum().reshape(1)
         dist.all_reduce(sq)
@@ -120,9 +133,13 @@ for clip in (None, 1.0):
             if clip is None and world == 2:
                 same = torch.equal(flat, ref_flat)
                 ema_same = all(torch.equal(v, ref_ema[i]) for i, v in ema.items())
-            else:       # the clip coefficient comes from a differently ordered (still deterministic) sum of the same squares
+            elif world == 2:    # the clip coefficient comes from a differently ordered (still deterministic) sum of the same squares
                 same = torch.allclose(flat, ref_flat, rtol=2 ** -6, atol=1e-6) and (flat != ref_flat).float().mean().item() < 0.05
                 ema_same = all(torch.allclose(v, ref_ema[i], rtol=2 ** -6, atol=1e-6) for i, v in ema.items())
+            else:               # > 2 ranks: NCCL's bf16 allreduce rounds partial sums, K-z rounds once -> bf16-level differences
+                same = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses)) < 5e-3 and \
+                    float((flat - ref_flat).norm() / ref_flat.norm()) < 2e-3
+                ema_same = all(float((v - ref_ema[i]).norm() / ref_ema[i].norm().clamp_min(1e-12)) < 2e-3 for i, v in ema.items())
             owned = len(m.optimizer_parameters)
             say(f"step clip={clip} graph={graph} overlap={overlap}: params_match_replicated={same} ema_match={ema_same} replicas_identical={replicas} "
                 f"losses {['%.5f' % x for x in losses]} vs {['%.5f' % x for x in ref_losses]} owned_tensors={owned}/{len(m.parameters)}")
