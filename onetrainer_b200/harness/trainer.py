@@ -393,10 +393,10 @@ class GraphedTrainStep:
     """
 
     def __init__(self, setup: DiffusionSetup, model: StandInModel, config, example_batch: dict, warmup: int = 3, *,
-                 pool=None, state=None, replay_after_capture: bool = True):
+                 pool=None, state=None):
         """`pool` / `state`: a graph memory pool and a DeviceStepState shared with other captures of the same model
-        (BucketedGraphedTrainStep: one capture per batch shape, never replayed concurrently).  `replay_after_capture=False`:
-        the capture itself takes no optimisation step (the host-side step counters it prepared are rolled back)."""
+        (BucketedGraphedTrainStep: one capture per batch shape, never replayed concurrently).  `warmup=0` captures straight
+        away — only after an eager step on this batch shape has initialised the shape-dependent library plans."""
         from .. import step_state
         self.setup, self.model, self.config = setup, model, config
         dev = setup.train_device
@@ -412,6 +412,16 @@ class GraphedTrainStep:
         self._replayed = None
         self.set_batch(example_batch)
         step_state.activate(self.state)
+        try:
+            self._warm_up_and_capture(warmup, pool)
+        except BaseException:
+            step_state.activate(None)            # a failed capture must not leave its device step state active
+            raise
+
+    def _warm_up_and_capture(self, warmup: int, pool) -> None:
+        from .. import step_state
+        dev = self.setup.train_device
+        model = self.model
         # warm-up on a side stream (allocator, lazy tables, cuBLAS/SDPA workspaces) as torch's capture rules require
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
@@ -433,11 +443,8 @@ class GraphedTrainStep:
         self.launches_per_step = ops.LAUNCHES - before      # libotb200 kernels inside one replay
         # capture records but does not execute; the host side of this step (Philox keys, AdamW step counters and
         # bias corrections) has been prepared, so run it now — otherwise the step would be counted but never taken
-        if replay_after_capture:
-            self.graph.replay()
-            self._after_step()
-        else:
-            self.driver.host_rollback()
+        self.graph.replay()
+        self._after_step()
 
     # host-side work that must precede every replay
     def _host_part(self) -> None:
@@ -527,10 +534,11 @@ class GraphedTrainStep:
 class BucketedGraphedTrainStep:
     """One captured step per BATCH SHAPE.  The reference trains aspect-ratio buckets — the latent height x width changes
     from step to step (modules/dataLoader/mixin/DataLoaderText2ImageMixin.py: aspect bucketing) — and a CUDA graph is
-    bound to one shape.  The first batch of a shape is stepped eagerly once (that IS its optimisation step: it also
-    warms the shape-dependent library plans up) and the step is captured for the shapes's later batches; every capture
-    shares one graph memory pool (they never replay concurrently, so the activations of all buckets occupy the memory
-    of the largest one) and one DeviceStepState.  `max_graphs` bounds the cache (least recently used capture dropped)."""
+    bound to one shape.  The first batch of a shape takes the eager step (which also initialises the shape-dependent
+    library plans); the second one captures the step for that shape and is stepped by the capture's first replay; later
+    ones replay.  Every batch is stepped exactly once.  All captures share one graph memory pool (they never replay
+    concurrently, so the activations of all buckets occupy the memory of the largest one) and one DeviceStepState.
+    `max_graphs` bounds the cache (least recently used capture dropped)."""
 
     def __init__(self, setup: DiffusionSetup, model: StandInModel, config, max_graphs: int = 16):
         from .. import step_state
@@ -538,25 +546,43 @@ class BucketedGraphedTrainStep:
         self.state = step_state.DeviceStepState(setup.train_device)
         self.max_graphs = max_graphs
         self._steps: dict[tuple, GraphedTrainStep] = {}
+        self._seen: set = set()
         self._pool = None
+        self._bucket = dp.GradientBucket(None)
+        self._side = None
         self.captures = 0
+        self.eager_steps = 0
 
     @staticmethod
     def shape_key(batch: dict) -> tuple:
         return tuple(sorted((k, tuple(tuple(t.shape) for t in v) if isinstance(v, list) else tuple(v.shape)) for k, v in batch.items()))
 
     def step(self, batch: dict) -> torch.Tensor:
+        from .. import step_state
         key = self.shape_key(batch)
         st = self._steps.pop(key, None)
         if st is not None:
             self._steps[key] = st                       # most recently used last
             return st.step(batch)
+        if key not in self._seen:                       # first batch of this shape: the eager step
+            self._seen.add(key)
+            step_state.activate(None)
+            self.eager_steps += 1
+            # on a side stream, like the warm-up steps of a capture: autograd remembers the stream a leaf's AccumulateGrad
+            # node first ran on, and a later capture must not be made to synchronise with the legacy default stream
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.setup.train_device)
+            cur = torch.cuda.current_stream(self.setup.train_device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                loss = train_step(self.setup, self.model, batch_to_device(batch, self.setup.train_device), self.config, self._bucket)
+            cur.wait_stream(self._side)
+            return loss
         while len(self._steps) >= self.max_graphs:
             old = self._steps.pop(next(iter(self._steps)))
             old.graph = None
-        # the eager step of this batch (warmup=1) + the capture; the capture itself takes no step
-        st = GraphedTrainStep(self.setup, self.model, self.config, batch, warmup=1, pool=self._pool, state=self.state,
-                              replay_after_capture=False)
+        # second batch of this shape: capture; the capture's first replay is this batch's step
+        st = GraphedTrainStep(self.setup, self.model, self.config, batch, warmup=0, pool=self._pool, state=self.state)
         if self._pool is None:
             self._pool = st.graph.pool()
         self._steps[key] = st

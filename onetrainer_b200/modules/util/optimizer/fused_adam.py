@@ -213,13 +213,6 @@ class FusedAdamDriver:
         self._last_active = active
         return True
 
-    def host_rollback(self) -> None:
-        """Undo the last host_prepare() whose device step will never run (a CUDA-graph capture records the step without
-        executing it): step counters and the stochastic-rounding stream position go back by one."""
-        if self.table is not None and getattr(self.table, "steps_flat", None) is not None:
-            self.table.steps_flat -= 1
-        self.step_count -= 1
-
     @torch.no_grad()
     def device_step(self, upload: bool = True) -> None:
         """The DEVICE side of `step()`: table upload, [grad-norm], fused clip+AdamW(+SR)(+EMA).  A captured step passes

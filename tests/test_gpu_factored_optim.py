@@ -152,3 +152,57 @@ def test_factored_optimizers_multi_tensor_equals_per_tensor_and_is_reproducible(
         w.grad = torch.randn_like(w) * 1e-2
         opt.step()
         assert not torch.equal(w, before) and hasattr(opt, "step_parameter")
+
+
+@pytest.mark.parametrize("kind", ["adafactor", "came"])
+def test_factored_optimizers_large_and_odd_tensors_vs_reference_on_gpu(dev, kind):
+    """The cluster path (8 CTAs per tensor, DSMEM sums) and both access widths against the UNMODIFIED reference optimizer
+    (baseline/_ref: patch_adafactor over transformers' Adafactor; the reference's CAME) running its ATen op sequence on the same
+    GPU: large matrices (> 128 k elements -> one cluster of 8 per tensor, 4-wide accesses), a matrix whose column count is not
+    a multiple of 4 (scalar accesses), a batch of small matrices, a vector.  fp32, three steps: parameters to 2e-5 relative
+    (reduction order differs), factored / first moments to 1e-4."""
+    from baseline import ref_arm
+    if not ref_arm.available():
+        pytest.skip("baseline/_ref did not travel")
+    ref_arm.load()
+    from transformers.optimization import Adafactor
+    shapes = [(1024, 640), (515, 333), (2560, 1280), (6, 96, 40), (3000,), (1280, 32)]
+
+    def make(reference: bool):
+        torch.manual_seed(11)
+        ps = [torch.nn.Parameter(torch.randn(*s, device=dev) * 0.05) for s in shapes]
+        if kind == "adafactor":
+            o = Adafactor(ps, lr=None, beta1=0.9, weight_decay=0.01, relative_step=True, scale_parameter=True, warmup_init=False)
+            if reference:
+                from modules.util.optimizer.adafactor_extensions import patch_adafactor as ref_patch
+                ref_patch(o, False)
+            else:
+                from onetrainer_b200.modules.util.optimizer.adafactor_extensions import patch_adafactor
+                patch_adafactor(o, False)
+        else:
+            if reference:
+                from modules.util.optimizer.CAME import CAME as RefCAME
+                o = RefCAME(ps, lr=1e-4, weight_decay=0.01, stochastic_rounding=False)
+            else:
+                from onetrainer_b200.modules.util.optimizer.CAME import CAME
+                o = CAME(ps, lr=1e-4, weight_decay=0.01, stochastic_rounding=False)
+        return ps, o
+
+    results = []
+    for reference in (True, False):
+        ps, o = make(reference)
+        gen = torch.Generator(device=dev).manual_seed(5)
+        for _ in range(3):
+            for p in ps:
+                p.grad = torch.randn(p.shape, device=dev, generator=gen) * 1e-2
+            o.step()
+        results.append((ps, o))
+    (rp, ro), (mp, mo) = results
+    for a, b, shape in zip(rp, mp, shapes):
+        torch.testing.assert_close(b.detach(), a.detach(), rtol=2e-5, atol=1e-7, msg=lambda m: f"{kind} {shape}: {m}")
+        sa, sb = ro.state[a], mo.state[b]
+        for key in ("exp_avg", "exp_avg_sq", "exp_avg_sq_row", "exp_avg_sq_col", "exp_avg_res_row", "exp_avg_res_col"):
+            if key in sa:
+                assert key in sb, (kind, shape, key)
+                torch.testing.assert_close(sb[key], sa[key].to(sb[key].dtype), rtol=1e-4, atol=1e-6 * float(sa[key].abs().max()),
+                                           msg=lambda m: f"{kind} {shape} {key}: {m}")

@@ -868,10 +868,12 @@ def test_graphed_step_matches_eager_for_lora_and_full_finetune(P, dev):
 
 
 def test_bucketed_graph_cache_follows_changing_batch_shapes(P, dev):
-    """Aspect-ratio buckets: the latent shape changes from step to step.  BucketedGraphedTrainStep steps the first batch of
-    a shape eagerly (once), captures that shape's step into a pool shared by all captures, and replays it for later
-    batches of the shape — the loss sequence equals the eager trainer's on the same batches, for the LoRA path and for
-    full fine-tuning (bit-identical weights there), and only two captures are taken for two shapes."""
+    """Aspect-ratio buckets: the latent shape changes from step to step.  BucketedGraphedTrainStep takes the eager step for
+    the first batch of a shape, captures that shape's step (into a pool shared by all captures) with the second one, and
+    replays it afterwards — every batch stepped exactly once, the loss sequence equals the eager trainer's on the same
+    batches, for the LoRA path and for full fine-tuning (bit-identical weights there); two captures for two shapes."""
+    from onetrainer_b200 import step_state
+    step_state.activate(None)
     B = 2
     shapes = [32, 16, 32, 16, 16, 32, 32, 16]
     batches = [P.trainer.synthetic_batch("tiny", B, dev, seed=100 + i, latent_hw=hw) for i, hw in enumerate(shapes)]
@@ -889,7 +891,7 @@ def test_bucketed_graph_cache_follows_changing_batch_shapes(P, dev):
             graphed = [g.step(b).item() for b in batches]
         finally:
             g.close()
-        assert g.captures == 2
+        assert g.captures == 2 and g.eager_steps == 2
         assert graphed == pytest.approx(eager, rel=2e-3 if not full else 1e-4), (full, eager, graphed)
         assert m_g.train_progress.global_step == m_e.train_progress.global_step == len(batches)
         if full:

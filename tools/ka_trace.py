@@ -21,7 +21,7 @@ traces = [torch.zeros(8 * 16, dtype=torch.int64, device=dev) for _ in range(nrep
 def run():
     for i in range(nrep):
         os.environ["OTB_KA_TRACE"] = hex(traces[i].data_ptr())
-        ops.lora_linear(xs[i & 1], ws[i], a, b, bias, 1 / 32, tile_n=tn)
+        ops.lora_linear(xs[i & 1], ws[i], a, b, bias, 1 / 32, tile_n=tn, static_weights=bool(int(os.environ.get('KA_STATIC', '0'))))
     os.environ.pop("OTB_KA_TRACE")
 
 
