@@ -364,9 +364,9 @@ def time_hbm_kernels(dev, hbm_peak: float) -> list:
 
 def profiled_traffic() -> tuple[float | None, str | None]:
     """DRAM bytes (read + write) of ONE launch of the dominant kernel from the committed `ncu --set full` summary
-    (newest profiles/r0*_ncu_ka_v3.md: M=4096, N=10240, K=1280, r=32) — per launch, not per step."""
+    (newest profiles/r0*_ncu_ka*.md: M=4096, N=10240, K=1280, r=32) — per launch, not per step."""
     import re
-    for name in ("r02_ncu_ka_v3.md", "r01b_ncu_ka_v3.md"):
+    for name in ("r02final_ncu_ka.md", "r02_ncu_ka.md", "r01b_ncu_ka_v3.md"):
         f = REPO / "profiles" / name
         if not f.exists():
             continue

@@ -36,6 +36,24 @@ def bench(M, N, K, R, tile_n, stages=0):
 
 
 os.environ["OTB_KA_VER"] = "3"
+if len(sys.argv) > 1 and sys.argv[1] == "tiles":
+    # tile-width sweep of every SDXL leaf shape class (after the epilogue fixes): does the planner still pick the best width?
+    shapes = [("c1280 qkvo", 4096, 1280, 1280), ("c1280 ff0 fwd", 4096, 10240, 1280), ("c1280 ff0 dX", 4096, 1280, 10240),
+              ("c1280 ff2 fwd", 4096, 1280, 5120), ("c1280 ff2 dX", 4096, 5120, 1280), ("c640 qkvo", 16384, 640, 640),
+              ("c640 ff0 fwd", 16384, 5120, 640), ("c640 ff0 dX", 16384, 640, 5120), ("c640 ff2 fwd", 16384, 640, 2560),
+              ("c640 ff2 dX", 16384, 2560, 640)]
+    for name, M, N, K in shapes:
+        fl = 2.0 * M * N * K + 2.0 * M * 32 * (K + N)
+        res = []
+        for tn in (0, 128, 160, 192, 208, 224, 288, 320, 352, 384, 416, 448, 480):
+            try:
+                res.append((tn, bench(M, N, K, 32, tn)))
+            except Exception as e:  # noqa: BLE001
+                pass
+        best = min(res[1:], key=lambda r: r[1])
+        print(f"{name} M={M} N={N} K={K}: auto {res[0][1]:.1f} us ({fl / res[0][1] / 1e6:.0f} TFLOP/s); best tile_n={best[0]} {best[1]:.1f} us; "
+              + " ".join(f"{tn}:{us:.1f}" for tn, us in res[1:]), flush=True)
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "epi":
     # where the output epilogue's time goes: TMA loads and MMAs off (debug 3), then pieces of the epilogue switched off
     for name, M, N, K, tn in [("c640 ff0 fwd", 16384, 5120, 640, 224), ("c640 ff0 fwd", 16384, 5120, 640, 192), ("c1280 ff0 fwd", 4096, 10240, 1280, 224)]:
