@@ -33,7 +33,7 @@ extern "C" {
 
 #define OTB_ABI_VERSION 5   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs.  3: otb_grad_exchange, otb_grad_norm_from_partials.
                                4: OTB_TS_TABLE (ts_cdf / ts_cdf_len appended to otb_noise_args); otb_lora_grad_batched; otb_lora_linear_grouped takes up to 32 members; otb_lora_linear_args.flags; otb_adafactor_multi / otb_came_multi; otb_dora_compose / otb_dora_backward.
-                               5: otb_shard_reduce / otb_shard_gather / otb_peer_barrier / otb_peer_signal / otb_peer_wait (K-z) */
+                               5: otb_shard_reduce / otb_shard_gather / otb_peer_barrier / otb_peer_signal / otb_peer_wait, otb_adamw_sr_ema_multi_peers (K-z) */
 
 /* error codes */
 #define OTB_OK            0
@@ -311,6 +311,18 @@ typedef struct otb_shard_exchange_args {
     int32_t   partial_slot;                 /* first index of this launch's partials in the table    */
     float     grad_prescale;                /* folded into the norm only; the arena holds the SUM    */
 } otb_shard_exchange_args;
+/* K-c with the all-gather folded in: otb_adamw_sr_ema_multi on the owner's tensors, every parameter store replicated into
+ * the other ranks' replicas of the symmetric parameter arena (P2P stores, or one multimem.st) — the step's updated
+ * parameters need no otb_shard_gather pass afterwards, only the closing otb_peer_barrier.  Every tensor's `p` must point
+ * into this rank's replica; OTB_FLAVOR_TORCH_CUDA only. */
+typedef struct otb_peer_store {
+    int64_t delta[OTB_MAX_RANKS];   /* byte offset from MY replica of the arena to rank i's mapping (0 for my own rank)   */
+    int64_t mc_delta;               /* NVLS: byte offset from my replica to the multicast mapping                         */
+    int32_t rank, world;
+    int32_t mode;                   /* OTB_EXCHANGE_*                                                                      */
+    int32_t reserved;
+} otb_peer_store;
+int otb_adamw_sr_ema_multi_peers(const otb_optim_launch* args, const otb_peer_store* peers, void* stream);
 int otb_shard_reduce(const otb_shard_exchange_args* args, void* stream);
 int otb_shard_gather(const otb_shard_exchange_args* args, void* stream);
 int otb_peer_barrier(uint32_t* const* peer_flags, int32_t rank, int32_t world, int32_t phase, void* stream);

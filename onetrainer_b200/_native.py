@@ -166,6 +166,10 @@ EXCHANGE_P2P, EXCHANGE_NVLS = 0, 1
 PEER_PHASES = 4          # include/otb200.h: OTB_PEER_PHASES
 
 
+class PeerStore(C.Structure):
+    _fields_ = [("delta", _i64 * MAX_RANKS), ("mc_delta", _i64), ("rank", _i32), ("world", _i32), ("mode", _i32), ("reserved", _i32)]
+
+
 class ShardExchangeArgs(C.Structure):
     _fields_ = [
         ("peer_base", _vp * MAX_RANKS), ("peer_partials", _vp * MAX_RANKS), ("mc_base", _vp), ("mc_partials", _vp),
@@ -186,6 +190,7 @@ SYMBOLS = {
     "otb_grad_scale_multi": (C.c_int, [C.POINTER(OptimLaunch), _vp, _vp]),
     "otb_grad_exchange_blocks": (C.c_int, [_i64, _i32]),
     "otb_grad_exchange": (C.c_int, [C.POINTER(GradExchangeArgs), _vp]),
+    "otb_adamw_sr_ema_multi_peers": (C.c_int, [C.POINTER(OptimLaunch), C.POINTER(PeerStore), _vp]),
     "otb_shard_reduce": (C.c_int, [C.POINTER(ShardExchangeArgs), _vp]),
     "otb_shard_gather": (C.c_int, [C.POINTER(ShardExchangeArgs), _vp]),
     "otb_peer_barrier": (C.c_int, [C.POINTER(_vp), _i32, _i32, _i32, _vp]),
@@ -209,7 +214,7 @@ SYMBOLS = {
     "otb_struct_sizes": (C.c_int, [C.POINTER(C.c_int32)]),
 }
 _STRUCTS = (OptimTensor, OptimLaunch, ShadowTensor, NoiseArgs, LossArgs, LoraLinearArgs, LoraGradArgs, GradExchangeArgs,
-            FactoredTensor, FactoredLaunch, DoraArgs, ShardExchangeArgs)
+            FactoredTensor, FactoredLaunch, DoraArgs, ShardExchangeArgs, PeerStore)
 
 _lib = None
 

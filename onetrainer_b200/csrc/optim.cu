@@ -183,9 +183,54 @@ __device__ __forceinline__ uint32_t sr_bits(const Philox4& r, int lane) {
     return (lane & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
-template <bool BF16, int FL>
+// ---- K-z: the updated parameters leave for the other replicas from the optimizer kernel itself (otb_peer_store): the
+// all-gather half of the sharded exchange rides on K-c's stores instead of being a second pass over the owner's range
+__device__ __forceinline__ void st_sys_u4(void* p, uint4 v) {
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_st_u4(void* mc, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(mc), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
+// 16 bytes at byte offset `off` of my replica -> every other replica
+__device__ __forceinline__ void peer_store16(const otb_peer_store& ps, void* mine, int64_t off, uint4 v) {
+    if (ps.mode == OTB_EXCHANGE_NVLS) {
+        multimem_st_u4((char*)mine + off + ps.mc_delta, v);
+    } else {
+        for (int r = 0; r < ps.world; ++r)
+            if (r != ps.rank) st_sys_u4((char*)mine + off + ps.delta[r], v);
+    }
+}
+template <bool BF16>
+__device__ __forceinline__ void peer_store8(const otb_peer_store& ps, void* base, int64_t i, const float (&f)[8]) {
+    if (BF16) {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = (__float_as_uint(f[2 * k]) >> 16) | (__float_as_uint(f[2 * k + 1]) & 0xFFFF0000u);
+        peer_store16(ps, base, i * 2, make_uint4(w[0], w[1], w[2], w[3]));
+    } else {
+        peer_store16(ps, base, i * 4, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+        peer_store16(ps, base, i * 4 + 16, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+    }
+}
+// scalar tail: plain peer stores in both modes (a multicast store needs 4-byte granularity at least)
+template <bool BF16>
+__device__ __forceinline__ void peer_store1(const otb_peer_store& ps, void* base, int64_t i, float v) {
+    for (int r = 0; r < ps.world; ++r) {
+        if (r == ps.rank) continue;
+        char* dst = (char*)base + ps.delta[r];
+        if (BF16) {
+            const uint16_t b = float_to_bf16_bits_rn(v);
+            asm volatile("st.relaxed.sys.global.u16 [%0], %1;" :: "l"((uint16_t*)dst + i), "h"(b) : "memory");
+        } else {
+            asm volatile("st.relaxed.sys.global.f32 [%0], %1;" :: "l"((float*)dst + i), "f"(v) : "memory");
+        }
+    }
+}
+
+template <bool BF16, int FL, bool PEERS = false>
 __device__ __forceinline__ void adam_chunk(const otb_optim_tensor& t, const OptScalars& s, int64_t start, int64_t end,
-                                           uint64_t seed, uint64_t offset) {
+                                           uint64_t seed, uint64_t offset, const otb_peer_store* ps = nullptr) {
     const bool has_ema = s.do_ema && t.ema != nullptr;
     const bool aligned = (t.flags & OPT_FLAG_ALIGNED16) != 0;
     int64_t vec_end = aligned ? start + ((end - start) & ~int64_t(7)) : start;
@@ -210,6 +255,7 @@ __device__ __forceinline__ void adam_chunk(const otb_optim_tensor& t, const OptS
             v[2 * k] = vv[0]; v[2 * k + 1] = vv[1]; e[2 * k] = ee[0]; e[2 * k + 1] = ee[1];
         }
         Pack8<BF16>::store(t.p, i, p);
+        if (PEERS) peer_store8<BF16>(*ps, t.p, i, p);
         Pack8<BF16>::store(t.exp_avg, i, m);
         Pack8<BF16>::store(t.exp_avg_sq, i, v);
         if (has_ema) Pack8<BF16>::store(t.ema, i, e);
@@ -233,6 +279,7 @@ __device__ __forceinline__ void adam_chunk(const otb_optim_tensor& t, const OptS
         }
         adam_pair<BF16, FL>(s, p, g, m, v, e, r16, has_ema);
         store_from_float(t.p, i, dt, p[0]);
+        if (PEERS) peer_store1<BF16>(*ps, t.p, i, p[0]);
         store_from_float(t.exp_avg, i, dt, m[0]);
         store_from_float(t.exp_avg_sq, i, dt, v[0]);
         if (has_ema) store_from_float(t.ema, i, dt, e[0]);
@@ -268,6 +315,32 @@ __global__ void __launch_bounds__(OPT_THREADS, 4) adamw_sr_ema_kernel(otb_optim_
         if (hot) adam_chunk<false, (int)OTB_FLAVOR_TORCH_CUDA>(t, s, start, end, a.seed, a.offset);
         else adam_chunk<false, -1>(t, s, start, end, a.seed, a.offset);
     }
+}
+
+// the same step with the parameter stores replicated into the peers' arenas (hot flavour only)
+__global__ void __launch_bounds__(OPT_THREADS, 4) adamw_sr_ema_peers_kernel(otb_optim_launch a, const otb_peer_store ps) {
+    if (a.dyn != nullptr) {
+        a.seed = a.dyn->seed; a.offset = a.dyn->offset;
+        a.ema_one_minus_decay = a.dyn->ema_one_minus_decay; a.do_ema = a.dyn->do_ema;
+    }
+    const int chunk = blockIdx.x;
+    const otb_optim_tensor t = a.tensors[a.chunk_tensor[chunk]];
+    const int64_t start = (int64_t)a.chunk_index[chunk] * a.chunk_elems;
+    int64_t end = start + a.chunk_elems;
+    if (end > t.numel) end = t.numel;
+    OptScalars s;
+    s.decay_mul = t.decay_mul; s.l2 = t.l2; s.lerp_w = t.lerp_w; s.beta2 = t.beta2; s.omb2 = t.one_minus_beta2;
+    s.bc2 = t.bc2_sqrt; s.inv_bc2 = t.inv_bc2_sqrt; s.eps = t.eps; s.nss = t.neg_step_size;
+    s.has_clip = a.clip_coef != nullptr;
+    s.clip = s.has_clip ? *a.clip_coef : 1.0f;
+    s.ema_omd = a.ema_one_minus_decay;
+    s.flavor = a.flavor;
+    s.sr = (t.flags & OPT_FLAG_SR) != 0;
+    s.maximize = (t.flags & OPT_FLAG_MAXIMIZE) != 0;
+    s.do_ema = a.do_ema != 0;
+    if (t.p_dtype == OTB_BF16) adam_chunk<true, (int)OTB_FLAVOR_TORCH_CUDA, true>(t, s, start, end, a.seed, a.offset, &ps);
+    else adam_chunk<false, (int)OTB_FLAVOR_TORCH_CUDA, true>(t, s, start, end, a.seed, a.offset, &ps);
+    __threadfence_system();                       // the peer stores are performed before the barrier that follows on the stream
 }
 
 // ------------------------------- EMA only -------------------------------------------
@@ -452,6 +525,21 @@ extern "C" int otb_adamw_sr_ema_multi(const otb_optim_launch* a, void* stream) {
     if (c) return c < 0 ? c : OTB_OK;
     adamw_sr_ema_kernel<<<a->n_chunks, OPT_THREADS, 0, (cudaStream_t)stream>>>(*a);
     OTB_LAUNCH_CHECK("adamw_sr_ema_kernel");
+    return OTB_OK;
+}
+
+extern "C" int otb_adamw_sr_ema_multi_peers(const otb_optim_launch* a, const otb_peer_store* ps, void* stream) {
+    OTB_CHECK_ARG(ps != nullptr, "null peer-store description");
+    OTB_CHECK_ARG(ps->world >= 2 && ps->world <= OTB_MAX_RANKS && ps->rank >= 0 && ps->rank < ps->world, "bad rank %d of %d", ps->rank, ps->world);
+    OTB_CHECK_ARG(ps->mode == OTB_EXCHANGE_P2P || ps->mode == OTB_EXCHANGE_NVLS, "unknown peer-store mode %d", ps->mode);
+    OTB_CHECK_ARG(ps->delta[ps->rank] == 0, "delta of the own rank must be 0");
+    for (int r = 0; r < ps->world; ++r) OTB_CHECK_ARG((ps->delta[r] & 15) == 0, "arena of rank %d is not 16-byte congruent with mine", r);
+    OTB_CHECK_ARG(ps->mode != OTB_EXCHANGE_NVLS || (ps->mc_delta != 0 && (ps->mc_delta & 15) == 0), "NVLS mode needs the multicast offset");
+    int c = check_launch(a);
+    if (c) return c < 0 ? c : OTB_OK;
+    OTB_UNSUPPORTED(a->flavor != OTB_FLAVOR_TORCH_CUDA, "the peer-store form of the optimizer step exists for OTB_FLAVOR_TORCH_CUDA only");
+    adamw_sr_ema_peers_kernel<<<a->n_chunks, OPT_THREADS, 0, (cudaStream_t)stream>>>(*a, *ps);
+    OTB_LAUNCH_CHECK("adamw_sr_ema_peers_kernel");
     return OTB_OK;
 }
 

@@ -414,6 +414,14 @@ class ShardedExchange:
                                                 **common)
         self._gather_args = N.ShardExchangeArgs(peer_base=peers(self.param_flat, handles[1]), peer_partials=(C.c_void_p * N.MAX_RANKS)(),
                                                 mc_base=multicast(self.param_flat, handles[1]), mc_partials=None, **common)
+        # K-c with the all-gather folded in (otb_adamw_sr_ema_multi_peers): byte offsets from my replica of the parameter arena
+        ps = N.PeerStore(rank=rk, world=ws, mode=N.EXCHANGE_NVLS if mode == "nvls" else N.EXCHANGE_P2P)
+        mine = handles[1].buffer_ptrs[rk]
+        for r in range(ws):
+            ps.delta[r] = handles[1].buffer_ptrs[r] - mine
+        ps.mc_delta = (handles[1].multicast_ptr - mine) if mode == "nvls" else 0
+        self.peer_store = ps if os.environ.get("OTB_KZ_FUSED_GATHER", "1") != "0" else None
+        self.gather_is_fused = False        # set by the owner of the optimizer once its driver carries `peer_store`
         self._flag_ptrs = peers(self.flags, handles[3])
         self._ready_ptrs = peers(self.ready, handles[4])
         self._my_ready = self.ready.data_ptr()
@@ -566,15 +574,19 @@ class ShardedExchange:
         def reduce():
             self.arm()
             self.finish()
+        fused = self.gather_is_fused
+        self.gather_is_fused = False                      # time the stand-alone gather kernel
         try:
             red, gat = timed(reduce), timed(self.gather)
         finally:
             self.overlap = keep
+            self.gather_is_fused = fused
         esz = self.grad_flat.element_size()
         nbytes = self.grad_flat.numel() * esz
         moved = (self.world - 1) / self.world * nbytes
         return {"mode": self.mode, "buckets": self.n_buckets, "arena_gb": nbytes / 1e9, "reduce_ms": red, "gather_ms": gat,
                 "reduce_gbs_in_per_gpu": moved / red / 1e6, "gather_gbs_out_per_gpu": moved / gat / 1e6,
+                "gather_folded_into_optimizer": fused,
                 "note": "reduce-scatter + squared norm / all-gather of the updated parameters, each timed alone with its barriers; in the "
                         "step " + ("the reduce of a bucket overlaps the rest of backward" if keep else "both run after backward / after the optimizer")}
 
@@ -583,11 +595,12 @@ class ShardedExchange:
         import ctypes as C
         from . import _native as N, ops
         a = self._gather_args
-        for b in range(self.n_buckets):
-            if self.owner[b] == self.rank:
-                a.begin, a.end, a.partial_slot = self.bounds[b], self.bounds[b + 1], 0
-                N.check(N.lib().otb_shard_gather(C.byref(a), ops._stream()), "otb_shard_gather")
-                ops._count(1)
+        if not self.gather_is_fused:                      # else: the optimizer launch already stored into every replica
+            for b in range(self.n_buckets):
+                if self.owner[b] == self.rank:
+                    a.begin, a.end, a.partial_slot = self.bounds[b], self.bounds[b + 1], 0
+                    N.check(N.lib().otb_shard_gather(C.byref(a), ops._stream()), "otb_shard_gather")
+                    ops._count(1)
         self._barrier(2)                                  # every replica is complete before the next forward reads it
         try:
             torch.autograd.graph.increment_version(self.parameters)

@@ -265,6 +265,9 @@ def build_model(kind: str, config, device, *, train_dtype=torch.bfloat16, lora_w
                     clip_grad_norm=config.clip_grad_norm if fused_clip else None)
         if isinstance(model.grad_reducer, dp.ShardedExchange):
             model.optimizer.otb_driver.rng_base_of = model.grad_reducer.rng_base_of
+            if model.grad_reducer.peer_store is not None:      # the all-gather rides on K-c's parameter stores
+                model.optimizer.otb_driver.peer_store = model.grad_reducer.peer_store
+                model.grad_reducer.gather_is_fused = True
         return model, DiffusionSetup(torch.device(device))
     GradArena.allocator = dp.symmetric_zeros if dp.peer_exchange_wanted() else None    # K-r needs a peer-mapped arena
     model.unet_lora = LoRAModuleWrapper(unet, "lora_unet", config, ["attentions"])

@@ -58,6 +58,7 @@ class FusedAdamDriver:
         self.norm_partials = None       # squared-norm partials of ALL active gradients, when the exchange kernel made them
         self.post_step_hooks = []       # e.g. LoRAModuleWrapper.refresh_shadows
         self.rng_base_of = None         # id(p) -> global element offset in the SR stream (dp.ShardedExchange), else table order
+        self.peer_store = None          # _native.PeerStore: replicate every parameter store into the peers' arenas (K-z)
         self.step_count = 0             # SR Philox offset (persisted as state_dict()["otb_sr_step_count"])
         self._sr_seed, self._sr_seed_src = None, None
         self.last_norm_coef: torch.Tensor | None = None
@@ -235,7 +236,8 @@ class FusedAdamDriver:
         seed, offset, omd, do_ema = self._dyn
         state = step_state.active()
         ops.adamw_sr_ema_multi(table, flavor=self.flavor, seed=seed, offset=offset, ema_one_minus_decay=omd, do_ema=do_ema,
-                               clip_coef=clip, dyn=state.dyn_ptr if state is not None else None)
+                               clip_coef=clip, dyn=state.dyn_ptr if state is not None else None,
+                               peer_store=self.peer_store if self.flavor == N.FLAVOR_TORCH_CUDA else None)
         _bump_versions([p for p, _ in self._last_active])
         for hook in self.post_step_hooks:
             hook()

@@ -578,9 +578,14 @@ def adam_scalars(lr: float, beta1: float, beta2: float, eps: float, weight_decay
         bc2_sqrt=f(bc2_sqrt), inv_bc2_sqrt=f(1.0 / bc2_sqrt), eps=f(eps), neg_step_size=f(-step_size))
 
 
-def adamw_sr_ema_multi(table: OptimTable, **kw) -> None:
+def adamw_sr_ema_multi(table: OptimTable, peer_store: "N.PeerStore | None" = None, **kw) -> None:
+    """`peer_store` (K-z, dp.ShardedExchange.peer_store): every parameter store also goes to the other ranks' replicas of the
+    symmetric parameter arena — the all-gather half of the sharded exchange folded into the optimizer launch."""
     a = table.launch_args(**kw)
-    N.check(N.lib().otb_adamw_sr_ema_multi(C.byref(a), _stream()), "otb_adamw_sr_ema_multi")
+    if peer_store is not None:
+        N.check(N.lib().otb_adamw_sr_ema_multi_peers(C.byref(a), C.byref(peer_store), _stream()), "otb_adamw_sr_ema_multi_peers")
+    else:
+        N.check(N.lib().otb_adamw_sr_ema_multi(C.byref(a), _stream()), "otb_adamw_sr_ema_multi")
     _count()
 
 
