@@ -360,9 +360,10 @@ class ShardedExchange:
         #                 with 32 / 16 / 8 blocks — peer loads need many SMs to keep up, and backward needs the same SMs;
         #   8 B200s, NVLS (profiles/r02p_logs): after backward 151.8 ms; during backward 148.6 ms — the switch does the adds, the
         #                 reduce is one request stream and disturbs backward less than it saves.
-        # Default: overlap in NVLS mode, not in P2P mode; OTB_KZ_OVERLAP=0|1 overrides.
+        #   4 B200s, NVLS (profiles/r02x_logs, r02y_logs): after backward 148.3 ms, during backward 150.0 ms (P2P after: 148.8 ms).
+        # Default: overlap from 8 ranks up in NVLS mode, otherwise reduce after backward; OTB_KZ_OVERLAP=0|1 overrides.
         env = os.environ.get("OTB_KZ_OVERLAP")
-        self.overlap = ((env != "0") if env is not None else mode == "nvls") if overlap is None else overlap
+        self.overlap = ((env != "0") if env is not None else (mode == "nvls" and ws >= 8)) if overlap is None else overlap
         self.parameters = list(parameters)
         offsets, total, bounds, first_param = self.plan([p.numel() for p in parameters], ws, n_buckets)
         self.param_flat = symmetric_zeros(total, dt, dev)
