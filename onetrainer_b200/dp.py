@@ -589,7 +589,9 @@ class ShardedExchange:
                 "reduce_gbs_in_per_gpu": moved / red / 1e6, "gather_gbs_out_per_gpu": moved / gat / 1e6,
                 "gather_folded_into_optimizer": fused,
                 "note": "reduce-scatter + squared norm / all-gather of the updated parameters, each timed alone with its barriers; in the "
-                        "step " + ("the reduce of a bucket overlaps the rest of backward" if keep else "both run after backward / after the optimizer")}
+                        "step " + ("the reduce of a bucket overlaps the rest of backward" if keep else "the reduce runs after backward")
+                        + ("; the gather is folded into the optimizer launch (its parameter stores go to every replica)" if fused
+                           else "; the gather runs after the optimizer")}
 
     def gather(self) -> None:
         """After the optimizer step on the owned tensors: push my parameter ranges into every replica."""
