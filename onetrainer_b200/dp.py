@@ -499,7 +499,6 @@ class ShardedExchange:
     def _handshake_and_reduce(self, b: int) -> None:
         """Per-bucket hand-shake (non-owners raise their word in the owner's table; the owner consumes them) and, on the
         owner, the reduce of the bucket.  Every rank runs this for every bucket in the same order."""
-        import ctypes as C
         from . import _native as N, ops
         lib = N.lib()
         own = self.owner[b]

@@ -6,7 +6,7 @@ import sys
 import torch
 import torch.distributed as dist
 sys.path.insert(0, ".")
-from onetrainer_b200 import dp, ops  # noqa: E402
+from onetrainer_b200 import dp  # noqa: E402
 
 rank, local, world = dp.init_from_env("nccl")
 dev = torch.device("cuda", local)
