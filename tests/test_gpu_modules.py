@@ -4,11 +4,21 @@ op sequence restated in plain torch on the same GPU."""
 import math
 
 import numpy as np
+import os
+
 import pytest
 import torch
 from torch import nn
 
 pytestmark = pytest.mark.gpu
+
+# the fp32 golden inputs of tests/golden/lora.npz are NOT bf16-representable, so the bf16 path carries 2^-9 of input rounding per
+# operand through K <= 216 products: measured worst error 0.54 % of the tensor's scale (OTB_TEST_VERBOSE=1 prints it).  The 2-ulp
+# bound of the north_star is held where it can be: on bf16-representable inputs (test_gpu_parity_fullsize.py, lora_bf16in.npz)
+TOL_SCALE = 0.0075
+# whole hooked network vs the torch restatement, both under bf16 autocast: measured 1.1e-4 on the loss, 0.8 % of scale on the worst gradient
+NET_LOSS_REL, NET_GRAD_REL = 1e-3, 0.015
+
 
 
 @pytest.fixture(scope="module")
@@ -67,7 +77,7 @@ class TorchLoRA(nn.Module):
 def test_lora_module_vs_reference_golden(P, dev, golden, name):
     """The reference's CPU fp32 forward/backward (config C1 arithmetic) vs the hooked fused module in bf16.
     Tolerance: inputs and weights are rounded to bf16 (2^-9 relative each) and the contraction runs over
-    K <= 216 terms: 2 bf16 ulp of the output magnitude + 1 % of the tensor's scale."""
+    K <= 216 terms: 2 bf16 ulp of the output magnitude + 0.75 % of the tensor's scale (TOL_SCALE above)."""
     g = golden("lora")
     x = torch.from_numpy(g[f"{name}_x"]).to(dev)
     w, bias = torch.from_numpy(g[f"{name}_w"]), g[f"{name}_bias"]
@@ -95,8 +105,11 @@ def test_lora_module_vs_reference_golden(P, dev, golden, name):
 
     def close(a, ref, what):
         ref = torch.from_numpy(ref).to(dev)
-        tol = ref.abs() * 2.0 ** -7 + 0.01 * ref.abs().max()
-        assert ((a.float() - ref).abs() <= tol).all(), f"{what}: max err {(a.float() - ref).abs().max().item()} vs scale {ref.abs().max().item()}"
+        tol = ref.abs() * 2.0 ** -7 + TOL_SCALE * ref.abs().max()
+        err = (a.float() - ref).abs()
+        if os.environ.get("OTB_TEST_VERBOSE"):
+            print(f"[{name}] {what}: worst err / max|ref| = {(err.max() / ref.abs().max()).item():.2e}, worst err / tol = {(err / tol).max().item():.3f}")
+        assert (err <= tol).all(), f"{what}: max err {err.max().item()} vs scale {ref.abs().max().item()}"
 
     close(y, g[f"{name}_y"], "y")
     close(dx, g[f"{name}_dx"], "dx")
@@ -174,8 +187,9 @@ def _inputs(dev, B=2, hw=16, seed=0):
 
 def test_wrapper_network_grads_vs_torch_restatement(P, dev):
     """A whole hooked network (24 leaves, attention dataflow) forward + backward: fused path vs the reference's
-    LoRA arithmetic in plain torch ops under the same bf16 autocast.  Loss within 1e-2 relative; every LoRA
-    gradient within 2 % of its tensor's scale (both paths carry bf16 rounding of every activation)."""
+    LoRA arithmetic in plain torch ops under the same bf16 autocast.  Loss within 1e-3 relative (the north_star's
+    tolerance); every LoRA gradient within 1.5 % of its tensor's scale (both paths carry bf16 rounding of every activation
+    through 24 leaves; the per-leaf 2-ulp bound on identical inputs is tests/test_gpu_parity_fullsize.py)."""
     cfg, net, wrap = _tiny(P, dev)
     x, t, ctx = _inputs(dev)
     assert len(wrap.lora_modules) == P.standin.count_lora_leaves(net, ["attentions"]) == 48
@@ -211,11 +225,18 @@ def test_wrapper_network_grads_vs_torch_restatement(P, dev):
         out_r = net(x, t, ctx).sample
         loss_r = (out_r.float() ** 2).mean()
     loss_r.backward()
-    assert loss.item() == pytest.approx(loss_r.item(), rel=1e-2)
+    worst = 0.0
     for k, ref in refs.items():
         for mine, r, what in ((fused[k][0], ref.A.grad, "dA"), (fused[k][1], ref.B.grad, "dB")):
             scale = r.abs().max().item()
-            assert (mine - r).abs().max().item() <= 0.02 * scale + 1e-7, f"{k} {what}: {(mine - r).abs().max().item()} vs scale {scale}"
+            worst = max(worst, (mine - r).abs().max().item() / max(scale, 1e-30))
+    if os.environ.get("OTB_TEST_VERBOSE"):
+        print(f"[wrapper network] loss rel diff {abs(loss.item() - loss_r.item()) / abs(loss_r.item()):.2e}, worst gradient err / scale {worst:.2e}")
+    assert loss.item() == pytest.approx(loss_r.item(), rel=NET_LOSS_REL)
+    for k, ref in refs.items():
+        for mine, r, what in ((fused[k][0], ref.A.grad, "dA"), (fused[k][1], ref.B.grad, "dB")):
+            scale = r.abs().max().item()
+            assert (mine - r).abs().max().item() <= NET_GRAD_REL * scale + 1e-7, f"{k} {what}: {(mine - r).abs().max().item()} vs scale {scale}"
 
 
 def test_lora_gradients_are_bit_reproducible(P, dev):
