@@ -18,6 +18,7 @@ pytestmark = pytest.mark.gpu
 TOL_SCALE = 0.0075
 # whole hooked network vs the torch restatement, both under bf16 autocast: measured 1.1e-4 on the loss, 0.8 % of scale on the worst gradient
 NET_LOSS_REL, NET_GRAD_REL = 1e-3, 0.015
+LOOP_LOSS_REL = 2e-3     # per-step loss of the 20-step training loops vs the torch twin: measured 3.9e-4 (SDXL-like) and 6.6e-5 (FLUX-like)
 
 
 
@@ -734,8 +735,10 @@ def test_training_loop_tracks_torch_restatement(P, dev):
         ref_opt.step()
         ref_opt.zero_grad(set_to_none=True)
         ref.append(rl.item())
+    if os.environ.get("OTB_TEST_VERBOSE"):
+        print(f"[20-step loop] worst per-step loss rel diff {max(abs(a - b) / abs(b) for a, b in zip(mine, ref)):.2e}")
     for a, b in zip(mine, ref):
-        assert a == pytest.approx(b, rel=2e-2), (mine, ref)
+        assert a == pytest.approx(b, rel=LOOP_LOSS_REL), (mine, ref)
     assert np.mean(mine[-5:]) < np.mean(mine[:5]) and np.mean(ref[-5:]) < np.mean(ref[:5])
 
 
@@ -811,8 +814,10 @@ def test_flux_training_loop_tracks_torch_restatement(P, dev):
         ref_opt.step()
         ref_opt.zero_grad(set_to_none=True)
         ref.append(rl.item())
+    if os.environ.get("OTB_TEST_VERBOSE"):
+        print(f"[20-step loop] worst per-step loss rel diff {max(abs(a - b) / abs(b) for a, b in zip(mine, ref)):.2e}")
     for a, b in zip(mine, ref):
-        assert a == pytest.approx(b, rel=2e-2), (mine, ref)
+        assert a == pytest.approx(b, rel=LOOP_LOSS_REL), (mine, ref)
     assert np.mean(mine[-4:]) < np.mean(mine[:4]) and np.mean(ref[-4:]) < np.mean(ref[:4])
 
 
