@@ -104,6 +104,31 @@ def test_restated_callers_equal_the_unmodified_callers_on_cpu(kind, ptype):
         assert data["prediction_type"] == data_r["prediction_type"] == ptype
 
 
+@needs_ref
+def test_dropin_arm_executes_the_same_caller_files_with_only_the_seams_redirected():
+    """Host logic of the drop-in arm (no GPU): the three family-caller source files are executed a second time from the very
+    same paths, the four seam mixins in their MRO come from onetrainer_b200, everything else in the MRO (BaseModelSetup, the
+    debug / embedding mixins) is still the reference's, and the reference arm itself stays untouched by the redirection."""
+    from baseline import ref_callers
+    ref = ref_callers.load(dropin=False)
+    own = ref_callers.load(dropin=True)
+    assert own.caller_files == ref.caller_files and all("baseline/_ref/modules/modelSetup/Base" in f for f in own.caller_files.values())
+    seams = {n.rsplit(".", 1)[-1] for n in ref_callers.SEAM_MODULES}
+    for ns_ in (own.SDXLSetup, own.SDSetup, own.FluxSetup):
+        owners = {c.__name__: c.__module__ for c in ns_.__mro__ if c.__name__.startswith("ModelSetup")}
+        assert {k for k, m in owners.items() if m.startswith("onetrainer_b200.")} == set(owners) & seams, owners
+        assert any(c.__module__ == "modules.modelSetup.BaseModelSetup" for c in ns_.__mro__)
+    for ns_ in (ref.SDXLSetup, ref.SDSetup, ref.FluxSetup):
+        assert all(c.__module__.startswith("modules.") for c in ns_.__mro__ if c.__name__.startswith("ModelSetup"))
+    # the predict() / calculate_loss() the two arms run are the same functions' source
+    import inspect
+    for a, b in ((own.SDXLSetup, ref.SDXLSetup), (own.SDSetup, ref.SDSetup), (own.FluxSetup, ref.FluxSetup)):
+        assert inspect.getsource(a.predict) == inspect.getsource(b.predict)
+        assert inspect.getsource(a.calculate_loss) == inspect.getsource(b.calculate_loss)
+    import sys
+    assert sys.modules["modules.modelSetup.mixin.ModelSetupNoiseMixin"].__file__.endswith("baseline/_ref/modules/modelSetup/mixin/ModelSetupNoiseMixin.py")
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _run_dropin_vs_reference(dev, kind, B, rank, cfg_kw, ptype="epsilon", latent_hw=None, masked=False):
     from baseline import ref_arm, ref_callers
