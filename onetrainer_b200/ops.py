@@ -73,18 +73,27 @@ class GradQueue:
         import os
         self.FLUSH_LEAVES = max(1, int(os.environ.get("OTB_GRAD_BATCH", self.FLUSH_LEAVES)))
         self._pending: dict[int, list] = {}
+        self._task: dict[int, int] = {}       # device -> id of the backward pass whose end-of-pass flush covers `_pending`
 
     def push(self, leaf: tuple, device: torch.device) -> None:
         """leaf = (x, dy, gs, ts, dA, dB); launched at the latest when the current backward pass ends."""
-        if self.FLUSH_LEAVES == 1 or torch._C._current_graph_task_id() < 0:
+        task = torch._C._current_graph_task_id()
+        if self.FLUSH_LEAVES == 1 or task < 0:
             lora_grad_batched([leaf])           # outside a backward pass nobody would flush the queue
             return
         idx = device.index if device.index is not None else torch.cuda.current_device()
         held = self._pending.setdefault(idx, [])
+        if held and self._task.get(idx) != task:
+            # leaves of ANOTHER backward pass are still queued: that pass raised before its end-of-pass callback ran (the
+            # engine drops the callbacks of a failed pass), or it is the outer pass of a re-entrant backward.  Launch them
+            # now — their operands are still referenced — so that this pass's callback only ever covers its own leaves
+            # and nothing stays queued past the pass that registered for it.
+            self.flush(idx)
+            held = self._pending[idx]
         held.append(leaf)
         if len(held) == 1:
-            # first pending leaf since the last flush: make sure this backward pass ends with one (registered per flush on
-            # purpose — a backward that raises never runs its callbacks and must not leave a flag behind)
+            # first pending leaf of this pass since the last flush: make sure the pass ends with one
+            self._task[idx] = task
             torch.autograd.Variable._execution_engine.queue_callback(self.flush_all)
         if len(held) >= self.FLUSH_LEAVES:
             self.flush(idx)

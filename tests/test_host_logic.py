@@ -431,3 +431,77 @@ def test_sharded_exchange_plan_is_contiguous_tensor_aligned_and_balanced():
     # fewer tensors than buckets asked for: never an empty bucket
     offsets, total, bounds, first = dp.ShardedExchange.plan([100, 200, 300], 2, n_buckets=8)
     assert len(bounds) - 1 <= 3 and all(a < b for a, b in zip(bounds, bounds[1:]))
+
+
+def test_grad_queue_never_carries_leaves_past_the_pass_that_queued_them(monkeypatch):
+    """ops.GradQueue (K-a' host logic): every queued dA/dB contraction is launched by the end of the backward pass that queued
+    it — also when an EARLIER pass raised after queueing (the engine drops a failed pass's callbacks), and when a re-entrant
+    backward runs inside another.  The launches are recorded instead of executed (no GPU here)."""
+    import contextlib
+    from onetrainer_b200 import ops
+    launched = []
+    monkeypatch.setattr(ops, "lora_grad_batched", lambda leaves: launched.extend(leaves))
+    monkeypatch.setattr(torch.cuda, "device", lambda idx: contextlib.nullcontext())
+    q = ops.GradQueue()
+    dev = torch.device("cuda", 0)
+
+    class Leaf(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, tag, boom):
+            ctx.tag, ctx.boom = tag, boom
+            return x * 1.0
+
+        @staticmethod
+        def backward(ctx, g):
+            q.push((ctx.tag,), dev)
+            if ctx.boom:
+                raise RuntimeError("boom")
+            return g, None, None
+
+    def chain(tags, boom_at=None):
+        x = torch.ones(3, requires_grad=True)
+        y = x
+        for t in tags:
+            y = Leaf.apply(y, t, t == boom_at)
+        return x, y.sum()
+
+    # outside a backward pass: launched at once
+    q.push(("eager",), dev)
+    assert launched == [("eager",)]
+    launched.clear()
+    # a pass that raises after queueing two leaves: nothing was flushed by it ...
+    _, loss = chain(["a3", "a2", "a1"], boom_at="a2")
+    with pytest.raises(RuntimeError, match="boom"):
+        loss.backward()
+    assert launched == [] and len(q._pending[0]) == 2
+    # ... the next pass launches the stale leaves first and still ends with its own flush
+    _, loss = chain(["b2", "b1"])
+    loss.backward()
+    assert [t[0] for t in launched] == ["a1", "a2", "b1", "b2"] and q._pending[0] == []
+    launched.clear()
+    # a full batch flushes by itself, the remainder at the end of the pass
+    q.FLUSH_LEAVES = 2
+    _, loss = chain(["c3", "c2", "c1"])
+    loss.backward()
+    assert [t[0] for t in launched] == ["c1", "c2", "c3"] and q._pending[0] == []
+    launched.clear()
+    q.FLUSH_LEAVES = 96
+
+    # re-entrant backward inside a backward pass: the inner pass flushes the outer pass's queued leaf and its own
+    class Nested(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            return x * 1.0
+
+        @staticmethod
+        def backward(ctx, g):
+            with torch.enable_grad():
+                _, inner = chain(["inner"])
+            inner.backward()
+            assert [t[0] for t in launched] == ["outer1", "inner"]
+            return g
+
+    x = torch.ones(3, requires_grad=True)
+    y = Leaf.apply(Nested.apply(Leaf.apply(x, "outer2", False)), "outer1", False)
+    y.sum().backward()
+    assert [t[0] for t in launched] == ["outer1", "inner", "outer2"] and q._pending[0] == []
