@@ -31,9 +31,10 @@
 extern "C" {
 #endif
 
-#define OTB_ABI_VERSION 5   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs.  3: otb_grad_exchange, otb_grad_norm_from_partials.
+#define OTB_ABI_VERSION 6   /* 2: otb_lora_linear_grouped; pack_w / pred_pack_w appended to the noise / loss argument structs.  3: otb_grad_exchange, otb_grad_norm_from_partials.
                                4: OTB_TS_TABLE (ts_cdf / ts_cdf_len appended to otb_noise_args); otb_lora_grad_batched; otb_lora_linear_grouped takes up to 32 members; otb_lora_linear_args.flags; otb_adafactor_multi / otb_came_multi; otb_dora_compose / otb_dora_backward.
-                               5: otb_shard_reduce / otb_shard_gather / otb_peer_barrier / otb_peer_signal / otb_peer_wait, otb_adamw_sr_ema_multi_peers (K-z) */
+                               5: otb_shard_reduce / otb_shard_gather / otb_peer_barrier / otb_peer_signal / otb_peer_wait, otb_adamw_sr_ema_multi_peers (K-z)
+                               6: otb_stochastic_round (the helpers of bf16_stochastic_rounding.py as stand-alone launches) */
 
 /* error codes */
 #define OTB_OK            0
@@ -551,12 +552,44 @@ int otb_lora_grad_batched(const otb_lora_grad_args* leaves, int32_t count, void*
                           int32_t chained, void* stream);
 int64_t otb_lora_grad_workspace_bytes(const otb_lora_grad_args* leaves, int32_t count);
 
+/* ------------------------------------------------------------------------------------
+ * The reference's bf16 stochastic-rounding helpers as stand-alone launches — what an optimizer of the reference that is
+ * NOT fused here (it imports these three functions) calls per tensor.
+ * Replaces: copy_stochastic_      modules/util/bf16_stochastic_rounding.py:5-30
+ *           add_stochastic_       modules/util/bf16_stochastic_rounding.py:33-45   (call sites CAME.py:167-176)
+ *           addcdiv_stochastic_   modules/util/bf16_stochastic_rounding.py:48-61   (call site adamw_extensions.py:139-144)
+ * One launch instead of 5-7, no fp32 / int32 temporaries:
+ *   COPY     r = src (fp32)
+ *   ADD      r = fp32(src) + alpha * fp32(target)        — alpha multiplies `target` (= the reference's `input`): the
+ *            reference computes `result = other.float(); result.add_(input, alpha=alpha)`, whatever its docstring says
+ *   ADDCDIV  r = fp32(target) + alpha * src / src2       — rounded as the `flavor` bits say (OTB_FLAVOR_FMA_ADD_ALPHA,
+ *            OTB_FLAVOR_ADDCDIV_MUL_LAST, OTB_FLAVOR_FMA_ADDCDIV: torch's CPU and CUDA kernels differ, see above)
+ * then target = high half of (int32(r) + 16 random bits) — element i draws the bits of element rng_base + i of the
+ * OTB_STREAM_SR Philox stream keyed by (seed, offset), the assignment K-c uses.  `src` / `src2` may alias `target`.
+ * ---------------------------------------------------------------------------------- */
+#define OTB_SR_COPY    0
+#define OTB_SR_ADD     1
+#define OTB_SR_ADDCDIV 2
+typedef struct otb_sr_args {
+    void*       target;      /* bf16 [n]: read by ADD / ADDCDIV, always written                   */
+    const void* src;         /* COPY: fp32 source; ADD: `other`; ADDCDIV: tensor1                 */
+    const void* src2;        /* ADDCDIV: tensor2 (same dtype as src), else NULL                   */
+    int64_t     n;
+    int64_t     rng_base;    /* position of target[0] in the SR stream; a multiple of 8           */
+    uint64_t    seed, offset;
+    int32_t     mode;        /* OTB_SR_*                                                          */
+    int32_t     src_dtype;   /* OTB_F32 | OTB_BF16 (COPY: OTB_F32)                                */
+    float       alpha;       /* ADD: alpha; ADDCDIV: value                                        */
+    uint32_t    flavor;      /* OTB_FLAVOR_* bits                                                 */
+} otb_sr_args;
+int otb_stochastic_round(const otb_sr_args* args, void* stream);
+
 /* Utility used by tests and the data-parallel bucket path: fp32 <-> bf16 casts with
  * round-to-nearest-even, and a device-side Philox dump for known-answer tests. */
 /* sizeof() of every argument struct, in declaration order: optim_tensor, optim_launch, shadow_tensor,
- * noise_args, loss_args, lora_linear_args, lora_grad_args, grad_exchange_args, factored_tensor, factored_launch, dora_args.
- * Bindings assert these at load time. */
-int otb_struct_sizes(int32_t* out11);
+ * noise_args, loss_args, lora_linear_args, lora_grad_args, grad_exchange_args, factored_tensor, factored_launch, dora_args,
+ * shard_exchange_args, peer_store, sr_args.  Bindings assert these at load time. */
+int otb_struct_sizes(int32_t* out14);
 
 int otb_philox_dump(uint64_t seed, uint64_t offset, uint32_t stream_id, int64_t first_group,
                     int64_t n_groups, uint32_t* out4, void* stream);

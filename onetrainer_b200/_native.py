@@ -12,7 +12,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "libotb200.so"
 
 # ---- enums (include/otb200.h) ---------------------------------------------------------
-ABI_VERSION = 5          # include/otb200.h: OTB_ABI_VERSION
+ABI_VERSION = 6          # include/otb200.h: OTB_ABI_VERSION
 OTB_OK, OTB_EINVAL, OTB_EUNSUPPORTED, OTB_ECUDA, OTB_EARCH = 0, -1, -2, -3, -4
 F32, BF16, F16 = 0, 1, 2
 
@@ -163,11 +163,17 @@ class GradExchangeArgs(C.Structure):
 
 
 EXCHANGE_P2P, EXCHANGE_NVLS = 0, 1
+SR_COPY, SR_ADD, SR_ADDCDIV = 0, 1, 2        # OTB_SR_*
 PEER_PHASES = 4          # include/otb200.h: OTB_PEER_PHASES
 
 
 class PeerStore(C.Structure):
     _fields_ = [("delta", _i64 * MAX_RANKS), ("mc_delta", _i64), ("rank", _i32), ("world", _i32), ("mode", _i32), ("reserved", _i32)]
+
+
+class SrArgs(C.Structure):
+    _fields_ = [("target", _vp), ("src", _vp), ("src2", _vp), ("n", _i64), ("rng_base", _i64), ("seed", _u64), ("offset", _u64),
+                ("mode", _i32), ("src_dtype", _i32), ("alpha", _f32), ("flavor", _u32)]
 
 
 class ShardExchangeArgs(C.Structure):
@@ -210,11 +216,12 @@ SYMBOLS = {
     "otb_dora_backward": (C.c_int, [C.POINTER(DoraArgs), _vp]),
     "otb_adafactor_multi": (C.c_int, [C.POINTER(FactoredLaunch), _vp]),
     "otb_came_multi": (C.c_int, [C.POINTER(FactoredLaunch), _vp]),
+    "otb_stochastic_round": (C.c_int, [C.POINTER(SrArgs), _vp]),
     "otb_philox_dump": (C.c_int, [_u64, _u64, _u32, _i64, _i64, _vp, _vp]),
     "otb_struct_sizes": (C.c_int, [C.POINTER(C.c_int32)]),
 }
 _STRUCTS = (OptimTensor, OptimLaunch, ShadowTensor, NoiseArgs, LossArgs, LoraLinearArgs, LoraGradArgs, GradExchangeArgs,
-            FactoredTensor, FactoredLaunch, DoraArgs, ShardExchangeArgs, PeerStore)
+            FactoredTensor, FactoredLaunch, DoraArgs, ShardExchangeArgs, PeerStore, SrArgs)
 
 _lib = None
 

@@ -15,7 +15,7 @@ REPO_DIR = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libotb200.so"
 
-SOURCES = ["api.cu", "optim.cu", "optim_factored.cu", "noise_loss.cu", "lora_gemm.cu", "lora_grad.cu", "dora.cu", "exchange.cu"]
+SOURCES = ["api.cu", "optim.cu", "optim_factored.cu", "noise_loss.cu", "lora_gemm.cu", "lora_grad.cu", "dora.cu", "exchange.cu", "sr_round.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

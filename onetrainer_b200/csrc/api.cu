@@ -115,6 +115,7 @@ extern "C" int otb_struct_sizes(int32_t* out) {
     out[10] = (int32_t)sizeof(otb_dora_args);
     out[11] = (int32_t)sizeof(otb_shard_exchange_args);
     out[12] = (int32_t)sizeof(otb_peer_store);
+    out[13] = (int32_t)sizeof(otb_sr_args);
     return OTB_OK;
 }
 

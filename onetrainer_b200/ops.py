@@ -628,6 +628,24 @@ def grad_scale_multi(table: OptimTable, coef: torch.Tensor) -> None:
     _count()
 
 
+def stochastic_round(mode: int, target: torch.Tensor, src: torch.Tensor, src2: torch.Tensor | None = None, *, alpha: float = 1.0,
+                     seed: int = 0, offset: int = 0, rng_base: int = 0, flavor: int = N.FLAVOR_TORCH_CUDA) -> None:
+    """One launch of otb_stochastic_round (include/otb200.h): N.SR_COPY target = SR(src); N.SR_ADD target = SR(fp32(src) +
+    alpha * target); N.SR_ADDCDIV target = SR(target + alpha * src / src2).  target: contiguous bf16, written in place."""
+    N.require_cuda(target, src, src2)
+    if target.dtype != torch.bfloat16 or not target.is_contiguous():
+        raise ValueError("stochastic_round: target must be a contiguous bf16 tensor")
+    for t in (src, src2):
+        if t is not None and (not t.is_contiguous() or t.numel() != target.numel() or t.dtype != src.dtype):
+            raise ValueError("stochastic_round: operands must be contiguous, of the target's size and of one dtype")
+    a = N.SrArgs(target=target.data_ptr(), src=src.data_ptr(), src2=N.ptr(src2), n=target.numel(), rng_base=int(rng_base),
+                 seed=int(seed) & (2**64 - 1), offset=int(offset) & (2**64 - 1), mode=int(mode), src_dtype=N.dtype_code(src.dtype),
+                 alpha=float(alpha), flavor=int(flavor))
+    N.check(N.lib().otb_stochastic_round(C.byref(a), _stream()), "otb_stochastic_round")
+    if target.numel():
+        _count()
+
+
 class ShadowTable:
     """bf16 (and transposed bf16) shadows of a list of 2-D master tensors, refreshed in one launch."""
 

@@ -19,6 +19,7 @@
  *   adam_step            modules/util/optimizer/adamw_extensions.py:79-146,
  *                        modules/util/optimizer/adam_extensions.py:71-90,
  *                        modules/util/bf16_stochastic_rounding.py:5-30,48-61
+ *   sr_helper            modules/util/bf16_stochastic_rounding.py:5-61 (copy_ / add_ / addcdiv_stochastic_)
  *   ema_step             modules/module/EMAModule.py:41-47
  *   clip (scale part)    torch.nn.utils.clip_grad_norm_ as called at GenericTrainer.py:712-713
  *   timesteps            modules/modelSetup/mixin/ModelSetupNoiseMixin.py:51-155
@@ -171,6 +172,40 @@ void otb_o_adam_step(void* p, const void* g_in, void* m, void* v, int64_t n, int
         } else {
             st(p, i, dt, r);
         }
+    }
+}
+
+/* The three helpers of modules/util/bf16_stochastic_rounding.py as their callers see them (CAME.py:167-176,
+ * adamw_extensions.py:139-144 use them; other optimizers of the reference import them the same way).  `bits16` = the 16-bit
+ * draw of every element (torch.randint_like(.., 0, 1 << 16) in the reference), `target` = bf16 bits, updated in place.
+ *   mode 0  copy_stochastic_(target, source):                 r = source                                   (:5-30)
+ *   mode 1  add_stochastic_(input, other, alpha):             r = fp32(other); r.add_(input, alpha=alpha)  (:33-45)
+ *           — alpha multiplies INPUT, not `other` (the docstring says otherwise; the code is what callers get)
+ *   mode 2  addcdiv_stochastic_(input, tensor1, tensor2, v):  r = fp32(input); r.addcdiv_(t1, t2, value=v) (:48-61)
+ * then bits = int32(r) + draw; bits &= 0xFFFF0000; target = high half. */
+void otb_o_sr_helper(uint16_t* target, const void* a, const void* b, int64_t n, int mode, int src_dt, float alpha,
+                     uint32_t flavor, const int32_t* bits16, float* r_out /* the fp32 value before rounding, or NULL */) {
+    int64_t i;
+#pragma omp parallel for
+    for (i = 0; i < n; ++i) {
+        float r;
+        if (mode == 0) {
+            r = ((const float*)a)[i];
+        } else if (mode == 1) {
+            const float o = ld(a, i, src_dt), in = bf16_to_f(target[i]);
+            r = (flavor & FL_FMA_ADD_ALPHA) ? fmaf(alpha, in, o) : o + alpha * in;
+        } else {
+            const float in = bf16_to_f(target[i]), t1 = ld(a, i, src_dt), t2 = ld(b, i, src_dt);
+            if (flavor & FL_ADDCDIV_MUL_LAST) {
+                const float q = t1 / t2;
+                r = (flavor & FL_FMA_ADDCDIV) ? fmaf(alpha, q, in) : in + alpha * q;
+            } else {
+                r = in + (alpha * t1) / t2;
+            }
+        }
+        if (r_out) r_out[i] = r;
+        const uint32_t u = f_bits(r) + (uint32_t)bits16[i];
+        target[i] = (uint16_t)((u & 0xffff0000u) >> 16);
     }
 }
 

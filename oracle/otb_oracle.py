@@ -10,6 +10,7 @@ Besides the ctypes wrappers of the C restatement, this file holds the numpy rest
   adafactor_step       step_adafactor_parameter                          modules/util/optimizer/adafactor_extensions.py:17-93
   came_step            CAME.step_parameter                               modules/util/optimizer/CAME.py:80-176
   stochastic_round_bf16  copy_stochastic_                                modules/util/bf16_stochastic_rounding.py:5-30
+  sr_helper            copy_ / add_ / addcdiv_stochastic_ (C restatement) modules/util/bf16_stochastic_rounding.py:5-61
 all pinned on outputs of the unmodified reference (tests/golden/, tools/make_golden.py).  The last four have no kernel
 yet: the oracle is in place first (task order: oracle, boundary, kernel).
 """
@@ -378,6 +379,29 @@ def stochastic_round_bf16(x32, bits):
     """copy_stochastic_ (bf16_stochastic_rounding.py:5-30): int32 view + 16 random bits, low half masked off."""
     u = np.ascontiguousarray(x32, dtype=np.float32).view(np.int32) + np.asarray(bits, dtype=np.int32).reshape(np.shape(x32))
     return (u & np.int32(-65536)).view(np.float32)
+
+
+SR_COPY, SR_ADD, SR_ADDCDIV = 0, 1, 2
+
+
+def sr_helper(mode: int, target_bits, a, b=None, *, alpha: float = 1.0, bits, flavor=FLAVOR_TORCH_CPU, want_r32: bool = False):
+    """copy_stochastic_ / add_stochastic_ / addcdiv_stochastic_ (modules/util/bf16_stochastic_rounding.py:5-61) as their
+    callers see them.  `target_bits`: uint16 bf16 bits of `target` / `input` (read by ADD and ADDCDIV); `a`, `b`: the other
+    operands, float32 arrays or uint16 arrays carrying bf16 bits; `bits`: the 16-bit draw of every element.  Returns the
+    new bf16 bits (the input array is not modified); with `want_r32` also the fp32 values before the rounding."""
+    out = np.ascontiguousarray(target_bits, dtype=np.uint16).copy()
+    a = np.ascontiguousarray(a)
+    src_dt = DT_BF16 if a.dtype == np.uint16 else DT_F32
+    assert a.dtype in (np.uint16, np.float32) and a.size == out.size and (mode != SR_COPY or src_dt == DT_F32)
+    if b is not None:
+        b = np.ascontiguousarray(b)
+        assert b.dtype == a.dtype and b.size == out.size
+    bits = np.ascontiguousarray(bits, dtype=np.int32)
+    assert bits.size == out.size and (mode == SR_ADDCDIV) == (b is not None)
+    r32 = np.empty(out.size, dtype=np.float32) if want_r32 else None
+    lib().otb_o_sr_helper(_p(out), _p(a), _p(b), C.c_int64(out.size), C.c_int(mode), C.c_int(src_dt), C.c_float(alpha),
+                          C.c_uint32(flavor), _p(bits), _p(r32))
+    return (out, r32) if want_r32 else out
 
 
 def came_step(p, grad, state, *, lr, eps=(1e-30, 1e-16), clip_threshold=1.0, betas=(0.9, 0.999, 0.9999), weight_decay=0.0,

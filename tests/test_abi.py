@@ -63,6 +63,19 @@ def test_argument_errors_surface_as_python_exceptions():
         N.check(rc, "otb_lora_linear")
 
 
+def test_stochastic_round_argument_validation():
+    """otb_stochastic_round (bf16_stochastic_rounding.py as a launch): an empty tensor is a no-op, bad arguments are errors —
+    checked on the host before anything is launched."""
+    from onetrainer_b200 import _native as N
+    lib = N.lib()
+    assert lib.otb_stochastic_round(C.byref(N.SrArgs(n=0, mode=N.SR_COPY)), None) == N.OTB_OK
+    ok = dict(target=16, src=32, n=64, mode=N.SR_ADD, src_dtype=N.F32)
+    for bad in (dict(n=-1), dict(target=None), dict(src=None), dict(mode=7), dict(mode=N.SR_ADDCDIV),      # addcdiv without tensor2
+                dict(mode=N.SR_COPY, src_dtype=N.BF16), dict(rng_base=4), dict(rng_base=-8), dict(src=34)):
+        assert lib.otb_stochastic_round(C.byref(N.SrArgs(**{**ok, **bad})), None) == N.OTB_EINVAL, bad
+    assert lib.otb_stochastic_round(C.byref(N.SrArgs(**{**ok, "src_dtype": N.F16})), None) == N.OTB_EUNSUPPORTED
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from onetrainer_b200 import _native as N
     monkeypatch.setattr(N, "_lib", None)

@@ -56,6 +56,53 @@ def test_sr_is_unbiased_like_reference_kat(oracle, golden):
     assert abs(ref_mean - (1 + 2.0 ** -10)) < 4.1e-5
 
 
+SR_HELPER_CASES = {"copy": ("copy", 1), "add_update": ("add", None), "add_decay": ("add", None), "add_half": ("add", None),
+                   "add_bf16": ("add", None), "add_third": ("add", None), "add_third_bf16": ("add", None),
+                   "addcdiv_bf16": ("addcdiv", None), "addcdiv_f32": ("addcdiv", None)}
+
+
+def run_sr_helper_case(oracle, g, name, flavor):
+    """One case of tests/golden/sr_helpers.npz through the oracle: (bf16 bits, fp32 values before the rounding)."""
+    seed, base = (int(x) for x in g["meta"])
+    kind = SR_HELPER_CASES[name][0]
+    if kind == "copy":
+        n = g["copy_src"].size
+        return oracle.sr_helper(oracle.SR_COPY, np.zeros(n, np.uint16), g["copy_src"], bits=oracle.sr_bits(seed, 1, base, n), want_r32=True)
+    alpha, off = g[f"{name}_meta"]
+    n = g[f"{name}_in"].size
+    draws = oracle.sr_bits(seed, int(off), base, n)
+    if kind == "add":
+        return oracle.sr_helper(oracle.SR_ADD, g[f"{name}_in"], g[f"{name}_other"], alpha=float(alpha), bits=draws, flavor=flavor, want_r32=True)
+    return oracle.sr_helper(oracle.SR_ADDCDIV, g[f"{name}_in"], g[f"{name}_t1"], g[f"{name}_t2"], alpha=float(alpha), bits=draws,
+                            flavor=flavor, want_r32=True)
+
+
+@pytest.mark.parametrize("name", list(SR_HELPER_CASES))
+def test_sr_helpers_bit_exact_vs_reference(oracle, golden, name):
+    """copy_stochastic_ / add_stochastic_ / addcdiv_stochastic_ (modules/util/bf16_stochastic_rounding.py) called directly:
+    the oracle fed the reference run's own 16-bit draws reproduces the bf16 result AND the fp32 value the reference formed
+    before rounding (captured at its randint_like call) bit for bit — including the corners of the integer trick (zeros,
+    exact bf16 values, mantissas that carry into the exponent, denormals) and `other` aliasing `input`."""
+    g = golden("sr_helpers")
+    out, r32 = run_sr_helper_case(oracle, g, name, oracle.FLAVOR_TORCH_CPU)
+    assert np.array_equal(out, g[f"{name}_out"])
+    if name != "copy":
+        assert np.array_equal(r32.view(np.int32), g[f"{name}_r32"].view(np.int32))
+
+
+def test_sr_helper_fixture_pins_the_rounding_flavour(oracle, golden):
+    """The fixture discriminates the arithmetic flavours: torch's CPU add_ with alpha is ONE fma, its addcdiv_ is
+    p + (value * t1) / t2 — the other orders differ from the recorded fp32 values on hundreds of elements."""
+    g = golden("sr_helpers")
+    no_fma = oracle.FLAVOR_TORCH_CPU & ~oracle.FL_FMA_ADD_ALPHA
+    for name in ("add_third", "add_third_bf16"):
+        _, r32 = run_sr_helper_case(oracle, g, name, no_fma)
+        assert (r32.view(np.int32) != g[f"{name}_r32"].view(np.int32)).sum() > 100
+    for name in ("addcdiv_bf16", "addcdiv_f32"):
+        _, r32 = run_sr_helper_case(oracle, g, name, oracle.FLAVOR_TORCH_CUDA)
+        assert (r32.view(np.int32) != g[f"{name}_r32"].view(np.int32)).sum() > 100
+
+
 @pytest.mark.parametrize("tag,dt", [("f32", 0), ("bf16", 1)])
 def test_ema_bit_exact_vs_reference(oracle, golden, tag, dt):
     """EMAModuleWrapper.step (EMAModule.py:37-54): decay warm-up, update interval 2, three roundings."""

@@ -1,5 +1,5 @@
 """Launch one kernel a few times at its roofline size — the target of `ncu --set full`.
-usage: python tools/kprof.py {kc_bf16|kc_fp32|kb1|kb2|ka|ka1280|kaqkv|kgrad|kgradb|adafactor|came|dora} [iters]"""
+usage: python tools/kprof.py {kc_bf16|kc_fp32|kb1|kb2|ka|ka1280|kaqkv|kgrad|kgradb|adafactor|came|dora|sr} [iters]"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -40,6 +40,37 @@ if which in ("kc_bf16", "kc_fp32"):
     ms = timed(lambda: ops.adamw_sr_ema_multi(tab, do_ema=True, ema_one_minus_decay=0.001, seed=1, offset=2))
     bpe = 18 if dt == torch.bfloat16 else 36
     print(f"{which}: {ms:.3f} ms, {n * bpe / ms / 1e6:.0f} GB/s")
+elif which == "sr":
+    # the three helpers of bf16_stochastic_rounding.py at the roofline size, ours (one launch) and the reference's op sequence
+    # (its own source lines, restated here so the tool needs no baseline/_ref) on the same GPU
+    n = 1 << 28
+    tgt = (torch.randn(n, device=dev) * 0.02).bfloat16()
+    src = torch.randn(n, device=dev) * 1e-4
+    t1 = (torch.randn(n, device=dev) * 1e-3).bfloat16(); t2 = (torch.rand(n, device=dev) * 1e-3 + 1e-8).bfloat16()
+
+    def ref_copy(target, source):
+        result = torch.randint_like(source, dtype=torch.int32, low=0, high=(1 << 16))
+        result.add_(source.view(dtype=torch.int32))
+        result.bitwise_and_(-65536)
+        target.copy_(result.view(dtype=torch.float32))
+
+    def ref_add(inp, other, alpha):
+        result = other.clone() if other.dtype == torch.float32 else other.to(dtype=torch.float32)
+        result.add_(inp, alpha=alpha)
+        ref_copy(inp, result)
+
+    def ref_addcdiv(inp, a, b, value):
+        result = inp.to(dtype=torch.float32)
+        result.addcdiv_(a, b, value=value)
+        ref_copy(inp, result)
+
+    for name, bpe, mine, ref in (
+            ("copy_stochastic_", 6, lambda: ops.stochastic_round(N.SR_COPY, tgt, src, seed=1, offset=2), lambda: ref_copy(tgt, src)),
+            ("add_stochastic_", 8, lambda: ops.stochastic_round(N.SR_ADD, tgt, src, alpha=1.0, seed=1, offset=2), lambda: ref_add(tgt, src, 1.0)),
+            ("addcdiv_stochastic_", 8, lambda: ops.stochastic_round(N.SR_ADDCDIV, tgt, t1, t2, alpha=-3e-4, seed=1, offset=2),
+             lambda: ref_addcdiv(tgt, t1, t2, -3e-4))):
+        ms, ms_ref = timed(mine), timed(ref)
+        print(f"sr {name}: {ms:.3f} ms, {n * bpe / ms / 1e6:.0f} GB/s of {bpe} B/elem; reference op sequence on the same GPU {ms_ref:.3f} ms ({ms_ref / ms:.1f}x)")
 elif which == "kb1":
     Bb = 4096
     lat = torch.randn(Bb, 4, 128, 128, device=dev)

@@ -47,7 +47,7 @@ from modules.modelSetup.mixin.ModelSetupFlowMatchingMixin import ModelSetupFlowM
 from modules.modelSetup.mixin.ModelSetupNoiseMixin import ModelSetupNoiseMixin  # noqa: E402
 from modules.module.EMAModule import EMAModuleWrapper  # noqa: E402
 from modules.module.LoRAModule import DoRAModule, LoRAModule  # noqa: E402
-from modules.util.bf16_stochastic_rounding import copy_stochastic_  # noqa: E402,F401
+from modules.util.bf16_stochastic_rounding import add_stochastic_, addcdiv_stochastic_, copy_stochastic_  # noqa: E402,F401
 from modules.util.config.TrainConfig import TrainConfig  # noqa: E402
 from modules.util.convert.rescale_noise_scheduler_to_zero_terminal_snr import rescale_noise_scheduler_to_zero_terminal_snr  # noqa: E402
 from modules.util.DiffusionScheduleCoefficients import DiffusionScheduleCoefficients  # noqa: E402
@@ -129,6 +129,66 @@ def gen_optimizer():
     copy_stochastic_(tgt, src)
     out["sr_kat_mean"] = np.array([tgt.float().mean().item()])
     np.savez(OUT / "optimizer.npz", **out)
+
+
+# ------------------------------------------------------------------------------------ the SR helpers themselves
+def gen_sr_helpers():
+    """copy_stochastic_ / add_stochastic_ / addcdiv_stochastic_ (modules/util/bf16_stochastic_rounding.py) called directly,
+    the way CAME.py:167-176 and other optimizers of the reference call them; the 16-bit draws come from this repo's Philox
+    stream (torch.randint_like patched for the call)."""
+    out = {}
+    n = 4099
+    seed, rng_base = 0xBADC0DE, 16
+    g = torch.Generator().manual_seed(23)
+
+    def with_draws(offset, fn, r32_key=None):
+        orig = torch.randint_like
+
+        def fake_randint_like(src, dtype=None, low=0, high=0):
+            assert low == 0 and high == (1 << 16) and dtype == torch.int32
+            if r32_key is not None:
+                out[r32_key] = src.detach().numpy().copy()     # the reference's fp32 result BEFORE the rounding (pins the FMA flavour)
+            return torch.from_numpy(O.sr_bits(seed, offset, rng_base, src.numel()).copy()).view(src.shape)
+        torch.randint_like = fake_randint_like
+        try:
+            fn()
+        finally:
+            torch.randint_like = orig
+
+    # copy: ordinary values plus the corners of the integer trick (zeros, exact bf16 values, a mantissa of all ones that
+    # carries into the exponent, denormals, large magnitudes, both signs)
+    src = torch.randn(n, generator=g) * 0.02
+    special = torch.tensor([0.0, -0.0, 1.0, -1.0, 1.0 + 2 ** -10, 1.0078125, 1e-30, -1e-30, 1e-40, -3.5e20, 3.3895e38, 65504.0], dtype=torch.float32)
+    carry = torch.tensor([0x3FFFFFFF, 0xBFFFFFFF, 0x3F7FFFFF, 0x007FFFFF, 0x00000001], dtype=torch.int64).to(torch.int32).view(torch.float32)
+    src[:special.numel()] = special
+    src[special.numel():special.numel() + carry.numel()] = carry
+    tgt = torch.empty(n, dtype=torch.bfloat16)
+    with_draws(1, lambda: copy_stochastic_(tgt, src))
+    out["copy_src"], out["copy_out"] = src.numpy().copy(), bits16(tgt)
+    # add: the two calls of CAME (p += -update; p += alpha * p) and a generic alpha
+    for name, other_dtype, alpha, offset, alias in (("add_update", torch.float32, 1.0, 2, False), ("add_decay", torch.bfloat16, -3e-6, 3, True),
+                                                    ("add_half", torch.float32, 0.5, 4, False), ("add_bf16", torch.bfloat16, 1.0, 5, False),
+                                                    ("add_third", torch.float32, 0.3, 8, False), ("add_third_bf16", torch.bfloat16, -0.7, 9, False)):
+        inp = (torch.randn(n, generator=g) * 0.02).bfloat16()
+        other = inp if alias else (torch.randn(n, generator=g) * (1e-2 if "third" in name else 1e-4)).to(other_dtype)
+        out[f"{name}_in"] = bits16(inp)
+        out[f"{name}_other"] = bits16(other) if other_dtype == torch.bfloat16 else other.numpy().copy()
+        with_draws(offset, lambda: add_stochastic_(inp, other, alpha=alpha), f"{name}_r32")            # noqa: B023
+        out[f"{name}_out"] = bits16(inp)
+        out[f"{name}_meta"] = np.array([alpha, offset], dtype=np.float64)
+    # addcdiv: AdamW's parameter update (adamw_extensions.py:139-144) and an fp32-operand variant
+    for name, dt, value, offset in (("addcdiv_bf16", torch.bfloat16, -3e-4, 6), ("addcdiv_f32", torch.float32, -1.7e-3, 7)):
+        inp = (torch.randn(n, generator=g) * 0.02).bfloat16()
+        t1 = (torch.randn(n, generator=g) * 1e-3).to(dt)
+        t2 = (torch.rand(n, generator=g) * 1e-3 + 1e-8).to(dt)
+        out[f"{name}_in"] = bits16(inp)
+        for key, t in (("t1", t1), ("t2", t2)):
+            out[f"{name}_{key}"] = bits16(t) if dt == torch.bfloat16 else t.numpy().copy()
+        with_draws(offset, lambda: addcdiv_stochastic_(inp, t1, t2, value=value), f"{name}_r32")     # noqa: B023
+        out[f"{name}_out"] = bits16(inp)
+        out[f"{name}_meta"] = np.array([value, offset], dtype=np.float64)
+    out["meta"] = np.array([seed, rng_base], dtype=np.int64)
+    np.savez(OUT / "sr_helpers.npz", **out)
 
 
 # ------------------------------------------------------------------------------------ Adafactor (oracle only so far)
@@ -533,7 +593,7 @@ def gen_clip():
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])              # e.g. `python tools/make_golden.py gen_lora` rewrites one fixture file
-    for fn in (gen_schedule, gen_optimizer, gen_adafactor, gen_came, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_lora_bf16in, gen_dora, gen_param_groups, gen_clip):
+    for fn in (gen_schedule, gen_optimizer, gen_sr_helpers, gen_adafactor, gen_came, gen_ema, gen_timesteps, gen_addnoise, gen_losses, gen_lora, gen_lora_bf16in, gen_dora, gen_param_groups, gen_clip):
         if only and fn.__name__ not in only:
             continue
         fn()
