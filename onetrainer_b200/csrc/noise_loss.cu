@@ -17,7 +17,9 @@
 
 #define NL_THREADS 256
 #define NB1_UNROLL 2   /* groups of 4 elements per thread per iteration, K-b1 */
-#define NB2_UNROLL 2   /* K-b2: measured 4.94 TB/s at 2 vs 4.61 (1) / 3.08 (4) on B200 */
+#define NB2_UNROLL 2   /* K-b2: measured 4.94 TB/s at 2 vs 4.61 (1) / 3.08 (4) on B200.  Groups of 8 elements (128-bit bf16
+                          accesses) were tried at the end of round 2 and are SLOWER: 0.394 ms (one group per thread) / 0.431 ms
+                          (two) against 0.379 ms for this layout at N = 2^28 (profiles/r03b_logs/kb2_ab.log) */
 
 namespace {
 
@@ -529,7 +531,12 @@ int blocks_per_sample_for(int64_t chw, int B, int unroll) {
     // resident blocks do blocks start to loop.
     int64_t slabs = (chw / 4 + NL_THREADS * unroll - 1) / (NL_THREADS * unroll);
     if (slabs < 1) slabs = 1;
-    int64_t want = (int64_t)otb_sm_count() * 8 * 64 / (B > 0 ? B : 1);
+    // A/B knob.  Measured at N = 2^28 (profiles/r03c_logs/ab.log): lifting the cap so that every block runs exactly one slab
+    // is SLOWER — K-b2 0.378 -> 0.483 ms, K-b1 0.470 -> 0.517 ms — the per-block prologue (timestep weight, barriers, the
+    // partial-sum hand-off) outweighs the serialised second iteration of the looping blocks.
+    int waves = 64;
+    if (const char* v = getenv("OTB_NB_WAVES")) { const int w = atoi(v); if (w >= 1 && w <= 4096) waves = w; }
+    int64_t want = (int64_t)otb_sm_count() * 8 * waves / (B > 0 ? B : 1);
     if (want < 1) want = 1;
     int64_t bps = slabs < want ? slabs : want;
     if (bps > 65535) bps = 65535;

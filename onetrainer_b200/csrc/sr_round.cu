@@ -9,12 +9,17 @@
 // (OTB_STREAM_SR, one Philox4x32-10 call per 8 elements — the same assignment K-c uses, restated in oracle/otb_oracle.c:
 // sr_rand16).  Algorithmic bytes per element: copy 4 + 2, add 2 + {4|2} + 2, addcdiv 2 + 2·{4|2} + 2.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
 constexpr int SR_THREADS = 256;
-constexpr int SR_UNROLL = 2;                               // groups of 8 elements per thread, loaded before any is stored
-constexpr int SR_GROUPS_PER_BLOCK = SR_THREADS * SR_UNROLL;
+// groups of 8 elements per thread, all loaded before any is stored: 2 where the arithmetic is light (copy, add); addcdiv's 16
+// IEEE divisions per thread cost registers (74 -> 3 blocks per SM), so it runs one group per thread at twice the occupancy.
+// Measured at n = 2^28 (profiles/r03b_logs/sr_ab.log): copy 0.235 ms = 6.84 TB/s, add 0.353 ms = 6.09 TB/s, addcdiv 0.449 ms =
+// 4.79 TB/s with one group (0.603 ms with two; 0.681 ms before the flavour became a compile-time constant) — the reference's
+// op sequence on the same B200: 1.57 / 2.74 / 4.14 ms.  addcdiv is issue-bound: 8 correctly rounded divisions per group.
+template <int MODE> constexpr int sr_unroll() { return MODE == OTB_SR_ADDCDIV ? 1 : 2; }
 
 __device__ __forceinline__ uint4 ld_u4_plain(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 
@@ -48,8 +53,12 @@ __device__ __forceinline__ uint32_t sr16(const Philox4& r, int lane) {
     return (lane & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
-template <int MODE, bool SRC_BF16>
+// FL: the arithmetic flavour at compile time (the hot instantiation is OTB_FLAVOR_TORCH_CUDA, what the module passes), or -1 to
+// read a.flavor at run time — with the flavour fixed each element carries one division site instead of two.
+template <int MODE, bool SRC_BF16, int FL, int SR_UNROLL>
 __global__ void __launch_bounds__(SR_THREADS) sr_round_kernel(const otb_sr_args a, const int vec_ok) {
+    constexpr int SR_GROUPS_PER_BLOCK = SR_THREADS * SR_UNROLL;
+    const uint32_t fl = FL >= 0 ? (uint32_t)FL : a.flavor;
     const int64_t groups = (a.n + 7) >> 3;
     const int64_t g0 = (int64_t)blockIdx.x * SR_GROUPS_PER_BLOCK + threadIdx.x;
     float in[SR_UNROLL][8], s1[SR_UNROLL][8], s2[SR_UNROLL][8];
@@ -81,12 +90,12 @@ __global__ void __launch_bounds__(SR_THREADS) sr_round_kernel(const otb_sr_args 
             if (MODE == OTB_SR_COPY) {
                 r = s1[u][k];
             } else if (MODE == OTB_SR_ADD) {                          // result = fp32(other); result.add_(input, alpha=alpha)
-                r = (a.flavor & OTB_FLAVOR_FMA_ADD_ALPHA) ? __fmaf_rn(a.alpha, in[u][k], s1[u][k])
+                r = (fl & OTB_FLAVOR_FMA_ADD_ALPHA) ? __fmaf_rn(a.alpha, in[u][k], s1[u][k])
                                                           : __fadd_rn(s1[u][k], __fmul_rn(a.alpha, in[u][k]));
             } else {                                                  // result = fp32(input); result.addcdiv_(t1, t2, value=alpha)
-                if (a.flavor & OTB_FLAVOR_ADDCDIV_MUL_LAST) {
+                if (fl & OTB_FLAVOR_ADDCDIV_MUL_LAST) {
                     const float q = __fdiv_rn(s1[u][k], s2[u][k]);
-                    r = (a.flavor & OTB_FLAVOR_FMA_ADDCDIV) ? __fmaf_rn(a.alpha, q, in[u][k]) : __fadd_rn(in[u][k], __fmul_rn(a.alpha, q));
+                    r = (fl & OTB_FLAVOR_FMA_ADDCDIV) ? __fmaf_rn(a.alpha, q, in[u][k]) : __fadd_rn(in[u][k], __fmul_rn(a.alpha, q));
                 } else {
                     r = __fadd_rn(in[u][k], __fdiv_rn(__fmul_rn(a.alpha, s1[u][k]), s2[u][k]));
                 }
@@ -106,15 +115,38 @@ __global__ void __launch_bounds__(SR_THREADS) sr_round_kernel(const otb_sr_args 
     }
 }
 
-template <int MODE>
-int launch_sr(const otb_sr_args& a, int vec_ok, cudaStream_t st) {
+template <int MODE, int FL, int SR_UNROLL>
+int launch_sr_unrolled(const otb_sr_args& a, int vec_ok, cudaStream_t st) {
+    constexpr int SR_GROUPS_PER_BLOCK = SR_THREADS * SR_UNROLL;
     const int64_t groups = (a.n + 7) >> 3;
     const int64_t blocks = (groups + SR_GROUPS_PER_BLOCK - 1) / SR_GROUPS_PER_BLOCK;
     OTB_CHECK_ARG(blocks <= 0x7FFFFFFF, "too many elements for one launch: %lld", (long long)a.n);
-    if (a.src_dtype == OTB_BF16) sr_round_kernel<MODE, true><<<(unsigned)blocks, SR_THREADS, 0, st>>>(a, vec_ok);
-    else sr_round_kernel<MODE, false><<<(unsigned)blocks, SR_THREADS, 0, st>>>(a, vec_ok);
+    if (a.src_dtype == OTB_BF16) sr_round_kernel<MODE, true, FL, SR_UNROLL><<<(unsigned)blocks, SR_THREADS, 0, st>>>(a, vec_ok);
+    else sr_round_kernel<MODE, false, FL, SR_UNROLL><<<(unsigned)blocks, SR_THREADS, 0, st>>>(a, vec_ok);
     OTB_LAUNCH_CHECK("sr_round_kernel");
     return OTB_OK;
+}
+
+// tuning knob for A/B runs on the GPU box (unset in production: the compiled default is used)
+template <int MODE, int FL>
+int launch_sr_flavor(const otb_sr_args& a, int vec_ok, cudaStream_t st) {
+    if constexpr (MODE == OTB_SR_ADDCDIV) {
+        const char* v = getenv("OTB_SR_UNROLL");
+        if (v && atoi(v) == 2) return launch_sr_unrolled<MODE, FL, 2>(a, vec_ok, st);
+    }
+    return launch_sr_unrolled<MODE, FL, sr_unroll<MODE>()>(a, vec_ok, st);
+}
+
+template <int MODE>
+int launch_sr(const otb_sr_args& a, int vec_ok, cudaStream_t st) {
+    // only three flavour bits reach this arithmetic; COPY has none
+    constexpr uint32_t USED = OTB_FLAVOR_FMA_ADD_ALPHA | OTB_FLAVOR_ADDCDIV_MUL_LAST | OTB_FLAVOR_FMA_ADDCDIV;
+    if constexpr (MODE == OTB_SR_COPY) {
+        return launch_sr_flavor<MODE, 0>(a, vec_ok, st);
+    } else {
+        if ((a.flavor & USED) == (OTB_FLAVOR_TORCH_CUDA & USED)) return launch_sr_flavor<MODE, (int)(OTB_FLAVOR_TORCH_CUDA & USED)>(a, vec_ok, st);
+        return launch_sr_flavor<MODE, -1>(a, vec_ok, st);
+    }
 }
 
 }  // namespace

@@ -31,7 +31,8 @@ if which in ("kc_bf16", "kc_fp32"):
     dt = torch.bfloat16 if which == "kc_bf16" else torch.float32
     n = 1 << 28 if dt == torch.bfloat16 else 1 << 27
     p = torch.zeros(n, device=dev, dtype=dt); g = torch.full_like(p, 1e-3); m = torch.zeros_like(p); v = torch.ones_like(p); e = torch.zeros_like(p)
-    tab = ops.OptimTable([dict(p=p, g=g, exp_avg=m, exp_avg_sq=v, ema=e)], dev)
+    import os
+    tab = ops.OptimTable([dict(p=p, g=g, exp_avg=m, exp_avg_sq=v, ema=e)], dev, chunk_elems=int(os.environ.get("OTB_KC_CHUNK", ops.CHUNK_ELEMS)))
     if dt == torch.bfloat16:
         tab.host["flags"][:] |= N.OPT_FLAG_SR
     for k, val in ops.adam_scalars(3e-4, 0.9, 0.999, 1e-8, 1e-2, 1.0, True).items():
