@@ -4,7 +4,8 @@ modules/util/bf16_stochastic_rounding.py:5-61 (copy_stochastic_ / add_stochastic
 
   (1) the golden fixture recorded from the unmodified reference (tests/golden/sr_helpers.npz, TORCH_CPU flavour): bit-exact,
   (2) the oracle on seeded inputs, ragged sizes and misaligned views (scalar path), both flavours: bit-exact,
-  (3) the reference's own op sequence run by torch on this GPU with the same 16-bit draws (TORCH_CUDA flavour): bit-exact,
+  (3) the reference's own op sequence run by torch on this GPU with the same 16-bit draws (TORCH_CUDA flavour) — restated,
+      and the unmodified reference file itself (baseline/_ref) with torch.randint_like answering from the same stream: bit-exact,
   (4) properties at the roofline size: unbiased within 5 sigma, every result one of the two bf16 neighbours.
 Everything is integer / bit-level work once the draws are shared, so the bar is equality of bits."""
 import math
@@ -138,6 +139,50 @@ def test_sr_helpers_vs_reference_op_sequence_on_this_gpu(K, dev, oracle, src_dty
     tgt = inp.clone()
     K.ops.stochastic_round(K.N.SR_ADDCDIV, tgt, other, t2, alpha=-1.7e-3, seed=seed, offset=off, rng_base=base, flavor=K.N.FLAVOR_TORCH_CUDA)
     assert np.array_equal(bits16(tgt), bits16(ref)), f"addcdiv: {(bits16(tgt) != bits16(ref)).sum()} of {n} differ"
+
+
+def test_sr_helpers_vs_the_unmodified_reference_module_on_this_gpu(K, dev, oracle, monkeypatch):
+    """The reference's own file (baseline/_ref/modules/util/bf16_stochastic_rounding.py, byte for byte) run on this GPU with
+    torch.randint_like answering from the library's Philox stream: its three functions and the one-launch kernels in the
+    TORCH_CUDA flavour leave the same bf16 bits — fp32 and bf16 operands, `other` aliasing `input` (CAME's decay call)."""
+    from baseline import ref_arm
+    if not ref_arm.available():
+        pytest.skip("baseline/_ref did not travel")
+    ref_arm.load()
+    import modules.util.bf16_stochastic_rounding as ref
+    n, seed, base = 200003, 4242, 8
+    state = {"offset": 0}
+
+    def fake_randint_like(src, dtype=None, low=0, high=0):
+        assert low == 0 and high == (1 << 16) and dtype == torch.int32 and src.numel() == n
+        return torch.from_numpy(oracle.sr_bits(seed, state["offset"], base, n).copy()).to(src.device).view(src.shape)
+
+    monkeypatch.setattr(torch, "randint_like", fake_randint_like)
+    torch.manual_seed(9)
+    inp = (torch.randn(n, device=dev) * 0.02).bfloat16()
+    src = torch.randn(n, device=dev) * 0.02
+    kw = dict(seed=seed, rng_base=base, flavor=K.N.FLAVOR_TORCH_CUDA)
+
+    state["offset"] = 1
+    want, got = torch.empty_like(inp), torch.empty_like(inp)
+    ref.copy_stochastic_(want, src)
+    K.ops.stochastic_round(K.N.SR_COPY, got, src, offset=1, **kw)
+    assert np.array_equal(bits16(got), bits16(want))
+    for off, other, alpha in ((2, torch.randn(n, device=dev) * 1e-4, 1.0), (3, None, -3e-6),
+                              (4, (torch.randn(n, device=dev) * 1e-2).bfloat16(), -0.7)):
+        state["offset"] = off
+        want, got = inp.clone(), inp.clone()
+        ref.add_stochastic_(want, want if other is None else other, alpha=alpha)
+        K.ops.stochastic_round(K.N.SR_ADD, got, got if other is None else other, alpha=alpha, offset=off, **kw)
+        assert np.array_equal(bits16(got), bits16(want)), f"add_stochastic_ case {off}: {(bits16(got) != bits16(want)).sum()} of {n} differ"
+    for off, dt, value in ((5, torch.bfloat16, -3e-4), (6, torch.float32, -1.7e-3)):
+        state["offset"] = off
+        t1 = (torch.randn(n, device=dev) * 1e-3).to(dt)
+        t2 = (torch.rand(n, device=dev) * 1e-3 + 1e-8).to(dt)
+        want, got = inp.clone(), inp.clone()
+        ref.addcdiv_stochastic_(want, t1, t2, value=value)
+        K.ops.stochastic_round(K.N.SR_ADDCDIV, got, t1, t2, alpha=value, offset=off, **kw)
+        assert np.array_equal(bits16(got), bits16(want)), f"addcdiv_stochastic_ {dt}: {(bits16(got) != bits16(want)).sum()} of {n} differ"
 
 
 def test_module_functions_are_seeded_unbiased_and_refuse_fallbacks(dev):
