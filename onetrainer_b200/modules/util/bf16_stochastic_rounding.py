@@ -23,7 +23,8 @@ from ... import _native as N
 from ... import ops, rng
 
 
-def _key(t: Tensor) -> tuple[int, int]:
+def _key(t: Tensor, *others: Tensor) -> tuple[int, int]:
+    N.require_cuda(t, *others)                      # before anything touches a CUDA generator: CPU tensors get the clear error
     if torch.cuda.is_current_stream_capturing():
         raise RuntimeError("bf16_stochastic_rounding: the default generator's offset cannot advance inside a CUDA-graph capture; "
                            "use the fused optimizers (their key is a device-side step counter)")
@@ -42,21 +43,21 @@ def copy_stochastic_(target: Tensor, source: Tensor):
     """copies source (fp32) into target (bf16) using stochastic rounding"""
     if source.dtype != torch.float32:
         raise ValueError("copy_stochastic_: source must be float32 (the reference reinterprets it as int32)")
-    seed, offset = _key(target)
+    seed, offset = _key(target, source)
     ops.stochastic_round(N.SR_COPY, target, _operand(source, target, "source"), seed=seed, offset=offset)
 
 
 def add_stochastic_(input: Tensor, other: Tensor, alpha: float = 1.0):
     """input <- SR(fp32(other) + alpha * input): the reference's arithmetic (`result = other.float(); result.add_(input,
     alpha=alpha)`), in which alpha multiplies `input`."""
-    seed, offset = _key(input)
+    seed, offset = _key(input, other)
     ops.stochastic_round(N.SR_ADD, input, _operand(other, input, "other"), alpha=alpha, seed=seed, offset=offset)
 
 
 def addcdiv_stochastic_(input: Tensor, tensor1: Tensor, tensor2: Tensor, value: float = 1.0):
     """input <- SR(input + value * tensor1 / tensor2), rounded the way torch's CUDA addcdiv_ rounds (fma(value, t1 / t2, input))."""
+    seed, offset = _key(input, tensor1, tensor2)
     t1, t2 = _operand(tensor1, input, "tensor1"), _operand(tensor2, input, "tensor2")
     if t1.dtype != t2.dtype:
         t1, t2 = t1.float(), t2.float()
-    seed, offset = _key(input)
     ops.stochastic_round(N.SR_ADDCDIV, input, t1, t2, alpha=value, seed=seed, offset=offset)

@@ -505,3 +505,31 @@ def test_grad_queue_never_carries_leaves_past_the_pass_that_queued_them(monkeypa
     y = Leaf.apply(Nested.apply(Leaf.apply(x, "outer2", False)), "outer1", False)
     y.sum().backward()
     assert [t[0] for t in launched] == ["outer1", "inner", "outer2"] and q._pending[0] == []
+
+
+def test_sr_helper_module_keeps_the_reference_signatures_and_has_no_cpu_path():
+    """modules/util/bf16_stochastic_rounding.py: the three functions of the reference's file under the same names with the same
+    parameter names and defaults (compared with the unmodified file when baseline/_ref is present, else with the signatures
+    written out here from bf16_stochastic_rounding.py:5,33,48), and CPU tensors get the 'no CPU fallback' error — not a
+    silent torch path, and not an index error from a CUDA generator that does not exist."""
+    import inspect
+    from onetrainer_b200.modules.util import bf16_stochastic_rounding as mine
+    want = {"copy_stochastic_": ["target", "source"], "add_stochastic_": ["input", "other", "alpha"],
+            "addcdiv_stochastic_": ["input", "tensor1", "tensor2", "value"]}
+    from baseline import ref_arm
+    if ref_arm.available():
+        ref_arm.load()
+        import modules.util.bf16_stochastic_rounding as ref
+        for name in want:
+            ps = inspect.signature(getattr(ref, name)).parameters
+            assert list(ps) == want[name], (name, list(ps))
+            assert [p.default for p in ps.values()] == [p.default for p in inspect.signature(getattr(mine, name)).parameters.values()]
+    for name, params in want.items():
+        assert list(inspect.signature(getattr(mine, name)).parameters) == params
+    p = torch.zeros(16, dtype=torch.bfloat16)
+    for call in (lambda: mine.copy_stochastic_(p, torch.zeros(16)), lambda: mine.add_stochastic_(p, torch.zeros(16), alpha=0.5),
+                 lambda: mine.addcdiv_stochastic_(p, torch.ones(16), torch.ones(16), value=-1.0)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+    with pytest.raises(ValueError, match="float32"):
+        mine.copy_stochastic_(p, torch.zeros(16, dtype=torch.bfloat16))
