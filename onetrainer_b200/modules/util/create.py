@@ -1,9 +1,9 @@
 """Optimizer and EMA construction for the fused step.
 
-Mirror of the ADAM / ADAMW branches of `create_optimizer` (/root/reference/modules/util/create.py:481-534) and of
-`create_ema` (:1089-1111): same argument meaning, same defaults, same RuntimeErrors.  Differences, all loud:
-every other optimizer raises NotImplementedError (SURVEY.md §8f rank 4 — their oracle restatements exist, their
-kernels do not); the optimizer is always patched, because the fused launch IS the step here; EMA on the CPU raises
+Mirror of the ADAM / ADAMW / ADAFACTOR / CAME branches of `create_optimizer` (/root/reference/modules/util/create.py:481-534,
+914-951), of the saved-state hand-over that follows them (:1038-1084) and of `create_ema` (:1089-1111): same argument
+meaning, same defaults, same RuntimeErrors.  Differences, all loud: every other optimizer raises NotImplementedError (no
+fused step on this path); the optimizer is always patched, because the fused launch IS the step here; EMA on the CPU raises
 (the fused EMA lives next to the parameters in HBM).
 """
 from __future__ import annotations
@@ -19,6 +19,42 @@ from .optimizer.adamw_extensions import patch_adamw
 
 def _or(value, default):
     return default if value is None else value
+
+
+def fit_state_dict_to_groups(state_dict: dict, optimizer, parameter_group_collection: NamedParameterGroupCollection, config) -> dict:
+    """A saved optimizer state made loadable into THIS run's parameter groups — what the reference does between building the
+    optimizer and `optimizer.load_state_dict` (create.py:1038-1084).  A backup carries `param_group_mapping` (the groups'
+    unique names, InternalModelSaverMixin.py:19-26) and `param_group_optimizer_mapping` (the optimizer each was trained with):
+    a group of this run takes over the saved state of the group with the same name if the optimizer type still matches —
+    its per-parameter states renumbered in the new order, its learning rates replaced by this run's — and starts empty
+    otherwise, so groups may be added, dropped or reordered between runs.  Without the mapping (old backups) only the
+    learning rates are refreshed, group by group.  The dict is edited in place and returned, as the reference edits it."""
+    if "param_group_mapping" not in state_dict:
+        for saved, mine in zip(state_dict["param_groups"], parameter_group_collection.parameters_for_optimizer(config)):
+            saved["lr"], saved["initial_lr"] = mine["lr"], mine["initial_lr"]
+        return state_dict
+    saved_state, saved_groups = state_dict["state"], state_dict["param_groups"]
+    saved_names, saved_kinds = state_dict["param_group_mapping"], state_dict["param_group_optimizer_mapping"]
+    fresh_groups = optimizer.state_dict()["param_groups"]
+    kind = str(config.optimizer.optimizer)
+    state, groups, next_index = {}, [], 0
+    for fresh, name in zip(fresh_groups, parameter_group_collection.unique_name_mapping):
+        at = saved_names.index(name) if name in saved_names else -1
+        if at >= 0 and saved_kinds[at] == kind:
+            group = saved_groups[at]
+            for slot, saved_index in enumerate(group["params"]):
+                if saved_index in saved_state:
+                    state[next_index] = saved_state[saved_index]
+                group["params"][slot] = next_index
+                next_index += 1
+            group["lr"], group["initial_lr"] = fresh["lr"], fresh["initial_lr"]
+        else:
+            group = fresh
+            group["params"][:] = range(next_index, next_index + len(group["params"]))
+            next_index += len(group["params"])
+        groups.append(group)
+    state_dict["state"], state_dict["param_groups"] = state, groups
+    return state_dict
 
 
 def create_optimizer(parameter_group_collection: NamedParameterGroupCollection, state_dict: dict | None, config,
@@ -43,7 +79,7 @@ def create_optimizer(parameter_group_collection: NamedParameterGroupCollection, 
         capturable=_or(oc.capturable, False), differentiable=_or(oc.differentiable, False), fused=_or(oc.fused, False))
     patch(optimizer, oc.stochastic_rounding, ema=ema, ema_step_fn=ema_step_fn, clip_grad_norm=clip_grad_norm)
     if state_dict is not None:
-        optimizer.load_state_dict(state_dict)
+        optimizer.load_state_dict(fit_state_dict_to_groups(state_dict, optimizer, parameter_group_collection, config))
     return optimizer
 
 
@@ -72,7 +108,7 @@ def _create_factored(name: str, parameter_group_collection, state_dict, config, 
                          betas=(_or(oc.beta1, 0.9), _or(oc.beta2, 0.999), _or(oc.beta3, 0.9999)), weight_decay=_or(oc.weight_decay, 0),
                          stochastic_rounding=oc.stochastic_rounding)
     if state_dict is not None:
-        optimizer.load_state_dict(state_dict)
+        optimizer.load_state_dict(fit_state_dict_to_groups(state_dict, optimizer, parameter_group_collection, config))
     return optimizer
 
 

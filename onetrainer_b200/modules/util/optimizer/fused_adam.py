@@ -257,6 +257,7 @@ class FusedAdamDriver:
             return
         if p.grad.is_sparse:
             raise RuntimeError("AdamW does not support sparse gradients")
+        N.require_cuda(p)
         st = self.opt.state[p]
         if len(st) == 0:
             _init_state(st, p, group)
@@ -274,6 +275,25 @@ class FusedAdamDriver:
         _bump_versions([p])
 
 
+def _opt_step(self, closure=None):
+    return self.otb_driver.step(closure)
+
+
+def _opt_step_parameter(self, p, group, i):
+    return self.otb_driver.step_parameter(p, group, i)
+
+
+def bind_to_optimizer(optimizer) -> None:
+    """`optimizer.step` / `optimizer.step_parameter` as methods BOUND TO THE OPTIMIZER, the way the reference binds them
+    (`step_adamw.__get__(optimizer, AdamW)`, adamw_extensions.py:202-205).  torch's LR schedulers wrap `optimizer.step` by
+    taking its `__func__` and re-binding it to the optimizer (lr_scheduler.py: patch_track_step_called) — the reference
+    creates its LambdaLR right after the optimizer (create.py), so a method bound to the driver would be called with the
+    optimizer as `self`."""
+    import types
+    optimizer.step = types.MethodType(_opt_step, optimizer)
+    optimizer.step_parameter = types.MethodType(_opt_step_parameter, optimizer)
+
+
 def install(optimizer, stochastic_rounding: bool, decoupled: bool, ema=None, ema_step_fn=None,
             clip_grad_norm: float | None = None):
     optimizer.stochastic_rounding = stochastic_rounding
@@ -282,8 +302,7 @@ def install(optimizer, stochastic_rounding: bool, decoupled: bool, ema=None, ema
     if ema is not None:
         ema.attach_fused_driver(driver)
     optimizer.otb_driver = driver
-    optimizer.step = driver.step
-    optimizer.step_parameter = driver.step_parameter
+    bind_to_optimizer(optimizer)
 
     # resume: the SR stream position travels with the optimizer state (a resumed run must not replay offsets 1, 2, ...),
     # and a load replaces the state tensors the cached pointer tables refer to

@@ -21,7 +21,7 @@ import torch
 
 from .... import ops
 from .... import _native as N
-from .fused_adam import _bump_versions
+from .fused_adam import _bump_versions, bind_to_optimizer
 
 _DT = np.dtype(N.FactoredTensor)
 
@@ -203,6 +203,5 @@ def install(optimizer, kind: str, stochastic_rounding: bool) -> FactoredDriver:
     optimizer.stochastic_rounding = stochastic_rounding
     driver = FactoredDriver(optimizer, kind)
     optimizer.otb_driver = driver
-    optimizer.step = driver.step
-    optimizer.step_parameter = driver.step_parameter
+    bind_to_optimizer(optimizer)        # bound to the optimizer, so that an LR scheduler's step wrapper finds the driver
     return driver

@@ -689,6 +689,31 @@ def test_step_parameter_fused_back_pass_mode(P, dev):
         assert p.grad is None and torch.equal(p, q)
 
 
+def test_patched_adamw_under_an_lr_scheduler_equals_torch_adamw(P, dev):
+    """The reference's order: create_optimizer (patch_adamw inside), THEN LambdaLR — whose constructor wraps `optimizer.step`
+    by re-binding its `__func__` to the optimizer.  Five steps of warm-up + decay, fp32 parameters (no SR): the patched
+    optimizer under the scheduler equals torch's own AdamW under the same scheduler bit for bit, and `lr` is re-read from
+    the param group every step."""
+    torch.manual_seed(4)
+    p = nn.Parameter(torch.randn(5000, device=dev) * 0.02)
+    q = nn.Parameter(p.detach().clone())
+    oa = torch.optim.AdamW([p], lr=3e-4, weight_decay=1e-2)
+    ob = torch.optim.AdamW([q], lr=3e-4, weight_decay=1e-2, foreach=False, fused=False)
+    P.patch_adamw(oa, False)
+    lam = lambda step: min(1.0, (step + 1) / 3) * 0.9 ** step      # noqa: E731
+    sa, sb = torch.optim.lr_scheduler.LambdaLR(oa, lam), torch.optim.lr_scheduler.LambdaLR(ob, lam)
+    for step in range(5):
+        g = torch.randn(5000, device=dev) * 1e-3
+        p.grad, q.grad = g.clone(), g.clone()
+        oa.step(); ob.step()
+        sa.step(); sb.step()
+        assert oa.param_groups[0]["lr"] == ob.param_groups[0]["lr"]
+        assert torch.equal(p, q), f"step {step}: {(p != q).sum().item()} of {p.numel()} differ"
+        for key in ("exp_avg", "exp_avg_sq"):
+            assert torch.equal(oa.state[p][key], ob.state[q][key])
+    assert float(oa.state[p]["step"]) == 5.0
+
+
 # ------------------------------------------------------------------------------------------ end to end
 def test_training_loop_tracks_torch_restatement(P, dev):
     """20 optimisation steps of the tiny stand-in through the whole path (fused noise/add-noise, hooked leaves,

@@ -533,3 +533,95 @@ def test_sr_helper_module_keeps_the_reference_signatures_and_has_no_cpu_path():
             call()
     with pytest.raises(ValueError, match="float32"):
         mine.copy_stochastic_(p, torch.zeros(16, dtype=torch.bfloat16))
+
+
+def test_patched_optimizers_survive_the_lr_scheduler_step_wrapper():
+    """The reference builds its LambdaLR right after the optimizer (create.py: create_optimizer, then create_lr_scheduler);
+    torch's scheduler wraps `optimizer.step` by re-binding `optimizer.step.__func__` to the optimizer
+    (lr_scheduler.py: patch_track_step_called).  The reference's patches are bound to the optimizer
+    (adamw_extensions.py:202-205), so must these be: a scheduler created AFTER the patch steps through the fused driver,
+    records the call, rewrites `lr` — and `step_parameter` keeps its (p, group, i) signature."""
+    import inspect
+    from transformers.optimization import Adafactor
+    from onetrainer_b200.modules.util.optimizer.adafactor_extensions import patch_adafactor
+    from onetrainer_b200.modules.util.optimizer.adam_extensions import patch_adam
+    from onetrainer_b200.modules.util.optimizer.adamw_extensions import patch_adamw
+    from onetrainer_b200.modules.util.optimizer.CAME import CAME
+
+    def params():
+        return [nn.Parameter(torch.zeros(8, 4))]
+
+    opts = []
+    o = torch.optim.AdamW(params(), lr=1e-3); patch_adamw(o, True); opts.append(o)
+    o = torch.optim.Adam(params(), lr=1e-3); patch_adam(o, False); opts.append(o)
+    o = Adafactor(params(), lr=1e-3, relative_step=False, scale_parameter=False); patch_adafactor(o, False); opts.append(o)
+    opts.append(CAME(params(), lr=1e-3))
+    for opt in opts:
+        assert opt.step.__self__ is opt and opt.step_parameter.__self__ is opt, type(opt).__name__
+        assert list(inspect.signature(opt.step_parameter).parameters) == ["p", "group", "i"]
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda step: 0.5 ** step)
+        assert getattr(opt.step, "_wrapped_by_lr_sched", False)
+        assert opt.step() is None and opt.step(lambda: 2.5) == 2.5          # no gradient anywhere: no launch, closure contract
+        assert opt._opt_called
+        sched.step()
+        assert opt.param_groups[0]["lr"] == pytest.approx(5e-4)
+        p = opt.param_groups[0]["params"][0]
+        p.grad = torch.ones_like(p)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):           # the wrapper reached the fused driver
+            opt.step()
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            opt.step_parameter(p, opt.param_groups[0], 0)
+
+
+def test_saved_optimizer_state_follows_the_group_names_on_resume():
+    """create_optimizer's hand-over of a backup's optimizer state (create.py:1038-1084 with the saver's two mapping lists,
+    InternalModelSaverMixin.py:19-26): groups are matched by unique name, so a resumed run may reorder, add or drop groups;
+    a group trained by another optimizer type starts empty; learning rates always come from the new config; without the
+    mapping (old backups) only the rates are refreshed.  The SR stream position travels in the same dict."""
+    from onetrainer_b200.modules.util import create
+    from onetrainer_b200.modules.util.config.TrainConfig import TrainOptimizerConfig
+    from onetrainer_b200.modules.util.enum import Optimizer
+    from onetrainer_b200.modules.util.NamedParameterGroup import NamedParameterGroup, NamedParameterGroupCollection
+
+    def collection(order):
+        sizes = {"unet_lora": (3, 2), "te_lora": (5,), "embeddings": (7,)}
+        col = NamedParameterGroupCollection()
+        for name in order:
+            col.add_group(NamedParameterGroup(name, [nn.Parameter(torch.zeros(n)) for n in sizes[name]], None))
+        return col
+
+    cfg = TrainConfig(learning_rate=3e-4, train_device="cpu", optimizer=TrainOptimizerConfig(stochastic_rounding=True))
+    first = collection(["unet_lora", "te_lora"])
+    opt = create.create_optimizer(first, None, cfg)
+    for k, p in enumerate(first.parameters()):          # what three steps would have left behind, recognisable per tensor
+        opt.state[p] = {"step": torch.tensor(3.0), "exp_avg": torch.full_like(p, k + 1.0), "exp_avg_sq": torch.full_like(p, 10.0 * (k + 1))}
+    opt.otb_driver.step_count = 3
+    saved = opt.state_dict()
+    assert saved["otb_sr_step_count"] == 3
+    saved["param_group_mapping"] = first.unique_name_mapping
+    saved["param_group_optimizer_mapping"] = [str(cfg.optimizer.optimizer) for _ in first.unique_name_mapping]
+    import copy
+
+    # resumed with the groups reordered, one added, a new learning rate
+    cfg2 = TrainConfig(learning_rate=1e-4, train_device="cpu", optimizer=TrainOptimizerConfig(stochastic_rounding=True))
+    second = collection(["te_lora", "embeddings", "unet_lora"])
+    opt2 = create.create_optimizer(second, copy.deepcopy(saved), cfg2)
+    te, emb, (u0, u1) = second._groups[0].parameters[0], second._groups[1].parameters[0], second._groups[2].parameters
+    assert float(opt2.state[te]["exp_avg"][0]) == 3.0 and opt2.state[te]["exp_avg"].shape == (5,)      # was the third tensor saved
+    assert float(opt2.state[u0]["exp_avg"][0]) == 1.0 and float(opt2.state[u1]["exp_avg_sq"][0]) == 20.0
+    assert len(opt2.state[emb]) == 0                                                                   # new group: empty state
+    assert [g["lr"] for g in opt2.param_groups] == [1e-4] * 3 and [g["initial_lr"] for g in opt2.param_groups] == [1e-4] * 3
+    assert opt2.otb_driver.step_count == 3 and opt2.otb_driver.table is None
+
+    # the same backup under another optimizer type: every group starts empty
+    cfg3 = TrainConfig(learning_rate=1e-4, train_device="cpu", optimizer=TrainOptimizerConfig(optimizer=Optimizer.ADAM))
+    third = collection(["unet_lora", "te_lora"])
+    opt3 = create.create_optimizer(third, copy.deepcopy(saved), cfg3)
+    assert all(len(opt3.state[p]) == 0 for p in third.parameters())
+
+    # an old backup without the mapping: loaded positionally, rates refreshed
+    old = copy.deepcopy(saved)
+    del old["param_group_mapping"], old["param_group_optimizer_mapping"]
+    fourth = collection(["unet_lora", "te_lora"])
+    opt4 = create.create_optimizer(fourth, old, cfg2)
+    assert float(opt4.state[fourth.parameters()[2]]["exp_avg"][0]) == 3.0 and opt4.param_groups[0]["lr"] == 1e-4
