@@ -714,6 +714,89 @@ def test_patched_adamw_under_an_lr_scheduler_equals_torch_adamw(P, dev):
     assert float(oa.state[p]["step"]) == 5.0
 
 
+def _build_in_reference_order(P, cfg, build_device, ema_device):
+    """StableDiffusionXLLoRASetup.setup_model (:103-158) + init_model_parameters (optimizer_util.py:50-65) + the trainer's
+    create_lr_scheduler, in the reference's ORDER: network and adapters are built where the loader left the weights
+    (`build_device`, the CPU in a real run), the optimizer, the EMA (already on the train device) and the LambdaLR are
+    created over those parameters, and only afterwards setup_train_device moves the network and its adapters."""
+    from onetrainer_b200.modules.util import create
+    from onetrainer_b200.modules.util.NamedParameterGroup import NamedParameterGroup, NamedParameterGroupCollection
+    torch.manual_seed(77)
+    with torch.device(build_device):
+        unet = P.standin.tiny_unet()
+    unet = unet.to(dtype=torch.bfloat16)
+    unet.requires_grad_(False)
+    unet.train()
+    wrapper = P.L.LoRAModuleWrapper(unet, "lora_unet", cfg, ["attentions"])
+    wrapper.set_dropout(cfg.dropout_probability)
+    wrapper.to(dtype=torch.float32)
+    g = torch.Generator(device=build_device).manual_seed(78)
+    for m in wrapper.lora_modules.values():
+        m.lora_up.weight.data.normal_(0.0, 0.05, generator=g)
+    wrapper.hook_to_module()
+    wrapper.requires_grad_(True)
+    col = NamedParameterGroupCollection()
+    col.add_group(NamedParameterGroup("unet_lora", wrapper.parameters(), None))
+    ema = P.EMAModuleWrapper(col.parameters(), decay=0.99, update_step_interval=1, device=torch.device(ema_device))
+    optimizer = create.create_optimizer(col, None, cfg)                     # the reference's call: no fused EMA / clip
+    scheduler = torch.optim.lr_scheduler.LambdaLR(optimizer, lambda step: min(1.0, (step + 1) / 2))
+    return unet, wrapper, col, ema, optimizer, scheduler
+
+
+def test_reference_setup_order_build_on_cpu_then_move_then_train(P, dev):
+    """The whole seam in the order the reference's trainer uses it — adapters, optimizer, EMA and LR scheduler created
+    while the weights are still on the CPU, the move to the GPU afterwards, then GenericTrainer's step body
+    (:683-747: predict, loss, backward, clip_grad_norm_, optimizer.step, lr_scheduler.step, zero_grad(set_to_none=True),
+    ema.step) — trains, and equals, bit for bit, the same run with everything created on the GPU from the start."""
+    from onetrainer_b200.modules.util.config.TrainConfig import TrainOptimizerConfig
+    cfg = P.TrainConfig(train_device=str(dev), batch_size=2, lora_rank=8, learning_rate=2e-3, clip_grad_norm=1.0,
+                        optimizer=TrainOptimizerConfig(stochastic_rounding=False))
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    batch = P.trainer.batch_to_device(P.trainer.synthetic_batch("tiny", 2, dev, latent_hw=32), dev)
+    runs = []
+    for build_device in ("cpu", dev):
+        unet, wrapper, col, ema, optimizer, scheduler = _build_in_reference_order(P, cfg, build_device, dev)
+        if build_device == "cpu":
+            cpu_state = {k: v.clone() for k, v in wrapper.state_dict().items()}
+            base_state = {k: v.clone() for k, v in unet.state_dict().items()}
+            unet.to(dev)                                                    # setup_train_device: model.unet_to(train_device)
+            wrapper.to(dev)                                                 # ... which also moves the adapter
+        else:                                                               # same numbers as the CPU-built run
+            unet.load_state_dict({k: v.to(dev) for k, v in base_state.items()})
+            wrapper.load_state_dict({k: v.to(dev) for k, v in cpu_state.items()})
+            for e, p in zip(ema.ema_parameters, col.parameters()):
+                e.copy_(p.detach())
+        params = col.parameters()
+        assert all(p.is_cuda for p in params) and all(e.is_cuda for e in ema.ema_parameters)
+        sched = P.standin.StandInScheduler(P.trainer.standin_betas().to(dev), "epsilon")
+        model = P.trainer.StandInModel(unet, sched, 0.18215, torch.bfloat16, sdxl=False)
+        model.unet_lora, model.parameters, model.optimizer, model.ema = wrapper, params, optimizer, ema
+        setup = P.trainer.DiffusionSetup(dev)
+        before = [p.detach().clone() for p in params]
+        losses, lrs = [], []
+        for step in range(3):
+            with sdpa_kernel(SDPBackend.MATH):                              # the stand-in's attention on its deterministic backend
+                data = setup.predict(model, batch, cfg, model.train_progress)
+                loss = setup.calculate_loss(model, batch, data, cfg)
+                loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, cfg.clip_grad_norm)
+            lrs.append(optimizer.param_groups[0]["lr"])
+            optimizer.step()
+            scheduler.step()
+            optimizer.zero_grad(set_to_none=True)
+            ema.step(params, model.train_progress.global_step)
+            model.train_progress.next_step(cfg.batch_size)
+            losses.append(loss.item())
+        assert lrs == [1e-3, 2e-3, 2e-3] and all(math.isfinite(x) for x in losses)
+        assert any(not torch.equal(a, b) for a, b in zip(before, params))
+        assert any(not torch.equal(e, p) for e, p in zip(ema.ema_parameters, params))
+        runs.append((losses, [p.detach().clone() for p in params], [e.clone() for e in ema.ema_parameters]))
+        wrapper.remove_hook_from_module()
+    (la, pa, ea), (lb, pb, eb) = runs
+    assert la == lb
+    assert all(torch.equal(a, b) for a, b in zip(pa, pb)) and all(torch.equal(a, b) for a, b in zip(ea, eb))
+
+
 # ------------------------------------------------------------------------------------------ end to end
 def test_training_loop_tracks_torch_restatement(P, dev):
     """20 optimisation steps of the tiny stand-in through the whole path (fused noise/add-noise, hooked leaves,
