@@ -521,7 +521,10 @@ class LoRAModule(PeftBase):
         if type(om) not in (nn.Linear, nn.Conv2d) and type(om).__name__ in ("LinearNf4", "LinearFp8", "Linear4bit", "Linear8bitLt"):
             raise NotImplementedError(f"quantized base layer {type(om).__name__} is not supported by the fused LoRA kernel")
         if isinstance(om, nn.Conv2d):
-            if om.groups != 1 or isinstance(om.padding, str) or om.padding_mode != "zeros":
+            # a padding MODE only matters where something is padded: `force_circular_padding` (conv_util.py:6-9, applied to
+            # the whole UNet before the adapters exist) also flips the 1x1 projections, whose padding is 0
+            unpadded = not isinstance(om.padding, str) and all(int(p) == 0 for p in om.padding)
+            if om.groups != 1 or isinstance(om.padding, str) or (om.padding_mode != "zeros" and not unpadded):
                 raise NotImplementedError(
                     "fused LoRA supports Linear and groups-1, zero-padded Conv2d leaves; "
                     f"got Conv2d(kernel={om.kernel_size}, padding={om.padding}, padding_mode={om.padding_mode}, groups={om.groups})")

@@ -110,6 +110,15 @@ def test_empty_filter_selects_everything_supported_and_unsupported_layers_raise(
         LoRAModule("p", nn.Conv2d(8, 8, 3, padding=1, groups=2), 8, 1.0)
     with pytest.raises(NotImplementedError, match="zero-padded"):
         LoRAModule("p", nn.Conv2d(8, 8, 3, padding=1, padding_mode="reflect"), 8, 1.0)
+    # force_circular_padding (conv_util.py:6-9) flips EVERY conv of the UNet before the adapters are built: the 1x1 projections
+    # pad nothing, so the mode changes nothing for them and they stay supported; a padded 3x3 in circular mode does not
+    for conv in (nn.Conv2d(8, 8, 1), nn.Conv2d(8, 16, 1, stride=2)):
+        conv.padding_mode = "circular"
+        assert LoRAModule("p", conv, 8, 1.0).lora_down.weight.shape[1] == 8
+    circ = nn.Conv2d(8, 8, 3, padding=1)
+    circ.padding_mode = "circular"
+    with pytest.raises(NotImplementedError, match="zero-padded"):
+        LoRAModule("p", circ, 8, 1.0)
     from onetrainer_b200.modules.module.LoRAModule import DoRAModule
     dora = LoRAModuleWrapper(_net(), "lora_unet", TrainConfig(train_device="cpu", lora_decompose=True), ["to_q"])     # DoRA (reference :448-457)
     assert dora.lora_modules and all(isinstance(m, DoRAModule) and m.dora_scale.dtype == torch.float32 for m in dora.lora_modules.values())
