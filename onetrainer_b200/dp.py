@@ -56,6 +56,26 @@ def global_sample_base(local_batch_size: int) -> int:
     return rank() * int(local_batch_size)
 
 
+_replicated = {"seed": None, "calls": 0}
+
+
+def replicated_key() -> tuple[int, int]:
+    """A Philox (seed, offset) that is THE SAME on every rank for the k-th call: rank 0's `torch.initial_seed()`, broadcast
+    once (collective: every rank must make its first call), and a call counter.  For draws that must not differ between
+    replicas whatever per-rank seeding the application uses — stochastic rounding of replicated bf16 parameters by the
+    stand-alone helpers (modules/util/bf16_stochastic_rounding.py): replicas make the same calls in the same order, so
+    they round identically and do not drift apart.  (Noise and timesteps are the opposite case: keyed per global sample.)"""
+    if _replicated["seed"] is None:
+        seed = torch.initial_seed() & (2 ** 63 - 1)
+        if world_size() > 1:
+            t = torch.tensor([seed], dtype=torch.int64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+            dist.broadcast(t, src=0)
+            seed = int(t.item())
+        _replicated["seed"] = seed
+    _replicated["calls"] += 1
+    return _replicated["seed"], 4 * _replicated["calls"]
+
+
 class GradientBucket:
     """Flat view of the trainable tensors' gradients for the one exchange step.
 

@@ -9,6 +9,8 @@ otb_stochastic_round (include/otb200.h, csrc/sr_round.cu): the fp32 result stays
 
 Random bits: the reference draws from the default CUDA generator; so does this — the Philox key is that generator's
 (seed, offset), and every call advances the offset, so `torch.manual_seed(s)` reproduces a run and successive calls differ.
+Under data parallelism (net-new; the reference is single-process) the key is instead rank 0's seed and a call counter
+(`dp.replicated_key`), so replicas of a parameter round identically whatever per-rank seeding the application uses.
 torch's own bit stream is deliberately not reproduced; given the same 16-bit draws the result is bit-identical
 to the reference (tests/golden/sr_helpers.npz, tests/test_gpu_kernels.py).
 
@@ -20,7 +22,7 @@ import torch
 from torch import Tensor
 
 from ... import _native as N
-from ... import ops, rng
+from ... import dp, ops, rng
 
 
 def _key(t: Tensor, *others: Tensor) -> tuple[int, int]:
@@ -28,6 +30,10 @@ def _key(t: Tensor, *others: Tensor) -> tuple[int, int]:
     if torch.cuda.is_current_stream_capturing():
         raise RuntimeError("bf16_stochastic_rounding: the default generator's offset cannot advance inside a CUDA-graph capture; "
                            "use the fused optimizers (their key is a device-side step counter)")
+    if dp.world_size() > 1:
+        # replicas must round identically or bf16 copies of one parameter drift apart: rank 0's seed and a call counter,
+        # not this rank's generator (applications commonly seed with seed + rank)
+        return dp.replicated_key()
     return rng.draw_key(None, t.device)
 
 

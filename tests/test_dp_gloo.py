@@ -74,6 +74,14 @@ def _worker(rank, world, port, out_dir):
     gathered = [torch.zeros_like(local) for _ in range(world)]
     torch.distributed.all_gather(gathered, 2 * local)    # what each rank held locally after both micro-batches
     assert torch.allclose(fa2.flat, sum(gathered), rtol=1e-6, atol=1e-6)
+    # (2d) draws that must be identical on every replica (stochastic rounding by the stand-alone helpers): rank 0's seed and
+    # a call counter, whatever this rank seeded torch with
+    torch.manual_seed(100 + rank)
+    keys = [dp.replicated_key() for _ in range(3)]
+    assert [k[1] for k in keys] == [4, 8, 12] and len({k[0] for k in keys}) == 1
+    got = [None] * world
+    torch.distributed.all_gather_object(got, keys)
+    assert all(g == got[0] for g in got) and keys[0][0] == 100                          # rank 0's seed everywhere
     # (3) loss averaging for logging
     assert dp.average_scalar(torch.tensor(float(rank))).item() == 0.5
     # (4) DP-invariant draws: this rank's samples of the global batch, through the oracle's stream definition
