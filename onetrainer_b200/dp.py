@@ -59,12 +59,8 @@ def global_sample_base(local_batch_size: int) -> int:
 _replicated = {"seed": None, "calls": 0}
 
 
-def replicated_key() -> tuple[int, int]:
-    """A Philox (seed, offset) that is THE SAME on every rank for the k-th call: rank 0's `torch.initial_seed()`, broadcast
-    once (collective: every rank must make its first call), and a call counter.  For draws that must not differ between
-    replicas whatever per-rank seeding the application uses — stochastic rounding of replicated bf16 parameters by the
-    stand-alone helpers (modules/util/bf16_stochastic_rounding.py): replicas make the same calls in the same order, so
-    they round identically and do not drift apart.  (Noise and timesteps are the opposite case: keyed per global sample.)"""
+def replicated_seed() -> int:
+    """Rank 0's `torch.initial_seed()` on every rank (broadcast once; collective on first use).  See replicated_key()."""
     if _replicated["seed"] is None:
         seed = torch.initial_seed() & (2 ** 63 - 1)
         if world_size() > 1:
@@ -72,8 +68,18 @@ def replicated_key() -> tuple[int, int]:
             dist.broadcast(t, src=0)
             seed = int(t.item())
         _replicated["seed"] = seed
+    return _replicated["seed"]
+
+
+def replicated_key() -> tuple[int, int]:
+    """A Philox (seed, offset) that is THE SAME on every rank for the k-th call: rank 0's `torch.initial_seed()`, broadcast
+    once (collective: every rank must make its first call), and a call counter.  For draws that must not differ between
+    replicas whatever per-rank seeding the application uses — stochastic rounding of replicated bf16 parameters by the
+    stand-alone helpers (modules/util/bf16_stochastic_rounding.py): replicas make the same calls in the same order, so
+    they round identically and do not drift apart.  (Noise and timesteps are the opposite case: keyed per global sample.)"""
+    seed = replicated_seed()
     _replicated["calls"] += 1
-    return _replicated["seed"], 4 * _replicated["calls"]
+    return seed, 4 * _replicated["calls"]
 
 
 class GradientBucket:

@@ -160,9 +160,16 @@ class FactoredDriver:
             if count == 0:
                 continue
             a = N.FactoredLaunch(tensors=entry["dev"].data_ptr() + first * _DT.itemsize, scratch=entry["scratch"].data_ptr(), n_tensors=count,
-                                 cluster=cluster, seed=torch.initial_seed() & (2 ** 64 - 1), offset=(self.step_count - 1) * wd_calls + 1)
+                                 cluster=cluster, seed=self._sr_seed() & (2 ** 64 - 1), offset=(self.step_count - 1) * wd_calls + 1)
             N.check(fn(C.byref(a), ops._stream()), f"otb_{self.kind}_multi")
             ops._count()
+
+    @staticmethod
+    def _sr_seed() -> int:
+        """Key of CAME's stochastic-rounding stream: torch's seed — and under data parallelism rank 0's, so that the bf16
+        replicas of a parameter round identically whatever per-rank seeding the application uses (as fused_adam.sr_seed)."""
+        from .... import dp
+        return dp.replicated_seed() if dp.world_size() > 1 else torch.initial_seed()
 
     # ---- entry points ------------------------------------------------------------------------
     @torch.no_grad()
