@@ -14,7 +14,8 @@ Under data parallelism (net-new; the reference is single-process) the key is ins
 torch's own bit stream is deliberately not reproduced; given the same 16-bit draws the result is bit-identical
 to the reference (tests/golden/sr_helpers.npz, tests/test_gpu_kernels.py).
 
-No fallback: CPU tensors, a target that is not bf16 or not contiguous, or operands of another size raise.
+No fallback: CPU tensors, a target that is not bf16, or operands of another size raise.  A strided target is rounded in a dense
+copy and written back (the reference's ATen ops accept any strides).
 """
 from __future__ import annotations
 
@@ -45,19 +46,32 @@ def _operand(t: Tensor, like: Tensor, what: str) -> Tensor:
     return t.contiguous()
 
 
+def _launch(mode: int, target: Tensor, src: Tensor, src2: Tensor | None = None, **kw) -> None:
+    if target.dtype != torch.bfloat16:
+        raise ValueError(f"stochastic rounding targets bf16 tensors; got {target.dtype}")
+    if target.is_contiguous():
+        ops.stochastic_round(mode, target, src, src2, **kw)
+        return
+    # a strided target (a transposed or sliced parameter): the kernel addresses dense memory, so round into a dense copy in the
+    # target's logical element order — the order `_operand` gives the other operands — and write it back
+    dense = target.contiguous()
+    ops.stochastic_round(mode, dense, src, src2, **kw)
+    target.copy_(dense)
+
+
 def copy_stochastic_(target: Tensor, source: Tensor):
     """copies source (fp32) into target (bf16) using stochastic rounding"""
     if source.dtype != torch.float32:
         raise ValueError("copy_stochastic_: source must be float32 (the reference reinterprets it as int32)")
     seed, offset = _key(target, source)
-    ops.stochastic_round(N.SR_COPY, target, _operand(source, target, "source"), seed=seed, offset=offset)
+    _launch(N.SR_COPY, target, _operand(source, target, "source"), seed=seed, offset=offset)
 
 
 def add_stochastic_(input: Tensor, other: Tensor, alpha: float = 1.0):
     """input <- SR(fp32(other) + alpha * input): the reference's arithmetic (`result = other.float(); result.add_(input,
     alpha=alpha)`), in which alpha multiplies `input`."""
     seed, offset = _key(input, other)
-    ops.stochastic_round(N.SR_ADD, input, _operand(other, input, "other"), alpha=alpha, seed=seed, offset=offset)
+    _launch(N.SR_ADD, input, _operand(other, input, "other"), alpha=alpha, seed=seed, offset=offset)
 
 
 def addcdiv_stochastic_(input: Tensor, tensor1: Tensor, tensor2: Tensor, value: float = 1.0):
@@ -66,4 +80,4 @@ def addcdiv_stochastic_(input: Tensor, tensor1: Tensor, tensor2: Tensor, value: 
     t1, t2 = _operand(tensor1, input, "tensor1"), _operand(tensor2, input, "tensor2")
     if t1.dtype != t2.dtype:
         t1, t2 = t1.float(), t2.float()
-    ops.stochastic_round(N.SR_ADDCDIV, input, t1, t2, alpha=value, seed=seed, offset=offset)
+    _launch(N.SR_ADDCDIV, input, t1, t2, alpha=value, seed=seed, offset=offset)

@@ -227,3 +227,25 @@ def test_module_functions_are_seeded_unbiased_and_refuse_fallbacks(dev):
     assert bool(((q.float() == lo) | (q.float() == hi)).all())
     with pytest.raises((RuntimeError, ValueError)):
         copy_stochastic_(torch.empty(8, dtype=torch.bfloat16), torch.zeros(8))
+
+
+def test_module_functions_accept_strided_targets(dev):
+    """The reference's ATen ops take any strides; the kernel addresses dense memory.  A transposed (non-contiguous) bf16 target
+    is rounded in a dense copy in its logical element order and written back: same bits as the same call on a contiguous
+    tensor holding the same values, under the same generator state."""
+    from onetrainer_b200.modules.util.bf16_stochastic_rounding import add_stochastic_, copy_stochastic_
+    torch.manual_seed(1)
+    base = (torch.randn(48, 80, device=dev) * 0.02).bfloat16()
+    upd = torch.randn(80, 48, device=dev) * 1e-4
+    strided, dense = base.clone().t(), base.t().contiguous()
+    assert not strided.is_contiguous() and torch.equal(strided, dense)
+    torch.manual_seed(21)
+    add_stochastic_(strided, upd, alpha=1.0)
+    torch.manual_seed(21)
+    add_stochastic_(dense, upd, alpha=1.0)
+    assert torch.equal(strided, dense) and not torch.equal(dense, base.t())
+    torch.manual_seed(22)
+    copy_stochastic_(strided, upd * 100)
+    torch.manual_seed(22)
+    copy_stochastic_(dense, upd * 100)
+    assert torch.equal(strided, dense)
